@@ -1,0 +1,222 @@
+/*
+ * mazu_b200.h -- C ABI of libmazu_b200.so: the B200 (sm_100a) implementation of mazu's batched
+ * k-mer query path.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * The reference (COMBINE-lab/mazu, Rust) has no FFI; its "operator API" for this path is the
+ * trait surface K2U / U2Pos / GetRefPos / Validate and four constructors.  Each entry point
+ * below names the reference interface it replaces (path:line under the mazu repository).
+ * INTEGRATION.md shows the Rust `extern "C"` block + `impl K2U for GpuIndex` a maintainer would add.
+ *
+ * Conventions
+ *  - every function returns a mazu_status_t (0 = ok, negative = error); the message of the last
+ *    error on the calling thread is available from mazu_b200_last_error().
+ *  - contract violations that PANIC in the reference (wrong k: src/index.rs:157-163,
+ *    src/kphf/sshash.rs:473, src/kphf/pfhash.rs:109) return MAZU_ERR_K_MISMATCH, never UB.
+ *  - a miss (`None` in the reference) is NOT an error: it is the record {~0,~0,~0,MAZU_NO_MATCH}.
+ *  - `mem` says where the caller's buffers live: MAZU_MEM_HOST (the library stages them through
+ *    its own device buffers, chunked and overlapped) or MAZU_MEM_DEVICE (device pointers, e.g.
+ *    torch tensors' data_ptr(); work is enqueued on `stream` and the call returns without
+ *    synchronising).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *  - an index handle is immutable after creation and may be used concurrently from several host
+ *    threads / streams (reference: queries take &self and are Sync, src/kphf/mod.rs:69-72).
+ */
+#ifndef MAZU_B200_H
+#define MAZU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t mazu_status_t;
+enum {
+  MAZU_OK = 0,
+  MAZU_ERR_IO = -1,               /* src/err.rs: Error::IO                        */
+  MAZU_ERR_INVALID_DATA = -2,     /* src/err.rs: Error::InvalidData               */
+  MAZU_ERR_EF_NOT_MONOTONE = -3,  /* src/err.rs: Error::EFNotMonotone             */
+  MAZU_ERR_EF_EMPTY = -4,         /* src/err.rs: Error::EFEmpty                   */
+  MAZU_ERR_CUDA = -5,             /* CUDA runtime / no device                     */
+  MAZU_ERR_K_MISMATCH = -6,       /* reference panics (see above)                 */
+  MAZU_ERR_INVALID_ARG = -7,
+  MAZU_ERR_NO_U2POS = -8,         /* occurrence query on an index without a U2Pos */
+  MAZU_ERR_NO_REFSEQ = -9,        /* validate_self needs reference sequence (src/index/validate.rs:25) */
+  MAZU_ERR_OTHER = -10            /* src/err.rs: Error::Other                     */
+};
+
+/* MatchType of the `kmers` crate as used by K2UPos.o (src/kphf/mod.rs:13-19) */
+enum { MAZU_NO_MATCH = 0, MAZU_IDENTITY_MATCH = 1, MAZU_TWIN_MATCH = 2,
+       MAZU_SKIPPED = 3 /* record filler for windows CanonicalKmerIterator skips (non-ACGT) */ };
+
+enum { MAZU_MEM_HOST = 0, MAZU_MEM_DEVICE = 1 };
+enum { MAZU_MODE_RANDOM = 0,    /* K2U::k2u per k-mer                 (src/bin/kphf/main.rs:311-322) */
+       MAZU_MODE_STREAMING = 1  /* .as_streaming() / StreamingK2U     (src/index/caching.rs:65-103); cursor reset per read */ };
+enum { MAZU_K2U_PFHASH = 0, MAZU_K2U_SSHASH = 1 };
+enum { MAZU_U2POS_NONE = 0, MAZU_U2POS_DENSE = 1, MAZU_U2POS_PISCEM = 2 };
+enum { MAZU_INDEX_PUFFERFISH_DENSE = 0, /* ModIndex<PFHash, DenseUnitigTable>  src/index/defaults.rs:14 */
+       MAZU_INDEX_PISCEM = 1            /* ModIndex<SSHash, PiscemUnitigTable> src/index/defaults.rs:15 */ };
+
+#define MAZU_SKEW_NONE UINT64_MAX /* skew_param == usize::MAX: no skew index (src/kphf/sshash.rs:81-84,222) */
+
+/* Option<K2UPos> (src/kphf/mod.rs:13-19); miss = {~0,~0,~0,MAZU_NO_MATCH} (src/index/caching.rs:48-53) */
+typedef struct mazu_hit {
+  uint32_t unitig_id;
+  uint32_t unitig_len;
+  uint32_t pos;
+  uint32_t match;
+} mazu_hit_t;
+
+/* UnitigOcc (src/index.rs:304-309) and MappedRefPos (src/index.rs:25-31); fw: Forward=1, Backward=0 (src/lib.rs:51-56) */
+typedef struct mazu_occ {
+  uint32_t ref_id;
+  uint32_t pos;
+  uint32_t fw;
+} mazu_occ_t;
+
+typedef struct mazu_index mazu_index_t; /* opaque: owns the device-resident index */
+
+/* UnitigSet (src/unitig_set.rs:31-36) as plain host arrays */
+typedef struct mazu_unitig_set_desc {
+  uint32_t k;
+  const uint64_t* useq_words; /* 2-bit packed concatenated unitigs, base i at bits [2i,2i+2), ceil(2*n_bases/64) words */
+  uint64_t n_bases;
+  const uint64_t* accum_lens; /* n_unitigs + 1 prefix lengths, accum_lens[0] == 0 */
+  uint64_t n_unitigs;
+} mazu_unitig_set_desc_t;
+
+/* simple-sds IntVector / pufferfish compact vector: `len` fields of `width` bits, LSB-first */
+typedef struct mazu_packed_vec_desc {
+  const uint64_t* words;
+  uint64_t width;
+  uint64_t len;
+} mazu_packed_vec_desc_t;
+
+/* C++ BooPHF as parsed by src/pf1/boophf/mod.rs:50-86,269-293 */
+typedef struct mazu_boophf_desc {
+  uint32_t n_levels;
+  const uint64_t* const* level_words; /* per level: bit array words            */
+  const uint64_t* level_n_bits;       /* per level: number of slots            */
+  uint64_t last_bitset_rank;
+  uint64_t n_elem;
+  const uint64_t* final_keys;         /* final_hash map, any order             */
+  const uint64_t* final_vals;
+  uint64_t n_final;
+} mazu_boophf_desc_t;
+
+const char* mazu_b200_last_error(void);
+/* number of visible CUDA devices; <=0 means the library cannot run (it has NO CPU fallback) */
+int32_t mazu_b200_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Construction (host work + one upload).  `device` = CUDA device ordinal.
+ * ------------------------------------------------------------------------------------------- */
+/* DenseIndex::deserialize_from_cpp(dir)                         src/pf1/dense_index.rs:33-97 */
+mazu_status_t mazu_b200_dense_index_deserialize_from_cpp(const char* dir, int32_t device, mazu_index_t** out);
+/* PufferfishDenseIndexDefault::from_cf_prefix / PiscemIndex::from_cf_prefix
+ *                                   src/index/defaults.rs:17-58, src/index/piscem_index.rs:14-58 */
+mazu_status_t mazu_b200_index_from_cf_prefix(const char* prefix, int32_t index_kind, uint32_t w, uint64_t skew_param,
+                                             uint64_t hash_seed, int32_t device, mazu_index_t** out);
+/* SSHash::from_unitig_set(unitigs, w, skew_param, WyHashState(seed))   src/kphf/sshash.rs:405-412
+ * (skew_param == MAZU_SKEW_NONE: from_unitig_set_no_skew_index, :397-403) */
+mazu_status_t mazu_b200_index_create_sshash(const mazu_unitig_set_desc_t* unitigs, uint32_t w, uint64_t skew_param,
+                                            uint64_t hash_seed, int32_t device, mazu_index_t** out);
+/* PFHash::from_unitig_set(unitigs)                                     src/kphf/pfhash.rs:40-73 */
+mazu_status_t mazu_b200_index_create_pfhash(const mazu_unitig_set_desc_t* unitigs, int32_t device, mazu_index_t** out);
+/* PFHash::from_parts(unitigs, BooPHF, pos)                             src/kphf/pfhash.rs:34-36 */
+mazu_status_t mazu_b200_index_create_pfhash_from_parts(const mazu_unitig_set_desc_t* unitigs, const mazu_boophf_desc_t* mphf,
+                                                       const mazu_packed_vec_desc_t* pos, int32_t device, mazu_index_t** out);
+/* ModIndex::from_parts(base, SSHash::from_unitig_set(idx.as_ref().clone(), ..), u2pos.clone(), refs.clone())
+ * as in src/pf1/dense_index.rs:315-328: new handle with a rebuilt K2U sharing U2Pos + refs */
+mazu_status_t mazu_b200_index_rebuild_k2u(const mazu_index_t* src, int32_t k2u_kind, uint32_t w, uint64_t skew_param,
+                                          uint64_t hash_seed, mazu_index_t** out);
+/* the U2Pos half of ModIndex::from_parts (src/index.rs:80-87):
+ * DenseUnitigTable{ctable: Vec<u64>, contig_offsets}    src/index/dense_unitig_table.rs:13-18 */
+mazu_status_t mazu_b200_index_attach_u2pos_dense(mazu_index_t* idx, const uint64_t* ctable, uint64_t n_occs,
+                                                 const mazu_packed_vec_desc_t* contig_offsets);
+/* PiscemUnitigTable{ref_shift,pos_mask,ctable: IntVector,contig_offsets}  src/index/dense_unitig_table.rs:109-118 */
+mazu_status_t mazu_b200_index_attach_u2pos_piscem(mazu_index_t* idx, const mazu_packed_vec_desc_t* ctable, uint64_t ref_shift,
+                                                  uint64_t pos_mask, const mazu_packed_vec_desc_t* contig_offsets);
+/* RefSeqCollection::from_parts(seq, prefix_sum)                        src/refseq.rs:124-126 */
+mazu_status_t mazu_b200_index_attach_refseq(mazu_index_t* idx, const uint64_t* seq_words, const uint64_t* prefix_sum,
+                                            uint64_t n_refs);
+void mazu_b200_index_destroy(mazu_index_t* idx);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2U accessors (src/kphf/mod.rs:58-67) and index stats
+ * ------------------------------------------------------------------------------------------- */
+enum { MAZU_INFO_K = 0, MAZU_INFO_N_UNITIGS = 1, MAZU_INFO_N_KMERS = 2, MAZU_INFO_SUM_UNITIGS_LEN = 3,
+       MAZU_INFO_N_MINIMIZERS = 4 /* SSHash::n_minimizers, sshash.rs:333-335 */,
+       MAZU_INFO_N_KMERS_IN_SKEW_INDEX = 5 /* sshash.rs:337-339 */, MAZU_INFO_N_REFS = 6, MAZU_INFO_N_TOTAL_OCCS = 7,
+       MAZU_INFO_K2U_KIND = 8, MAZU_INFO_U2POS_KIND = 9, MAZU_INFO_DEVICE_BYTES = 10, MAZU_INFO_W = 11,
+       MAZU_INFO_N_MINIMIZER_OCCS = 12, MAZU_INFO_MPHF_LEVELS = 13, MAZU_INFO_DEVICE = 14 };
+uint64_t mazu_b200_index_info(const mazu_index_t* idx, int32_t what);
+/* K2U::unitig_len(id)  src/kphf/mod.rs:61 ; UnitigSet::unitig_start_pos  src/unitig_set.rs:197-199 */
+mazu_status_t mazu_b200_unitig_len(const mazu_index_t* idx, uint64_t unitig_id, uint64_t* len, uint64_t* start_pos);
+
+/* ---------------------------------------------------------------------------------------------
+ * Queries
+ * ------------------------------------------------------------------------------------------- */
+/* K2U::k2u for a batch of forward k-mer words (src/kphf/mod.rs:66; PFHash src/kphf/pfhash.rs:108-134,
+ * SSHash src/kphf/sshash.rs:471-555).  fw_words[i] holds a k-mer with base j at bits [2j,2j+2);
+ * `k` is the query k-mer length (must equal the index's k).  A Rust `impl K2U` calls this with n = 1. */
+mazu_status_t mazu_b200_k2u_batch(const mazu_index_t* idx, const uint64_t* fw_words, uint64_t n, uint32_t k,
+                                  mazu_hit_t* out_hits, int32_t mem, void* stream);
+
+/* The read loop of `kphf bench` / validate_ckmers (src/bin/kphf/main.rs:299-322,
+ * src/index/validate.rs:54-81, src/index/caching.rs:175-201): CanonicalKmerIterator::from_u8_slice
+ * over each read + k2u (MAZU_MODE_RANDOM) or StreamingK2U::k2u_streaming (MAZU_MODE_STREAMING).
+ *   bases         ASCII reads, concatenated
+ *   read_offsets  n_reads+1 byte offsets; may be NULL when uniform_read_len > 0 (read r = bases[r*len, (r+1)*len))
+ *   kmer_offsets  optional out, n_reads+1: slot of read r's first k-mer = sum_{r'<r} max(len-k+1,0)
+ *   out_hits      optional out, one record per k-mer slot (slot = kmer_offsets[r] + position in read);
+ *                 windows with a non-ACGT base get {~0,~0,~0,MAZU_SKIPPED}
+ *   counts        optional out {n_kmers (valid windows), n_hit, n_miss} -- the counters of main.rs:282-284
+ * In MAZU_MEM_DEVICE all four are device pointers and counts is ACCUMULATED into (zero it first). */
+mazu_status_t mazu_b200_query_reads(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets,
+                                    uint64_t n_reads, uint64_t uniform_read_len, int32_t mode, uint64_t* kmer_offsets,
+                                    mazu_hit_t* out_hits, uint64_t* counts, int32_t mem, void* stream);
+/* number of k-mer slots query_reads writes for this batch (host arithmetic; read_offsets on host or NULL) */
+uint64_t mazu_b200_count_kmer_slots(const mazu_index_t* idx, const uint64_t* read_offsets, uint64_t n_reads,
+                                    uint64_t uniform_read_len);
+
+/* Stage 1 alone (kmers::CanonicalKmerIterator + Kmer::canonical_minimizer):
+ * per k-mer slot of ONE uniform batch: fw word, rc word, minimizer word, minimizer offset, valid flag.
+ * Device pointers only; any output may be NULL. For PFHash indexes (no w) the minimizer outputs are zero. */
+mazu_status_t mazu_b200_encode_reads(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets,
+                                     uint64_t n_reads, uint64_t uniform_read_len, const uint64_t* kmer_offsets,
+                                     uint64_t* out_fw, uint64_t* out_rc, uint64_t* out_mm_word, uint32_t* out_mm_offset,
+                                     uint8_t* out_valid, void* stream);
+
+/* U2Pos::encoded_unitig_occs + decode_unitig_occs for a batch of unitig ids
+ * (src/index.rs:349-361, src/index/dense_unitig_table.rs:55-76,127-153, UnitigOcc::decode_pf1 src/index.rs:335-346,
+ * UnitigOcc::decode_piscem src/spt_compact.rs:99-110).  unitig id ~0 (a miss) yields an empty list.
+ *   out_offsets  n+1 prefix of list lengths (always written)
+ *   out_occs     capacity `cap` records; may be NULL to only size the output (then *out_total is the need)
+ * Returns MAZU_ERR_INVALID_ARG if cap is too small (out_total still valid). */
+mazu_status_t mazu_b200_decode_occs(const mazu_index_t* idx, const uint32_t* unitig_ids, uint64_t n, uint64_t* out_offsets,
+                                    mazu_occ_t* out_occs, uint64_t cap, uint64_t* out_total, int32_t mem, void* stream);
+/* GetRefPos::project_hits / project_onto_u_occs for a batch of hits (src/index.rs:174-216): same output
+ * convention as decode_occs but records are MappedRefPos.  Misses / skipped records yield empty lists. */
+mazu_status_t mazu_b200_project_hits(const mazu_index_t* idx, const mazu_hit_t* hits, uint64_t n, uint64_t* out_offsets,
+                                     mazu_occ_t* out_mrps, uint64_t cap, uint64_t* out_total, int32_t mem, void* stream);
+
+/* Validate::validate_self (src/index/validate.rs:24-52): every reference k-mer must map back to its own
+ * (ref_id,pos).  counts = {n_queries, n_identity, n_twin, n_projected, n_fail}; the reference panics when n_fail != 0. */
+mazu_status_t mazu_b200_validate_self(const mazu_index_t* idx, uint64_t counts[5]);
+/* K2U::validate_self / validate_self_parallel (src/kphf/mod.rs:69-139): every unitig k-mer, fw then swapped */
+mazu_status_t mazu_b200_k2u_validate_self(const mazu_index_t* idx, uint64_t counts[5]);
+
+/* ---------------------------------------------------------------------------------------------
+ * Measurement helper: independent random 32-byte gathers over a table (the P_rand denominator of
+ * DESIGN.md / BASELINE.md section 2).  table_bytes of device memory are allocated internally.
+ * Returns achieved sectors per second in *sectors_per_s.
+ * ------------------------------------------------------------------------------------------- */
+mazu_status_t mazu_b200_measure_random_gather(uint64_t table_bytes, uint64_t n_gathers, int32_t iters, int32_t device,
+                                              double* sectors_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAZU_B200_H */

@@ -1,0 +1,804 @@
+// extern "C" surface of libmazu_b200.so (include/mazu_b200.h): index upload, kernel launches, and the
+// chunked host<->device pipelines behind MAZU_MEM_HOST calls.  There is no CPU fallback: every query
+// entry point launches the CUDA kernels of kernels.cuh or fails with MAZU_ERR_CUDA.
+#include <cub/device/device_scan.cuh>
+
+#include <mutex>
+
+#include "formats.hpp"
+#include "kernels.cuh"
+
+using namespace mazu;
+
+namespace {
+
+thread_local std::string g_err;
+
+#define MZ_CUDA(expr)                                                                                                   \
+  do {                                                                                                                  \
+    cudaError_t _e = (expr);                                                                                            \
+    if (_e != cudaSuccess) throw Error(MAZU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+  } while (0)
+
+template <class F>
+mazu_status_t guarded(F&& f) {
+  try {
+    f();
+    return MAZU_OK;
+  } catch (const Error& e) {
+    g_err = e.what();
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    g_err = "out of host memory";
+    return MAZU_ERR_OTHER;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return MAZU_ERR_OTHER;
+  }
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    MZ_CUDA(cudaSetDevice(dev));
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int device = 0;
+  DevBuf(size_t n, int dev) : bytes(n), device(dev) { MZ_CUDA(cudaMalloc(&p, n ? n : 1)); }
+  ~DevBuf() {
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    cudaFree(p);
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+using DevBufP = std::shared_ptr<DevBuf>;
+
+template <class T>
+DevBufP upload(const T* host, size_t n, int dev, size_t pad_elems = 0) {
+  auto b = std::make_shared<DevBuf>((n + pad_elems) * sizeof(T), dev);
+  if (pad_elems) MZ_CUDA(cudaMemset(b->p, 0, (n + pad_elems) * sizeof(T)));
+  if (n) MZ_CUDA(cudaMemcpy(b->p, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return b;
+}
+template <class T>
+DevBufP upload(const std::vector<T>& v, int dev, size_t pad_elems = 0) {
+  return upload(v.data(), v.size(), dev, pad_elems);
+}
+
+// a group of device buffers + the view fields they back; groups are shared between handles
+// created by rebuild_k2u (the reference clones u2pos / refs there; they are immutable so we share)
+struct UnitigsDev {
+  std::vector<DevBufP> bufs;
+  UnitigsView view{};
+  size_t bytes = 0;
+};
+struct K2UDev {
+  std::vector<DevBufP> bufs;
+  size_t bytes = 0;
+};
+struct U2PosDev {
+  std::vector<DevBufP> bufs;
+  size_t bytes = 0;
+};
+struct RefsDev {
+  std::vector<DevBufP> bufs;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct mazu_index {
+  int device = 0;
+  int sm_count = 148;
+  std::shared_ptr<const UnitigSetHost> unitigs;
+  std::shared_ptr<K2UHost> k2u;
+  std::shared_ptr<U2PosHost> u2pos;
+  std::shared_ptr<RefSeqHost> refs;
+  std::shared_ptr<UnitigsDev> d_unitigs;
+  std::shared_ptr<K2UDev> d_k2u;
+  std::shared_ptr<U2PosDev> d_u2pos;
+  std::shared_ptr<RefsDev> d_refs;
+  IndexView view{};
+  u64 device_bytes() const {
+    return (d_unitigs ? d_unitigs->bytes : 0) + (d_k2u ? d_k2u->bytes : 0) + (d_u2pos ? d_u2pos->bytes : 0) + (d_refs ? d_refs->bytes : 0);
+  }
+};
+
+namespace {
+
+static const u32 DIR_SHIFT = 6;  // one directory entry per 64 bases
+
+std::shared_ptr<UnitigsDev> upload_unitigs(const UnitigSetHost& us, int dev) {
+  auto d = std::make_shared<UnitigsDev>();
+  const u64 L = us.total_len(), U = us.n_unitigs();
+  if (U >> 32) throw Error(MAZU_ERR_INVALID_ARG, "more than 2^32 unitigs");
+  u64 nw = (2 * L + 63) / 64;
+  auto b_seq = upload(us.useq.data(), std::min<u64>(nw, us.useq.size()), dev, 4);
+  // directory: unitig containing the first base of every 2^DIR_SHIFT block
+  u64 nd = (L >> DIR_SHIFT) + 2;
+  std::vector<u32> dir(nd, (u32)(U ? U - 1 : 0));
+  {
+    u64 ui = 0;
+    for (u64 b = 0; b < nd; ++b) {
+      u64 p = b << DIR_SHIFT;
+      if (p >= L) break;
+      while (us.accum[ui + 1] <= p) ++ui;
+      dir[b] = (u32)ui;
+    }
+  }
+  auto b_dir = upload(dir, dev);
+  auto b_starts = upload(us.accum, dev, 4);
+  d->bufs = {b_seq, b_dir, b_starts};
+  d->bytes = b_seq->bytes + b_dir->bytes + b_starts->bytes;
+  d->view.useq = (const u64*)b_seq->p;
+  d->view.dir = (const u32*)b_dir->p;
+  d->view.starts = (const u64*)b_starts->p;
+  d->view.total_len = L;
+  d->view.n_unitigs = U;
+  d->view.k = us.k;
+  d->view.dir_shift = DIR_SHIFT;
+  return d;
+}
+
+RankedLevels upload_mphf(const MphfHost& m, int dev, K2UDev& d) {
+  RankedLevels v = m.view();
+  auto b = upload(m.blocks, dev, 8);
+  auto fk = upload(m.fb_keys, dev), fv = upload(m.fb_vals, dev);
+  d.bufs.insert(d.bufs.end(), {b, fk, fv});
+  d.bytes += b->bytes + fk->bytes + fv->bytes;
+  v.blocks = (const u32*)b->p;
+  v.fb_keys = (const u64*)fk->p;
+  v.fb_vals = (const u64*)fv->p;
+  return v;
+}
+PackedVecView upload_packed(const PackedVec& pv, int dev, std::vector<DevBufP>& bufs, size_t& bytes) {
+  auto b = upload(pv.words, dev, 2);
+  bufs.push_back(b);
+  bytes += b->bytes;
+  return PackedVecView{(const u64*)b->p, pv.len, (u32)pv.width, 0};
+}
+
+void upload_k2u(mazu_index& ix) {
+  auto d = std::make_shared<K2UDev>();
+  const K2UHost& h = *ix.k2u;
+  IndexView& v = ix.view;
+  v.k2u_kind = (u32)h.kind;
+  v.mphf = upload_mphf(h.mphf, ix.device, *d);
+  v.pos = upload_packed(h.pos, ix.device, d->bufs, d->bytes);
+  v.w = h.w;
+  v.seed = h.seed;
+  v.skew_param = h.skew_param;
+  v.has_skew = h.has_skew ? 1u : 0u;
+  if (h.kind == MAZU_K2U_SSHASH) {
+    auto bb = upload(h.sizes.blocks, ix.device, 4);
+    auto be = upload(h.sizes.exceptions, ix.device);
+    d->bufs.insert(d->bufs.end(), {bb, be});
+    d->bytes += bb->bytes + be->bytes;
+    v.sizes = BlockedEFView{(const u64*)bb->p, (const u64*)be->p, h.sizes.n, h.sizes.l, h.sizes.log_s};
+    if (h.has_skew) {
+      v.skew_mphf = upload_mphf(h.skew_mphf, ix.device, *d);
+      v.skew_pos = upload_packed(h.skew_pos, ix.device, d->bufs, d->bytes);
+    }
+  }
+  ix.d_k2u = d;
+}
+void upload_u2pos(mazu_index& ix) {
+  IndexView& v = ix.view;
+  v.u2pos_kind = MAZU_U2POS_NONE;
+  if (!ix.u2pos || ix.u2pos->kind == MAZU_U2POS_NONE) return;
+  if (!ix.d_u2pos) {
+    auto d = std::make_shared<U2PosDev>();
+    auto b = upload(ix.u2pos->ctable_words, ix.device, 2);
+    d->bufs.push_back(b);
+    d->bytes += b->bytes;
+    upload_packed(ix.u2pos->contig_offsets, ix.device, d->bufs, d->bytes);
+    ix.d_u2pos = d;
+  }
+  const U2PosHost& u = *ix.u2pos;
+  v.u2pos_kind = (u32)u.kind;
+  v.ctable_words = (const u64*)ix.d_u2pos->bufs[0]->p;
+  v.n_occs = u.n_occs;
+  v.ctable_width = u.ctable_width;
+  v.ref_shift = (u32)u.ref_shift;
+  v.pos_mask = u.pos_mask;
+  v.contig_offsets = PackedVecView{(const u64*)ix.d_u2pos->bufs[1]->p, u.contig_offsets.len, (u32)u.contig_offsets.width, 0};
+}
+void upload_refs(mazu_index& ix) {
+  IndexView& v = ix.view;
+  v.refseq = nullptr;
+  v.ref_prefix = nullptr;
+  v.n_refs = ix.refs ? ix.refs->n_refs() : 0;
+  if (!ix.refs || !ix.refs->has_seq) return;
+  if (!ix.d_refs) {
+    auto d = std::make_shared<RefsDev>();
+    auto bs = upload(ix.refs->seq_words, ix.device, 2);
+    auto bp = upload(ix.refs->prefix, ix.device);
+    d->bufs = {bs, bp};
+    d->bytes = bs->bytes + bp->bytes;
+    ix.d_refs = d;
+  }
+  v.refseq = (const u64*)ix.d_refs->bufs[0]->p;
+  v.ref_prefix = (const u64*)ix.d_refs->bufs[1]->p;
+}
+
+mazu_index* finalize_index(std::unique_ptr<mazu_index> ix) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) throw Error(MAZU_ERR_CUDA, "no CUDA device visible: libmazu_b200 has no CPU fallback");
+  if (ix->device < 0 || ix->device >= n) throw Error(MAZU_ERR_INVALID_ARG, "device ordinal out of range");
+  DeviceGuard g(ix->device);
+  cudaDeviceProp prop;
+  MZ_CUDA(cudaGetDeviceProperties(&prop, ix->device));
+  ix->sm_count = prop.multiProcessorCount;
+  if (!ix->d_unitigs) ix->d_unitigs = upload_unitigs(*ix->unitigs, ix->device);
+  ix->view.unitigs = ix->d_unitigs->view;
+  upload_k2u(*ix);
+  upload_u2pos(*ix);
+  upload_refs(*ix);
+  MZ_CUDA(cudaDeviceSynchronize());
+  return ix.release();
+}
+
+mazu_index* index_from_loaded(LoadedIndex&& L, int device) {
+  auto ix = std::make_unique<mazu_index>();
+  ix->device = device;
+  ix->unitigs = L.unitigs;
+  ix->k2u = L.k2u;
+  ix->u2pos = L.u2pos;
+  ix->refs = L.refs;
+  return finalize_index(std::move(ix));
+}
+
+template <class K>
+int grid_for(K kernel, int block, const mazu_index* ix, u64 work_items_per_block_hint, u64 n_items) {
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0) != cudaSuccess || occ < 1) occ = 1;
+  u64 want = (n_items + work_items_per_block_hint - 1) / work_items_per_block_hint;
+  u64 cap = (u64)ix->sm_count * (u64)occ;
+  return (int)std::max<u64>(1, std::min(want, cap));
+}
+
+void check_k(const mazu_index* ix, u32 k) {
+  if (k != ix->unitigs->k)
+    throw Error(MAZU_ERR_K_MISMATCH, "Got query k-mer size k=" + std::to_string(k) + ", expected k=" + std::to_string(ix->unitigs->k) + ".");
+}
+
+void launch_k2u_batch(const mazu_index* ix, const u64* d_words, u64 n, Hit* d_out, cudaStream_t s) {
+  if (n == 0) return;
+  int grid = grid_for(k2u_batch_kernel, 256, ix, 256, n);
+  k2u_batch_kernel<<<grid, 256, 0, s>>>(ix->view, d_words, n, d_out);
+  MZ_CUDA(cudaGetLastError());
+}
+
+void launch_query_reads(const mazu_index* ix, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, int mode,
+                        const u64* d_kmer_offsets, Hit* d_out, u64* d_counts, cudaStream_t s) {
+  if (n_reads == 0) return;
+  if (mode == MAZU_MODE_RANDOM) {
+    int grid = grid_for(query_reads_kernel<0>, QR_WARPS * 32, ix, QR_WARPS, n_reads);
+    query_reads_kernel<0><<<grid, QR_WARPS * 32, 0, s>>>(ix->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out,
+                                                         (unsigned long long*)d_counts);
+  } else {
+    int grid = grid_for(query_reads_kernel<1>, QR_WARPS * 32, ix, QR_WARPS, n_reads);
+    query_reads_kernel<1><<<grid, QR_WARPS * 32, 0, s>>>(ix->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out,
+                                                         (unsigned long long*)d_counts);
+  }
+  MZ_CUDA(cudaGetLastError());
+}
+
+// exclusive scan with the total appended: out[0..n] from in[0..n)
+void device_exclusive_scan(const u64* d_in, u64* d_out, u64 n, cudaStream_t s) {
+  // scan n+1 items where the last input is ignored: simplest is an exclusive scan over n items plus one tail kernel-free trick:
+  // run ExclusiveSum over n+1 elements with in[n] readable (callers allocate n+1).
+  size_t tmp_bytes = 0;
+  MZ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_in, d_out, (size_t)(n + 1), s));
+  void* tmp = nullptr;
+  MZ_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, s));
+  MZ_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_in, d_out, (size_t)(n + 1), s));
+  MZ_CUDA(cudaFreeAsync(tmp, s));
+}
+
+struct StreamPair {
+  cudaStream_t s[2] = {nullptr, nullptr};
+  StreamPair() {
+    for (auto& x : s) MZ_CUDA(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+  }
+  ~StreamPair() {
+    for (auto& x : s)
+      if (x) cudaStreamDestroy(x);
+  }
+};
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* mazu_b200_last_error(void) { return g_err.c_str(); }
+
+int32_t mazu_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+mazu_status_t mazu_b200_dense_index_deserialize_from_cpp(const char* dir, int32_t device, mazu_index_t** out) {
+  return guarded([&] {
+    if (!dir || !out) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    *out = index_from_loaded(load_pf1_dense(dir), device);
+  });
+}
+
+mazu_status_t mazu_b200_index_from_cf_prefix(const char* prefix, int32_t index_kind, uint32_t w, uint64_t skew_param, uint64_t hash_seed,
+                                             int32_t device, mazu_index_t** out) {
+  return guarded([&] {
+    if (!prefix || !out) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    *out = index_from_loaded(load_cf_prefix(prefix, index_kind, w, skew_param, hash_seed), device);
+  });
+}
+
+mazu_status_t mazu_b200_index_create_sshash(const mazu_unitig_set_desc_t* unitigs, uint32_t w, uint64_t skew_param, uint64_t hash_seed,
+                                            int32_t device, mazu_index_t** out) {
+  return guarded([&] {
+    if (!unitigs || !out) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    LoadedIndex L;
+    L.unitigs = std::make_shared<UnitigSetHost>(UnitigSetHost::from_desc(*unitigs));
+    L.k2u = build_sshash(L.unitigs, w, skew_param, hash_seed);
+    *out = index_from_loaded(std::move(L), device);
+  });
+}
+
+mazu_status_t mazu_b200_index_create_pfhash(const mazu_unitig_set_desc_t* unitigs, int32_t device, mazu_index_t** out) {
+  return guarded([&] {
+    if (!unitigs || !out) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    LoadedIndex L;
+    L.unitigs = std::make_shared<UnitigSetHost>(UnitigSetHost::from_desc(*unitigs));
+    L.k2u = build_pfhash(L.unitigs);
+    *out = index_from_loaded(std::move(L), device);
+  });
+}
+
+mazu_status_t mazu_b200_index_create_pfhash_from_parts(const mazu_unitig_set_desc_t* unitigs, const mazu_boophf_desc_t* mphf,
+                                                       const mazu_packed_vec_desc_t* pos, int32_t device, mazu_index_t** out) {
+  return guarded([&] {
+    if (!unitigs || !mphf || !pos || !out) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    LoadedIndex L;
+    L.unitigs = std::make_shared<UnitigSetHost>(UnitigSetHost::from_desc(*unitigs));
+    L.k2u = pfhash_from_parts(L.unitigs, *mphf, *pos);
+    *out = index_from_loaded(std::move(L), device);
+  });
+}
+
+mazu_status_t mazu_b200_index_rebuild_k2u(const mazu_index_t* src, int32_t k2u_kind, uint32_t w, uint64_t skew_param, uint64_t hash_seed,
+                                          mazu_index_t** out) {
+  return guarded([&] {
+    if (!src || !out) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    auto ix = std::make_unique<mazu_index>();
+    ix->device = src->device;
+    ix->unitigs = src->unitigs;
+    ix->u2pos = src->u2pos;
+    ix->refs = src->refs;
+    ix->d_unitigs = src->d_unitigs;
+    ix->d_u2pos = src->d_u2pos;
+    ix->d_refs = src->d_refs;
+    if (k2u_kind == MAZU_K2U_SSHASH) ix->k2u = build_sshash(ix->unitigs, w, skew_param, hash_seed);
+    else if (k2u_kind == MAZU_K2U_PFHASH) ix->k2u = build_pfhash(ix->unitigs);
+    else throw Error(MAZU_ERR_INVALID_ARG, "unknown k2u kind");
+    *out = finalize_index(std::move(ix));
+  });
+}
+
+mazu_status_t mazu_b200_index_attach_u2pos_dense(mazu_index_t* idx, const uint64_t* ctable, uint64_t n_occs,
+                                                 const mazu_packed_vec_desc_t* contig_offsets) {
+  return guarded([&] {
+    if (!idx || !ctable || !contig_offsets) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    if (contig_offsets->len != idx->unitigs->n_unitigs() + 1) throw Error(MAZU_ERR_INVALID_DATA, "contig_offsets.len != n_unitigs + 1");
+    auto u = std::make_shared<U2PosHost>();
+    u->kind = MAZU_U2POS_DENSE;
+    u->ctable_words.assign(ctable, ctable + n_occs);
+    u->n_occs = n_occs;
+    u->ctable_width = 64;
+    u->contig_offsets = PackedVec::from_desc(*contig_offsets);
+    DeviceGuard g(idx->device);
+    idx->u2pos = u;
+    idx->d_u2pos.reset();
+    upload_u2pos(*idx);
+  });
+}
+
+mazu_status_t mazu_b200_index_attach_u2pos_piscem(mazu_index_t* idx, const mazu_packed_vec_desc_t* ctable, uint64_t ref_shift,
+                                                  uint64_t pos_mask, const mazu_packed_vec_desc_t* contig_offsets) {
+  return guarded([&] {
+    if (!idx || !ctable || !contig_offsets) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    if (contig_offsets->len != idx->unitigs->n_unitigs() + 1) throw Error(MAZU_ERR_INVALID_DATA, "contig_offsets.len != n_unitigs + 1");
+    if (ref_shift >= 64) throw Error(MAZU_ERR_INVALID_ARG, "ref_shift must be < 64");
+    auto u = std::make_shared<U2PosHost>();
+    u->kind = MAZU_U2POS_PISCEM;
+    PackedVec ct = PackedVec::from_desc(*ctable);
+    u->ctable_words = ct.words;
+    u->n_occs = ct.len;
+    u->ctable_width = (u32)ct.width;
+    u->ref_shift = ref_shift;
+    u->pos_mask = pos_mask;
+    u->contig_offsets = PackedVec::from_desc(*contig_offsets);
+    DeviceGuard g(idx->device);
+    idx->u2pos = u;
+    idx->d_u2pos.reset();
+    upload_u2pos(*idx);
+  });
+}
+
+mazu_status_t mazu_b200_index_attach_refseq(mazu_index_t* idx, const uint64_t* seq_words, const uint64_t* prefix_sum, uint64_t n_refs) {
+  return guarded([&] {
+    if (!idx || !prefix_sum) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    auto r = std::make_shared<RefSeqHost>();
+    r->prefix.assign(prefix_sum, prefix_sum + n_refs + 1);
+    if (seq_words) {
+      r->has_seq = true;
+      u64 nw = (2 * r->prefix.back() + 63) / 64;
+      r->seq_words.assign(seq_words, seq_words + nw);
+    }
+    DeviceGuard g(idx->device);
+    idx->refs = r;
+    idx->d_refs.reset();
+    upload_refs(*idx);
+  });
+}
+
+void mazu_b200_index_destroy(mazu_index_t* idx) { delete idx; }
+
+uint64_t mazu_b200_index_info(const mazu_index_t* idx, int32_t what) {
+  if (!idx) return 0;
+  switch (what) {
+    case MAZU_INFO_K: return idx->unitigs->k;
+    case MAZU_INFO_N_UNITIGS: return idx->unitigs->n_unitigs();
+    case MAZU_INFO_N_KMERS: return idx->unitigs->n_kmers();
+    case MAZU_INFO_SUM_UNITIGS_LEN: return idx->unitigs->total_len();
+    case MAZU_INFO_N_MINIMIZERS: return idx->k2u->kind == MAZU_K2U_SSHASH ? idx->k2u->sizes.n : 0;  // len of the prefix sum (sshash.rs:333-335)
+    case MAZU_INFO_N_KMERS_IN_SKEW_INDEX: return idx->k2u->n_skew_kmers;
+    case MAZU_INFO_N_REFS: return idx->refs ? idx->refs->n_refs() : 0;
+    case MAZU_INFO_N_TOTAL_OCCS: return idx->u2pos ? idx->u2pos->n_occs : 0;
+    case MAZU_INFO_K2U_KIND: return (u64)idx->k2u->kind;
+    case MAZU_INFO_U2POS_KIND: return idx->u2pos ? (u64)idx->u2pos->kind : 0;
+    case MAZU_INFO_DEVICE_BYTES: return idx->device_bytes();
+    case MAZU_INFO_W: return idx->k2u->w;
+    case MAZU_INFO_N_MINIMIZER_OCCS: return idx->k2u->n_minimizer_occs;
+    case MAZU_INFO_MPHF_LEVELS: return idx->view.mphf.n_levels;
+    case MAZU_INFO_DEVICE: return (u64)idx->device;
+  }
+  return 0;
+}
+
+mazu_status_t mazu_b200_unitig_len(const mazu_index_t* idx, uint64_t unitig_id, uint64_t* len, uint64_t* start_pos) {
+  return guarded([&] {
+    if (!idx) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    if (unitig_id >= idx->unitigs->n_unitigs()) throw Error(MAZU_ERR_INVALID_ARG, "unitig id out of range");
+    if (len) *len = idx->unitigs->unitig_len(unitig_id);
+    if (start_pos) *start_pos = idx->unitigs->accum[unitig_id];
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+mazu_status_t mazu_b200_k2u_batch(const mazu_index_t* idx, const uint64_t* fw_words, uint64_t n, uint32_t k, mazu_hit_t* out_hits,
+                                  int32_t mem, void* stream) {
+  return guarded([&] {
+    if (!idx || (n && (!fw_words || !out_hits))) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    check_k(idx, k);
+    DeviceGuard g(idx->device);
+    if (mem == MAZU_MEM_DEVICE) {
+      launch_k2u_batch(idx, fw_words, n, (Hit*)out_hits, (cudaStream_t)stream);
+      return;
+    }
+    // host buffers: double-buffered chunks, H2D -> kernel -> D2H on two streams
+    const u64 CH = 1ull << 22;
+    StreamPair sp;
+    DevBuf din0(std::min(n, CH) * 8, idx->device), din1(std::min(n, CH) * 8, idx->device);
+    DevBuf dout0(std::min(n, CH) * 16, idx->device), dout1(std::min(n, CH) * 16, idx->device);
+    DevBuf* din[2] = {&din0, &din1};
+    DevBuf* dout[2] = {&dout0, &dout1};
+    int b = 0;
+    for (u64 o = 0; o < n; o += CH, b ^= 1) {
+      u64 m = std::min(CH, n - o);
+      MZ_CUDA(cudaMemcpyAsync(din[b]->p, fw_words + o, m * 8, cudaMemcpyHostToDevice, sp.s[b]));
+      launch_k2u_batch(idx, (const u64*)din[b]->p, m, (Hit*)dout[b]->p, sp.s[b]);
+      MZ_CUDA(cudaMemcpyAsync(out_hits + o, dout[b]->p, m * 16, cudaMemcpyDeviceToHost, sp.s[b]));
+    }
+    MZ_CUDA(cudaStreamSynchronize(sp.s[0]));
+    MZ_CUDA(cudaStreamSynchronize(sp.s[1]));
+  });
+}
+
+uint64_t mazu_b200_count_kmer_slots(const mazu_index_t* idx, const uint64_t* read_offsets, uint64_t n_reads, uint64_t uniform_read_len) {
+  if (!idx) return 0;
+  const u64 k = idx->unitigs->k;
+  if (uniform_read_len) return uniform_read_len >= k ? n_reads * (uniform_read_len - k + 1) : 0;
+  if (!read_offsets) return 0;
+  u64 acc = 0;
+  for (u64 r = 0; r < n_reads; ++r) {
+    u64 len = read_offsets[r + 1] - read_offsets[r];
+    if (len >= k) acc += len - k + 1;
+  }
+  return acc;
+}
+
+mazu_status_t mazu_b200_query_reads(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                                    uint64_t uniform_read_len, int32_t mode, uint64_t* kmer_offsets, mazu_hit_t* out_hits,
+                                    uint64_t* counts, int32_t mem, void* stream) {
+  return guarded([&] {
+    if (!idx) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    if (mode != MAZU_MODE_RANDOM && mode != MAZU_MODE_STREAMING) throw Error(MAZU_ERR_INVALID_ARG, "unknown query mode");
+    if (n_reads && !bases) throw Error(MAZU_ERR_INVALID_ARG, "null bases");
+    if (n_reads && !uniform_read_len && !read_offsets) throw Error(MAZU_ERR_INVALID_ARG, "read_offsets is required for ragged reads");
+    const u32 k = idx->unitigs->k;
+    DeviceGuard g(idx->device);
+    if (mem == MAZU_MEM_DEVICE) {
+      cudaStream_t s = (cudaStream_t)stream;
+      u64* d_koffs = kmer_offsets;
+      void* tmp_koffs = nullptr;
+      if (!uniform_read_len && n_reads) {
+        if (!d_koffs) {
+          MZ_CUDA(cudaMallocAsync(&tmp_koffs, (n_reads + 1) * 8, s));
+          d_koffs = (u64*)tmp_koffs;
+        }
+        void* lens = nullptr;
+        MZ_CUDA(cudaMallocAsync(&lens, (n_reads + 1) * 8, s));
+        MZ_CUDA(cudaMemsetAsync(lens, 0, (n_reads + 1) * 8, s));
+        kmer_counts_kernel<<<(int)std::min<u64>((n_reads + 255) / 256, 4096), 256, 0, s>>>(read_offsets, n_reads, k, (u64*)lens);
+        MZ_CUDA(cudaGetLastError());
+        device_exclusive_scan((const u64*)lens, d_koffs, n_reads, s);
+        MZ_CUDA(cudaFreeAsync(lens, s));
+      }
+      launch_query_reads(idx, bases, read_offsets, n_reads, uniform_read_len, mode, d_koffs, (Hit*)out_hits, counts, s);
+      if (tmp_koffs) MZ_CUDA(cudaFreeAsync(tmp_koffs, s));
+      return;
+    }
+    // ---- host buffers: chunk the batch, overlap H2D / kernel / D2H on two streams ----
+    std::vector<u64> koffs_local;
+    const u64* koffs = nullptr;
+    if (!uniform_read_len) {
+      u64* dst = kmer_offsets;
+      if (!dst) {
+        koffs_local.resize(n_reads + 1);
+        dst = koffs_local.data();
+      }
+      u64 acc = 0;
+      for (u64 r = 0; r < n_reads; ++r) {
+        dst[r] = acc;
+        u64 len = read_offsets[r + 1] - read_offsets[r];
+        if (len >= k) acc += len - k + 1;
+      }
+      dst[n_reads] = acc;
+      koffs = dst;
+    } else if (kmer_offsets) {
+      u64 per = uniform_read_len >= k ? uniform_read_len - k + 1 : 0;
+      for (u64 r = 0; r <= n_reads; ++r) kmer_offsets[r] = r * per;
+    }
+    auto base_off = [&](u64 r) { return uniform_read_len ? r * uniform_read_len : read_offsets[r]; };
+    auto slot_off = [&](u64 r) { return uniform_read_len ? r * (uniform_read_len >= k ? uniform_read_len - k + 1 : 0) : koffs[r]; };
+    // chunk boundaries: ~32 MiB of bases per chunk
+    const u64 TARGET = 32ull << 20;
+    std::vector<u64> cuts{0};
+    {
+      u64 r = 0;
+      while (r < n_reads) {
+        u64 r1;
+        if (uniform_read_len) r1 = std::min(n_reads, r + std::max<u64>(1, TARGET / uniform_read_len));
+        else {
+          u64 lim = read_offsets[r] + TARGET;
+          r1 = (u64)(std::upper_bound(read_offsets + r + 1, read_offsets + n_reads + 1, lim) - read_offsets) - 1;
+          r1 = std::max(r1, r + 1);
+        }
+        cuts.push_back(r1);
+        r = r1;
+      }
+    }
+    u64 max_bases = 0, max_slots = 0, max_reads = 0;
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+      max_bases = std::max(max_bases, base_off(cuts[c + 1]) - base_off(cuts[c]));
+      max_slots = std::max(max_slots, slot_off(cuts[c + 1]) - slot_off(cuts[c]));
+      max_reads = std::max(max_reads, cuts[c + 1] - cuts[c]);
+    }
+    StreamPair sp;
+    std::unique_ptr<DevBuf> d_bases[2], d_ro[2], d_ko[2], d_hits[2];
+    DevBuf d_counts(3 * 8, idx->device);
+    MZ_CUDA(cudaMemset(d_counts.p, 0, 24));
+    for (int b = 0; b < 2; ++b) {
+      d_bases[b] = std::make_unique<DevBuf>(max_bases + 16, idx->device);
+      if (!uniform_read_len) {
+        d_ro[b] = std::make_unique<DevBuf>((max_reads + 1) * 8, idx->device);
+        d_ko[b] = std::make_unique<DevBuf>((max_reads + 1) * 8, idx->device);
+      }
+      if (out_hits) d_hits[b] = std::make_unique<DevBuf>(max_slots * 16 + 16, idx->device);
+    }
+    int b = 0;
+    for (size_t c = 0; c + 1 < cuts.size(); ++c, b ^= 1) {
+      u64 r0 = cuts[c], r1 = cuts[c + 1];
+      u64 b0 = base_off(r0), nb = base_off(r1) - b0;
+      u64 s0 = slot_off(r0), ns = slot_off(r1) - s0;
+      cudaStream_t s = sp.s[b];
+      MZ_CUDA(cudaMemcpyAsync(d_bases[b]->p, bases + b0, nb, cudaMemcpyHostToDevice, s));
+      const u64* dro = nullptr;
+      const u64* dko = nullptr;
+      if (!uniform_read_len) {
+        MZ_CUDA(cudaMemcpyAsync(d_ro[b]->p, read_offsets + r0, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, s));
+        MZ_CUDA(cudaMemcpyAsync(d_ko[b]->p, koffs + r0, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, s));
+        dro = (const u64*)d_ro[b]->p;
+        dko = (const u64*)d_ko[b]->p;
+      }
+      // offsets uploaded are absolute: rebase the data pointers instead of the offset arrays
+      const u8* dbases = (const u8*)d_bases[b]->p - (uniform_read_len ? 0 : b0);
+      Hit* dh = out_hits ? (Hit*)d_hits[b]->p - (uniform_read_len ? 0 : s0) : nullptr;
+      launch_query_reads(idx, dbases, dro, r1 - r0, uniform_read_len, mode, dko, dh, (u64*)d_counts.p, s);
+      if (out_hits && ns) MZ_CUDA(cudaMemcpyAsync(out_hits + s0, d_hits[b]->p, ns * 16, cudaMemcpyDeviceToHost, s));
+    }
+    MZ_CUDA(cudaStreamSynchronize(sp.s[0]));
+    MZ_CUDA(cudaStreamSynchronize(sp.s[1]));
+    if (counts) MZ_CUDA(cudaMemcpy(counts, d_counts.p, 24, cudaMemcpyDeviceToHost));
+  });
+}
+
+mazu_status_t mazu_b200_encode_reads(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                                     uint64_t uniform_read_len, const uint64_t* kmer_offsets, uint64_t* out_fw, uint64_t* out_rc,
+                                     uint64_t* out_mm_word, uint32_t* out_mm_offset, uint8_t* out_valid, void* stream) {
+  return guarded([&] {
+    if (!idx || (n_reads && !bases)) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    if (n_reads && !uniform_read_len && (!read_offsets || !kmer_offsets)) throw Error(MAZU_ERR_INVALID_ARG, "ragged reads need read_offsets and kmer_offsets");
+    if (!n_reads) return;
+    DeviceGuard g(idx->device);
+    int grid = grid_for(encode_reads_kernel, QR_WARPS * 32, idx, QR_WARPS, n_reads);
+    encode_reads_kernel<<<grid, QR_WARPS * 32, 0, (cudaStream_t)stream>>>(idx->view, bases, read_offsets, n_reads, uniform_read_len, kmer_offsets,
+                                                                          out_fw, out_rc, out_mm_word, out_mm_offset, out_valid);
+    MZ_CUDA(cudaGetLastError());
+  });
+}
+
+// shared driver of decode_occs / project_hits
+static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu_hit_t* hits, uint64_t n, uint64_t* out_offsets,
+                       mazu_occ_t* out, uint64_t cap, uint64_t* out_total, int32_t mem, void* stream) {
+  if (!idx || !out_offsets) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+  if (idx->view.u2pos_kind == MAZU_U2POS_NONE) throw Error(MAZU_ERR_NO_U2POS, "index has no U2Pos table");
+  DeviceGuard g(idx->device);
+  const bool project = hits != nullptr;
+  cudaStream_t s = (cudaStream_t)stream;
+  std::unique_ptr<StreamPair> sp;
+  std::unique_ptr<DevBuf> d_in, d_offs, d_out;
+  const u32* d_uids = uids;
+  const Hit* d_hits = (const Hit*)hits;
+  u64* d_offsets = out_offsets;
+  if (mem == MAZU_MEM_HOST) {
+    sp = std::make_unique<StreamPair>();
+    s = sp->s[0];
+    d_in = std::make_unique<DevBuf>(n * (project ? 16 : 4) + 16, idx->device);
+    MZ_CUDA(cudaMemcpyAsync(d_in->p, project ? (const void*)hits : (const void*)uids, n * (project ? 16 : 4), cudaMemcpyHostToDevice, s));
+    d_uids = project ? nullptr : (const u32*)d_in->p;
+    d_hits = project ? (const Hit*)d_in->p : nullptr;
+    d_offs = std::make_unique<DevBuf>((n + 1) * 8, idx->device);
+    d_offsets = (u64*)d_offs->p;
+  }
+  void* lens = nullptr;
+  MZ_CUDA(cudaMallocAsync(&lens, (n + 1) * 8, s));
+  MZ_CUDA(cudaMemsetAsync(lens, 0, (n + 1) * 8, s));
+  if (n) {
+    occ_lens_kernel<<<(int)std::min<u64>((n + 255) / 256, (u64)idx->sm_count * 8), 256, 0, s>>>(idx->view, d_uids, d_hits, n, (u64*)lens);
+    MZ_CUDA(cudaGetLastError());
+  }
+  device_exclusive_scan((const u64*)lens, d_offsets, n, s);
+  MZ_CUDA(cudaFreeAsync(lens, s));
+  u64 total = 0;
+  bool need_total = mem == MAZU_MEM_HOST || out_total != nullptr;
+  if (need_total) {
+    MZ_CUDA(cudaMemcpyAsync(&total, d_offsets + n, 8, cudaMemcpyDeviceToHost, s));
+    MZ_CUDA(cudaStreamSynchronize(s));
+    if (out_total) *out_total = total;
+  }
+  if (mem == MAZU_MEM_HOST) MZ_CUDA(cudaMemcpyAsync(out_offsets, d_offsets, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+  if (!out) {
+    if (mem == MAZU_MEM_HOST) MZ_CUDA(cudaStreamSynchronize(s));
+    return;
+  }
+  if (need_total && total > cap) {
+    if (mem == MAZU_MEM_HOST) MZ_CUDA(cudaStreamSynchronize(s));
+    throw Error(MAZU_ERR_INVALID_ARG, "output capacity too small: need " + std::to_string(total) + " records");
+  }
+  OccRec* d_o = (OccRec*)out;
+  if (mem == MAZU_MEM_HOST) {
+    d_out = std::make_unique<DevBuf>(total * 12 + 16, idx->device);
+    d_o = (OccRec*)d_out->p;
+  }
+  if (n) {
+    int grid = (int)std::min<u64>((n + 255) / 256, (u64)idx->sm_count * 8);
+    if (project) occ_fill_kernel<true><<<grid, 256, 0, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o);
+    else occ_fill_kernel<false><<<grid, 256, 0, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o);
+    MZ_CUDA(cudaGetLastError());
+  }
+  if (mem == MAZU_MEM_HOST) {
+    if (total) MZ_CUDA(cudaMemcpyAsync(out, d_o, total * 12, cudaMemcpyDeviceToHost, s));
+    MZ_CUDA(cudaStreamSynchronize(s));
+  }
+}
+
+mazu_status_t mazu_b200_decode_occs(const mazu_index_t* idx, const uint32_t* unitig_ids, uint64_t n, uint64_t* out_offsets,
+                                    mazu_occ_t* out_occs, uint64_t cap, uint64_t* out_total, int32_t mem, void* stream) {
+  return guarded([&] {
+    if (n && !unitig_ids) throw Error(MAZU_ERR_INVALID_ARG, "null unitig_ids");
+    occ_driver(idx, unitig_ids, nullptr, n, out_offsets, out_occs, cap, out_total, mem, stream);
+  });
+}
+
+mazu_status_t mazu_b200_project_hits(const mazu_index_t* idx, const mazu_hit_t* hits, uint64_t n, uint64_t* out_offsets,
+                                     mazu_occ_t* out_mrps, uint64_t cap, uint64_t* out_total, int32_t mem, void* stream) {
+  return guarded([&] {
+    if (!hits) throw Error(MAZU_ERR_INVALID_ARG, "null hits");
+    occ_driver(idx, nullptr, hits, n, out_offsets, out_mrps, cap, out_total, mem, stream);
+  });
+}
+
+static void run_validate(const mazu_index_t* idx, bool k2u_only, uint64_t counts[5]) {
+  if (!idx || !counts) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+  DeviceGuard g(idx->device);
+  DevBuf d(5 * 8, idx->device);
+  MZ_CUDA(cudaMemset(d.p, 0, 40));
+  if (k2u_only) {
+    u64 n = idx->unitigs->total_len();
+    int grid = (int)std::max<u64>(1, std::min<u64>((n + 255) / 256, (u64)idx->sm_count * 8));
+    k2u_validate_self_kernel<<<grid, 256>>>(idx->view, (unsigned long long*)d.p);
+  } else {
+    if (!idx->refs || !idx->refs->has_seq) throw Error(MAZU_ERR_NO_REFSEQ, "validate_self: index has no reference sequence (assert has_refseq)");
+    if (idx->view.u2pos_kind == MAZU_U2POS_NONE) throw Error(MAZU_ERR_NO_U2POS, "validate_self: index has no U2Pos table");
+    u64 n = idx->refs->prefix.back();
+    int grid = (int)std::max<u64>(1, std::min<u64>((n + 255) / 256, (u64)idx->sm_count * 8));
+    validate_self_kernel<<<grid, 256>>>(idx->view, (unsigned long long*)d.p);
+  }
+  MZ_CUDA(cudaGetLastError());
+  MZ_CUDA(cudaMemcpy(counts, d.p, 40, cudaMemcpyDeviceToHost));
+}
+
+mazu_status_t mazu_b200_validate_self(const mazu_index_t* idx, uint64_t counts[5]) {
+  return guarded([&] { run_validate(idx, false, counts); });
+}
+mazu_status_t mazu_b200_k2u_validate_self(const mazu_index_t* idx, uint64_t counts[5]) {
+  return guarded([&] { run_validate(idx, true, counts); });
+}
+
+mazu_status_t mazu_b200_measure_random_gather(uint64_t table_bytes, uint64_t n_gathers, int32_t iters, int32_t device, double* sectors_per_s) {
+  return guarded([&] {
+    if (!sectors_per_s || table_bytes < 64) throw Error(MAZU_ERR_INVALID_ARG, "bad argument");
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    MZ_CUDA(cudaGetDeviceProperties(&prop, device));
+    DevBuf table(table_bytes, device), sink(8, device);
+    MZ_CUDA(cudaMemset(table.p, 1, table_bytes));
+    MZ_CUDA(cudaMemset(sink.p, 0, 8));
+    cudaEvent_t e0, e1;
+    MZ_CUDA(cudaEventCreate(&e0));
+    MZ_CUDA(cudaEventCreate(&e1));
+    double best = 0;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, random_gather_kernel, 256, 0);
+    int grid = prop.multiProcessorCount * std::max(occ, 1);
+    for (int it = 0; it < iters + 1; ++it) {
+      MZ_CUDA(cudaEventRecord(e0));
+      random_gather_kernel<<<grid, 256>>>((const uint4*)table.p, table_bytes / 32, n_gathers, 0x1234 + it, (unsigned long long*)sink.p);
+      MZ_CUDA(cudaEventRecord(e1));
+      MZ_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      MZ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (it > 0) best = std::max(best, (double)n_gathers / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *sectors_per_s = best;
+  });
+}
+
+}  // extern "C"

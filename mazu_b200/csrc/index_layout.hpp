@@ -1,0 +1,298 @@
+// Device-resident index layout (what lives in HBM) and the lookup primitives over it.
+//
+// Everything here is laid out for 32-byte DRAM sectors: each logically distinct step of the
+// reference's dependent chain (MPHF level probe, bucket bounds, bucket positions, k-mer window,
+// unitig id/bounds) touches ONE aligned 32-byte block wherever possible.  See DESIGN.md
+// "Data layout in HBM".  The structs hold raw pointers; they are filled by DeviceIndex (device
+// pointers) for kernels, and by the host builders (host pointers) where a builder needs to
+// evaluate its own MPHF.
+#pragma once
+#include "kmer.hpp"
+
+namespace mazu {
+
+#if defined(__CUDA_ARCH__)
+#define MZ_POPC(x) __popc(x)
+#define MZ_POPCLL(x) __popcll(x)
+#define MZ_LDG(p) __ldg(p)
+#else
+#define MZ_POPC(x) __builtin_popcount(x)
+#define MZ_POPCLL(x) __builtin_popcountll(x)
+#define MZ_LDG(p) (*(p))
+#endif
+
+static const u32 MPHF_MAX_LEVELS = 32;
+static const u32 MPHF_BLOCK_BITS = 224;  // payload bits per 32-byte block (7 x u32) + 1 x u32 rank
+enum : u32 { MPHF_FAMILY_BOOPHF = 0, MPHF_FAMILY_NATIVE = 1 };
+
+// ---------------------------------------------------------------------------------------------
+// Ranked bitset blocks: the storage of both MPHF flavours.
+//   block (32 B, aligned) = { u32 ones_before_block_in_level ; u32 bits[7] }   (224 slots)
+// A level probe reads the slot's u32; on a set bit it reads the block's other words to get the
+// rank -- one sector per probed level.  The reference BooPHF keeps bits and 512-bit rank samples
+// in separate arrays (src/pf1/boophf/mod.rs:250-266: 1 bit word + 1 sample + <=8 words).
+// ---------------------------------------------------------------------------------------------
+struct RankedLevels {
+  const u32* blocks;
+  u32 family;
+  u32 n_levels;
+  u64 n_keys;
+  u64 size[MPHF_MAX_LEVELS];       // BOOPHF: n_bits of the level (fastrange modulus); NATIVE: n_blocks
+  u64 block_off[MPHF_MAX_LEVELS];  // first block of the level
+  u64 rank_base[MPHF_MAX_LEVELS];  // keys placed in earlier levels
+  const u64* fb_keys;              // fallback ("final hash"): sorted keys ...
+  const u64* fb_vals;              // ... and their hash values
+  u32 n_fb;
+  u32 _pad;
+};
+
+MZ_HD u32 mulhi32(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (u32)(((u64)a * b) >> 32);
+#endif
+}
+
+// slot -> (block, bit) for the native family: block by the high hash half, bit by the low half
+MZ_HD void native_slot(u64 key, u32 level, u64 n_blocks, u64& blk, u32& bit) {
+  u64 h = fmix64(key ^ (0x9E3779B97F4A7C15ULL * (u64)(level + 1)));
+  blk = mulhi32((u32)(h >> 32), (u32)n_blocks);
+  bit = mulhi32((u32)h, MPHF_BLOCK_BITS);
+}
+
+MZ_HD bool ranked_probe(const RankedLevels& m, u32 level, u64 blk, u32 bit, u64& out) {
+  const u32* b = m.blocks + (m.block_off[level] + blk) * 8;
+  u32 wi = 1 + (bit >> 5), sh = bit & 31;
+  u32 word = MZ_LDG(b + wi);
+  if (!((word >> sh) & 1u)) return false;
+  u32 r = MZ_LDG(b) + MZ_POPC(word & ((1u << sh) - 1u));
+#pragma unroll
+  for (u32 j = 1; j < 7; ++j)
+    if (j < wi) r += MZ_POPC(MZ_LDG(b + j));
+  out = m.rank_base[level] + r;
+  return true;
+}
+
+// MPHF::try_hash_u64 (src/kphf/mod.rs:54-56).  BOOPHF reproduces BooPHF<u64>::lookup
+// (src/pf1/boophf/mod.rs:96-181) bit-exactly; NATIVE is this library's own BBHash-style MPHF.
+// Like boomphf::try_hash, a non-member key may return a false-positive value < n_keys.
+MZ_HD bool mphf_lookup(const RankedLevels& m, u64 key, u64& out) {
+  if (m.family == MPHF_FAMILY_NATIVE) {
+    for (u32 l = 0; l < m.n_levels; ++l) {
+      u64 blk;
+      u32 bit;
+      native_slot(key, l, m.size[l], blk, bit);
+      if (ranked_probe(m, l, blk, bit, out)) return true;
+    }
+  } else {
+    u64 s0 = BOOPHF_SEED0, s1 = BOOPHF_SEED1;  // MultiHashState (src/pf1/boophf/hash.rs:91-97)
+    for (u32 l = 0; l < m.n_levels; ++l) {
+      u64 h;
+      if (l == 0) {
+        h = boophf_hash64(key, BOOPHF_SEED0);
+        s0 = h;
+      } else if (l == 1) {
+        h = boophf_hash64(key, BOOPHF_SEED1);
+        s1 = h;
+      } else {
+        u64 a = s0, b = s1;
+        a ^= a << 23;
+        a = a ^ b ^ (a >> 17) ^ (b >> 26);
+        h = a + b;
+        s0 = b;
+        s1 = a;
+      }
+      u64 pos = mulhi64(h, m.size[l]);  // fast_range_64 (mod.rs:136-144)
+      u64 blk = pos / MPHF_BLOCK_BITS;
+      u32 bit = (u32)(pos - blk * MPHF_BLOCK_BITS);
+      if (ranked_probe(m, l, blk, bit, out)) return true;
+    }
+  }
+  // lookup_in_final_hash (mod.rs:177-181) / native leftovers
+  u32 lo = 0, hi = m.n_fb;
+  while (lo < hi) {
+    u32 mid = (lo + hi) >> 1;
+    u64 kk = MZ_LDG(m.fb_keys + mid);
+    if (kk == key) {
+      out = MZ_LDG(m.fb_vals + mid);
+      return true;
+    }
+    if (kk < key) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Packed integer vector (simple-sds IntVector / pufferfish compact vector), LSB-first.
+// ---------------------------------------------------------------------------------------------
+struct PackedVecView {
+  const u64* words;  // padded by >= 1 word
+  u64 len;
+  u32 width;
+  u32 _pad;
+};
+MZ_HD u64 packed_get(const PackedVecView& v, u64 i) {
+  u64 bit = i * v.width, wi = bit >> 6;
+  u32 sh = (u32)(bit & 63);
+  u64 x = MZ_LDG(v.words + wi) >> sh;
+  if (sh + v.width > 64) x |= MZ_LDG(v.words + wi + 1) << (64 - sh);
+  return v.width >= 64 ? x : (x & ((1ULL << v.width) - 1ULL));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Blocked Elias-Fano: EFVector (src/elias_fano.rs) re-partitioned so that get(i) and get(i+1)
+// -- the bucket bounds of SSHash::k2u (src/kphf/sshash.rs:482-483) -- come from ONE 32-byte block.
+//   block b covers elements [b*S, b*S + S] (S+1 elements, neighbouring blocks overlap by one):
+//     word0          : value of element b*S (the block base); bit 63 set => exception block,
+//                      then bits 0..62 = index of S+1 plain u64 values in `exceptions`
+//     word1, word2   : upper-bits bucket in negated-unary form, relative to (base >> l):
+//                      element j has its bit at position ((x_j >> l) - (x_0 >> l)) + j   (<128)
+//     word3          : lower bits, element j at bits [j*l, (j+1)*l)                      (<=64)
+//   l follows the reference rule l = max(1, msb(u / n)) (elias_fano.rs:63-75).
+// ---------------------------------------------------------------------------------------------
+struct BlockedEFView {
+  const u64* blocks;      // 4 words per block
+  const u64* exceptions;  // (S+1) words per exception block
+  u64 n;                  // number of elements
+  u32 l;
+  u32 log_s;
+};
+
+// position of the j-th (0-based) set bit of the 128-bit value hi:lo; caller guarantees it exists
+MZ_HD u32 select128(u64 lo, u64 hi, u32 j) {
+  u32 c = (u32)MZ_POPCLL(lo);
+  u64 w = lo;
+  u32 base = 0;
+  if (j >= c) {
+    j -= c;
+    w = hi;
+    base = 64;
+  }
+  u32 wl = (u32)w, wh = (u32)(w >> 32);
+  u32 cl = (u32)MZ_POPC(wl);
+  u32 x = wl;
+  if (j >= cl) {
+    j -= cl;
+    x = wh;
+    base += 32;
+  }
+#if defined(__CUDA_ARCH__)
+  return base + __fns(x, 0, (int)j + 1);
+#else
+  for (u32 t = 0; t < j; ++t) x &= x - 1;
+  return base + (u32)__builtin_ctz(x);
+#endif
+}
+
+// returns x_i in `a` and x_{i+1} in `b`; requires i + 1 < n
+MZ_HD void blocked_ef_get2(const BlockedEFView& ef, u64 i, u64& a, u64& b) {
+  u64 blk = i >> ef.log_s;
+  u32 j = (u32)(i & ((1ULL << ef.log_s) - 1ULL));
+  const u64* p = ef.blocks + blk * 4;
+#if defined(__CUDA_ARCH__)
+  const ulonglong2 q0 = __ldg(reinterpret_cast<const ulonglong2*>(p));
+  const ulonglong2 q1 = __ldg(reinterpret_cast<const ulonglong2*>(p) + 1);
+  u64 w0 = q0.x, w1 = q0.y, w2 = q1.x, w3 = q1.y;
+#else
+  u64 w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3];
+#endif
+  if (w0 >> 63) {
+    const u64* e = ef.exceptions + (w0 & ~(1ULL << 63)) * ((1ULL << ef.log_s) + 1ULL);
+    a = MZ_LDG(e + j);
+    b = MZ_LDG(e + j + 1);
+    return;
+  }
+  u32 pj = select128(w1, w2, j);
+  // next set bit after pj
+  u32 pn;
+  if (pj < 63) {
+    u64 rest = w1 & (~0ULL << (pj + 1));
+#if defined(__CUDA_ARCH__)
+    pn = rest ? (u32)(__ffsll((long long)rest) - 1) : 64u + (u32)(__ffsll((long long)w2) - 1);
+#else
+    pn = rest ? (u32)__builtin_ctzll(rest) : 64u + (u32)__builtin_ctzll(w2);
+#endif
+  } else {
+    u64 rest = pj == 63 ? w2 : (pj == 127 ? 0ULL : (w2 & (~0ULL << (pj - 63))));
+#if defined(__CUDA_ARCH__)
+    pn = 64u + (u32)(__ffsll((long long)rest) - 1);
+#else
+    pn = 64u + (u32)__builtin_ctzll(rest);
+#endif
+  }
+  u64 lmask = (1ULL << ef.l) - 1ULL;
+  u64 hb = w0 >> ef.l;
+  a = ((hb + (u64)(pj - j)) << ef.l) | ((w3 >> (j * ef.l)) & lmask);
+  b = ((hb + (u64)(pn - (j + 1))) << ef.l) | ((w3 >> ((j + 1) * ef.l)) & lmask);
+}
+
+// ---------------------------------------------------------------------------------------------
+// UnitigSet (src/unitig_set.rs:31-36) on the device.
+//   useq    2-bit packed concatenated unitigs (+2 pad words: get_kmer_u64 may read past the end)
+//   dir     dir[p >> dir_shift] = id of the unitig containing position (p >> dir_shift) << dir_shift
+//   starts  n_unitigs+1 plain u64 prefix lengths
+// locate(pos) replaces the reference's rank over an L-bit end-marker vector plus 3-4 Elias-Fano
+// get()s (unitig_set.rs:178-209) with one directory sector + one or two `starts` sectors.
+// ---------------------------------------------------------------------------------------------
+struct UnitigsView {
+  const u64* useq;
+  const u32* dir;
+  const u64* starts;
+  u64 total_len;
+  u64 n_unitigs;
+  u32 k;
+  u32 dir_shift;
+};
+// SeqVector::get_kmer_u64(pos, k): 2k bits at bit 2*pos (unitig_set.rs:226-229)
+MZ_HD u64 useq_window(const UnitigsView& u, u64 pos) {
+  u64 bit = 2 * pos, wi = bit >> 6;
+  u32 sh = (u32)(bit & 63);
+  u64 x = MZ_LDG(u.useq + wi) >> sh;
+  if (sh + 2 * u.k > 64) x |= MZ_LDG(u.useq + wi + 1) << (64 - sh);
+  return x & kmer_mask(u.k);
+}
+// pos_to_id + unitig_start_pos + unitig_end_pos (unitig_set.rs:185-204)
+MZ_HD void unitig_locate(const UnitigsView& u, u64 pos, u64& id, u64& start, u64& end) {
+  u64 i = MZ_LDG(u.dir + (pos >> u.dir_shift));
+  u64 e = MZ_LDG(u.starts + i + 1);
+  while (e <= pos) {
+    ++i;
+    e = MZ_LDG(u.starts + i + 1);
+  }
+  id = i;
+  start = MZ_LDG(u.starts + i);
+  end = e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The whole index as the kernels see it (passed by value as a __grid_constant__ parameter).
+// ---------------------------------------------------------------------------------------------
+struct IndexView {
+  u32 k2u_kind;  // MAZU_K2U_PFHASH / MAZU_K2U_SSHASH
+  u32 u2pos_kind;
+  UnitigsView unitigs;
+  RankedLevels mphf;  // PFHash: over canonical k-mers; SSHash: over minimizers
+  PackedVecView pos;  // PFHash: k-mer positions; SSHash: minimizer occurrence positions ("Offsets")
+  // SSHash only
+  BlockedEFView sizes;  // occs_prefix_sum ("Sizes"), n_minimizers + 1 elements
+  u32 w;
+  u32 has_skew;
+  u64 seed;
+  u64 skew_param;
+  RankedLevels skew_mphf;
+  PackedVecView skew_pos;
+  // U2Pos
+  const u64* ctable_words;  // DENSE: one u64 per occurrence; PISCEM: packed `ctable_width`-bit fields
+  u64 n_occs;
+  u32 ctable_width;
+  u32 ref_shift;
+  u64 pos_mask;
+  PackedVecView contig_offsets;
+  // references (validate_self)
+  const u64* refseq;
+  const u64* ref_prefix;
+  u64 n_refs;
+};
+
+}  // namespace mazu

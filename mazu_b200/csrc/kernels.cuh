@@ -1,0 +1,687 @@
+// CUDA kernels of the batched k-mer query path (sm_100a).
+//
+//  K1  encode / roll canonical k-mers / minimizers            (warp per read; ballot + redux + smem)
+//  K2  random-access lookup: MPHF -> bucket bounds -> positions -> k-mer verify -> unitig bounds
+//  K3  streaming walk (.as_streaming()), one warp per read, speculate-then-commit
+//  K4  occurrence decode (+ projection)
+//  plus the GPU validate drivers and the random-gather roofline probe.
+//
+// None of this is GEMM-shaped: no tensor cores.  The bound is L2/HBM sector traffic and
+// dependent-load latency, so the kernels are organised around (a) one aligned 32-byte block per
+// dependent step (index_layout.hpp) and (b) keeping consecutive k-mers of a read in adjacent
+// lanes, which makes lanes that share a minimizer issue identical addresses (the LSU merges them).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "index_layout.hpp"
+
+namespace mazu {
+
+struct __align__(16) Hit {
+  u32 unitig_id, unitig_len, pos, match;
+};
+struct OccRec {
+  u32 ref_id, pos, fw;
+};
+
+__device__ __forceinline__ Hit hit_none(u32 match) { return Hit{~0u, ~0u, ~0u, match}; }
+__device__ __forceinline__ void store_hit(Hit* out, const Hit& h) {
+  *reinterpret_cast<uint4*>(out) = make_uint4(h.unitig_id, h.unitig_len, h.pos, h.match);
+}
+
+// kmers::CanonicalKmer::get_word_equivalency
+__device__ __forceinline__ u32 word_equivalency(u64 fw, u64 rc, u64 kw) {
+  return kw == fw ? (u32)IDENTITY_MATCH : (kw == rc ? (u32)TWIN_MATCH : (u32)NO_MATCH);
+}
+
+// K2UPos from a verified useq position: pos_to_id, unitig_len, unitig_start_pos (+ the boundary
+// guard of src/kphf/sshash.rs:513-514,539-541 when `guard` is set)
+__device__ __forceinline__ bool finish_hit(const UnitigsView& u, u64 km_pos, u32 mt, bool guard, Hit& out) {
+  u64 id, start, end;
+  unitig_locate(u, km_pos, id, start, end);
+  if (guard && km_pos + u.k > end) return false;
+  out.unitig_id = (u32)id;
+  out.unitig_len = (u32)(end - start);
+  out.pos = (u32)(km_pos - start);
+  out.match = mt;
+  return true;
+}
+
+// PFHash::k2u (src/kphf/pfhash.rs:108-134)
+__device__ __forceinline__ bool pfhash_k2u(const IndexView& ix, u64 fw, u64 rc, Hit& out) {
+  u64 word = fw <= rc ? fw : rc;
+  u64 h;
+  if (!mphf_lookup(ix.mphf, word, h)) return false;
+  if (h >= ix.pos.len) return false;
+  u64 km_pos = packed_get(ix.pos, h);
+  u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, km_pos));
+  if (mt == NO_MATCH) return false;
+  return finish_hit(ix.unitigs, km_pos, mt, false, out);
+}
+
+// SSHash::k2u (src/kphf/sshash.rs:471-555) given the canonical minimizer (word, offset in fw-mer coordinates)
+__device__ __forceinline__ bool sshash_k2u(const IndexView& ix, u64 fw, u64 rc, u64 mm_word, u32 offset, Hit& out) {
+  u64 h;
+  if (!mphf_lookup(ix.mphf, mm_word, h)) return false;
+  if (h + 1 >= ix.sizes.n) return false;
+  u64 pos_start, pos_end;
+  blocked_ef_get2(ix.sizes, h, pos_start, pos_end);  // occs_prefix_sum.get(h), get(h+1)
+  if (pos_end - pos_start > ix.skew_param) {         // k2u_skew_index (sshash.rs:415-433)
+    if (!ix.has_skew) return false;
+    u64 word = fw <= rc ? fw : rc, hs;
+    if (!mphf_lookup(ix.skew_mphf, word, hs)) return false;
+    if (hs >= ix.skew_pos.len) return false;
+    u64 p = packed_get(ix.skew_pos, hs);
+    u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, p));
+    if (mt == NO_MATCH) return false;
+    return finish_hit(ix.unitigs, p, mt, false, out);
+  }
+  const u32 k = ix.unitigs.k;
+  const u64 last_km_start_pos = ix.unitigs.total_len - k;
+  const u64 rc_offset = (u64)(k - offset - ix.w);
+  for (u64 pi = pos_start; pi < pos_end; ++pi) {
+    u64 mm_pos = packed_get(ix.pos, pi);
+    if (mm_pos >= offset && mm_pos - offset <= last_km_start_pos) {  // sshash.rs:498
+      u64 km_pos = mm_pos - offset;
+      u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, km_pos));
+      if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out)) return true;
+    }
+    if (mm_pos >= rc_offset && mm_pos - rc_offset <= last_km_start_pos) {  // sshash.rs:527
+      u64 km_pos = mm_pos - rc_offset;
+      u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, km_pos));
+      if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out)) return true;
+    }
+  }
+  return false;
+}
+
+__device__ __forceinline__ bool k2u_any(const IndexView& ix, u64 fw, u64 rc, Hit& out) {
+  if (ix.k2u_kind == MAZU_K2U_PFHASH) return pfhash_k2u(ix, fw, rc, out);
+  MinimizerResult m = canonical_minimizer_naive(fw, rc, ix.unitigs.k, ix.w, ix.seed);
+  return sshash_k2u(ix, fw, rc, m.word, m.offset, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 on a flat batch of k-mer words: K2U::k2u per element (random order, no read context)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k2u_batch_kernel(const __grid_constant__ IndexView ix, const u64* __restrict__ fw_words, u64 n,
+                                                        Hit* __restrict__ out) {
+  const u32 k = ix.unitigs.k;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    u64 fw = fw_words[i] & kmer_mask(k);
+    u64 rc = revcomp(fw, k);
+    Hit h;
+    if (!k2u_any(ix, fw, rc, h)) h = hit_none(NO_MATCH);
+    store_hit(out + i, h);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Read chunk staging shared by K1 / K2-on-reads / K3.  A warp owns one read and walks it in
+// chunks of CHUNK k-mer start positions.
+// ---------------------------------------------------------------------------------------------
+static const int QR_WARPS = 8;         // warps per CTA
+static const int QR_CHUNK = 128;       // k-mer start positions per chunk
+static const int QR_BASES = 160;       // bases staged per chunk (CHUNK + k - 1 <= 159)
+static const int QR_WORDS = 6;         // 5 words of 32 bases + 1 zero pad
+
+struct ChunkRegs {
+  u64 w[QR_WORDS];  // 2-bit packed bases of the chunk; word t holds chunk bases [32t, 32t+32)
+  u32 inv[QR_WORDS];  // bit j of inv[t]: base 32t+j is not ACGT or lies beyond the read
+};
+
+// 2-bit encode 160 bases starting at seq[c0]: coalesced byte loads, one warp-wide OR-reduction per
+// 32-base word (redux.sync), invalid-base masks by ballot.
+__device__ __forceinline__ void load_chunk(const u8* __restrict__ seq, u64 len, u64 c0, u32 lane, ChunkRegs& c) {
+#pragma unroll
+  for (int t = 0; t < 5; ++t) {
+    u64 q = c0 + 32u * t + lane;
+    u32 code = 4;
+    if (q < len) code = base_code(seq[q]);
+    bool bad = code > 3;
+    c.inv[t] = __ballot_sync(0xffffffffu, bad);
+    u32 v = bad ? 0u : code;
+    u32 lo = __reduce_or_sync(0xffffffffu, lane < 16 ? (v << (2 * lane)) : 0u);
+    u32 hi = __reduce_or_sync(0xffffffffu, lane >= 16 ? (v << (2 * (lane - 16))) : 0u);
+    c.w[t] = ((u64)hi << 32) | lo;
+  }
+  c.w[5] = 0;
+  c.inv[5] = 0xffffffffu;
+}
+// 2-bit window of `nb` bases starting at chunk position 32*t + lane
+__device__ __forceinline__ u64 chunk_window(const ChunkRegs& c, int t, u32 lane, u32 nb) {
+  u32 sh = 2 * lane;
+  u64 x = c.w[t] >> sh;
+  if (sh) x |= c.w[t + 1] << (64 - sh);
+  return x & kmer_mask(nb);
+}
+__device__ __forceinline__ bool chunk_window_valid(const ChunkRegs& c, int t, u32 lane, u32 nb) {
+  u64 m = ((u64)c.inv[t] | ((u64)c.inv[t + 1] << 32)) >> lane;
+  return (m & ((1ULL << nb) - 1ULL)) == 0ULL;  // nb <= 32
+}
+
+// minimizer of the k-mer starting at chunk position p from the per-chunk w-mer hash arrays
+// (argmin over the CANONICAL k-mer's w-mers, leftmost wins; offset in fw-mer coordinates)
+__device__ __forceinline__ void chunk_minimizer(const u64* __restrict__ hf, const u64* __restrict__ hr, u32 p, u64 fw, u64 rc,
+                                                u32 k, u32 w, u64& mm_word, u32& offset) {
+  const bool fw_canon = fw <= rc;
+  const u32 span = k - w;
+  const u64* h = fw_canon ? hf + p : hr + p + span;
+  const int step = fw_canon ? 1 : -1;
+  u64 best = h[0];
+  u32 bi = 0;
+  for (u32 ci = 1; ci <= span; ++ci) {
+    u64 v = h[(int)ci * step];
+    if (v < best) {
+      best = v;
+      bi = ci;
+    }
+  }
+  mm_word = ((fw_canon ? fw : rc) >> (2 * bi)) & kmer_mask(w);
+  offset = fw_canon ? bi : span - bi;
+}
+
+struct StreamState {  // StreamingK2U { is_warm, prev_k2upos } (src/index/caching.rs:13-17)
+  u32 warm, uid, ulen, pos, o;
+  u64 ustart;
+};
+
+// One kernel for the read loop of `kphf bench` / validate_ckmers, both modes.
+//   MODE 0: K2U::k2u per k-mer.  MODE 1: StreamingK2U::k2u_streaming with the cursor reset per read.
+template <int MODE>
+__global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
+                                                                    const u64* __restrict__ read_offsets, u64 n_reads, u64 uniform_len,
+                                                                    const u64* __restrict__ kmer_offsets, Hit* __restrict__ out,
+                                                                    unsigned long long* __restrict__ counts) {
+  __shared__ u64 s_hf[QR_WARPS][QR_BASES];
+  __shared__ u64 s_hr[QR_WARPS][QR_BASES];
+  __shared__ u64 s_fw[MODE == 1 ? QR_WARPS : 1][MODE == 1 ? QR_CHUNK : 1];
+  const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const u32 k = ix.unitigs.k, w = ix.w;
+  const bool ss = ix.k2u_kind == MAZU_K2U_SSHASH;
+  u64* hf = s_hf[wib];
+  u64* hr = s_hr[wib];
+  u32 n_valid = 0, n_hit = 0;
+  const u32 lt_mask = (1u << lane) - 1u;
+
+  for (u64 r = (u64)blockIdx.x * QR_WARPS + wib; r < n_reads; r += (u64)gridDim.x * QR_WARPS) {
+    u64 beg, len, slot0;
+    if (uniform_len) {
+      beg = r * uniform_len;
+      len = uniform_len;
+      slot0 = uniform_len >= k ? r * (uniform_len - k + 1) : 0;
+    } else {
+      beg = read_offsets[r];
+      len = read_offsets[r + 1] - beg;
+      slot0 = kmer_offsets[r];
+    }
+    const u8* seq = bases + beg;
+    const u64 nk = len >= k ? len - k + 1 : 0;
+    StreamState st;
+    st.warm = 0;
+    st.uid = st.ulen = st.pos = ~0u;
+    st.o = NO_MATCH;
+    st.ustart = 0;
+
+    for (u64 c0 = 0; c0 < nk; c0 += QR_CHUNK) {
+      ChunkRegs c;
+      load_chunk(seq, len, c0, lane, c);
+      const u32 n_c = (u32)min((u64)QR_CHUNK, nk - c0);
+      if (ss) {
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+          u64 wf = chunk_window(c, t, lane, w);
+          hf[32 * t + lane] = mm_hash64(wf, ix.seed);
+          hr[32 * t + lane] = mm_hash64(revcomp(wf, w), ix.seed);
+        }
+        __syncwarp();
+      }
+      if (MODE == 0) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          u32 p = 32 * t + lane;
+          if (p < n_c) {
+            Hit h = hit_none(SKIPPED);
+            if (chunk_window_valid(c, t, lane, k)) {
+              u64 fw = chunk_window(c, t, lane, k);
+              u64 rc = revcomp(fw, k);
+              bool ok;
+              if (ss) {
+                u64 mmw;
+                u32 off;
+                chunk_minimizer(hf, hr, p, fw, rc, k, w, mmw, off);
+                ok = sshash_k2u(ix, fw, rc, mmw, off, h);
+              } else {
+                ok = pfhash_k2u(ix, fw, rc, h);
+              }
+              ++n_valid;
+              if (ok) ++n_hit; else h = hit_none(NO_MATCH);
+            }
+            if (out) store_hit(out + slot0 + c0 + p, h);
+          }
+        }
+      } else {
+        // ---- K3: stage fw words (0 marks nothing: validity is kept in a per-lane bitmask) ----
+        u32 vbits = 0;  // bit t: k-mer 32t+lane is a valid window
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          s_fw[wib][32 * t + lane] = chunk_window(c, t, lane, k);
+          if (32u * t + lane < n_c && chunk_window_valid(c, t, lane, k)) vbits |= 1u << t;
+        }
+        __syncwarp();
+        u32 vm[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) vm[t] = __ballot_sync(0xffffffffu, (vbits >> t) & 1u);
+        u32 i = 0;
+        while (i < n_c) {
+          const u32 q = i + lane;
+          const bool active = q < n_c;
+          bool valid = false;
+          u64 fw = 0, rc = 0;
+          if (active) {
+            u32 word = q >> 5;
+            u32 m = word == 0 ? vm[0] : word == 1 ? vm[1] : word == 2 ? vm[2] : vm[3];
+            valid = (m >> (q & 31)) & 1u;
+            fw = s_fw[wib][q];
+            rc = revcomp(fw, k);
+          }
+          const u32 vmask = __ballot_sync(0xffffffffu, valid);
+          const u32 amask = __ballot_sync(0xffffffffu, active);
+          const u32 rnk = __popc(vmask & lt_mask);
+          if (st.warm) {
+            // Phase W: extend along the current unitig (k2u_warm, caching.rs:73-97), 32 k-mers at once
+            u32 np = st.pos + 1 + rnk;
+            u32 m = NO_MATCH;
+            if (valid && (u64)np + k <= (u64)st.ulen) m = word_equivalency(fw, rc, useq_window(ix.unitigs, st.ustart + np));
+            const bool okw = active && (!valid || m != NO_MATCH);
+            const u32 bad = __ballot_sync(0xffffffffu, !okw);
+            const u32 run = bad ? (u32)(__ffs(bad) - 1) : 32u;
+            if (run > 0) {
+              if (lane < run) {
+                Hit h = hit_none(SKIPPED);
+                if (valid) {
+                  h = Hit{st.uid, st.ulen, np, m};
+                  ++n_valid;
+                  ++n_hit;
+                }
+                if (out) store_hit(out + slot0 + c0 + q, h);
+              }
+              const u32 run_mask = run >= 32 ? 0xffffffffu : ((1u << run) - 1u);
+              const u32 vr = vmask & run_mask;
+              if (vr) {
+                int last = 31 - __clz(vr);
+                st.pos += __popc(vr);
+                st.o = __shfl_sync(0xffffffffu, m, last);
+              }
+              i += run;
+              continue;
+            }
+          }
+          // Phase C: cold lookups for all 32 lanes, then commit in read order (k2u_cold, caching.rs:99-103)
+          Hit res = hit_none(NO_MATCH);
+          bool hit = false;
+          if (valid) {
+            if (st.warm && lane > 0 && (u64)st.pos + 1 + k <= (u64)st.ulen) {
+              // same cursor as lane 0 saw (earlier lanes are assumed misses): warm check against pos+1
+              u32 m = word_equivalency(fw, rc, useq_window(ix.unitigs, st.ustart + st.pos + 1));
+              if (m != NO_MATCH) {
+                res = Hit{st.uid, st.ulen, st.pos + 1, m};
+                hit = true;
+              }
+            }
+          }
+          Hit cold = hit_none(NO_MATCH);
+          bool cold_hit = false;
+          if (valid) {
+            if (ss) {
+              u64 mmw;
+              u32 off;
+              chunk_minimizer(hf, hr, q, fw, rc, k, w, mmw, off);
+              cold_hit = sshash_k2u(ix, fw, rc, mmw, off, cold);
+            } else {
+              cold_hit = pfhash_k2u(ix, fw, rc, cold);
+            }
+            if (!cold_hit) cold = hit_none(NO_MATCH);
+            if (!hit && cold_hit) {
+              res = cold;
+              hit = true;
+            }
+          }
+          const u32 hitmask = __ballot_sync(0xffffffffu, hit);
+          if (hitmask == 0) {
+            if (active) {
+              if (valid) ++n_valid;
+              if (out) store_hit(out + slot0 + c0 + q, hit_none(valid ? (u32)NO_MATCH : (u32)SKIPPED));
+            }
+            i += 32;
+            continue;
+          }
+          const u32 f = (u32)(__ffs(hitmask) - 1);
+          const u32 uid_f = __shfl_sync(0xffffffffu, res.unitig_id, f);
+          const u32 pos_f = __shfl_sync(0xffffffffu, res.pos, f);
+          // lanes after f commit their cold result iff it is exactly the warm extension of the cursor
+          const u32 after = ~((2u << f) - 1u);  // lanes > f   (f == 31 -> 0)
+          const u32 r2 = __popc(vmask & lt_mask & after);
+          const bool ok_ext = lane > f && active && (!valid || (cold_hit && cold.unitig_id == uid_f && cold.pos == pos_f + 1 + r2));
+          u32 bad = __ballot_sync(0xffffffffu, lane > f && !ok_ext);
+          const u32 g = bad ? (u32)(__ffs(bad) - 1) : 32u;  // first lane not committed
+          if (lane < g && active) {
+            Hit h;
+            if (!valid) h = hit_none(SKIPPED);
+            else {
+              ++n_valid;
+              if (lane < f) h = hit_none(NO_MATCH);
+              else {
+                h = lane == f ? res : cold;
+                ++n_hit;
+              }
+            }
+            if (out) store_hit(out + slot0 + c0 + q, h);
+          }
+          {
+            const u32 gm = g >= 32 ? 0xffffffffu : ((1u << g) - 1u);
+            const u32 committed_valid = vmask & gm & ~((1u << f) - 1u);  // valid lanes in [f, g)
+            const int last = 31 - __clz(committed_valid);
+            Hit src = (u32)last == f ? res : cold;
+            st.uid = __shfl_sync(0xffffffffu, src.unitig_id, last);
+            st.ulen = __shfl_sync(0xffffffffu, src.unitig_len, last);
+            st.pos = __shfl_sync(0xffffffffu, src.pos, last);
+            st.o = __shfl_sync(0xffffffffu, src.match, last);
+            st.warm = 1;
+            st.ustart = __ldg(ix.unitigs.starts + st.uid);  // uniform address: one broadcast load
+          }
+          (void)amask;
+          i += g;
+        }
+      }
+    }
+  }
+  // counters of src/bin/kphf/main.rs:282-284
+  if (counts) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
+      n_hit += __shfl_xor_sync(0xffffffffu, n_hit, o);
+    }
+    if (lane == 0 && n_valid) {
+      atomicAdd(counts + 0, (unsigned long long)n_valid);
+      atomicAdd(counts + 1, (unsigned long long)n_hit);
+      atomicAdd(counts + 2, (unsigned long long)(n_valid - n_hit));
+    }
+  }
+}
+
+// K1 alone: per k-mer slot fw / rc / minimizer word / minimizer offset / valid
+__global__ void __launch_bounds__(QR_WARPS * 32) encode_reads_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
+                                                                     const u64* __restrict__ read_offsets, u64 n_reads, u64 uniform_len,
+                                                                     const u64* __restrict__ kmer_offsets, u64* __restrict__ out_fw,
+                                                                     u64* __restrict__ out_rc, u64* __restrict__ out_mm, u32* __restrict__ out_off,
+                                                                     u8* __restrict__ out_valid) {
+  __shared__ u64 s_hf[QR_WARPS][QR_BASES];
+  __shared__ u64 s_hr[QR_WARPS][QR_BASES];
+  const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const u32 k = ix.unitigs.k, w = ix.w;
+  const bool ss = ix.k2u_kind == MAZU_K2U_SSHASH;
+  u64* hf = s_hf[wib];
+  u64* hr = s_hr[wib];
+  for (u64 r = (u64)blockIdx.x * QR_WARPS + wib; r < n_reads; r += (u64)gridDim.x * QR_WARPS) {
+    u64 beg, len, slot0;
+    if (uniform_len) {
+      beg = r * uniform_len;
+      len = uniform_len;
+      slot0 = uniform_len >= k ? r * (uniform_len - k + 1) : 0;
+    } else {
+      beg = read_offsets[r];
+      len = read_offsets[r + 1] - beg;
+      slot0 = kmer_offsets[r];
+    }
+    const u8* seq = bases + beg;
+    const u64 nk = len >= k ? len - k + 1 : 0;
+    for (u64 c0 = 0; c0 < nk; c0 += QR_CHUNK) {
+      ChunkRegs c;
+      load_chunk(seq, len, c0, lane, c);
+      const u32 n_c = (u32)min((u64)QR_CHUNK, nk - c0);
+      if (ss) {
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+          u64 wf = chunk_window(c, t, lane, w);
+          hf[32 * t + lane] = mm_hash64(wf, ix.seed);
+          hr[32 * t + lane] = mm_hash64(revcomp(wf, w), ix.seed);
+        }
+        __syncwarp();
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        u32 p = 32 * t + lane;
+        if (p < n_c) {
+          u64 fw = 0, rc = 0, mmw = 0;
+          u32 off = 0;
+          bool valid = chunk_window_valid(c, t, lane, k);
+          if (valid) {
+            fw = chunk_window(c, t, lane, k);
+            rc = revcomp(fw, k);
+            if (ss) chunk_minimizer(hf, hr, p, fw, rc, k, w, mmw, off);
+          }
+          u64 s = slot0 + c0 + p;
+          if (out_fw) out_fw[s] = fw;
+          if (out_rc) out_rc[s] = rc;
+          if (out_mm) out_mm[s] = mmw;
+          if (out_off) out_off[s] = off;
+          if (out_valid) out_valid[s] = valid ? 1 : 0;
+        }
+      }
+    }
+  }
+}
+
+// per-read k-mer slot counts (input of the exclusive scan that yields kmer_offsets)
+__global__ void kmer_counts_kernel(const u64* __restrict__ read_offsets, u64 n_reads, u32 k, u64* __restrict__ counts) {
+  for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (u64)gridDim.x * blockDim.x) {
+    u64 len = read_offsets[r + 1] - read_offsets[r];
+    counts[r] = len >= k ? len - k + 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: U2Pos decode / projection
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void occ_range(const IndexView& ix, u32 uid, u64& s, u64& e) {
+  s = packed_get(ix.contig_offsets, uid);  // dense_unitig_table.rs:58-63 / :130-135
+  e = packed_get(ix.contig_offsets, (u64)uid + 1);
+}
+__device__ __forceinline__ OccRec occ_decode(const IndexView& ix, u64 i) {
+  OccRec o;
+  if (ix.u2pos_kind == MAZU_U2POS_DENSE) {  // UnitigOcc::decode_pf1 (index.rs:335-346)
+    u64 word = __ldg(ix.ctable_words + i);
+    o.ref_id = (u32)(word & 0xFFFFFFFFULL);
+    u64 pw = word >> 32;
+    o.pos = (u32)(pw & 0x7FFFFFFFULL);
+    o.fw = (pw & 0x80000000ULL) ? 1u : 0u;
+  } else {  // UnitigOcc::decode_piscem (spt_compact.rs:99-110)
+    PackedVecView v{ix.ctable_words, ix.n_occs, ix.ctable_width, 0};
+    u64 enc = packed_get(v, i);
+    o.ref_id = (u32)(enc >> ix.ref_shift);
+    o.pos = (u32)((enc >> 1) & ix.pos_mask);
+    o.fw = (u32)(enc & 1ULL);
+  }
+  return o;
+}
+// project_onto_u_occ (index.rs:194-216)
+__device__ __forceinline__ OccRec project_occ(u32 k, const Hit& h, const OccRec& occ) {
+  OccRec m;
+  m.ref_id = occ.ref_id;
+  m.pos = occ.fw ? h.pos + occ.pos : occ.pos + (h.unitig_len - h.pos) - k;
+  u32 o = h.match == IDENTITY_MATCH ? 1u : 0u;
+  m.fw = occ.fw ? o : (o ^ 1u);
+  return m;
+}
+
+// list lengths: from unitig ids (hits == nullptr) or from hit records
+__global__ void occ_lens_kernel(const __grid_constant__ IndexView ix, const u32* __restrict__ uids, const Hit* __restrict__ hits, u64 n,
+                                u64* __restrict__ lens) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    u32 uid;
+    if (hits) {
+      Hit h = hits[i];
+      uid = (h.match == IDENTITY_MATCH || h.match == TWIN_MATCH) ? h.unitig_id : ~0u;
+    } else {
+      uid = uids[i];
+    }
+    u64 len = 0;
+    if (uid != ~0u) {
+      u64 s, e;
+      occ_range(ix, uid, s, e);
+      len = e - s;
+    }
+    lens[i] = len;
+  }
+}
+// fill: a warp takes 32 queries; short lists are written by their own lane, long lists by the whole warp
+template <bool PROJECT>
+__global__ void __launch_bounds__(256) occ_fill_kernel(const __grid_constant__ IndexView ix, const u32* __restrict__ uids,
+                                                       const Hit* __restrict__ hits, u64 n, const u64* __restrict__ out_offsets,
+                                                       OccRec* __restrict__ out) {
+  const u32 lane = threadIdx.x & 31;
+  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  const u32 k = ix.unitigs.k;
+  for (u64 base = warp * 32; base < n; base += n_warps * 32) {
+    u64 i = base + lane;
+    u64 s = 0, len = 0, o0 = 0;
+    Hit h = hit_none(NO_MATCH);
+    if (i < n) {
+      u32 uid;
+      if (PROJECT) {
+        h = hits[i];
+        uid = (h.match == IDENTITY_MATCH || h.match == TWIN_MATCH) ? h.unitig_id : ~0u;
+      } else {
+        uid = uids[i];
+      }
+      if (uid != ~0u) {
+        u64 e;
+        occ_range(ix, uid, s, e);
+        len = e - s;
+        o0 = out_offsets[i];
+      }
+    }
+    const bool is_long = len > 4;
+    if (!is_long) {
+      for (u64 j = 0; j < len; ++j) {
+        OccRec o = occ_decode(ix, s + j);
+        if (PROJECT) o = project_occ(k, h, o);
+        out[o0 + j] = o;
+      }
+    }
+    u32 longmask = __ballot_sync(0xffffffffu, is_long);
+    while (longmask) {
+      int src = __ffs(longmask) - 1;
+      longmask &= longmask - 1;
+      u64 ls = __shfl_sync(0xffffffffu, s, src), ll = __shfl_sync(0xffffffffu, len, src), lo = __shfl_sync(0xffffffffu, o0, src);
+      Hit lh;
+      lh.unitig_id = __shfl_sync(0xffffffffu, h.unitig_id, src);
+      lh.unitig_len = __shfl_sync(0xffffffffu, h.unitig_len, src);
+      lh.pos = __shfl_sync(0xffffffffu, h.pos, src);
+      lh.match = __shfl_sync(0xffffffffu, h.match, src);
+      for (u64 j = lane; j < ll; j += 32) {
+        OccRec o = occ_decode(ix, ls + j);
+        if (PROJECT) o = project_occ(k, lh, o);
+        out[lo + j] = o;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GPU validate drivers.  counts = {n_queries, n_identity, n_twin, n_projected, n_fail}
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 packed2_window(const u64* __restrict__ words, u64 pos, u32 k) {
+  u64 bit = 2 * pos, wi = bit >> 6;
+  u32 sh = (u32)(bit & 63);
+  u64 x = __ldg(words + wi) >> sh;
+  if (sh + 2 * k > 64) x |= __ldg(words + wi + 1) << (64 - sh);
+  return x & kmer_mask(k);
+}
+__device__ __forceinline__ void block_accumulate(unsigned long long* counts, u32 v[5]) {
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    u32 x = v[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(counts + j, (unsigned long long)x);
+  }
+}
+// Validate::validate_self (src/index/validate.rs:24-52): thread per reference position
+__global__ void __launch_bounds__(256) validate_self_kernel(const __grid_constant__ IndexView ix, unsigned long long* counts) {
+  const u32 k = ix.unitigs.k;
+  const u64 total = ix.ref_prefix[ix.n_refs];
+  u32 v[5] = {0, 0, 0, 0, 0};
+  for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (u64)gridDim.x * blockDim.x) {
+    // reference containing p (few references: binary search)
+    u64 lo = 0, hi = ix.n_refs;
+    while (hi - lo > 1) {
+      u64 mid = (lo + hi) >> 1;
+      if (ix.ref_prefix[mid] <= p) lo = mid; else hi = mid;
+    }
+    u64 rs = ix.ref_prefix[lo], re = ix.ref_prefix[lo + 1];
+    if (p + k > re) continue;
+    u64 fw = packed2_window(ix.refseq, p, k), rc = revcomp(fw, k);
+    Hit h;
+    ++v[0];
+    if (!k2u_any(ix, fw, rc, h)) {
+      ++v[4];
+      continue;
+    }
+    ++v[h.match == IDENTITY_MATCH ? 1 : 2];
+    u64 s, e;
+    occ_range(ix, h.unitig_id, s, e);
+    bool found = false;
+    for (u64 j = s; j < e; ++j) {
+      OccRec m = project_occ(k, h, occ_decode(ix, j));
+      found |= (m.pos == (u32)(p - rs)) && (m.ref_id == (u32)lo);
+    }
+    v[3] += (u32)(e - s);
+    if (!found) ++v[4];
+  }
+  block_accumulate(counts, v);
+}
+// K2U::validate_self (src/kphf/mod.rs:69-103): thread per useq position, fw then swapped
+__global__ void __launch_bounds__(256) k2u_validate_self_kernel(const __grid_constant__ IndexView ix, unsigned long long* counts) {
+  const u32 k = ix.unitigs.k;
+  const u64 total = ix.unitigs.total_len;
+  u32 v[5] = {0, 0, 0, 0, 0};
+  for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p + k <= total; p += (u64)gridDim.x * blockDim.x) {
+    u64 id, s, e;
+    unitig_locate(ix.unitigs, p, id, s, e);
+    if (p + k > e) continue;  // window straddles a unitig boundary: not a k-mer of the set
+    u64 fw = useq_window(ix.unitigs, p), rc = revcomp(fw, k);
+    for (int t = 0; t < 2; ++t) {
+      Hit h;
+      ++v[0];
+      u32 want = t == 0 ? IDENTITY_MATCH : TWIN_MATCH;
+      bool ok = t == 0 ? k2u_any(ix, fw, rc, h) : k2u_any(ix, rc, fw, h);
+      if (!ok || h.unitig_id != (u32)id || h.unitig_len != (u32)(e - s) || h.pos != (u32)(p - s) || h.match != want) ++v[4];
+      else ++v[t == 0 ? 1 : 2];
+    }
+  }
+  block_accumulate(counts, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Roofline probe: independent random 32-byte gathers (one aligned uint4 pair per thread step)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) random_gather_kernel(const uint4* __restrict__ table, u64 n_sectors, u64 n_gathers, u64 seed,
+                                                            unsigned long long* __restrict__ sink) {
+  u64 acc = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_gathers; i += (u64)gridDim.x * blockDim.x) {
+    u64 h = fmix64(i * 0x9E3779B97F4A7C15ULL + seed);
+    u64 s = mulhi64(h, n_sectors);
+    uint4 a = __ldg(table + 2 * s);
+    acc += a.x + a.w;
+  }
+  if (acc == 0x1234567887654321ULL) atomicAdd(sink, 1ULL);
+}
+
+}  // namespace mazu

@@ -1,0 +1,124 @@
+// 2-bit k-mer arithmetic shared by host builders and device kernels.
+//
+// Encoding (the `kmers` crate the reference builds on): A=0 C=1 G=2 T=3,
+// base i of a k-mer at bits [2i, 2i+2) of a u64, canonical form = min(fw, rc) as integers.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define MZ_HD __host__ __device__ __forceinline__
+#else
+#define MZ_HD inline
+#endif
+
+namespace mazu {
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef uint8_t u8;
+
+enum : u32 { NO_MATCH = 0, IDENTITY_MATCH = 1, TWIN_MATCH = 2, SKIPPED = 3 };
+
+MZ_HD u64 kmer_mask(u32 k) { return k >= 32 ? ~0ULL : ((1ULL << (2 * k)) - 1ULL); }
+
+// ASCII -> 2-bit code, or 4 for anything that is not ACGTacgt
+MZ_HD u32 base_code(u32 c) {
+  c &= 0xDFu;  // fold case
+  u32 code = (c >> 1) & 3u;  // A(0x41)->0  C(0x43)->1  G(0x47)->3  T(0x54)->2
+  code ^= code >> 1;         // swap 2<->3 : A0 C1 G2 T3
+  bool ok = (c == 'A') | (c == 'C') | (c == 'G') | (c == 'T');
+  return ok ? code : 4u;
+}
+
+// reverse complement of the low 2k bits
+MZ_HD u64 revcomp(u64 x, u32 k) {
+  x = ~x;  // complement: 3 - b
+#if defined(__CUDA_ARCH__)
+  x = __brevll(x);
+#else
+  x = ((x >> 32) | (x << 32));
+  x = ((x & 0xFFFF0000FFFF0000ULL) >> 16) | ((x & 0x0000FFFF0000FFFFULL) << 16);
+  x = ((x & 0xFF00FF00FF00FF00ULL) >> 8) | ((x & 0x00FF00FF00FF00FFULL) << 8);
+  x = ((x & 0xF0F0F0F0F0F0F0F0ULL) >> 4) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+  x = ((x & 0xCCCCCCCCCCCCCCCCULL) >> 2) | ((x & 0x3333333333333333ULL) << 2);
+  x = ((x & 0xAAAAAAAAAAAAAAAAULL) >> 1) | ((x & 0x5555555555555555ULL) << 1);
+#endif
+  // full bit reversal also reversed the two bits inside each base: swap them back
+  x = ((x & 0xAAAAAAAAAAAAAAAAULL) >> 1) | ((x & 0x5555555555555555ULL) << 1);
+  return k >= 32 ? x : (x >> (64 - 2 * k));
+}
+
+MZ_HD u64 mulhi64(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b);
+#else
+  return (u64)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+MZ_HD u64 mum64(u64 a, u64 b) { return (a * b) ^ mulhi64(a, b); }
+
+// Minimizer order (DESIGN.md "Minimizer order v1"): a WyHash-v1-style mum mixer of the w-mer word.
+// Stands in for kmers::canonical_minimizer + wyhash 0.5.0 (not in the reference tree, parity
+// unpinned); k-mer->unitig results do not depend on it.
+MZ_HD u64 mm_hash64(u64 x, u64 seed) {
+  const u64 P0 = 0xa0761d6478bd642fULL, P1 = 0xe7037ed1a0b428dbULL, P4 = 0x1d8e4e27c47d124fULL;
+  u64 a = (x & 0xffffffffULL) ^ seed ^ P0;
+  u64 b = (x >> 32) ^ seed ^ P1;
+  return mum64(mum64(a, b), 8ULL ^ P4);
+}
+
+// murmur3 finaliser: the per-level hash of the native MPHF ("kphf" tables)
+MZ_HD u64 fmix64(u64 x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+
+// pufferfish BooPHF hashing (src/pf1/boophf/hash.rs:33-49,111-135)
+MZ_HD u64 boophf_hash64(u64 key, u64 seed) {
+  u64 hash = seed;
+  hash ^= (hash << 7) ^ (key * (hash >> 3)) ^ (~((hash << 11) + (key ^ (hash >> 5))));
+  hash = (~hash) + (hash << 21);
+  hash = hash ^ (hash >> 24);
+  hash = (hash + (hash << 3)) + (hash << 8);
+  hash = hash ^ (hash >> 14);
+  hash = (hash + (hash << 2)) + (hash << 4);
+  hash = hash ^ (hash >> 28);
+  hash = hash + (hash << 31);
+  return hash;
+}
+static const u64 BOOPHF_SEED0 = 0xAAAAAAAA55555555ULL;
+static const u64 BOOPHF_SEED1 = 0x33333333CCCCCCCCULL;
+
+// minimizer of a k-mer given as fw/rc words: argmin over the canonical k-mer's w-mers, leftmost
+// wins; `offset` is reported in the coordinates of the fw k-mer (sshash.rs:563-624 pins this).
+struct MinimizerResult {
+  u64 word;
+  u32 offset;
+};
+MZ_HD MinimizerResult canonical_minimizer_naive(u64 fw, u64 rc, u32 k, u32 w, u64 seed) {
+  bool fw_canon = fw <= rc;
+  u64 c = fw_canon ? fw : rc;
+  u64 wmask = kmer_mask(w);
+  u64 best_h = ~0ULL;
+  u64 best_w = 0;
+  u32 best_i = 0;
+  for (u32 i = 0; i + w <= k; ++i) {
+    u64 wm = (c >> (2 * i)) & wmask;
+    u64 h = mm_hash64(wm, seed);
+    if (i == 0 || h < best_h) {
+      best_h = h;
+      best_w = wm;
+      best_i = i;
+    }
+  }
+  MinimizerResult r;
+  r.word = best_w;
+  r.offset = fw_canon ? best_i : (k - best_i - w);
+  return r;
+}
+
+}  // namespace mazu

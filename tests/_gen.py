@@ -1,0 +1,91 @@
+"""Synthetic inputs shared by tests and bench.py (numpy only)."""
+import numpy as np
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+COMP = np.array([3, 2, 1, 0], dtype=np.uint8)
+
+
+def unpack_2bit(words, n):
+    """uint64 words (base i at bits [2i,2i+2)) -> uint8 codes[n]."""
+    words = np.asarray(words, dtype=np.uint64)
+    shifts = (np.arange(32, dtype=np.uint64) * np.uint64(2))
+    codes = ((words[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8).reshape(-1)
+    return codes[:n]
+
+
+def kmer_words_from_codes(codes, k):
+    """all k-mer words of a code sequence (vectorised): word[p] = sum codes[p+i] << 2i."""
+    n = len(codes) - k + 1
+    if n <= 0:
+        return np.zeros(0, dtype=np.uint64)
+    w = np.zeros(n, dtype=np.uint64)
+    c = codes.astype(np.uint64)
+    for i in range(k):
+        w |= c[i:i + n] << np.uint64(2 * i)
+    return w
+
+
+def sample_reads(ref_codes, n_reads, read_len, seed, frac_ref=0.5, sub_rate=0.0, n_rate=0.0, ragged=False):
+    """Reads as ASCII bytes + offsets.  A fraction frac_ref is sampled from ref_codes at a uniform
+    start on a random strand (with i.i.d. substitutions at sub_rate), the rest is uniform random ACGT.
+    n_rate injects 'N' bytes; ragged draws lengths in [0, read_len]."""
+    rng = np.random.default_rng(seed)
+    if ragged:
+        lens = rng.integers(0, read_len + 1, size=n_reads)
+    else:
+        lens = np.full(n_reads, read_len, dtype=np.int64)
+    offs = np.zeros(n_reads + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    total = int(offs[-1])
+    codes = rng.integers(0, 4, size=total, dtype=np.uint8)
+    is_ref = rng.random(n_reads) < frac_ref
+    L = len(ref_codes)
+    for r in np.nonzero(is_ref)[0]:
+        ln = int(lens[r])
+        if ln == 0 or ln > L:
+            continue
+        s = int(rng.integers(0, L - ln + 1))
+        seg = ref_codes[s:s + ln]
+        if rng.integers(0, 2):
+            seg = COMP[seg[::-1]]
+        codes[int(offs[r]):int(offs[r]) + ln] = seg
+    if sub_rate > 0:
+        m = rng.random(total) < sub_rate
+        codes[m] = (codes[m] + rng.integers(1, 4, size=int(m.sum()), dtype=np.uint8)) & 3
+    bases = ACGT[codes].copy()
+    if n_rate > 0:
+        m = rng.random(total) < n_rate
+        bases[m] = ord("N")
+    # sprinkle lower case: the path is case-insensitive (src/pf1/dense_index.rs:180-183)
+    m = rng.random(total) < 0.1
+    bases[m] |= 0x20
+    return bases, offs
+
+
+def sample_reads_fast(ref_codes, n_reads, read_len, seed, frac_ref=0.5, sub_rate=0.0):
+    """Vectorised uniform-length generator for large batches (bench.py): same mix as sample_reads."""
+    rng = np.random.default_rng(seed)
+    L = len(ref_codes)
+    is_ref = rng.random(n_reads) < frac_ref
+    starts = rng.integers(0, L - read_len + 1, size=n_reads)
+    strand = rng.integers(0, 2, size=n_reads).astype(bool)
+    idx = starts[:, None] + np.arange(read_len)[None, :]
+    codes = ref_codes[idx]
+    rc = COMP[codes[:, ::-1]]
+    codes = np.where(strand[:, None], rc, codes)
+    rnd = rng.integers(0, 4, size=(n_reads, read_len), dtype=np.uint8)
+    codes = np.where(is_ref[:, None], codes, rnd)
+    if sub_rate > 0:
+        m = rng.random((n_reads, read_len)) < sub_rate
+        codes = np.where(m, (codes + rng.integers(1, 4, size=(n_reads, read_len), dtype=np.uint8)) & 3, codes)
+    return ACGT[codes.astype(np.uint8)].reshape(-1).copy()
+
+
+def synthetic_unitigs(n_unitigs, mean_extra, k, seed):
+    """uniform-random unitig set: lengths = k + Geometric(mean mean_extra); returns (codes, accum)."""
+    rng = np.random.default_rng(seed)
+    lens = k + rng.geometric(1.0 / max(mean_extra, 1), size=n_unitigs) - 1
+    accum = np.zeros(n_unitigs + 1, dtype=np.uint64)
+    accum[1:] = np.cumsum(lens)
+    codes = rng.integers(0, 4, size=int(accum[-1]), dtype=np.uint8)
+    return codes, accum

@@ -1,0 +1,68 @@
+"""CPU-only checks of the product: the C-ABI library loads and exports every symbol the header
+declares, the header and the ctypes binding agree, and the host builders / device layouts are
+self-consistent (tests/host_check.cpp).  No compute calls are made without a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import mazu_b200 as mz
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(mz.HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mazu_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_matches_binding():
+    assert _header_symbols() == mz.exported_symbols()
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(mz.LIB_PATH), "libmazu_b200.so not built (run __graft_entry__.build())"
+    L = C.CDLL(mz.LIB_PATH)
+    for name in _header_symbols():
+        assert hasattr(L, name), name
+
+
+def test_library_has_sm100a_code():
+    out = subprocess.run(["cuobjdump", "-lelf", mz.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device the product must fail loudly, never compute on the CPU."""
+    if mz.device_count() > 0:
+        pytest.skip("a GPU is visible here")
+    with pytest.raises(mz.MazuError) as e:
+        mz.DenseIndex.deserialize_from_cpp(os.path.join(ROOT, "tests", "data", "pf1", "tiny_index"))
+    assert e.value.code == -5
+
+
+def test_product_does_not_reference_oracle():
+    """Nothing under mazu_b200/ or include/ may include, link or import oracle/."""
+    for base in ("mazu_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".so", ".log", ".pyc")):
+                    continue
+                text = open(os.path.join(dp, f), errors="replace").read()
+                assert "oracle" not in text.lower(), os.path.join(dp, f)
+    out = subprocess.run(["ldd", mz.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+def test_host_builders_self_consistent(tmp_path):
+    exe = str(tmp_path / "host_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-Wno-unknown-pragmas", os.path.join(ROOT, "tests", "host_check.cpp"), "-o", exe])
+    r = subprocess.run([exe, os.path.join(ROOT, "tests/data/pf1/yeast_chr01_index"), os.path.join(ROOT, "tests/data/cf/tiny/tiny")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "host_check: 0 failures" in r.stdout

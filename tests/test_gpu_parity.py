@@ -1,0 +1,513 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (libmazu_b200.so), must be
+bit-exact with the CPU oracle on the same inputs.  Every test is marked `gpu`."""
+import os
+
+import numpy as np
+import pytest
+
+import _gen
+import _oracle as O
+import mazu_b200 as mz
+from _oracle import OracleIndex
+
+pytestmark = pytest.mark.gpu
+
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+PF1 = os.path.join(DATA, "pf1")
+TINY_INDEX = os.path.join(PF1, "tiny_index")
+TINY_REFS_INDEX = os.path.join(PF1, "tiny-multi-refs", "tiny-multi-refs_index")
+SMALL_TXOME = os.path.join(PF1, "small_txome_index")
+YEAST_CHR01 = os.path.join(PF1, "yeast_chr01_index")
+TINY_CF = os.path.join(DATA, "cf", "tiny", "tiny")
+YEAST_CF = os.path.join(DATA, "cf", "yeast_chr7", "yeast_chr7")
+NOSKEW = mz.SKEW_NONE
+
+
+def _revcomp(s):
+    return s.upper()[::-1].translate(str.maketrans("ACGT", "TGCA"))
+
+
+def assert_hits_equal(got, want, what=""):
+    got = np.asarray(got)
+    want = np.asarray(want)
+    assert got.shape == want.shape, what
+    if not np.array_equal(got, want):
+        bad = np.nonzero(got != want)[0]
+        i = int(bad[0])
+        raise AssertionError("%s: %d/%d records differ; first at %d: got %s want %s" % (what, len(bad), len(got), i, got[i], want[i]))
+
+
+def read_fasta(path):
+    recs, cur = [], None
+    for line in open(path):
+        line = line.rstrip("\r\n")
+        if line.startswith(">"):
+            cur = []
+            recs.append(cur)
+        elif cur is not None:
+            cur.append(line)
+    return ["".join(r) for r in recs]
+
+
+def fasta_as_reads(path):
+    seqs = read_fasta(path)
+    offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(s) for s in seqs])
+    return np.frombuffer("".join(seqs).encode(), dtype=np.uint8).copy(), offs
+
+
+# --------------------------------------------------------------------------------------------
+# fixtures: (device index, oracle index) pairs
+# --------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def yeast_dense():
+    return mz.DenseIndex.deserialize_from_cpp(YEAST_CHR01), OracleIndex.dense_from_pf1(YEAST_CHR01)
+
+
+@pytest.fixture(scope="module")
+def yeast_sshash(yeast_dense):
+    g, o = yeast_dense
+    return g.rebuild_k2u(mz.K2U_SSHASH, w=15, skew_param=32, seed=0), o.rebuild_k2u(1, w=15, skew=32, seed=0)
+
+
+@pytest.fixture(scope="module")
+def yeast_queries(yeast_dense):
+    """all reference k-mers + all unitig k-mers fw and rc + random negatives (config 1's query set)."""
+    _, o = yeast_dense
+    k = o.k
+    ref_codes = _gen.unpack_2bit(o.refseq_words(), int(o.ref_prefix()[-1]))
+    ref_kmers = _gen.kmer_words_from_codes(ref_codes, k)
+    useq_codes = _gen.unpack_2bit(o.useq_words(), o.total_len)
+    u_kmers = _gen.kmer_words_from_codes(useq_codes, k)  # includes boundary-straddling windows: fine, they are queries too
+    rng = np.random.default_rng(1)
+    neg = rng.integers(0, 1 << 62, size=50000, dtype=np.uint64)
+    rc = np.array([O.lib().orc_revcomp(int(x), k) for x in u_kmers[:20000]], dtype=np.uint64)
+    q = np.concatenate([ref_kmers, u_kmers, rc, neg])
+    rng.shuffle(q)
+    return q, ref_codes
+
+
+# --------------------------------------------------------------------------------------------
+# pf1/dense_index.rs:109-328 through the GPU path
+# --------------------------------------------------------------------------------------------
+def test_tiny_dense_golden_answers():
+    idx = mz.DenseIndex.deserialize_from_cpp(TINY_INDEX)
+    assert idx.n_unitigs == 1 and idx.k == 3
+    for pos, km in enumerate(["aaa", "aac", "acc", "ccc"]):
+        assert idx.get_ref_pos_eager(km) == [(0, pos, 1)]
+        assert idx.get_ref_pos_eager(_revcomp(km)) == [(0, pos, 0)]
+    for km in ["tat", "ata", "act", "ctg", "cct"]:
+        assert idx.get_ref_pos_eager(km) is None
+    for bad in ["aaaaaa", "aa"]:  # the reference panics (dense_index.rs:148-163)
+        with pytest.raises(mz.MazuError) as e:
+            idx.get_ref_pos_eager(bad)
+        assert e.value.code == mz.ERR_K_MISMATCH
+    # same answers with SSHash w=2 behind the same U2Pos (dense_index.rs:214-265)
+    ss = idx.rebuild_k2u(mz.K2U_SSHASH, w=2, skew_param=NOSKEW)
+    for pos, km in enumerate(["aaa", "aac", "acc", "ccc"]):
+        assert ss.get_ref_pos_eager(km) == [(0, pos, 1)]
+        assert ss.get_ref_pos_eager(_revcomp(km)) == [(0, pos, 0)]
+    assert ss.validate_self()[4] == 0
+
+
+@pytest.mark.parametrize("d", [TINY_INDEX, TINY_REFS_INDEX, SMALL_TXOME, YEAST_CHR01])
+def test_validate_self_dense(d):
+    g, o = mz.DenseIndex.deserialize_from_cpp(d), OracleIndex.dense_from_pf1(d)
+    assert (g.k, g.n_unitigs, g.n_kmers, g.sum_unitigs_len) == (o.k, o.n_unitigs, o.n_kmers, o.total_len)
+    want = o.validate_self()
+    assert g.validate_self() == want and want[4] == 0
+    assert g.k2u_validate_self() == o.k2u_validate_self()
+    if d == YEAST_CHR01:
+        assert want == [230188, 170689, 59499, 262130, 0]
+
+
+def test_validate_self_yeast_sshash(yeast_sshash):
+    g, o = yeast_sshash
+    assert g.validate_self() == [230188, 170689, 59499, 262130, 0]
+    c = g.k2u_validate_self()
+    assert c == o.k2u_validate_self() and c[0] == 443836 and c[4] == 0
+    assert g.n_kmers_in_skew_index == o.n_kmers_in_skew_index > 0
+
+
+def test_k2u_batch_pfhash_yeast(yeast_dense, yeast_queries):
+    g, o = yeast_dense
+    q, _ = yeast_queries
+    assert_hits_equal(g.k2u_batch(q), o.k2u_batch(q), "PFHash/BooPHF k2u")
+
+
+def test_k2u_batch_native_pfhash_yeast(yeast_dense, yeast_queries):
+    g, o = yeast_dense
+    q, _ = yeast_queries
+    g2 = g.rebuild_k2u(mz.K2U_PFHASH)
+    assert_hits_equal(g2.k2u_batch(q), o.k2u_batch(q), "PFHash/native MPHF k2u")
+    assert g2.validate_self() == [230188, 170689, 59499, 262130, 0]
+
+
+@pytest.mark.parametrize("w,skew", [(15, 32), (15, NOSKEW), (19, 4), (9, 64), (31, 0), (1, 8)])
+def test_k2u_batch_sshash_yeast(yeast_dense, yeast_queries, w, skew):
+    g, o = yeast_dense
+    q, _ = yeast_queries
+    q = q[:200000]
+    gs = g.rebuild_k2u(mz.K2U_SSHASH, w=w, skew_param=skew, seed=7)
+    os_ = o.rebuild_k2u(1, w=w, skew=skew, seed=7)
+    assert_hits_equal(gs.k2u_batch(q), os_.k2u_batch(q), "SSHash k2u w=%d skew=%s" % (w, skew))
+    assert gs.n_kmers_in_skew_index == os_.n_kmers_in_skew_index
+
+
+def test_k2u_batch_device_mode_matches_host_mode(yeast_sshash, yeast_queries):
+    import torch
+    g, _ = yeast_sshash
+    q, _ = yeast_queries
+    q = q[:100000]
+    host = g.k2u_batch(q)
+    dq = torch.from_numpy(q.view(np.int64)).cuda()
+    dout = torch.empty((len(q), 4), dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream()
+    g.k2u_batch(dq, out=dout, mem=mz.MEM_DEVICE, stream=s.cuda_stream, n=len(q))
+    s.synchronize()
+    dev = dout.cpu().numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE)
+    assert_hits_equal(dev, host, "device-mode vs host-mode")
+
+
+def test_k2u_batch_edge_cases(yeast_sshash):
+    g, _ = yeast_sshash
+    assert len(g.k2u_batch(np.zeros(0, dtype=np.uint64))) == 0
+    with pytest.raises(mz.MazuError) as e:
+        g.k2u_batch(np.zeros(4, dtype=np.uint64), k=g.k + 1)
+    assert e.value.code == mz.ERR_K_MISMATCH
+    one = g.k2u_batch(np.array([0], dtype=np.uint64))  # a single k-mer = what a Rust `impl K2U` would send
+    assert len(one) == 1
+
+
+# --------------------------------------------------------------------------------------------
+# kphf/sshash.rs:633-884 golden answers through the GPU path
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w", list(range(1, 8)))
+def test_sshash_tiny_golden(w):
+    g = mz.PiscemIndex.from_cf_prefix(TINY_CF, w, NOSKEW)
+    cases = [("CACACAC", 0, 0), ("ACACACC", 0, 1), ("ACACCAC", 0, 3), ("CCTCAAT", 1, 0), ("CAATACG", 1, 3)]
+    q = np.array([mz.encode_kmer(s) for s, _, _ in cases] + [mz.encode_kmer(_revcomp(s)) for s, _, _ in cases]
+                 + [mz.encode_kmer("AAAAAAA"), mz.encode_kmer("TTTTTTT")], dtype=np.uint64)
+    h = g.k2u_batch(q)
+    for i, (_, uid, pos) in enumerate(cases):
+        assert tuple(h[i]) == (uid, 10, pos, mz.IDENTITY_MATCH)
+        assert tuple(h[i + 5]) == (uid, 10, pos, mz.TWIN_MATCH)
+    assert tuple(h[10]) == (mz.MISS, mz.MISS, mz.MISS, mz.NO_MATCH) and h[11]["match"] == mz.NO_MATCH
+    assert g.k2u_validate_self()[4] == 0
+
+
+def test_sshash_tiny_skew_equals_no_skew():
+    a = mz.PiscemIndex.from_cf_prefix(TINY_CF, 3, 0)
+    b = mz.PiscemIndex.from_cf_prefix(TINY_CF, 3, NOSKEW)
+    assert a.n_kmers_in_skew_index == a.n_kmers
+    q = np.array([mz.encode_kmer(s) for s in ["CACACAC", "ACACCAC", "CCTCAAT", "GTGTGTG", "ATTGAGG", "AAAAAAA"]], dtype=np.uint64)
+    assert_hits_equal(a.k2u_batch(q), b.k2u_batch(q))
+    assert a.k2u_validate_self()[4] == 0
+
+
+def test_sshash_unitigs_share_mmer():
+    seqs = ["ACAACTTACCCTCCATTACCCTACCTCCCCA", "CAACTTACCCTCCATTACCCTACCTCCCCAC"]
+    g = mz.SSHash.from_unitig_set_no_skew_index(mz.UnitigSet.from_seqs(seqs, 31), 15)
+    o = OracleIndex.from_seqs(seqs, 31, 1, w=15)
+    q = np.array([mz.encode_kmer(s) for s in seqs] + [mz.encode_kmer(_revcomp(s)) for s in seqs], dtype=np.uint64)
+    h = g.k2u_batch(q)
+    assert tuple(h[0]) == (0, 31, 0, mz.IDENTITY_MATCH) and tuple(h[1]) == (1, 31, 0, mz.IDENTITY_MATCH)
+    assert_hits_equal(h, o.k2u_batch(q))
+    assert g.k2u_validate_self() == o.k2u_validate_self()
+
+
+# --------------------------------------------------------------------------------------------
+# K1: encode / canonical k-mers / minimizers
+# --------------------------------------------------------------------------------------------
+def test_encode_reads_matches_oracle(yeast_sshash, yeast_queries):
+    import torch
+    g, o = yeast_sshash
+    _, ref_codes = yeast_queries
+    bases, offs = _gen.sample_reads(ref_codes, 300, 200, seed=3, frac_ref=0.6, sub_rate=0.01, n_rate=0.004, ragged=True)
+    koffs = o.kmer_offsets(offs)
+    n = int(koffs[-1])
+    dev = lambda a: torch.from_numpy(a).cuda()
+    d_bases, d_offs, d_koffs = dev(bases), dev(offs.view(np.int64)), dev(koffs.view(np.int64))
+    fw = torch.zeros(n, dtype=torch.int64, device="cuda"); rc = torch.zeros_like(fw); mm = torch.zeros_like(fw)
+    off = torch.zeros(n, dtype=torch.int32, device="cuda"); valid = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    g.encode_reads(d_bases, d_offs, len(offs) - 1, 0, d_koffs, fw, rc, mm, off, valid, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    fw, rc, mm = (t.cpu().numpy().view(np.uint64) for t in (fw, rc, mm))
+    off, valid = off.cpu().numpy().view(np.uint32), valid.cpu().numpy()
+    k, w = o.k, 15
+    for r in range(len(offs) - 1):
+        seq = bases[int(offs[r]):int(offs[r + 1])]
+        ns = int(koffs[r + 1] - koffs[r])
+        efw = np.zeros(max(ns, 1), dtype=np.uint64); erc = np.zeros_like(efw); emm = np.zeros_like(efw)
+        eoff = np.zeros(max(ns, 1), dtype=np.uint32); ev = np.zeros(max(ns, 1), dtype=np.uint8)
+        O.lib().orc_encode_read(O._ptr(seq), len(seq), k, w, 0, O._ptr(efw), O._ptr(erc), O._ptr(emm), O._ptr(eoff), O._ptr(ev))
+        s = slice(int(koffs[r]), int(koffs[r]) + ns)
+        assert np.array_equal(valid[s], ev[:ns]), r
+        assert np.array_equal(fw[s], efw[:ns]) and np.array_equal(rc[s], erc[:ns]), r
+        assert np.array_equal(mm[s], emm[:ns]) and np.array_equal(off[s], eoff[:ns]), r
+
+
+# --------------------------------------------------------------------------------------------
+# query_reads: random-access and streaming
+# --------------------------------------------------------------------------------------------
+def _check_reads(g, o, bases, offs, mode):
+    streaming = mode == mz.MODE_STREAMING
+    want, wcnt, wk = o.query_reads(bases, offs, streaming=streaming, reset_per_read=True)
+    got, gcnt, gk = g.query_reads(bases, offs, mode=mode)
+    assert np.array_equal(gk, wk)
+    assert_hits_equal(got, want, "query_reads mode=%d" % mode)
+    assert list(gcnt) == list(wcnt)
+    # counts-only call (the `kphf bench` shape)
+    _, c2, _ = g.query_reads(bases, offs, mode=mode, want_hits=False)
+    assert list(c2) == list(wcnt)
+    return want, wcnt
+
+
+@pytest.mark.parametrize("mode", [mz.MODE_RANDOM, mz.MODE_STREAMING])
+@pytest.mark.parametrize("which", ["sshash", "pfhash"])
+def test_query_reads_mixed_ragged(yeast_dense, yeast_sshash, yeast_queries, mode, which):
+    g, o = yeast_sshash if which == "sshash" else yeast_dense
+    _, ref_codes = yeast_queries
+    bases, offs = _gen.sample_reads(ref_codes, 4000, 260, seed=11, frac_ref=0.7, sub_rate=0.01, n_rate=0.002, ragged=True)
+    want, cnt = _check_reads(g, o, bases, offs, mode)
+    assert cnt[1] > 0 and cnt[2] > 0 and (want["match"] == mz.SKIPPED).any()
+
+
+@pytest.mark.parametrize("mode", [mz.MODE_RANDOM, mz.MODE_STREAMING])
+def test_query_reads_uniform_150bp(yeast_sshash, yeast_queries, mode):
+    """config 2/3 shape: uniform 150 bp reads through the uniform_read_len fast path == ragged path == oracle."""
+    g, o = yeast_sshash
+    _, ref_codes = yeast_queries
+    bases, offs = _gen.sample_reads(ref_codes, 20000, 150, seed=42, frac_ref=0.5, sub_rate=0.01 if mode else 0.0)
+    want, wcnt = _check_reads(g, o, bases, offs, mode)
+    got_u, cnt_u, _ = g.query_reads(bases, None, uniform_read_len=150, mode=mode)
+    assert_hits_equal(got_u, want, "uniform path")
+    assert list(cnt_u) == list(wcnt)
+
+
+def test_query_reads_edge_cases(yeast_sshash):
+    g, o = yeast_sshash
+    k = g.k
+    # empty batch, empty reads, reads shorter than k, exactly k, all-N
+    seqs = ["", "ACGT", "A" * (k - 1), "ACGTACGTACGTACGTACGTACGTACGTACG", "N" * 64, "acgtn" * 20, ""]
+    offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(s) for s in seqs])
+    bases = np.frombuffer("".join(seqs).encode(), dtype=np.uint8).copy()
+    for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+        _check_reads(g, o, bases, offs, mode)
+    hits, cnt, ko = g.query_reads(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64))
+    assert len(hits) == 0 and list(cnt) == [0, 0, 0] and list(ko) == [0]
+
+
+def test_query_reads_device_mode(yeast_sshash, yeast_queries):
+    import torch
+    g, o = yeast_sshash
+    _, ref_codes = yeast_queries
+    bases, offs = _gen.sample_reads(ref_codes, 3000, 180, seed=5, frac_ref=0.6, sub_rate=0.02, n_rate=0.001, ragged=True)
+    for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+        want, wcnt, wk = o.query_reads(bases, offs, streaming=bool(mode))
+        d_bases = torch.from_numpy(bases).cuda()
+        d_offs = torch.from_numpy(offs.view(np.int64)).cuda()
+        d_k = torch.zeros(len(offs), dtype=torch.int64, device="cuda")
+        d_hits = torch.zeros((len(want), 4), dtype=torch.int32, device="cuda")
+        d_cnt = torch.zeros(3, dtype=torch.int64, device="cuda")
+        g.query_reads(d_bases, d_offs, n_reads=len(offs) - 1, mode=mode, out_hits=d_hits, kmer_offsets=d_k, counts=d_cnt,
+                      mem=mz.MEM_DEVICE, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_k.cpu().numpy().view(np.uint64), wk)
+        assert_hits_equal(d_hits.cpu().numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE), want, "device mode %d" % mode)
+        assert list(d_cnt.cpu().numpy()) == list(wcnt.astype(np.int64))
+
+
+def test_streaming_exact_with_duplicate_kmers():
+    """A unitig set whose canonical k-mers are NOT unique (not a valid cdBG): random-access and
+    streaming answers differ there, and the GPU walk must reproduce the reference's sequential
+    warm/cold decisions (caching.rs:65-103) exactly, including first-match order inside a bucket."""
+    rng = np.random.default_rng(9)
+    k = 15
+    core = "".join("ACGT"[i] for i in rng.integers(0, 4, size=60))
+    seqs = [core[:40], core[10:60], "".join("ACGT"[i] for i in rng.integers(0, 4, size=50)), _revcomp(core[5:45]), core[20:50] + "ACGTTGCA"]
+    us = mz.UnitigSet.from_seqs(seqs, k)
+    reads = [core, _revcomp(core), core[3:33] + "T" + core[34:], seqs[2] + core[10:40], core[:25] + "N" + core[26:], core[12:58]]
+    offs = np.zeros(len(reads) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in reads])
+    bases = np.frombuffer("".join(reads).encode(), dtype=np.uint8).copy()
+    differs = False
+    for w, skew in [(7, NOSKEW), (5, 1), (11, 0)]:
+        g = mz.SSHash.from_unitig_set(us, w, skew)
+        o = OracleIndex.from_seqs(seqs, k, 1, w=w, skew=skew)
+        r_want, _ = _check_reads(g, o, bases, offs, mz.MODE_RANDOM)
+        s_want, _ = _check_reads(g, o, bases, offs, mz.MODE_STREAMING)
+        differs |= not np.array_equal(r_want, s_want)
+    gp, op = mz.PFHash.from_unitig_set(us), None
+    assert differs, "test input should make streaming and random-access answers differ"
+    assert gp.n_kmers > 0
+
+
+# --------------------------------------------------------------------------------------------
+# validate_fasta on the cuttlefish fixtures (piscem_index.rs:63-99, defaults.rs:60-71, caching.rs:238-253)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["piscem", "pufferfish"])
+def test_validate_fasta_tiny_with_poly_n(kind):
+    if kind == "piscem":
+        g, o = mz.PiscemIndex.from_cf_prefix(TINY_CF, 3, 2), OracleIndex.from_cf(TINY_CF, 1, w=3, skew=2)
+    else:
+        g, o = mz.PufferfishDenseIndex.from_cf_prefix(TINY_CF), OracleIndex.from_cf(TINY_CF, 0)
+    bases, offs = fasta_as_reads(TINY_CF + ".fa")
+    for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+        want, cnt = _check_reads(g, o, bases, offs, mode)
+        assert cnt[0] == 16 and cnt[2] == 0
+    # projected positions contain (record, pos) for every valid window
+    hits, _, koffs = g.query_reads(bases, offs)
+    poffs, mrps = g.project_hits(hits)
+    ooffs, omrps = o.project_hits(hits)
+    assert np.array_equal(poffs, ooffs) and np.array_equal(mrps, omrps)
+    for r in range(len(offs) - 1):
+        for p in range(int(koffs[r + 1] - koffs[r])):
+            i = int(koffs[r]) + p
+            if hits[i]["match"] == mz.SKIPPED:
+                continue
+            lst = mrps[int(poffs[i]):int(poffs[i + 1])]
+            assert any(m["ref_id"] == r and m["pos"] == p for m in lst)
+
+
+@pytest.mark.parametrize("kind", ["piscem", "pufferfish"])
+def test_validate_fasta_yeast_chr7_long_record(kind):
+    """One 1.09 Mbp record: exercises the chunked walk of a long read in both modes."""
+    if kind == "piscem":
+        g, o = mz.PiscemIndex.from_cf_prefix(YEAST_CF, 15, 32), OracleIndex.from_cf(YEAST_CF, 1, w=15, skew=32)
+        assert g.n_kmers_in_skew_index == o.n_kmers_in_skew_index != 0
+        assert g.n_minimizers == o.n_minimizers < g.n_kmers
+    else:
+        g, o = mz.PufferfishDenseIndex.from_cf_prefix(YEAST_CF), OracleIndex.from_cf(YEAST_CF, 0)
+    bases, offs = fasta_as_reads(YEAST_CF + ".fa")
+    for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+        want, cnt = _check_reads(g, o, bases, offs, mode)
+        assert cnt[0] == 1090910 and cnt[2] == 0
+    hits, _, _ = g.query_reads(bases, offs)
+    poffs, mrps = g.project_hits(hits)
+    ooffs, omrps = o.project_hits(hits)
+    assert np.array_equal(poffs, ooffs) and np.array_equal(mrps, omrps)
+    # every k-mer maps back to its own position on reference 0 (validate_ckmers)
+    pos = np.arange(len(hits), dtype=np.uint32)
+    owner = np.repeat(pos, np.diff(poffs).astype(np.int64))
+    ok = np.zeros(len(hits), dtype=bool)
+    ok[owner[(mrps["ref_id"] == 0) & (mrps["pos"] == owner)]] = True
+    assert ok.all()
+    assert g.k2u_validate_self() == o.k2u_validate_self()
+
+
+# --------------------------------------------------------------------------------------------
+# K4: occurrence decode and projection
+# --------------------------------------------------------------------------------------------
+def test_decode_occs_fixtures(yeast_dense):
+    g, o = yeast_dense
+    ids = np.arange(g.n_unitigs, dtype=np.uint32)
+    go, gx = g.decode_occs(ids)
+    oo, ox = o.decode_occs(ids)
+    assert np.array_equal(go, oo) and np.array_equal(gx, ox) and len(gx) == 1029
+    for prefix, kind in [(TINY_CF, 0), (TINY_CF, 1), (YEAST_CF, 1)]:
+        gi = mz.ModIndex.from_cf_prefix(prefix, kind, w=3 if prefix == TINY_CF else 15)
+        oi = OracleIndex.from_cf(prefix, kind, w=3 if prefix == TINY_CF else 15)
+        ids = np.concatenate([np.arange(gi.n_unitigs, dtype=np.uint32), np.array([mz.MISS], dtype=np.uint32)])
+        a, b = gi.decode_occs(ids), oi.decode_occs(ids)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    gi = mz.ModIndex.from_cf_prefix(TINY_CF, 1, w=3)
+    offs, occs = gi.decode_occs(np.array([0, 1], dtype=np.uint32))
+    assert list(offs) == [0, 2, 4] and [tuple(x) for x in occs] == [(0, 3, 1), (1, 11, 0), (0, 14, 0), (1, 0, 1)]  # spt.rs:156-211
+
+
+def _synthetic_u2pos(n_unitigs, n_refs, max_ref_len, seed, max_mult):
+    rng = np.random.default_rng(seed)
+    mult = np.minimum(rng.zipf(1.2, size=n_unitigs), max_mult).astype(np.uint64)
+    offsets = np.zeros(n_unitigs + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(mult)
+    n = int(offsets[-1])
+    ref_ids = rng.integers(0, n_refs, size=n, dtype=np.uint32)
+    poss = rng.integers(0, max_ref_len - 2000, size=n, dtype=np.uint32)
+    fws = rng.integers(0, 2, size=n, dtype=np.uint8)
+    return offsets, ref_ids, poss, fws
+
+
+@pytest.mark.parametrize("kind", ["dense", "piscem"])
+def test_decode_and_project_synthetic_high_multiplicity(kind):
+    """config 4 shape at test size: Zipf(1.2) multiplicities, both encodings, queries drawn ~ multiplicity."""
+    k, U = 31, 3000
+    codes, accum = _gen.synthetic_unitigs(U, 68, k, seed=44)
+    us = mz.UnitigSet(k, mz.pack_2bit(codes), len(codes), accum)
+    g = mz.SSHash.from_unitig_set(us, 19, 64)
+    o = OracleIndex.from_packed(k, us.useq_words, us.n_bases, accum, 1, w=19, skew=64)
+    n_refs, max_ref_len = 4096, 1 << 27
+    offsets, ref_ids, poss, fws = _synthetic_u2pos(U, n_refs, max_ref_len, 44, 5000)
+    o.attach_u2pos(0 if kind == "dense" else 1, offsets, ref_ids, poss, fws, max_ref_len, n_refs)
+    off_vec = mz.PackedVec.pack(offsets)
+    if kind == "dense":
+        words = ((poss.astype(np.uint64) | (fws.astype(np.uint64) << np.uint64(31))) << np.uint64(32)) | ref_ids.astype(np.uint64)
+        g.attach_u2pos_dense(words, off_vec)
+    else:
+        out = np.zeros(3, dtype=np.uint32)
+        assert O.lib().orc_required_num_bits(max_ref_len, n_refs, O._ptr(out)) == 0
+        pos_bits, ref_bits, total = (int(x) for x in out)
+        assert (pos_bits, ref_bits, total) == (28, 13, 42)
+        ref_shift, pos_mask = pos_bits + 1, (1 << pos_bits) - 1
+        enc = (ref_ids.astype(np.uint64) << np.uint64(ref_shift)) | (poss.astype(np.uint64) << np.uint64(1)) | fws.astype(np.uint64)
+        g.attach_u2pos_piscem(mz.PackedVec.pack(enc, total), ref_shift, pos_mask, off_vec)
+    rng = np.random.default_rng(45)
+    mult = np.diff(offsets).astype(np.float64)
+    q = rng.choice(U, size=20000, p=mult / mult.sum()).astype(np.uint32)
+    q[::97] = mz.MISS
+    a, b = g.decode_occs(q), o.decode_occs(q)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # projection for a random (pos, orientation) per query
+    hits = np.zeros(len(q), dtype=mz.HIT_DTYPE)
+    ulen = np.diff(accum).astype(np.uint32)
+    valid = q != mz.MISS
+    hits["unitig_id"] = q
+    hits["unitig_len"][valid] = ulen[q[valid]]
+    hits["pos"][valid] = (rng.random(int(valid.sum())) * (ulen[q[valid]] - k + 1)).astype(np.uint32)
+    hits["match"] = np.where(valid, rng.integers(1, 3, size=len(q)), 0)
+    hits["unitig_id"][~valid] = mz.MISS
+    a, b = g.project_hits(hits), o.project_hits(hits)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and len(a[1]) > len(q)
+    with pytest.raises(mz.MazuError) as e:
+        mz.SSHash.from_unitig_set(us, 19, 64).decode_occs(q)
+    assert e.value.code == mz.ERR_NO_U2POS
+
+
+# --------------------------------------------------------------------------------------------
+# larger synthetic index: size-independent properties + sampled oracle comparison
+# --------------------------------------------------------------------------------------------
+def test_synthetic_index_properties():
+    k = 31
+    codes, accum = _gen.synthetic_unitigs(60000, 68, k, seed=45)  # ~6e6 bases
+    us = mz.UnitigSet(k, mz.pack_2bit(codes), len(codes), accum)
+    g = mz.SSHash.from_unitig_set(us, 19, 64)
+    c = g.k2u_validate_self()  # every unitig k-mer, fw and swapped, maps back to itself
+    assert c[0] == 2 * g.n_kmers and c[4] == 0 and c[1] == c[2] == g.n_kmers
+    # reads sampled from the unitig concatenation: every hit must verify against the sequence
+    bases = _gen.sample_reads_fast(codes, 50000, 150, seed=46, frac_ref=0.7, sub_rate=0.01)
+    hr, cr, _ = g.query_reads(bases, None, uniform_read_len=150)
+    hs, cs, _ = g.as_streaming().query_reads(bases, None, uniform_read_len=150)
+    assert_hits_equal(hs, hr, "streaming == random on an index with unique canonical k-mers")
+    assert list(cr) == list(cs) and cr[0] == 50000 * 120
+    hit = hr["match"] != 0
+    assert 0.2 < hit.mean() < 0.8
+    starts = accum[hr["unitig_id"][hit].astype(np.int64)] + hr["pos"][hit]
+    read_codes = np.frombuffer(bases, dtype=np.uint8)
+    lut = np.zeros(256, dtype=np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        lut[ch] = i
+    rk = _gen.kmer_words_from_codes(lut[read_codes], k).reshape(-1)
+    # slot i of read r starts at base r*150 + p
+    slot = np.nonzero(hit)[0]
+    base_idx = (slot // 120) * 150 + (slot % 120)
+    fw = rk[base_idx]
+    uk = _gen.kmer_words_from_codes(codes, k)[starts.astype(np.int64)]
+    rc = np.array([O.lib().orc_revcomp(int(x), k) for x in fw[:5000]], dtype=np.uint64)
+    ident = hr["match"][hit] == mz.IDENTITY_MATCH
+    assert np.array_equal(uk[ident], fw[ident])
+    assert np.array_equal(uk[:5000][~ident[:5000]], rc[~ident[:5000]])
+    # sampled oracle comparison
+    o = OracleIndex.from_packed(k, us.useq_words, us.n_bases, accum, 1, w=19, skew=64)
+    want, _, _ = o.query_reads(bases[:150 * 3000], np.arange(3001, dtype=np.uint64) * 150)
+    assert_hits_equal(hr[:120 * 3000], want, "sampled oracle comparison")
