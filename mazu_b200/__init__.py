@@ -343,7 +343,10 @@ class ModIndex:
             else:
                 ro = np.ascontiguousarray(read_offsets, dtype=np.uint64)
                 n_reads = len(ro) - 1
-            koffs = np.zeros(n_reads + 1, dtype=np.uint64) if kmer_offsets is None else kmer_offsets
+            if kmer_offsets is None:  # implied by arithmetic for uniform reads; materialised only for ragged batches
+                koffs = None if uniform_read_len else np.zeros(n_reads + 1, dtype=np.uint64)
+            else:
+                koffs = kmer_offsets
             if want_hits and out_hits is None:
                 out_hits = np.empty(self.count_kmer_slots(ro, n_reads, uniform_read_len), dtype=HIT_DTYPE)
             cnt = np.zeros(3, dtype=np.uint64) if counts is None else counts

@@ -326,7 +326,9 @@ def test_streaming_exact_with_duplicate_kmers():
     rng = np.random.default_rng(9)
     k = 15
     core = "".join("ACGT"[i] for i in rng.integers(0, 4, size=60))
-    seqs = [core[:40], core[10:60], "".join("ACGT"[i] for i in rng.integers(0, 4, size=50)), _revcomp(core[5:45]), core[20:50] + "ACGTTGCA"]
+    # unitig 1 owns k-mers 0..9 of `core` alone and shares 10..25 with unitig 0, which is earlier in
+    # bucket order: a walk that enters on unitig 1 stays there, a random-access lookup answers unitig 0
+    seqs = [core[10:60], core[:40], "".join("ACGT"[i] for i in rng.integers(0, 4, size=50)), _revcomp(core[5:45]), core[20:50] + "ACGTTGCA"]
     us = mz.UnitigSet.from_seqs(seqs, k)
     reads = [core, _revcomp(core), core[3:33] + "T" + core[34:], seqs[2] + core[10:40], core[:25] + "N" + core[26:], core[12:58]]
     offs = np.zeros(len(reads) + 1, dtype=np.uint64)
@@ -339,9 +341,7 @@ def test_streaming_exact_with_duplicate_kmers():
         r_want, _ = _check_reads(g, o, bases, offs, mz.MODE_RANDOM)
         s_want, _ = _check_reads(g, o, bases, offs, mz.MODE_STREAMING)
         differs |= not np.array_equal(r_want, s_want)
-    gp, op = mz.PFHash.from_unitig_set(us), None
     assert differs, "test input should make streaming and random-access answers differ"
-    assert gp.n_kmers > 0
 
 
 # --------------------------------------------------------------------------------------------
