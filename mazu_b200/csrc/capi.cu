@@ -281,18 +281,31 @@ void launch_k2u_batch(const mazu_index* ix, const u64* d_words, u64 n, Hit* d_ou
   MZ_CUDA(cudaGetLastError());
 }
 
+template <int MODE, int KIND, u32 FAMILY>
+void launch_qr(const mazu_index* ix, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, const u64* d_kmer_offsets,
+               Hit* d_out, u64* d_counts, cudaStream_t s) {
+  auto kern = query_reads_kernel<MODE, KIND, FAMILY>;
+  int grid = grid_for(kern, QR_WARPS * 32, ix, QR_WARPS, n_reads);
+  kern<<<grid, QR_WARPS * 32, 0, s>>>(ix->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out,
+                                      (unsigned long long*)d_counts);
+}
+
 void launch_query_reads(const mazu_index* ix, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, int mode,
                         const u64* d_kmer_offsets, Hit* d_out, u64* d_counts, cudaStream_t s) {
   if (n_reads == 0) return;
-  if (mode == MAZU_MODE_RANDOM) {
-    int grid = grid_for(query_reads_kernel<0>, QR_WARPS * 32, ix, QR_WARPS, n_reads);
-    query_reads_kernel<0><<<grid, QR_WARPS * 32, 0, s>>>(ix->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out,
-                                                         (unsigned long long*)d_counts);
+  const bool ss = ix->view.k2u_kind == MAZU_K2U_SSHASH;
+  const bool native = ix->view.mphf.family == MPHF_FAMILY_NATIVE;
+  const bool st = mode == MAZU_MODE_STREAMING;
+#define MZ_QR(M, K, F) launch_qr<M, K, F>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, d_counts, s)
+  if (ss) {
+    if (!native) throw Error(MAZU_ERR_OTHER, "internal: SSHash index without a native MPHF");
+    if (st) MZ_QR(1, MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE); else MZ_QR(0, MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE);
+  } else if (native) {
+    if (st) MZ_QR(1, MAZU_K2U_PFHASH, MPHF_FAMILY_NATIVE); else MZ_QR(0, MAZU_K2U_PFHASH, MPHF_FAMILY_NATIVE);
   } else {
-    int grid = grid_for(query_reads_kernel<1>, QR_WARPS * 32, ix, QR_WARPS, n_reads);
-    query_reads_kernel<1><<<grid, QR_WARPS * 32, 0, s>>>(ix->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out,
-                                                         (unsigned long long*)d_counts);
+    if (st) MZ_QR(1, MAZU_K2U_PFHASH, MPHF_FAMILY_BOOPHF); else MZ_QR(0, MAZU_K2U_PFHASH, MPHF_FAMILY_BOOPHF);
   }
+#undef MZ_QR
   MZ_CUDA(cudaGetLastError());
 }
 

@@ -427,7 +427,7 @@ struct MinOcc {
 
 // minimizer occurrences of one unitig in the reference's order (src/kphf/sshash.rs:100-143):
 // the fw-canonical k-mers' stream then the rc-canonical k-mers' stream, each run-length deduped.
-inline void collect_unitig_minimizers(const UnitigSetHost& us, u64 ui, u32 w, u64 seed, std::vector<u64>& hf, std::vector<u64>& hr,
+inline void collect_unitig_minimizers(const UnitigSetHost& us, u64 ui, u32 w, u64 seed, std::vector<u32>& hf, std::vector<u32>& hr,
                                       std::vector<MinOcc>& out) {
   const u32 k = us.k;
   const u64 s = us.accum[ui], e = us.accum[ui + 1];
@@ -444,8 +444,8 @@ inline void collect_unitig_minimizers(const UnitigSetHost& us, u64 ui, u32 w, u6
       f = ((f >> 2) | (c << (2 * (w - 1)))) & wmask;
       r = ((r << 2) | (3 - c)) & wmask;
       if (i + 1 >= w) {
-        hf[i + 1 - w] = mm_hash64(f, seed);
-        hr[i + 1 - w] = mm_hash64(r, seed);
+        hf[i + 1 - w] = mm_hash32(f, seed) & MM_KEY_MASK;
+        hr[i + 1 - w] = mm_hash32(r, seed) & MM_KEY_MASK;
       }
     }
   }
@@ -463,16 +463,13 @@ inline void collect_unitig_minimizers(const UnitigSetHost& us, u64 ui, u32 w, u6
       u64 p = i + 1 - k;  // k-mer start inside the unitig
       bool fw_canon = fw <= rc;
       if (fw_canon != (pass == 0)) continue;
-      // leftmost minimum in the canonical k-mer's coordinates
-      u64 best_h = 0;
-      u32 best_i = 0;
+      // smallest (hash key | offset in the canonical k-mer): minimizer order v2 (kmer.hpp)
+      u32 best = 0xFFFFFFFFu;
       for (u32 ci = 0; ci <= span; ++ci) {
-        u64 h = fw_canon ? hf[p + ci] : hr[p + span - ci];
-        if (ci == 0 || h < best_h) {
-          best_h = h;
-          best_i = ci;
-        }
+        u32 key = (fw_canon ? hf[p + ci] : hr[p + span - ci]) | ci;
+        best = key < best ? key : best;
       }
+      u32 best_i = best & 31u;
       u64 word = ((fw_canon ? fw : rc) >> (2 * best_i)) & wmask;
       u64 off_fw = fw_canon ? best_i : (span - best_i);  // offset in fw-mer coordinates
       MinOcc cur{word, s + p + off_fw};
@@ -513,7 +510,7 @@ inline std::shared_ptr<K2UHost> build_sshash(std::shared_ptr<const UnitigSetHost
     std::vector<std::thread> ts;
     for (unsigned t = 0; t < parts; ++t)
       ts.emplace_back([&, t] {
-        std::vector<u64> hf, hr;
+        std::vector<u32> hf, hr;
         for (u64 ui = cut[t]; ui < cut[t + 1]; ++ui) collect_unitig_minimizers(us, ui, w, seed, hf, hr, per[t]);
       });
     for (auto& t : ts) t.join();

@@ -77,8 +77,11 @@ MZ_HD bool ranked_probe(const RankedLevels& m, u32 level, u64 blk, u32 bit, u64&
 // MPHF::try_hash_u64 (src/kphf/mod.rs:54-56).  BOOPHF reproduces BooPHF<u64>::lookup
 // (src/pf1/boophf/mod.rs:96-181) bit-exactly; NATIVE is this library's own BBHash-style MPHF.
 // Like boomphf::try_hash, a non-member key may return a false-positive value < n_keys.
-MZ_HD bool mphf_lookup(const RankedLevels& m, u64 key, u64& out) {
-  if (m.family == MPHF_FAMILY_NATIVE) {
+// Templated on the family so a kernel only carries the code of the family it serves.
+template <u32 FAMILY>
+MZ_HD bool mphf_lookup_t(const RankedLevels& m, u64 key, u64& out) {
+  if (FAMILY == MPHF_FAMILY_NATIVE) {
+#pragma unroll 1
     for (u32 l = 0; l < m.n_levels; ++l) {
       u64 blk;
       u32 bit;
@@ -87,6 +90,7 @@ MZ_HD bool mphf_lookup(const RankedLevels& m, u64 key, u64& out) {
     }
   } else {
     u64 s0 = BOOPHF_SEED0, s1 = BOOPHF_SEED1;  // MultiHashState (src/pf1/boophf/hash.rs:91-97)
+#pragma unroll 1
     for (u32 l = 0; l < m.n_levels; ++l) {
       u64 h;
       if (l == 0) {
@@ -121,6 +125,9 @@ MZ_HD bool mphf_lookup(const RankedLevels& m, u64 key, u64& out) {
     if (kk < key) lo = mid + 1; else hi = mid;
   }
   return false;
+}
+MZ_HD bool mphf_lookup(const RankedLevels& m, u64 key, u64& out) {
+  return m.family == MPHF_FAMILY_NATIVE ? mphf_lookup_t<MPHF_FAMILY_NATIVE>(m, key, out) : mphf_lookup_t<MPHF_FAMILY_BOOPHF>(m, key, out);
 }
 
 // ---------------------------------------------------------------------------------------------

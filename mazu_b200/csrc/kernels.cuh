@@ -117,68 +117,225 @@ __global__ void __launch_bounds__(256) k2u_batch_kernel(const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Read chunk staging shared by K1 / K2-on-reads / K3.  A warp owns one read and walks it in
-// chunks of CHUNK k-mer start positions.
+// Read kernels (K1 / K2-on-reads / K3).  A warp owns one read and walks it in chunks of QR_CHUNK
+// k-mer start positions; everything a chunk needs is staged in that warp's slice of shared memory:
+//
+//   stage E  encode: coalesced byte loads -> 2-bit words by warp OR-reduction (redux.sync) and
+//            ballot; the chunk's k-mer words go to smem (fw[]), validity to four ballot masks
+//   stage M  minimizers: one 32-bit hash per w-mer and strand (hf[], hr[]), then per k-mer the
+//            smallest (hash | offset) key over its window of k-w+1 w-mers
+//   stage B  buckets: k-mers of a super-k-mer share their minimizer, hence MPHF slot and bucket;
+//            the FIRST k-mer of every run of equal minimizers is a leader.  Leaders of the whole
+//            chunk (~15 of 128 k-mers) are compacted and resolved in one pass:
+//            MPHF -> blocked Elias-Fano bounds -> (start, size) parked in smem at the leader's slot
+//   stage V  verify, per k-mer: bucket positions -> candidate windows -> equality -> unitig id / bounds
+//
+// So the dependent MPHF/Elias-Fano chain runs once per super-k-mer, not once per k-mer, and the
+// kernel holds ONE copy of each stage (the first version inlined the lookup four times; ncu showed
+// 72 % of stall samples in `no_instruction`, i.e. instruction-cache misses -- profiles/r01_*).
 // ---------------------------------------------------------------------------------------------
-static const int QR_WARPS = 8;         // warps per CTA
-static const int QR_CHUNK = 128;       // k-mer start positions per chunk
-static const int QR_BASES = 160;       // bases staged per chunk (CHUNK + k - 1 <= 159)
-static const int QR_WORDS = 6;         // 5 words of 32 bases + 1 zero pad
+static const int QR_WARPS = 8;    // warps per CTA
+static const int QR_CHUNK = 128;  // k-mer start positions per chunk
+static const int QR_BASES = 160;  // bases staged per chunk (CHUNK + k - 1 <= 159)
+static const u32 BN_SKEW = 0xFFFFFFFFu;
 
-struct ChunkRegs {
-  u64 w[QR_WORDS];  // 2-bit packed bases of the chunk; word t holds chunk bases [32t, 32t+32)
-  u32 inv[QR_WORDS];  // bit j of inv[t]: base 32t+j is not ACGT or lies beyond the read
+struct WarpStage {
+  u64 fw[QR_CHUNK];      // forward k-mer word per chunk position (garbage where invalid)
+  u64 bstart[QR_CHUNK];  // leaders only: first bucket entry
+  u32 bn[QR_CHUNK];      // leaders only: bucket size, 0 = minimizer unknown, BN_SKEW = heavy bucket
+  u32 hf[QR_BASES];      // w-mer hash keys, forward strand
+  u32 hr[QR_BASES];      // w-mer hash keys, reverse strand
+  u8 off[QR_CHUNK];      // minimizer offset in fw-mer coordinates
+  u8 leader[QR_CHUNK];   // chunk position of this k-mer's leader
+  u8 lead_list[QR_CHUNK];
 };
 
-// 2-bit encode 160 bases starting at seq[c0]: coalesced byte loads, one warp-wide OR-reduction per
-// 32-base word (redux.sync), invalid-base masks by ballot.
-__device__ __forceinline__ void load_chunk(const u8* __restrict__ seq, u64 len, u64 c0, u32 lane, ChunkRegs& c) {
+struct ChunkInfo {
+  u32 vm[4];  // ballot masks: bit `lane` of vm[t] <=> k-mer 32t+lane is a valid window inside the read
+  u32 n_c;    // k-mer positions of this chunk that lie inside the read
+};
+
+// stage E
+__device__ __forceinline__ void stage_encode(const u8* __restrict__ seq, u64 len, u64 c0, u32 n_c, u32 k, u32 lane, WarpStage& S, ChunkInfo& ci) {
+  u64 w[6];
+  u32 inv[6];
 #pragma unroll
   for (int t = 0; t < 5; ++t) {
     u64 q = c0 + 32u * t + lane;
     u32 code = 4;
     if (q < len) code = base_code(seq[q]);
     bool bad = code > 3;
-    c.inv[t] = __ballot_sync(0xffffffffu, bad);
+    inv[t] = __ballot_sync(0xffffffffu, bad);
     u32 v = bad ? 0u : code;
     u32 lo = __reduce_or_sync(0xffffffffu, lane < 16 ? (v << (2 * lane)) : 0u);
     u32 hi = __reduce_or_sync(0xffffffffu, lane >= 16 ? (v << (2 * (lane - 16))) : 0u);
-    c.w[t] = ((u64)hi << 32) | lo;
+    w[t] = ((u64)hi << 32) | lo;
   }
-  c.w[5] = 0;
-  c.inv[5] = 0xffffffffu;
-}
-// 2-bit window of `nb` bases starting at chunk position 32*t + lane
-__device__ __forceinline__ u64 chunk_window(const ChunkRegs& c, int t, u32 lane, u32 nb) {
-  u32 sh = 2 * lane;
-  u64 x = c.w[t] >> sh;
-  if (sh) x |= c.w[t + 1] << (64 - sh);
-  return x & kmer_mask(nb);
-}
-__device__ __forceinline__ bool chunk_window_valid(const ChunkRegs& c, int t, u32 lane, u32 nb) {
-  u64 m = ((u64)c.inv[t] | ((u64)c.inv[t + 1] << 32)) >> lane;
-  return (m & ((1ULL << nb) - 1ULL)) == 0ULL;  // nb <= 32
+  w[5] = 0;
+  inv[5] = 0xffffffffu;
+  const u64 kmask = kmer_mask(k);
+  const u64 vmask = (1ULL << k) - 1ULL;  // k <= 32
+  const u32 sh = 2 * lane;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    u64 x = w[t] >> sh;
+    if (sh) x |= w[t + 1] << (64 - sh);
+    S.fw[32 * t + lane] = x & kmask;
+    u64 m = ((u64)inv[t] | ((u64)inv[t + 1] << 32)) >> lane;
+    bool valid = (32u * t + lane < n_c) && ((m & vmask) == 0ULL);
+    ci.vm[t] = __ballot_sync(0xffffffffu, valid);
+  }
+  ci.n_c = n_c;
 }
 
-// minimizer of the k-mer starting at chunk position p from the per-chunk w-mer hash arrays
-// (argmin over the CANONICAL k-mer's w-mers, leftmost wins; offset in fw-mer coordinates)
-__device__ __forceinline__ void chunk_minimizer(const u64* __restrict__ hf, const u64* __restrict__ hr, u32 p, u64 fw, u64 rc,
-                                                u32 k, u32 w, u64& mm_word, u32& offset) {
-  const bool fw_canon = fw <= rc;
-  const u32 span = k - w;
-  const u64* h = fw_canon ? hf + p : hr + p + span;
-  const int step = fw_canon ? 1 : -1;
-  u64 best = h[0];
-  u32 bi = 0;
-  for (u32 ci = 1; ci <= span; ++ci) {
-    u64 v = h[(int)ci * step];
-    if (v < best) {
-      best = v;
-      bi = ci;
+__device__ __forceinline__ bool chunk_valid(const ChunkInfo& ci, u32 q) {
+  u32 word = q >> 5;
+  u32 m = word == 0 ? ci.vm[0] : word == 1 ? ci.vm[1] : word == 2 ? ci.vm[2] : ci.vm[3];
+  return (m >> (q & 31)) & 1u;
+}
+
+// canonical-orientation minimizer word of the k-mer at chunk position p, from its stored offset
+__device__ __forceinline__ u64 mm_word_of(u64 fw, u64 rc, u32 off_fw, u32 k, u32 w) {
+  bool fw_canon = fw <= rc;
+  u32 ci = fw_canon ? off_fw : (k - w - off_fw);
+  return ((fw_canon ? fw : rc) >> (2 * ci)) & kmer_mask(w);
+}
+
+// stage M + stage B (SSHash only)
+template <u32 FAMILY>
+__device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkInfo& ci, u32 lane, WarpStage& S) {
+  const u32 k = ix.unitigs.k, w = ix.w, span = k - w;
+  const u64 wmask = kmer_mask(w);
+  __syncwarp();
+  // w-mer hash keys for chunk positions [0, 160): w-mer q is the low 2w bits of k-mer q (q < 128),
+  // positions beyond come from the tail of k-mer 127
+#pragma unroll 1
+  for (int t = 0; t < 5; ++t) {
+    u32 q = 32 * t + lane;
+    u64 x;
+    if (q < QR_CHUNK) x = S.fw[q];
+    else {
+      u32 d = q - (QR_CHUNK - 1);  // 1..32
+      x = d < 32 ? (S.fw[QR_CHUNK - 1] >> (2 * d)) : 0ULL;
+    }
+    u64 wf = x & wmask;
+    S.hf[q] = mm_hash32(wf, ix.seed) & MM_KEY_MASK;
+    S.hr[q] = mm_hash32(revcomp(wf, w), ix.seed) & MM_KEY_MASK;
+  }
+  __syncwarp();
+  // per k-mer minimizer, leader detection, leader compaction
+  u32 n_lead = 0;
+  u64 carry_mm = 0;
+  u32 carry_valid = 0, carry_leader = 0;
+#pragma unroll 1
+  for (int t = 0; t < 4; ++t) {
+    const u32 p = 32 * t + lane;
+    const u32 vmask = ci.vm[t];
+    const bool valid = (vmask >> lane) & 1u;
+    u64 mmw = 0;
+    if (valid) {
+      u64 fw = S.fw[p], rc = revcomp(fw, k);
+      bool fw_canon = fw <= rc;
+      const u32* h = fw_canon ? S.hf + p : S.hr + p + span;
+      const int step = fw_canon ? 1 : -1;
+      u32 best = 0xFFFFFFFFu;
+      for (u32 c = 0; c <= span; ++c) {
+        u32 key = h[(int)c * step] | c;
+        best = min(best, key);
+      }
+      u32 bi = best & 31u;
+      mmw = ((fw_canon ? fw : rc) >> (2 * bi)) & wmask;
+      S.off[p] = (u8)(fw_canon ? bi : span - bi);
+    }
+    // neighbour's minimizer (lane-1, or lane 31 of the previous pass)
+    u64 prev_mm = __shfl_up_sync(0xffffffffu, mmw, 1);
+    u32 prev_valid = (vmask << 1) & (1u << lane);
+    if (lane == 0) {
+      prev_mm = carry_mm;
+      prev_valid = carry_valid;
+    }
+    const bool is_leader = valid && (!prev_valid || prev_mm != mmw);
+    const u32 lmask = __ballot_sync(0xffffffffu, is_leader);
+    if (valid) {
+      u32 lm = lmask & ((2u << lane) - 1u);  // leaders at lanes <= lane
+      S.leader[p] = (u8)(lm ? 32 * t + (31 - __clz(lm)) : carry_leader);
+    }
+    if (is_leader) S.lead_list[n_lead + __popc(lmask & ((1u << lane) - 1u))] = (u8)p;
+    n_lead += __popc(lmask);
+    carry_mm = __shfl_sync(0xffffffffu, mmw, 31);
+    carry_valid = (vmask >> 31) & 1u;
+    if (lmask) carry_leader = 32 * t + (31 - __clz(lmask));
+  }
+  __syncwarp();
+  // resolve the leaders' buckets: MPHF -> Elias-Fano bounds (SSHash::k2u, sshash.rs:476-490)
+#pragma unroll 1
+  for (u32 i = 0; i < n_lead; i += 32) {
+    if (i + lane < n_lead) {
+      u32 p = S.lead_list[i + lane];
+      u64 fw = S.fw[p], rc = revcomp(fw, k);
+      u64 mmw = mm_word_of(fw, rc, S.off[p], k, w);
+      u64 h, a = 0, b = 0;
+      u32 n = 0;
+      if (mphf_lookup_t<FAMILY>(ix.mphf, mmw, h) && h + 1 < ix.sizes.n) {
+        blocked_ef_get2(ix.sizes, h, a, b);
+        u64 cnt = b - a;
+        n = cnt > ix.skew_param ? BN_SKEW : (u32)cnt;
+      }
+      S.bstart[p] = a;
+      S.bn[p] = n;
     }
   }
-  mm_word = ((fw_canon ? fw : rc) >> (2 * bi)) & kmer_mask(w);
-  offset = fw_canon ? bi : span - bi;
+  __syncwarp();
+}
+
+// stage V for one k-mer of an SSHash index: the loop of sshash.rs:494-552 / k2u_skew_index
+template <u32 FAMILY>
+__device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpStage& S, u32 p, u64 fw, u64 rc, Hit& out) {
+  const u32 lp = S.leader[p];
+  const u32 n = S.bn[lp];
+  if (n == 0) return false;
+  const u32 k = ix.unitigs.k;
+  if (n == BN_SKEW) {
+    if (!ix.has_skew) return false;
+    u64 word = fw <= rc ? fw : rc, hs;
+    if (!mphf_lookup_t<FAMILY>(ix.skew_mphf, word, hs)) return false;
+    if (hs >= ix.skew_pos.len) return false;
+    u64 pos = packed_get(ix.skew_pos, hs);
+    u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, pos));
+    if (mt == NO_MATCH) return false;
+    return finish_hit(ix.unitigs, pos, mt, false, out);
+  }
+  const u64 pos_start = S.bstart[lp];
+  const u64 offset = S.off[p];
+  const u64 rc_offset = (u64)(k - ix.w) - offset;
+  const u64 last_km_start_pos = ix.unitigs.total_len - k;
+#pragma unroll 1
+  for (u32 e = 0; e < n; ++e) {
+    u64 mm_pos = packed_get(ix.pos, pos_start + e);
+    if (mm_pos >= offset && mm_pos - offset <= last_km_start_pos) {  // sshash.rs:498
+      u64 km_pos = mm_pos - offset;
+      u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, km_pos));
+      if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out)) return true;
+    }
+    if (rc_offset != offset && mm_pos >= rc_offset && mm_pos - rc_offset <= last_km_start_pos) {  // sshash.rs:527 (same window when equal)
+      u64 km_pos = mm_pos - rc_offset;
+      u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, km_pos));
+      if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out)) return true;
+    }
+  }
+  return false;
+}
+
+template <u32 FAMILY>
+__device__ __forceinline__ bool pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc, Hit& out) {
+  u64 word = fw <= rc ? fw : rc;
+  u64 h;
+  if (!mphf_lookup_t<FAMILY>(ix.mphf, word, h)) return false;
+  if (h >= ix.pos.len) return false;
+  u64 km_pos = packed_get(ix.pos, h);
+  u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, km_pos));
+  if (mt == NO_MATCH) return false;
+  return finish_hit(ix.unitigs, km_pos, mt, false, out);
 }
 
 struct StreamState {  // StreamingK2U { is_warm, prev_k2upos } (src/index/caching.rs:13-17)
@@ -186,21 +343,19 @@ struct StreamState {  // StreamingK2U { is_warm, prev_k2upos } (src/index/cachin
   u64 ustart;
 };
 
-// One kernel for the read loop of `kphf bench` / validate_ckmers, both modes.
-//   MODE 0: K2U::k2u per k-mer.  MODE 1: StreamingK2U::k2u_streaming with the cursor reset per read.
-template <int MODE>
+// One kernel for the read loop of `kphf bench` / validate_ckmers.
+//   MODE 0: K2U::k2u per k-mer.  MODE 1: StreamingK2U::k2u_streaming, cursor reset per read.
+//   KIND: MAZU_K2U_PFHASH / MAZU_K2U_SSHASH.  FAMILY: MPHF family of the index.
+template <int MODE, int KIND, u32 FAMILY>
 __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
                                                                     const u64* __restrict__ read_offsets, u64 n_reads, u64 uniform_len,
                                                                     const u64* __restrict__ kmer_offsets, Hit* __restrict__ out,
                                                                     unsigned long long* __restrict__ counts) {
-  __shared__ u64 s_hf[QR_WARPS][QR_BASES];
-  __shared__ u64 s_hr[QR_WARPS][QR_BASES];
-  __shared__ u64 s_fw[MODE == 1 ? QR_WARPS : 1][MODE == 1 ? QR_CHUNK : 1];
+  __shared__ WarpStage s_stage[QR_WARPS];
   const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const u32 k = ix.unitigs.k, w = ix.w;
-  const bool ss = ix.k2u_kind == MAZU_K2U_SSHASH;
-  u64* hf = s_hf[wib];
-  u64* hr = s_hr[wib];
+  WarpStage& S = s_stage[wib];
+  const u32 k = ix.unitigs.k;
+  constexpr bool SS = KIND == MAZU_K2U_SSHASH;
   u32 n_valid = 0, n_hit = 0;
   const u32 lt_mask = (1u << lane) - 1u;
 
@@ -223,72 +378,41 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
     st.o = NO_MATCH;
     st.ustart = 0;
 
+#pragma unroll 1
     for (u64 c0 = 0; c0 < nk; c0 += QR_CHUNK) {
-      ChunkRegs c;
-      load_chunk(seq, len, c0, lane, c);
+      ChunkInfo ci;
       const u32 n_c = (u32)min((u64)QR_CHUNK, nk - c0);
-      if (ss) {
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < 5; ++t) {
-          u64 wf = chunk_window(c, t, lane, w);
-          hf[32 * t + lane] = mm_hash64(wf, ix.seed);
-          hr[32 * t + lane] = mm_hash64(revcomp(wf, w), ix.seed);
-        }
-        __syncwarp();
-      }
+      __syncwarp();
+      stage_encode(seq, len, c0, n_c, k, lane, S, ci);
+      __syncwarp();
+      Hit* o = out ? out + slot0 + c0 : nullptr;
       if (MODE == 0) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          u32 p = 32 * t + lane;
-          if (p < n_c) {
-            Hit h = hit_none(SKIPPED);
-            if (chunk_window_valid(c, t, lane, k)) {
-              u64 fw = chunk_window(c, t, lane, k);
-              u64 rc = revcomp(fw, k);
-              bool ok;
-              if (ss) {
-                u64 mmw;
-                u32 off;
-                chunk_minimizer(hf, hr, p, fw, rc, k, w, mmw, off);
-                ok = sshash_k2u(ix, fw, rc, mmw, off, h);
-              } else {
-                ok = pfhash_k2u(ix, fw, rc, h);
-              }
-              ++n_valid;
-              if (ok) ++n_hit; else h = hit_none(NO_MATCH);
-            }
-            if (out) store_hit(out + slot0 + c0 + p, h);
+        if (SS) stage_buckets<FAMILY>(ix, ci, lane, S);
+#pragma unroll 1
+        for (u32 p = lane; p < n_c; p += 32) {
+          Hit h = hit_none(SKIPPED);
+          if (chunk_valid(ci, p)) {
+            u64 fw = S.fw[p], rc = revcomp(fw, k);
+            bool ok = SS ? verify_sshash<FAMILY>(ix, S, p, fw, rc, h) : pfhash_k2u_t<FAMILY>(ix, fw, rc, h);
+            ++n_valid;
+            if (ok) ++n_hit; else h = hit_none(NO_MATCH);
           }
+          if (o) store_hit(o + p, h);
         }
       } else {
-        // ---- K3: stage fw words (0 marks nothing: validity is kept in a per-lane bitmask) ----
-        u32 vbits = 0;  // bit t: k-mer 32t+lane is a valid window
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          s_fw[wib][32 * t + lane] = chunk_window(c, t, lane, k);
-          if (32u * t + lane < n_c && chunk_window_valid(c, t, lane, k)) vbits |= 1u << t;
-        }
-        __syncwarp();
-        u32 vm[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) vm[t] = __ballot_sync(0xffffffffu, (vbits >> t) & 1u);
+        bool prepared = false;  // stage M/B run lazily: a fully warm chunk never needs them
         u32 i = 0;
+#pragma unroll 1
         while (i < n_c) {
           const u32 q = i + lane;
           const bool active = q < n_c;
-          bool valid = false;
+          const bool valid = active && chunk_valid(ci, q);
           u64 fw = 0, rc = 0;
-          if (active) {
-            u32 word = q >> 5;
-            u32 m = word == 0 ? vm[0] : word == 1 ? vm[1] : word == 2 ? vm[2] : vm[3];
-            valid = (m >> (q & 31)) & 1u;
-            fw = s_fw[wib][q];
+          if (valid) {
+            fw = S.fw[q];
             rc = revcomp(fw, k);
           }
           const u32 vmask = __ballot_sync(0xffffffffu, valid);
-          const u32 amask = __ballot_sync(0xffffffffu, active);
           const u32 rnk = __popc(vmask & lt_mask);
           if (st.warm) {
             // Phase W: extend along the current unitig (k2u_warm, caching.rs:73-97), 32 k-mers at once
@@ -306,7 +430,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
                   ++n_valid;
                   ++n_hit;
                 }
-                if (out) store_hit(out + slot0 + c0 + q, h);
+                if (o) store_hit(o + q, h);
               }
               const u32 run_mask = run >= 32 ? 0xffffffffu : ((1u << run) - 1u);
               const u32 vr = vmask & run_mask;
@@ -320,29 +444,24 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
             }
           }
           // Phase C: cold lookups for all 32 lanes, then commit in read order (k2u_cold, caching.rs:99-103)
+          if (SS && !prepared) {
+            stage_buckets<FAMILY>(ix, ci, lane, S);
+            prepared = true;
+          }
           Hit res = hit_none(NO_MATCH);
           bool hit = false;
-          if (valid) {
-            if (st.warm && lane > 0 && (u64)st.pos + 1 + k <= (u64)st.ulen) {
-              // same cursor as lane 0 saw (earlier lanes are assumed misses): warm check against pos+1
-              u32 m = word_equivalency(fw, rc, useq_window(ix.unitigs, st.ustart + st.pos + 1));
-              if (m != NO_MATCH) {
-                res = Hit{st.uid, st.ulen, st.pos + 1, m};
-                hit = true;
-              }
+          if (valid && st.warm && lane > 0 && (u64)st.pos + 1 + k <= (u64)st.ulen) {
+            // same cursor lane 0 saw (earlier lanes are assumed misses): warm check against pos+1
+            u32 m = word_equivalency(fw, rc, useq_window(ix.unitigs, st.ustart + st.pos + 1));
+            if (m != NO_MATCH) {
+              res = Hit{st.uid, st.ulen, st.pos + 1, m};
+              hit = true;
             }
           }
           Hit cold = hit_none(NO_MATCH);
           bool cold_hit = false;
           if (valid) {
-            if (ss) {
-              u64 mmw;
-              u32 off;
-              chunk_minimizer(hf, hr, q, fw, rc, k, w, mmw, off);
-              cold_hit = sshash_k2u(ix, fw, rc, mmw, off, cold);
-            } else {
-              cold_hit = pfhash_k2u(ix, fw, rc, cold);
-            }
+            cold_hit = SS ? verify_sshash<FAMILY>(ix, S, q, fw, rc, cold) : pfhash_k2u_t<FAMILY>(ix, fw, rc, cold);
             if (!cold_hit) cold = hit_none(NO_MATCH);
             if (!hit && cold_hit) {
               res = cold;
@@ -353,7 +472,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
           if (hitmask == 0) {
             if (active) {
               if (valid) ++n_valid;
-              if (out) store_hit(out + slot0 + c0 + q, hit_none(valid ? (u32)NO_MATCH : (u32)SKIPPED));
+              if (o) store_hit(o + q, hit_none(valid ? (u32)NO_MATCH : (u32)SKIPPED));
             }
             i += 32;
             continue;
@@ -365,7 +484,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
           const u32 after = ~((2u << f) - 1u);  // lanes > f   (f == 31 -> 0)
           const u32 r2 = __popc(vmask & lt_mask & after);
           const bool ok_ext = lane > f && active && (!valid || (cold_hit && cold.unitig_id == uid_f && cold.pos == pos_f + 1 + r2));
-          u32 bad = __ballot_sync(0xffffffffu, lane > f && !ok_ext);
+          const u32 bad = __ballot_sync(0xffffffffu, lane > f && !ok_ext);
           const u32 g = bad ? (u32)(__ffs(bad) - 1) : 32u;  // first lane not committed
           if (lane < g && active) {
             Hit h;
@@ -378,21 +497,18 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
                 ++n_hit;
               }
             }
-            if (out) store_hit(out + slot0 + c0 + q, h);
+            if (o) store_hit(o + q, h);
           }
-          {
-            const u32 gm = g >= 32 ? 0xffffffffu : ((1u << g) - 1u);
-            const u32 committed_valid = vmask & gm & ~((1u << f) - 1u);  // valid lanes in [f, g)
-            const int last = 31 - __clz(committed_valid);
-            Hit src = (u32)last == f ? res : cold;
-            st.uid = __shfl_sync(0xffffffffu, src.unitig_id, last);
-            st.ulen = __shfl_sync(0xffffffffu, src.unitig_len, last);
-            st.pos = __shfl_sync(0xffffffffu, src.pos, last);
-            st.o = __shfl_sync(0xffffffffu, src.match, last);
-            st.warm = 1;
-            st.ustart = __ldg(ix.unitigs.starts + st.uid);  // uniform address: one broadcast load
-          }
-          (void)amask;
+          const u32 gm = g >= 32 ? 0xffffffffu : ((1u << g) - 1u);
+          const u32 committed_valid = vmask & gm & ~((1u << f) - 1u);  // valid lanes in [f, g)
+          const int last = 31 - __clz(committed_valid);
+          Hit src = (u32)last == f ? res : cold;
+          st.uid = __shfl_sync(0xffffffffu, src.unitig_id, last);
+          st.ulen = __shfl_sync(0xffffffffu, src.unitig_len, last);
+          st.pos = __shfl_sync(0xffffffffu, src.pos, last);
+          st.o = __shfl_sync(0xffffffffu, src.match, last);
+          st.warm = 1;
+          st.ustart = __ldg(ix.unitigs.starts + st.uid);  // uniform address: one broadcast load
           i += g;
         }
       }
@@ -401,9 +517,9 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
   // counters of src/bin/kphf/main.rs:282-284
   if (counts) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
-      n_hit += __shfl_xor_sync(0xffffffffu, n_hit, o);
+    for (int d = 16; d > 0; d >>= 1) {
+      n_valid += __shfl_xor_sync(0xffffffffu, n_valid, d);
+      n_hit += __shfl_xor_sync(0xffffffffu, n_hit, d);
     }
     if (lane == 0 && n_valid) {
       atomicAdd(counts + 0, (unsigned long long)n_valid);
@@ -419,13 +535,11 @@ __global__ void __launch_bounds__(QR_WARPS * 32) encode_reads_kernel(const __gri
                                                                      const u64* __restrict__ kmer_offsets, u64* __restrict__ out_fw,
                                                                      u64* __restrict__ out_rc, u64* __restrict__ out_mm, u32* __restrict__ out_off,
                                                                      u8* __restrict__ out_valid) {
-  __shared__ u64 s_hf[QR_WARPS][QR_BASES];
-  __shared__ u64 s_hr[QR_WARPS][QR_BASES];
+  __shared__ WarpStage s_stage[QR_WARPS];
   const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  WarpStage& S = s_stage[wib];
   const u32 k = ix.unitigs.k, w = ix.w;
   const bool ss = ix.k2u_kind == MAZU_K2U_SSHASH;
-  u64* hf = s_hf[wib];
-  u64* hr = s_hr[wib];
   for (u64 r = (u64)blockIdx.x * QR_WARPS + wib; r < n_reads; r += (u64)gridDim.x * QR_WARPS) {
     u64 beg, len, slot0;
     if (uniform_len) {
@@ -440,38 +554,30 @@ __global__ void __launch_bounds__(QR_WARPS * 32) encode_reads_kernel(const __gri
     const u8* seq = bases + beg;
     const u64 nk = len >= k ? len - k + 1 : 0;
     for (u64 c0 = 0; c0 < nk; c0 += QR_CHUNK) {
-      ChunkRegs c;
-      load_chunk(seq, len, c0, lane, c);
+      ChunkInfo ci;
       const u32 n_c = (u32)min((u64)QR_CHUNK, nk - c0);
-      if (ss) {
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < 5; ++t) {
-          u64 wf = chunk_window(c, t, lane, w);
-          hf[32 * t + lane] = mm_hash64(wf, ix.seed);
-          hr[32 * t + lane] = mm_hash64(revcomp(wf, w), ix.seed);
-        }
-        __syncwarp();
-      }
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        u32 p = 32 * t + lane;
-        if (p < n_c) {
-          u64 fw = 0, rc = 0, mmw = 0;
-          u32 off = 0;
-          bool valid = chunk_window_valid(c, t, lane, k);
-          if (valid) {
-            fw = chunk_window(c, t, lane, k);
-            rc = revcomp(fw, k);
-            if (ss) chunk_minimizer(hf, hr, p, fw, rc, k, w, mmw, off);
+      __syncwarp();
+      stage_encode(seq, len, c0, n_c, k, lane, S, ci);
+      __syncwarp();
+      if (ss) stage_buckets<MPHF_FAMILY_NATIVE>(ix, ci, lane, S);
+      for (u32 p = lane; p < n_c; p += 32) {
+        u64 fw = 0, rc = 0, mmw = 0;
+        u32 off = 0;
+        bool valid = chunk_valid(ci, p);
+        if (valid) {
+          fw = S.fw[p];
+          rc = revcomp(fw, k);
+          if (ss) {
+            off = S.off[p];
+            mmw = mm_word_of(fw, rc, off, k, w);
           }
-          u64 s = slot0 + c0 + p;
-          if (out_fw) out_fw[s] = fw;
-          if (out_rc) out_rc[s] = rc;
-          if (out_mm) out_mm[s] = mmw;
-          if (out_off) out_off[s] = off;
-          if (out_valid) out_valid[s] = valid ? 1 : 0;
         }
+        u64 s = slot0 + c0 + p;
+        if (out_fw) out_fw[s] = fw;
+        if (out_rc) out_rc[s] = rc;
+        if (out_mm) out_mm[s] = mmw;
+        if (out_off) out_off[s] = off;
+        if (out_valid) out_valid[s] = valid ? 1 : 0;
       }
     }
   }

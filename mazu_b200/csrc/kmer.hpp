@@ -55,17 +55,24 @@ MZ_HD u64 mulhi64(u64 a, u64 b) {
   return (u64)(((unsigned __int128)a * b) >> 64);
 #endif
 }
-MZ_HD u64 mum64(u64 a, u64 b) { return (a * b) ^ mulhi64(a, b); }
 
-// Minimizer order (DESIGN.md "Minimizer order v1"): a WyHash-v1-style mum mixer of the w-mer word.
-// Stands in for kmers::canonical_minimizer + wyhash 0.5.0 (not in the reference tree, parity
-// unpinned); k-mer->unitig results do not depend on it.
-MZ_HD u64 mm_hash64(u64 x, u64 seed) {
-  const u64 P0 = 0xa0761d6478bd642fULL, P1 = 0xe7037ed1a0b428dbULL, P4 = 0x1d8e4e27c47d124fULL;
-  u64 a = (x & 0xffffffffULL) ^ seed ^ P0;
-  u64 b = (x >> 32) ^ seed ^ P1;
-  return mum64(mum64(a, b), 8ULL ^ P4);
+// Minimizer order v2 (DESIGN.md "Minimizer order"): a seeded 32-bit multiplicative mixer of the
+// w-mer word.  A w-mer at offset ci (0..k-w, k-w <= 31) of the CANONICAL k-mer gets the key
+//     (mm_hash32(wmer) & 0xFFFFFFE0) | ci
+// and the minimizer is the w-mer with the smallest key (top 27 hash bits, ties -> leftmost).
+// Stands in for kmers::canonical_minimizer + wyhash 0.5.0 (neither is in the reference tree, so
+// no hash could be pinned); k-mer -> unitig results do not depend on it.
+MZ_HD u32 mm_hash32(u64 x, u64 seed) {
+  u32 h = ((u32)x ^ (u32)seed) * 0x85EBCA6Bu;
+  h ^= ((u32)(x >> 32) ^ (u32)(seed >> 32)) * 0xC2B2AE35u;
+  h ^= h >> 16;
+  h *= 0x7FEB352Du;
+  h ^= h >> 15;
+  h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return h;
 }
+static const u32 MM_KEY_MASK = 0xFFFFFFE0u;
 
 // murmur3 finaliser: the per-level hash of the native MPHF ("kphf" tables)
 MZ_HD u64 fmix64(u64 x) {
@@ -103,20 +110,14 @@ MZ_HD MinimizerResult canonical_minimizer_naive(u64 fw, u64 rc, u32 k, u32 w, u6
   bool fw_canon = fw <= rc;
   u64 c = fw_canon ? fw : rc;
   u64 wmask = kmer_mask(w);
-  u64 best_h = ~0ULL;
-  u64 best_w = 0;
-  u32 best_i = 0;
+  u32 best = 0xFFFFFFFFu;
   for (u32 i = 0; i + w <= k; ++i) {
-    u64 wm = (c >> (2 * i)) & wmask;
-    u64 h = mm_hash64(wm, seed);
-    if (i == 0 || h < best_h) {
-      best_h = h;
-      best_w = wm;
-      best_i = i;
-    }
+    u32 key = (mm_hash32((c >> (2 * i)) & wmask, seed) & MM_KEY_MASK) | i;
+    best = key < best ? key : best;
   }
+  u32 best_i = best & 31u;
   MinimizerResult r;
-  r.word = best_w;
+  r.word = (c >> (2 * best_i)) & wmask;
   r.offset = fw_canon ? best_i : (k - best_i - w);
   return r;
 }

@@ -159,20 +159,21 @@ inline void for_each_canonical_kmer(const u8* seq, u64 len, int k, F&& f) {
 
 // ------------------------------------------------------------------------------------
 // Minimizer order.  PARITY UNPINNED: stands in for kmers::Kmer::canonical_minimizer(w,&bh)
-// with bh = WyHashState(0) (kphf/mod.rs:32-52).  A WyHash-v1-style "mum" mixer of the
-// w-mer word; ties are broken towards the leftmost w-mer of the canonical k-mer.
-// Definition (sshash.rs:32-37): mini(g*) = mini(min(g, g')), i.e. the minimizer of the
-// CANONICAL k-mer string; `offset` is its offset inside the canonical k-mer.
+// with bh = WyHashState(seed) (kphf/mod.rs:32-52); neither `kmers` nor `wyhash` is in the
+// reference tree.  Order v2 (shared definition): the w-mer at offset ci of the
+// CANONICAL k-mer has key (mm_hash32(wmer) & 0xFFFFFFE0) | ci; the smallest key wins (top 27
+// hash bits, ties -> leftmost).  Definition of "canonical minimizer" (sshash.rs:32-37):
+// mini(g*) = mini(min(g, g')).
 // ------------------------------------------------------------------------------------
-inline u64 mum64(u64 a, u64 b) {
-  __uint128_t r = (__uint128_t)a * b;
-  return (u64)r ^ (u64)(r >> 64);
-}
-inline u64 mm_hash64(u64 x, u64 seed) {
-  const u64 P0 = 0xa0761d6478bd642fULL, P1 = 0xe7037ed1a0b428dbULL, P4 = 0x1d8e4e27c47d124fULL;
-  u64 a = (x & 0xffffffffULL) ^ seed ^ P0;
-  u64 b = (x >> 32) ^ seed ^ P1;
-  return mum64(mum64(a, b), 8 ^ P4);
+inline u32 mm_hash32(u64 x, u64 seed) {
+  u32 h = ((u32)x ^ (u32)seed) * 0x85EBCA6Bu;
+  h ^= ((u32)(x >> 32) ^ (u32)(seed >> 32)) * 0xC2B2AE35u;
+  h ^= h >> 16;
+  h *= 0x7FEB352Du;
+  h ^= h >> 15;
+  h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return h;
 }
 struct Minimizer {
   u64 word;    // w-mer word as read off the canonical k-mer
@@ -186,12 +187,12 @@ inline Minimizer canonical_minimizer(u64 fw_word, int k, int w, u64 seed) {
   const bool fw_canon = fw_word <= rc;
   const u64 wmask = kmer_mask(w);
   Minimizer best{0, 0};
-  u64 best_h = 0;
-  for (int i = 0; i + w <= k; ++i) {  // i = offset inside the canonical k-mer; leftmost minimum wins
+  u32 best_key = 0;
+  for (int i = 0; i + w <= k; ++i) {  // i = offset inside the canonical k-mer
     u64 wm = (c >> (2 * i)) & wmask;
-    u64 h = mm_hash64(wm, seed);
-    if (i == 0 || h < best_h) {
-      best_h = h;
+    u32 key = (mm_hash32(wm, seed) & 0xFFFFFFE0u) | (u32)i;
+    if (i == 0 || key < best_key) {
+      best_key = key;
       best = Minimizer{wm, fw_canon ? (u64)i : (u64)(k - i - w)};
     }
   }

@@ -52,7 +52,7 @@ def lib():
             "orc_decode_piscem": (None, [u64, u64, u64, vp]),
             "orc_required_num_bits": (i32, [u64, u64, vp]),
             "orc_revcomp": (u64, [u64, i32]),
-            "orc_mm_hash64": (u64, [u64, u64]),
+            "orc_mm_hash32": (u64, [u64, u64]),
             "orc_canonical_minimizer": (None, [u64, i32, i32, u64, vp, vp]),
             "orc_encode_read": (u64, [vp, u64, i32, i32, u64, vp, vp, vp, vp, vp]),
             "orc_dense_index_load": (vp, [cp]),
