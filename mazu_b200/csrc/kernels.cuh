@@ -36,10 +36,11 @@ __device__ __forceinline__ u32 word_equivalency(u64 fw, u64 rc, u64 kw) {
 
 // K2UPos from a verified useq position: pos_to_id, unitig_len, unitig_start_pos (+ the boundary
 // guard of src/kphf/sshash.rs:513-514,539-541 when `guard` is set)
-__device__ __forceinline__ bool finish_hit(const UnitigsView& u, u64 km_pos, u32 mt, bool guard, Hit& out) {
+__device__ __forceinline__ bool finish_hit(const UnitigsView& u, u64 km_pos, u32 mt, bool guard, Hit& out, u64* ustart = nullptr) {
   u64 id, start, end;
   unitig_locate(u, km_pos, id, start, end);
   if (guard && km_pos + u.k > end) return false;
+  if (ustart) *ustart = start;
   out.unitig_id = (u32)id;
   out.unitig_len = (u32)(end - start);
   out.pos = (u32)(km_pos - start);
@@ -290,7 +291,7 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
 
 // stage V for one k-mer of an SSHash index: the loop of sshash.rs:494-552 / k2u_skew_index
 template <u32 FAMILY>
-__device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpStage& S, u32 p, u64 fw, u64 rc, Hit& out) {
+__device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpStage& S, u32 p, u64 fw, u64 rc, Hit& out, u64* ustart = nullptr) {
   const u32 lp = S.leader[p];
   const u32 n = S.bn[lp];
   if (n == 0) return false;
@@ -303,7 +304,7 @@ __device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpSta
     u64 pos = packed_get(ix.skew_pos, hs);
     u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, pos));
     if (mt == NO_MATCH) return false;
-    return finish_hit(ix.unitigs, pos, mt, false, out);
+    return finish_hit(ix.unitigs, pos, mt, false, out, ustart);
   }
   const u64 pos_start = S.bstart[lp];
   const u64 offset = S.off[p];
@@ -315,19 +316,19 @@ __device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpSta
     if (mm_pos >= offset && mm_pos - offset <= last_km_start_pos) {  // sshash.rs:498
       u64 km_pos = mm_pos - offset;
       u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, km_pos));
-      if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out)) return true;
+      if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out, ustart)) return true;
     }
     if (rc_offset != offset && mm_pos >= rc_offset && mm_pos - rc_offset <= last_km_start_pos) {  // sshash.rs:527 (same window when equal)
       u64 km_pos = mm_pos - rc_offset;
       u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, km_pos));
-      if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out)) return true;
+      if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out, ustart)) return true;
     }
   }
   return false;
 }
 
 template <u32 FAMILY>
-__device__ __forceinline__ bool pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc, Hit& out) {
+__device__ __forceinline__ bool pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc, Hit& out, u64* ustart = nullptr) {
   u64 word = fw <= rc ? fw : rc;
   u64 h;
   if (!mphf_lookup_t<FAMILY>(ix.mphf, word, h)) return false;
@@ -335,7 +336,7 @@ __device__ __forceinline__ bool pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc
   u64 km_pos = packed_get(ix.pos, h);
   u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, km_pos));
   if (mt == NO_MATCH) return false;
-  return finish_hit(ix.unitigs, km_pos, mt, false, out);
+  return finish_hit(ix.unitigs, km_pos, mt, false, out, ustart);
 }
 
 struct StreamState {  // StreamingK2U { is_warm, prev_k2upos } (src/index/caching.rs:13-17)
@@ -448,67 +449,69 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
             stage_buckets<FAMILY>(ix, ci, lane, S);
             prepared = true;
           }
-          Hit res = hit_none(NO_MATCH);
-          bool hit = false;
-          if (valid && st.warm && lane > 0 && (u64)st.pos + 1 + k <= (u64)st.ulen) {
-            // same cursor lane 0 saw (earlier lanes are assumed misses): warm check against pos+1
-            u32 m = word_equivalency(fw, rc, useq_window(ix.unitigs, st.ustart + st.pos + 1));
-            if (m != NO_MATCH) {
-              res = Hit{st.uid, st.ulen, st.pos + 1, m};
-              hit = true;
-            }
-          }
+          // Every valid lane does its cold lookup C_j.  Hypothesis: each lane's answer IS its cold
+          // answer, so the cursor a lane sees is the cold hit of the nearest earlier hit lane (or the
+          // incoming cursor).  Each lane checks that in parallel by doing the warm test the reference
+          // would do against that cursor (caching.rs:73-97).  The first lane whose warm test lands
+          // somewhere else than its cold answer (only possible when canonical k-mers are duplicated)
+          // still commits -- its own cursor was right -- and the walk restarts after it.
           Hit cold = hit_none(NO_MATCH);
+          u64 cold_ustart = 0;
           bool cold_hit = false;
           if (valid) {
-            cold_hit = SS ? verify_sshash<FAMILY>(ix, S, q, fw, rc, cold) : pfhash_k2u_t<FAMILY>(ix, fw, rc, cold);
+            cold_hit = SS ? verify_sshash<FAMILY>(ix, S, q, fw, rc, cold, &cold_ustart) : pfhash_k2u_t<FAMILY>(ix, fw, rc, cold, &cold_ustart);
             if (!cold_hit) cold = hit_none(NO_MATCH);
-            if (!hit && cold_hit) {
-              res = cold;
-              hit = true;
+          }
+          const u32 chm = __ballot_sync(0xffffffffu, cold_hit);
+          const u32 before = chm & lt_mask;
+          const int prev = before ? 31 - __clz(before) : 0;
+          u32 s_uid = __shfl_sync(0xffffffffu, cold.unitig_id, prev);
+          u32 s_ulen = __shfl_sync(0xffffffffu, cold.unitig_len, prev);
+          u32 s_pos = __shfl_sync(0xffffffffu, cold.pos, prev);
+          u64 s_ustart = __shfl_sync(0xffffffffu, cold_ustart, prev);
+          bool s_warm = before != 0;
+          if (!before) {
+            s_uid = st.uid;
+            s_ulen = st.ulen;
+            s_pos = st.pos;
+            s_ustart = st.ustart;
+            s_warm = st.warm;
+          }
+          Hit res = cold;
+          bool res_hit = cold_hit;
+          bool differs = false;
+          if (valid && s_warm && (u64)s_pos + 1 + k <= (u64)s_ulen &&
+              !(cold_hit && cold.unitig_id == s_uid && cold.pos == s_pos + 1)) {
+            u32 m = word_equivalency(fw, rc, useq_window(ix.unitigs, s_ustart + s_pos + 1));
+            if (m != NO_MATCH) {  // the walk answers here although the cold lookup answered elsewhere (or missed)
+              res = Hit{s_uid, s_ulen, s_pos + 1, m};
+              res_hit = true;
+              differs = true;
             }
           }
-          const u32 hitmask = __ballot_sync(0xffffffffu, hit);
-          if (hitmask == 0) {
-            if (active) {
-              if (valid) ++n_valid;
-              if (o) store_hit(o + q, hit_none(valid ? (u32)NO_MATCH : (u32)SKIPPED));
-            }
-            i += 32;
-            continue;
-          }
-          const u32 f = (u32)(__ffs(hitmask) - 1);
-          const u32 uid_f = __shfl_sync(0xffffffffu, res.unitig_id, f);
-          const u32 pos_f = __shfl_sync(0xffffffffu, res.pos, f);
-          // lanes after f commit their cold result iff it is exactly the warm extension of the cursor
-          const u32 after = ~((2u << f) - 1u);  // lanes > f   (f == 31 -> 0)
-          const u32 r2 = __popc(vmask & lt_mask & after);
-          const bool ok_ext = lane > f && active && (!valid || (cold_hit && cold.unitig_id == uid_f && cold.pos == pos_f + 1 + r2));
-          const u32 bad = __ballot_sync(0xffffffffu, lane > f && !ok_ext);
-          const u32 g = bad ? (u32)(__ffs(bad) - 1) : 32u;  // first lane not committed
+          const u32 dm = __ballot_sync(0xffffffffu, differs);
+          const u32 g = dm ? (u32)__ffs(dm) : 32u;  // lanes [0, g) commit (g includes the first differing lane)
           if (lane < g && active) {
-            Hit h;
+            Hit h = res;
             if (!valid) h = hit_none(SKIPPED);
             else {
               ++n_valid;
-              if (lane < f) h = hit_none(NO_MATCH);
-              else {
-                h = lane == f ? res : cold;
-                ++n_hit;
-              }
+              if (res_hit) ++n_hit;
             }
             if (o) store_hit(o + q, h);
           }
           const u32 gm = g >= 32 ? 0xffffffffu : ((1u << g) - 1u);
-          const u32 committed_valid = vmask & gm & ~((1u << f) - 1u);  // valid lanes in [f, g)
-          const int last = 31 - __clz(committed_valid);
-          Hit src = (u32)last == f ? res : cold;
-          st.uid = __shfl_sync(0xffffffffu, src.unitig_id, last);
-          st.ulen = __shfl_sync(0xffffffffu, src.unitig_len, last);
-          st.pos = __shfl_sync(0xffffffffu, src.pos, last);
-          st.o = __shfl_sync(0xffffffffu, src.match, last);
-          st.warm = 1;
-          st.ustart = __ldg(ix.unitigs.starts + st.uid);  // uniform address: one broadcast load
+          const u32 hm = __ballot_sync(0xffffffffu, res_hit) & gm;
+          if (hm) {  // cursor = last committed hit (a miss leaves it untouched, caching.rs:100)
+            const int last = 31 - __clz(hm);
+            u64 us = differs ? s_ustart : cold_ustart;
+            st.uid = __shfl_sync(0xffffffffu, res.unitig_id, last);
+            st.ulen = __shfl_sync(0xffffffffu, res.unitig_len, last);
+            st.pos = __shfl_sync(0xffffffffu, res.pos, last);
+            st.o = __shfl_sync(0xffffffffu, res.match, last);
+            st.ustart = __shfl_sync(0xffffffffu, us, last);
+            st.warm = 1;
+          }
           i += g;
         }
       }
