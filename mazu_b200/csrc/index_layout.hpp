@@ -61,32 +61,53 @@ MZ_HD void native_slot(u64 key, u32 level, u64 n_blocks, u64& blk, u32& bit) {
   bit = mulhi32((u32)h, MPHF_BLOCK_BITS);
 }
 
-MZ_HD bool ranked_probe(const RankedLevels& m, u32 level, u64 blk, u32 bit, u64& out) {
+// bit test of one slot: reads a single u32 of the block
+MZ_HD bool ranked_test(const RankedLevels& m, u32 level, u64 blk, u32 bit) {
   const u32* b = m.blocks + (m.block_off[level] + blk) * 8;
-  u32 wi = 1 + (bit >> 5), sh = bit & 31;
-  u32 word = MZ_LDG(b + wi);
-  if (!((word >> sh) & 1u)) return false;
-  u32 r = MZ_LDG(b) + MZ_POPC(word & ((1u << sh) - 1u));
+  return (MZ_LDG(b + 1 + (bit >> 5)) >> (bit & 31)) & 1u;
+}
+// rank of a set slot: block header + popcounts inside the same 32-byte block
+MZ_HD u64 ranked_rank(const RankedLevels& m, u32 level, u64 blk, u32 bit) {
+  const u32* b = m.blocks + (m.block_off[level] + blk) * 8;
+#if defined(__CUDA_ARCH__)
+  const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(b));
+  const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(b) + 1);
+  const u32 w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#else
+  const u32* w = b;
+#endif
+  const u32 wi = 1 + (bit >> 5), sh = bit & 31;
+  u32 r = w[0];
 #pragma unroll
-  for (u32 j = 1; j < 7; ++j)
-    if (j < wi) r += MZ_POPC(MZ_LDG(b + j));
-  out = m.rank_base[level] + r;
-  return true;
+  for (u32 j = 1; j < 8; ++j) {
+    u32 x = w[j];
+    if (j == wi) x &= (1u << sh) - 1u;
+    if (j <= wi) r += MZ_POPC(x);
+  }
+  return m.rank_base[level] + r;
 }
 
 // MPHF::try_hash_u64 (src/kphf/mod.rs:54-56).  BOOPHF reproduces BooPHF<u64>::lookup
 // (src/pf1/boophf/mod.rs:96-181) bit-exactly; NATIVE is this library's own BBHash-style MPHF.
 // Like boomphf::try_hash, a non-member key may return a false-positive value < n_keys.
-// Templated on the family so a kernel only carries the code of the family it serves.
+// Templated on the family so a kernel only carries the code of the family it serves.  The level
+// loop only tests bits (divergent lanes leave at different levels); the rank is taken once after it.
 template <u32 FAMILY>
 MZ_HD bool mphf_lookup_t(const RankedLevels& m, u64 key, u64& out) {
+  u32 hit_level = MPHF_MAX_LEVELS, hit_bit = 0;
+  u64 hit_blk = 0;
   if (FAMILY == MPHF_FAMILY_NATIVE) {
 #pragma unroll 1
     for (u32 l = 0; l < m.n_levels; ++l) {
       u64 blk;
       u32 bit;
       native_slot(key, l, m.size[l], blk, bit);
-      if (ranked_probe(m, l, blk, bit, out)) return true;
+      if (ranked_test(m, l, blk, bit)) {
+        hit_level = l;
+        hit_blk = blk;
+        hit_bit = bit;
+        break;
+      }
     }
   } else {
     u64 s0 = BOOPHF_SEED0, s1 = BOOPHF_SEED1;  // MultiHashState (src/pf1/boophf/hash.rs:91-97)
@@ -110,8 +131,17 @@ MZ_HD bool mphf_lookup_t(const RankedLevels& m, u64 key, u64& out) {
       u64 pos = mulhi64(h, m.size[l]);  // fast_range_64 (mod.rs:136-144)
       u64 blk = pos / MPHF_BLOCK_BITS;
       u32 bit = (u32)(pos - blk * MPHF_BLOCK_BITS);
-      if (ranked_probe(m, l, blk, bit, out)) return true;
+      if (ranked_test(m, l, blk, bit)) {
+        hit_level = l;
+        hit_blk = blk;
+        hit_bit = bit;
+        break;
+      }
     }
+  }
+  if (hit_level < MPHF_MAX_LEVELS) {
+    out = ranked_rank(m, hit_level, hit_blk, hit_bit);
+    return true;
   }
   // lookup_in_final_hash (mod.rs:177-181) / native leftovers
   u32 lo = 0, hi = m.n_fb;
@@ -184,12 +214,17 @@ MZ_HD u32 select128(u64 lo, u64 hi, u32 j) {
     x = wh;
     base += 32;
   }
-#if defined(__CUDA_ARCH__)
-  return base + __fns(x, 0, (int)j + 1);
-#else
-  for (u32 t = 0; t < j; ++t) x &= x - 1;
-  return base + (u32)__builtin_ctz(x);
-#endif
+  // j-th set bit of the 32-bit word x by halving (popcount binary search; __fns is a 32-step loop)
+  u32 pos = 0;
+#pragma unroll
+  for (u32 width = 16; width >= 1; width >>= 1) {
+    u32 c2 = (u32)MZ_POPC((x >> pos) & ((1u << width) - 1u));
+    if (j >= c2) {
+      j -= c2;
+      pos += width;
+    }
+  }
+  return base + pos;
 }
 
 // returns x_i in `a` and x_{i+1} in `b`; requires i + 1 < n
