@@ -1,19 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- k-mer lookups/s of the batched query path on N B200s (one process per GPU).
 
-Workload (BASELINE.json configs[1], the configuration the metric is quoted on): SSHash rebuilt from
-the yeast chr01 unitigs of tests/data/pf1/yeast_chr01_index (k=31, w=15, skew 32, hash seed 0), queried
-in random-access mode with synthetic 150 bp reads: 50 % sampled from the 230,218 bp reference on a
-random strand, 50 % uniform random ACGT.  One "step" = one pass of the hot path (encode -> canonical
-k-mers -> minimizers -> MPHF -> bucket bounds -> positions -> verify -> unitig id/offset/orientation)
-over one batch of --reads reads per GPU (default 10 M reads = 1.2e9 k-mer lookups).  Multi-GPU:
-index replicated, reads sharded (each rank its own batch, weak scaling), no data-path collective.
+Default workload (BASELINE.json configs[1], the configuration the metric is quoted on): SSHash rebuilt
+from the yeast chr01 unitigs of tests/data/pf1/yeast_chr01_index (k=31, w=15, skew 32, hash seed 0),
+queried in random-access mode with synthetic 150 bp reads: 50 % sampled from the 230,218 bp reference
+on a random strand, 50 % uniform random ACGT.  One "step" = one pass of the hot path (encode ->
+canonical k-mers -> minimizers -> MPHF -> bucket bounds -> positions -> verify -> unitig id / offset /
+orientation) over one batch of --reads reads per GPU (default 10 M reads = 1.2e9 k-mer lookups).
+Multi-GPU: index replicated, reads sharded (each rank its own batch, weak scaling), no data-path
+collective; one all_reduce of three counters after the timed region.
 
-  value      whole-job lookups/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e        same metric through the C ABI with HOST (pinned) buffers: H2D of the reads and D2H of every
-             16-byte hit record inside the timed region
-  roofline   dominant kernel (query_reads_kernel<0>): algorithmic bytes (273.25 B/lookup for an
-             SSHash random lookup) / measured kernel time vs MEASURED_PEAKS.json hbm_gbs
+Other workloads (--workload), same JSON line:
+  config3        the same index through .as_streaming(): 70 % reference-sampled reads with 1 % substitutions / 30 % random
+  config1        pufferfish yeast_chr01 DenseIndex (PFHash + C++ BooPHF): all reference + unitig k-mers, shuffled, via k2u_batch
+  config4        U2Pos occurrence decode on a synthetic high-multiplicity unitig table (metric: occurrences/s)
+  config5        synthetic unitig set (len 31+Geom(68)), SSHash k=31 w=19 skew 64, --scale 1.0 = 36,145,130 unitigs / ~2.5e9 k-mers;
+                 index >> L2, reads generated on the device (70/30 mix); --mode random|streaming
+  config5-kmers  the same index queried with a flat batch of random-order k-mers (k2u_batch): the random-access HBM regime
+
+  value      whole-job units/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e        same metric through the C ABI with HOST (pinned) buffers: H2D of the inputs and D2H of every result record
+  roofline   dominant kernel: algorithmic bytes / measured kernel time vs the measured peak
   cpu_baseline   the CPU oracle (a C++ port of mazu's query path; the Rust reference cannot be built here)
              timed on this box's host cores on a bounded sample of the same workload
 
@@ -34,11 +41,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 
 YEAST = os.path.join(ROOT, "tests", "data", "pf1", "yeast_chr01_index")
-K, W, SKEW, SEED = 31, 15, 32, 0
 READ_LEN = 150
-ALG_BYTES_PER_LOOKUP = 273.25  # 8 sectors * 32 B + 17.25 B stream (SSHash random lookup)
+ALG_SSHASH = 273.25   # 8 sectors * 32 B + 17.25 B stream per SSHash random lookup
+ALG_PFHASH = 209.25   # 6 sectors + 17.25 B
 METRIC = "k-mer lookups/sec (pos+neg, bit-exact)"
 UNIT = "lookups/s"
+HUMAN_UNITIGS = 36_145_130
 
 
 def parse_args():
@@ -47,26 +55,18 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mazu_b200", choices=["mazu_b200", "reference"])
-    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
-    ap.add_argument("--mode", default="random", choices=["random", "streaming"])
+    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3", "config4", "config5", "config5-kmers"])
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads (or k-mers / 120, or unitig queries) per GPU per step")
+    ap.add_argument("--mode", default=None, choices=["random", "streaming"])
+    ap.add_argument("--scale", type=float, default=0.1, help="config5: fraction of the human-scale unitig count")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU seconds for the cpu_baseline sample")
-    return ap.parse_args()
-
-
-def config_dict(args, n_gpus):
-    return {
-        "workload": "configs[1]: SSHash(yeast chr01 unitigs, k=31, m=15, skew=32, seed 0) random-access queries of "
-                    "%d synthetic 150bp reads per GPU (50%% reference-sampled random strand / 50%% uniform random)" % args.reads,
-        "mode": args.mode,
-        "reads_per_gpu": args.reads,
-        "read_len": READ_LEN,
-        "lookups_per_step_per_gpu": args.reads * (READ_LEN - K + 1),
-        "parallelism": "index replicated x%d, reads sharded by batch, no collective" % n_gpus,
-        "l2_policy": "inputs (%.2f GB of reads + %.1f GB of results per step) are larger than the 126 MB L2" %
-                     (args.reads * READ_LEN / 1e9, args.reads * (READ_LEN - K + 1) * 16 / 1e9),
-    }
+    ap.add_argument("--validate", action="store_true", help="config5: also run k2u_validate_self on the device (every unitig k-mer)")
+    a = ap.parse_args()
+    if a.mode is None:
+        a.mode = "streaming" if a.workload == "config3" else "random"
+    return a
 
 
 class ClockSampler:
@@ -89,10 +89,11 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.1)
 
     def __enter__(self):
         self.th.start()
+        time.sleep(0.25)
         return self
 
     def __exit__(self, *a):
@@ -100,41 +101,50 @@ class ClockSampler:
         self.th.join(timeout=6)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in self.rows if r and num(r[0]) is not None]
+        mx = [num(r[1]) for r in self.rows if len(r) > 1 and num(r[1]) is not None]
+        pw = [num(r[2]) for r in self.rows if len(r) > 2 and num(r[2]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
+                "reasons": reasons, "samples": len(self.rows)}
 
 
-def load_oracle_index():
+# ------------------------------------------------------------------------------------------------
+# oracle helpers (checker + CPU baseline; never on the timed GPU path)
+# ------------------------------------------------------------------------------------------------
+def load_oracle_yeast(sshash=True):
     import _oracle
     o = _oracle.OracleIndex.dense_from_pf1(YEAST)
-    return o, o.rebuild_k2u(1, w=W, skew=SKEW, seed=SEED)
+    return o, (o.rebuild_k2u(1, w=15, skew=32, seed=0) if sshash else o)
 
 
-def ref_codes_from_oracle(o):
+def yeast_ref_codes(o):
     import _gen
     return _gen.unpack_2bit(o.refseq_words(), int(o.ref_prefix()[-1]))
 
 
-def cpu_sample_reads(ref_codes, n_reads, seed, mode):
+def mix_of(mode):
+    return (0.5, 0.0) if mode == "random" else (0.7, 0.01)
+
+
+def time_oracle_reads(os_idx, ref_codes, target_seconds, mode, threads, k, seed=4242):
+    """CPU port on a bounded sample: calibrate on 20k reads, then size the sample for ~target_seconds."""
     import _gen
-    return _gen.sample_reads_fast(ref_codes, n_reads, READ_LEN, seed, frac_ref=0.5 if mode == "random" else 0.7,
-                                  sub_rate=0.0 if mode == "random" else 0.01)
-
-
-def time_oracle(os_idx, ref_codes, target_seconds, mode, threads, seed=4242):
-    """CPU port timed on a bounded sample: calibrate on 20k reads, then size the sample for ~target_seconds."""
+    frac_ref, sub = mix_of(mode)
     streaming = mode == "streaming"
-    cal = cpu_sample_reads(ref_codes, 20000, seed, mode)
+    cal = _gen.sample_reads_fast(ref_codes, 20000, READ_LEN, seed, frac_ref, sub)
     offs = np.arange(20001, dtype=np.uint64) * READ_LEN
     t0 = time.time()
     _, c, _ = os_idx.query_reads(cal, offs, streaming=streaming, want_hits=False, n_threads=threads)
     rate = float(c[0]) / max(time.time() - t0, 1e-6)
-    n_reads = int(min(2_000_000, max(20000, rate * target_seconds / (READ_LEN - K + 1))))
-    bases = cpu_sample_reads(ref_codes, n_reads, seed + 1, mode)
+    n_reads = int(min(2_000_000, max(20000, rate * target_seconds / (READ_LEN - k + 1))))
+    bases = _gen.sample_reads_fast(ref_codes, n_reads, READ_LEN, seed + 1, frac_ref, sub)
     offs = np.arange(n_reads + 1, dtype=np.uint64) * READ_LEN
     t0 = time.time()
     _, c, _ = os_idx.query_reads(bases, offs, streaming=streaming, want_hits=True, n_threads=threads)
@@ -143,23 +153,25 @@ def time_oracle(os_idx, ref_codes, target_seconds, mode, threads, seed=4242):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path.  The Rust crate cannot be built
-    in this image (no cargo/rustc, four un-vendored crates), so this arm runs the C++ port (oracle/)
-    with all host threads; each step is a bounded sample of the workload."""
+    """--impl reference: the reference's CPU implementation of the path.  The Rust crate cannot be built in
+    this image (no cargo/rustc, four un-vendored crates), so this arm runs the C++ port (oracle/) with all
+    host threads on the default workload's index; each step is a bounded sample of the workload."""
     if rank != 0:
         return
-    o, os_idx = load_oracle_index()
-    ref_codes = ref_codes_from_oracle(o)
+    import _gen
+    o, os_idx = load_oracle_yeast(sshash=args.workload != "config1")
+    ref_codes = yeast_ref_codes(o)
     threads = os.cpu_count() or 1
     streaming = args.mode == "streaming"
-    # size one step for ~cpu_seconds / 2 of work
-    cal = cpu_sample_reads(ref_codes, 20000, 99, args.mode)
+    frac_ref, sub = mix_of(args.mode)
+    k = os_idx.k
+    cal = _gen.sample_reads_fast(ref_codes, 20000, READ_LEN, 99, frac_ref, sub)
     offs = np.arange(20001, dtype=np.uint64) * READ_LEN
     t0 = time.time()
     _, c, _ = os_idx.query_reads(cal, offs, streaming=streaming, want_hits=False, n_threads=threads)
     rate = float(c[0]) / max(time.time() - t0, 1e-6)
-    n_reads = int(min(args.reads, max(20000, rate * 4.0 / (READ_LEN - K + 1))))
-    bases = cpu_sample_reads(ref_codes, n_reads, 42, args.mode)
+    n_reads = int(min(args.reads, max(20000, rate * 4.0 / (READ_LEN - k + 1))))
+    bases = _gen.sample_reads_fast(ref_codes, n_reads, READ_LEN, 42, frac_ref, sub)
     offs = np.arange(n_reads + 1, dtype=np.uint64) * READ_LEN
     for _ in range(args.warmup):
         os_idx.query_reads(bases[:READ_LEN * 20000], offs[:20001], streaming=streaming, want_hits=True, n_threads=threads)
@@ -170,11 +182,11 @@ def run_reference(args, rank, world):
         total += int(c[0])
     dt = time.time() - t0
     v = total / dt
-    sample = "%d reads x %d bp (%d lookups) per step, %d steps" % (n_reads, READ_LEN, n_reads * (READ_LEN - K + 1), args.steps)
+    sample = "%d reads x %d bp (%d lookups) per step, %d steps" % (n_reads, READ_LEN, n_reads * (READ_LEN - k + 1), args.steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-        "data": "synthetic", "config": config_dict(args, args.gpus),
+        "data": "synthetic", "config": {"workload": workload_name(args), "mode": args.mode, "read_len": READ_LEN},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "note": "C++ restatement of mazu's query path (oracle/); the Rust reference cannot be built in this image"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -183,18 +195,29 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def workload_name(args):
+    return {
+        "config1": "configs[0]: pufferfish yeast_chr01 DenseIndex (PFHash + BooPHF): all reference k-mers + unitig fw/rc k-mers, shuffled (seed 1), k2u_batch",
+        "config2": "configs[1]: SSHash(yeast chr01 unitigs, k=31, m=15, skew=32, seed 0) random-access queries of %d synthetic 150bp reads per GPU "
+                   "(50%% reference-sampled random strand / 50%% uniform random)" % args.reads,
+        "config3": "configs[2]: same SSHash index via as_streaming(), %d synthetic 150bp reads per GPU (70%% reference-sampled with 1%% substitutions / 30%% random)" % args.reads,
+        "config4": "configs[3]: u2pos occurrence decode, synthetic table (4096 refs, max ref 2^27, Zipf(1.2) multiplicity <= 65536), queries ~ multiplicity",
+        "config5": "configs[4]: synthetic unitig set scale %.3g (%d unitigs, len 31+Geom(68)), SSHash k=31 w=19 skew 64, %d synthetic 150bp reads per GPU (70/30 mix)" %
+                   (args.scale, int(HUMAN_UNITIGS * args.scale), args.reads),
+        "config5-kmers": "configs[4] index (scale %.3g) queried with a flat random-order k-mer batch (50%% present / 50%% random), k2u_batch" % args.scale,
+    }[args.workload]
+
+
 def main():
     args = parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.gpus > 1 and world == 1 and "RANK" not in os.environ:
-        # launched without torchrun: re-launch one process per GPU
-        port = 29500 + (os.getpid() % 2000)
+        port = 29500 + (os.getpid() % 2000)  # launched without torchrun: re-launch one process per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
                "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -211,57 +234,240 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    mode = mz.MODE_RANDOM if args.mode == "random" else mz.MODE_STREAMING
-    # ---- index: pufferfish yeast_chr01 unitigs -> SSHash::from_unitig_set(k=31, w=15, skew 32, seed 0), replicated per GPU
-    dense = mz.DenseIndex.deserialize_from_cpp(YEAST, device=local_rank)
-    index = dense.rebuild_k2u(mz.K2U_SSHASH, w=W, skew_param=SKEW, seed=SEED)
-    assert index.k == K
-
-    # ---- synthetic reads, generated on the device (seed 42 + rank); reference codes from refseq.bin
-    import _oracle  # only the host-side fixture reader + checker; never on the timed path
-    o, os_idx = load_oracle_index() if rank == 0 else (None, None)
-    if rank == 0:
-        ref_codes = ref_codes_from_oracle(o)
-    else:
-        oo = _oracle.OracleIndex.dense_from_pf1(YEAST)
-        ref_codes = ref_codes_from_oracle(oo)
-        del oo
-    n_reads = args.reads
-    nk_per_read = READ_LEN - K + 1
-    n_lookups = n_reads * nk_per_read
+    stream = torch.cuda.current_stream()
     gen = torch.Generator(device=dev)
     gen.manual_seed(42 + rank)
-    ref_t = torch.from_numpy(ref_codes.astype(np.uint8)).to(dev)
-    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
-    comp = torch.tensor([3, 2, 1, 0], dtype=torch.uint8, device=dev)
-    frac_ref = 0.5 if args.mode == "random" else 0.7
-    sub_rate = 0.0 if args.mode == "random" else 0.01
-    bases = torch.empty(n_reads * READ_LEN, dtype=torch.uint8, device=dev)
-    CH = 1_000_000
-    ar = torch.arange(READ_LEN, device=dev)
-    for r0 in range(0, n_reads, CH):
-        n = min(CH, n_reads - r0)
-        starts = torch.randint(0, len(ref_codes) - READ_LEN + 1, (n,), generator=gen, device=dev)
-        codes = ref_t[starts[:, None] + ar[None, :]]
-        strand = torch.rand(n, generator=gen, device=dev) < 0.5
-        rc = comp[codes.flip(1).long()]
-        codes = torch.where(strand[:, None], rc, codes)
-        is_ref = torch.rand(n, generator=gen, device=dev) < frac_ref
-        rnd = torch.randint(0, 4, (n, READ_LEN), generator=gen, device=dev, dtype=torch.uint8)
-        codes = torch.where(is_ref[:, None], codes, rnd)
-        if sub_rate > 0:
-            m = torch.rand((n, READ_LEN), generator=gen, device=dev) < sub_rate
-            codes = torch.where(m, (codes + torch.randint(1, 4, (n, READ_LEN), generator=gen, device=dev, dtype=torch.uint8)) & 3, codes)
-        bases[r0 * READ_LEN:(r0 + n) * READ_LEN] = acgt[codes.long()].reshape(-1)
-    del ref_t
-    hits = torch.empty((n_lookups, 4), dtype=torch.int32, device=dev)
-    counts = torch.zeros(3, dtype=torch.int64, device=dev)
-    stream = torch.cuda.current_stream()
+    mode = mz.MODE_RANDOM if args.mode == "random" else mz.MODE_STREAMING
+    frac_ref, sub_rate = mix_of(args.mode)
+    W = args.workload
+    info = {}
+    unit, metric = UNIT, METRIC
+    check = None          # callable -> bool : parity spot check (rank 0)
+    e2e_step = None       # callable: one end-to-end step through host buffers
+    e2e_bytes = (0, 0)
+    cpu_fn = None         # callable -> cpu_baseline dict
+    t_build = time.time()
 
-    def step():
-        index.query_reads(bases, None, n_reads=n_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=hits, counts=counts,
-                          mem=mz.MEM_DEVICE, stream=stream.cuda_stream)
+    # ---------------------------------------------------------------- indexes
+    if W in ("config1", "config2", "config3"):
+        dense = mz.DenseIndex.deserialize_from_cpp(YEAST, device=local_rank)
+        index = dense if W == "config1" else dense.rebuild_k2u(mz.K2U_SSHASH, w=15, skew_param=32, seed=0)
+        o, os_idx = load_oracle_yeast(sshash=W != "config1")
+        ref_codes = yeast_ref_codes(o)
+        alg = ALG_PFHASH if W == "config1" else ALG_SSHASH
+        peak_kind = "hbm"
+    elif W in ("config5", "config5-kmers"):
+        n_unitigs = max(1000, int(HUMAN_UNITIGS * args.scale))
+        words, n_bases, accum = _gen.synthetic_unitigs_packed(n_unitigs, 68, 31, seed=45)
+        us = mz.UnitigSet(31, words, n_bases, accum)
+        index = mz.SSHash.from_unitig_set(us, 19, 64, seed=0, device=local_rank)
+        info["index"] = {"n_unitigs": index.n_unitigs, "n_kmers": index.n_kmers, "sum_unitigs_len": index.sum_unitigs_len,
+                         "n_minimizers": index.n_minimizers, "n_kmers_in_skew_index": index.n_kmers_in_skew_index,
+                         "mphf_levels": index.info(mz.INFO_MPHF_LEVELS)}
+        useq_dev = torch.from_numpy(words.view(np.int64)).to(dev)
+        alg = ALG_SSHASH
+        peak_kind = "prand"
+    else:  # config4
+        k = 31
+        n_unitigs = 1_000_000
+        codes, accum = _gen.synthetic_unitigs(2000, 68, k, seed=44)  # the K2U half is irrelevant for the decode; keep it tiny
+        rng = np.random.default_rng(44)
+        us = mz.UnitigSet(k, mz.pack_2bit(codes), len(codes), accum)
+        # a unitig set with n_unitigs entries is needed for the offsets vector: build a trivial one
+        lens = np.full(n_unitigs, k, dtype=np.uint64)
+        accum4 = np.zeros(n_unitigs + 1, dtype=np.uint64)
+        np.cumsum(lens, out=accum4[1:])
+        words4 = rng.integers(0, np.iinfo(np.uint64).max, size=(2 * int(accum4[-1]) + 63) // 64, dtype=np.uint64)
+        index = mz.PFHash.from_unitig_set(mz.UnitigSet(k, words4, int(accum4[-1]), accum4), device=local_rank)
+        mult = np.minimum(rng.zipf(1.2, size=n_unitigs), 65536).astype(np.uint64)
+        offsets = np.zeros(n_unitigs + 1, dtype=np.uint64)
+        np.cumsum(mult, out=offsets[1:])
+        n_occ = int(offsets[-1])
+        n_refs, max_ref_len = 4096, 1 << 27
+        ref_ids = rng.integers(0, n_refs, size=n_occ, dtype=np.uint64)
+        poss = rng.integers(0, max_ref_len - 4096, size=n_occ, dtype=np.uint64)
+        fws = rng.integers(0, 2, size=n_occ, dtype=np.uint64)
+        pos_bits, ref_bits = 28, 13
+        enc = (ref_ids << np.uint64(pos_bits + 1)) | (poss << np.uint64(1)) | fws
+        index.attach_u2pos_piscem(mz.PackedVec.pack(enc, 1 + pos_bits + ref_bits), pos_bits + 1, (1 << pos_bits) - 1, mz.PackedVec.pack(offsets))
+        info["index"] = {"n_unitigs": n_unitigs, "n_occs": n_occ, "encoding": "piscem 42-bit packed"}
+        peak_kind = "hbm"
+    info["index_build_s"] = round(time.time() - t_build, 2)
+    info["index_device_bytes"] = index.device_bytes
+    K = index.k
+    nk_per_read = READ_LEN - K + 1
+
+    # ---------------------------------------------------------------- inputs + step closures
+    if W in ("config2", "config3", "config5"):
+        n_reads = args.reads
+        n_units = n_reads * nk_per_read
+        if W == "config5":
+            bases = _gen.device_reads_from_packed(torch, useq_dev, n_bases, n_reads, READ_LEN, gen, 0.7, 0.01)
+        else:
+            ref_t = torch.from_numpy(ref_codes.astype(np.uint8)).to(dev)
+            bases = torch.empty(n_reads * READ_LEN, dtype=torch.uint8, device=dev)
+            acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+            ar = torch.arange(READ_LEN, device=dev)
+            for r0 in range(0, n_reads, 1_000_000):
+                n = min(1_000_000, n_reads - r0)
+                starts = torch.randint(0, len(ref_codes) - READ_LEN + 1, (n,), generator=gen, device=dev)
+                codes = ref_t[starts[:, None] + ar[None, :]]
+                strand = torch.rand(n, generator=gen, device=dev) < 0.5
+                codes = torch.where(strand[:, None], 3 - codes.flip(1), codes)
+                is_ref = torch.rand(n, generator=gen, device=dev) < frac_ref
+                rnd = torch.randint(0, 4, (n, READ_LEN), generator=gen, device=dev, dtype=torch.uint8)
+                codes = torch.where(is_ref[:, None], codes, rnd)
+                if sub_rate > 0:
+                    m = torch.rand((n, READ_LEN), generator=gen, device=dev) < sub_rate
+                    codes = torch.where(m, (codes + torch.randint(1, 4, (n, READ_LEN), generator=gen, device=dev, dtype=torch.uint8)) & 3, codes)
+                bases[r0 * READ_LEN:(r0 + n) * READ_LEN] = acgt[codes.long()].reshape(-1)
+        hits = torch.empty((n_units, 4), dtype=torch.int32, device=dev)
+        counts = torch.zeros(3, dtype=torch.int64, device=dev)
+        kernel_name = "mazu::query_reads_kernel<%d,SSHASH,NATIVE>" % (0 if mode == mz.MODE_RANDOM else 1)
+        launches_per_step = 1
+
+        def step():
+            index.query_reads(bases, None, n_reads=n_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=hits, counts=counts,
+                              mem=mz.MEM_DEVICE, stream=stream.cuda_stream)
+
+        if not args.no_e2e:
+            h_bases = torch.empty(n_reads * READ_LEN, dtype=torch.uint8, pin_memory=True)
+            h_bases.copy_(bases)
+            h_hits = torch.empty((n_units, 4), dtype=torch.int32, pin_memory=True)
+            h_cnt = np.zeros(3, dtype=np.uint64)
+            hb = h_bases.numpy()
+
+            def e2e_step():
+                index.query_reads(hb, None, n_reads=n_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=h_hits, counts=h_cnt)
+
+            e2e_bytes = (n_reads * READ_LEN, n_units * 16 + 24)
+
+        def check():
+            if W == "config5":  # no oracle index at this scale: verify sampled hits directly against the packed sequence
+                n = min(n_reads, 20000)
+                h = hits[: n * nk_per_read].cpu().numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE)
+                b = bases[: n * READ_LEN].cpu().numpy()
+                lut = np.zeros(256, dtype=np.uint8)
+                for i, ch in enumerate(b"ACGT"):
+                    lut[ch] = i
+                rk = _gen.kmer_words_from_codes(lut[b], K)
+                slot = np.nonzero(h["match"] != 0)[0]
+                fw = rk[(slot // nk_per_read) * READ_LEN + (slot % nk_per_read)]
+                gpos = accum[h["unitig_id"][slot].astype(np.int64)] + h["pos"][slot].astype(np.uint64)
+                wi, sh = (gpos >> np.uint64(5)).astype(np.int64), (gpos & np.uint64(31)) << np.uint64(1)
+                wpad = np.concatenate([words, np.zeros(2, dtype=np.uint64)])
+                lo = wpad[wi] >> sh
+                hi = np.where(sh == 0, np.uint64(0), wpad[wi + 1] << ((np.uint64(64) - sh) & np.uint64(63)))
+                uk = (lo | hi) & np.uint64((1 << (2 * K)) - 1)
+                ident = h["match"][slot] == mz.IDENTITY_MATCH
+                import _oracle
+                rc = np.array([_oracle.lib().orc_revcomp(int(x), K) for x in fw[~ident][:20000]], dtype=np.uint64)
+                ok = bool(np.array_equal(uk[ident], fw[ident])) and bool(np.array_equal(uk[~ident][:20000], rc))
+                ok &= bool((h["unitig_len"][slot] == (accum[h["unitig_id"][slot].astype(np.int64) + 1] - accum[h["unitig_id"][slot].astype(np.int64)])).all())
+                return ok and len(slot) > 0
+            n_chk = min(n_reads, 5000)
+            chk = bases[: n_chk * READ_LEN].cpu().numpy()
+            want, _, _ = os_idx.query_reads(chk, np.arange(n_chk + 1, dtype=np.uint64) * READ_LEN, streaming=(mode == mz.MODE_STREAMING))
+            got = hits[: n_chk * nk_per_read].cpu().numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE)
+            return bool(np.array_equal(got, want))
+
+        if W != "config5":
+            def cpu_fn():
+                threads = os.cpu_count() or 1
+                v, n_s, dt, c = time_oracle_reads(os_idx, ref_codes, args.cpu_seconds, args.mode, threads, K)
+                v1, _, _, _ = time_oracle_reads(os_idx, ref_codes, min(args.cpu_seconds, 6.0), args.mode, 1, K)
+                return {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": "%d reads x %d bp (%d lookups) of the same workload, %.1f s" % (n_s, READ_LEN, int(c[0]), dt),
+                        "single_thread_value": v1, "ns_per_kmer_single_thread": 1e9 / v1,
+                        "note": "C++ restatement of mazu's query path (oracle/); the Rust reference cannot be built in this image"}
+
+    elif W in ("config1", "config5-kmers"):
+        if W == "config1":
+            useq_codes = _gen.unpack_2bit(o.useq_words(), o.total_len)
+            uk = _gen.kmer_words_from_codes(useq_codes, K)
+            import _oracle
+            qs = np.concatenate([_gen.kmer_words_from_codes(ref_codes, K), uk])
+            rng = np.random.default_rng(1)
+            reps = max(1, min(300, (args.reads * nk_per_read) // len(qs)))  # >= 2e8 queries at the default size
+            q = np.tile(qs, reps)
+            rng.shuffle(q)
+            kmers = torch.from_numpy(q.view(np.int64)).to(dev)
+            kernel_name = "mazu::k2u_batch_kernel (PFHash/BooPHF)"
+        else:
+            n = args.reads * nk_per_read
+            kmers = _gen.device_kmers_from_packed(torch, useq_dev, n_bases, n, K, gen, 0.5)
+            kernel_name = "mazu::k2u_batch_kernel (SSHash)"
+        n_units = int(kmers.numel())
+        hits = torch.empty((n_units, 4), dtype=torch.int32, device=dev)
+        launches_per_step = 1
+
+        def step():
+            index.k2u_batch(kmers, out=hits, mem=mz.MEM_DEVICE, stream=stream.cuda_stream, n=n_units)
+
+        if not args.no_e2e:
+            h_k = torch.empty(n_units, dtype=torch.int64, pin_memory=True)
+            h_k.copy_(kmers)
+            h_hits = torch.empty((n_units, 4), dtype=torch.int32, pin_memory=True)
+            hk = h_k.numpy().view(np.uint64)
+
+            def e2e_step():
+                index.k2u_batch(hk, out=h_hits)
+
+            e2e_bytes = (n_units * 8, n_units * 16)
+
+        def check():
+            n_chk = min(n_units, 200000)
+            got = hits[:n_chk].cpu().numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE)
+            qq = kmers[:n_chk].cpu().numpy().view(np.uint64)
+            if W == "config1":
+                return bool(np.array_equal(got, os_idx.k2u_batch(qq, n_threads=os.cpu_count() or 1)))
+            hit = got["match"] != 0  # verify hits against the packed sequence
+            gpos = accum[got["unitig_id"][hit].astype(np.int64)] + got["pos"][hit].astype(np.uint64)
+            wi, sh = (gpos >> np.uint64(5)).astype(np.int64), (gpos & np.uint64(31)) << np.uint64(1)
+            wpad = np.concatenate([words, np.zeros(2, dtype=np.uint64)])
+            ukk = ((wpad[wi] >> sh) | np.where(sh == 0, np.uint64(0), wpad[wi + 1] << ((np.uint64(64) - sh) & np.uint64(63)))) & np.uint64((1 << (2 * K)) - 1)
+            ident = got["match"][hit] == mz.IDENTITY_MATCH
+            return bool(np.array_equal(ukk[ident], qq[hit][ident])) and 0.3 < hit.mean() < 0.7
+
+        if W == "config1":
+            def cpu_fn():
+                threads = os.cpu_count() or 1
+                qq = kmers[: min(n_units, 40_000_000)].cpu().numpy().view(np.uint64)
+                t0 = time.time()
+                os_idx.k2u_batch(qq, n_threads=threads)
+                dt = time.time() - t0
+                return {"value": len(qq) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": "%d k-mers of the same shuffled query set, %.1f s" % (len(qq), dt),
+                        "note": "C++ restatement of PFHash::k2u over the C++ BooPHF (oracle/)"}
+    else:  # config4
+        metric, unit = "unitig occurrences decoded+projected/sec", "occurrences/s"
+        n_q = args.reads
+        rng = np.random.default_rng(45 + rank)
+        p = mult.astype(np.float64)
+        qids = rng.choice(n_unitigs, size=n_q, p=p / p.sum()).astype(np.uint32)
+        d_q = torch.from_numpy(qids.view(np.int32)).to(dev)
+        d_offs = torch.zeros(n_q + 1, dtype=torch.int64, device=dev)
+        total = int(mult[qids].sum())
+        d_out = torch.empty((total, 3), dtype=torch.int32, device=dev)
+        n_units = total
+        alg = (32.0 * n_q + (6 + 12) * total) / total  # bytes per occurrence: offsets pair per query + 42-bit word in + 12 B out
+        kernel_name = "mazu::occ_fill_kernel<false> (+ occ_lens_kernel + cub scan)"
+        launches_per_step = 4
+        import ctypes as C
+
+        def step():
+            mz._check(mz.lib().mazu_b200_decode_occs(index._h, mz._any_ptr(d_q), n_q, mz._any_ptr(d_offs), mz._any_ptr(d_out), total, None,
+                                                     mz.MEM_DEVICE, mz._any_ptr(stream.cuda_stream)))
+
+        def check():
+            n_chk = min(n_q, 20000)
+            offs_h = d_offs[: n_chk + 1].cpu().numpy().view(np.uint64)
+            out_h = d_out[: int(offs_h[-1])].cpu().numpy().view(np.uint32)
+            ok = np.array_equal(np.diff(offs_h), mult[qids[:n_chk]])
+            first = offsets[qids[:n_chk]].astype(np.int64)
+            ok &= np.array_equal(out_h[offs_h[:-1].astype(np.int64), 0], ref_ids[first].astype(np.uint32))
+            ok &= np.array_equal(out_h[offs_h[:-1].astype(np.int64), 1], poss[first].astype(np.uint32))
+            return bool(ok)
 
     def barrier():
         torch.cuda.synchronize()
@@ -272,8 +478,8 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    counts.zero_()
-    # ---- timed region: exactly K steps, CUDA events on the launching stream, per-step events for the kernel time
+    if W in ("config2", "config3", "config5"):
+        counts.zero_()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     with ClockSampler(local_rank) as clk:
         barrier()
@@ -288,45 +494,32 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     max_ms = float(t.item())
-    cnt = counts.cpu().numpy().astype(np.int64)
-    assert cnt[0] == n_lookups * args.steps, "every window of the synthetic reads is a valid k-mer"
-    tot_cnt = torch.tensor(cnt, dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot_cnt, op=dist.ReduceOp.SUM)  # final gather of per-shard hit counts (off the hot path)
-    tot_cnt = tot_cnt.cpu().numpy()
-    value = float(n_lookups) * args.steps * world / (max_ms * 1e-3)
+    cnt_line = None
+    if W in ("config2", "config3", "config5"):
+        tot_cnt = counts.clone()
+        if world > 1:
+            dist.all_reduce(tot_cnt, op=dist.ReduceOp.SUM)  # final gather of per-shard hit counts (off the hot path)
+        tot_cnt = tot_cnt.cpu().numpy()
+        cnt_line = {"n_kmers": int(tot_cnt[0]), "n_hit": int(tot_cnt[1]), "n_miss": int(tot_cnt[2])}
+    value = float(n_units) * args.steps * world / (max_ms * 1e-3)
     kernel_ms = float(np.mean(step_ms))
 
-    # ---- e2e: same metric through the C ABI with HOST buffers (pinned): H2D reads + D2H every hit record, per step
     e2e = None
-    if not args.no_e2e:
-        h_bases = torch.empty(n_reads * READ_LEN, dtype=torch.uint8, pin_memory=True)
-        h_bases.copy_(bases)
-        h_hits = torch.empty((n_lookups, 4), dtype=torch.int32, pin_memory=True)
-        h_cnt = np.zeros(3, dtype=np.uint64)
-        hb = h_bases.numpy()
-        e2e_steps = args.steps
-
-        def e2e_step():
-            index.query_reads(hb, None, n_reads=n_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=h_hits, counts=h_cnt)
-
+    if e2e_step is not None:
         e2e_step()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
+        for _ in range(args.steps):
             e2e_step()
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_val = float(n_lookups) * e2e_steps * world / float(tt.item())
-        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n_reads * READ_LEN * world,
-               "d2h_bytes_per_step": (n_lookups * 16 + 24) * world, "steps": e2e_steps,
-               "api": "mazu_b200_query_reads(MAZU_MEM_HOST): pinned host reads in, every 16-byte mazu_hit_t out"}
-        # the e2e result must equal the device-resident result
-        same = bool(torch.equal(h_hits[: 120 * 50000], hits[: 120 * 50000].cpu()))
-        e2e["matches_device_path"] = same
+        e2e = {"value": float(n_units) * args.steps * world / float(tt.item()), "unit": unit, "h2d_bytes_per_step": e2e_bytes[0] * world,
+               "d2h_bytes_per_step": e2e_bytes[1] * world, "steps": args.steps,
+               "api": "C ABI with MAZU_MEM_HOST: pinned host inputs in, every result record out",
+               "matches_device_path": bool(torch.equal(h_hits[:1_000_000], hits[:1_000_000].cpu()))}
 
     if rank != 0:
         if world > 1:
@@ -334,57 +527,49 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- parity spot check against the oracle on the first reads of this exact batch
-    n_chk = min(n_reads, 5000)
-    chk_bases = bases[: n_chk * READ_LEN].cpu().numpy()
-    want, wcnt, _ = os_idx.query_reads(chk_bases, np.arange(n_chk + 1, dtype=np.uint64) * READ_LEN, streaming=(mode == mz.MODE_STREAMING))
-    got = hits[: n_chk * nk_per_read].cpu().numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE)
-    parity_ok = bool(np.array_equal(got, want))
-
-    # ---- CPU baseline (port) on a bounded sample, rank 0 only
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        threads = os.cpu_count() or 1
-        v, n_s, dt, c = time_oracle(os_idx, ref_codes, args.cpu_seconds, args.mode, threads)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d reads x %d bp (%d lookups) of the same workload, %.1f s" % (n_s, READ_LEN, int(c[0]), dt),
-               "note": "C++ restatement of mazu's query path (oracle/); the Rust reference cannot be built in this image"}
-        v1, n1, dt1, c1 = time_oracle(os_idx, ref_codes, min(args.cpu_seconds, 6.0), args.mode, 1)
-        cpu["single_thread_value"] = v1
-        cpu["ns_per_kmer_single_thread"] = 1e9 / v1
+    parity_ok = check() if check else None
+    if args.validate and W.startswith("config5"):
+        c = index.k2u_validate_self()
+        info["k2u_validate_self"] = {"n_queries": c[0], "n_identity": c[1], "n_twin": c[2], "n_fail": c[4]}
+    cpu = cpu_fn() if (cpu_fn and not args.no_cpu_baseline and world == 1) else None
 
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):
         peaks = json.load(open(pk_path))
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = n_lookups * ALG_BYTES_PER_LOOKUP / (kernel_ms * 1e-3) / 1e9
+    achieved = n_units * alg / (kernel_ms * 1e-3) / 1e9
+    if peak_kind == "hbm":
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_source = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+    else:
+        pr = json.load(open(os.path.join(ROOT, "profiles", "r01_prand.json")))
+        peak = float(pr["32GiB"]["GBps"])
+        peak_source = "P_rand: measured independent random 32-byte gathers over a 32 GiB table (profiles/r01_prand.json), in GB/s of sectors"
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr_path):
+    if os.path.exists(tr_path) and W in ("config2", "config3"):
         try:
-            tj = json.load(open(tr_path))
-            per_lookup = tj.get("query_reads_kernel<%d>" % (0 if args.mode == "random" else 1), {}).get("dram_bytes_per_lookup")
-            if per_lookup is not None:
-                traffic = per_lookup * n_lookups
+            per = json.load(open(tr_path)).get("query_reads_kernel<%d>" % (0 if mode == mz.MODE_RANDOM else 1), {}).get("dram_bytes_per_lookup")
+            traffic = per * n_units if per is not None else None
         except Exception:
             traffic = None
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-        "data": "synthetic (torch.Generator seed 42+rank; reads sampled from refseq.bin of the yeast_chr01 fixture)",
-        "config": config_dict(args, world),
+        "data": "synthetic (torch.Generator seed 42+rank on the device; fixture sequences from tests/data)",
+        "config": {"workload": workload_name(args), "mode": args.mode, "units_per_step_per_gpu": n_units,
+                   "parallelism": "index replicated x%d, inputs sharded by batch, no collective" % world,
+                   "l2_policy": "inputs and results per step (%.2f GB) are larger than the 126 MB L2" % ((e2e_bytes[0] + e2e_bytes[1]) / 1e9 if e2e_bytes[0] else n_units * 17.25 / 1e9)},
         "clocks": clk.summary(),
-        "gpu_launches": args.steps,
-        "kernel": "mazu::query_reads_kernel<%d>" % (0 if args.mode == "random" else 1),
+        "gpu_launches": args.steps * launches_per_step,
+        "kernel": kernel_name,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                     "algorithmic_bytes_per_lookup": ALG_BYTES_PER_LOOKUP, "lookups_per_launch": n_lookups, "kernel_ms": kernel_ms,
-                     "note": "the yeast index (~1 MB) is L2-resident: DRAM carries only the read/result stream; see DESIGN.md"},
-        "counts": {"n_kmers": int(tot_cnt[0]), "n_hit": int(tot_cnt[1]), "n_miss": int(tot_cnt[2])},
-        "parity_spot_check_vs_oracle": parity_ok,
-        "index_device_bytes": index.device_bytes,
+                     "peak_source": peak_source, "algorithmic_bytes_per_unit": alg, "units_per_launch": n_units, "kernel_ms": kernel_ms},
+        "parity_spot_check": parity_ok,
     }
+    line.update(info)
+    if cnt_line:
+        line["counts"] = cnt_line
     if e2e is not None:
         line["e2e"] = e2e
     if cpu is not None:

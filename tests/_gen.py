@@ -89,3 +89,66 @@ def synthetic_unitigs(n_unitigs, mean_extra, k, seed):
     accum[1:] = np.cumsum(lens)
     codes = rng.integers(0, 4, size=int(accum[-1]), dtype=np.uint8)
     return codes, accum
+
+
+# ------------------------------------------------------------------------------------------------
+# large synthetic inputs (bench.py config 5): packed random unitigs on the host, reads on the device
+# ------------------------------------------------------------------------------------------------
+def synthetic_unitigs_packed(n_unitigs, mean_extra, k, seed):
+    """Uniform-random unitig set without materialising per-base codes: random u64 words ARE random
+    2-bit sequences.  lengths = k + Geometric(mean mean_extra).  Returns (words, n_bases, accum)."""
+    rng = np.random.default_rng(seed)
+    lens = (k + rng.geometric(1.0 / max(mean_extra, 1), size=n_unitigs) - 1).astype(np.uint64)
+    accum = np.zeros(n_unitigs + 1, dtype=np.uint64)
+    np.cumsum(lens, out=accum[1:])
+    n_bases = int(accum[-1])
+    nw = (2 * n_bases + 63) // 64
+    words = rng.integers(0, np.iinfo(np.uint64).max, size=nw, dtype=np.uint64, endpoint=True)
+    if (2 * n_bases) & 63:
+        words[-1] &= np.uint64((1 << ((2 * n_bases) & 63)) - 1)
+    return words, n_bases, accum
+
+
+def device_reads_from_packed(torch, useq_words_dev, n_bases, n_reads, read_len, gen, frac_ref, sub_rate, chunk=1_000_000):
+    """ASCII reads on the device: frac_ref sampled from the packed sequence at a uniform start on a
+    random strand (i.i.d. substitutions at sub_rate), the rest uniform random.  useq_words_dev: int64 view."""
+    dev = useq_words_dev.device
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    bases = torch.empty(n_reads * read_len, dtype=torch.uint8, device=dev)
+    ar = torch.arange(read_len, device=dev)
+    for r0 in range(0, n_reads, chunk):
+        n = min(chunk, n_reads - r0)
+        starts = torch.randint(0, n_bases - read_len + 1, (n,), generator=gen, device=dev)
+        p = starts[:, None] + ar[None, :]
+        codes = ((useq_words_dev[p >> 5] >> ((p & 31) << 1)) & 3).to(torch.uint8)
+        strand = torch.rand(n, generator=gen, device=dev) < 0.5
+        rc = (3 - codes.flip(1))
+        codes = torch.where(strand[:, None], rc, codes)
+        is_ref = torch.rand(n, generator=gen, device=dev) < frac_ref
+        rnd = torch.randint(0, 4, (n, read_len), generator=gen, device=dev, dtype=torch.uint8)
+        codes = torch.where(is_ref[:, None], codes, rnd)
+        if sub_rate > 0:
+            m = torch.rand((n, read_len), generator=gen, device=dev) < sub_rate
+            codes = torch.where(m, (codes + torch.randint(1, 4, (n, read_len), generator=gen, device=dev, dtype=torch.uint8)) & 3, codes)
+        bases[r0 * read_len:(r0 + n) * read_len] = acgt[codes.long()].reshape(-1)
+    return bases
+
+
+def device_kmers_from_packed(torch, useq_words_dev, n_bases, n, k, gen, frac_pos):
+    """forward k-mer words on the device: frac_pos sampled from the packed sequence (random strand is
+    left to the index: a window IS a k-mer of the set unless it straddles a unitig boundary), rest random."""
+    dev = useq_words_dev.device
+    pos = torch.randint(0, n_bases - k + 1, (n,), generator=gen, device=dev)
+    wi, sh = pos >> 5, (pos & 31) << 1
+    lo = useq_words_dev[wi]
+    hi = useq_words_dev[wi + 1]
+    # logical funnel shift on int64 storage: mask off the sign-extension of the arithmetic >>
+    keep = torch.where(sh == 0, torch.full_like(sh, -1), (torch.ones_like(sh) << (64 - sh).clamp(max=63)) - 1)
+    lo_s = (lo >> sh) & keep
+    hi_s = torch.where(sh == 0, torch.zeros_like(hi), hi << (64 - sh))
+    w = lo_s | hi_s
+    mask = (1 << (2 * k)) - 1 if k < 32 else -1
+    w = w & mask
+    rnd = torch.randint(0, 1 << 62, (n,), generator=gen, device=dev) & mask
+    is_pos = torch.rand(n, generator=gen, device=dev) < frac_pos
+    return torch.where(is_pos, w, rnd)
