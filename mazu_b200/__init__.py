@@ -207,13 +207,19 @@ class PackedVec:
             width = max(1, int(values.max()).bit_length()) if len(values) else 1
         n = len(values)
         words = np.zeros((n * width + 63) // 64 + 1, dtype=np.uint64)
-        bit = np.arange(n, dtype=np.uint64) * np.uint64(width)
-        wi = (bit >> np.uint64(6)).astype(np.int64)
-        sh = bit & np.uint64(63)
-        np.bitwise_or.at(words, wi, values << sh)
-        spill = (sh + np.uint64(width)) > np.uint64(64)
-        if spill.any():
-            np.bitwise_or.at(words, wi[spill] + 1, values[spill] >> (np.uint64(64) - sh[spill]))
+        if n:
+            bit = np.arange(n, dtype=np.uint64) * np.uint64(width)
+            wi = (bit >> np.uint64(6)).astype(np.int64)
+            sh = bit & np.uint64(63)
+
+            def scatter_or(idx, vals):  # idx is non-decreasing: OR-reduce each run, one store per word
+                first = np.flatnonzero(np.concatenate(([True], idx[1:] != idx[:-1])))
+                words[idx[first]] |= np.bitwise_or.reduceat(vals, first)
+
+            scatter_or(wi, values << sh)
+            spill = (sh + np.uint64(width)) > np.uint64(64)
+            if spill.any():
+                scatter_or(wi[spill] + 1, values[spill] >> (np.uint64(64) - sh[spill]))
         return cls(words, width, n)
 
     def desc(self):
