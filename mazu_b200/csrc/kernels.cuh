@@ -781,20 +781,17 @@ __global__ void __launch_bounds__(256) k2u_validate_self_kernel(const __grid_con
 // ---------------------------------------------------------------------------------------------
 // Roofline probe: independent random 32-byte gathers (one aligned uint4 pair per thread step)
 // ---------------------------------------------------------------------------------------------
+// One independent gather per thread and iteration; memory-level parallelism comes from the 2048
+// resident threads per SM.  (A variant with 8 gathers in flight per thread measured LOWER: 2.6e10 vs
+// 3.4e10 sectors/s over a 32 GiB table -- profiles/r01_prand.json keeps the better figure.)
 __global__ void __launch_bounds__(256) random_gather_kernel(const uint4* __restrict__ table, u64 n_sectors, u64 n_gathers, u64 seed,
                                                             unsigned long long* __restrict__ sink) {
   u64 acc = 0;
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  // 8 independent gathers in flight per thread and iteration (memory-level parallelism, not a dependent chain)
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_gathers; i += 8 * stride) {
-    uint4 v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      u64 h = fmix64((i + j * stride) * 0x9E3779B97F4A7C15ULL + seed);
-      v[j] = __ldg(table + 2 * mulhi64(h, n_sectors));
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc += v[j].x + v[j].w;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_gathers; i += (u64)gridDim.x * blockDim.x) {
+    u64 h = fmix64(i * 0x9E3779B97F4A7C15ULL + seed);
+    u64 s = mulhi64(h, n_sectors);
+    uint4 a = __ldg(table + 2 * s);
+    acc += a.x + a.w;
   }
   if (acc == 0x1234567887654321ULL) atomicAdd(sink, 1ULL);
 }
