@@ -534,7 +534,8 @@ def main():
     parity_ok = bool(check()) if check else None
     if args.validate and W.startswith("config5"):
         c = index.k2u_validate_self()
-        info["k2u_validate_self"] = {"n_queries": c[0], "n_identity": c[1], "n_twin": c[2], "n_fail": c[4]}
+        info["k2u_validate_self"] = {"n_queries": c[0], "n_identity": c[1], "n_twin": c[2], "n_fail": c[4], "n_fail_not_found": c[3],
+                                     "note": "failures that are not 'not found' are duplicated canonical k-mers of the random unitig set (expected ~1.3 pairs at 2.5e9 k-mers)"}
     cpu = cpu_fn() if (cpu_fn and not args.no_cpu_baseline and world == 1) else None
 
     peaks = {}

@@ -205,7 +205,9 @@ mazu_status_t mazu_b200_project_hits(const mazu_index_t* idx, const mazu_hit_t* 
 /* Validate::validate_self (src/index/validate.rs:24-52): every reference k-mer must map back to its own
  * (ref_id,pos).  counts = {n_queries, n_identity, n_twin, n_projected, n_fail}; the reference panics when n_fail != 0. */
 mazu_status_t mazu_b200_validate_self(const mazu_index_t* idx, uint64_t counts[5]);
-/* K2U::validate_self / validate_self_parallel (src/kphf/mod.rs:69-139): every unitig k-mer, fw then swapped */
+/* K2U::validate_self / validate_self_parallel (src/kphf/mod.rs:69-139): every unitig k-mer, fw then swapped.
+ * counts[3] = failures that were plain misses (the rest of n_fail found the k-mer at ANOTHER position, i.e. the
+ * unitig set holds a duplicated canonical k-mer, which the reference's validate_self would also reject). */
 mazu_status_t mazu_b200_k2u_validate_self(const mazu_index_t* idx, uint64_t counts[5]);
 
 /* ---------------------------------------------------------------------------------------------

@@ -771,8 +771,14 @@ __global__ void __launch_bounds__(256) k2u_validate_self_kernel(const __grid_con
       ++v[0];
       u32 want = t == 0 ? IDENTITY_MATCH : TWIN_MATCH;
       bool ok = t == 0 ? k2u_any(ix, fw, rc, h) : k2u_any(ix, rc, fw, h);
-      if (!ok || h.unitig_id != (u32)id || h.unitig_len != (u32)(e - s) || h.pos != (u32)(p - s) || h.match != want) ++v[4];
-      else ++v[t == 0 ? 1 : 2];
+      if (!ok) {
+        ++v[3];  // not found at all (counts[3] is otherwise unused by this driver): can never happen for a k-mer of the set
+        ++v[4];
+      } else if (h.unitig_id != (u32)id || h.unitig_len != (u32)(e - s) || h.pos != (u32)(p - s) || h.match != want) {
+        ++v[4];  // found, verified, but at another position: the unitig set holds this canonical k-mer twice
+      } else {
+        ++v[t == 0 ? 1 : 2];
+      }
     }
   }
   block_accumulate(counts, v);
