@@ -729,7 +729,7 @@ static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu
     d_o = (OccRec*)d_out->p;
   }
   if (n) {
-    int grid = (int)std::min<u64>((n + 255) / 256, (u64)idx->sm_count * 8);
+    int grid = idx->sm_count * 8;  // tiles of the OUTPUT are grid-strided; the kernel reads the total from out_offsets[n]
     if (project) occ_fill_kernel<true><<<grid, 256, 0, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o);
     else occ_fill_kernel<false><<<grid, 256, 0, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o);
     MZ_CUDA(cudaGetLastError());

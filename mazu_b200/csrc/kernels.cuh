@@ -648,7 +648,26 @@ __global__ void occ_lens_kernel(const __grid_constant__ IndexView ix, const u32*
     lens[i] = len;
   }
 }
-// fill: a warp takes 32 queries; short lists are written by their own lane, long lists by the whole warp
+// largest q in [0, n) with off[q] <= x, found by the whole warp with a 32-ary search (off[0] == 0 <= x)
+__device__ __forceinline__ u64 warp_last_le(const u64* __restrict__ off, u64 n, u64 x, u32 lane) {
+  u64 lo = 0, hi = n;  // answer in [lo, hi)
+  while (hi - lo > 1) {
+    u64 step = (hi - lo + 31) / 32;
+    u64 probe = lo + (u64)(lane + 1) * step;
+    bool le = probe < hi && __ldg(off + probe) <= x;
+    u32 c = __popc(__ballot_sync(0xffffffffu, le));  // off is monotone: the lanes that pass form a prefix
+    lo += (u64)c * step;
+    hi = min(hi, lo + step);
+  }
+  return lo;
+}
+
+// fill, load-balanced over the OUTPUT: a warp owns a tile of 1024 consecutive output records, locates the
+// queries overlapping the tile once (32-ary search over the scanned offsets), then every lane maps its
+// records to (query, element) with a short binary search inside that range.  A 65,536-entry list is
+// therefore spread over 64 warps instead of serialising one, and consecutive lanes read consecutive
+// occurrence words and write consecutive 12-byte records.
+static const u64 OCC_TILE = 1024;
 template <bool PROJECT>
 __global__ void __launch_bounds__(256) occ_fill_kernel(const __grid_constant__ IndexView ix, const u32* __restrict__ uids,
                                                        const Hit* __restrict__ hits, u64 n, const u64* __restrict__ out_offsets,
@@ -657,48 +676,29 @@ __global__ void __launch_bounds__(256) occ_fill_kernel(const __grid_constant__ I
   const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
   const u32 k = ix.unitigs.k;
-  for (u64 base = warp * 32; base < n; base += n_warps * 32) {
-    u64 i = base + lane;
-    u64 s = 0, len = 0, o0 = 0;
-    Hit h = hit_none(NO_MATCH);
-    if (i < n) {
+  const u64 total = __ldg(out_offsets + n);
+  for (u64 t0 = warp * OCC_TILE; t0 < total; t0 += n_warps * OCC_TILE) {
+    const u64 t1 = min(t0 + OCC_TILE, total);
+    const u64 qlo = warp_last_le(out_offsets, n, t0, lane);
+    const u64 qhi = warp_last_le(out_offsets, n, t1 - 1, lane);
+    for (u64 rec = t0 + lane; rec < t1; rec += 32) {
+      u64 a = qlo, b = qhi;  // off[a] <= rec, answer in [a, b]
+      while (a < b) {
+        u64 m = (a + b + 1) >> 1;
+        if (__ldg(out_offsets + m) <= rec) a = m; else b = m - 1;
+      }
+      Hit h = hit_none(NO_MATCH);
       u32 uid;
       if (PROJECT) {
-        h = hits[i];
-        uid = (h.match == IDENTITY_MATCH || h.match == TWIN_MATCH) ? h.unitig_id : ~0u;
+        h = hits[a];
+        uid = h.unitig_id;
       } else {
-        uid = uids[i];
+        uid = uids[a];
       }
-      if (uid != ~0u) {
-        u64 e;
-        occ_range(ix, uid, s, e);
-        len = e - s;
-        o0 = out_offsets[i];
-      }
-    }
-    const bool is_long = len > 4;
-    if (!is_long) {
-      for (u64 j = 0; j < len; ++j) {
-        OccRec o = occ_decode(ix, s + j);
-        if (PROJECT) o = project_occ(k, h, o);
-        out[o0 + j] = o;
-      }
-    }
-    u32 longmask = __ballot_sync(0xffffffffu, is_long);
-    while (longmask) {
-      int src = __ffs(longmask) - 1;
-      longmask &= longmask - 1;
-      u64 ls = __shfl_sync(0xffffffffu, s, src), ll = __shfl_sync(0xffffffffu, len, src), lo = __shfl_sync(0xffffffffu, o0, src);
-      Hit lh;
-      lh.unitig_id = __shfl_sync(0xffffffffu, h.unitig_id, src);
-      lh.unitig_len = __shfl_sync(0xffffffffu, h.unitig_len, src);
-      lh.pos = __shfl_sync(0xffffffffu, h.pos, src);
-      lh.match = __shfl_sync(0xffffffffu, h.match, src);
-      for (u64 j = lane; j < ll; j += 32) {
-        OccRec o = occ_decode(ix, ls + j);
-        if (PROJECT) o = project_occ(k, lh, o);
-        out[lo + j] = o;
-      }
+      u64 s = packed_get(ix.contig_offsets, uid);  // dense_unitig_table.rs:58-63 / :130-135
+      OccRec o = occ_decode(ix, s + (rec - __ldg(out_offsets + a)));
+      if (PROJECT) o = project_occ(k, h, o);
+      out[rec] = o;
     }
   }
 }
