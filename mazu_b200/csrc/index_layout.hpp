@@ -54,11 +54,22 @@ MZ_HD u32 mulhi32(u32 a, u32 b) {
 #endif
 }
 
-// slot -> (block, bit) for the native family: block by the high hash half, bit by the low half
+// slot -> (block, bit) for the native family.  One 64-bit mix of the key per lookup, then a cheap
+// 32-bit remix per level (the level loop is the divergent part of a lookup, so it is kept short).
+MZ_HD void native_slot_from(u64 h, u32 level, u64 n_blocks, u64& blk, u32& bit) {
+  u32 a = (u32)(h >> 32) + level * 0x9E3779B1u;
+  u32 b = (u32)h ^ (level * 0x85EBCA77u);
+  a ^= b;
+  a *= 0x2C1B3C6Du;
+  a ^= a >> 15;
+  b += a;
+  b *= 0x297A2D39u;
+  b ^= b >> 16;
+  blk = mulhi32(a, (u32)n_blocks);
+  bit = mulhi32(b, MPHF_BLOCK_BITS);
+}
 MZ_HD void native_slot(u64 key, u32 level, u64 n_blocks, u64& blk, u32& bit) {
-  u64 h = fmix64(key ^ (0x9E3779B97F4A7C15ULL * (u64)(level + 1)));
-  blk = mulhi32((u32)(h >> 32), (u32)n_blocks);
-  bit = mulhi32((u32)h, MPHF_BLOCK_BITS);
+  native_slot_from(fmix64(key), level, n_blocks, blk, bit);
 }
 
 // bit test of one slot: reads a single u32 of the block
@@ -97,11 +108,12 @@ MZ_HD bool mphf_lookup_t(const RankedLevels& m, u64 key, u64& out) {
   u32 hit_level = MPHF_MAX_LEVELS, hit_bit = 0;
   u64 hit_blk = 0;
   if (FAMILY == MPHF_FAMILY_NATIVE) {
+    const u64 hk = fmix64(key);
 #pragma unroll 1
     for (u32 l = 0; l < m.n_levels; ++l) {
       u64 blk;
       u32 bit;
-      native_slot(key, l, m.size[l], blk, bit);
+      native_slot_from(hk, l, m.size[l], blk, bit);
       if (ranked_test(m, l, blk, bit)) {
         hit_level = l;
         hit_blk = blk;

@@ -145,7 +145,7 @@ struct WarpStage {
   u64 bstart[QR_CHUNK];  // leaders only: first bucket entry
   u32 bn[QR_CHUNK];      // leaders only: bucket size, 0 = minimizer unknown, BN_SKEW = heavy bucket
   u32 hf[QR_BASES];      // w-mer hash keys, forward strand
-  u32 hr[QR_BASES];      // w-mer hash keys, reverse strand
+  u32 hr[QR_BASES];      // w-mer hash keys, reverse strand, stored REVERSED (hr[QR_BASES-1-q]) so both strands scan upwards
   u8 off[QR_CHUNK];      // minimizer offset in fw-mer coordinates
   u8 leader[QR_CHUNK];   // chunk position of this k-mer's leader
   u8 lead_list[QR_CHUNK];
@@ -202,6 +202,26 @@ __device__ __forceinline__ u64 mm_word_of(u64 fw, u64 rc, u32 off_fw, u32 k, u32
   return ((fw_canon ? fw : rc) >> (2 * ci)) & kmer_mask(w);
 }
 
+// smallest (hash key | offset) over h[0..span]; unrolled for the spans of the named configs
+template <int SPAN>
+__device__ __forceinline__ u32 window_min_fixed(const u32* __restrict__ h) {
+  u32 best = h[0];
+#pragma unroll
+  for (int c = 1; c <= SPAN; ++c) best = min(best, h[c] | (u32)c);
+  return best;
+}
+__device__ __forceinline__ u32 window_min(const u32* __restrict__ h, u32 span) {
+  switch (span) {
+    case 16: return window_min_fixed<16>(h);  // k=31, w=15
+    case 12: return window_min_fixed<12>(h);  // k=31, w=19
+    default: {
+      u32 best = h[0];
+      for (u32 c = 1; c <= span; ++c) best = min(best, h[c] | c);
+      return best;
+    }
+  }
+}
+
 // stage M + stage B (SSHash only)
 template <u32 FAMILY>
 __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkInfo& ci, u32 lane, WarpStage& S) {
@@ -221,7 +241,7 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
     }
     u64 wf = x & wmask;
     S.hf[q] = mm_hash32(wf, ix.seed) & MM_KEY_MASK;
-    S.hr[q] = mm_hash32(revcomp(wf, w), ix.seed) & MM_KEY_MASK;
+    S.hr[QR_BASES - 1 - q] = mm_hash32(revcomp(wf, w), ix.seed) & MM_KEY_MASK;
   }
   __syncwarp();
   // per k-mer minimizer, leader detection, leader compaction
@@ -237,13 +257,9 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
     if (valid) {
       u64 fw = S.fw[p], rc = revcomp(fw, k);
       bool fw_canon = fw <= rc;
-      const u32* h = fw_canon ? S.hf + p : S.hr + p + span;
-      const int step = fw_canon ? 1 : -1;
-      u32 best = 0xFFFFFFFFu;
-      for (u32 c = 0; c <= span; ++c) {
-        u32 key = h[(int)c * step] | c;
-        best = min(best, key);
-      }
+      // offset c in the canonical k-mer: fw strand position p+c, rc strand position p+span-c (= reversed index below + c)
+      const u32* h = fw_canon ? S.hf + p : S.hr + (QR_BASES - 1 - p - span);
+      u32 best = window_min(h, span);
       u32 bi = best & 31u;
       mmw = ((fw_canon ? fw : rc) >> (2 * bi)) & wmask;
       S.off[p] = (u8)(fw_canon ? bi : span - bi);
