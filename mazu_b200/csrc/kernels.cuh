@@ -697,6 +697,34 @@ __global__ void __launch_bounds__(256) occ_fill_kernel(const __grid_constant__ I
     const u64 t1 = min(t0 + OCC_TILE, total);
     const u64 qlo = warp_last_le(out_offsets, n, t0, lane);
     const u64 qhi = warp_last_le(out_offsets, n, t1 - 1, lane);
+    if (qhi - qlo <= 32) {
+      // few, long lists in this tile: walk the overlapping queries (warp-uniform), lanes stride over each
+      // segment with plain arithmetic -- no per-record search; 4 independent records in flight per lane
+      for (u64 q = qlo; q <= qhi; ++q) {
+        const u64 ob = __ldg(out_offsets + q), oe = __ldg(out_offsets + q + 1);
+        const u64 sb = max(ob, t0), se = min(oe, t1);
+        if (sb >= se) continue;
+        Hit h = hit_none(NO_MATCH);
+        u32 uid;
+        if (PROJECT) {
+          h = hits[q];
+          uid = h.unitig_id;
+        } else {
+          uid = uids[q];
+        }
+        const u64 e0 = packed_get(ix.contig_offsets, uid) - ob;  // element index = e0 + rec
+        for (u64 rec = sb + lane; rec < se; rec += 128) {
+          OccRec o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (rec + 32 * j < se) o[j] = occ_decode(ix, e0 + rec + 32 * j);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (rec + 32 * j < se) out[rec + 32 * j] = PROJECT ? project_occ(k, h, o[j]) : o[j];
+        }
+      }
+      continue;
+    }
     for (u64 rec = t0 + lane; rec < t1; rec += 32) {
       u64 a = qlo, b = qhi;  // off[a] <= rec, answer in [a, b]
       while (a < b) {

@@ -511,3 +511,43 @@ def test_synthetic_index_properties():
     o = OracleIndex.from_packed(k, us.useq_words, us.n_bases, accum, 1, w=19, skew=64)
     want, _, _ = o.query_reads(bases[:150 * 3000], np.arange(3001, dtype=np.uint64) * 150)
     assert_hits_equal(hr[:120 * 3000], want, "sampled oracle comparison")
+
+
+# --------------------------------------------------------------------------------------------
+# other k / w, including the maximum k = 32 (even k: palindromic k-mers have fw == rc)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,w,skew", [(32, 20, 8), (32, 32, NOSKEW), (21, 11, 4), (15, 7, 0), (5, 3, 2), (31, 1, 64)])
+def test_other_k_w_synthetic(k, w, skew):
+    codes, accum = _gen.synthetic_unitigs(400, 40, k, seed=100 + k)
+    if k <= 7:  # tiny k: random unitigs repeat k-mers; still must match the oracle's first-match order
+        codes, accum = _gen.synthetic_unitigs(12, 6, k, seed=100 + k)
+    us = mz.UnitigSet(k, mz.pack_2bit(codes), len(codes), accum)
+    g = mz.SSHash.from_unitig_set(us, w, skew, seed=3)
+    o = OracleIndex.from_packed(k, us.useq_words, us.n_bases, accum, 1, w=w, skew=skew, seed=3)
+    gp = mz.PFHash.from_unitig_set(us)
+    assert g.k2u_validate_self() == o.k2u_validate_self()
+    bases, offs = _gen.sample_reads(codes, 600, 180, seed=k, frac_ref=0.7, sub_rate=0.02, n_rate=0.003, ragged=True)
+    for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+        want, _ = _check_reads(g, o, bases, offs, mode)
+    if k > 7:  # unique canonical k-mers: PFHash (native MPHF) must give the same answers as SSHash
+        got, _, _ = gp.query_reads(bases, offs)
+        assert_hits_equal(got, o.query_reads(bases, offs)[0], "PFHash native on synthetic k=%d" % k)
+    rng = np.random.default_rng(k)
+    q = np.concatenate([_gen.kmer_words_from_codes(codes, k), rng.integers(0, 1 << 62, size=2000, dtype=np.uint64) & np.uint64((1 << (2 * k)) - 1 if k < 32 else 0xFFFFFFFFFFFFFFFF)])
+    assert_hits_equal(g.k2u_batch(q), o.k2u_batch(q), "k2u_batch k=%d w=%d" % (k, w))
+
+
+def test_palindromic_kmers_even_k():
+    """even k: a palindromic k-mer equals its reverse complement; the reference reports IdentityMatch first."""
+    k = 8
+    seqs = ["ACGTACGTTTGACCA", "GGATCCGGAAGCTTCA", "TTTTAAAACCCCGGGG"]  # ACGTACGT, GGATCC.., AAGCTT.. contain palindromes
+    us = mz.UnitigSet.from_seqs(seqs, k)
+    for w, skew in [(4, NOSKEW), (3, 0)]:
+        g = mz.SSHash.from_unitig_set(us, w, skew)
+        o = OracleIndex.from_seqs(seqs, k, 1, w=w, skew=skew)
+        codes = _gen.unpack_2bit(us.useq_words, us.n_bases)
+        q = _gen.kmer_words_from_codes(codes, k)
+        rc = np.array([O.lib().orc_revcomp(int(x), k) for x in q], dtype=np.uint64)
+        assert (q == rc).any(), "test needs at least one palindromic k-mer"
+        both = np.concatenate([q, rc])
+        assert_hits_equal(g.k2u_batch(both), o.k2u_batch(both), "palindromes")
