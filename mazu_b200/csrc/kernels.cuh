@@ -693,6 +693,7 @@ __global__ void __launch_bounds__(256) occ_fill_kernel(const __grid_constant__ I
   const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
   const u32 k = ix.unitigs.k;
   const u64 total = __ldg(out_offsets + n);
+  const bool out_aligned = (reinterpret_cast<unsigned long long>(out) & 15ULL) == 0;
   for (u64 t0 = warp * OCC_TILE; t0 < total; t0 += n_warps * OCC_TILE) {
     const u64 t1 = min(t0 + OCC_TILE, total);
     const u64 qlo = warp_last_le(out_offsets, n, t0, lane);
@@ -713,14 +714,29 @@ __global__ void __launch_bounds__(256) occ_fill_kernel(const __grid_constant__ I
           uid = uids[q];
         }
         const u64 e0 = packed_get(ix.contig_offsets, uid) - ob;  // element index = e0 + rec
-        for (u64 rec = sb + lane; rec < se; rec += 128) {
+        // body: every lane owns 4 CONSECUTIVE records = 48 contiguous output bytes = three 16-byte stores
+        // (record index a multiple of 4 <=> byte offset a multiple of 16); head/tail records go one by one
+        u64 body_b = (sb + 3) & ~3ULL, body_e = body_b + ((se > body_b ? se - body_b : 0) & ~3ULL);
+        if (!out_aligned || body_b >= se) body_b = body_e = sb;
+        for (u64 rec = sb + lane; rec < body_b; rec += 32) {
+          OccRec o = occ_decode(ix, e0 + rec);
+          out[rec] = PROJECT ? project_occ(k, h, o) : o;
+        }
+        for (u64 base = body_b + 4 * lane; base < body_e; base += 128) {
           OccRec o[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (rec + 32 * j < se) o[j] = occ_decode(ix, e0 + rec + 32 * j);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (rec + 32 * j < se) out[rec + 32 * j] = PROJECT ? project_occ(k, h, o[j]) : o[j];
+          for (int j = 0; j < 4; ++j) {
+            o[j] = occ_decode(ix, e0 + base + j);
+            if (PROJECT) o[j] = project_occ(k, h, o[j]);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(out + base);
+          dst[0] = make_uint4(o[0].ref_id, o[0].pos, o[0].fw, o[1].ref_id);
+          dst[1] = make_uint4(o[1].pos, o[1].fw, o[2].ref_id, o[2].pos);
+          dst[2] = make_uint4(o[2].fw, o[3].ref_id, o[3].pos, o[3].fw);
+        }
+        for (u64 rec = body_e + lane; rec < se; rec += 32) {
+          OccRec o = occ_decode(ix, e0 + rec);
+          out[rec] = PROJECT ? project_occ(k, h, o) : o;
         }
       }
       continue;
