@@ -244,6 +244,7 @@ def main():
     unit, metric = UNIT, METRIC
     check = None          # callable -> bool : parity spot check (rank 0)
     e2e_step = None       # callable: one end-to-end step through host buffers
+    e2e_compact_step = None  # same with 8-byte records
     e2e_bytes = (0, 0)
     cpu_fn = None         # callable -> cpu_baseline dict
     t_build = time.time()
@@ -341,6 +342,10 @@ def main():
                 index.query_reads(hb, None, n_reads=n_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=h_hits, counts=h_cnt)
 
             e2e_bytes = (n_reads * READ_LEN, n_units * 16 + 24)
+            h_hits8 = torch.empty((n_units, 2), dtype=torch.int32, pin_memory=True)
+
+            def e2e_compact_step():
+                index.query_reads(hb, None, n_reads=n_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=h_hits8, counts=h_cnt, compact=True)
 
         def check():
             if W == "config5":  # no oracle index at this scale: verify sampled hits directly against the packed sequence
@@ -524,6 +529,19 @@ def main():
                "d2h_bytes_per_step": e2e_bytes[1] * world, "steps": args.steps,
                "api": "C ABI with MAZU_MEM_HOST: pinned host inputs in, every result record out",
                "matches_device_path": bool(torch.equal(h_hits[:1_000_000], hits[:1_000_000].cpu()))}
+        if e2e_compact_step is not None:
+            e2e_compact_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                e2e_compact_step()
+            barrier()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e["compact_records"] = {"value": float(n_units) * args.steps * world / float(tt.item()), "unit": unit,
+                                      "d2h_bytes_per_step": (n_units * 8 + 24) * world,
+                                      "api": "mazu_b200_query_reads_compact: 8-byte {unitig_id, pos|match<<30} records"}
 
     if rank != 0:
         if world > 1:

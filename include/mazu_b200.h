@@ -68,6 +68,14 @@ typedef struct mazu_hit {
   uint32_t match;
 } mazu_hit_t;
 
+/* Compact K2UPos for bandwidth-bound callers (PCIe): unitig_len is omitted because the caller owns the UnitigSet
+ * (K2U::unitig_len(unitig_id), src/kphf/mod.rs:61).  pos_match = pos | match << 30; miss = {~0, 0x3FFFFFFF | MAZU_NO_MATCH << 30};
+ * skipped window = {~0, 0x3FFFFFFF | MAZU_SKIPPED << 30}.  Requires every unitig to be shorter than 2^30 bases. */
+typedef struct mazu_hit8 {
+  uint32_t unitig_id;
+  uint32_t pos_match;
+} mazu_hit8_t;
+
 /* UnitigOcc (src/index.rs:304-309) and MappedRefPos (src/index.rs:25-31); fw: Forward=1, Backward=0 (src/lib.rs:51-56) */
 typedef struct mazu_occ {
   uint32_t ref_id;
@@ -177,6 +185,10 @@ mazu_status_t mazu_b200_k2u_batch(const mazu_index_t* idx, const uint64_t* fw_wo
 mazu_status_t mazu_b200_query_reads(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets,
                                     uint64_t n_reads, uint64_t uniform_read_len, int32_t mode, uint64_t* kmer_offsets,
                                     mazu_hit_t* out_hits, uint64_t* counts, int32_t mem, void* stream);
+/* same call, 8-byte mazu_hit8_t records (halves the device->host traffic of the 16-byte form) */
+mazu_status_t mazu_b200_query_reads_compact(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets,
+                                            uint64_t n_reads, uint64_t uniform_read_len, int32_t mode, uint64_t* kmer_offsets,
+                                            mazu_hit8_t* out_hits, uint64_t* counts, int32_t mem, void* stream);
 /* number of k-mer slots query_reads writes for this batch (host arithmetic; read_offsets on host or NULL) */
 uint64_t mazu_b200_count_kmer_slots(const mazu_index_t* idx, const uint64_t* read_offsets, uint64_t n_reads,
                                     uint64_t uniform_read_len);

@@ -26,6 +26,7 @@ LIB_PATH = os.path.join(_HERE, "libmazu_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mazu_b200.h")
 
 HIT_DTYPE = np.dtype([("unitig_id", "<u4"), ("unitig_len", "<u4"), ("pos", "<u4"), ("match", "<u4")])
+HIT8_DTYPE = np.dtype([("unitig_id", "<u4"), ("pos_match", "<u4")])
 OCC_DTYPE = np.dtype([("ref_id", "<u4"), ("pos", "<u4"), ("fw", "<u4")])
 
 NO_MATCH, IDENTITY_MATCH, TWIN_MATCH, SKIPPED = 0, 1, 2, 3
@@ -93,6 +94,7 @@ def _signatures():
         "mazu_b200_k2u_batch": (i32, [vp, vp, u64, u32, vp, i32, vp]),
         "mazu_b200_count_kmer_slots": (u64, [vp, vp, u64, u64]),
         "mazu_b200_query_reads": (i32, [vp, vp, vp, u64, u64, i32, vp, vp, vp, i32, vp]),
+        "mazu_b200_query_reads_compact": (i32, [vp, vp, vp, u64, u64, i32, vp, vp, vp, i32, vp]),
         "mazu_b200_encode_reads": (i32, [vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp]),
         "mazu_b200_decode_occs": (i32, [vp, vp, u64, vp, vp, u64, vp, i32, vp]),
         "mazu_b200_project_hits": (i32, [vp, vp, u64, vp, vp, u64, vp, i32, vp]),
@@ -339,8 +341,10 @@ class ModIndex:
         return int(lib().mazu_b200_count_kmer_slots(self._h, _np_ptr(ro), n_reads, uniform_read_len))
 
     def query_reads(self, bases, read_offsets=None, n_reads=None, uniform_read_len=0, mode=MODE_RANDOM, want_hits=True,
-                    out_hits=None, kmer_offsets=None, counts=None, mem=MEM_HOST, stream=None):
-        """The read loop of `kphf bench` / validate_ckmers.  Host mode returns (hits, counts, kmer_offsets)."""
+                    out_hits=None, kmer_offsets=None, counts=None, mem=MEM_HOST, stream=None, compact=False):
+        """The read loop of `kphf bench` / validate_ckmers.  Host mode returns (hits, counts, kmer_offsets).
+        compact=True writes 8-byte mazu_hit8_t records (HIT8_DTYPE) instead of 16-byte mazu_hit_t."""
+        fn = lib().mazu_b200_query_reads_compact if compact else lib().mazu_b200_query_reads
         if mem == MEM_HOST:
             bases = np.ascontiguousarray(bases, dtype=np.uint8)
             if uniform_read_len:
@@ -354,13 +358,13 @@ class ModIndex:
             else:
                 koffs = kmer_offsets
             if want_hits and out_hits is None:
-                out_hits = np.empty(self.count_kmer_slots(ro, n_reads, uniform_read_len), dtype=HIT_DTYPE)
+                out_hits = np.empty(self.count_kmer_slots(ro, n_reads, uniform_read_len), dtype=HIT8_DTYPE if compact else HIT_DTYPE)
             cnt = np.zeros(3, dtype=np.uint64) if counts is None else counts
-            _check(lib().mazu_b200_query_reads(self._h, _np_ptr(bases), _np_ptr(ro), n_reads, uniform_read_len, mode, _np_ptr(koffs),
+            _check(fn(self._h, _np_ptr(bases), _np_ptr(ro), n_reads, uniform_read_len, mode, _np_ptr(koffs),
                                                _any_ptr(out_hits) if want_hits else None, _np_ptr(cnt), MEM_HOST, None))
             return out_hits, cnt, koffs
-        _check(lib().mazu_b200_query_reads(self._h, _any_ptr(bases), _any_ptr(read_offsets), n_reads, uniform_read_len, mode,
-                                           _any_ptr(kmer_offsets), _any_ptr(out_hits), _any_ptr(counts), MEM_DEVICE, _any_ptr(stream)))
+        _check(fn(self._h, _any_ptr(bases), _any_ptr(read_offsets), n_reads, uniform_read_len, mode,
+                  _any_ptr(kmer_offsets), _any_ptr(out_hits), _any_ptr(counts), MEM_DEVICE, _any_ptr(stream)))
         return out_hits, counts, kmer_offsets
 
     def encode_reads(self, bases, read_offsets, n_reads, uniform_read_len, kmer_offsets, out_fw, out_rc, out_mm, out_off, out_valid,

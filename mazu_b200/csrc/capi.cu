@@ -283,20 +283,20 @@ void launch_k2u_batch(const mazu_index* ix, const u64* d_words, u64 n, Hit* d_ou
 
 template <int MODE, int KIND, u32 FAMILY>
 void launch_qr(const mazu_index* ix, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, const u64* d_kmer_offsets,
-               Hit* d_out, u64* d_counts, cudaStream_t s) {
+               void* d_out, u32 compact, u64* d_counts, cudaStream_t s) {
   auto kern = query_reads_kernel<MODE, KIND, FAMILY>;
   int grid = grid_for(kern, QR_WARPS * 32, ix, QR_WARPS, n_reads);
-  kern<<<grid, QR_WARPS * 32, 0, s>>>(ix->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out,
+  kern<<<grid, QR_WARPS * 32, 0, s>>>(ix->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact,
                                       (unsigned long long*)d_counts);
 }
 
 void launch_query_reads(const mazu_index* ix, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, int mode,
-                        const u64* d_kmer_offsets, Hit* d_out, u64* d_counts, cudaStream_t s) {
+                        const u64* d_kmer_offsets, void* d_out, u32 compact, u64* d_counts, cudaStream_t s) {
   if (n_reads == 0) return;
   const bool ss = ix->view.k2u_kind == MAZU_K2U_SSHASH;
   const bool native = ix->view.mphf.family == MPHF_FAMILY_NATIVE;
   const bool st = mode == MAZU_MODE_STREAMING;
-#define MZ_QR(M, K, F) launch_qr<M, K, F>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, d_counts, s)
+#define MZ_QR(M, K, F) launch_qr<M, K, F>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, s)
   if (ss) {
     if (!native) throw Error(MAZU_ERR_OTHER, "internal: SSHash index without a native MPHF");
     if (st) MZ_QR(1, MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE); else MZ_QR(0, MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE);
@@ -544,9 +544,10 @@ uint64_t mazu_b200_count_kmer_slots(const mazu_index_t* idx, const uint64_t* rea
   return acc;
 }
 
-mazu_status_t mazu_b200_query_reads(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
-                                    uint64_t uniform_read_len, int32_t mode, uint64_t* kmer_offsets, mazu_hit_t* out_hits,
-                                    uint64_t* counts, int32_t mem, void* stream) {
+static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                                      uint64_t uniform_read_len, int32_t mode, uint64_t* kmer_offsets, void* out_hits, uint32_t compact,
+                                      uint64_t* counts, int32_t mem, void* stream) {
+  const u64 rec = compact ? 8 : 16;
   return guarded([&] {
     if (!idx) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
     if (mode != MAZU_MODE_RANDOM && mode != MAZU_MODE_STREAMING) throw Error(MAZU_ERR_INVALID_ARG, "unknown query mode");
@@ -571,7 +572,7 @@ mazu_status_t mazu_b200_query_reads(const mazu_index_t* idx, const uint8_t* base
         device_exclusive_scan((const u64*)lens, d_koffs, n_reads, s);
         MZ_CUDA(cudaFreeAsync(lens, s));
       }
-      launch_query_reads(idx, bases, read_offsets, n_reads, uniform_read_len, mode, d_koffs, (Hit*)out_hits, counts, s);
+      launch_query_reads(idx, bases, read_offsets, n_reads, uniform_read_len, mode, d_koffs, out_hits, compact, counts, s);
       if (tmp_koffs) MZ_CUDA(cudaFreeAsync(tmp_koffs, s));
       return;
     }
@@ -631,7 +632,7 @@ mazu_status_t mazu_b200_query_reads(const mazu_index_t* idx, const uint8_t* base
         d_ro[b] = std::make_unique<DevBuf>((max_reads + 1) * 8, idx->device);
         d_ko[b] = std::make_unique<DevBuf>((max_reads + 1) * 8, idx->device);
       }
-      if (out_hits) d_hits[b] = std::make_unique<DevBuf>(max_slots * 16 + 16, idx->device);
+      if (out_hits) d_hits[b] = std::make_unique<DevBuf>(max_slots * rec + 16, idx->device);
     }
     int b = 0;
     for (size_t c = 0; c + 1 < cuts.size(); ++c, b ^= 1) {
@@ -650,14 +651,39 @@ mazu_status_t mazu_b200_query_reads(const mazu_index_t* idx, const uint8_t* base
       }
       // offsets uploaded are absolute: rebase the data pointers instead of the offset arrays
       const u8* dbases = (const u8*)d_bases[b]->p - (uniform_read_len ? 0 : b0);
-      Hit* dh = out_hits ? (Hit*)d_hits[b]->p - (uniform_read_len ? 0 : s0) : nullptr;
-      launch_query_reads(idx, dbases, dro, r1 - r0, uniform_read_len, mode, dko, dh, (u64*)d_counts.p, s);
-      if (out_hits && ns) MZ_CUDA(cudaMemcpyAsync(out_hits + s0, d_hits[b]->p, ns * 16, cudaMemcpyDeviceToHost, s));
+      void* dh = out_hits ? (void*)((char*)d_hits[b]->p - (uniform_read_len ? 0 : s0 * rec)) : nullptr;
+      launch_query_reads(idx, dbases, dro, r1 - r0, uniform_read_len, mode, dko, dh, compact, (u64*)d_counts.p, s);
+      if (out_hits && ns) MZ_CUDA(cudaMemcpyAsync((char*)out_hits + s0 * rec, d_hits[b]->p, ns * rec, cudaMemcpyDeviceToHost, s));
     }
     MZ_CUDA(cudaStreamSynchronize(sp.s[0]));
     MZ_CUDA(cudaStreamSynchronize(sp.s[1]));
     if (counts) MZ_CUDA(cudaMemcpy(counts, d_counts.p, 24, cudaMemcpyDeviceToHost));
   });
+}
+
+mazu_status_t mazu_b200_query_reads(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                                    uint64_t uniform_read_len, int32_t mode, uint64_t* kmer_offsets, mazu_hit_t* out_hits,
+                                    uint64_t* counts, int32_t mem, void* stream) {
+  return query_reads_impl(idx, bases, read_offsets, n_reads, uniform_read_len, mode, kmer_offsets, out_hits, 0, counts, mem, stream);
+}
+
+mazu_status_t mazu_b200_query_reads_compact(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                                            uint64_t uniform_read_len, int32_t mode, uint64_t* kmer_offsets, mazu_hit8_t* out_hits,
+                                            uint64_t* counts, int32_t mem, void* stream) {
+  if (idx) {
+    // pos shares a word with the match type: every unitig must be shorter than 2^30 bases
+    const auto& acc = idx->unitigs->accum;
+    static thread_local const mazu_index* checked = nullptr;
+    if (checked != idx) {
+      for (size_t i = 0; i + 1 < acc.size(); ++i)
+        if (acc[i + 1] - acc[i] >= (1ULL << 30)) {
+          g_err = "compact hit records need every unitig shorter than 2^30 bases";
+          return MAZU_ERR_INVALID_ARG;
+        }
+      checked = idx;
+    }
+  }
+  return query_reads_impl(idx, bases, read_offsets, n_reads, uniform_read_len, mode, kmer_offsets, out_hits, 1, counts, mem, stream);
 }
 
 mazu_status_t mazu_b200_encode_reads(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,

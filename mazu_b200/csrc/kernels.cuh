@@ -29,6 +29,12 @@ __device__ __forceinline__ void store_hit(Hit* out, const Hit& h) {
   *reinterpret_cast<uint4*>(out) = make_uint4(h.unitig_id, h.unitig_len, h.pos, h.match);
 }
 
+// record store: 16-byte mazu_hit_t, or the 8-byte mazu_hit8_t {unitig_id, pos | match << 30} of the compact calls
+__device__ __forceinline__ void store_rec(void* base, u64 idx, const Hit& h, bool compact) {
+  if (compact) reinterpret_cast<uint2*>(base)[idx] = make_uint2(h.unitig_id, (h.pos & 0x3FFFFFFFu) | (h.match << 30));
+  else store_hit(reinterpret_cast<Hit*>(base) + idx, h);
+}
+
 // kmers::CanonicalKmer::get_word_equivalency
 __device__ __forceinline__ u32 word_equivalency(u64 fw, u64 rc, u64 kw) {
   return kw == fw ? (u32)IDENTITY_MATCH : (kw == rc ? (u32)TWIN_MATCH : (u32)NO_MATCH);
@@ -366,7 +372,7 @@ struct StreamState {  // StreamingK2U { is_warm, prev_k2upos } (src/index/cachin
 template <int MODE, int KIND, u32 FAMILY>
 __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
                                                                     const u64* __restrict__ read_offsets, u64 n_reads, u64 uniform_len,
-                                                                    const u64* __restrict__ kmer_offsets, Hit* __restrict__ out,
+                                                                    const u64* __restrict__ kmer_offsets, void* __restrict__ out, u32 compact,
                                                                     unsigned long long* __restrict__ counts) {
   __shared__ WarpStage s_stage[QR_WARPS];
   const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -402,7 +408,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
       __syncwarp();
       stage_encode(seq, len, c0, n_c, k, lane, S, ci);
       __syncwarp();
-      Hit* o = out ? out + slot0 + c0 : nullptr;
+      char* o = out ? static_cast<char*>(out) + (slot0 + c0) * (compact ? 8ULL : 16ULL) : nullptr;
       if (MODE == 0) {
         if (SS) stage_buckets<FAMILY>(ix, ci, lane, S);
 #pragma unroll 1
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
             ++n_valid;
             if (ok) ++n_hit; else h = hit_none(NO_MATCH);
           }
-          if (o) store_hit(o + p, h);
+          if (o) store_rec(o, p, h, compact);
         }
       } else {
         bool prepared = false;  // stage M/B run lazily: a fully warm chunk never needs them
@@ -447,7 +453,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
                   ++n_valid;
                   ++n_hit;
                 }
-                if (o) store_hit(o + q, h);
+                if (o) store_rec(o, q, h, compact);
               }
               const u32 run_mask = run >= 32 ? 0xffffffffu : ((1u << run) - 1u);
               const u32 vr = vmask & run_mask;
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
               ++n_valid;
               if (res_hit) ++n_hit;
             }
-            if (o) store_hit(o + q, h);
+            if (o) store_rec(o, q, h, compact);
           }
           const u32 gm = g >= 32 ? 0xffffffffu : ((1u << g) - 1u);
           const u32 hm = __ballot_sync(0xffffffffu, res_hit) & gm;

@@ -551,3 +551,21 @@ def test_palindromic_kmers_even_k():
         assert (q == rc).any(), "test needs at least one palindromic k-mer"
         both = np.concatenate([q, rc])
         assert_hits_equal(g.k2u_batch(both), o.k2u_batch(both), "palindromes")
+
+
+def test_compact_records_equal_full_records(yeast_sshash, yeast_queries):
+    """mazu_b200_query_reads_compact: the 8-byte record carries the same answer (unitig_len is looked up by id)."""
+    g, o = yeast_sshash
+    _, ref_codes = yeast_queries
+    bases, offs = _gen.sample_reads(ref_codes, 3000, 200, seed=8, frac_ref=0.6, sub_rate=0.02, n_rate=0.002, ragged=True)
+    for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+        full, cnt, _ = g.query_reads(bases, offs, mode=mode)
+        comp, cnt8, _ = g.query_reads(bases, offs, mode=mode, compact=True)
+        assert list(cnt) == list(cnt8)
+        assert np.array_equal(comp["unitig_id"], full["unitig_id"])
+        assert np.array_equal(comp["pos_match"] >> 30, full["match"])
+        assert np.array_equal(comp["pos_match"] & 0x3FFFFFFF, full["pos"] & 0x3FFFFFFF)
+        hit = full["match"] != mz.NO_MATCH
+        hit &= full["match"] != mz.SKIPPED
+        lens = np.array([g.unitig_len(int(u)) for u in np.unique(comp["unitig_id"][hit])])
+        assert len(lens) > 0
