@@ -569,3 +569,98 @@ def test_compact_records_equal_full_records(yeast_sshash, yeast_queries):
         hit &= full["match"] != mz.SKIPPED
         lens = np.array([g.unitig_len(int(u)) for u in np.unique(comp["unitig_id"][hit])])
         assert len(lens) > 0
+
+
+# --------------------------------------------------------------------------------------------
+# boundary: descriptors, error codes, concurrency
+# --------------------------------------------------------------------------------------------
+def _parse_boophf(path):
+    """mphf.bin -> (levels words, n_bits, last_bitset_rank, n_elem, final keys, final vals); src/pf1/boophf/mod.rs:50-86,269-293"""
+    import struct
+    b = open(path, "rb").read()
+    p = 0
+    gamma, = struct.unpack_from("<d", b, p); p += 8
+    nl, = struct.unpack_from("<i", b, p); p += 4
+    lbr, n_elem = struct.unpack_from("<QQ", b, p); p += 16
+    words, nbits = [], []
+    for _ in range(nl):
+        nb, nw = struct.unpack_from("<QQ", b, p); p += 16
+        words.append(np.frombuffer(b, dtype="<u8", count=nw, offset=p).copy()); p += 8 * nw
+        rs, = struct.unpack_from("<Q", b, p); p += 8 + 8 * rs
+        nbits.append(nb)
+    nf, = struct.unpack_from("<Q", b, p); p += 8
+    kv = np.frombuffer(b, dtype="<u8", count=2 * nf, offset=p).reshape(-1, 2) if nf else np.zeros((0, 2), dtype=np.uint64)
+    return words, np.array(nbits, dtype=np.uint64), lbr, n_elem, kv[:, 0].copy(), kv[:, 1].copy()
+
+
+def test_from_parts_descriptors(yeast_dense, yeast_queries):
+    """ModIndex::from_parts through plain descriptors: UnitigSet + C++ BooPHF + pos vector + U2Pos + refseq, as a
+    Rust host would pass them (PFHash::from_parts, src/kphf/pfhash.rs:34-36; src/index.rs:80-87)."""
+    import ctypes as C
+    g, o = yeast_dense
+    q, _ = yeast_queries
+    us = mz.UnitigSet(o.k, o.useq_words(), o.total_len, o.unitig_starts())
+    words, nbits, lbr, n_elem, fk, fv = _parse_boophf(os.path.join(YEAST_CHR01, "mphf.bin"))
+    ptrs = (C.c_void_p * len(words))(*[w.ctypes.data for w in words])
+    bd = mz.BooPHFDesc(len(words), ptrs, nbits.ctypes.data_as(C.c_void_p), lbr, n_elem, fk.ctypes.data_as(C.c_void_p),
+                       fv.ctypes.data_as(C.c_void_p), len(fk))
+    w, n = C.c_uint64(0), C.c_uint64(0)
+    assert O.lib().orc_compact_vector_read(os.path.join(YEAST_CHR01, "pos.bin").encode(), C.byref(w), C.byref(n), None, 0) == 0
+    vals = np.zeros(n.value, dtype=np.uint64)
+    O.lib().orc_compact_vector_read(os.path.join(YEAST_CHR01, "pos.bin").encode(), C.byref(w), C.byref(n), O._ptr(vals), n.value)
+    pos = mz.PackedVec.pack(vals, w.value)
+    out = C.c_void_p(0)
+    ud, pd = us.desc(), pos.desc()
+    mz._check(mz.lib().mazu_b200_index_create_pfhash_from_parts(C.byref(ud), C.byref(bd), C.byref(pd), 0, C.byref(out)))
+    idx = mz.ModIndex(out.value)
+    assert_hits_equal(idx.k2u_batch(q[:100000]), o.k2u_batch(q[:100000]), "from_parts")
+    # U2Pos + refseq attached from decoded parts -> validate_self as the loader-built index
+    offs, occs = o.decode_occs(np.arange(o.n_unitigs, dtype=np.uint32))
+    ctable = ((occs["pos"].astype(np.uint64) | (occs["fw"].astype(np.uint64) << np.uint64(31))) << np.uint64(32)) | occs["ref_id"].astype(np.uint64)
+    idx.attach_u2pos_dense(ctable, mz.PackedVec.pack(offs))
+    with pytest.raises(mz.MazuError) as e:
+        idx.validate_self()
+    assert e.value.code == mz.ERR_NO_REFSEQ
+    idx.attach_refseq(o.refseq_words(), o.ref_prefix())
+    assert idx.validate_self() == [230188, 170689, 59499, 262130, 0]
+
+
+def test_error_codes():
+    import ctypes as C
+    with pytest.raises(mz.MazuError) as e:
+        mz.DenseIndex.deserialize_from_cpp(os.path.join(PF1, "does_not_exist"))
+    assert e.value.code == -1  # MAZU_ERR_IO
+    us = mz.UnitigSet.from_seqs(["ACGTACGTAC", "TTGACCATGA"], 7)
+    bad = mz.UnitigSet(7, us.useq_words, us.n_bases, np.array([0, 12, 10, 20], dtype=np.uint64))
+    with pytest.raises(mz.MazuError) as e:
+        mz.SSHash.from_unitig_set(bad, 3, mz.SKEW_NONE)
+    assert e.value.code == -3  # MAZU_ERR_EF_NOT_MONOTONE (EFVector::from_iter, src/elias_fano.rs:89-91)
+    with pytest.raises(mz.MazuError) as e:
+        mz.SSHash.from_unitig_set(us, 9, mz.SKEW_NONE)  # assert!(w <= k), src/kphf/sshash.rs:92
+    assert e.value.code == -7
+    with pytest.raises(mz.MazuError):
+        mz.UnitigSet.from_seqs(["ACGTNACGT"], 3)
+    idx = mz.SSHash.from_unitig_set(us, 3, mz.SKEW_NONE)
+    with pytest.raises(mz.MazuError) as e:
+        idx.query_reads(np.frombuffer(b"ACGTACGTAC", dtype=np.uint8), np.array([0, 10], dtype=np.uint64), mode=7)
+    assert e.value.code == -7
+
+
+def test_concurrent_queries_on_one_handle(yeast_sshash, yeast_queries):
+    """queries take &self and are Sync in the reference (src/kphf/mod.rs:69-72): one immutable handle, many host threads."""
+    import threading
+    g, o = yeast_sshash
+    _, ref_codes = yeast_queries
+    inputs = [_gen.sample_reads(ref_codes, 2000, 150, seed=50 + t, frac_ref=0.6, sub_rate=0.01) for t in range(6)]
+    want = [o.query_reads(b, offs, streaming=bool(t % 2))[0] for t, (b, offs) in enumerate(inputs)]
+    got = [None] * len(inputs)
+
+    def work(t):
+        for _ in range(3):
+            got[t] = g.query_reads(inputs[t][0], inputs[t][1], mode=t % 2)[0]
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(len(inputs))]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    for t in range(len(inputs)):
+        assert_hits_equal(got[t], want[t], "thread %d" % t)
