@@ -246,6 +246,7 @@ def main():
     e2e_step = None       # callable: one end-to-end step through host buffers
     e2e_compact_step = None  # same with 8-byte records
     e2e_bytes = (0, 0)
+    e2e_units = None      # units per e2e step (defaults to n_units)
     cpu_fn = None         # callable -> cpu_baseline dict
     t_build = time.time()
 
@@ -332,20 +333,24 @@ def main():
                               mem=mz.MEM_DEVICE, stream=stream.cuda_stream)
 
         if not args.no_e2e:
-            h_bases = torch.empty(n_reads * READ_LEN, dtype=torch.uint8, pin_memory=True)
-            h_bases.copy_(bases)
-            h_hits = torch.empty((n_units, 4), dtype=torch.int32, pin_memory=True)
+            # pinned host buffers: 150 B in + 1920 B out per read.  With several ranks on one host the e2e step is a
+            # bounded batch of the same reads so that N ranks never pin more than ~8 GB each.
+            e2e_reads = n_reads if world == 1 else min(n_reads, 2_500_000)
+            e2e_units = e2e_reads * nk_per_read
+            h_bases = torch.empty(e2e_reads * READ_LEN, dtype=torch.uint8, pin_memory=True)
+            h_bases.copy_(bases[: e2e_reads * READ_LEN])
+            h_hits = torch.empty((e2e_units, 4), dtype=torch.int32, pin_memory=True)
             h_cnt = np.zeros(3, dtype=np.uint64)
             hb = h_bases.numpy()
 
             def e2e_step():
-                index.query_reads(hb, None, n_reads=n_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=h_hits, counts=h_cnt)
+                index.query_reads(hb, None, n_reads=e2e_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=h_hits, counts=h_cnt)
 
-            e2e_bytes = (n_reads * READ_LEN, n_units * 16 + 24)
-            h_hits8 = torch.empty((n_units, 2), dtype=torch.int32, pin_memory=True)
+            e2e_bytes = (e2e_reads * READ_LEN, e2e_units * 16 + 24)
+            h_hits8 = torch.empty((e2e_units, 2), dtype=torch.int32, pin_memory=True)
 
             def e2e_compact_step():
-                index.query_reads(hb, None, n_reads=n_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=h_hits8, counts=h_cnt, compact=True)
+                index.query_reads(hb, None, n_reads=e2e_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=h_hits8, counts=h_cnt, compact=True)
 
         def check():
             if W == "config5":  # no oracle index at this scale: verify sampled hits directly against the packed sequence
@@ -525,7 +530,9 @@ def main():
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": float(n_units) * args.steps * world / float(tt.item()), "unit": unit, "h2d_bytes_per_step": e2e_bytes[0] * world,
+        eu = e2e_units if e2e_units is not None else n_units
+        e2e = {"value": float(eu) * args.steps * world / float(tt.item()), "unit": unit, "units_per_step_per_gpu": eu,
+               "h2d_bytes_per_step": e2e_bytes[0] * world,
                "d2h_bytes_per_step": e2e_bytes[1] * world, "steps": args.steps,
                "api": "C ABI with MAZU_MEM_HOST: pinned host inputs in, every result record out",
                "matches_device_path": bool(torch.equal(h_hits[:1_000_000], hits[:1_000_000].cpu()))}
@@ -539,8 +546,8 @@ def main():
             tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e["compact_records"] = {"value": float(n_units) * args.steps * world / float(tt.item()), "unit": unit,
-                                      "d2h_bytes_per_step": (n_units * 8 + 24) * world,
+            e2e["compact_records"] = {"value": float(eu) * args.steps * world / float(tt.item()), "unit": unit,
+                                      "d2h_bytes_per_step": (eu * 8 + 24) * world,
                                       "api": "mazu_b200_query_reads_compact: 8-byte {unitig_id, pos|match<<30} records"}
 
     if rank != 0:
