@@ -53,7 +53,8 @@ enum { MAZU_NO_MATCH = 0, MAZU_IDENTITY_MATCH = 1, MAZU_TWIN_MATCH = 2,
 enum { MAZU_MEM_HOST = 0, MAZU_MEM_DEVICE = 1 };
 enum { MAZU_MODE_RANDOM = 0,    /* K2U::k2u per k-mer                 (src/bin/kphf/main.rs:311-322) */
        MAZU_MODE_STREAMING = 1  /* .as_streaming() / StreamingK2U     (src/index/caching.rs:65-103); cursor reset per read */ };
-enum { MAZU_K2U_PFHASH = 0, MAZU_K2U_SSHASH = 1 };
+enum { MAZU_K2U_PFHASH = 0, MAZU_K2U_SSHASH = 1,
+       MAZU_K2U_SAMPLED_PFHASH = 2 /* pufferfish sparse index, load-only (src/kphf/pfhash.rs:137-285) */ };
 enum { MAZU_U2POS_NONE = 0, MAZU_U2POS_DENSE = 1, MAZU_U2POS_PISCEM = 2 };
 enum { MAZU_INDEX_PUFFERFISH_DENSE = 0, /* ModIndex<PFHash, DenseUnitigTable>  src/index/defaults.rs:14 */
        MAZU_INDEX_PISCEM = 1            /* ModIndex<SSHash, PiscemUnitigTable> src/index/defaults.rs:15 */ };
@@ -122,6 +123,8 @@ int32_t mazu_b200_device_count(void);
  * ------------------------------------------------------------------------------------------- */
 /* DenseIndex::deserialize_from_cpp(dir)                         src/pf1/dense_index.rs:33-97 */
 mazu_status_t mazu_b200_dense_index_deserialize_from_cpp(const char* dir, int32_t device, mazu_index_t** out);
+/* SparseIndex::deserialize_from_cpp(dir): ModIndex<SampledPFHash<BooPHF>, DenseUnitigTable>   src/pf1/sparse_index.rs:32-110 */
+mazu_status_t mazu_b200_sparse_index_deserialize_from_cpp(const char* dir, int32_t device, mazu_index_t** out);
 /* PufferfishDenseIndexDefault::from_cf_prefix / PiscemIndex::from_cf_prefix
  *                                   src/index/defaults.rs:17-58, src/index/piscem_index.rs:14-58 */
 mazu_status_t mazu_b200_index_from_cf_prefix(const char* prefix, int32_t index_kind, uint32_t w, uint64_t skew_param,
@@ -158,7 +161,8 @@ enum { MAZU_INFO_K = 0, MAZU_INFO_N_UNITIGS = 1, MAZU_INFO_N_KMERS = 2, MAZU_INF
        MAZU_INFO_N_MINIMIZERS = 4 /* SSHash::n_minimizers, sshash.rs:333-335 */,
        MAZU_INFO_N_KMERS_IN_SKEW_INDEX = 5 /* sshash.rs:337-339 */, MAZU_INFO_N_REFS = 6, MAZU_INFO_N_TOTAL_OCCS = 7,
        MAZU_INFO_K2U_KIND = 8, MAZU_INFO_U2POS_KIND = 9, MAZU_INFO_DEVICE_BYTES = 10, MAZU_INFO_W = 11,
-       MAZU_INFO_N_MINIMIZER_OCCS = 12, MAZU_INFO_MPHF_LEVELS = 13, MAZU_INFO_DEVICE = 14 };
+       MAZU_INFO_N_MINIMIZER_OCCS = 12, MAZU_INFO_MPHF_LEVELS = 13, MAZU_INFO_DEVICE = 14,
+       MAZU_INFO_SAMPLE_SIZE = 15, MAZU_INFO_EXTENSION_SIZE = 16 /* SampledPFHash, src/kphf/pfhash.rs:149-150 */ };
 uint64_t mazu_b200_index_info(const mazu_index_t* idx, int32_t what);
 /* K2U::unitig_len(id)  src/kphf/mod.rs:61 ; UnitigSet::unitig_start_pos  src/unitig_set.rs:197-199 */
 mazu_status_t mazu_b200_unitig_len(const mazu_index_t* idx, uint64_t unitig_id, uint64_t* len, uint64_t* start_pos);

@@ -32,7 +32,7 @@ OCC_DTYPE = np.dtype([("ref_id", "<u4"), ("pos", "<u4"), ("fw", "<u4")])
 NO_MATCH, IDENTITY_MATCH, TWIN_MATCH, SKIPPED = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 MODE_RANDOM, MODE_STREAMING = 0, 1
-K2U_PFHASH, K2U_SSHASH = 0, 1
+K2U_PFHASH, K2U_SSHASH, K2U_SAMPLED_PFHASH = 0, 1, 2
 U2POS_NONE, U2POS_DENSE, U2POS_PISCEM = 0, 1, 2
 INDEX_PUFFERFISH_DENSE, INDEX_PISCEM = 0, 1
 SKEW_NONE = 0xFFFFFFFFFFFFFFFF
@@ -44,7 +44,7 @@ ERR_NO_REFSEQ = -9
 
 (INFO_K, INFO_N_UNITIGS, INFO_N_KMERS, INFO_SUM_UNITIGS_LEN, INFO_N_MINIMIZERS, INFO_N_KMERS_IN_SKEW_INDEX, INFO_N_REFS,
  INFO_N_TOTAL_OCCS, INFO_K2U_KIND, INFO_U2POS_KIND, INFO_DEVICE_BYTES, INFO_W, INFO_N_MINIMIZER_OCCS, INFO_MPHF_LEVELS,
- INFO_DEVICE) = range(15)
+ INFO_DEVICE, INFO_SAMPLE_SIZE, INFO_EXTENSION_SIZE) = range(17)
 
 
 class MazuError(RuntimeError):
@@ -80,6 +80,7 @@ def _signatures():
         "mazu_b200_last_error": (cp, []),
         "mazu_b200_device_count": (i32, []),
         "mazu_b200_dense_index_deserialize_from_cpp": (i32, [cp, i32, pp]),
+        "mazu_b200_sparse_index_deserialize_from_cpp": (i32, [cp, i32, pp]),
         "mazu_b200_index_from_cf_prefix": (i32, [cp, i32, u32, u64, u64, i32, pp]),
         "mazu_b200_index_create_sshash": (i32, [C.POINTER(UnitigSetDesc), u32, u64, u64, i32, pp]),
         "mazu_b200_index_create_pfhash": (i32, [C.POINTER(UnitigSetDesc), i32, pp]),
@@ -430,6 +431,16 @@ class StreamingIndex:
 
 class DenseIndex(ModIndex):
     """pf1::DenseIndex = ModIndex<PFHash<BooPHF<u64>>, DenseUnitigTable> (src/pf1/dense_index.rs:25)."""
+
+
+class SparseIndex:
+    """pf1::SparseIndex = ModIndex<SampledPFHash<BooPHF<u64>>, DenseUnitigTable> (src/pf1/sparse_index.rs:24)."""
+
+    @staticmethod
+    def deserialize_from_cpp(d, device=0):
+        out = C.c_void_p(0)
+        _check(lib().mazu_b200_sparse_index_deserialize_from_cpp(os.fspath(d).encode(), device, C.byref(out)))
+        return ModIndex(out.value)
 
 
 class PiscemIndex:

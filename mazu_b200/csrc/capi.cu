@@ -192,6 +192,17 @@ void upload_k2u(mazu_index& ix) {
       v.skew_pos = upload_packed(h.skew_pos, ix.device, d->bufs, d->bytes);
     }
   }
+  if (h.kind == MAZU_K2U_SAMPLED_PFHASH) {
+    v.sampled = upload_mphf(h.sampled, ix.device, *d);
+    auto bc = upload(h.canonical_bits, ix.device, 2), bd = upload(h.direction_bits, ix.device, 2);
+    d->bufs.insert(d->bufs.end(), {bc, bd});
+    d->bytes += bc->bytes + bd->bytes;
+    v.canonical_bits = (const u64*)bc->p;
+    v.direction_bits = (const u64*)bd->p;
+    v.ext_sizes = upload_packed(h.ext_sizes, ix.device, d->bufs, d->bytes);
+    v.ext_bases = upload_packed(h.ext_bases, ix.device, d->bufs, d->bytes);
+    v.extension_size = (u32)h.extension_size;
+  }
   ix.d_k2u = d;
 }
 void upload_u2pos(mazu_index& ix) {
@@ -300,6 +311,8 @@ void launch_query_reads(const mazu_index* ix, const u8* d_bases, const u64* d_re
   if (ss) {
     if (!native) throw Error(MAZU_ERR_OTHER, "internal: SSHash index without a native MPHF");
     if (st) MZ_QR(1, MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE); else MZ_QR(0, MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE);
+  } else if (ix->view.k2u_kind == MAZU_K2U_SAMPLED_PFHASH) {
+    if (st) MZ_QR(1, MAZU_K2U_SAMPLED_PFHASH, MPHF_FAMILY_BOOPHF); else MZ_QR(0, MAZU_K2U_SAMPLED_PFHASH, MPHF_FAMILY_BOOPHF);
   } else if (native) {
     if (st) MZ_QR(1, MAZU_K2U_PFHASH, MPHF_FAMILY_NATIVE); else MZ_QR(0, MAZU_K2U_PFHASH, MPHF_FAMILY_NATIVE);
   } else {
@@ -349,6 +362,13 @@ mazu_status_t mazu_b200_dense_index_deserialize_from_cpp(const char* dir, int32_
   return guarded([&] {
     if (!dir || !out) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
     *out = index_from_loaded(load_pf1_dense(dir), device);
+  });
+}
+
+mazu_status_t mazu_b200_sparse_index_deserialize_from_cpp(const char* dir, int32_t device, mazu_index_t** out) {
+  return guarded([&] {
+    if (!dir || !out) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    *out = index_from_loaded(load_pf1_sparse(dir), device);
   });
 }
 
@@ -488,6 +508,8 @@ uint64_t mazu_b200_index_info(const mazu_index_t* idx, int32_t what) {
     case MAZU_INFO_N_MINIMIZER_OCCS: return idx->k2u->n_minimizer_occs;
     case MAZU_INFO_MPHF_LEVELS: return idx->view.mphf.n_levels;
     case MAZU_INFO_DEVICE: return (u64)idx->device;
+    case MAZU_INFO_SAMPLE_SIZE: return idx->k2u->sample_size;
+    case MAZU_INFO_EXTENSION_SIZE: return idx->k2u->extension_size;
   }
   return 0;
 }

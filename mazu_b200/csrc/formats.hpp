@@ -138,12 +138,12 @@ struct LoadedIndex {
   std::shared_ptr<RefSeqHost> refs;
 };
 
-// DenseIndex::deserialize_from_cpp (src/pf1/dense_index.rs:33-97)
-inline LoadedIndex load_pf1_dense(const std::string& dir) {
-  LoadedIndex L;
+// the parts every pufferfish index directory shares: unitigs (seq.bin + rank.bin), ctable + ctg_offsets, references
+inline void load_pf1_unitigs_u2pos_refs(const std::string& dir, LoadedIndex& L, u32& k_out) {
   std::string info_path = dir + "/info.json";
   std::string info = read_text(info_path);
   u32 k = (u32)json_u64_field(info, "k", info_path);
+  k_out = k;
   // unitigs: seq.bin (2-bit) + rank.bin (1 at the last base of each unitig)
   PackedVec seq = load_compact_vector(dir + "/seq.bin");
   if (seq.width != 2) throw Error(MAZU_ERR_INVALID_DATA, "seq.bin: width != 2");
@@ -167,10 +167,6 @@ inline LoadedIndex load_pf1_dense(const std::string& dir) {
   }
   us->validate();
   L.unitigs = us;
-  BooPHFFile mphf = load_boophf(dir + "/mphf.bin");
-  PackedVec pos = load_compact_vector(dir + "/pos.bin");
-  mazu_packed_vec_desc_t pd{pos.words.data(), pos.width, pos.len};
-  L.k2u = pfhash_from_parts(us, mphf.desc(), pd);
   // ctable.bin: Vec<String> ref_names, Vec<u32> ref_exts, Vec<u64> ctable, EOF (unitig_table.rs:28-49)
   auto up = std::make_shared<U2PosHost>();
   {
@@ -211,6 +207,63 @@ inline LoadedIndex load_pf1_dense(const std::string& dir) {
     for (u64 i = 0; i < n; ++i) rs->prefix.push_back(r.get<u64>());
   }
   L.refs = rs;
+}
+
+
+// DenseIndex::deserialize_from_cpp (src/pf1/dense_index.rs:33-97)
+inline LoadedIndex load_pf1_dense(const std::string& dir) {
+  LoadedIndex L;
+  u32 k = 0;
+  load_pf1_unitigs_u2pos_refs(dir, L, k);
+  BooPHFFile mphf = load_boophf(dir + "/mphf.bin");
+  PackedVec pos = load_compact_vector(dir + "/pos.bin");
+  mazu_packed_vec_desc_t pd{pos.words.data(), pos.width, pos.len};
+  L.k2u = pfhash_from_parts(L.unitigs, mphf.desc(), pd);
+  return L;
+}
+
+// SparseIndex::deserialize_from_cpp (src/pf1/sparse_index.rs:32-110): the dense loader's unitigs / U2Pos / references
+// plus the sampled position table, presence / canonical / direction bits and the extension words
+inline LoadedIndex load_pf1_sparse(const std::string& dir) {
+  LoadedIndex L;
+  u32 k = 0;
+  load_pf1_unitigs_u2pos_refs(dir, L, k);
+  std::string info_path = dir + "/info.json";
+  std::string info = read_text(info_path);
+  auto H = std::make_shared<K2UHost>();
+  H->kind = MAZU_K2U_SAMPLED_PFHASH;
+  H->unitigs = L.unitigs;
+  BooPHFFile mphf = load_boophf(dir + "/mphf.bin");
+  H->mphf = MphfHost::from_boophf(mphf.desc());
+  H->pos = load_compact_vector(dir + "/sample_pos.bin");
+  H->ext_sizes = load_compact_vector(dir + "/extensionSize.bin");
+  H->ext_bases = load_compact_vector(dir + "/extension.bin");
+  H->sample_size = json_u64_field(info, "sample_size", info_path);
+  H->extension_size = json_u64_field(info, "extension_size", info_path);
+  if (H->extension_size == 0 || H->extension_size > 32) throw Error(MAZU_ERR_INVALID_DATA, info_path + ": extension_size out of range");
+  auto bits = [&](const char* name, u64& len) {
+    PackedVec v = load_compact_vector(dir + "/" + name);
+    if (v.width != 1) throw Error(MAZU_ERR_INVALID_DATA, std::string(name) + ": width != 1");
+    len = v.len;
+    std::vector<u64> w((v.len + 63) / 64 + 2, 0);
+    for (size_t i = 0; i < (v.len + 63) / 64; ++i) w[i] = v.words[i];
+    if (v.len & 63) w[v.len >> 6] &= (1ULL << (v.len & 63)) - 1;
+    return w;
+  };
+  u64 n_presence = 0, n_c = 0, n_d = 0;
+  std::vector<u64> presence = bits("presence.bin", n_presence);
+  H->canonical_bits = bits("canonical.bin", n_c);
+  H->direction_bits = bits("direction.bin", n_d);
+  if (n_presence != L.unitigs->n_kmers()) throw Error(MAZU_ERR_INVALID_DATA, "presence.bin: len != n_kmers");
+  H->sampled.meta.family = MPHF_FAMILY_BOOPHF;
+  H->sampled.meta.n_keys = n_presence;
+  H->sampled.append_level_from_bits(presence, n_presence, n_presence);
+  H->sampled.fb_keys.push_back(0);
+  H->sampled.fb_vals.push_back(0);
+  if (H->sampled.total_level_ones() != H->pos.len) throw Error(MAZU_ERR_INVALID_DATA, "presence.bin: #ones != sample_pos.len");
+  if (H->ext_sizes.len != n_presence - H->pos.len || H->ext_bases.len != H->ext_sizes.len || n_c < H->ext_sizes.len || n_d < H->ext_sizes.len)
+    throw Error(MAZU_ERR_INVALID_DATA, "sparse index: extension tables do not match the number of unsampled k-mers");
+  L.k2u = H;
   return L;
 }
 

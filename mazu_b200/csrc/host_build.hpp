@@ -419,6 +419,11 @@ struct K2UHost {
   MphfHost skew_mphf;
   PackedVec skew_pos;
   u64 n_skew_kmers = 0;
+  // SampledPFHash (pufferfish sparse index): `pos` holds sampled_pos
+  MphfHost sampled;  // presence bits as a single ranked level
+  std::vector<u64> canonical_bits, direction_bits;
+  PackedVec ext_sizes, ext_bases;
+  u64 sample_size = 0, extension_size = 0;
 };
 
 struct MinOcc {

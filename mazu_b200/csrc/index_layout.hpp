@@ -336,6 +336,14 @@ struct IndexView {
   u64 skew_param;
   RankedLevels skew_mphf;
   PackedVecView skew_pos;
+  // SampledPFHash only (src/kphf/pfhash.rs:139-151): pos is `sampled_pos`
+  RankedLevels sampled;        // `sampled_vec` as one level of ranked blocks (bit test + rank in one sector)
+  const u64* canonical_bits;   // `canonical_vec`
+  const u64* direction_bits;   // `direction_vec`
+  PackedVecView ext_sizes;
+  PackedVecView ext_bases;
+  u32 extension_size;
+  u32 _pad_sampled;
   // U2Pos
   const u64* ctable_words;  // DENSE: one u64 per occurrence; PISCEM: packed `ctable_width`-bit fields
   u64 n_occs;

@@ -102,8 +102,11 @@ __device__ __forceinline__ bool sshash_k2u(const IndexView& ix, u64 fw, u64 rc, 
   return false;
 }
 
+template <u32 FAMILY>
+__device__ __forceinline__ bool sampled_pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc, Hit& out, u64* ustart);
 __device__ __forceinline__ bool k2u_any(const IndexView& ix, u64 fw, u64 rc, Hit& out) {
   if (ix.k2u_kind == MAZU_K2U_PFHASH) return pfhash_k2u(ix, fw, rc, out);
+  if (ix.k2u_kind == MAZU_K2U_SAMPLED_PFHASH) return sampled_pfhash_k2u_t<MPHF_FAMILY_BOOPHF>(ix, fw, rc, out, nullptr);
   MinimizerResult m = canonical_minimizer_naive(fw, rc, ix.unitigs.k, ix.w, ix.seed);
   return sshash_k2u(ix, fw, rc, m.word, m.offset, out);
 }
@@ -361,6 +364,62 @@ __device__ __forceinline__ bool pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc
   return finish_hit(ix.unitigs, km_pos, mt, false, out, ustart);
 }
 
+// SampledPFHash::k2u (src/kphf/pfhash.rs:190-285): sampled k-mers carry their position; the others walk
+// <= extension_size stored bases to the nearest sampled k-mer, re-hash, and shift the sampled position back.
+template <u32 FAMILY>
+__device__ __forceinline__ bool sampled_pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc, Hit& out, u64* ustart) {
+  const u32 k = ix.unitigs.k;
+  u64 idx;
+  if (!mphf_lookup_t<FAMILY>(ix.mphf, fw <= rc ? fw : rc, idx)) return false;
+  if (idx >= ix.sampled.n_keys) return false;
+  u64 blk = idx / MPHF_BLOCK_BITS;
+  u32 bit = (u32)(idx - blk * MPHF_BLOCK_BITS);
+  u64 pos;
+  if (ranked_test(ix.sampled, 0, blk, bit)) {
+    pos = packed_get(ix.pos, ranked_rank(ix.sampled, 0, blk, bit));
+  } else {
+    const u64 ext_pos = idx - ranked_rank(ix.sampled, 0, blk, bit);  // unsampled k-mers have one extension entry each
+    const u64 ext_word = packed_get(ix.ext_bases, ext_pos);
+    u64 f = fw, r = rc;
+    const bool canon_bit = (__ldg(ix.canonical_bits + (ext_pos >> 6)) >> (ext_pos & 63)) & 1ULL;
+    if ((!canon_bit) != (!(f <= r))) {  // km.swap() (pfhash.rs:213-215)
+      u64 t = f;
+      f = r;
+      r = t;
+    }
+    const bool shift_fw = (__ldg(ix.direction_bits + (ext_pos >> 6)) >> (ext_pos & 63)) & 1ULL;
+    const u32 n_ext = (u32)packed_get(ix.ext_sizes, ext_pos) + 1;  // extension_size - llimit
+    const u64 mask = kmer_mask(k);
+    long long shift = 0;
+    for (u32 j = 0; j < n_ext; ++j) {
+      u64 code = (ext_word >> (2 * (ix.extension_size - 1 - j))) & 3ULL;
+      if (shift_fw) {  // append_base
+        f = ((f >> 2) | (code << (2 * (k - 1)))) & mask;
+        r = ((r << 2) | (3ULL - code)) & mask;
+        --shift;
+      } else {  // prepend_base
+        f = ((f << 2) | code) & mask;
+        r = (r >> 2) | ((3ULL - code) << (2 * (k - 1)));
+        ++shift;
+      }
+    }
+    if (!mphf_lookup_t<FAMILY>(ix.mphf, f <= r ? f : r, idx)) return false;
+    if (idx >= ix.sampled.n_keys) return false;
+    blk = idx / MPHF_BLOCK_BITS;
+    bit = (u32)(idx - blk * MPHF_BLOCK_BITS);
+    if (!ranked_test(ix.sampled, 0, blk, bit)) return false;
+    pos = (u64)((long long)packed_get(ix.pos, ranked_rank(ix.sampled, 0, blk, bit)) + shift);
+    // is_valid_useq_pos (unitig_set.rs:235-245)
+    if (pos > ix.unitigs.total_len - k) return false;
+    u64 id, s, e;
+    unitig_locate(ix.unitigs, pos, id, s, e);
+    if (pos + k > e) return false;
+  }
+  u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, pos));
+  if (mt == NO_MATCH) return false;
+  return finish_hit(ix.unitigs, pos, mt, false, out, ustart);
+}
+
 struct StreamState {  // StreamingK2U { is_warm, prev_k2upos } (src/index/caching.rs:13-17)
   u32 warm, uid, ulen, pos, o;
   u64 ustart;
@@ -416,7 +475,8 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
           Hit h = hit_none(SKIPPED);
           if (chunk_valid(ci, p)) {
             u64 fw = S.fw[p], rc = revcomp(fw, k);
-            bool ok = SS ? verify_sshash<FAMILY>(ix, S, p, fw, rc, h) : pfhash_k2u_t<FAMILY>(ix, fw, rc, h);
+            bool ok = SS ? verify_sshash<FAMILY>(ix, S, p, fw, rc, h)
+                         : (KIND == MAZU_K2U_SAMPLED_PFHASH ? sampled_pfhash_k2u_t<FAMILY>(ix, fw, rc, h, nullptr) : pfhash_k2u_t<FAMILY>(ix, fw, rc, h));
             ++n_valid;
             if (ok) ++n_hit; else h = hit_none(NO_MATCH);
           }
@@ -481,7 +541,9 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
           u64 cold_ustart = 0;
           bool cold_hit = false;
           if (valid) {
-            cold_hit = SS ? verify_sshash<FAMILY>(ix, S, q, fw, rc, cold, &cold_ustart) : pfhash_k2u_t<FAMILY>(ix, fw, rc, cold, &cold_ustart);
+            cold_hit = SS ? verify_sshash<FAMILY>(ix, S, q, fw, rc, cold, &cold_ustart)
+                          : (KIND == MAZU_K2U_SAMPLED_PFHASH ? sampled_pfhash_k2u_t<FAMILY>(ix, fw, rc, cold, &cold_ustart)
+                                                             : pfhash_k2u_t<FAMILY>(ix, fw, rc, cold, &cold_ustart));
             if (!cold_hit) cold = hit_none(NO_MATCH);
           }
           const u32 chm = __ballot_sync(0xffffffffu, cold_hit);

@@ -190,6 +190,13 @@ void* orc_dense_index_load(const char* dir) {  // pf1/dense_index.rs:33-97
     return h;
   });
 }
+void* orc_sparse_index_load(const char* dir) {  // pf1/sparse_index.rs:32-110
+  return guard_ptr([&]() -> void* {
+    auto h = new Handle();
+    h->idx = sparse_index_from_pf1(dir);
+    return h;
+  });
+}
 void* orc_index_from_cf(const char* prefix, int kind, int w, u64 skew, u64 seed) {
   return guard_ptr([&]() -> void* { return make_cf(prefix, kind, w, skew, seed); });
 }
@@ -265,7 +272,8 @@ int orc_attach_u2pos(void* hp, int kind, const u64* offsets, u64 n_unitigs, cons
 void orc_index_free(void* hp) { delete (Handle*)hp; }
 
 // what: 0 k, 1 n_unitigs, 2 n_kmers, 3 total_len, 4 n_minimizers (len of prefix sum), 5 n_kmers_in_skew,
-//       6 n_refs, 7 n_total_occs, 8 n_minimizer_occs, 9 piscem ref_shift, 10 piscem pos_mask, 11 has_refseq
+//       6 n_refs, 7 n_total_occs, 8 n_minimizer_occs, 9 piscem ref_shift, 10 piscem pos_mask, 11 has_refseq,
+//       12 sparse sample_size, 13 sparse extension_size
 u64 orc_index_info(void* hp, int what) {
   Handle* h = (Handle*)hp;
   const UnitigSet& us = h->idx->k2u->unitigs();
@@ -282,6 +290,8 @@ u64 orc_index_info(void* hp, int what) {
     case 9: { auto* p = dynamic_cast<PiscemUnitigTable*>(h->idx->u2pos.get()); return p ? p->ref_shift : 0; }
     case 10: { auto* p = dynamic_cast<PiscemUnitigTable*>(h->idx->u2pos.get()); return p ? p->pos_mask : 0; }
     case 11: return h->idx->refs && h->idx->refs->has_seq;
+    case 12: { auto* p = dynamic_cast<SampledPFHash*>(h->idx->k2u.get()); return p ? p->sample_size : 0; }
+    case 13: { auto* p = dynamic_cast<SampledPFHash*>(h->idx->k2u.get()); return p ? p->extension_size : 0; }
   }
   return 0;
 }

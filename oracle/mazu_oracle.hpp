@@ -1263,6 +1263,100 @@ inline std::unique_ptr<ModIndex> dense_index_from_pf1(const std::string& dir) {
 }
 
 // ------------------------------------------------------------------------------------
+// kphf/pfhash.rs:137-285 SampledPFHash (pufferfish sparse index, load-only) and its loader
+// pf1/sparse_index.rs:32-110.  CanonicalKmer::append_base / prepend_base belong to the `kmers`
+// crate (not in tree); their meaning is pinned by validate_self on small_txome_index_sparse
+// (sparse_index.rs:163-192): append = drop the first base and add one at the end of the fw
+// k-mer, prepend = drop the last base and add one at the front.
+// ------------------------------------------------------------------------------------
+inline BitVector bitvector_from_compact(const std::string& path) {
+  IntVector iv = read_compact_vector(path);
+  if (iv.width != 1) throw OracleError(path + ": width != 1");
+  BitVector bv(iv.len);
+  for (size_t i = 0; i < bv.words.size() && i < iv.words.size(); ++i) bv.words[i] = iv.words[i];
+  if (iv.len & 63) bv.words[iv.len >> 6] &= (1ULL << (iv.len & 63)) - 1;
+  for (size_t i = (iv.len + 63) / 64; i < bv.words.size(); ++i) bv.words[i] = 0;
+  bv.enable_rank();
+  return bv;
+}
+struct SampledPFHash : K2U {
+  UnitigSet us;
+  BooPHF mphf;
+  IntVector sampled_pos, ext_sizes, ext_bases;
+  BitVector sampled_vec, canonical_vec, direction_vec;
+  u64 sample_size = 0, extension_size = 0;
+  const UnitigSet& unitigs() const override { return us; }
+  bool k2u_w_pos(const CanonicalKmer& km, u64 pos, K2UPos& out) const {  // pfhash.rs:262-285
+    u64 kw = us.get_kmer_u64_from_useq_pos(pos);
+    MatchType mt = km.word_equivalency(kw);
+    if (mt == NoMatch) return false;
+    u64 uid = us.pos_to_id(pos);
+    out.unitig_id = uid;
+    out.unitig_len = us.unitig_len(uid);
+    out.pos = pos - us.unitig_start_pos(uid);
+    out.o = mt;
+    return true;
+  }
+  bool k2u(const CanonicalKmer& kmer, K2UPos& out) const override {  // pfhash.rs:190-259
+    u64 idx;
+    if (!mphf.lookup(kmer.canonical_word(), idx)) return false;
+    if (idx >= sampled_vec.len) return false;
+    if (sampled_vec.bit(idx)) {
+      u64 pos = sampled_pos.get(sampled_vec.rank(idx));
+      return k2u_w_pos(kmer, pos, out);
+    }
+    int64_t signed_shift = 0;
+    u64 current_rank = sampled_vec.rank(idx);
+    u64 extension_pos = idx - current_rank;
+    u64 extension_word = ext_bases.get(extension_pos);
+    CanonicalKmer km = kmer;
+    if ((!canonical_vec.bit(extension_pos)) ^ (!km.is_fw_canonical())) km.swap();
+    bool shift_fw = direction_vec.bit(extension_pos);
+    u64 llimit = extension_size - (ext_sizes.get(extension_pos) + 1);
+    const u64 mask = kmer_mask(km.k);
+    for (u64 i = extension_size; i >= llimit + 1; --i) {
+      u64 ssize = 2 * (i - 1);
+      u64 code = (extension_word >> ssize) & 3;
+      if (shift_fw) {  // append_base
+        km.fw = ((km.fw >> 2) | (code << (2 * (km.k - 1)))) & mask;
+        km.rc = ((km.rc << 2) | (3 - code)) & mask;
+        signed_shift -= 1;
+      } else {  // prepend_base
+        km.fw = ((km.fw << 2) | code) & mask;
+        km.rc = (km.rc >> 2) | ((3 - code) << (2 * (km.k - 1)));
+        signed_shift += 1;
+      }
+    }
+    if (!mphf.lookup(km.canonical_word(), idx)) return false;
+    if (idx >= sampled_vec.len || !sampled_vec.bit(idx)) return false;
+    u64 sample_pos = sampled_pos.get(sampled_vec.rank(idx));
+    u64 pos = (u64)((int64_t)sample_pos + signed_shift);
+    if (!us.is_valid_useq_pos(pos)) return false;
+    return k2u_w_pos(kmer, pos, out);
+  }
+};
+inline std::unique_ptr<ModIndex> sparse_index_from_pf1(const std::string& dir) {  // pf1/sparse_index.rs:32-110
+  std::string info = slurp(dir + "/info.json");
+  int k = (int)json_u64(info, "k");
+  auto idx = std::make_unique<ModIndex>();
+  auto h = std::make_unique<SampledPFHash>();
+  h->us = unitig_set_from_pf1(dir, k);
+  h->mphf = BooPHF::load(dir + "/mphf.bin");
+  h->sampled_pos = read_compact_vector(dir + "/sample_pos.bin");
+  h->canonical_vec = bitvector_from_compact(dir + "/canonical.bin");
+  h->direction_vec = bitvector_from_compact(dir + "/direction.bin");
+  h->ext_sizes = read_compact_vector(dir + "/extensionSize.bin");
+  h->ext_bases = read_compact_vector(dir + "/extension.bin");
+  h->sampled_vec = bitvector_from_compact(dir + "/presence.bin");
+  h->sample_size = json_u64(info, "sample_size");
+  h->extension_size = json_u64(info, "extension_size");
+  idx->k2u = std::move(h);
+  idx->u2pos = dense_unitig_table_from_pf1(dir);
+  idx->refs = refseq_from_pf1(dir);
+  return idx;
+}
+
+// ------------------------------------------------------------------------------------
 // cuttlefish.rs:11-183, unitig_set.rs:119-165, spt.rs:67-140, spt_compact.rs:287-389
 // ------------------------------------------------------------------------------------
 struct CfToken {

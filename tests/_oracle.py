@@ -56,6 +56,7 @@ def lib():
             "orc_canonical_minimizer": (None, [u64, i32, i32, u64, vp, vp]),
             "orc_encode_read": (u64, [vp, u64, i32, i32, u64, vp, vp, vp, vp, vp]),
             "orc_dense_index_load": (vp, [cp]),
+            "orc_sparse_index_load": (vp, [cp]),
             "orc_index_from_cf": (vp, [cp, i32, i32, u64, u64]),
             "orc_index_from_packed": (vp, [i32, vp, u64, vp, u64, i32, i32, u64, u64]),
             "orc_index_from_seqs": (vp, [cp, vp, u64, i32, i32, i32, u64, u64]),
@@ -129,6 +130,10 @@ class OracleIndex:
     @classmethod
     def dense_from_pf1(cls, d):
         return cls(lib().orc_dense_index_load(d.encode()))
+
+    @classmethod
+    def sparse_from_pf1(cls, d):
+        return cls(lib().orc_sparse_index_load(d.encode()))
 
     @classmethod
     def from_cf(cls, prefix, kind, w=0, skew=USIZE_MAX, seed=0):

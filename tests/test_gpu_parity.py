@@ -664,3 +664,32 @@ def test_concurrent_queries_on_one_handle(yeast_sshash, yeast_queries):
     [t.join() for t in ths]
     for t in range(len(inputs)):
         assert_hits_equal(got[t], want[t], "thread %d" % t)
+
+
+# --------------------------------------------------------------------------------------------
+# SampledPFHash -- the pufferfish sparse index (src/pf1/sparse_index.rs:145-192)
+# --------------------------------------------------------------------------------------------
+SMALL_TXOME_SPARSE = os.path.join(PF1, "small_txome_index_sparse")
+
+
+def test_sparse_index_validate_and_parity():
+    g = mz.SparseIndex.deserialize_from_cpp(SMALL_TXOME_SPARSE)
+    o = OracleIndex.sparse_from_pf1(SMALL_TXOME_SPARSE)
+    assert g.info(mz.INFO_SAMPLE_SIZE) == 9 and g.info(mz.INFO_EXTENSION_SIZE) == 4
+    assert g.info(mz.INFO_K2U_KIND) == mz.K2U_SAMPLED_PFHASH
+    c = g.k2u_validate_self()
+    assert c == o.k2u_validate_self() and c[0] == 2 * 18902 and c[4] == 0
+    v = g.validate_self()
+    assert v == o.validate_self() and v[0] == 28112 and v[4] == 0
+    # k-mers: every unitig k-mer both strands, boundary-straddling windows, random negatives
+    codes = _gen.unpack_2bit(o.useq_words(), o.total_len)
+    rng = np.random.default_rng(4)
+    q = np.concatenate([_gen.kmer_words_from_codes(codes, o.k), rng.integers(0, 1 << 62, size=20000, dtype=np.uint64)])
+    assert_hits_equal(g.k2u_batch(q), o.k2u_batch(q), "SampledPFHash k2u")
+    ref_codes = _gen.unpack_2bit(o.refseq_words(), int(o.ref_prefix()[-1]))
+    bases, offs = _gen.sample_reads(ref_codes, 3000, 200, seed=6, frac_ref=0.7, sub_rate=0.01, n_rate=0.002, ragged=True)
+    for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+        _check_reads(g, o, bases, offs, mode)
+    # sshash_drop_in (sparse_index.rs:176-191)
+    ss = g.rebuild_k2u(mz.K2U_SSHASH, w=2, skew_param=NOSKEW)
+    assert ss.validate_self()[4] == 0

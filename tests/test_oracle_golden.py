@@ -397,3 +397,24 @@ def test_pufferfish_dense_from_cf_validate_yeast():
     c = idx.validate_fasta(YEAST_CF + ".fa")
     assert c[0] == 1090910 and c[4] == 0
     assert idx.validate_fasta(YEAST_CF + ".fa", streaming=True) == c
+
+
+# ---- pf1/sparse_index.rs:145-192 (SampledPFHash, pufferfish sparse index) ------------------------
+SMALL_TXOME_SPARSE = os.path.join(PF1, "small_txome_index_sparse")
+
+
+def test_sparse_index_params_and_validate():
+    idx = OracleIndex.sparse_from_pf1(SMALL_TXOME_SPARSE)
+    assert idx.info(12) == 9 and idx.info(13) == 4  # sample_size, extension_size
+    c = idx.k2u_validate_self()
+    assert c[0] == 2 * 18902 and c[4] == 0
+    v = idx.validate_self()
+    assert v[0] == 28112 and v[4] == 0
+    dense = OracleIndex.dense_from_pf1(SMALL_TXOME).validate_self()
+    assert (v[0], v[4]) == (dense[0], dense[4])  # same transcriptome through the dense index
+
+
+def test_sparse_index_sshash_drop_in():
+    idx = OracleIndex.sparse_from_pf1(SMALL_TXOME_SPARSE)
+    ss = idx.rebuild_k2u(1, w=2, skew=NOSKEW)
+    assert ss.validate_self()[4] == 0
