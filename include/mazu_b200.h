@@ -218,6 +218,13 @@ mazu_status_t mazu_b200_decode_occs(const mazu_index_t* idx, const uint32_t* uni
 mazu_status_t mazu_b200_project_hits(const mazu_index_t* idx, const mazu_hit_t* hits, uint64_t n, uint64_t* out_offsets,
                                      mazu_occ_t* out_mrps, uint64_t cap, uint64_t* out_total, int32_t mem, void* stream);
 
+/* ModIndex::iter_unitigs_on_ref / RefSeqContigIterator (src/index.rs:363-424): the unitig tiling of reference `ref_id`.
+ * Records are RefSeqUnitigOcc {unitig_id, unitig_len, pos (on the reference), fw} in a mazu_hit_t (match field = 1 forward,
+ * 0 backward).  Every reference position is looked up on the device in one pass; the unitig-jumping walk
+ * (pos += unitig_len - k + 1) then runs over those answers.  Host buffers.  A reference k-mer that is not in the index is
+ * MAZU_ERR_INVALID_DATA (the reference unwraps a None there).  *n_out receives the number of tiles even if cap is too small. */
+mazu_status_t mazu_b200_iter_unitigs_on_ref(const mazu_index_t* idx, uint64_t ref_id, mazu_hit_t* out, uint64_t cap, uint64_t* n_out);
+
 /* Validate::validate_self (src/index/validate.rs:24-52): every reference k-mer must map back to its own
  * (ref_id,pos).  counts = {n_queries, n_identity, n_twin, n_projected, n_fail}; the reference panics when n_fail != 0. */
 mazu_status_t mazu_b200_validate_self(const mazu_index_t* idx, uint64_t counts[5]);

@@ -26,6 +26,7 @@ LIB_PATH = os.path.join(_HERE, "libmazu_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mazu_b200.h")
 
 HIT_DTYPE = np.dtype([("unitig_id", "<u4"), ("unitig_len", "<u4"), ("pos", "<u4"), ("match", "<u4")])
+TILE_DTYPE = np.dtype([("unitig_id", "<u4"), ("unitig_len", "<u4"), ("pos", "<u4"), ("fw", "<u4")])
 HIT8_DTYPE = np.dtype([("unitig_id", "<u4"), ("pos_match", "<u4")])
 OCC_DTYPE = np.dtype([("ref_id", "<u4"), ("pos", "<u4"), ("fw", "<u4")])
 
@@ -99,6 +100,7 @@ def _signatures():
         "mazu_b200_encode_reads": (i32, [vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp]),
         "mazu_b200_decode_occs": (i32, [vp, vp, u64, vp, vp, u64, vp, i32, vp]),
         "mazu_b200_project_hits": (i32, [vp, vp, u64, vp, vp, u64, vp, i32, vp]),
+        "mazu_b200_iter_unitigs_on_ref": (i32, [vp, u64, vp, u64, vp]),
         "mazu_b200_validate_self": (i32, [vp, vp]),
         "mazu_b200_k2u_validate_self": (i32, [vp, vp]),
         "mazu_b200_measure_random_gather": (i32, [u64, u64, i32, i32, C.POINTER(C.c_double)]),
@@ -400,6 +402,15 @@ class ModIndex:
             return None
         _, mrps = self.project_hits(hit)
         return [(int(m["ref_id"]), int(m["pos"]), int(m["fw"])) for m in mrps]
+
+    def iter_unitigs_on_ref(self, ref_id):
+        """ModIndex::iter_unitigs_on_ref (src/index.rs:363-424): tiles as records {unitig_id, unitig_len, pos, fw}."""
+        n = C.c_uint64(0)
+        _check(lib().mazu_b200_iter_unitigs_on_ref(self._h, ref_id, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=TILE_DTYPE)
+        if n.value:
+            _check(lib().mazu_b200_iter_unitigs_on_ref(self._h, ref_id, _np_ptr(out), n.value, C.byref(n)))
+        return out
 
     def validate_self(self):
         c = np.zeros(5, dtype=np.uint64)

@@ -804,6 +804,36 @@ mazu_status_t mazu_b200_project_hits(const mazu_index_t* idx, const mazu_hit_t* 
   });
 }
 
+mazu_status_t mazu_b200_iter_unitigs_on_ref(const mazu_index_t* idx, uint64_t ref_id, mazu_hit_t* out, uint64_t cap, uint64_t* n_out) {
+  return guarded([&] {
+    if (!idx || !n_out) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    if (!idx->refs || !idx->refs->has_seq) throw Error(MAZU_ERR_NO_REFSEQ, "Refseq is None");
+    if (ref_id >= idx->refs->n_refs()) throw Error(MAZU_ERR_INVALID_ARG, "reference id out of range");
+    const u64 k = idx->unitigs->k;
+    const u64 begin = idx->refs->prefix[ref_id], len = idx->refs->prefix[ref_id + 1] - begin;
+    *n_out = 0;
+    if (len < k) return;
+    const u64 n_pos = len - k + 1;  // index.rs:368
+    DeviceGuard g(idx->device);
+    DevBuf d(n_pos * 16, idx->device);
+    int grid = (int)std::max<u64>(1, std::min<u64>((n_pos + 255) / 256, (u64)idx->sm_count * 8));
+    ref_hits_kernel<<<grid, 256>>>(idx->view, begin, n_pos, (Hit*)d.p);
+    MZ_CUDA(cudaGetLastError());
+    std::vector<Hit> hits(n_pos);
+    MZ_CUDA(cudaMemcpy(hits.data(), d.p, n_pos * 16, cudaMemcpyDeviceToHost));
+    u64 n = 0;
+    for (u64 pos = 0; pos < n_pos;) {
+      const Hit& h = hits[pos];
+      if (h.match == NO_MATCH) throw Error(MAZU_ERR_INVALID_DATA, "iter_unitigs_on_ref: reference k-mer at position " + std::to_string(pos) + " is not in the index");
+      if (out && n < cap) out[n] = mazu_hit_t{h.unitig_id, h.unitig_len, (uint32_t)pos, h.match == IDENTITY_MATCH ? 1u : 0u};
+      ++n;
+      pos += (u64)h.unitig_len - k + 1;
+    }
+    *n_out = n;
+    if (out && n > cap) throw Error(MAZU_ERR_INVALID_ARG, "output capacity too small: need " + std::to_string(n) + " records");
+  });
+}
+
 static void run_validate(const mazu_index_t* idx, bool k2u_only, uint64_t counts[5]) {
   if (!idx || !counts) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
   DeviceGuard g(idx->device);

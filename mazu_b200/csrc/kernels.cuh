@@ -884,6 +884,17 @@ __global__ void __launch_bounds__(256) validate_self_kernel(const __grid_constan
   }
   block_accumulate(counts, v);
 }
+// K2U::k2u for every k-mer start of one reference (input of the iter_unitigs_on_ref walk, src/index.rs:396-423)
+__global__ void __launch_bounds__(256) ref_hits_kernel(const __grid_constant__ IndexView ix, u64 ref_begin, u64 n_pos, Hit* __restrict__ out) {
+  const u32 k = ix.unitigs.k;
+  for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < n_pos; p += (u64)gridDim.x * blockDim.x) {
+    u64 fw = packed2_window(ix.refseq, ref_begin + p, k), rc = revcomp(fw, k);
+    Hit h;
+    if (!k2u_any(ix, fw, rc, h)) h = hit_none(NO_MATCH);
+    store_hit(out + p, h);
+  }
+}
+
 // K2U::validate_self (src/kphf/mod.rs:69-103): thread per useq position, fw then swapped
 __global__ void __launch_bounds__(256) k2u_validate_self_kernel(const __grid_constant__ IndexView ix, unsigned long long* counts) {
   const u32 k = ix.unitigs.k;

@@ -472,6 +472,19 @@ int orc_validate_fasta(void* hp, const char* path, int streaming, u64* counts) {
     counts[0] = tot.n_queries; counts[1] = tot.n_identity; counts[2] = tot.n_twin; counts[3] = tot.n_projected; counts[4] = tot.n_fail;
   });
 }
+// ModIndex::iter_unitigs_on_ref (index.rs:363-424): out = 4 x u32 per tile {unitig_id, unitig_len, ref pos, fw}; returns #tiles or -1
+long long orc_iter_unitigs_on_ref(void* hp, u64 ref_id, u32* out, u64 cap) {
+  long long n = -1;
+  guard([&] {
+    auto v = iter_unitigs_on_ref(*((Handle*)hp)->idx, ref_id);
+    for (u64 i = 0; i < v.size() && i < cap; ++i) {
+      out[4 * i] = (u32)v[i].unitig_id; out[4 * i + 1] = (u32)v[i].unitig_len; out[4 * i + 2] = (u32)v[i].pos; out[4 * i + 3] = v[i].fw;
+    }
+    n = (long long)v.size();
+  });
+  return n;
+}
+
 // single eager query on a k-mer string (index.rs:139-142); returns #MappedRefPos or -1 (None) or -2 (error/panic)
 int orc_get_ref_pos_eager_str(void* hp, const char* kmer, void* out_mrps, int cap, void* out_hit) {
   int n = -2;

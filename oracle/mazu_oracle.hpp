@@ -1175,6 +1175,28 @@ struct ModIndex {
   }
 };
 
+// index.rs:363-424 iter_unitigs_on_ref / RefSeqContigIterator: the unitig tiling of one reference
+struct RefSeqUnitigOcc {
+  u64 unitig_id, unitig_len, pos;
+  u32 fw;
+};
+inline std::vector<RefSeqUnitigOcc> iter_unitigs_on_ref(const ModIndex& idx, u64 ref_id) {
+  if (!idx.refs || !idx.refs->has_seq) throw OracleError("Refseq is None");
+  std::vector<RefSeqUnitigOcc> out;
+  int k = idx.k();
+  u64 s = idx.refs->prefix[ref_id], len = idx.refs->ref_len(ref_id);
+  u64 end_pos = len + 1 - (u64)k;  // index.rs:368
+  u64 pos = 0;
+  while (pos < end_pos) {
+    CanonicalKmer km = CanonicalKmer::from_u64(idx.refs->seq.get_kmer_u64(s + pos, k), k);
+    K2UPos hit;
+    if (!idx.k2u->k2u(km, hit)) throw OracleError("called `Option::unwrap()` on a `None` value");  // index.rs:403
+    out.push_back(RefSeqUnitigOcc{hit.unitig_id, hit.unitig_len, pos, hit.o == IdentityMatch ? 1u : 0u});
+    pos += hit.unitig_len - (u64)k + 1;
+  }
+  return out;
+}
+
 // kphf/mod.rs:69-103 K2U::validate_self (counts instead of panics)
 inline ValidateCounts k2u_validate_self(const K2U& h) {
   ValidateCounts c;

@@ -14,6 +14,7 @@ LIB = os.path.join(ORACLE_DIR, "liboracle.so")
 
 HIT = np.dtype([("unitig_id", "<u4"), ("unitig_len", "<u4"), ("pos", "<u4"), ("match", "<u4")])
 OCC = np.dtype([("ref_id", "<u4"), ("pos", "<u4"), ("fw", "<u4")])
+TILE = np.dtype([("unitig_id", "<u4"), ("unitig_len", "<u4"), ("pos", "<u4"), ("fw", "<u4")])
 MISS = 0xFFFFFFFF
 MATCH_NONE, MATCH_IDENTITY, MATCH_TWIN, MATCH_SKIPPED = 0, 1, 2, 3
 USIZE_MAX = 0xFFFFFFFFFFFFFFFF
@@ -80,6 +81,7 @@ def lib():
             "orc_validate_self": (i32, [vp, vp]),
             "orc_k2u_validate_self": (i32, [vp, vp]),
             "orc_validate_fasta": (i32, [vp, cp, i32, vp]),
+            "orc_iter_unitigs_on_ref": (C.c_longlong, [vp, u64, vp, u64]),
             "orc_get_ref_pos_eager_str": (i32, [vp, cp, vp, i32, vp]),
         }
         for name, (res, args) in sig.items():
@@ -268,6 +270,14 @@ class OracleIndex:
         c = np.zeros(5, dtype=np.uint64)
         _check(lib().orc_validate_fasta(self.h, path.encode(), int(streaming), _ptr(c)))
         return [int(x) for x in c]
+
+    def iter_unitigs_on_ref(self, ref_id):
+        cap = self.ref_len(ref_id) + 1
+        out = np.zeros((cap, 4), dtype=np.uint32)
+        n = lib().orc_iter_unitigs_on_ref(self.h, ref_id, _ptr(out), cap)
+        if n < 0:
+            raise OracleError(lib().orc_last_error().decode())
+        return out[:n].copy().view(TILE).reshape(-1)
 
     def get_ref_pos_eager(self, kmer):
         """Returns None (miss) or (hit_record, [(ref_id,pos,fw),...]); raises on contract panic."""

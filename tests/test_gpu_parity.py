@@ -693,3 +693,26 @@ def test_sparse_index_validate_and_parity():
     # sshash_drop_in (sparse_index.rs:176-191)
     ss = g.rebuild_k2u(mz.K2U_SSHASH, w=2, skew_param=NOSKEW)
     assert ss.validate_self()[4] == 0
+
+
+# --------------------------------------------------------------------------------------------
+# ModIndex::iter_unitigs_on_ref (src/index.rs:363-424; golden: src/refseq.rs:280-309)
+# --------------------------------------------------------------------------------------------
+def test_iter_unitigs_on_ref():
+    g = mz.DenseIndex.deserialize_from_cpp(TINY_REFS_INDEX)
+    t0, t1 = g.iter_unitigs_on_ref(0), g.iter_unitigs_on_ref(1)
+    assert list(t0["unitig_len"]) == [5, 8, 9, 8, 5] and list(t0["unitig_id"]) == [0, 1, 2, 3, 4]
+    assert list(t1["unitig_len"]) == [5, 9, 9, 9, 5] and list(t1["unitig_id"]) == [0, 5, 2, 6, 4]
+    for d, loader, oloader in [(YEAST_CHR01, mz.DenseIndex.deserialize_from_cpp, OracleIndex.dense_from_pf1),
+                               (SMALL_TXOME, mz.DenseIndex.deserialize_from_cpp, OracleIndex.dense_from_pf1),
+                               (SMALL_TXOME_SPARSE, mz.SparseIndex.deserialize_from_cpp, OracleIndex.sparse_from_pf1)]:
+        gi, oi = loader(d), oloader(d)
+        for r in range(oi.n_refs):
+            a, b = gi.iter_unitigs_on_ref(r), oi.iter_unitigs_on_ref(r)
+            assert np.array_equal(a, b), (d, r)
+            # the tiles rebuild the reference length: sum(len - k + 1) + k - 1
+            assert int((a["unitig_len"].astype(np.int64) - gi.k + 1).sum()) + gi.k - 1 == oi.ref_len(r)
+    ss = mz.DenseIndex.deserialize_from_cpp(YEAST_CHR01).rebuild_k2u(mz.K2U_SSHASH, w=15, skew_param=32)
+    assert np.array_equal(ss.iter_unitigs_on_ref(0), OracleIndex.dense_from_pf1(YEAST_CHR01).iter_unitigs_on_ref(0))
+    with pytest.raises(mz.MazuError):
+        mz.PiscemIndex.from_cf_prefix(TINY_CF, 3, NOSKEW).iter_unitigs_on_ref(0)  # no reference sequence

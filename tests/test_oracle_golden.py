@@ -418,3 +418,12 @@ def test_sparse_index_sshash_drop_in():
     idx = OracleIndex.sparse_from_pf1(SMALL_TXOME_SPARSE)
     ss = idx.rebuild_k2u(1, w=2, skew=NOSKEW)
     assert ss.validate_self()[4] == 0
+
+
+# ---- refseq.rs:280-309 test_contig_iter (ModIndex::iter_unitigs_on_ref, index.rs:363-424) ----------
+def test_contig_iter_tiny_multi_refs():
+    idx = OracleIndex.dense_from_pf1(TINY_REFS_INDEX)
+    t0, t1 = idx.iter_unitigs_on_ref(0), idx.iter_unitigs_on_ref(1)
+    assert list(t0["unitig_len"]) == [5, 8, 9, 8, 5] and list(t0["unitig_id"]) == [0, 1, 2, 3, 4]
+    assert list(t1["unitig_len"]) == [5, 9, 9, 9, 5] and list(t1["unitig_id"]) == [0, 5, 2, 6, 4]
+    assert idx.ref_len(1) == 21 and idx.k == 5
