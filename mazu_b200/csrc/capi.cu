@@ -182,11 +182,11 @@ void upload_k2u(mazu_index& ix) {
   v.skew_param = h.skew_param;
   v.has_skew = h.has_skew ? 1u : 0u;
   if (h.kind == MAZU_K2U_SSHASH) {
-    auto bb = upload(h.sizes.blocks, ix.device, 4);
+    auto bb = upload(h.sizes.blocks, ix.device, 8);
     auto be = upload(h.sizes.exceptions, ix.device);
     d->bufs.insert(d->bufs.end(), {bb, be});
     d->bytes += bb->bytes + be->bytes;
-    v.sizes = BlockedEFView{(const u64*)bb->p, (const u64*)be->p, h.sizes.n, h.sizes.l, h.sizes.log_s};
+    v.sizes = BlockedEFView{(const u64*)bb->p, (const u64*)be->p, h.sizes.n, h.sizes.l, h.sizes.log_s, h.sizes.wpb, 0};
     if (h.has_skew) {
       v.skew_mphf = upload_mphf(h.skew_mphf, ix.device, *d);
       v.skew_pos = upload_packed(h.skew_pos, ix.device, d->bufs, d->bytes);

@@ -155,7 +155,9 @@ struct BlockedEF {
   u64 n = 0;
   std::vector<u64> blocks, exceptions;
   u64 n_exception_blocks = 0;
-  static BlockedEF build(const std::vector<u64>& xs) {
+  u32 wpb = 4;  // words per block: 4, or 8 when fingerprints ride along (element i's byte at word 4 + j/8 of its block)
+  // fps: optional, one byte per element i in [0, n-1) (the fingerprint of the key whose MPHF value is i)
+  static BlockedEF build(const std::vector<u64>& xs, const std::vector<u8>* fps = nullptr) {
     if (xs.empty()) throw Error(MAZU_ERR_EF_EMPTY, "EFVector: empty input");  // elias_fano.rs:124-140
     for (size_t i = 1; i < xs.size(); ++i)
       if (xs[i] < xs[i - 1]) throw Error(MAZU_ERR_EF_NOT_MONOTONE, "EFVector: sequence is not monotone");  // :89-91
@@ -171,12 +173,16 @@ struct BlockedEF {
     ef.log_s = log_s;
     u64 S = 1ULL << log_s;
     u64 nb = (n + S - 1) / S;  // block b covers [b*S, b*S+S]
-    ef.blocks.assign(nb * 4, 0);
+    ef.wpb = fps ? 8 : 4;
+    const u64 wpb = ef.wpb;
+    ef.blocks.assign(nb * wpb, 0);
     for (u64 b = 0; b < nb; ++b) {
       u64 i0 = b * S, cnt = std::min<u64>(S + 1, n - i0);
       u64 hb = xs[i0] >> l;
       bool exc = all_exc || ((xs[i0 + cnt - 1] >> l) - hb) + (cnt - 1) >= 128;
-      u64* w = &ef.blocks[b * 4];
+      u64* w = &ef.blocks[b * wpb];
+      if (fps)
+        for (u64 j = 0; j < S && i0 + j < fps->size(); ++j) w[4 + (j >> 3)] |= (u64)(*fps)[i0 + j] << (8 * (j & 7));
       if (exc) {
         w[0] = (1ULL << 63) | ef.n_exception_blocks++;
         for (u64 j = 0; j <= S; ++j) ef.exceptions.push_back(j < cnt ? xs[i0 + j] : xs[i0 + cnt - 1]);
@@ -194,7 +200,7 @@ struct BlockedEF {
     if (ef.exceptions.empty()) ef.exceptions.push_back(0);
     return ef;
   }
-  BlockedEFView view() const { return BlockedEFView{blocks.data(), exceptions.data(), n, l, log_s}; }
+  BlockedEFView view() const { return BlockedEFView{blocks.data(), exceptions.data(), n, l, log_s, wpb, 0}; }
   u64 get(u64 i) const {  // EFVector::get, elias_fano.rs:116-122
     u64 a, b;
     BlockedEFView v = view();
@@ -593,7 +599,11 @@ inline std::shared_ptr<K2UHost> build_sshash(std::shared_ptr<const UnitigSetHost
     H->skew_pos = PackedVec::packed(sp);
   }
   // finish (sshash.rs:310-329): Elias-Fano encode the prefix sums, bit-pack the positions
-  H->sizes = BlockedEF::build(prefix);
+  std::vector<u8> fps(M, 0);
+  parallel_ranges(M, T, [&](unsigned, u64 lo, u64 hi) {
+    for (u64 i = lo; i < hi; ++i) fps[hashes[i]] = (u8)mphf_fingerprint(mm_set[i]);
+  });
+  H->sizes = BlockedEF::build(prefix, &fps);
   H->pos = PackedVec::packed(pos);
   return H;
 }

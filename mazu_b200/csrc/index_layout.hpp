@@ -201,12 +201,26 @@ MZ_HD u64 packed_get(const PackedVecView& v, u64 i) {
 //   l follows the reference rule l = max(1, msb(u / n)) (elias_fano.rs:63-75).
 // ---------------------------------------------------------------------------------------------
 struct BlockedEFView {
-  const u64* blocks;      // 4 words per block
+  const u64* blocks;      // wpb words per block: 4 (Elias-Fano only) or 8 (+ one fingerprint byte per element, words 4..7)
   const u64* exceptions;  // (S+1) words per exception block
   u64 n;                  // number of elements
   u32 l;
   u32 log_s;
+  u32 wpb;
+  u32 _pad;
 };
+
+// Fingerprint of an MPHF key, stored next to the bucket bounds of slot h (same 64-byte block, same 128-byte
+// DRAM line).  An MPHF maps most NON-member keys to some slot (boomphf's try_hash does the same,
+// src/kphf/sshash.rs:478); the reference then pays bucket bounds + positions + window compare to find out.
+// A fingerprint mismatch proves "not a member" after one load; a match (1/256 of non-members) proceeds as the
+// reference does, so answers are unchanged.
+MZ_HD u32 mphf_fingerprint(u64 key) { return (u32)(fmix64(key ^ 0xD6E8FEB86659FD93ULL) >> 56); }
+MZ_HD u32 blocked_ef_fp(const BlockedEFView& ef, u64 i) {
+  u64 blk = i >> ef.log_s;
+  u32 j = (u32)(i & ((1ULL << ef.log_s) - 1ULL));
+  return (u32)((MZ_LDG(ef.blocks + blk * ef.wpb + 4 + (j >> 3)) >> (8 * (j & 7))) & 0xFFULL);
+}
 
 // position of the j-th (0-based) set bit of the 128-bit value hi:lo; caller guarantees it exists
 MZ_HD u32 select128(u64 lo, u64 hi, u32 j) {
@@ -243,7 +257,7 @@ MZ_HD u32 select128(u64 lo, u64 hi, u32 j) {
 MZ_HD void blocked_ef_get2(const BlockedEFView& ef, u64 i, u64& a, u64& b) {
   u64 blk = i >> ef.log_s;
   u32 j = (u32)(i & ((1ULL << ef.log_s) - 1ULL));
-  const u64* p = ef.blocks + blk * 4;
+  const u64* p = ef.blocks + blk * ef.wpb;
 #if defined(__CUDA_ARCH__)
   const ulonglong2 q0 = __ldg(reinterpret_cast<const ulonglong2*>(p));
   const ulonglong2 q1 = __ldg(reinterpret_cast<const ulonglong2*>(p) + 1);

@@ -71,6 +71,7 @@ __device__ __forceinline__ bool sshash_k2u(const IndexView& ix, u64 fw, u64 rc, 
   u64 h;
   if (!mphf_lookup(ix.mphf, mm_word, h)) return false;
   if (h + 1 >= ix.sizes.n) return false;
+  if (blocked_ef_fp(ix.sizes, h) != mphf_fingerprint(mm_word)) return false;  // provably not a member (index_layout.hpp)
   u64 pos_start, pos_end;
   blocked_ef_get2(ix.sizes, h, pos_start, pos_end);  // occs_prefix_sum.get(h), get(h+1)
   if (pos_end - pos_start > ix.skew_param) {         // k2u_skew_index (sshash.rs:415-433)
@@ -302,7 +303,7 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
       u64 mmw = mm_word_of(fw, rc, S.off[p], k, w);
       u64 h, a = 0, b = 0;
       u32 n = 0;
-      if (mphf_lookup_t<FAMILY>(ix.mphf, mmw, h) && h + 1 < ix.sizes.n) {
+      if (mphf_lookup_t<FAMILY>(ix.mphf, mmw, h) && h + 1 < ix.sizes.n && blocked_ef_fp(ix.sizes, h) == mphf_fingerprint(mmw)) {
         blocked_ef_get2(ix.sizes, h, a, b);
         u64 cnt = b - a;
         n = cnt > ix.skew_param ? BN_SKEW : (u32)cnt;

@@ -122,6 +122,7 @@ static void check_sshash_tables(const K2UHost& h) {
         bool ok = mphf_lookup(mv, mm.word, hh);
         CHECK(ok && hh + 1 < ev.n, "minimizer not in mphf");
         if (!ok) continue;
+        CHECK(ev.wpb == 8 && blocked_ef_fp(ev, hh) == mphf_fingerprint(mm.word), "fingerprint of a member minimizer");
         u64 a, b;
         blocked_ef_get2(ev, hh, a, b);
         CHECK(b > a, "empty bucket");
