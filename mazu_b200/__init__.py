@@ -84,6 +84,8 @@ def _signatures():
         "mazu_b200_sparse_index_deserialize_from_cpp": (i32, [cp, i32, pp]),
         "mazu_b200_index_from_cf_prefix": (i32, [cp, i32, u32, u64, u64, i32, pp]),
         "mazu_b200_index_create_sshash": (i32, [C.POINTER(UnitigSetDesc), u32, u64, u64, i32, pp]),
+        "mazu_b200_index_create_sshash_gpu": (i32, [C.POINTER(UnitigSetDesc), u32, u64, u64, i32, pp]),
+        "mazu_b200_debug_table_digest": (i32, [vp, i32, vp, vp]),
         "mazu_b200_index_create_pfhash": (i32, [C.POINTER(UnitigSetDesc), i32, pp]),
         "mazu_b200_index_create_pfhash_from_parts": (i32, [C.POINTER(UnitigSetDesc), C.POINTER(BooPHFDesc), C.POINTER(PackedVecDesc), i32, pp]),
         "mazu_b200_index_rebuild_k2u": (i32, [vp, i32, u32, u64, u64, pp]),
@@ -269,6 +271,19 @@ class ModIndex:
         d = unitigs.desc()
         _check(lib().mazu_b200_index_create_sshash(C.byref(d), w, skew_param, seed, device, C.byref(out)))
         return cls(out.value)
+
+    @classmethod
+    def sshash_from_unitig_set_gpu(cls, unitigs, w, skew_param=SKEW_NONE, seed=0, device=0):
+        """SSHash::from_unitig_set with every build stage on the device (tables bit-identical to the host builder)."""
+        out = cls._out()
+        d = unitigs.desc()
+        _check(lib().mazu_b200_index_create_sshash_gpu(C.byref(d), w, skew_param, seed, device, C.byref(out)))
+        return cls(out.value)
+
+    def table_digest(self, which):
+        dg, nb = C.c_uint64(0), C.c_uint64(0)
+        _check(lib().mazu_b200_debug_table_digest(self._h, which, C.byref(dg), C.byref(nb)))
+        return dg.value, nb.value
 
     @classmethod
     def pfhash_from_unitig_set(cls, unitigs, device=0):
@@ -468,7 +483,9 @@ class PufferfishDenseIndex:
 
 class SSHash:
     @staticmethod
-    def from_unitig_set(unitigs, w, skew_param, seed=0, device=0):
+    def from_unitig_set(unitigs, w, skew_param, seed=0, device=0, builder="host"):
+        if builder == "gpu":
+            return ModIndex.sshash_from_unitig_set_gpu(unitigs, w, skew_param, seed, device)
         return ModIndex.sshash_from_unitig_set(unitigs, w, skew_param, seed, device)
 
     @staticmethod

@@ -716,3 +716,57 @@ def test_iter_unitigs_on_ref():
     assert np.array_equal(ss.iter_unitigs_on_ref(0), OracleIndex.dense_from_pf1(YEAST_CHR01).iter_unitigs_on_ref(0))
     with pytest.raises(mz.MazuError):
         mz.PiscemIndex.from_cf_prefix(TINY_CF, 3, NOSKEW).iter_unitigs_on_ref(0)  # no reference sequence
+
+
+# --------------------------------------------------------------------------------------------
+# index construction on the device (SSHashBuilder::from_unitig_set, src/kphf/sshash.rs:86-329)
+# --------------------------------------------------------------------------------------------
+TABLES = ["mphf blocks", "bucket-bound blocks", "bucket-bound exceptions", "packed positions", "skew mphf blocks", "skew positions", "mphf fallback keys"]
+
+
+def _assert_same_tables(a, b, what):
+    for i, name in enumerate(TABLES):
+        assert a.table_digest(i) == b.table_digest(i), "%s: table '%s' differs between the host and the GPU builder" % (what, name)
+
+
+@pytest.mark.parametrize("w,skew", [(15, 32), (15, NOSKEW), (19, 4), (9, 2), (31, 0), (3, 8)])
+def test_gpu_builder_bit_identical_yeast(yeast_dense, yeast_queries, w, skew):
+    _, o = yeast_dense
+    q, ref_codes = yeast_queries
+    us = mz.UnitigSet(o.k, o.useq_words(), o.total_len, o.unitig_starts())
+    host = mz.SSHash.from_unitig_set(us, w, skew, seed=5)
+    gpu = mz.SSHash.from_unitig_set(us, w, skew, seed=5, builder="gpu")
+    for what in (mz.INFO_N_MINIMIZERS, mz.INFO_N_MINIMIZER_OCCS, mz.INFO_N_KMERS_IN_SKEW_INDEX, mz.INFO_MPHF_LEVELS):
+        assert host.info(what) == gpu.info(what), what
+    _assert_same_tables(host, gpu, "yeast w=%d skew=%s" % (w, skew))
+    c = gpu.k2u_validate_self()
+    assert c[0] == 443836 and c[4] == 0
+    os_ = o.rebuild_k2u(1, w=w, skew=skew, seed=5)
+    assert_hits_equal(gpu.k2u_batch(q[:100000]), os_.k2u_batch(q[:100000]), "GPU-built index vs oracle")
+    bases, offs = _gen.sample_reads(ref_codes, 1500, 200, seed=77, frac_ref=0.7, sub_rate=0.01, n_rate=0.002, ragged=True)
+    for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+        _check_reads(gpu, os_, bases, offs, mode)
+
+
+def test_gpu_builder_small_and_odd_sets():
+    # tiny cuttlefish unitigs, every w; duplicated k-mers; k = 32; unitigs of length exactly k
+    tiny = mz.UnitigSet.from_seqs(["CACACACCAC", "CCTCAATACG"], 7)
+    for w in range(1, 8):
+        for skew in (NOSKEW, 0, 1):
+            _assert_same_tables(mz.SSHash.from_unitig_set(tiny, w, skew), mz.SSHash.from_unitig_set(tiny, w, skew, builder="gpu"), "tiny w=%d" % w)
+    for k, w, skew, n_u, extra, seed in [(32, 20, 8, 300, 50, 1), (21, 11, 4, 500, 30, 2), (15, 7, 3, 200, 40, 3), (31, 19, 64, 2000, 1, 4), (5, 3, 2, 10, 6, 5)]:
+        codes, accum = _gen.synthetic_unitigs(n_u, extra, k, seed=seed)
+        us = mz.UnitigSet(k, mz.pack_2bit(codes), len(codes), accum)
+        host, gpu = mz.SSHash.from_unitig_set(us, w, skew), mz.SSHash.from_unitig_set(us, w, skew, builder="gpu")
+        _assert_same_tables(host, gpu, "synthetic k=%d w=%d" % (k, w))
+        assert gpu.k2u_validate_self() == host.k2u_validate_self()
+
+
+def test_gpu_builder_larger_synthetic():
+    k = 31
+    codes, accum = _gen.synthetic_unitigs(200000, 68, k, seed=45)  # ~2e7 bases
+    us = mz.UnitigSet(k, mz.pack_2bit(codes), len(codes), accum)
+    host, gpu = mz.SSHash.from_unitig_set(us, 19, 64), mz.SSHash.from_unitig_set(us, 19, 64, builder="gpu")
+    _assert_same_tables(host, gpu, "2e7-base synthetic set")
+    c = gpu.k2u_validate_self()
+    assert c[0] == 2 * gpu.n_kmers and c[4] == 0
