@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU seconds for the cpu_baseline sample")
+    ap.add_argument("--builder", default="gpu", choices=["host", "gpu"], help="config5: where SSHash::from_unitig_set runs")
     ap.add_argument("--validate", action="store_true", help="config5: also run k2u_validate_self on the device (every unitig k-mer)")
     a = ap.parse_args()
     if a.mode is None:
@@ -262,7 +263,9 @@ def main():
         n_unitigs = max(1000, int(HUMAN_UNITIGS * args.scale))
         words, n_bases, accum = _gen.synthetic_unitigs_packed(n_unitigs, 68, 31, seed=45)
         us = mz.UnitigSet(31, words, n_bases, accum)
-        index = mz.SSHash.from_unitig_set(us, 19, 64, seed=0, device=local_rank)
+        t_b = time.time()
+        index = mz.SSHash.from_unitig_set(us, 19, 64, seed=0, device=local_rank, builder=args.builder)
+        info["index_builder"] = {"where": args.builder, "seconds": round(time.time() - t_b, 2)}
         info["index"] = {"n_unitigs": index.n_unitigs, "n_kmers": index.n_kmers, "sum_unitigs_len": index.sum_unitigs_len,
                          "n_minimizers": index.n_minimizers, "n_kmers_in_skew_index": index.n_kmers_in_skew_index,
                          "mphf_levels": index.info(mz.INFO_MPHF_LEVELS)}
