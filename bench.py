@@ -597,7 +597,10 @@ def main():
         "gpu_launches": args.steps * launches_per_step,
         "kernel": kernel_name,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_source, "algorithmic_bytes_per_unit": alg, "units_per_launch": n_units, "kernel_ms": kernel_ms},
+                     "peak_source": peak_source, "algorithmic_bytes_per_unit": alg, "units_per_launch": n_units, "kernel_ms": kernel_ms,
+                     "note": "algorithmic bytes = SURVEY 8(d) ideal-layout figure with nothing cached or shared; consecutive k-mers of a read share "
+                             "minimizer, bucket and window sectors and small indexes are L2-resident, so `traffic` (measured DRAM bytes) is far below it "
+                             "and frac can exceed 1 -- see DESIGN.md 7b for the DRAM/issue figures from ncu"},
         "parity_spot_check": parity_ok,
     }
     line.update(info)
