@@ -137,6 +137,8 @@ mazu_status_t mazu_b200_index_create_sshash(const mazu_unitig_set_desc_t* unitig
  * Elias-Fano encoding, packing): produces tables bit-identical to mazu_b200_index_create_sshash    */
 mazu_status_t mazu_b200_index_create_sshash_gpu(const mazu_unitig_set_desc_t* unitigs, uint32_t w, uint64_t skew_param,
                                                 uint64_t hash_seed, int32_t device, mazu_index_t** out);
+/* PFHash::from_unitig_set on the device (tables bit-identical to mazu_b200_index_create_pfhash) */
+mazu_status_t mazu_b200_index_create_pfhash_gpu(const mazu_unitig_set_desc_t* unitigs, int32_t device, mazu_index_t** out);
 /* test hook: FNV-1a digest and logical size of one device table (0 MPHF blocks, 1 bucket-bound blocks, 2 their exceptions,
  * 3 packed positions, 4 skew MPHF blocks, 5 skew positions, 6 MPHF fallback keys) */
 mazu_status_t mazu_b200_debug_table_digest(const mazu_index_t* idx, int32_t which, uint64_t* digest, uint64_t* n_bytes);

@@ -85,6 +85,7 @@ def _signatures():
         "mazu_b200_index_from_cf_prefix": (i32, [cp, i32, u32, u64, u64, i32, pp]),
         "mazu_b200_index_create_sshash": (i32, [C.POINTER(UnitigSetDesc), u32, u64, u64, i32, pp]),
         "mazu_b200_index_create_sshash_gpu": (i32, [C.POINTER(UnitigSetDesc), u32, u64, u64, i32, pp]),
+        "mazu_b200_index_create_pfhash_gpu": (i32, [C.POINTER(UnitigSetDesc), i32, pp]),
         "mazu_b200_debug_table_digest": (i32, [vp, i32, vp, vp]),
         "mazu_b200_index_create_pfhash": (i32, [C.POINTER(UnitigSetDesc), i32, pp]),
         "mazu_b200_index_create_pfhash_from_parts": (i32, [C.POINTER(UnitigSetDesc), C.POINTER(BooPHFDesc), C.POINTER(PackedVecDesc), i32, pp]),
@@ -286,10 +287,11 @@ class ModIndex:
         return dg.value, nb.value
 
     @classmethod
-    def pfhash_from_unitig_set(cls, unitigs, device=0):
+    def pfhash_from_unitig_set(cls, unitigs, device=0, builder="host"):
         out = cls._out()
         d = unitigs.desc()
-        _check(lib().mazu_b200_index_create_pfhash(C.byref(d), device, C.byref(out)))
+        fn = lib().mazu_b200_index_create_pfhash_gpu if builder == "gpu" else lib().mazu_b200_index_create_pfhash
+        _check(fn(C.byref(d), device, C.byref(out)))
         return cls(out.value)
 
     def rebuild_k2u(self, k2u_kind, w=0, skew_param=SKEW_NONE, seed=0):
@@ -495,8 +497,8 @@ class SSHash:
 
 class PFHash:
     @staticmethod
-    def from_unitig_set(unitigs, device=0):
-        return ModIndex.pfhash_from_unitig_set(unitigs, device)
+    def from_unitig_set(unitigs, device=0, builder="host"):
+        return ModIndex.pfhash_from_unitig_set(unitigs, device, builder)
 
 
 def measure_random_gather(table_bytes, n_gathers, iters=3, device=0):

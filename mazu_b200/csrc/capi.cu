@@ -397,9 +397,12 @@ DevMphf build_mphf_gpu(CubTemp& tmp, const u64* d_keys, u64 n, double gamma, int
 }
 
 // bit-pack a device array of u64 values; returns the buffer and the width chosen like PackedVec::packed
-DevBufP pack_gpu(CubTemp& tmp, const u64* d_vals, u64 n, int dev, int sm, u32& width_out, u64& logical_bytes) {
-  u64 mx = reduce_max_u64(tmp, d_vals, n, dev);
-  u32 width = mx == 0 ? 1 : (u32)msb(mx) + 1;
+DevBufP pack_gpu(CubTemp& tmp, const u64* d_vals, u64 n, int dev, int sm, u32& width_out, u64& logical_bytes, u32 fixed_width = 0) {
+  u32 width = fixed_width;
+  if (!width) {
+    u64 mx = reduce_max_u64(tmp, d_vals, n, dev);
+    width = mx == 0 ? 1 : (u32)msb(mx) + 1;
+  }
   width_out = width;
   u64 nw = (n * width + 63) / 64;
   auto b = std::make_shared<DevBuf>((nw + 2) * 8, dev);
@@ -426,6 +429,56 @@ u64 group_sorted_gpu(CubTemp& tmp, const u64* d_keys, const u64* d_vals, u64 n, 
   MZ_CUDA(cudaGetLastError());
   MZ_CUDA(cudaMemcpy((u64*)ranges->p + M, &n, 8, cudaMemcpyHostToDevice));
   return M;
+}
+
+// PFHash::from_unitig_set on the device (twin of build_pfhash in host_build.hpp)
+void build_pfhash_gpu(mazu_index& ix, double gamma = 2.0) {
+  const UnitigSetHost& us = *ix.unitigs;
+  const u32 k = us.k;
+  const int dev = ix.device, sm = ix.sm_count;
+  const UnitigsView uv = ix.d_unitigs->view;
+  const u64 N = us.n_kmers();
+  for (u64 ui = 0; ui < us.n_unitigs(); ++ui)
+    if (us.unitig_len(ui) < k) throw Error(MAZU_ERR_INVALID_DATA, "a unitig is shorter than k");
+  CubTemp tmp;
+  auto d = std::make_shared<K2UDev>();
+  DevBuf keys(std::max<u64>(N, 1) * 8, dev), positions(std::max<u64>(N, 1) * 8, dev), bad(8, dev);
+  pfhash_keys_kernel<<<grid_1d(us.total_len(), sm), 256>>>(uv, (u64*)keys.p, (u64*)positions.p);
+  MZ_CUDA(cudaGetLastError());
+  DevMphf mphf = build_mphf_gpu(tmp, (const u64*)keys.p, N, gamma, dev, sm);
+  for (auto& b : mphf.bufs) {
+    d->bufs.push_back(b);
+    d->bytes += b->bytes;
+  }
+  const u64 n_slots = mphf.view.n_keys;
+  DevBuf vals(std::max<u64>(n_slots, 1) * 8, dev);
+  MZ_CUDA(cudaMemset(vals.p, 0, std::max<u64>(n_slots, 1) * 8));
+  MZ_CUDA(cudaMemset(bad.p, 0, 8));
+  pfhash_scatter_kernel<<<grid_1d(N, sm), 256>>>(mphf.view, (const u64*)keys.p, (const u64*)positions.p, N, n_slots, (u64*)vals.p,
+                                                 (unsigned long long*)bad.p);
+  MZ_CUDA(cudaGetLastError());
+  if (d2h_value((const u64*)bad.p) != 0) throw Error(MAZU_ERR_OTHER, "internal: GPU-built MPHF misses one of its keys");
+  u32 width = 1;
+  u64 bytes = 0;
+  DevBufP pos = pack_gpu(tmp, (const u64*)vals.p, n_slots, dev, sm, width, bytes, (u32)std::max<u64>(1, msb(std::max<u64>(us.total_len(), 1)) + 1));
+  d->bufs.push_back(pos);
+  d->bytes += pos->bytes;
+  auto H = std::make_shared<K2UHost>();
+  H->kind = MAZU_K2U_PFHASH;
+  H->unitigs = ix.unitigs;
+  IndexView& v = ix.view;
+  v.k2u_kind = MAZU_K2U_PFHASH;
+  v.mphf = mphf.view;
+  v.pos = PackedVecView{(const u64*)pos->p, n_slots, width, 0};
+  v.w = 0;
+  v.has_skew = 0;
+  v.skew_param = MAZU_SKEW_NONE;
+  ix.tables[0] = {v.mphf.blocks, mphf.block_bytes};
+  ix.tables[3] = {v.pos.words, bytes};
+  ix.tables[6] = {v.mphf.fb_keys, mphf.n_fb * 8};
+  MZ_CUDA(cudaDeviceSynchronize());
+  ix.k2u = H;
+  ix.d_k2u = d;
 }
 
 // SSHashBuilder::from_unitig_set + finish on the device; fills ix.view / ix.k2u metadata / ix.d_k2u
@@ -750,6 +803,17 @@ mazu_status_t mazu_b200_index_create_sshash_gpu(const mazu_unitig_set_desc_t* un
     ix->device = device;
     ix->unitigs = std::make_shared<UnitigSetHost>(UnitigSetHost::from_desc(*unitigs));
     ix->gpu_builder = [=](mazu_index& m) { build_sshash_gpu(m, w, skew_param, hash_seed); };
+    *out = finalize_index(std::move(ix));
+  });
+}
+
+mazu_status_t mazu_b200_index_create_pfhash_gpu(const mazu_unitig_set_desc_t* unitigs, int32_t device, mazu_index_t** out) {
+  return guarded([&] {
+    if (!unitigs || !out) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    auto ix = std::make_unique<mazu_index>();
+    ix->device = device;
+    ix->unitigs = std::make_shared<UnitigSetHost>(UnitigSetHost::from_desc(*unitigs));
+    ix->gpu_builder = [](mazu_index& m) { build_pfhash_gpu(m); };
     *out = finalize_index(std::move(ix));
   });
 }

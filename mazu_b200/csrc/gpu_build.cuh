@@ -252,6 +252,33 @@ __global__ void skew_tuples_kernel(const __grid_constant__ UnitigsView uv, u32 w
   }
 }
 
+// PFHash::from_unitig_set (src/kphf/pfhash.rs:40-73): canonical k-mer of every valid start position, in unitig order
+// (k-mer index of position p inside unitig ui = p - ui * (k - 1), every unitig being at least k long)
+__global__ void pfhash_keys_kernel(const __grid_constant__ UnitigsView uv, u64* __restrict__ keys, u64* __restrict__ positions) {
+  const u32 k = uv.k;
+  for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p + k <= uv.total_len; p += (u64)gridDim.x * blockDim.x) {
+    u64 id, s, e;
+    unitig_locate(uv, p, id, s, e);
+    if (p + k > e) continue;
+    u64 fw = useq_window(uv, p), rc = revcomp(fw, k);
+    u64 i = p - id * (u64)(k - 1);
+    keys[i] = fw <= rc ? fw : rc;
+    positions[i] = p;
+  }
+}
+// pos[h(kmer)] = position (pfhash.rs:60-68)
+__global__ void pfhash_scatter_kernel(const __grid_constant__ RankedLevels m, const u64* __restrict__ keys, const u64* __restrict__ positions, u64 n,
+                                      u64 n_slots, u64* __restrict__ out, unsigned long long* __restrict__ bad) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    u64 h;
+    if (!mphf_lookup_t<MPHF_FAMILY_NATIVE>(m, keys[i], h) || h >= n_slots) {
+      atomicAdd(bad, 1ULL);
+      continue;
+    }
+    out[h] = positions[i];
+  }
+}
+
 // stage 8: blocked Elias-Fano (host twin: BlockedEF::build)
 template <bool WRITE>
 __global__ void ef_blocks_kernel(const u64* __restrict__ xs, u64 n, u32 l, u32 log_s, u32 wpb, bool all_exc, const u8* __restrict__ fps, u64 n_fps,

@@ -770,3 +770,21 @@ def test_gpu_builder_larger_synthetic():
     _assert_same_tables(host, gpu, "2e7-base synthetic set")
     c = gpu.k2u_validate_self()
     assert c[0] == 2 * gpu.n_kmers and c[4] == 0
+
+
+def test_gpu_builder_pfhash_bit_identical(yeast_dense, yeast_queries):
+    _, o = yeast_dense
+    q, _ = yeast_queries
+    us = mz.UnitigSet(o.k, o.useq_words(), o.total_len, o.unitig_starts())
+    host, gpu = mz.PFHash.from_unitig_set(us), mz.PFHash.from_unitig_set(us, builder="gpu")
+    for i in (0, 3, 6):
+        assert host.table_digest(i) == gpu.table_digest(i), TABLES[i]
+    assert gpu.k2u_validate_self() == host.k2u_validate_self() == o.k2u_validate_self()
+    assert_hits_equal(gpu.k2u_batch(q[:100000]), o.k2u_batch(q[:100000]), "GPU-built PFHash vs oracle")
+    codes, accum = _gen.synthetic_unitigs(100000, 40, 31, seed=9)
+    us2 = mz.UnitigSet(31, mz.pack_2bit(codes), len(codes), accum)
+    a, b = mz.PFHash.from_unitig_set(us2), mz.PFHash.from_unitig_set(us2, builder="gpu")
+    for i in (0, 3, 6):
+        assert a.table_digest(i) == b.table_digest(i), TABLES[i]
+    c = b.k2u_validate_self()
+    assert c[0] == 2 * b.n_kmers and c[4] == 0
