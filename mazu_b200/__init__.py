@@ -22,7 +22,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmazu_b200.so")
+LIB_PATH = os.environ.get("MAZU_B200_LIB") or os.path.join(_HERE, "libmazu_b200.so")  # override: A/B of two builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mazu_b200.h")
 
 HIT_DTYPE = np.dtype([("unitig_id", "<u4"), ("unitig_len", "<u4"), ("pos", "<u4"), ("match", "<u4")])
