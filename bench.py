@@ -71,7 +71,9 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).
+    Read in-process through NVML: spawning nvidia-smi ten times a second visibly disturbed workloads whose
+    whole timed region is a few tens of milliseconds (config 4).  Falls back to nvidia-smi if pynvml is missing."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -80,21 +82,51 @@ class ClockSampler:
         self.stop = threading.Event()
         self.gpu = gpu_index
         self.th = threading.Thread(target=self.run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                ids = [x.strip() for x in vis.split(",") if x.strip()]
+                if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                    phys = int(ids[gpu_index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        act = lambda bit: "Active" if r & bit else "Not Active"
+        # NVML bit masks: SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+        return [str(sm), str(mx), "%.2f" % pw, act(0x8), act(0x40), act(0x20), act(0x4)]
 
     def run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self.sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.02 if self.nvml is not None else 0.1)
 
     def __enter__(self):
         self.th.start()
-        time.sleep(0.25)
+        time.sleep(0.05 if self.nvml is not None else 0.25)
         return self
 
     def __exit__(self, *a):
@@ -539,6 +571,13 @@ def main():
                "d2h_bytes_per_step": e2e_bytes[1] * world, "steps": args.steps,
                "api": "C ABI with MAZU_MEM_HOST: pinned host inputs in, every result record out",
                "matches_device_path": bool(torch.equal(h_hits[:1_000_000], hits[:1_000_000].cpu()))}
+        try:  # what bounds it: the box's pinned-copy bandwidth with both directions busy (profiles/pcie_probe.py)
+            pc = json.load(open(os.path.join(ROOT, "profiles", "r01_pcie.json")))
+            d2h_gbs = e2e_bytes[1] * args.steps / float(tt.item()) / 1e9
+            e2e["bound"] = {"kind": "pcie d2h (16 B per lookup out)", "achieved_d2h_gbs_per_gpu": d2h_gbs, "measured_duplex_peak_gbs": pc["duplex_each_gbs"],
+                            "measured_d2h_alone_gbs": pc["d2h_gbs"], "frac_of_duplex_peak": d2h_gbs / pc["duplex_each_gbs"]}
+        except Exception:
+            pass
         if e2e_compact_step is not None:
             e2e_compact_step()
             barrier()
@@ -571,6 +610,12 @@ def main():
     if os.path.exists(pk_path):
         peaks = json.load(open(pk_path))
     achieved = n_units * alg / (kernel_ms * 1e-3) / 1e9
+    if W == "config4":
+        note = "streaming decode: algorithmic bytes = 32 B (offset pair) per queried unitig + 6 B packed word in + 12 B record out per occurrence"
+    else:
+        note = ("algorithmic bytes = SURVEY 8(d) ideal-layout figure with nothing cached or shared; consecutive k-mers of a read share "
+                "minimizer, bucket and window sectors and small indexes are L2-resident, so `traffic` (measured DRAM bytes) is far below it "
+                "and frac can exceed 1 -- see DESIGN.md 7b for the DRAM/issue figures from ncu")
     if peak_kind == "hbm":
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_source = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
@@ -598,9 +643,7 @@ def main():
         "kernel": kernel_name,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_source, "algorithmic_bytes_per_unit": alg, "units_per_launch": n_units, "kernel_ms": kernel_ms,
-                     "note": "algorithmic bytes = SURVEY 8(d) ideal-layout figure with nothing cached or shared; consecutive k-mers of a read share "
-                             "minimizer, bucket and window sectors and small indexes are L2-resident, so `traffic` (measured DRAM bytes) is far below it "
-                             "and frac can exceed 1 -- see DESIGN.md 7b for the DRAM/issue figures from ncu"},
+                     "step_ms": [round(x, 3) for x in step_ms], "note": note},
         "parity_spot_check": parity_ok,
     }
     line.update(info)

@@ -116,6 +116,13 @@ struct mazu_index {
   // host-built and the GPU-built index table by table
   std::function<void(mazu_index&)> gpu_builder;  // set when the K2U tables are to be built on the device
   std::vector<std::pair<const void*, u64>> tables = std::vector<std::pair<const void*, u64>>(8, {nullptr, 0});
+  // per-handle stream-ordered pool for per-call scratch (scan temporaries, list lengths).  It keeps what it has freed
+  // (release threshold = max), so a call after a synchronisation does not pay for fresh physical memory again
+  // (measured: 1.5-4 ms on the first decode call after every sync with the default pool's threshold of 0).
+  cudaMemPool_t pool = nullptr;
+  ~mazu_index() {
+    if (pool) cudaMemPoolDestroy(pool);
+  }
   u64 device_bytes() const {
     return (d_unitigs ? d_unitigs->bytes : 0) + (d_k2u ? d_k2u->bytes : 0) + (d_u2pos ? d_u2pos->bytes : 0) + (d_refs ? d_refs->bytes : 0);
   }
@@ -655,6 +662,16 @@ mazu_index* finalize_index(std::unique_ptr<mazu_index> ix) {
   cudaDeviceProp prop;
   MZ_CUDA(cudaGetDeviceProperties(&prop, ix->device));
   ix->sm_count = prop.multiProcessorCount;
+  {
+    cudaMemPoolProps pp{};
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = ix->device;
+    MZ_CUDA(cudaMemPoolCreate(&ix->pool, &pp));
+    unsigned long long keep = ~0ULL;
+    MZ_CUDA(cudaMemPoolSetAttribute(ix->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   if (!ix->d_unitigs) ix->d_unitigs = upload_unitigs(*ix->unitigs, ix->device);
   ix->view.unitigs = ix->d_unitigs->view;
   if (ix->gpu_builder) ix->gpu_builder(*ix);  // tables are produced in HBM (gpu_build.cuh)
@@ -727,13 +744,13 @@ void launch_query_reads(const mazu_index* ix, const u8* d_bases, const u64* d_re
 }
 
 // exclusive scan with the total appended: out[0..n] from in[0..n)
-void device_exclusive_scan(const u64* d_in, u64* d_out, u64 n, cudaStream_t s) {
+void device_exclusive_scan(const u64* d_in, u64* d_out, u64 n, cudaMemPool_t pool, cudaStream_t s) {
   // scan n+1 items where the last input is ignored: simplest is an exclusive scan over n items plus one tail kernel-free trick:
   // run ExclusiveSum over n+1 elements with in[n] readable (callers allocate n+1).
   size_t tmp_bytes = 0;
   MZ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_in, d_out, (size_t)(n + 1), s));
   void* tmp = nullptr;
-  MZ_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, s));
+  MZ_CUDA(cudaMallocFromPoolAsync(&tmp, tmp_bytes ? tmp_bytes : 1, pool, s));
   MZ_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_in, d_out, (size_t)(n + 1), s));
   MZ_CUDA(cudaFreeAsync(tmp, s));
 }
@@ -1024,15 +1041,15 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       void* tmp_koffs = nullptr;
       if (!uniform_read_len && n_reads) {
         if (!d_koffs) {
-          MZ_CUDA(cudaMallocAsync(&tmp_koffs, (n_reads + 1) * 8, s));
+          MZ_CUDA(cudaMallocFromPoolAsync(&tmp_koffs, (n_reads + 1) * 8, idx->pool, s));
           d_koffs = (u64*)tmp_koffs;
         }
         void* lens = nullptr;
-        MZ_CUDA(cudaMallocAsync(&lens, (n_reads + 1) * 8, s));
+        MZ_CUDA(cudaMallocFromPoolAsync(&lens, (n_reads + 1) * 8, idx->pool, s));
         MZ_CUDA(cudaMemsetAsync(lens, 0, (n_reads + 1) * 8, s));
         kmer_counts_kernel<<<(int)std::min<u64>((n_reads + 255) / 256, 4096), 256, 0, s>>>(read_offsets, n_reads, k, (u64*)lens);
         MZ_CUDA(cudaGetLastError());
-        device_exclusive_scan((const u64*)lens, d_koffs, n_reads, s);
+        device_exclusive_scan((const u64*)lens, d_koffs, n_reads, idx->pool, s);
         MZ_CUDA(cudaFreeAsync(lens, s));
       }
       launch_query_reads(idx, bases, read_offsets, n_reads, uniform_read_len, mode, d_koffs, out_hits, compact, counts, s);
@@ -1188,13 +1205,13 @@ static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu
     d_offsets = (u64*)d_offs->p;
   }
   void* lens = nullptr;
-  MZ_CUDA(cudaMallocAsync(&lens, (n + 1) * 8, s));
+  MZ_CUDA(cudaMallocFromPoolAsync(&lens, (n + 1) * 8, idx->pool, s));
   MZ_CUDA(cudaMemsetAsync(lens, 0, (n + 1) * 8, s));
   if (n) {
     occ_lens_kernel<<<(int)std::min<u64>((n + 255) / 256, (u64)idx->sm_count * 8), 256, 0, s>>>(idx->view, d_uids, d_hits, n, (u64*)lens);
     MZ_CUDA(cudaGetLastError());
   }
-  device_exclusive_scan((const u64*)lens, d_offsets, n, s);
+  device_exclusive_scan((const u64*)lens, d_offsets, n, idx->pool, s);
   MZ_CUDA(cudaFreeAsync(lens, s));
   u64 total = 0;
   bool need_total = mem == MAZU_MEM_HOST || out_total != nullptr;
