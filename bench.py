@@ -278,6 +278,7 @@ def main():
     check = None          # callable -> bool : parity spot check (rank 0)
     e2e_step = None       # callable: one end-to-end step through host buffers
     e2e_compact_step = None  # same with 8-byte records
+    e2e_extra = {}        # name -> (callable, d2h bytes per step, api description): further end-to-end variants, reported next to the headline
     e2e_bytes = (0, 0)
     e2e_units = None      # units per e2e step (defaults to n_units)
     cpu_fn = None         # callable -> cpu_baseline dict
@@ -386,6 +387,14 @@ def main():
 
             def e2e_compact_step():
                 index.query_reads(hb, None, n_reads=e2e_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=h_hits8, counts=h_cnt, compact=True)
+
+            def e2e_devout_step():  # reads from pinned host memory, records left in HBM for the next device stage, counters back
+                index.query_reads(hb, None, n_reads=e2e_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=hits, counts=h_cnt,
+                                  mem=mz.MEM_HOST_IN_DEVICE_OUT)
+
+            e2e_extra = {"host_reads_in_device_records_out": (e2e_devout_step, 24,
+                         "MAZU_MEM_HOST_IN_DEVICE_OUT: pinned host reads in, 16-byte records stay in HBM (input of project_hits on the device), "
+                         "the three counters of `kphf bench` (src/bin/kphf/main.rs:282-284) come back")}
 
         def check():
             if W == "config5":  # no oracle index at this scale: verify sampled hits directly against the packed sequence
@@ -591,6 +600,19 @@ def main():
             e2e["compact_records"] = {"value": float(eu) * args.steps * world / float(tt.item()), "unit": unit,
                                       "d2h_bytes_per_step": (eu * 8 + 24) * world,
                                       "api": "mazu_b200_query_reads_compact: 8-byte {unitig_id, pos|match<<30} records"}
+
+        for name, (fn, d2h, api) in e2e_extra.items():
+            fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                fn()
+            barrier()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e[name] = {"value": float(eu) * args.steps * world / float(tt.item()), "unit": unit, "h2d_bytes_per_step": e2e_bytes[0] * world,
+                         "d2h_bytes_per_step": d2h * world, "api": api}
 
     if rank != 0:
         if world > 1:

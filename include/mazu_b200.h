@@ -16,7 +16,10 @@
  *  - `mem` says where the caller's buffers live: MAZU_MEM_HOST (the library stages them through
  *    its own device buffers, chunked and overlapped) or MAZU_MEM_DEVICE (device pointers, e.g.
  *    torch tensors' data_ptr(); work is enqueued on `stream` and the call returns without
- *    synchronising).
+ *    synchronising).  mazu_b200_query_reads[_compact] also take MAZU_MEM_HOST_IN_DEVICE_OUT: reads
+ *    (bases, read_offsets, kmer_offsets, counts) on the host, out_hits a DEVICE pointer -- the hit
+ *    records stay in HBM for the next device stage (mazu_b200_project_hits with MAZU_MEM_DEVICE)
+ *    and only the three counters come back; the call returns after the last chunk has finished.
  *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
  *  - an index handle is immutable after creation and may be used concurrently from several host
  *    threads / streams (reference: queries take &self and are Sync, src/kphf/mod.rs:69-72).
@@ -50,7 +53,7 @@ enum {
 enum { MAZU_NO_MATCH = 0, MAZU_IDENTITY_MATCH = 1, MAZU_TWIN_MATCH = 2,
        MAZU_SKIPPED = 3 /* record filler for windows CanonicalKmerIterator skips (non-ACGT) */ };
 
-enum { MAZU_MEM_HOST = 0, MAZU_MEM_DEVICE = 1 };
+enum { MAZU_MEM_HOST = 0, MAZU_MEM_DEVICE = 1, MAZU_MEM_HOST_IN_DEVICE_OUT = 2 };
 enum { MAZU_MODE_RANDOM = 0,    /* K2U::k2u per k-mer                 (src/bin/kphf/main.rs:311-322) */
        MAZU_MODE_STREAMING = 1  /* .as_streaming() / StreamingK2U     (src/index/caching.rs:65-103); cursor reset per read */ };
 enum { MAZU_K2U_PFHASH = 0, MAZU_K2U_SSHASH = 1,

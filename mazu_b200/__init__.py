@@ -31,7 +31,7 @@ HIT8_DTYPE = np.dtype([("unitig_id", "<u4"), ("pos_match", "<u4")])
 OCC_DTYPE = np.dtype([("ref_id", "<u4"), ("pos", "<u4"), ("fw", "<u4")])
 
 NO_MATCH, IDENTITY_MATCH, TWIN_MATCH, SKIPPED = 0, 1, 2, 3
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_HOST_IN_DEVICE_OUT = 0, 1, 2
 MODE_RANDOM, MODE_STREAMING = 0, 1
 K2U_PFHASH, K2U_SSHASH, K2U_SAMPLED_PFHASH = 0, 1, 2
 U2POS_NONE, U2POS_DENSE, U2POS_PISCEM = 0, 1, 2
@@ -365,7 +365,7 @@ class ModIndex:
         """The read loop of `kphf bench` / validate_ckmers.  Host mode returns (hits, counts, kmer_offsets).
         compact=True writes 8-byte mazu_hit8_t records (HIT8_DTYPE) instead of 16-byte mazu_hit_t."""
         fn = lib().mazu_b200_query_reads_compact if compact else lib().mazu_b200_query_reads
-        if mem == MEM_HOST:
+        if mem in (MEM_HOST, MEM_HOST_IN_DEVICE_OUT):
             bases = np.ascontiguousarray(bases, dtype=np.uint8)
             if uniform_read_len:
                 n_reads = len(bases) // uniform_read_len if n_reads is None else n_reads
@@ -377,11 +377,13 @@ class ModIndex:
                 koffs = None if uniform_read_len else np.zeros(n_reads + 1, dtype=np.uint64)
             else:
                 koffs = kmer_offsets
+            if mem == MEM_HOST_IN_DEVICE_OUT and want_hits and out_hits is None:
+                raise ValueError("MEM_HOST_IN_DEVICE_OUT needs a device buffer in out_hits")
             if want_hits and out_hits is None:
                 out_hits = np.empty(self.count_kmer_slots(ro, n_reads, uniform_read_len), dtype=HIT8_DTYPE if compact else HIT_DTYPE)
             cnt = np.zeros(3, dtype=np.uint64) if counts is None else counts
             _check(fn(self._h, _np_ptr(bases), _np_ptr(ro), n_reads, uniform_read_len, mode, _np_ptr(koffs),
-                                               _any_ptr(out_hits) if want_hits else None, _np_ptr(cnt), MEM_HOST, None))
+                                               _any_ptr(out_hits) if want_hits else None, _np_ptr(cnt), mem, None))
             return out_hits, cnt, koffs
         _check(fn(self._h, _any_ptr(bases), _any_ptr(read_offsets), n_reads, uniform_read_len, mode,
                   _any_ptr(kmer_offsets), _any_ptr(out_hits), _any_ptr(counts), MEM_DEVICE, _any_ptr(stream)))

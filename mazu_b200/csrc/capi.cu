@@ -988,6 +988,7 @@ mazu_status_t mazu_b200_k2u_batch(const mazu_index_t* idx, const uint64_t* fw_wo
     if (!idx || (n && (!fw_words || !out_hits))) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
     check_k(idx, k);
     DeviceGuard g(idx->device);
+    if (mem != MAZU_MEM_HOST && mem != MAZU_MEM_DEVICE) throw Error(MAZU_ERR_INVALID_ARG, "unknown mem mode");
     if (mem == MAZU_MEM_DEVICE) {
       launch_k2u_batch(idx, fw_words, n, (Hit*)out_hits, (cudaStream_t)stream);
       return;
@@ -1056,6 +1057,8 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       if (tmp_koffs) MZ_CUDA(cudaFreeAsync(tmp_koffs, s));
       return;
     }
+    if (mem != MAZU_MEM_HOST && mem != MAZU_MEM_HOST_IN_DEVICE_OUT) throw Error(MAZU_ERR_INVALID_ARG, "unknown mem mode");
+    const bool dev_out = mem == MAZU_MEM_HOST_IN_DEVICE_OUT;  // records are written straight into the caller's device buffer
     // ---- host buffers: chunk the batch, overlap H2D / kernel / D2H on two streams ----
     std::vector<u64> koffs_local;
     const u64* koffs = nullptr;
@@ -1080,7 +1083,11 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
     auto base_off = [&](u64 r) { return uniform_read_len ? r * uniform_read_len : read_offsets[r]; };
     auto slot_off = [&](u64 r) { return uniform_read_len ? r * (uniform_read_len >= k ? uniform_read_len - k + 1 : 0) : koffs[r]; };
     // chunk boundaries: ~32 MiB of bases per chunk
-    const u64 TARGET = 32ull << 20;
+    u64 TARGET = 32ull << 20;
+    if (const char* e = getenv("MAZU_B200_CHUNK_MIB")) {  // tuning knob: bases per pipeline chunk
+      long v = atol(e);
+      if (v > 0) TARGET = (u64)v << 20;
+    }
     std::vector<u64> cuts{0};
     {
       u64 r = 0;
@@ -1112,7 +1119,7 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
         d_ro[b] = std::make_unique<DevBuf>((max_reads + 1) * 8, idx->device);
         d_ko[b] = std::make_unique<DevBuf>((max_reads + 1) * 8, idx->device);
       }
-      if (out_hits) d_hits[b] = std::make_unique<DevBuf>(max_slots * rec + 16, idx->device);
+      if (out_hits && !dev_out) d_hits[b] = std::make_unique<DevBuf>(max_slots * rec + 16, idx->device);
     }
     int b = 0;
     for (size_t c = 0; c + 1 < cuts.size(); ++c, b ^= 1) {
@@ -1131,9 +1138,11 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       }
       // offsets uploaded are absolute: rebase the data pointers instead of the offset arrays
       const u8* dbases = (const u8*)d_bases[b]->p - (uniform_read_len ? 0 : b0);
-      void* dh = out_hits ? (void*)((char*)d_hits[b]->p - (uniform_read_len ? 0 : s0 * rec)) : nullptr;
+      void* dh = nullptr;
+      if (out_hits && dev_out) dh = (char*)out_hits + (uniform_read_len ? s0 * rec : 0);
+      else if (out_hits) dh = (char*)d_hits[b]->p - (uniform_read_len ? 0 : s0 * rec);
       launch_query_reads(idx, dbases, dro, r1 - r0, uniform_read_len, mode, dko, dh, compact, (u64*)d_counts.p, s);
-      if (out_hits && ns) MZ_CUDA(cudaMemcpyAsync((char*)out_hits + s0 * rec, d_hits[b]->p, ns * rec, cudaMemcpyDeviceToHost, s));
+      if (out_hits && !dev_out && ns) MZ_CUDA(cudaMemcpyAsync((char*)out_hits + s0 * rec, d_hits[b]->p, ns * rec, cudaMemcpyDeviceToHost, s));
     }
     MZ_CUDA(cudaStreamSynchronize(sp.s[0]));
     MZ_CUDA(cudaStreamSynchronize(sp.s[1]));
@@ -1186,6 +1195,7 @@ static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu
                        mazu_occ_t* out, uint64_t cap, uint64_t* out_total, int32_t mem, void* stream) {
   if (!idx || !out_offsets) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
   if (idx->view.u2pos_kind == MAZU_U2POS_NONE) throw Error(MAZU_ERR_NO_U2POS, "index has no U2Pos table");
+  if (mem != MAZU_MEM_HOST && mem != MAZU_MEM_DEVICE) throw Error(MAZU_ERR_INVALID_ARG, "unknown mem mode");
   DeviceGuard g(idx->device);
   const bool project = hits != nullptr;
   cudaStream_t s = (cudaStream_t)stream;

@@ -319,6 +319,36 @@ def test_query_reads_device_mode(yeast_sshash, yeast_queries):
         assert list(d_cnt.cpu().numpy()) == list(wcnt.astype(np.int64))
 
 
+@pytest.mark.parametrize("ragged", [True, False])
+def test_query_reads_host_in_device_out(yeast_sshash, yeast_queries, ragged):
+    """MAZU_MEM_HOST_IN_DEVICE_OUT: reads on the host, records left in HBM (then projected on the device), counters back."""
+    import torch
+    g, o = yeast_sshash
+    _, ref_codes = yeast_queries
+    bases, offs = _gen.sample_reads(ref_codes, 2500, 150, seed=9, frac_ref=0.6, sub_rate=0.02, n_rate=0.001, ragged=ragged)
+    for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+        for compact in (False, True):
+            want, wcnt, wk = o.query_reads(bases, offs, streaming=bool(mode))
+            d_hits = torch.zeros((len(want), 2 if compact else 4), dtype=torch.int32, device="cuda")
+            kw = dict(read_offsets=offs) if ragged else dict(uniform_read_len=150)
+            _, cnt, ko = g.query_reads(bases, mode=mode, out_hits=d_hits, mem=mz.MEM_HOST_IN_DEVICE_OUT, compact=compact, **kw)
+            assert list(cnt) == list(wcnt)
+            if ragged:
+                assert np.array_equal(ko, wk)
+            got = d_hits.cpu().numpy().view(np.uint32).reshape(-1)
+            if compact:
+                got = got.view(mz.HIT8_DTYPE)
+                hit = (want["match"] == mz.IDENTITY_MATCH) | (want["match"] == mz.TWIN_MATCH)
+                assert np.array_equal(got["unitig_id"][hit], want["unitig_id"][hit])
+                assert np.array_equal(got["pos_match"] >> 30, want["match"])
+                assert np.array_equal((got["pos_match"] & 0x3FFFFFFF)[hit], want["pos"][hit])
+            else:
+                assert_hits_equal(got.view(mz.HIT_DTYPE), want, "host-in/device-out mode %d" % mode)
+    with pytest.raises(mz.MazuError) as e:  # the other entry points only know HOST and DEVICE
+        g.k2u_batch(np.zeros(4, dtype=np.uint64), out=np.zeros(4, dtype=mz.HIT_DTYPE), mem=mz.MEM_HOST_IN_DEVICE_OUT, n=4)
+    assert e.value.code == -7
+
+
 def test_streaming_exact_with_duplicate_kmers():
     """A unitig set whose canonical k-mers are NOT unique (not a valid cdBG): random-access and
     streaming answers differ there, and the GPU walk must reproduce the reference's sequential
