@@ -339,7 +339,7 @@ DevMphf build_mphf_gpu(CubTemp& tmp, const u64* d_keys, u64 n, double gamma, int
   std::vector<u64> level_nb;
   u64 n_cur = n, total_ones = 0, total_nb = 0;
   for (u32 lvl = 0; lvl < MPHF_MAX_LEVELS && n_cur > 0; ++lvl) {
-    const u64 nb = (u64)((gamma * (double)n_cur) / MPHF_BLOCK_BITS) + 1;
+    const u64 nb = (u64)((native_level_gamma(gamma, lvl) * (double)n_cur) / MPHF_BLOCK_BITS) + 1;
     if (nb >> 32) throw Error(MAZU_ERR_INVALID_ARG, "MPHF level too large");
     auto seen = std::make_shared<DevBuf>(nb * 32, dev);
     DevBuf coll(nb * 32, dev), ones((nb + 1) * 4, dev), prefix((nb + 1) * 4, dev);

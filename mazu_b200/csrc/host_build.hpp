@@ -317,7 +317,7 @@ struct MphfHost {
     std::vector<u64> keys = keys_in, next;
     for (u32 lvl = 0; lvl < MPHF_MAX_LEVELS && !keys.empty(); ++lvl) {
       u64 n = keys.size();
-      u64 nb = (u64)((gamma * (double)n) / MPHF_BLOCK_BITS) + 1;
+      u64 nb = (u64)((native_level_gamma(gamma, lvl) * (double)n) / MPHF_BLOCK_BITS) + 1;
       if (nb >> 32) throw Error(MAZU_ERR_INVALID_ARG, "MPHF level too large");
       u64 n_slots = nb * MPHF_BLOCK_BITS;
       std::vector<u64> seen((n_slots + 63) / 64, 0), coll((n_slots + 63) / 64, 0);

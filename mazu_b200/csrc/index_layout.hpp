@@ -98,6 +98,14 @@ MZ_HD u64 ranked_rank(const RankedLevels& m, u32 level, u64 blk, u32 bit) {
   return m.rank_base[level] + r;
 }
 
+// Load factor of level `l` of the native cascade.  The first two levels use gamma (2 slots per key) and place
+// ~85 % of the keys; after that gamma escalates (x4, then x32) so the few keys left are placed almost without
+// collisions and the cascade ends after 5-6 levels instead of ~9 (yeast minimizers) / ~20 (human scale).  The
+// level loop of a warp runs until its slowest lane is done, and a NON-member key walks all levels unless it
+// meets a set bit (30 % per level at gamma = 2), so the depth of the cascade -- not the average level of a
+// member -- is what a warp of mixed lookups pays for.  Costs ~5.2 instead of 3.3 bits per key.
+MZ_HD double native_level_gamma(double gamma, u32 level) { return level < 2 ? gamma : (level == 2 ? 4.0 * gamma : 32.0 * gamma); }
+
 // MPHF::try_hash_u64 (src/kphf/mod.rs:54-56).  BOOPHF reproduces BooPHF<u64>::lookup
 // (src/pf1/boophf/mod.rs:96-181) bit-exactly; NATIVE is this library's own BBHash-style MPHF.
 // Like boomphf::try_hash, a non-member key may return a false-positive value < n_keys.
