@@ -152,6 +152,7 @@ static const u32 BN_SKEW = 0xFFFFFFFFu;
 
 struct WarpStage {
   u64 fw[QR_CHUNK];      // forward k-mer word per chunk position (garbage where invalid)
+  u64 rc[QR_CHUNK];      // its reverse complement, written by stage M (SSHash only) so stages B and V do not recompute it
   u64 bstart[QR_CHUNK];  // leaders only: first bucket entry
   u32 bn[QR_CHUNK];      // leaders only: bucket size, 0 = minimizer unknown, BN_SKEW = heavy bucket
   u32 hf[QR_BASES];      // w-mer hash keys, forward strand
@@ -266,6 +267,7 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
     u64 mmw = 0;
     if (valid) {
       u64 fw = S.fw[p], rc = revcomp(fw, k);
+      S.rc[p] = rc;
       bool fw_canon = fw <= rc;
       // offset c in the canonical k-mer: fw strand position p+c, rc strand position p+span-c (= reversed index below + c)
       const u32* h = fw_canon ? S.hf + p : S.hr + (QR_BASES - 1 - p - span);
@@ -299,7 +301,7 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
   for (u32 i = 0; i < n_lead; i += 32) {
     if (i + lane < n_lead) {
       u32 p = S.lead_list[i + lane];
-      u64 fw = S.fw[p], rc = revcomp(fw, k);
+      u64 fw = S.fw[p], rc = S.rc[p];
       u64 mmw = mm_word_of(fw, rc, S.off[p], k, w);
       u64 h, a = 0, b = 0;
       u32 n = 0;
@@ -475,7 +477,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
         for (u32 p = lane; p < n_c; p += 32) {
           Hit h = hit_none(SKIPPED);
           if (chunk_valid(ci, p)) {
-            u64 fw = S.fw[p], rc = revcomp(fw, k);
+            u64 fw = S.fw[p], rc = SS ? S.rc[p] : revcomp(fw, k);
             bool ok = SS ? verify_sshash<FAMILY>(ix, S, p, fw, rc, h)
                          : (KIND == MAZU_K2U_SAMPLED_PFHASH ? sampled_pfhash_k2u_t<FAMILY>(ix, fw, rc, h, nullptr) : pfhash_k2u_t<FAMILY>(ix, fw, rc, h));
             ++n_valid;
