@@ -239,8 +239,14 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
   const u32 k = ix.unitigs.k, w = ix.w, span = k - w;
   const u64 wmask = kmer_mask(w);
   __syncwarp();
+  // reverse complement of every k-mer word of the chunk, once (stages M, B and V read it from here)
+#pragma unroll
+  for (int t = 0; t < 4; ++t) S.rc[32 * t + lane] = revcomp(S.fw[32 * t + lane], k);
+  __syncwarp();
   // w-mer hash keys for chunk positions [0, 160): w-mer q is the low 2w bits of k-mer q (q < 128),
-  // positions beyond come from the tail of k-mer 127
+  // positions beyond come from the tail of k-mer 127.  Its reverse complement is the low 2w bits of
+  // rc(k-mer q - span) (the top w bases of that k-mer), so no w-mer is reverse-complemented on its own.
+  // Only w-mers q <= 127 + span belong to a k-mer of the chunk; the keys beyond are never read.
 #pragma unroll 1
   for (int t = 0; t < 5; ++t) {
     u32 q = 32 * t + lane;
@@ -251,8 +257,9 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
       x = d < 32 ? (S.fw[QR_CHUNK - 1] >> (2 * d)) : 0ULL;
     }
     u64 wf = x & wmask;
+    u64 wr = q >= span ? S.rc[min(q - span, (u32)QR_CHUNK - 1)] : (S.rc[0] >> (2 * (span - q)));
     S.hf[q] = mm_hash32(wf, ix.seed) & MM_KEY_MASK;
-    S.hr[QR_BASES - 1 - q] = mm_hash32(revcomp(wf, w), ix.seed) & MM_KEY_MASK;
+    S.hr[QR_BASES - 1 - q] = mm_hash32(wr & wmask, ix.seed) & MM_KEY_MASK;
   }
   __syncwarp();
   // per k-mer minimizer, leader detection, leader compaction
@@ -266,8 +273,7 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
     const bool valid = (vmask >> lane) & 1u;
     u64 mmw = 0;
     if (valid) {
-      u64 fw = S.fw[p], rc = revcomp(fw, k);
-      S.rc[p] = rc;
+      u64 fw = S.fw[p], rc = S.rc[p];
       bool fw_canon = fw <= rc;
       // offset c in the canonical k-mer: fw strand position p+c, rc strand position p+span-c (= reversed index below + c)
       const u32* h = fw_canon ? S.hf + p : S.hr + (QR_BASES - 1 - p - span);
