@@ -23,6 +23,13 @@ def test_header_matches_binding():
     assert _header_symbols() == mz.exported_symbols()
 
 
+def test_rust_sys_crate_declares_every_symbol():
+    """bindings/rust/mazu-b200-sys mirrors include/mazu_b200.h symbol for symbol (no Rust toolchain here: a text check)."""
+    text = open(os.path.join(ROOT, "bindings", "rust", "mazu-b200-sys", "src", "lib.rs")).read()
+    rust = sorted(set(re.findall(r"pub fn (mazu_b200_[a-z0-9_]+)\s*\(", text)))
+    assert rust == _header_symbols()
+
+
 def test_library_exports_every_declared_symbol():
     assert os.path.exists(mz.LIB_PATH), "libmazu_b200.so not built (run __graft_entry__.build())"
     L = C.CDLL(mz.LIB_PATH)
