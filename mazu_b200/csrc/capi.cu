@@ -713,13 +713,25 @@ void launch_k2u_batch(const mazu_index* ix, const u64* d_words, u64 n, Hit* d_ou
   MZ_CUDA(cudaGetLastError());
 }
 
-template <int MODE, int KIND, u32 FAMILY>
-void launch_qr(const mazu_index* ix, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, const u64* d_kmer_offsets,
-               void* d_out, u32 compact, u64* d_counts, cudaStream_t s) {
-  auto kern = query_reads_kernel<MODE, KIND, FAMILY>;
+template <int MODE, int KIND, u32 FAMILY, int OCC>
+void launch_qr_occ(const mazu_index* ix, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, const u64* d_kmer_offsets,
+                   void* d_out, u32 compact, u64* d_counts, cudaStream_t s) {
+  auto kern = query_reads_kernel<MODE, KIND, FAMILY, OCC>;
   int grid = grid_for(kern, QR_WARPS * 32, ix, QR_WARPS, n_reads);
   kern<<<grid, QR_WARPS * 32, 0, s>>>(ix->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact,
                                       (unsigned long long*)d_counts);
+}
+template <int MODE, int KIND, u32 FAMILY>
+void launch_qr(const mazu_index* ix, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, const u64* d_kmer_offsets,
+               void* d_out, u32 compact, u64* d_counts, cudaStream_t s) {
+  // streaming walk: 3 resident CTAs (80 registers) while the index sits in the 126 MB L2, 4 (64 registers) once it does not
+  if constexpr (MODE == 1) {
+    if (ix->device_bytes() <= (96ull << 20)) {
+      launch_qr_occ<MODE, KIND, FAMILY, 3>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, s);
+      return;
+    }
+  }
+  launch_qr_occ<MODE, KIND, FAMILY, MODE == 1 ? 4 : 0>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, s);
 }
 
 void launch_query_reads(const mazu_index* ix, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, int mode,

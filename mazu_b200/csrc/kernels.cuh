@@ -437,8 +437,12 @@ struct StreamState {  // StreamingK2U { is_warm, prev_k2upos } (src/index/cachin
 // One kernel for the read loop of `kphf bench` / validate_ckmers.
 //   MODE 0: K2U::k2u per k-mer.  MODE 1: StreamingK2U::k2u_streaming, cursor reset per read.
 //   KIND: MAZU_K2U_PFHASH / MAZU_K2U_SSHASH.  FAMILY: MPHF family of the index.
-template <int MODE, int KIND, u32 FAMILY>
-__global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
+// OCC = resident CTAs per SM the instantiation is compiled for (register budget: 3 -> <= 80, 4 -> <= 64).  The streaming
+// walk wants its 80 registers while the index is cache-resident (+3.5 % on the yeast configs) and the extra warps once
+// lookups wait on DRAM (+13 % on a 1.7 GB index); the launcher picks by index size.  Random-access mode passes 0 (no
+// minimum: ptxas settles on 64 registers by itself).
+template <int MODE, int KIND, u32 FAMILY, int OCC>
+__global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
                                                                     const u64* __restrict__ read_offsets, u64 n_reads, u64 uniform_len,
                                                                     const u64* __restrict__ kmer_offsets, void* __restrict__ out, u32 compact,
                                                                     unsigned long long* __restrict__ counts) {
@@ -492,120 +496,105 @@ __global__ void __launch_bounds__(QR_WARPS * 32) query_reads_kernel(const __grid
           if (o) store_rec(o, p, h, compact);
         }
       } else {
-        bool prepared = false;  // stage M/B run lazily: a fully warm chunk never needs them
-        u32 i = 0;
+        // StreamingK2U::k2u_streaming (caching.rs:65-103).  Every k-mer of the chunk first gets its COLD answer through the
+        // same staged path as the random-access mode (stages M, B, V -- the dependent chain runs once per super-k-mer),
+        // then the sequential cursor semantics are settled per group of 32 consecutive k-mers:
+        //   hypothesis  each lane's answer is its cold answer, so the cursor a lane sees is the cold hit of the nearest
+        //               earlier hit lane (or the cursor carried in).
+        //   check       a lane whose cold answer is exactly "cursor + 1 on the same unitig" needs nothing: the warm test of
+        //               the reference (k2u_warm, caching.rs:73-97) reads that very window and answers the same.  Any other
+        //               lane with a warm cursor in range does the warm test; if it matches, the walk answers THERE although
+        //               the cold lookup answered elsewhere or missed (only possible with duplicated canonical k-mers).
+        //   commit      lanes up to and including the first such lane commit (its own cursor was right), the cursor becomes
+        //               its warm answer and the remaining lanes of the group are re-checked against it -- their cold answers
+        //               are kept, nothing is looked up twice.  A miss leaves the cursor untouched (`?` at caching.rs:100).
+        // (An earlier version extended warm cursors first and looked up cold only on demand; on a GPU the cold path is
+        // already amortised per super-k-mer: always-cold + verify measured +5 % on config 3 and, being small enough for the
+        // 64-register build, +15 % on a 1.7 GB index.)
+        if (SS) stage_buckets<FAMILY>(ix, ci, lane, S);
 #pragma unroll 1
-        while (i < n_c) {
-          const u32 q = i + lane;
+        for (u32 g0 = 0; g0 < n_c; g0 += 32) {
+          const u32 q = g0 + lane;
           const bool active = q < n_c;
           const bool valid = active && chunk_valid(ci, q);
           u64 fw = 0, rc = 0;
-          if (valid) {
-            fw = S.fw[q];
-            rc = revcomp(fw, k);
-          }
-          const u32 vmask = __ballot_sync(0xffffffffu, valid);
-          const u32 rnk = __popc(vmask & lt_mask);
-          if (st.warm) {
-            // Phase W: extend along the current unitig (k2u_warm, caching.rs:73-97), 32 k-mers at once
-            u32 np = st.pos + 1 + rnk;
-            u32 m = NO_MATCH;
-            if (valid && (u64)np + k <= (u64)st.ulen) m = word_equivalency(fw, rc, useq_window(ix.unitigs, st.ustart + np));
-            const bool okw = active && (!valid || m != NO_MATCH);
-            const u32 bad = __ballot_sync(0xffffffffu, !okw);
-            const u32 run = bad ? (u32)(__ffs(bad) - 1) : 32u;
-            if (run > 0) {
-              if (lane < run) {
-                Hit h = hit_none(SKIPPED);
-                if (valid) {
-                  h = Hit{st.uid, st.ulen, np, m};
-                  ++n_valid;
-                  ++n_hit;
-                }
-                if (o) store_rec(o, q, h, compact);
-              }
-              const u32 run_mask = run >= 32 ? 0xffffffffu : ((1u << run) - 1u);
-              const u32 vr = vmask & run_mask;
-              if (vr) {
-                int last = 31 - __clz(vr);
-                st.pos += __popc(vr);
-                st.o = __shfl_sync(0xffffffffu, m, last);
-              }
-              i += run;
-              continue;
-            }
-          }
-          // Phase C: cold lookups for all 32 lanes, then commit in read order (k2u_cold, caching.rs:99-103)
-          if (SS && !prepared) {
-            stage_buckets<FAMILY>(ix, ci, lane, S);
-            prepared = true;
-          }
-          // Every valid lane does its cold lookup C_j.  Hypothesis: each lane's answer IS its cold
-          // answer, so the cursor a lane sees is the cold hit of the nearest earlier hit lane (or the
-          // incoming cursor).  Each lane checks that in parallel by doing the warm test the reference
-          // would do against that cursor (caching.rs:73-97).  The first lane whose warm test lands
-          // somewhere else than its cold answer (only possible when canonical k-mers are duplicated)
-          // still commits -- its own cursor was right -- and the walk restarts after it.
           Hit cold = hit_none(NO_MATCH);
           u64 cold_ustart = 0;
           bool cold_hit = false;
           if (valid) {
+            fw = S.fw[q];
+            rc = SS ? S.rc[q] : revcomp(fw, k);
             cold_hit = SS ? verify_sshash<FAMILY>(ix, S, q, fw, rc, cold, &cold_ustart)
                           : (KIND == MAZU_K2U_SAMPLED_PFHASH ? sampled_pfhash_k2u_t<FAMILY>(ix, fw, rc, cold, &cold_ustart)
                                                              : pfhash_k2u_t<FAMILY>(ix, fw, rc, cold, &cold_ustart));
             if (!cold_hit) cold = hit_none(NO_MATCH);
           }
           const u32 chm = __ballot_sync(0xffffffffu, cold_hit);
-          const u32 before = chm & lt_mask;
-          const int prev = before ? 31 - __clz(before) : 0;
-          u32 s_uid = __shfl_sync(0xffffffffu, cold.unitig_id, prev);
-          u32 s_ulen = __shfl_sync(0xffffffffu, cold.unitig_len, prev);
-          u32 s_pos = __shfl_sync(0xffffffffu, cold.pos, prev);
-          u64 s_ustart = __shfl_sync(0xffffffffu, cold_ustart, prev);
-          bool s_warm = before != 0;
-          if (!before) {
-            s_uid = st.uid;
-            s_ulen = st.ulen;
-            s_pos = st.pos;
-            s_ustart = st.ustart;
-            s_warm = st.warm;
-          }
-          Hit res = cold;
-          bool res_hit = cold_hit;
-          bool differs = false;
-          if (valid && s_warm && (u64)s_pos + 1 + k <= (u64)s_ulen &&
-              !(cold_hit && cold.unitig_id == s_uid && cold.pos == s_pos + 1)) {
-            u32 m = word_equivalency(fw, rc, useq_window(ix.unitigs, s_ustart + s_pos + 1));
-            if (m != NO_MATCH) {  // the walk answers here although the cold lookup answered elsewhere (or missed)
-              res = Hit{s_uid, s_ulen, s_pos + 1, m};
-              res_hit = true;
-              differs = true;
+          u32 start = 0;  // first lane of the group that has not committed yet
+#pragma unroll 1
+          while (true) {
+            const u32 ge_start = 0xffffffffu << start;
+            const bool mine = active && lane >= start;
+            if ((chm & ge_start) == 0 && !st.warm) {
+              // no cursor reaches any remaining lane (cold on entry, no cold hit ahead): every answer is its cold miss
+              if (mine) {
+                if (valid) ++n_valid;
+                if (o) store_rec(o, q, hit_none(valid ? (u32)NO_MATCH : (u32)SKIPPED), compact);
+              }
+              break;
             }
-          }
-          const u32 dm = __ballot_sync(0xffffffffu, differs);
-          const u32 g = dm ? (u32)__ffs(dm) : 32u;  // lanes [0, g) commit (g includes the first differing lane)
-          if (lane < g && active) {
-            Hit h = res;
-            if (!valid) h = hit_none(SKIPPED);
-            else {
-              ++n_valid;
-              if (res_hit) ++n_hit;
+            const u32 before = chm & lt_mask & ge_start;
+            const int prev = before ? 31 - __clz(before) : 0;
+            u32 s_uid = __shfl_sync(0xffffffffu, cold.unitig_id, prev);
+            u32 s_ulen = __shfl_sync(0xffffffffu, cold.unitig_len, prev);
+            u32 s_pos = __shfl_sync(0xffffffffu, cold.pos, prev);
+            u64 s_ustart = __shfl_sync(0xffffffffu, cold_ustart, prev);
+            bool s_warm = before != 0;
+            if (!before) {
+              s_uid = st.uid;
+              s_ulen = st.ulen;
+              s_pos = st.pos;
+              s_ustart = st.ustart;
+              s_warm = st.warm;
             }
-            if (o) store_rec(o, q, h, compact);
+            Hit res = cold;
+            bool res_hit = cold_hit;
+            bool differs = false;
+            if (mine && valid && s_warm && (u64)s_pos + 1 + k <= (u64)s_ulen &&
+                !(cold_hit && cold.unitig_id == s_uid && cold.pos == s_pos + 1)) {
+              u32 m = word_equivalency(fw, rc, useq_window(ix.unitigs, s_ustart + s_pos + 1));
+              if (m != NO_MATCH) {  // the walk answers here although the cold lookup answered elsewhere (or missed)
+                res = Hit{s_uid, s_ulen, s_pos + 1, m};
+                res_hit = true;
+                differs = true;
+              }
+            }
+            const u32 dm = __ballot_sync(0xffffffffu, differs);
+            const u32 g = dm ? (u32)__ffs(dm) : 32u;  // lanes [start, g) commit (g includes the first differing lane)
+            if (mine && lane < g) {
+              Hit h = res;
+              if (!valid) h = hit_none(SKIPPED);
+              else {
+                ++n_valid;
+                if (res_hit) ++n_hit;
+              }
+              if (o) store_rec(o, q, h, compact);
+            }
+            const u32 gm = g >= 32 ? 0xffffffffu : ((1u << g) - 1u);
+            const u32 hm = __ballot_sync(0xffffffffu, res_hit && mine) & gm;
+            if (hm) {  // cursor = last committed hit (a miss leaves it untouched, caching.rs:100)
+              const int last = 31 - __clz(hm);
+              u64 us = differs ? s_ustart : cold_ustart;
+              st.uid = __shfl_sync(0xffffffffu, res.unitig_id, last);
+              st.ulen = __shfl_sync(0xffffffffu, res.unitig_len, last);
+              st.pos = __shfl_sync(0xffffffffu, res.pos, last);
+              st.o = __shfl_sync(0xffffffffu, res.match, last);
+              st.ustart = __shfl_sync(0xffffffffu, us, last);
+              st.warm = 1;
+            }
+            if (g >= 32) break;
+            start = g;
           }
-          const u32 gm = g >= 32 ? 0xffffffffu : ((1u << g) - 1u);
-          const u32 hm = __ballot_sync(0xffffffffu, res_hit) & gm;
-          if (hm) {  // cursor = last committed hit (a miss leaves it untouched, caching.rs:100)
-            const int last = 31 - __clz(hm);
-            u64 us = differs ? s_ustart : cold_ustart;
-            st.uid = __shfl_sync(0xffffffffu, res.unitig_id, last);
-            st.ulen = __shfl_sync(0xffffffffu, res.unitig_len, last);
-            st.pos = __shfl_sync(0xffffffffu, res.pos, last);
-            st.o = __shfl_sync(0xffffffffu, res.match, last);
-            st.ustart = __shfl_sync(0xffffffffu, us, last);
-            st.warm = 1;
-          }
-          i += g;
         }
       }
     }
