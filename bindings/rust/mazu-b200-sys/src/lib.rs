@@ -117,6 +117,7 @@ extern "C" {
                                                contig_offsets: *const mazu_packed_vec_desc_t) -> mazu_status_t;
     pub fn mazu_b200_index_attach_refseq(idx: *mut mazu_index_t, seq_words: *const u64, prefix_sum: *const u64, n_refs: u64) -> mazu_status_t;
     pub fn mazu_b200_index_destroy(idx: *mut mazu_index_t);
+    pub fn mazu_b200_index_release_scratch(idx: *mut mazu_index_t, released: *mut u64) -> mazu_status_t;
     pub fn mazu_b200_index_info(idx: *const mazu_index_t, what: i32) -> u64;
     pub fn mazu_b200_unitig_len(idx: *const mazu_index_t, unitig_id: u64, len: *mut u64, start_pos: *mut u64) -> mazu_status_t;
     pub fn mazu_b200_k2u_batch(idx: *const mazu_index_t, fw_words: *const u64, n: u64, k: u32, out_hits: *mut mazu_hit_t, mem: i32,

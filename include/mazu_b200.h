@@ -165,6 +165,10 @@ mazu_status_t mazu_b200_index_attach_u2pos_piscem(mazu_index_t* idx, const mazu_
 mazu_status_t mazu_b200_index_attach_refseq(mazu_index_t* idx, const uint64_t* seq_words, const uint64_t* prefix_sum,
                                             uint64_t n_refs);
 void mazu_b200_index_destroy(mazu_index_t* idx);
+/* Calls with host buffers stage through device scratch taken from a pool the handle owns; the pool keeps what it
+ * has used (about 1 GB after a large mazu_b200_query_reads) so later calls pay no allocation.  This returns the
+ * idle scratch to the driver; *released (optional) receives the bytes given back. */
+mazu_status_t mazu_b200_index_release_scratch(mazu_index_t* idx, uint64_t* released);
 
 /* ---------------------------------------------------------------------------------------------
  * K2U accessors (src/kphf/mod.rs:58-67) and index stats

@@ -94,6 +94,7 @@ def _signatures():
         "mazu_b200_index_attach_u2pos_piscem": (i32, [vp, C.POINTER(PackedVecDesc), u64, u64, C.POINTER(PackedVecDesc)]),
         "mazu_b200_index_attach_refseq": (i32, [vp, vp, vp, u64]),
         "mazu_b200_index_destroy": (None, [vp]),
+        "mazu_b200_index_release_scratch": (i32, [vp, vp]),
         "mazu_b200_index_info": (u64, [vp, i32]),
         "mazu_b200_unitig_len": (i32, [vp, u64, vp, vp]),
         "mazu_b200_k2u_batch": (i32, [vp, vp, u64, u32, vp, i32, vp]),
@@ -248,6 +249,12 @@ class ModIndex:
                 self._h = None
         except Exception:
             pass
+
+    def release_scratch(self):
+        """Give the handle's idle staging memory back to the driver; returns the bytes released."""
+        n = C.c_uint64(0)
+        _check(lib().mazu_b200_index_release_scratch(self._h, C.byref(n)))
+        return int(n.value)
 
     # --- construction ----------------------------------------------------------------------
     @staticmethod

@@ -778,6 +778,35 @@ struct StreamPair {
   }
 };
 
+// Per-call device scratch of the host-buffer paths, taken from the handle's stream-ordered pool on stream `s` and given
+// back on destruction (after the caller has synchronised its streams).  No cudaMalloc / cudaFree per call: both
+// synchronise the whole device, which serialised concurrent callers of one handle and cost milliseconds per batch.
+struct PoolScratch {
+  cudaMemPool_t pool;
+  cudaStream_t s;
+  std::vector<void*> ptrs;
+  PoolScratch(cudaMemPool_t p, cudaStream_t st) : pool(p), s(st) {}
+  void* get(size_t n) {
+    void* p = nullptr;
+    MZ_CUDA(cudaMallocFromPoolAsync(&p, n ? n : 1, pool, s));
+    ptrs.push_back(p);
+    return p;
+  }
+  // make allocations done so far usable on `other`
+  void publish(cudaStream_t other) {
+    cudaEvent_t e;
+    MZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    MZ_CUDA(cudaEventRecord(e, s));
+    MZ_CUDA(cudaStreamWaitEvent(other, e, 0));
+    cudaEventDestroy(e);
+  }
+  ~PoolScratch() {
+    for (void* p : ptrs) cudaFreeAsync(p, s);
+  }
+  PoolScratch(const PoolScratch&) = delete;
+  PoolScratch& operator=(const PoolScratch&) = delete;
+};
+
 }  // namespace
 
 // =============================================================================================
@@ -960,6 +989,19 @@ mazu_status_t mazu_b200_index_attach_refseq(mazu_index_t* idx, const uint64_t* s
 
 void mazu_b200_index_destroy(mazu_index_t* idx) { delete idx; }
 
+mazu_status_t mazu_b200_index_release_scratch(mazu_index_t* idx, uint64_t* released) {
+  return guarded([&] {
+    if (!idx) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    DeviceGuard g(idx->device);
+    unsigned long long before = 0, after = 0;
+    MZ_CUDA(cudaMemPoolGetAttribute(idx->pool, cudaMemPoolAttrReservedMemCurrent, &before));
+    MZ_CUDA(cudaDeviceSynchronize());  // frees queued by earlier calls become visible to the trim
+    MZ_CUDA(cudaMemPoolTrimTo(idx->pool, 0));
+    MZ_CUDA(cudaMemPoolGetAttribute(idx->pool, cudaMemPoolAttrReservedMemCurrent, &after));
+    if (released) *released = before > after ? before - after : 0;
+  });
+}
+
 uint64_t mazu_b200_index_info(const mazu_index_t* idx, int32_t what) {
   if (!idx) return 0;
   switch (what) {
@@ -1008,19 +1050,19 @@ mazu_status_t mazu_b200_k2u_batch(const mazu_index_t* idx, const uint64_t* fw_wo
     // host buffers: double-buffered chunks, H2D -> kernel -> D2H on two streams
     const u64 CH = 1ull << 22;
     StreamPair sp;
-    DevBuf din0(std::min(n, CH) * 8, idx->device), din1(std::min(n, CH) * 8, idx->device);
-    DevBuf dout0(std::min(n, CH) * 16, idx->device), dout1(std::min(n, CH) * 16, idx->device);
-    DevBuf* din[2] = {&din0, &din1};
-    DevBuf* dout[2] = {&dout0, &dout1};
+    PoolScratch scratch(idx->pool, sp.s[0]);
+    void* din[2] = {scratch.get(std::min(n, CH) * 8), scratch.get(std::min(n, CH) * 8)};
+    void* dout[2] = {scratch.get(std::min(n, CH) * 16), scratch.get(std::min(n, CH) * 16)};
+    scratch.publish(sp.s[1]);
     int b = 0;
     for (u64 o = 0; o < n; o += CH, b ^= 1) {
       u64 m = std::min(CH, n - o);
-      MZ_CUDA(cudaMemcpyAsync(din[b]->p, fw_words + o, m * 8, cudaMemcpyHostToDevice, sp.s[b]));
-      launch_k2u_batch(idx, (const u64*)din[b]->p, m, (Hit*)dout[b]->p, sp.s[b]);
-      MZ_CUDA(cudaMemcpyAsync(out_hits + o, dout[b]->p, m * 16, cudaMemcpyDeviceToHost, sp.s[b]));
+      MZ_CUDA(cudaMemcpyAsync(din[b], fw_words + o, m * 8, cudaMemcpyHostToDevice, sp.s[b]));
+      launch_k2u_batch(idx, (const u64*)din[b], m, (Hit*)dout[b], sp.s[b]);
+      MZ_CUDA(cudaMemcpyAsync(out_hits + o, dout[b], m * 16, cudaMemcpyDeviceToHost, sp.s[b]));
     }
-    MZ_CUDA(cudaStreamSynchronize(sp.s[0]));
     MZ_CUDA(cudaStreamSynchronize(sp.s[1]));
+    MZ_CUDA(cudaStreamSynchronize(sp.s[0]));
   });
 }
 
@@ -1122,43 +1164,45 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       max_reads = std::max(max_reads, cuts[c + 1] - cuts[c]);
     }
     StreamPair sp;
-    std::unique_ptr<DevBuf> d_bases[2], d_ro[2], d_ko[2], d_hits[2];
-    DevBuf d_counts(3 * 8, idx->device);
-    MZ_CUDA(cudaMemset(d_counts.p, 0, 24));
+    PoolScratch scratch(idx->pool, sp.s[0]);
+    void *d_bases[2] = {nullptr, nullptr}, *d_ro[2] = {nullptr, nullptr}, *d_ko[2] = {nullptr, nullptr}, *d_hits[2] = {nullptr, nullptr};
+    void* d_counts = scratch.get(3 * 8);
+    MZ_CUDA(cudaMemsetAsync(d_counts, 0, 24, sp.s[0]));
     for (int b = 0; b < 2; ++b) {
-      d_bases[b] = std::make_unique<DevBuf>(max_bases + 16, idx->device);
+      d_bases[b] = scratch.get(max_bases + 16);
       if (!uniform_read_len) {
-        d_ro[b] = std::make_unique<DevBuf>((max_reads + 1) * 8, idx->device);
-        d_ko[b] = std::make_unique<DevBuf>((max_reads + 1) * 8, idx->device);
+        d_ro[b] = scratch.get((max_reads + 1) * 8);
+        d_ko[b] = scratch.get((max_reads + 1) * 8);
       }
-      if (out_hits && !dev_out) d_hits[b] = std::make_unique<DevBuf>(max_slots * rec + 16, idx->device);
+      if (out_hits && !dev_out) d_hits[b] = scratch.get(max_slots * rec + 16);
     }
+    scratch.publish(sp.s[1]);
     int b = 0;
     for (size_t c = 0; c + 1 < cuts.size(); ++c, b ^= 1) {
       u64 r0 = cuts[c], r1 = cuts[c + 1];
       u64 b0 = base_off(r0), nb = base_off(r1) - b0;
       u64 s0 = slot_off(r0), ns = slot_off(r1) - s0;
       cudaStream_t s = sp.s[b];
-      MZ_CUDA(cudaMemcpyAsync(d_bases[b]->p, bases + b0, nb, cudaMemcpyHostToDevice, s));
+      MZ_CUDA(cudaMemcpyAsync(d_bases[b], bases + b0, nb, cudaMemcpyHostToDevice, s));
       const u64* dro = nullptr;
       const u64* dko = nullptr;
       if (!uniform_read_len) {
-        MZ_CUDA(cudaMemcpyAsync(d_ro[b]->p, read_offsets + r0, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, s));
-        MZ_CUDA(cudaMemcpyAsync(d_ko[b]->p, koffs + r0, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, s));
-        dro = (const u64*)d_ro[b]->p;
-        dko = (const u64*)d_ko[b]->p;
+        MZ_CUDA(cudaMemcpyAsync(d_ro[b], read_offsets + r0, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, s));
+        MZ_CUDA(cudaMemcpyAsync(d_ko[b], koffs + r0, (r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, s));
+        dro = (const u64*)d_ro[b];
+        dko = (const u64*)d_ko[b];
       }
       // offsets uploaded are absolute: rebase the data pointers instead of the offset arrays
-      const u8* dbases = (const u8*)d_bases[b]->p - (uniform_read_len ? 0 : b0);
+      const u8* dbases = (const u8*)d_bases[b] - (uniform_read_len ? 0 : b0);
       void* dh = nullptr;
       if (out_hits && dev_out) dh = (char*)out_hits + (uniform_read_len ? s0 * rec : 0);
-      else if (out_hits) dh = (char*)d_hits[b]->p - (uniform_read_len ? 0 : s0 * rec);
-      launch_query_reads(idx, dbases, dro, r1 - r0, uniform_read_len, mode, dko, dh, compact, (u64*)d_counts.p, s);
-      if (out_hits && !dev_out && ns) MZ_CUDA(cudaMemcpyAsync((char*)out_hits + s0 * rec, d_hits[b]->p, ns * rec, cudaMemcpyDeviceToHost, s));
+      else if (out_hits) dh = (char*)d_hits[b] - (uniform_read_len ? 0 : s0 * rec);
+      launch_query_reads(idx, dbases, dro, r1 - r0, uniform_read_len, mode, dko, dh, compact, (u64*)d_counts, s);
+      if (out_hits && !dev_out && ns) MZ_CUDA(cudaMemcpyAsync((char*)out_hits + s0 * rec, d_hits[b], ns * rec, cudaMemcpyDeviceToHost, s));
     }
-    MZ_CUDA(cudaStreamSynchronize(sp.s[0]));
     MZ_CUDA(cudaStreamSynchronize(sp.s[1]));
-    if (counts) MZ_CUDA(cudaMemcpy(counts, d_counts.p, 24, cudaMemcpyDeviceToHost));
+    if (counts) MZ_CUDA(cudaMemcpyAsync(counts, d_counts, 24, cudaMemcpyDeviceToHost, sp.s[0]));
+    MZ_CUDA(cudaStreamSynchronize(sp.s[0]));
   });
 }
 
@@ -1212,19 +1256,21 @@ static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu
   const bool project = hits != nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   std::unique_ptr<StreamPair> sp;
-  std::unique_ptr<DevBuf> d_in, d_offs, d_out;
+  std::unique_ptr<PoolScratch> scratch;  // declared after `sp`: released before the streams go away
+  void *d_in = nullptr, *d_offs = nullptr, *d_out = nullptr;
   const u32* d_uids = uids;
   const Hit* d_hits = (const Hit*)hits;
   u64* d_offsets = out_offsets;
   if (mem == MAZU_MEM_HOST) {
     sp = std::make_unique<StreamPair>();
     s = sp->s[0];
-    d_in = std::make_unique<DevBuf>(n * (project ? 16 : 4) + 16, idx->device);
-    MZ_CUDA(cudaMemcpyAsync(d_in->p, project ? (const void*)hits : (const void*)uids, n * (project ? 16 : 4), cudaMemcpyHostToDevice, s));
-    d_uids = project ? nullptr : (const u32*)d_in->p;
-    d_hits = project ? (const Hit*)d_in->p : nullptr;
-    d_offs = std::make_unique<DevBuf>((n + 1) * 8, idx->device);
-    d_offsets = (u64*)d_offs->p;
+    scratch = std::make_unique<PoolScratch>(idx->pool, s);
+    d_in = scratch->get(n * (project ? 16 : 4) + 16);
+    MZ_CUDA(cudaMemcpyAsync(d_in, project ? (const void*)hits : (const void*)uids, n * (project ? 16 : 4), cudaMemcpyHostToDevice, s));
+    d_uids = project ? nullptr : (const u32*)d_in;
+    d_hits = project ? (const Hit*)d_in : nullptr;
+    d_offs = scratch->get((n + 1) * 8);
+    d_offsets = (u64*)d_offs;
   }
   void* lens = nullptr;
   MZ_CUDA(cudaMallocFromPoolAsync(&lens, (n + 1) * 8, idx->pool, s));
@@ -1253,8 +1299,8 @@ static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu
   }
   OccRec* d_o = (OccRec*)out;
   if (mem == MAZU_MEM_HOST) {
-    d_out = std::make_unique<DevBuf>(total * 12 + 16, idx->device);
-    d_o = (OccRec*)d_out->p;
+    d_out = scratch->get(total * 12 + 16);
+    d_o = (OccRec*)d_out;
   }
   if (n) {
     int grid = idx->sm_count * 8;  // tiles of the OUTPUT are grid-strided; the kernel reads the total from out_offsets[n]

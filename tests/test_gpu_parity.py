@@ -676,6 +676,22 @@ def test_error_codes():
     assert e.value.code == -7
 
 
+def test_scratch_pool_is_reused_and_released(yeast_sshash, yeast_queries):
+    """host-buffer calls stage through the handle's pool: results stay exact call after call, and release_scratch gives the memory back"""
+    g, o = yeast_sshash
+    _, ref_codes = yeast_queries
+    bases, offs = _gen.sample_reads(ref_codes, 4000, 150, seed=21, frac_ref=0.6, sub_rate=0.01, n_rate=0.0, ragged=False)
+    want, wcnt, _ = o.query_reads(bases, offs)
+    for _ in range(3):
+        got, cnt, _ = g.query_reads(bases, uniform_read_len=150)
+        assert_hits_equal(got, want, "repeat")
+        assert list(cnt) == list(wcnt)
+    assert g.release_scratch() > 0
+    assert g.release_scratch() == 0
+    got, cnt, _ = g.query_reads(bases, uniform_read_len=150)
+    assert_hits_equal(got, want, "after release")
+
+
 def test_concurrent_queries_on_one_handle(yeast_sshash, yeast_queries):
     """queries take &self and are Sync in the reference (src/kphf/mod.rs:69-72): one immutable handle, many host threads."""
     import threading
