@@ -713,25 +713,41 @@ void launch_k2u_batch(const mazu_index* ix, const u64* d_words, u64 n, Hit* d_ou
   MZ_CUDA(cudaGetLastError());
 }
 
+void device_exclusive_scan(const u64* d_in, u64* d_out, u64 n, cudaMemPool_t pool, cudaStream_t s);
+
 template <int MODE, int KIND, u32 FAMILY, int OCC>
 void launch_qr_occ(const mazu_index* ix, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, const u64* d_kmer_offsets,
-                   void* d_out, u32 compact, u64* d_counts, cudaStream_t s) {
+                   void* d_out, u32 compact, u64* d_counts, const u64* d_seg_offsets, cudaStream_t s) {
   auto kern = query_reads_kernel<MODE, KIND, FAMILY, OCC>;
-  int grid = grid_for(kern, QR_WARPS * 32, ix, QR_WARPS, n_reads);
+  // with a segment table the number of work items is only known on the device: launch every resident CTA, idle warps leave at once
+  int grid = grid_for(kern, QR_WARPS * 32, ix, QR_WARPS, d_seg_offsets ? ~0ULL >> 8 : n_reads);
   kern<<<grid, QR_WARPS * 32, 0, s>>>(ix->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact,
-                                      (unsigned long long*)d_counts);
+                                      (unsigned long long*)d_counts, d_seg_offsets);
 }
 template <int MODE, int KIND, u32 FAMILY>
 void launch_qr(const mazu_index* ix, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, const u64* d_kmer_offsets,
                void* d_out, u32 compact, u64* d_counts, cudaStream_t s) {
   // streaming walk: 3 resident CTAs (80 registers) while the index sits in the 126 MB L2, 4 (64 registers) once it does not
   if constexpr (MODE == 1) {
-    if (ix->device_bytes() <= (96ull << 20)) {
-      launch_qr_occ<MODE, KIND, FAMILY, 3>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, s);
-      return;
+    if (ix->device_bytes() <= (96ull << 20))
+      launch_qr_occ<MODE, KIND, FAMILY, 3>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, nullptr, s);
+    else
+      launch_qr_occ<MODE, KIND, FAMILY, 4>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, nullptr, s);
+  } else {
+    // ragged batches: per-read work-item counts -> scan; the kernel cuts long reads into segments (kernels.cuh, QR_SEGMENT)
+    void *cnt = nullptr, *seg = nullptr;
+    if (!uniform_len) {
+      MZ_CUDA(cudaMallocFromPoolAsync(&cnt, (n_reads + 1) * 8, ix->pool, s));
+      MZ_CUDA(cudaMallocFromPoolAsync(&seg, (n_reads + 1) * 8, ix->pool, s));
+      MZ_CUDA(cudaMemsetAsync(cnt, 0, (n_reads + 1) * 8, s));
+      segment_counts_kernel<<<(int)std::min<u64>((n_reads + 255) / 256, 4096), 256, 0, s>>>(d_read_offsets, n_reads, ix->unitigs->k, (u64*)cnt);
+      MZ_CUDA(cudaGetLastError());
+      device_exclusive_scan((const u64*)cnt, (u64*)seg, n_reads, ix->pool, s);
     }
+    launch_qr_occ<MODE, KIND, FAMILY, 0>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, (const u64*)seg, s);
+    if (cnt) MZ_CUDA(cudaFreeAsync(cnt, s));
+    if (seg) MZ_CUDA(cudaFreeAsync(seg, s));
   }
-  launch_qr_occ<MODE, KIND, FAMILY, MODE == 1 ? 4 : 0>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, s);
 }
 
 void launch_query_reads(const mazu_index* ix, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, int mode,

@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256) k2u_batch_kernel(const __grid_constant__ 
 static const int QR_WARPS = 8;    // warps per CTA
 static const int QR_CHUNK = 128;  // k-mer start positions per chunk
 static const int QR_BASES = 160;  // bases staged per chunk (CHUNK + k - 1 <= 159)
+static const u64 QR_SEGMENT = 2048;  // k-mer positions per work item when a long read is cut up (a multiple of QR_CHUNK)
 static const u32 BN_SKEW = 0xFFFFFFFFu;
 
 struct WarpStage {
@@ -445,7 +446,7 @@ template <int MODE, int KIND, u32 FAMILY, int OCC>
 __global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
                                                                     const u64* __restrict__ read_offsets, u64 n_reads, u64 uniform_len,
                                                                     const u64* __restrict__ kmer_offsets, void* __restrict__ out, u32 compact,
-                                                                    unsigned long long* __restrict__ counts) {
+                                                                    unsigned long long* __restrict__ counts, const u64* __restrict__ seg_offsets) {
   __shared__ WarpStage s_stage[QR_WARPS];
   const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   WarpStage& S = s_stage[wib];
@@ -453,8 +454,25 @@ __global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const _
   constexpr bool SS = KIND == MAZU_K2U_SSHASH;
   u32 n_valid = 0, n_hit = 0;
   const u32 lt_mask = (1u << lane) - 1u;
+  // Work items.  Normally one per read.  Random-access lookups of one read are independent, so ragged batches that
+  // contain LONG reads (a chromosome through validate_fasta, nanopore reads) are cut into segments of QR_SEGMENT k-mer
+  // positions: seg_offsets[r] = first item of read r, seg_offsets[n_reads] = number of items; when that equals n_reads
+  // no read is long and item == read.  The streaming walk is sequential per read and never segments.
+  const u64 n_items = (MODE == 0 && seg_offsets) ? seg_offsets[n_reads] : n_reads;
+  const bool segmented = n_items != n_reads;
 
-  for (u64 r = (u64)blockIdx.x * QR_WARPS + wib; r < n_reads; r += (u64)gridDim.x * QR_WARPS) {
+  for (u64 item = (u64)blockIdx.x * QR_WARPS + wib; item < n_items; item += (u64)gridDim.x * QR_WARPS) {
+    u64 r = item, c_begin = 0, c_end = ~0ULL;
+    if (MODE == 0 && segmented) {
+      u64 lo = 0, hi = n_reads;  // largest r with seg_offsets[r] <= item
+      while (hi - lo > 1) {
+        u64 mid = (lo + hi) >> 1;
+        if (seg_offsets[mid] <= item) lo = mid; else hi = mid;
+      }
+      r = lo;
+      c_begin = (item - seg_offsets[r]) * QR_SEGMENT;
+      c_end = c_begin + QR_SEGMENT;
+    }
     u64 beg, len, slot0;
     if (uniform_len) {
       beg = r * uniform_len;
@@ -473,10 +491,11 @@ __global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const _
     st.o = NO_MATCH;
     st.ustart = 0;
 
+    const u64 c_stop = min(nk, c_end);
 #pragma unroll 1
-    for (u64 c0 = 0; c0 < nk; c0 += QR_CHUNK) {
+    for (u64 c0 = c_begin; c0 < c_stop; c0 += QR_CHUNK) {
       ChunkInfo ci;
-      const u32 n_c = (u32)min((u64)QR_CHUNK, nk - c0);
+      const u32 n_c = (u32)min((u64)QR_CHUNK, c_stop - c0);
       __syncwarp();
       stage_encode(seq, len, c0, n_c, k, lane, S, ci);
       __syncwarp();
@@ -669,6 +688,14 @@ __global__ void __launch_bounds__(QR_WARPS * 32) encode_reads_kernel(const __gri
 }
 
 // per-read k-mer slot counts (input of the exclusive scan that yields kmer_offsets)
+// per-read work items of the random-access kernel: ceil(k-mer slots / QR_SEGMENT), at least one
+__global__ void segment_counts_kernel(const u64* __restrict__ read_offsets, u64 n_reads, u32 k, u64* __restrict__ counts) {
+  for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (u64)gridDim.x * blockDim.x) {
+    u64 len = read_offsets[r + 1] - read_offsets[r];
+    u64 nk = len >= k ? len - k + 1 : 0;
+    counts[r] = nk <= QR_SEGMENT ? 1 : (nk + QR_SEGMENT - 1) / QR_SEGMENT;
+  }
+}
 __global__ void kmer_counts_kernel(const u64* __restrict__ read_offsets, u64 n_reads, u32 k, u64* __restrict__ counts) {
   for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (u64)gridDim.x * blockDim.x) {
     u64 len = read_offsets[r + 1] - read_offsets[r];

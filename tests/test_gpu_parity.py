@@ -349,6 +349,47 @@ def test_query_reads_host_in_device_out(yeast_sshash, yeast_queries, ragged):
     assert e.value.code == -7
 
 
+@pytest.mark.parametrize("which", ["dense", "sshash"])
+def test_long_reads_are_cut_into_segments(yeast_dense, yeast_sshash, yeast_queries, which):
+    """Random-access lookups of one read are independent: the kernel cuts reads longer than 2048 k-mer positions into
+    segments handled by different warps.  Lengths around the segment boundary, mixed with short and empty reads; the
+    streaming walk (sequential per read, never segmented) must agree with its own oracle on the same batch."""
+    g, o = yeast_dense if which == "dense" else yeast_sshash
+    _, ref_codes = yeast_queries
+    k = g.k
+    rng = np.random.default_rng(77)
+    lens = [0, k - 1, k, 150, 2047 + k, 2048 + k - 1, 2048 + k, 4096 + k - 1, 4097 + k - 1, 30000, 150, 7, 100000, 2048 * 3 + k - 1, 151]
+    parts, offs = [], [0]
+    for i, ln in enumerate(lens):
+        if i % 3 == 2 or ln > len(ref_codes):
+            codes = rng.integers(0, 4, size=ln, dtype=np.uint8)
+        else:
+            s0 = int(rng.integers(0, len(ref_codes) - ln + 1))
+            codes = ref_codes[s0:s0 + ln].copy()
+            if i % 2:
+                codes = _gen.COMP[codes[::-1]]
+        m = rng.random(ln) < 0.003
+        codes[m] = (codes[m] + 1) & 3
+        b = _gen.ACGT[codes].copy()
+        b[rng.random(ln) < 0.0005] = ord("N")
+        parts.append(b)
+        offs.append(offs[-1] + ln)
+    bases = np.concatenate(parts)
+    offs = np.array(offs, dtype=np.uint64)
+    for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+        _check_reads(g, o, bases, offs, mode)
+    # device-pointer mode goes through the same segment table
+    import torch
+    want, wcnt, wk = o.query_reads(bases, offs, streaming=False)
+    d_hits = torch.zeros((len(want), 4), dtype=torch.int32, device="cuda")
+    d_cnt = torch.zeros(3, dtype=torch.int64, device="cuda")
+    g.query_reads(torch.from_numpy(bases).cuda(), torch.from_numpy(offs.view(np.int64)).cuda(), n_reads=len(offs) - 1, out_hits=d_hits,
+                  counts=d_cnt, mem=mz.MEM_DEVICE, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert_hits_equal(d_hits.cpu().numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE), want, "segmented, device mode")
+    assert list(d_cnt.cpu().numpy()) == list(wcnt.astype(np.int64))
+
+
 def test_streaming_exact_with_duplicate_kmers():
     """A unitig set whose canonical k-mers are NOT unique (not a valid cdBG): random-access and
     streaming answers differ there, and the GPU walk must reproduce the reference's sequential
