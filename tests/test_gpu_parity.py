@@ -584,6 +584,68 @@ def test_synthetic_index_properties():
     assert_hits_equal(hr[:120 * 3000], want, "sampled oracle comparison")
 
 
+def test_full_size_config2_properties(yeast_sshash, yeast_queries):
+    """BASELINE.json configs[1]/[2] at FULL size (10 M reads x 150 bp = 1.2e9 lookups, far more than the oracle can
+    replay in a test): size-independent properties instead.  (1) counters add up; (2) every k-mer of an error-free
+    reference read hits and no k-mer of a uniform-random read does, so n_hit is known exactly from the generator;
+    (3) the streaming walk equals random access on an index with unique canonical k-mers; (4) every hit of a sampled
+    slice verifies against the unitig sequence; (5) the slice equals the oracle."""
+    import torch
+    g, o = yeast_sshash
+    _, ref_codes = yeast_queries
+    k, L, n = g.k, 150, 10_000_000
+    nk = L - k + 1
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4242)
+    ref_t = torch.from_numpy(ref_codes.astype(np.uint8)).to(dev)
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    ar = torch.arange(L, device=dev)
+    bases = torch.empty(n * L, dtype=torch.uint8, device=dev)
+    n_ref = 0
+    for r0 in range(0, n, 1_000_000):
+        m = min(1_000_000, n - r0)
+        starts = torch.randint(0, len(ref_codes) - L + 1, (m,), generator=gen, device=dev)
+        codes = ref_t[starts[:, None] + ar[None, :]]
+        strand = torch.rand(m, generator=gen, device=dev) < 0.5
+        codes = torch.where(strand[:, None], 3 - codes.flip(1), codes)
+        is_ref = torch.rand(m, generator=gen, device=dev) < 0.5
+        rnd = torch.randint(0, 4, (m, L), generator=gen, device=dev, dtype=torch.uint8)
+        codes = torch.where(is_ref[:, None], codes, rnd)
+        n_ref += int(is_ref.sum().item())
+        bases[r0 * L:(r0 + m) * L] = acgt[codes.long()].reshape(-1)
+    st = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+        hits = torch.empty((n * nk, 4), dtype=torch.int32, device=dev)
+        cnt = torch.zeros(3, dtype=torch.int64, device=dev)
+        g.query_reads(bases, None, n_reads=n, uniform_read_len=L, mode=mode, out_hits=hits, counts=cnt, mem=mz.MEM_DEVICE, stream=st)
+        torch.cuda.synchronize()
+        c = cnt.cpu().numpy()
+        assert c[0] == n * nk and c[1] + c[2] == c[0]                     # (1)
+        assert c[1] == n_ref * nk                                          # (2)
+        res[mode] = hits
+    assert torch.equal(res[mz.MODE_RANDOM], res[mz.MODE_STREAMING])        # (3)
+    hits = res[mz.MODE_RANDOM]
+    assert int((hits[:, 3] == mz.IDENTITY_MATCH).sum().item() + (hits[:, 3] == mz.TWIN_MATCH).sum().item()) == n_ref * nk
+    # (4) + (5) on the last 20,000 reads
+    m = 20000
+    h = hits[(n - m) * nk:].cpu().numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE)
+    b = bases[(n - m) * L:].cpu().numpy()
+    want, _, _ = o.query_reads(b, np.arange(m + 1, dtype=np.uint64) * L)
+    assert_hits_equal(h, want, "tail slice of the full-size batch")
+    lut = np.zeros(256, dtype=np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        lut[ch] = i
+    rk = _gen.kmer_words_from_codes(lut[b], k)
+    useq_codes = _gen.unpack_2bit(o.useq_words(), o.total_len)
+    uk = _gen.kmer_words_from_codes(useq_codes, k)
+    accum = np.array([0] + list(np.cumsum([g.unitig_len(u) for u in range(g.n_unitigs)])), dtype=np.uint64)
+    slot = np.nonzero(h["match"] == mz.IDENTITY_MATCH)[0]
+    fw = rk[(slot // nk) * L + (slot % nk)]
+    assert len(slot) > 0 and np.array_equal(uk[(accum[h["unitig_id"][slot].astype(np.int64)] + h["pos"][slot]).astype(np.int64)], fw)
+
+
 # --------------------------------------------------------------------------------------------
 # other k / w, including the maximum k = 32 (even k: palindromic k-mers have fw == rc)
 # --------------------------------------------------------------------------------------------
