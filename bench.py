@@ -665,7 +665,9 @@ def main():
         "kernel": kernel_name,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_source, "algorithmic_bytes_per_unit": alg, "units_per_launch": n_units, "kernel_ms": kernel_ms,
-                     "step_ms": [round(x, 3) for x in step_ms], "note": note},
+                     "step_ms": [round(x, 3) for x in step_ms], "note": note,
+                     # what the kernel is actually limited by (ncu, profiles/*.summary.txt): measured DRAM bytes / time against the same peak
+                     "dram_frac_measured": (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if (traffic and peak_kind == "hbm") else None},
         "parity_spot_check": parity_ok,
     }
     line.update(info)
