@@ -139,5 +139,7 @@ extern "C" {
     pub fn mazu_b200_iter_unitigs_on_ref(idx: *const mazu_index_t, ref_id: u64, out: *mut mazu_hit_t, cap: u64, n_out: *mut u64) -> mazu_status_t;
     pub fn mazu_b200_validate_self(idx: *const mazu_index_t, counts: *mut u64) -> mazu_status_t;
     pub fn mazu_b200_k2u_validate_self(idx: *const mazu_index_t, counts: *mut u64) -> mazu_status_t;
+    pub fn mazu_b200_alloc_pinned(bytes: u64, out: *mut *mut c_void) -> mazu_status_t;
+    pub fn mazu_b200_free_pinned(p: *mut c_void);
     pub fn mazu_b200_measure_random_gather(table_bytes: u64, n_gathers: u64, iters: i32, device: i32, sectors_per_s: *mut f64) -> mazu_status_t;
 }

@@ -250,6 +250,15 @@ mazu_status_t mazu_b200_validate_self(const mazu_index_t* idx, uint64_t counts[5
 mazu_status_t mazu_b200_k2u_validate_self(const mazu_index_t* idx, uint64_t counts[5]);
 
 /* ---------------------------------------------------------------------------------------------
+ * Page-locked host memory for MAZU_MEM_HOST callers that do not link the CUDA runtime themselves (a Rust
+ * Vec is pageable: copies from / to it are staged by the driver, synchronously, and the H2D / kernel / D2H
+ * overlap of the host path is lost -- results are identical, throughput is not).  Buffers obtained here
+ * are pinned and portable across devices.
+ * ------------------------------------------------------------------------------------------- */
+mazu_status_t mazu_b200_alloc_pinned(uint64_t bytes, void** out);
+void mazu_b200_free_pinned(void* p);
+
+/* ---------------------------------------------------------------------------------------------
  * Measurement helper: independent random 32-byte gathers over a table (the P_rand denominator of
  * DESIGN.md / BASELINE.md section 2).  table_bytes of device memory are allocated internally.
  * Returns achieved sectors per second in *sectors_per_s.

@@ -48,6 +48,28 @@ ERR_NO_REFSEQ = -9
  INFO_DEVICE, INFO_SAMPLE_SIZE, INFO_EXTENSION_SIZE) = range(17)
 
 
+class PinnedArray:
+    """numpy view of page-locked host memory from mazu_b200_alloc_pinned (freed with the object)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * self.dtype.itemsize
+        p = C.c_void_p(0)
+        _check(lib().mazu_b200_alloc_pinned(n, C.byref(p)))
+        self._p = p.value
+        buf = (C.c_uint8 * max(n, 1)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_p", None):
+                self.array = None
+                lib().mazu_b200_free_pinned(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
 class MazuError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("[%d] %s" % (code, msg))
@@ -95,6 +117,8 @@ def _signatures():
         "mazu_b200_index_attach_refseq": (i32, [vp, vp, vp, u64]),
         "mazu_b200_index_destroy": (None, [vp]),
         "mazu_b200_index_release_scratch": (i32, [vp, vp]),
+        "mazu_b200_alloc_pinned": (i32, [u64, vp]),
+        "mazu_b200_free_pinned": (None, [vp]),
         "mazu_b200_index_info": (u64, [vp, i32]),
         "mazu_b200_unitig_len": (i32, [vp, u64, vp, vp]),
         "mazu_b200_k2u_batch": (i32, [vp, vp, u64, u32, vp, i32, vp]),

@@ -1005,6 +1005,17 @@ mazu_status_t mazu_b200_index_attach_refseq(mazu_index_t* idx, const uint64_t* s
 
 void mazu_b200_index_destroy(mazu_index_t* idx) { delete idx; }
 
+mazu_status_t mazu_b200_alloc_pinned(uint64_t bytes, void** out) {
+  return guarded([&] {
+    if (!out) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    MZ_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  });
+}
+void mazu_b200_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 mazu_status_t mazu_b200_index_release_scratch(mazu_index_t* idx, uint64_t* released) {
   return guarded([&] {
     if (!idx) throw Error(MAZU_ERR_INVALID_ARG, "null argument");

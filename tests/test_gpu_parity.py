@@ -779,6 +779,21 @@ def test_error_codes():
     assert e.value.code == -7
 
 
+def test_pinned_host_buffers(yeast_sshash, yeast_queries):
+    """mazu_b200_alloc_pinned: page-locked buffers for callers that do not link CUDA; same answers as pageable numpy arrays"""
+    g, o = yeast_sshash
+    _, ref_codes = yeast_queries
+    bases, offs = _gen.sample_reads(ref_codes, 3000, 150, seed=31, frac_ref=0.6, sub_rate=0.01, n_rate=0.001, ragged=False)
+    want, wcnt, _ = o.query_reads(bases, offs)
+    pb = mz.PinnedArray(bases.shape, np.uint8)
+    pb.array[:] = bases
+    ph = mz.PinnedArray((len(want),), mz.HIT_DTYPE)
+    got, cnt, _ = g.query_reads(pb.array, uniform_read_len=150, out_hits=ph.array)
+    assert got is ph.array
+    assert_hits_equal(ph.array, want, "pinned buffers")
+    assert list(cnt) == list(wcnt)
+
+
 def test_scratch_pool_is_reused_and_released(yeast_sshash, yeast_queries):
     """host-buffer calls stage through the handle's pool: results stay exact call after call, and release_scratch gives the memory back"""
     g, o = yeast_sshash
