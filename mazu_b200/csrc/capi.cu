@@ -235,7 +235,7 @@ void upload_u2pos(mazu_index& ix) {
   if (!ix.u2pos || ix.u2pos->kind == MAZU_U2POS_NONE) return;
   if (!ix.d_u2pos) {
     auto d = std::make_shared<U2PosDev>();
-    auto b = upload(ix.u2pos->ctable_words, ix.device, 2);
+    auto b = upload(ix.u2pos->ctable_words, ix.device, 4);
     d->bufs.push_back(b);
     d->bytes += b->bytes;
     upload_packed(ix.u2pos->contig_offsets, ix.device, d->bufs, d->bytes);

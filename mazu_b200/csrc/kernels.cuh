@@ -778,7 +778,9 @@ __device__ __forceinline__ u64 warp_last_le(const u64* __restrict__ off, u64 n, 
 // occurrence words and write consecutive 12-byte records.
 static const u64 OCC_TILE = 1024;
 template <bool PROJECT>
-__global__ void __launch_bounds__(256) occ_fill_kernel(const __grid_constant__ IndexView ix, const u32* __restrict__ uids,
+// (256, 1): ptxas takes ~51 registers and keeps a lane's four packed-word loads in flight; forcing 6 or 8 resident CTAs
+// (40 / 32 registers, spills) measured 5 % / 18 % slower
+__global__ void __launch_bounds__(256, 1) occ_fill_kernel(const __grid_constant__ IndexView ix, const u32* __restrict__ uids,
                                                        const Hit* __restrict__ hits, u64 n, const u64* __restrict__ out_offsets,
                                                        OccRec* __restrict__ out) {
   const u32 lane = threadIdx.x & 31;
@@ -817,10 +819,30 @@ __global__ void __launch_bounds__(256) occ_fill_kernel(const __grid_constant__ I
         }
         for (u64 base = body_b + 4 * lane; base < body_e; base += 128) {
           OccRec o[4];
+          if (ix.u2pos_kind == MAZU_U2POS_PISCEM && ix.ctable_width <= 48) {
+            // four consecutive packed fields span at most 4 words (4 * 48 + 63 < 256 bits): 4 loads instead of 8
+            const u32 wd = ix.ctable_width;
+            const u64 bit0 = (e0 + base) * wd, wi = bit0 >> 6;
+            const u64 w0 = __ldg(ix.ctable_words + wi), w1 = __ldg(ix.ctable_words + wi + 1), w2 = __ldg(ix.ctable_words + wi + 2),
+                      w3 = __ldg(ix.ctable_words + wi + 3);
+            const u64 fmask = (1ULL << wd) - 1ULL;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            o[j] = occ_decode(ix, e0 + base + j);
-            if (PROJECT) o[j] = project_occ(k, h, o[j]);
+            for (int j = 0; j < 4; ++j) {
+              const u32 b = (u32)(bit0 & 63) + (u32)j * wd;  // < 64 + 3 * 48 = 208
+              const u32 q = b >> 6, sh = b & 63u;
+              const u64 lo = q == 0 ? w0 : (q == 1 ? w1 : (q == 2 ? w2 : w3)), hi = q == 0 ? w1 : (q == 1 ? w2 : w3);
+              const u64 enc = (sh ? (lo >> sh) | (hi << (64 - sh)) : lo) & fmask;
+              o[j].ref_id = (u32)(enc >> ix.ref_shift);
+              o[j].pos = (u32)((enc >> 1) & ix.pos_mask);
+              o[j].fw = (u32)(enc & 1ULL);
+              if (PROJECT) o[j] = project_occ(k, h, o[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              o[j] = occ_decode(ix, e0 + base + j);
+              if (PROJECT) o[j] = project_occ(k, h, o[j]);
+            }
           }
           uint4* dst = reinterpret_cast<uint4*>(out + base);
           dst[0] = make_uint4(o[0].ref_id, o[0].pos, o[0].fw, o[1].ref_id);
