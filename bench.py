@@ -517,6 +517,47 @@ def main():
             mz._check(mz.lib().mazu_b200_decode_occs(index._h, mz._any_ptr(d_q), n_q, mz._any_ptr(d_offs), mz._any_ptr(d_out), total, None,
                                                      mz.MEM_DEVICE, mz._any_ptr(stream.cuda_stream)))
 
+        # the projected variant (GetRefPos::project_hits, src/index.rs:156-216): one hit record per query with a random position /
+        # orientation on its unitig; measured after the main loop and reported as `projected`
+        h_np = np.zeros(n_q, dtype=mz.HIT_DTYPE)
+        h_np["unitig_id"] = qids
+        h_np["unitig_len"] = 4096
+        h_np["pos"] = rng.integers(0, 4096 - k + 1, size=n_q)
+        h_np["match"] = rng.integers(1, 3, size=n_q)
+        d_hits_q = torch.from_numpy(h_np.view(np.uint32).reshape(-1, 4).view(np.int32)).to(dev)
+
+        def project_step():
+            mz._check(mz.lib().mazu_b200_project_hits(index._h, mz._any_ptr(d_hits_q), n_q, mz._any_ptr(d_offs), mz._any_ptr(d_out), total, None,
+                                                      mz.MEM_DEVICE, mz._any_ptr(stream.cuda_stream)))
+
+        def projected_line():
+            for _ in range(3):
+                project_step()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(args.steps):
+                project_step()
+            b.record(stream)
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / args.steps
+            # spot check against project_onto_u_occ on the host
+            offs_h = d_offs[:2001].cpu().numpy().view(np.uint64)
+            out_h = d_out[: int(offs_h[-1])].cpu().numpy().view(np.uint32)
+            ok = True
+            for q in range(0, 2000, 97):
+                e = int(offsets[qids[q]])
+                fwd = bool(fws[e])
+                want_pos = int(h_np["pos"][q]) + int(poss[e]) if fwd else int(poss[e]) + (4096 - int(h_np["pos"][q])) - k
+                o = 1 if h_np["match"][q] == 1 else 0
+                want_o = o if fwd else o ^ 1
+                r = out_h[int(offs_h[q])]
+                ok &= (int(r[0]) == int(ref_ids[e])) and (int(r[1]) == want_pos % (1 << 32)) and (int(r[2]) == want_o)
+            return {"value": total / (ms * 1e-3), "unit": unit, "ms_per_step": ms, "frac_of_hbm_peak": total * (alg + 16.0 * n_q / total) / (ms * 1e-3) / 1e9 / 6553.9,
+                    "parity_spot_check": bool(ok), "kernel": "mazu::occ_fill_kernel<true>"}
+
+        info["projected_fn"] = projected_line
+
         def check():
             n_chk = min(n_q, 20000)
             offs_h = d_offs[: n_chk + 1].cpu().numpy().view(np.uint64)
@@ -621,6 +662,8 @@ def main():
         return
 
     parity_ok = bool(check()) if check else None
+    if "projected_fn" in info:
+        info["projected"] = info.pop("projected_fn")()
     if args.validate and W.startswith("config5"):
         c = index.k2u_validate_self()
         info["k2u_validate_self"] = {"n_queries": c[0], "n_identity": c[1], "n_twin": c[2], "n_fail": c[4], "n_fail_not_found": c[3],
