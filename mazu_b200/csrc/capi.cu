@@ -1,658 +1,10 @@
 // extern "C" surface of libmazu_b200.so (include/mazu_b200.h): index upload, kernel launches, and the
 // chunked host<->device pipelines behind MAZU_MEM_HOST calls.  There is no CPU fallback: every query
 // entry point launches the CUDA kernels of kernels.cuh or fails with MAZU_ERR_CUDA.
-#include <cub/device/device_scan.cuh>
-
-#include <functional>
-#include <mutex>
-
-#include "formats.hpp"
-#include "kernels.cuh"
-
-using namespace mazu;
+#include "device_index.cuh"
+#include "gpu_build_driver.cuh"
 
 namespace {
-
-thread_local std::string g_err;
-
-#define MZ_CUDA(expr)                                                                                                   \
-  do {                                                                                                                  \
-    cudaError_t _e = (expr);                                                                                            \
-    if (_e != cudaSuccess) throw Error(MAZU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));              \
-  } while (0)
-
-template <class F>
-mazu_status_t guarded(F&& f) {
-  try {
-    f();
-    return MAZU_OK;
-  } catch (const Error& e) {
-    g_err = e.what();
-    return e.code;
-  } catch (const std::bad_alloc&) {
-    g_err = "out of host memory";
-    return MAZU_ERR_OTHER;
-  } catch (const std::exception& e) {
-    g_err = e.what();
-    return MAZU_ERR_OTHER;
-  }
-}
-
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    MZ_CUDA(cudaSetDevice(dev));
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  int device = 0;
-  DevBuf(size_t n, int dev) : bytes(n), device(dev) { MZ_CUDA(cudaMalloc(&p, n ? n : 1)); }
-  ~DevBuf() {
-    int prev = -1;
-    cudaGetDevice(&prev);
-    cudaSetDevice(device);
-    cudaFree(p);
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-  DevBuf(const DevBuf&) = delete;
-  DevBuf& operator=(const DevBuf&) = delete;
-};
-using DevBufP = std::shared_ptr<DevBuf>;
-
-template <class T>
-DevBufP upload(const T* host, size_t n, int dev, size_t pad_elems = 0) {
-  auto b = std::make_shared<DevBuf>((n + pad_elems) * sizeof(T), dev);
-  if (pad_elems) MZ_CUDA(cudaMemset(b->p, 0, (n + pad_elems) * sizeof(T)));
-  if (n) MZ_CUDA(cudaMemcpy(b->p, host, n * sizeof(T), cudaMemcpyHostToDevice));
-  return b;
-}
-template <class T>
-DevBufP upload(const std::vector<T>& v, int dev, size_t pad_elems = 0) {
-  return upload(v.data(), v.size(), dev, pad_elems);
-}
-
-// a group of device buffers + the view fields they back; groups are shared between handles
-// created by rebuild_k2u (the reference clones u2pos / refs there; they are immutable so we share)
-struct UnitigsDev {
-  std::vector<DevBufP> bufs;
-  UnitigsView view{};
-  size_t bytes = 0;
-};
-struct K2UDev {
-  std::vector<DevBufP> bufs;
-  size_t bytes = 0;
-};
-struct U2PosDev {
-  std::vector<DevBufP> bufs;
-  size_t bytes = 0;
-};
-struct RefsDev {
-  std::vector<DevBufP> bufs;
-  size_t bytes = 0;
-};
-
-}  // namespace
-
-struct mazu_index {
-  int device = 0;
-  int sm_count = 148;
-  std::shared_ptr<const UnitigSetHost> unitigs;
-  std::shared_ptr<K2UHost> k2u;
-  std::shared_ptr<U2PosHost> u2pos;
-  std::shared_ptr<RefSeqHost> refs;
-  std::shared_ptr<UnitigsDev> d_unitigs;
-  std::shared_ptr<K2UDev> d_k2u;
-  std::shared_ptr<U2PosDev> d_u2pos;
-  std::shared_ptr<RefsDev> d_refs;
-  IndexView view{};
-  // named device tables (pointer, logical bytes) for mazu_b200_debug_table_digest: lets a test compare the
-  // host-built and the GPU-built index table by table
-  std::function<void(mazu_index&)> gpu_builder;  // set when the K2U tables are to be built on the device
-  std::vector<std::pair<const void*, u64>> tables = std::vector<std::pair<const void*, u64>>(8, {nullptr, 0});
-  // per-handle stream-ordered pool for per-call scratch (scan temporaries, list lengths).  It keeps what it has freed
-  // (release threshold = max), so a call after a synchronisation does not pay for fresh physical memory again
-  // (measured: 1.5-4 ms on the first decode call after every sync with the default pool's threshold of 0).
-  cudaMemPool_t pool = nullptr;
-  ~mazu_index() {
-    if (pool) cudaMemPoolDestroy(pool);
-  }
-  u64 device_bytes() const {
-    return (d_unitigs ? d_unitigs->bytes : 0) + (d_k2u ? d_k2u->bytes : 0) + (d_u2pos ? d_u2pos->bytes : 0) + (d_refs ? d_refs->bytes : 0);
-  }
-};
-
-namespace {
-
-static const u32 DIR_SHIFT = 6;  // one directory entry per 64 bases
-
-std::shared_ptr<UnitigsDev> upload_unitigs(const UnitigSetHost& us, int dev) {
-  auto d = std::make_shared<UnitigsDev>();
-  const u64 L = us.total_len(), U = us.n_unitigs();
-  if (U >> 32) throw Error(MAZU_ERR_INVALID_ARG, "more than 2^32 unitigs");
-  u64 nw = (2 * L + 63) / 64;
-  auto b_seq = upload(us.useq.data(), std::min<u64>(nw, us.useq.size()), dev, 4);
-  // directory: unitig containing the first base of every 2^DIR_SHIFT block
-  u64 nd = (L >> DIR_SHIFT) + 2;
-  std::vector<u32> dir(nd, (u32)(U ? U - 1 : 0));
-  {
-    u64 ui = 0;
-    for (u64 b = 0; b < nd; ++b) {
-      u64 p = b << DIR_SHIFT;
-      if (p >= L) break;
-      while (us.accum[ui + 1] <= p) ++ui;
-      dir[b] = (u32)ui;
-    }
-  }
-  auto b_dir = upload(dir, dev);
-  auto b_starts = upload(us.accum, dev, 4);
-  d->bufs = {b_seq, b_dir, b_starts};
-  d->bytes = b_seq->bytes + b_dir->bytes + b_starts->bytes;
-  d->view.useq = (const u64*)b_seq->p;
-  d->view.dir = (const u32*)b_dir->p;
-  d->view.starts = (const u64*)b_starts->p;
-  d->view.total_len = L;
-  d->view.n_unitigs = U;
-  d->view.k = us.k;
-  d->view.dir_shift = DIR_SHIFT;
-  return d;
-}
-
-RankedLevels upload_mphf(const MphfHost& m, int dev, K2UDev& d) {
-  RankedLevels v = m.view();
-  auto b = upload(m.blocks, dev, 8);
-  auto fk = upload(m.fb_keys, dev), fv = upload(m.fb_vals, dev);
-  d.bufs.insert(d.bufs.end(), {b, fk, fv});
-  d.bytes += b->bytes + fk->bytes + fv->bytes;
-  v.blocks = (const u32*)b->p;
-  v.fb_keys = (const u64*)fk->p;
-  v.fb_vals = (const u64*)fv->p;
-  return v;
-}
-PackedVecView upload_packed(const PackedVec& pv, int dev, std::vector<DevBufP>& bufs, size_t& bytes) {
-  auto b = upload(pv.words, dev, 2);
-  bufs.push_back(b);
-  bytes += b->bytes;
-  return PackedVecView{(const u64*)b->p, pv.len, (u32)pv.width, 0};
-}
-
-void upload_k2u(mazu_index& ix) {
-  auto d = std::make_shared<K2UDev>();
-  const K2UHost& h = *ix.k2u;
-  IndexView& v = ix.view;
-  v.k2u_kind = (u32)h.kind;
-  v.mphf = upload_mphf(h.mphf, ix.device, *d);
-  v.pos = upload_packed(h.pos, ix.device, d->bufs, d->bytes);
-  v.w = h.w;
-  v.seed = h.seed;
-  v.skew_param = h.skew_param;
-  v.has_skew = h.has_skew ? 1u : 0u;
-  if (h.kind == MAZU_K2U_SSHASH) {
-    auto bb = upload(h.sizes.blocks, ix.device, 8);
-    auto be = upload(h.sizes.exceptions, ix.device);
-    d->bufs.insert(d->bufs.end(), {bb, be});
-    d->bytes += bb->bytes + be->bytes;
-    v.sizes = BlockedEFView{(const u64*)bb->p, (const u64*)be->p, h.sizes.n, h.sizes.l, h.sizes.log_s, h.sizes.wpb, 0};
-    if (h.has_skew) {
-      v.skew_mphf = upload_mphf(h.skew_mphf, ix.device, *d);
-      v.skew_pos = upload_packed(h.skew_pos, ix.device, d->bufs, d->bytes);
-    }
-  }
-  if (h.kind == MAZU_K2U_SAMPLED_PFHASH) {
-    v.sampled = upload_mphf(h.sampled, ix.device, *d);
-    auto bc = upload(h.canonical_bits, ix.device, 2), bd = upload(h.direction_bits, ix.device, 2);
-    d->bufs.insert(d->bufs.end(), {bc, bd});
-    d->bytes += bc->bytes + bd->bytes;
-    v.canonical_bits = (const u64*)bc->p;
-    v.direction_bits = (const u64*)bd->p;
-    v.ext_sizes = upload_packed(h.ext_sizes, ix.device, d->bufs, d->bytes);
-    v.ext_bases = upload_packed(h.ext_bases, ix.device, d->bufs, d->bytes);
-    v.extension_size = (u32)h.extension_size;
-  }
-  ix.d_k2u = d;
-  auto packed_bytes = [](const PackedVec& pv) { return ((pv.len * pv.width + 63) / 64) * 8; };
-  ix.tables[0] = {v.mphf.blocks, h.mphf.blocks.size() * 4};
-  ix.tables[3] = {v.pos.words, packed_bytes(h.pos)};
-  ix.tables[6] = {v.mphf.fb_keys, h.mphf.n_fb_real() * 8};
-  if (h.kind == MAZU_K2U_SSHASH) {
-    ix.tables[1] = {v.sizes.blocks, h.sizes.blocks.size() * 8};
-    ix.tables[2] = {v.sizes.exceptions, h.sizes.n_exception_blocks * ((1ULL << h.sizes.log_s) + 1) * 8};
-    if (h.has_skew) {
-      ix.tables[4] = {v.skew_mphf.blocks, h.skew_mphf.blocks.size() * 4};
-      ix.tables[5] = {v.skew_pos.words, packed_bytes(h.skew_pos)};
-    }
-  }
-}
-void upload_u2pos(mazu_index& ix) {
-  IndexView& v = ix.view;
-  v.u2pos_kind = MAZU_U2POS_NONE;
-  if (!ix.u2pos || ix.u2pos->kind == MAZU_U2POS_NONE) return;
-  if (!ix.d_u2pos) {
-    auto d = std::make_shared<U2PosDev>();
-    auto b = upload(ix.u2pos->ctable_words, ix.device, 4);
-    d->bufs.push_back(b);
-    d->bytes += b->bytes;
-    upload_packed(ix.u2pos->contig_offsets, ix.device, d->bufs, d->bytes);
-    ix.d_u2pos = d;
-  }
-  const U2PosHost& u = *ix.u2pos;
-  v.u2pos_kind = (u32)u.kind;
-  v.ctable_words = (const u64*)ix.d_u2pos->bufs[0]->p;
-  v.n_occs = u.n_occs;
-  v.ctable_width = u.ctable_width;
-  v.ref_shift = (u32)u.ref_shift;
-  v.pos_mask = u.pos_mask;
-  v.contig_offsets = PackedVecView{(const u64*)ix.d_u2pos->bufs[1]->p, u.contig_offsets.len, (u32)u.contig_offsets.width, 0};
-}
-void upload_refs(mazu_index& ix) {
-  IndexView& v = ix.view;
-  v.refseq = nullptr;
-  v.ref_prefix = nullptr;
-  v.n_refs = ix.refs ? ix.refs->n_refs() : 0;
-  if (!ix.refs || !ix.refs->has_seq) return;
-  if (!ix.d_refs) {
-    auto d = std::make_shared<RefsDev>();
-    auto bs = upload(ix.refs->seq_words, ix.device, 2);
-    auto bp = upload(ix.refs->prefix, ix.device);
-    d->bufs = {bs, bp};
-    d->bytes = bs->bytes + bp->bytes;
-    ix.d_refs = d;
-  }
-  v.refseq = (const u64*)ix.d_refs->bufs[0]->p;
-  v.ref_prefix = (const u64*)ix.d_refs->bufs[1]->p;
-}
-
-}  // namespace
-#include "gpu_build.cuh"
-namespace {
-
-template <class T>
-T d2h_value(const T* p) {
-  T v;
-  MZ_CUDA(cudaMemcpy(&v, p, sizeof(T), cudaMemcpyDeviceToHost));
-  return v;
-}
-int grid_1d(u64 n, int sm_count, int block = 256) { return (int)std::max<u64>(1, std::min<u64>((n + block - 1) / block, (u64)sm_count * 16)); }
-
-struct CubTemp {  // grow-only scratch for cub primitives
-  void* p = nullptr;
-  size_t bytes = 0;
-  void need(size_t n) {
-    if (n > bytes) {
-      if (p) cudaFree(p);
-      MZ_CUDA(cudaMalloc(&p, n));
-      bytes = n;
-    }
-  }
-  ~CubTemp() {
-    if (p) cudaFree(p);
-  }
-};
-void exclusive_scan_u64(CubTemp& t, const u64* in, u64* out, u64 n_items) {
-  size_t b = 0;
-  MZ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b, in, out, (size_t)n_items));
-  t.need(b ? b : 1);
-  MZ_CUDA(cub::DeviceScan::ExclusiveSum(t.p, b, in, out, (size_t)n_items));
-}
-void inclusive_scan_u64(CubTemp& t, const u64* in, u64* out, u64 n_items) {
-  size_t b = 0;
-  MZ_CUDA(cub::DeviceScan::InclusiveSum(nullptr, b, in, out, (size_t)n_items));
-  t.need(b ? b : 1);
-  MZ_CUDA(cub::DeviceScan::InclusiveSum(t.p, b, in, out, (size_t)n_items));
-}
-void sort_pairs_u64(CubTemp& t, const u64* kin, u64* kout, const u64* vin, u64* vout, u64 n, int end_bit) {
-  size_t b = 0;
-  MZ_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b, kin, kout, vin, vout, (size_t)n, 0, end_bit));
-  t.need(b ? b : 1);
-  MZ_CUDA(cub::DeviceRadixSort::SortPairs(t.p, b, kin, kout, vin, vout, (size_t)n, 0, end_bit));
-}
-u64 reduce_max_u64(CubTemp& t, const u64* in, u64 n, int dev) {
-  if (n == 0) return 0;
-  DevBuf out(8, dev);
-  size_t b = 0;
-  MZ_CUDA(cub::DeviceReduce::Max(nullptr, b, in, (u64*)out.p, (size_t)n));
-  t.need(b ? b : 1);
-  MZ_CUDA(cub::DeviceReduce::Max(t.p, b, in, (u64*)out.p, (size_t)n));
-  return d2h_value((const u64*)out.p);
-}
-
-struct DevMphf {
-  RankedLevels view{};
-  std::vector<DevBufP> bufs;
-  size_t bytes = 0;
-  u64 block_bytes = 0, n_fb = 0;
-};
-// MphfHost::build_native on the device: same level sizes, same slots, hence the same bits
-DevMphf build_mphf_gpu(CubTemp& tmp, const u64* d_keys, u64 n, double gamma, int dev, int sm) {
-  DevMphf m;
-  m.view.family = MPHF_FAMILY_NATIVE;
-  auto cur = std::make_shared<DevBuf>(std::max<u64>(n, 1) * 8, dev), nxt = std::make_shared<DevBuf>(std::max<u64>(n, 1) * 8, dev);
-  if (n) MZ_CUDA(cudaMemcpy(cur->p, d_keys, n * 8, cudaMemcpyDeviceToDevice));
-  DevBuf counter(8, dev);
-  std::vector<DevBufP> level_blocks;
-  std::vector<u64> level_nb;
-  u64 n_cur = n, total_ones = 0, total_nb = 0;
-  for (u32 lvl = 0; lvl < MPHF_MAX_LEVELS && n_cur > 0; ++lvl) {
-    const u64 nb = (u64)((native_level_gamma(gamma, lvl) * (double)n_cur) / MPHF_BLOCK_BITS) + 1;
-    if (nb >> 32) throw Error(MAZU_ERR_INVALID_ARG, "MPHF level too large");
-    auto seen = std::make_shared<DevBuf>(nb * 32, dev);
-    DevBuf coll(nb * 32, dev), ones((nb + 1) * 4, dev), prefix((nb + 1) * 4, dev);
-    MZ_CUDA(cudaMemset(seen->p, 0, nb * 32));
-    MZ_CUDA(cudaMemset(coll.p, 0, nb * 32));
-    MZ_CUDA(cudaMemset(ones.p, 0, (nb + 1) * 4));
-    mphf_mark_kernel<<<grid_1d(n_cur, sm), 256>>>((const u64*)cur->p, n_cur, lvl, nb, (u32*)seen->p, (u32*)coll.p);
-    mphf_finalize_kernel<<<grid_1d(nb, sm), 256>>>((u32*)seen->p, (const u32*)coll.p, nb, (u32*)ones.p);
-    {
-      size_t b = 0;
-      MZ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b, (const u32*)ones.p, (u32*)prefix.p, (size_t)(nb + 1)));
-      tmp.need(b ? b : 1);
-      MZ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, b, (const u32*)ones.p, (u32*)prefix.p, (size_t)(nb + 1)));
-    }
-    mphf_set_ranks_kernel<<<grid_1d(nb, sm), 256>>>((u32*)seen->p, (const u32*)prefix.p, nb);
-    const u64 lvl_ones = d2h_value((const u32*)prefix.p + nb);
-    MZ_CUDA(cudaMemset(counter.p, 0, 8));
-    mphf_filter_kernel<<<grid_1d(n_cur, sm), 256>>>((const u64*)cur->p, n_cur, lvl, nb, (const u32*)coll.p, (u64*)nxt->p,
-                                                     (unsigned long long*)counter.p);
-    MZ_CUDA(cudaGetLastError());
-    const u64 n_next = d2h_value((const u64*)counter.p);
-    m.view.size[lvl] = nb;
-    m.view.block_off[lvl] = total_nb;
-    m.view.rank_base[lvl] = total_ones;
-    m.view.n_levels = lvl + 1;
-    total_nb += nb;
-    total_ones += lvl_ones;
-    level_blocks.push_back(seen);
-    level_nb.push_back(nb);
-    std::swap(cur, nxt);
-    n_cur = n_next;
-  }
-  // leftovers -> sorted fallback
-  std::vector<u64> left(n_cur);
-  if (n_cur) MZ_CUDA(cudaMemcpy(left.data(), cur->p, n_cur * 8, cudaMemcpyDeviceToHost));
-  std::sort(left.begin(), left.end());
-  left.erase(std::unique(left.begin(), left.end()), left.end());
-  std::vector<u64> fbv(left.size());
-  for (u64 i = 0; i < left.size(); ++i) fbv[i] = total_ones + i;
-  m.n_fb = left.size();
-  m.view.n_keys = total_ones + left.size();
-  m.view.n_fb = (u32)left.size();
-  if (left.empty()) {
-    left.push_back(0);
-    fbv.push_back(0);
-  }
-  auto fk = upload(left, dev), fv = upload(fbv, dev);
-  auto blocks = std::make_shared<DevBuf>((total_nb + 1) * 32, dev);
-  MZ_CUDA(cudaMemset(blocks->p, 0, (total_nb + 1) * 32));
-  u64 off = 0;
-  for (size_t l = 0; l < level_blocks.size(); ++l) {
-    MZ_CUDA(cudaMemcpy((char*)blocks->p + off * 32, level_blocks[l]->p, level_nb[l] * 32, cudaMemcpyDeviceToDevice));
-    off += level_nb[l];
-  }
-  m.view.blocks = (const u32*)blocks->p;
-  m.view.fb_keys = (const u64*)fk->p;
-  m.view.fb_vals = (const u64*)fv->p;
-  m.bufs = {blocks, fk, fv};
-  m.bytes = blocks->bytes + fk->bytes + fv->bytes;
-  m.block_bytes = total_nb * 32;
-  return m;
-}
-
-// bit-pack a device array of u64 values; returns the buffer and the width chosen like PackedVec::packed
-DevBufP pack_gpu(CubTemp& tmp, const u64* d_vals, u64 n, int dev, int sm, u32& width_out, u64& logical_bytes, u32 fixed_width = 0) {
-  u32 width = fixed_width;
-  if (!width) {
-    u64 mx = reduce_max_u64(tmp, d_vals, n, dev);
-    width = mx == 0 ? 1 : (u32)msb(mx) + 1;
-  }
-  width_out = width;
-  u64 nw = (n * width + 63) / 64;
-  auto b = std::make_shared<DevBuf>((nw + 2) * 8, dev);
-  MZ_CUDA(cudaMemset(b->p, 0, (nw + 2) * 8));
-  if (nw) pack_kernel<<<grid_1d(nw, sm), 256>>>(d_vals, n, width, (u64*)b->p, nw);
-  MZ_CUDA(cudaGetLastError());
-  logical_bytes = nw * 8;
-  return b;
-}
-
-// distinct keys of a sorted key array: returns M and fills set / ranges (M+1 entries) / optional first values / gid
-u64 group_sorted_gpu(CubTemp& tmp, const u64* d_keys, const u64* d_vals, u64 n, int dev, int sm, DevBufP& set, DevBufP& ranges, DevBufP* first_vals,
-                     DevBufP& gid) {
-  DevBuf flags(std::max<u64>(n, 1) * 8, dev);
-  gid = std::make_shared<DevBuf>(std::max<u64>(n, 1) * 8, dev);
-  mark_heads_kernel<<<grid_1d(n, sm), 256>>>(d_keys, n, (u64*)flags.p);
-  inclusive_scan_u64(tmp, (const u64*)flags.p, (u64*)gid->p, n);
-  const u64 M = d2h_value((const u64*)gid->p + (n - 1));
-  set = std::make_shared<DevBuf>(M * 8, dev);
-  ranges = std::make_shared<DevBuf>((M + 1) * 8, dev);
-  if (first_vals) *first_vals = std::make_shared<DevBuf>(M * 8, dev);
-  scatter_groups_kernel<<<grid_1d(n, sm), 256>>>(d_keys, d_vals, (const u64*)flags.p, (const u64*)gid->p, n, (u64*)set->p,
-                                                 first_vals ? (u64*)(*first_vals)->p : nullptr, (u64*)ranges->p);
-  MZ_CUDA(cudaGetLastError());
-  MZ_CUDA(cudaMemcpy((u64*)ranges->p + M, &n, 8, cudaMemcpyHostToDevice));
-  return M;
-}
-
-// PFHash::from_unitig_set on the device (twin of build_pfhash in host_build.hpp)
-void build_pfhash_gpu(mazu_index& ix, double gamma = 2.0) {
-  const UnitigSetHost& us = *ix.unitigs;
-  const u32 k = us.k;
-  const int dev = ix.device, sm = ix.sm_count;
-  const UnitigsView uv = ix.d_unitigs->view;
-  const u64 N = us.n_kmers();
-  for (u64 ui = 0; ui < us.n_unitigs(); ++ui)
-    if (us.unitig_len(ui) < k) throw Error(MAZU_ERR_INVALID_DATA, "a unitig is shorter than k");
-  CubTemp tmp;
-  auto d = std::make_shared<K2UDev>();
-  DevBuf keys(std::max<u64>(N, 1) * 8, dev), positions(std::max<u64>(N, 1) * 8, dev), bad(8, dev);
-  pfhash_keys_kernel<<<grid_1d(us.total_len(), sm), 256>>>(uv, (u64*)keys.p, (u64*)positions.p);
-  MZ_CUDA(cudaGetLastError());
-  DevMphf mphf = build_mphf_gpu(tmp, (const u64*)keys.p, N, gamma, dev, sm);
-  for (auto& b : mphf.bufs) {
-    d->bufs.push_back(b);
-    d->bytes += b->bytes;
-  }
-  const u64 n_slots = mphf.view.n_keys;
-  DevBuf vals(std::max<u64>(n_slots, 1) * 8, dev);
-  MZ_CUDA(cudaMemset(vals.p, 0, std::max<u64>(n_slots, 1) * 8));
-  MZ_CUDA(cudaMemset(bad.p, 0, 8));
-  pfhash_scatter_kernel<<<grid_1d(N, sm), 256>>>(mphf.view, (const u64*)keys.p, (const u64*)positions.p, N, n_slots, (u64*)vals.p,
-                                                 (unsigned long long*)bad.p);
-  MZ_CUDA(cudaGetLastError());
-  if (d2h_value((const u64*)bad.p) != 0) throw Error(MAZU_ERR_OTHER, "internal: GPU-built MPHF misses one of its keys");
-  u32 width = 1;
-  u64 bytes = 0;
-  DevBufP pos = pack_gpu(tmp, (const u64*)vals.p, n_slots, dev, sm, width, bytes, (u32)std::max<u64>(1, msb(std::max<u64>(us.total_len(), 1)) + 1));
-  d->bufs.push_back(pos);
-  d->bytes += pos->bytes;
-  auto H = std::make_shared<K2UHost>();
-  H->kind = MAZU_K2U_PFHASH;
-  H->unitigs = ix.unitigs;
-  IndexView& v = ix.view;
-  v.k2u_kind = MAZU_K2U_PFHASH;
-  v.mphf = mphf.view;
-  v.pos = PackedVecView{(const u64*)pos->p, n_slots, width, 0};
-  v.w = 0;
-  v.has_skew = 0;
-  v.skew_param = MAZU_SKEW_NONE;
-  ix.tables[0] = {v.mphf.blocks, mphf.block_bytes};
-  ix.tables[3] = {v.pos.words, bytes};
-  ix.tables[6] = {v.mphf.fb_keys, mphf.n_fb * 8};
-  MZ_CUDA(cudaDeviceSynchronize());
-  ix.k2u = H;
-  ix.d_k2u = d;
-}
-
-// SSHashBuilder::from_unitig_set + finish on the device; fills ix.view / ix.k2u metadata / ix.d_k2u
-void build_sshash_gpu(mazu_index& ix, u32 w, u64 skew_param, u64 seed, double gamma = 2.0) {
-  const UnitigSetHost& us = *ix.unitigs;
-  const u32 k = us.k;
-  if (w == 0 || w > k) throw Error(MAZU_ERR_INVALID_ARG, "minimizer length w must satisfy 1 <= w <= k");
-  if (us.n_kmers() == 0 || us.total_len() < k) throw Error(MAZU_ERR_INVALID_DATA, "unitig set holds no k-mer");
-  const int dev = ix.device, sm = ix.sm_count;
-  const UnitigsView uv = ix.d_unitigs->view;
-  const u64 U = us.n_unitigs();
-  CubTemp tmp;
-  auto d = std::make_shared<K2UDev>();
-  auto keep = [&](const DevBufP& b) {
-    d->bufs.push_back(b);
-    d->bytes += b->bytes;
-  };
-  // 1. collect
-  int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, collect_minimizers_kernel<true>, QR_WARPS * 32, 0);
-  const int cgrid = (int)std::max<u64>(1, std::min<u64>((U + QR_WARPS - 1) / QR_WARPS, (u64)sm * std::max(occ, 1)));
-  DevBuf counts((2 * U + 1) * 8, dev), bases((2 * U + 1) * 8, dev);
-  MZ_CUDA(cudaMemset(counts.p, 0, (2 * U + 1) * 8));
-  collect_minimizers_kernel<false><<<cgrid, QR_WARPS * 32>>>(uv, w, seed, (u64*)counts.p, nullptr, nullptr, nullptr);
-  MZ_CUDA(cudaGetLastError());
-  exclusive_scan_u64(tmp, (const u64*)counts.p, (u64*)bases.p, 2 * U + 1);
-  const u64 n = d2h_value((const u64*)bases.p + 2 * U);
-  if (n == 0) throw Error(MAZU_ERR_INVALID_DATA, "no minimizer occurrence collected");
-  DevBufP words = std::make_shared<DevBuf>(n * 8, dev), poss = std::make_shared<DevBuf>(n * 8, dev);
-  collect_minimizers_kernel<true><<<cgrid, QR_WARPS * 32>>>(uv, w, seed, nullptr, (const u64*)bases.p, (u64*)words->p, (u64*)poss->p);
-  MZ_CUDA(cudaGetLastError());
-  // 2. stable sort by minimizer word
-  DevBufP words_s = std::make_shared<DevBuf>(n * 8, dev), poss_s = std::make_shared<DevBuf>(n * 8, dev);
-  sort_pairs_u64(tmp, (const u64*)words->p, (u64*)words_s->p, (const u64*)poss->p, (u64*)poss_s->p, n, (int)std::min<u32>(64, 2 * w));
-  words.reset();
-  poss.reset();
-  // 3. group
-  DevBufP mm_set, ranges, gid;
-  const u64 M = group_sorted_gpu(tmp, (const u64*)words_s->p, nullptr, n, dev, sm, mm_set, ranges, nullptr, gid);
-  words_s.reset();
-  // 4. MPHF over the minimizer set
-  DevMphf mphf = build_mphf_gpu(tmp, (const u64*)mm_set->p, M, gamma, dev, sm);
-  for (auto& b : mphf.bufs) keep(b);
-  // 5. bucket sizes in MPHF order, fingerprints, prefix sum
-  DevBuf hashes(M * 8, dev), sizes_by_h((M + 1) * 8, dev), prefix((M + 1) * 8, dev), fps(M + 1, dev), bad(8, dev);
-  MZ_CUDA(cudaMemset(sizes_by_h.p, 0, (M + 1) * 8));
-  MZ_CUDA(cudaMemset(bad.p, 0, 8));
-  group_hash_kernel<<<grid_1d(M, sm), 256>>>(mphf.view, (const u64*)mm_set->p, (const u64*)ranges->p, M, (u64*)hashes.p, (u64*)sizes_by_h.p,
-                                             (u8*)fps.p, (unsigned long long*)bad.p);
-  MZ_CUDA(cudaGetLastError());
-  if (d2h_value((const u64*)bad.p) != 0) throw Error(MAZU_ERR_OTHER, "internal: GPU-built MPHF is not a bijection on its keys");
-  exclusive_scan_u64(tmp, (const u64*)sizes_by_h.p, (u64*)prefix.p, M + 1);
-  // 6. scatter positions into bucket order
-  DevBuf pos_out(n * 8, dev);
-  scatter_positions_kernel<<<grid_1d(n, sm), 256>>>((const u64*)poss_s->p, (const u64*)gid->p, (const u64*)ranges->p, (const u64*)hashes.p,
-                                                    (const u64*)prefix.p, n, (u64*)pos_out.p);
-  MZ_CUDA(cudaGetLastError());
-  // 9a. pack the positions
-  u32 pos_width = 1;
-  u64 pos_bytes = 0;
-  DevBufP pos_packed = pack_gpu(tmp, (const u64*)pos_out.p, n, dev, sm, pos_width, pos_bytes);
-  keep(pos_packed);
-  // 8. blocked Elias-Fano of the prefix sums (+ fingerprints)
-  const u64 nE = M + 1, u = d2h_value((const u64*)prefix.p + M);
-  u64 l = msb(u / nE);
-  if (l == 0) l = 1;
-  u32 log_s = 5;
-  while (log_s > 0 && ((1ULL << log_s) + 1) * l > 64) --log_s;
-  const bool all_exc = ((1ULL << log_s) + 1) * l > 64 || (u >> 63);
-  const u64 S = 1ULL << log_s, nbE = (nE + S - 1) / S;
-  DevBuf exc_flags((nbE + 1) * 8, dev), exc_index((nbE + 1) * 8, dev);
-  MZ_CUDA(cudaMemset(exc_flags.p, 0, (nbE + 1) * 8));
-  ef_blocks_kernel<false><<<grid_1d(nbE, sm), 256>>>((const u64*)prefix.p, nE, (u32)l, log_s, 8, all_exc, (const u8*)fps.p, M, (u64*)exc_flags.p, nullptr,
-                                                      nullptr, nullptr);
-  MZ_CUDA(cudaGetLastError());
-  exclusive_scan_u64(tmp, (const u64*)exc_flags.p, (u64*)exc_index.p, nbE + 1);
-  const u64 n_exc = d2h_value((const u64*)exc_index.p + nbE);
-  DevBufP ef_blocks = std::make_shared<DevBuf>((nbE * 8 + 8) * 8, dev), ef_exc = std::make_shared<DevBuf>(std::max<u64>(1, n_exc * (S + 1)) * 8, dev);
-  MZ_CUDA(cudaMemset(ef_blocks->p, 0, (nbE * 8 + 8) * 8));
-  MZ_CUDA(cudaMemset(ef_exc->p, 0, std::max<u64>(1, n_exc * (S + 1)) * 8));
-  ef_blocks_kernel<true><<<grid_1d(nbE, sm), 256>>>((const u64*)prefix.p, nE, (u32)l, log_s, 8, all_exc, (const u8*)fps.p, M, nullptr,
-                                                     (const u64*)exc_index.p, (u64*)ef_blocks->p, (u64*)ef_exc->p);
-  MZ_CUDA(cudaGetLastError());
-  keep(ef_blocks);
-  keep(ef_exc);
-  // host-side metadata
-  auto H = std::make_shared<K2UHost>();
-  H->kind = MAZU_K2U_SSHASH;
-  H->unitigs = ix.unitigs;
-  H->w = w;
-  H->seed = seed;
-  H->skew_param = skew_param;
-  H->n_minimizers = M;
-  H->n_minimizer_occs = n;
-  H->sizes.n = nE;
-  H->sizes.l = (u32)l;
-  H->sizes.log_s = log_s;
-  H->sizes.wpb = 8;
-  H->sizes.n_exception_blocks = n_exc;
-  IndexView& v = ix.view;
-  v.k2u_kind = MAZU_K2U_SSHASH;
-  v.mphf = mphf.view;
-  v.pos = PackedVecView{(const u64*)pos_packed->p, n, pos_width, 0};
-  v.sizes = BlockedEFView{(const u64*)ef_blocks->p, (const u64*)ef_exc->p, nE, (u32)l, log_s, 8, 0};
-  v.w = w;
-  v.seed = seed;
-  v.skew_param = skew_param;
-  v.has_skew = 0;
-  ix.tables[0] = {v.mphf.blocks, mphf.block_bytes};
-  ix.tables[1] = {v.sizes.blocks, nbE * 8 * 8};
-  ix.tables[2] = {v.sizes.exceptions, n_exc * (S + 1) * 8};
-  ix.tables[3] = {v.pos.words, pos_bytes};
-  ix.tables[6] = {v.mphf.fb_keys, mphf.n_fb * 8};
-  // 7. skew index
-  if (skew_param != MAZU_SKEW_NONE) {
-    H->has_skew = true;
-    v.has_skew = 1;
-    DevBuf cnts((n + 1) * 8, dev), sb((n + 1) * 8, dev);
-    MZ_CUDA(cudaMemset(cnts.p, 0, (n + 1) * 8));
-    skew_tuples_kernel<false><<<grid_1d(n, sm), 256>>>(uv, w, skew_param, (const u64*)poss_s->p, (const u64*)gid->p, (const u64*)ranges->p, n,
-                                                        (u64*)cnts.p, nullptr, nullptr, nullptr);
-    MZ_CUDA(cudaGetLastError());
-    exclusive_scan_u64(tmp, (const u64*)cnts.p, (u64*)sb.p, n + 1);
-    const u64 T = d2h_value((const u64*)sb.p + n);
-    DevMphf smphf;
-    smphf.view.family = MPHF_FAMILY_NATIVE;
-    u64 Ms = 0, spos_bytes = 0;
-    u32 swidth = 1;
-    DevBufP spos_packed;
-    if (T > 0) {
-      DevBufP sw = std::make_shared<DevBuf>(T * 8, dev), sp = std::make_shared<DevBuf>(T * 8, dev);
-      skew_tuples_kernel<true><<<grid_1d(n, sm), 256>>>(uv, w, skew_param, (const u64*)poss_s->p, (const u64*)gid->p, (const u64*)ranges->p, n, nullptr,
-                                                         (const u64*)sb.p, (u64*)sw->p, (u64*)sp->p);
-      MZ_CUDA(cudaGetLastError());
-      DevBufP sw_s = std::make_shared<DevBuf>(T * 8, dev), sp_s = std::make_shared<DevBuf>(T * 8, dev);
-      sort_pairs_u64(tmp, (const u64*)sw->p, (u64*)sw_s->p, (const u64*)sp->p, (u64*)sp_s->p, T, (int)std::min<u32>(64, 2 * k));
-      sw.reset();
-      sp.reset();
-      DevBufP km_set, ranges2, first_pos, gid2;
-      Ms = group_sorted_gpu(tmp, (const u64*)sw_s->p, (const u64*)sp_s->p, T, dev, sm, km_set, ranges2, &first_pos, gid2);  // dedup keeps the first
-      smphf = build_mphf_gpu(tmp, (const u64*)km_set->p, Ms, gamma, dev, sm);
-      DevBuf hashes2(Ms * 8, dev), svals(Ms * 8, dev);
-      MZ_CUDA(cudaMemset(bad.p, 0, 8));
-      group_hash_kernel<<<grid_1d(Ms, sm), 256>>>(smphf.view, (const u64*)km_set->p, (const u64*)ranges2->p, Ms, (u64*)hashes2.p, nullptr, nullptr,
-                                                  (unsigned long long*)bad.p);
-      MZ_CUDA(cudaGetLastError());
-      if (d2h_value((const u64*)bad.p) != 0) throw Error(MAZU_ERR_OTHER, "internal: GPU-built skew MPHF is not a bijection on its keys");
-      scatter_by_hash_kernel<<<grid_1d(Ms, sm), 256>>>((const u64*)first_pos->p, (const u64*)hashes2.p, Ms, (u64*)svals.p);
-      MZ_CUDA(cudaGetLastError());
-      spos_packed = pack_gpu(tmp, (const u64*)svals.p, Ms, dev, sm, swidth, spos_bytes);
-    } else {
-      smphf = build_mphf_gpu(tmp, nullptr, 0, gamma, dev, sm);
-      spos_packed = std::make_shared<DevBuf>(16, dev);
-      MZ_CUDA(cudaMemset(spos_packed->p, 0, 16));
-    }
-    for (auto& b : smphf.bufs) keep(b);
-    keep(spos_packed);
-    H->n_skew_kmers = Ms;
-    v.skew_mphf = smphf.view;
-    v.skew_pos = PackedVecView{(const u64*)spos_packed->p, Ms, swidth, 0};
-    ix.tables[4] = {v.skew_mphf.blocks, smphf.block_bytes};
-    ix.tables[5] = {v.skew_pos.words, spos_bytes};
-  }
-  MZ_CUDA(cudaDeviceSynchronize());
-  ix.k2u = H;
-  ix.d_k2u = d;
-}
 
 mazu_index* finalize_index(std::unique_ptr<mazu_index> ix) {
   int n = 0;
