@@ -690,10 +690,20 @@ def main():
         peak_source = "P_rand: measured independent random 32-byte gathers over a 32 GiB table (profiles/r01_prand.json), in GB/s of sectors"
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr_path) and W in ("config2", "config3"):
+    if os.path.exists(tr_path):
         try:
-            per = json.load(open(tr_path)).get("query_reads_kernel<%d>" % (0 if mode == mz.MODE_RANDOM else 1), {}).get("dram_bytes_per_lookup")
+            tj = json.load(open(tr_path))
+            if W in ("config2", "config3"):
+                per = tj.get("query_reads_kernel<%d>" % (0 if mode == mz.MODE_RANDOM else 1), {}).get("dram_bytes_per_lookup")
+            elif W == "config5" and mode == mz.MODE_RANDOM:
+                per = tj.get("config5 query_reads_kernel<0>", {}).get("dram_bytes_per_lookup")
+            elif W == "config5-kmers":
+                per = tj.get("config5 k2u_batch_kernel", {}).get("dram_bytes_per_lookup")
+            else:
+                per = None
             traffic = per * n_units if per is not None else None
+            if W == "config4":
+                traffic = tj.get("occ_fill_kernel<false>", {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     line = {
@@ -710,7 +720,7 @@ def main():
                      "peak_source": peak_source, "algorithmic_bytes_per_unit": alg, "units_per_launch": n_units, "kernel_ms": kernel_ms,
                      "step_ms": [round(x, 3) for x in step_ms], "note": note,
                      # what the kernel is actually limited by (ncu, profiles/*.summary.txt): measured DRAM bytes / time against the same peak
-                     "dram_frac_measured": (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if (traffic and peak_kind == "hbm") else None},
+                     "dram_frac_measured": (traffic / (kernel_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0))) if traffic else None},
         "parity_spot_check": parity_ok,
     }
     line.update(info)
