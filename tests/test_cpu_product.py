@@ -30,6 +30,24 @@ def test_rust_sys_crate_declares_every_symbol():
     assert rust == _header_symbols()
 
 
+def _build_c_example(tmp_path):
+    exe = str(tmp_path / "query_reads")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "query_reads.c"),
+           "-L" + os.path.dirname(mz.LIB_PATH), "-lmazu_b200", "-Wl,-rpath," + os.path.dirname(mz.LIB_PATH), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_example_links(tmp_path):
+    """include/mazu_b200.h compiles as C99 with -Wall -Wextra -Werror and a C program links against the library;
+    without a GPU the example stops at its device check (exit 3), never in a fallback."""
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "data", "pf1", "yeast_chr01_index")], capture_output=True, text=True)
+    if mz.device_count() <= 0:
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
 def test_library_exports_every_declared_symbol():
     assert os.path.exists(mz.LIB_PATH), "libmazu_b200.so not built (run __graft_entry__.build())"
     L = C.CDLL(mz.LIB_PATH)

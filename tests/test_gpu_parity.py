@@ -779,6 +779,20 @@ def test_error_codes():
     assert e.value.code == -7
 
 
+def test_c_example_runs(tmp_path):
+    """examples/query_reads.c: a plain C caller of the ABI end to end (load, rebuild K2U, validate_self, query both modes, project)"""
+    import subprocess
+    from test_cpu_product import _build_c_example
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([exe, YEAST_CHR01], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "validate_self: 230188 queries, 170689 identity, 59499 twin, 262130 projected, 0 failures" in r.stdout
+    # the oracle's answer for the two reads of the example: 32 + 1 valid windows (the N invalidates 31 of 32), the poly-T 31-mer hits
+    assert "mode 0: 33 k-mers, 1 hits, 32 misses, 64 slots" in r.stdout
+    assert "mode 1: 33 k-mers, 1 hits, 32 misses, 64 slots" in r.stdout
+    assert "projected reference positions: 6" in r.stdout
+
+
 def test_pinned_host_buffers(yeast_sshash, yeast_queries):
     """mazu_b200_alloc_pinned: page-locked buffers for callers that do not link CUDA; same answers as pageable numpy arrays"""
     g, o = yeast_sshash
