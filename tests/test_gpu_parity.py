@@ -779,6 +779,28 @@ def test_error_codes():
     assert e.value.code == -7
 
 
+def test_cuda_path_reproduces_golden_fixture():
+    """tests/golden/yeast_chr01_queries.npz: committed answers for a seeded batch; compared here without loading the oracle"""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "yeast_chr01_queries.npz"))
+    bases, offs = g["bases"], g["read_offsets"]
+    dense = mz.DenseIndex.deserialize_from_cpp(YEAST_CHR01)
+    assert dense.validate_self() == [int(x) for x in g["validate_self"]]
+    ss = dense.rebuild_k2u(mz.K2U_SSHASH, w=15, skew_param=32, seed=0)
+    ss_gpu = None
+    for name, ix in (("pfhash", dense), ("sshash", ss)):
+        for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+            hits, cnt, koffs = ix.query_reads(bases, offs, mode=mode)
+            tag = "%s_%s" % (name, "streaming" if mode == mz.MODE_STREAMING else "random")
+            assert np.array_equal(hits.view(np.uint32).reshape(-1, 4), g[tag + "_hits"]), tag
+            assert [int(x) for x in cnt] == [int(x) for x in g[tag + "_counts"]]
+            assert np.array_equal(koffs, g["kmer_offsets"])
+    hits, _, _ = ss.query_reads(bases, offs)
+    po, pr = ss.project_hits(hits)
+    assert np.array_equal(po, g["project_offsets"]) and np.array_equal(pr.view(np.uint32).reshape(-1, 3), g["project_records"])
+    do, dr = dense.decode_occs(g["decode_unitig_ids"])
+    assert np.array_equal(do, g["decode_offsets"]) and np.array_equal(dr.view(np.uint32).reshape(-1, 3), g["decode_records"])
+
+
 def test_c_example_runs(tmp_path):
     """examples/query_reads.c: a plain C caller of the ABI end to end (load, rebuild K2U, validate_self, query both modes, project)"""
     import subprocess

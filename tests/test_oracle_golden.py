@@ -427,3 +427,25 @@ def test_contig_iter_tiny_multi_refs():
     assert list(t0["unitig_len"]) == [5, 8, 9, 8, 5] and list(t0["unitig_id"]) == [0, 1, 2, 3, 4]
     assert list(t1["unitig_len"]) == [5, 9, 9, 9, 5] and list(t1["unitig_id"]) == [0, 5, 2, 6, 4]
     assert idx.ref_len(1) == 21 and idx.k == 5
+
+
+def test_oracle_reproduces_golden_fixture():
+    """tests/golden/yeast_chr01_queries.npz (made by tests/golden/make_golden.py) is still what the oracle answers"""
+    import os
+    import sys
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden
+    g = np.load(os.path.join(here, "golden", "yeast_chr01_queries.npz"))
+    o, bases, offs = make_golden.inputs()
+    assert np.array_equal(bases, g["bases"]) and np.array_equal(offs, g["read_offsets"])
+    assert list(o.validate_self()) == list(g["validate_self"])
+    ss = o.rebuild_k2u(1, w=15, skew=32, seed=0)
+    for name, ix in (("pfhash", o), ("sshash", ss)):
+        for streaming in (False, True):
+            hits, cnt, koffs = ix.query_reads(bases, offs, streaming=streaming, reset_per_read=True)
+            tag = "%s_%s" % (name, "streaming" if streaming else "random")
+            assert np.array_equal(hits.view(np.uint32).reshape(-1, 4), g[tag + "_hits"]), tag
+            assert list(cnt) == list(g[tag + "_counts"])
+            assert np.array_equal(koffs, g["kmer_offsets"])
