@@ -723,6 +723,15 @@ def main():
                      "dram_frac_measured": (traffic / (kernel_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0))) if traffic else None},
         "parity_spot_check": parity_ok,
     }
+    # both denominators, always -- the streaming HBM peak and the measured random-gather rate (32-byte sectors)
+    try:
+        pr = json.load(open(os.path.join(ROOT, "profiles", "r01_prand.json")))
+        p_rand = float(pr["32GiB"]["GBps"])
+        line["roofline"]["vs_hbm_stream_peak"] = achieved / float(peaks.get("hbm_gbs", 6650.0))
+        line["roofline"]["vs_random_gather_peak"] = achieved / p_rand
+        line["roofline"]["random_gather_peak_gbs_of_sectors"] = p_rand
+    except Exception:
+        pass
     line.update(info)
     if cnt_line:
         line["counts"] = cnt_line
