@@ -509,7 +509,7 @@ def main():
         d_out = torch.empty((total, 3), dtype=torch.int32, device=dev)
         n_units = total
         alg = (32.0 * n_q + (6 + 12) * total) / total  # bytes per occurrence: offsets pair per query + 42-bit word in + 12 B out
-        kernel_name = "mazu::occ_fill_kernel<false> (+ occ_lens_kernel + cub scan)"
+        kernel_name = "mazu::occ_fill_tma_kernel<false> (+ occ_lens_kernel + cub scan)"
         launches_per_step = 4
         import ctypes as C
 
@@ -554,7 +554,7 @@ def main():
                 r = out_h[int(offs_h[q])]
                 ok &= (int(r[0]) == int(ref_ids[e])) and (int(r[1]) == want_pos % (1 << 32)) and (int(r[2]) == want_o)
             return {"value": total / (ms * 1e-3), "unit": unit, "ms_per_step": ms, "frac_of_hbm_peak": total * (alg + 16.0 * n_q / total) / (ms * 1e-3) / 1e9 / 6553.9,
-                    "parity_spot_check": bool(ok), "kernel": "mazu::occ_fill_kernel<true>"}
+                    "parity_spot_check": bool(ok), "kernel": "mazu::occ_fill_tma_kernel<true>"}
 
         info["projected_fn"] = projected_line
 

@@ -682,9 +682,25 @@ static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu
     d_o = (OccRec*)d_out;
   }
   if (n) {
-    int grid = idx->sm_count * 8;  // tiles of the OUTPUT are grid-strided; the kernel reads the total from out_offsets[n]
-    if (project) occ_fill_kernel<true><<<grid, 256, 0, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o);
-    else occ_fill_kernel<false><<<grid, 256, 0, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o);
+    // tiles of the OUTPUT are grid-strided; the kernels read the total from out_offsets[n]
+    static const bool use_tma = [] {
+      const char* e = getenv("MAZU_B200_OCC_TMA");
+      return e ? atoi(e) != 0 : true;
+    }();
+    if (use_tma) {  // bulk-copy staged fill: one CTA of 8 warps per SM, 161 KB of dynamic shared memory
+      static std::once_flag once;
+      std::call_once(once, [] {
+        cudaFuncSetAttribute(occ_fill_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OCC_TMA_SMEM);
+        cudaFuncSetAttribute(occ_fill_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OCC_TMA_SMEM);
+      });
+      int grid = idx->sm_count;
+      if (project) occ_fill_tma_kernel<true><<<grid, OCC_TMA_WARPS * 32, OCC_TMA_SMEM, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o);
+      else occ_fill_tma_kernel<false><<<grid, OCC_TMA_WARPS * 32, OCC_TMA_SMEM, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o);
+    } else {
+      int grid = idx->sm_count * 8;
+      if (project) occ_fill_kernel<true><<<grid, 256, 0, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o);
+      else occ_fill_kernel<false><<<grid, 256, 0, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o);
+    }
     MZ_CUDA(cudaGetLastError());
   }
   if (mem == MAZU_MEM_HOST) {

@@ -13,6 +13,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cuda/ptx>
+
 #include "index_layout.hpp"
 
 namespace mazu {
@@ -777,6 +779,95 @@ __device__ __forceinline__ u64 warp_last_le(const u64* __restrict__ off, u64 n, 
 // therefore spread over 64 warps instead of serialising one, and consecutive lanes read consecutive
 // occurrence words and write consecutive 12-byte records.
 static const u64 OCC_TILE = 1024;
+// one tile [t0, t1) of the output, overlapping the queries qlo..qhi (generic path: plain loads and stores)
+template <bool PROJECT>
+__device__ __forceinline__ void occ_fill_tile(const IndexView& ix, const u32* __restrict__ uids, const Hit* __restrict__ hits,
+                                              const u64* __restrict__ out_offsets, OccRec* __restrict__ out, u64 t0, u64 t1, u64 qlo, u64 qhi,
+                                              u32 lane, u32 k, bool out_aligned) {
+  if (qhi - qlo <= 32) {
+    // few, long lists in this tile: walk the overlapping queries (warp-uniform), lanes stride over each
+    // segment with plain arithmetic -- no per-record search; 4 independent records in flight per lane
+    for (u64 q = qlo; q <= qhi; ++q) {
+      const u64 ob = __ldg(out_offsets + q), oe = __ldg(out_offsets + q + 1);
+      const u64 sb = max(ob, t0), se = min(oe, t1);
+      if (sb >= se) continue;
+      Hit h = hit_none(NO_MATCH);
+      u32 uid;
+      if (PROJECT) {
+        h = hits[q];
+        uid = h.unitig_id;
+      } else {
+        uid = uids[q];
+      }
+      const u64 e0 = packed_get(ix.contig_offsets, uid) - ob;  // element index = e0 + rec
+      // body: every lane owns 4 CONSECUTIVE records = 48 contiguous output bytes = three 16-byte stores
+      // (record index a multiple of 4 <=> byte offset a multiple of 16); head/tail records go one by one
+      u64 body_b = (sb + 3) & ~3ULL, body_e = body_b + ((se > body_b ? se - body_b : 0) & ~3ULL);
+      if (!out_aligned || body_b >= se) body_b = body_e = sb;
+      for (u64 rec = sb + lane; rec < body_b; rec += 32) {
+        OccRec o = occ_decode(ix, e0 + rec);
+        out[rec] = PROJECT ? project_occ(k, h, o) : o;
+      }
+      for (u64 base = body_b + 4 * lane; base < body_e; base += 128) {
+        OccRec o[4];
+        if (ix.u2pos_kind == MAZU_U2POS_PISCEM && ix.ctable_width <= 48) {
+          // four consecutive packed fields span at most 4 words (4 * 48 + 63 < 256 bits): 4 loads instead of 8
+          const u32 wd = ix.ctable_width;
+          const u64 bit0 = (e0 + base) * wd, wi = bit0 >> 6;
+          const u64 w0 = __ldg(ix.ctable_words + wi), w1 = __ldg(ix.ctable_words + wi + 1), w2 = __ldg(ix.ctable_words + wi + 2),
+                    w3 = __ldg(ix.ctable_words + wi + 3);
+          const u64 fmask = (1ULL << wd) - 1ULL;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const u32 b = (u32)(bit0 & 63) + (u32)j * wd;  // < 64 + 3 * 48 = 208
+            const u32 q = b >> 6, sh = b & 63u;
+            const u64 lo = q == 0 ? w0 : (q == 1 ? w1 : (q == 2 ? w2 : w3)), hi = q == 0 ? w1 : (q == 1 ? w2 : w3);
+            const u64 enc = (sh ? (lo >> sh) | (hi << (64 - sh)) : lo) & fmask;
+            o[j].ref_id = (u32)(enc >> ix.ref_shift);
+            o[j].pos = (u32)((enc >> 1) & ix.pos_mask);
+            o[j].fw = (u32)(enc & 1ULL);
+            if (PROJECT) o[j] = project_occ(k, h, o[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            o[j] = occ_decode(ix, e0 + base + j);
+            if (PROJECT) o[j] = project_occ(k, h, o[j]);
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + base);
+        dst[0] = make_uint4(o[0].ref_id, o[0].pos, o[0].fw, o[1].ref_id);
+        dst[1] = make_uint4(o[1].pos, o[1].fw, o[2].ref_id, o[2].pos);
+        dst[2] = make_uint4(o[2].fw, o[3].ref_id, o[3].pos, o[3].fw);
+      }
+      for (u64 rec = body_e + lane; rec < se; rec += 32) {
+        OccRec o = occ_decode(ix, e0 + rec);
+        out[rec] = PROJECT ? project_occ(k, h, o) : o;
+      }
+    }
+    return;
+  }
+  for (u64 rec = t0 + lane; rec < t1; rec += 32) {
+    u64 a = qlo, b = qhi;  // off[a] <= rec, answer in [a, b]
+    while (a < b) {
+      u64 m = (a + b + 1) >> 1;
+      if (__ldg(out_offsets + m) <= rec) a = m; else b = m - 1;
+    }
+    Hit h = hit_none(NO_MATCH);
+    u32 uid;
+    if (PROJECT) {
+      h = hits[a];
+      uid = h.unitig_id;
+    } else {
+      uid = uids[a];
+    }
+    u64 s = packed_get(ix.contig_offsets, uid);  // dense_unitig_table.rs:58-63 / :130-135
+    OccRec o = occ_decode(ix, s + (rec - __ldg(out_offsets + a)));
+    if (PROJECT) o = project_occ(k, h, o);
+    out[rec] = o;
+  }
+}
+
 template <bool PROJECT>
 // (256, 1): ptxas takes ~51 registers and keeps a lane's four packed-word loads in flight; forcing 6 or 8 resident CTAs
 // (40 / 32 registers, spills) measured 5 % / 18 % slower
@@ -793,89 +884,192 @@ __global__ void __launch_bounds__(256, 1) occ_fill_kernel(const __grid_constant_
     const u64 t1 = min(t0 + OCC_TILE, total);
     const u64 qlo = warp_last_le(out_offsets, n, t0, lane);
     const u64 qhi = warp_last_le(out_offsets, n, t1 - 1, lane);
-    if (qhi - qlo <= 32) {
-      // few, long lists in this tile: walk the overlapping queries (warp-uniform), lanes stride over each
-      // segment with plain arithmetic -- no per-record search; 4 independent records in flight per lane
-      for (u64 q = qlo; q <= qhi; ++q) {
-        const u64 ob = __ldg(out_offsets + q), oe = __ldg(out_offsets + q + 1);
-        const u64 sb = max(ob, t0), se = min(oe, t1);
-        if (sb >= se) continue;
-        Hit h = hit_none(NO_MATCH);
-        u32 uid;
-        if (PROJECT) {
-          h = hits[q];
-          uid = h.unitig_id;
-        } else {
-          uid = uids[q];
-        }
-        const u64 e0 = packed_get(ix.contig_offsets, uid) - ob;  // element index = e0 + rec
-        // body: every lane owns 4 CONSECUTIVE records = 48 contiguous output bytes = three 16-byte stores
-        // (record index a multiple of 4 <=> byte offset a multiple of 16); head/tail records go one by one
-        u64 body_b = (sb + 3) & ~3ULL, body_e = body_b + ((se > body_b ? se - body_b : 0) & ~3ULL);
-        if (!out_aligned || body_b >= se) body_b = body_e = sb;
-        for (u64 rec = sb + lane; rec < body_b; rec += 32) {
-          OccRec o = occ_decode(ix, e0 + rec);
-          out[rec] = PROJECT ? project_occ(k, h, o) : o;
-        }
-        for (u64 base = body_b + 4 * lane; base < body_e; base += 128) {
-          OccRec o[4];
-          if (ix.u2pos_kind == MAZU_U2POS_PISCEM && ix.ctable_width <= 48) {
-            // four consecutive packed fields span at most 4 words (4 * 48 + 63 < 256 bits): 4 loads instead of 8
-            const u32 wd = ix.ctable_width;
-            const u64 bit0 = (e0 + base) * wd, wi = bit0 >> 6;
-            const u64 w0 = __ldg(ix.ctable_words + wi), w1 = __ldg(ix.ctable_words + wi + 1), w2 = __ldg(ix.ctable_words + wi + 2),
-                      w3 = __ldg(ix.ctable_words + wi + 3);
-            const u64 fmask = (1ULL << wd) - 1ULL;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const u32 b = (u32)(bit0 & 63) + (u32)j * wd;  // < 64 + 3 * 48 = 208
-              const u32 q = b >> 6, sh = b & 63u;
-              const u64 lo = q == 0 ? w0 : (q == 1 ? w1 : (q == 2 ? w2 : w3)), hi = q == 0 ? w1 : (q == 1 ? w2 : w3);
-              const u64 enc = (sh ? (lo >> sh) | (hi << (64 - sh)) : lo) & fmask;
-              o[j].ref_id = (u32)(enc >> ix.ref_shift);
-              o[j].pos = (u32)((enc >> 1) & ix.pos_mask);
-              o[j].fw = (u32)(enc & 1ULL);
-              if (PROJECT) o[j] = project_occ(k, h, o[j]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              o[j] = occ_decode(ix, e0 + base + j);
-              if (PROJECT) o[j] = project_occ(k, h, o[j]);
-            }
-          }
-          uint4* dst = reinterpret_cast<uint4*>(out + base);
-          dst[0] = make_uint4(o[0].ref_id, o[0].pos, o[0].fw, o[1].ref_id);
-          dst[1] = make_uint4(o[1].pos, o[1].fw, o[2].ref_id, o[2].pos);
-          dst[2] = make_uint4(o[2].fw, o[3].ref_id, o[3].pos, o[3].fw);
-        }
-        for (u64 rec = body_e + lane; rec < se; rec += 32) {
-          OccRec o = occ_decode(ix, e0 + rec);
-          out[rec] = PROJECT ? project_occ(k, h, o) : o;
-        }
-      }
-      continue;
-    }
-    for (u64 rec = t0 + lane; rec < t1; rec += 32) {
-      u64 a = qlo, b = qhi;  // off[a] <= rec, answer in [a, b]
-      while (a < b) {
-        u64 m = (a + b + 1) >> 1;
-        if (__ldg(out_offsets + m) <= rec) a = m; else b = m - 1;
-      }
-      Hit h = hit_none(NO_MATCH);
-      u32 uid;
-      if (PROJECT) {
-        h = hits[a];
-        uid = h.unitig_id;
-      } else {
-        uid = uids[a];
-      }
-      u64 s = packed_get(ix.contig_offsets, uid);  // dense_unitig_table.rs:58-63 / :130-135
-      OccRec o = occ_decode(ix, s + (rec - __ldg(out_offsets + a)));
-      if (PROJECT) o = project_occ(k, h, o);
-      out[rec] = o;
+    occ_fill_tile<PROJECT>(ix, uids, hits, out_offsets, out, t0, t1, qlo, qhi, lane, k, out_aligned);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4 with bulk-copy (TMA) staging.  A full tile that lies inside ONE occurrence list -- the case that carries almost all
+// bytes when lists are long -- reads a contiguous bit range of the table and writes contiguous records.  Each warp owns
+// two input buffers and one output buffer in shared memory:
+//   lane 0   cp.async.bulk global -> shared of the NEXT tile's packed words into the idle input buffer (completion on that
+//            buffer's mbarrier) before the warp touches the current tile: a load is always in flight per warp
+//   warp     waits on the current buffer's mbarrier, decodes fields out of shared memory into 12-byte records
+//   lane 0   fence.proxy.async + cp.async.bulk shared -> global of the records (bulk group); the output buffer is reused
+//            after cp.async.bulk.wait_group.read
+// No register staging, no per-lane global addresses.  A warp walks runs of OCC_TMA_RUN consecutive tiles, so the search
+// that maps a tile to its list is done once per run while the list lasts.  Tiles that straddle lists, the last partial
+// tile, and tables wider than 48 bits take occ_fill_tile().  One CTA of 12 warps per SM (175 KB of dynamic shared memory).
+// ---------------------------------------------------------------------------------------------
+constexpr u32 OCC_TMA_WARPS = 12;
+constexpr u32 OCC_TMA_TILE = 512;        // records per staged tile
+constexpr u32 OCC_TMA_RUN = 8;           // consecutive tiles a warp takes at a time
+constexpr u32 OCC_TMA_IN_BYTES = 4224;   // 512 x 64 bit (pf1 words) + alignment slack, a multiple of 128
+constexpr u32 OCC_TMA_OUT_BYTES = OCC_TMA_TILE * 12;
+constexpr u32 OCC_TMA_WARP_BYTES = 2 * OCC_TMA_IN_BYTES + OCC_TMA_OUT_BYTES;
+constexpr u32 OCC_TMA_SMEM = OCC_TMA_WARPS * OCC_TMA_WARP_BYTES + OCC_TMA_WARPS * 16 + 128;
+
+struct OccTilePlan {
+  u64 t0, t1;
+  u64 qlo, qhi;
+  const char* src;  // 16-byte aligned start of the bulk load
+  u32 bytes;        // multiple of 16
+  u32 shift;        // bit offset of the tile's first field inside the staged bytes
+  u32 tma;          // 1: staged path, 0: generic path
+  u32 valid;
+};
+struct OccListCache {  // the list the previous tile of this warp was in
+  u64 q, ob, oe, e0;
+  u32 valid;
+};
+
+template <bool PROJECT>
+__device__ __forceinline__ void occ_plan_tile(const IndexView& ix, const u32* __restrict__ uids, const Hit* __restrict__ hits, u64 n,
+                                              const u64* __restrict__ out_offsets, u64 total, u32 lane, bool stage_ok, OccListCache& c,
+                                              OccTilePlan& p) {
+  p.t1 = min(p.t0 + OCC_TMA_TILE, total);
+  p.src = nullptr;
+  p.bytes = p.shift = p.tma = 0;
+  if (c.valid && p.t0 >= c.ob && p.t1 <= c.oe) {
+    p.qlo = p.qhi = c.q;
+  } else {
+    p.qlo = warp_last_le(out_offsets, n, p.t0, lane);
+    p.qhi = warp_last_le(out_offsets, n, p.t1 - 1, lane);
+    c.valid = 0;
+    if (p.qlo == p.qhi) {
+      const u32 uid = PROJECT ? hits[p.qlo].unitig_id : uids[p.qlo];
+      c.q = p.qlo;
+      c.ob = __ldg(out_offsets + p.qlo);
+      c.oe = __ldg(out_offsets + p.qlo + 1);
+      c.e0 = packed_get(ix.contig_offsets, uid);
+      c.valid = 1;
     }
   }
+  if (stage_ok && c.valid && p.t1 - p.t0 == OCC_TMA_TILE) {
+    const u64 e_first = c.e0 + (p.t0 - c.ob);
+    const u32 wd = ix.u2pos_kind == MAZU_U2POS_DENSE ? 64u : ix.ctable_width;
+    const u64 bit0 = e_first * wd, bit1 = bit0 + (u64)OCC_TMA_TILE * wd;
+    const u64 byte0 = (bit0 >> 3) & ~15ULL, byte1 = (((bit1 + 7) >> 3) + 8 + 15) & ~15ULL;  // + 8: the decoder reads one word past a field
+    p.src = reinterpret_cast<const char*>(ix.ctable_words) + byte0;
+    p.bytes = (u32)(byte1 - byte0);
+    p.shift = (u32)(bit0 - 8 * byte0);
+    p.tma = p.bytes <= OCC_TMA_IN_BYTES ? 1u : 0u;
+  }
+}
+
+template <bool PROJECT>
+__global__ void __launch_bounds__(OCC_TMA_WARPS * 32, 1) occ_fill_tma_kernel(const __grid_constant__ IndexView ix, const u32* __restrict__ uids,
+                                                                              const Hit* __restrict__ hits, u64 n,
+                                                                              const u64* __restrict__ out_offsets, OccRec* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char occ_smem[];
+  namespace ptx = cuda::ptx;
+  const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const u64 warp = (u64)blockIdx.x * OCC_TMA_WARPS + wib, n_warps = (u64)gridDim.x * OCC_TMA_WARPS;
+  const u32 k = ix.unitigs.k;
+  const u64 total = __ldg(out_offsets + n);
+  const bool out_aligned = (reinterpret_cast<unsigned long long>(out) & 15ULL) == 0;
+  const bool stage_ok = out_aligned && (ix.u2pos_kind == MAZU_U2POS_DENSE || ix.ctable_width <= 48);
+  unsigned char* in_buf[2];
+  in_buf[0] = occ_smem + wib * OCC_TMA_WARP_BYTES;
+  in_buf[1] = in_buf[0] + OCC_TMA_IN_BYTES;
+  unsigned char* out_buf = in_buf[1] + OCC_TMA_IN_BYTES;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(occ_smem + OCC_TMA_WARPS * OCC_TMA_WARP_BYTES) + 2 * wib;
+  if (lane == 0) {
+    ptx::mbarrier_init(bar, 1);
+    ptx::mbarrier_init(bar + 1, 1);
+  }
+  ptx::fence_proxy_async();  // the initialised barriers become visible to the async proxy
+  __syncwarp();
+  u32 parity0 = 0, parity1 = 0, buf = 0;  // buf: input buffer the CURRENT tile uses
+  auto issue_load = [&](const OccTilePlan& p, u32 b) {
+    if (lane == 0) {
+      ptx::mbarrier_arrive_expect_tx(ptx::sem_release, ptx::scope_cta, ptx::space_shared, bar + b, p.bytes);
+      ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, in_buf[b], p.src, p.bytes, bar + b);
+    }
+  };
+  // this warp's tiles: runs of OCC_TMA_RUN consecutive tiles, runs strided over all warps
+  const u64 run_bytes = (u64)OCC_TMA_RUN * OCC_TMA_TILE;
+  u64 run0 = warp * run_bytes;
+  u32 j = 0;
+  auto next_t0 = [&](u64& t0) -> bool {  // successor of the tile starting at t0
+    ++j;
+    if (j == OCC_TMA_RUN) {
+      j = 0;
+      run0 += n_warps * run_bytes;
+    }
+    t0 = run0 + (u64)j * OCC_TMA_TILE;
+    return t0 < total;
+  };
+  OccListCache cache;
+  cache.valid = 0;
+  OccTilePlan cur, nxt;
+  cur.t0 = run0;
+  cur.valid = cur.t0 < total ? 1u : 0u;
+  if (!cur.valid) return;
+  occ_plan_tile<PROJECT>(ix, uids, hits, n, out_offsets, total, lane, stage_ok, cache, cur);
+  if (cur.tma) issue_load(cur, buf);
+  while (true) {
+    nxt.t0 = cur.t0;
+    nxt.valid = next_t0(nxt.t0) ? 1u : 0u;
+    nxt.tma = 0;
+    if (nxt.valid) {
+      occ_plan_tile<PROJECT>(ix, uids, hits, n, out_offsets, total, lane, stage_ok, cache, nxt);
+      if (nxt.tma) issue_load(nxt, cur.tma ? (buf ^ 1u) : buf);  // the idle input buffer
+    }
+    if (cur.tma) {
+      if (buf == 0) {
+        while (!ptx::mbarrier_try_wait_parity(bar, parity0)) {
+        }
+        parity0 ^= 1u;
+      } else {
+        while (!ptx::mbarrier_try_wait_parity(bar + 1, parity1)) {
+        }
+        parity1 ^= 1u;
+      }
+      if (lane == 0) ptx::cp_async_bulk_wait_group_read(ptx::n32_t<0>{});  // the previous store has finished reading out_buf
+      __syncwarp();
+      Hit h = hit_none(NO_MATCH);
+      if (PROJECT) h = hits[cur.qlo];
+      const u64* in64 = reinterpret_cast<const u64*>(in_buf[buf]);
+      u32* o32 = reinterpret_cast<u32*>(out_buf);
+      const bool dense = ix.u2pos_kind == MAZU_U2POS_DENSE;
+      const u32 wd = dense ? 64u : ix.ctable_width;
+      const u64 fmask = wd >= 64 ? ~0ULL : ((1ULL << wd) - 1ULL);
+#pragma unroll 4
+      for (u32 r = lane; r < OCC_TMA_TILE; r += 32) {
+        const u32 bit = cur.shift + r * wd, w = bit >> 6, sh = bit & 63u;
+        const u64 lo = in64[w], hi = in64[w + 1];
+        const u64 enc = (sh ? (lo >> sh) | (hi << (64 - sh)) : lo) & fmask;
+        OccRec oc;
+        if (dense) {  // UnitigOcc::decode_pf1 (index.rs:335-346)
+          oc.ref_id = (u32)(enc & 0xFFFFFFFFULL);
+          oc.pos = (u32)((enc >> 32) & 0x7FFFFFFFULL);
+          oc.fw = (u32)(enc >> 63);
+        } else {  // UnitigOcc::decode_piscem (spt_compact.rs:99-110)
+          oc.ref_id = (u32)(enc >> ix.ref_shift);
+          oc.pos = (u32)((enc >> 1) & ix.pos_mask);
+          oc.fw = (u32)(enc & 1ULL);
+        }
+        if (PROJECT) oc = project_occ(k, h, oc);
+        o32[3 * r] = oc.ref_id;  // stride of 3 words across lanes: conflict-free
+        o32[3 * r + 1] = oc.pos;
+        o32[3 * r + 2] = oc.fw;
+      }
+      ptx::fence_proxy_async();  // this lane's generic-proxy writes to out_buf -> visible to the async proxy (the bulk store)
+      __syncwarp();              // every lane is done with the input buffer and has written (and fenced) out_buf
+      if (lane == 0) {
+        ptx::cp_async_bulk(ptx::space_global, ptx::space_shared, reinterpret_cast<char*>(out + cur.t0), out_buf, u32(OCC_TMA_OUT_BYTES));
+        ptx::cp_async_bulk_commit_group();
+      }
+      if (nxt.tma) buf ^= 1u;  // the next staged tile was loaded into the other buffer
+    } else {
+      occ_fill_tile<PROJECT>(ix, uids, hits, out_offsets, out, cur.t0, cur.t1, cur.qlo, cur.qhi, lane, k, out_aligned);
+    }
+    if (!nxt.valid) break;
+    cur = nxt;
+  }
+  if (lane == 0) ptx::cp_async_bulk_wait_group_read(ptx::n32_t<0>{});  // shared memory must outlive the last store's reads
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
