@@ -688,8 +688,7 @@ static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu
       return e ? atoi(e) != 0 : true;
     }();
     if (use_tma) {  // bulk-copy staged fill: one CTA of 8 warps per SM, 161 KB of dynamic shared memory
-      static std::once_flag once;
-      std::call_once(once, [] {
+      std::call_once(idx->occ_attr_once, [] {
         cudaFuncSetAttribute(occ_fill_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OCC_TMA_SMEM);
         cudaFuncSetAttribute(occ_fill_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OCC_TMA_SMEM);
       });

@@ -120,6 +120,8 @@ struct mazu_index {
   // (release threshold = max), so a call after a synchronisation does not pay for fresh physical memory again
   // (measured: 1.5-4 ms on the first decode call after every sync with the default pool's threshold of 0).
   cudaMemPool_t pool = nullptr;
+  // function attributes are per device: the staged decode kernel's dynamic shared memory limit is raised once per handle
+  mutable std::once_flag occ_attr_once;
   ~mazu_index() {
     if (pool) cudaMemPoolDestroy(pool);
   }

@@ -830,6 +830,40 @@ def test_pinned_host_buffers(yeast_sshash, yeast_queries):
     assert list(cnt) == list(wcnt)
 
 
+def test_two_devices_in_one_process(yeast_queries):
+    """index replicated per device, reads sharded by batch, one host thread per device, no collective.
+    Skipped on a single-GPU box (the driver's GPU tier); run with `gpurun --gpus 2`."""
+    import threading
+    if mz.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _, ref_codes = yeast_queries
+    o = OracleIndex.dense_from_pf1(YEAST_CHR01).rebuild_k2u(1, w=15, skew=32, seed=0)
+    bases, offs = _gen.sample_reads(ref_codes, 6000, 150, seed=41, frac_ref=0.6, sub_rate=0.01, n_rate=0.001, ragged=False)
+    want, wcnt, _ = o.query_reads(bases, offs)
+    wpo, wpr = o.project_hits(want)
+    half = 3000
+    res = [None, None]
+
+    def work(dev):
+        g = mz.DenseIndex.deserialize_from_cpp(YEAST_CHR01, device=dev).rebuild_k2u(mz.K2U_SSHASH, w=15, skew_param=32, seed=0)
+        b = bases[dev * half * 150:(dev + 1) * half * 150]
+        hits, cnt, _ = g.query_reads(b, uniform_read_len=150)
+        po, pr = g.project_hits(hits)  # the staged decode kernel raises its shared-memory limit per device
+        res[dev] = (hits, cnt, po, pr)
+
+    th = [threading.Thread(target=work, args=(d,)) for d in (0, 1)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert res[0] is not None and res[1] is not None
+    got = np.concatenate([res[0][0], res[1][0]])
+    assert_hits_equal(got, want, "two devices")
+    assert [int(a) + int(b) for a, b in zip(res[0][1], res[1][1])] == [int(x) for x in wcnt]  # the final host-side gather of counters
+    pr = np.concatenate([res[0][3], res[1][3]])
+    assert np.array_equal(pr.view(np.uint32).reshape(-1, 3), np.asarray(wpr).view(np.uint32).reshape(-1, 3))
+
+
 def test_scratch_pool_is_reused_and_released(yeast_sshash, yeast_queries):
     """host-buffer calls stage through the handle's pool: results stay exact call after call, and release_scratch gives the memory back"""
     g, o = yeast_sshash
