@@ -670,6 +670,45 @@ def test_other_k_w_synthetic(k, w, skew):
     assert_hits_equal(g.k2u_batch(q), o.k2u_batch(q), "k2u_batch k=%d w=%d" % (k, w))
 
 
+def test_fuzz_small_indexes():
+    """Differential fuzzing with a fixed seed: 150 (MAZU_FUZZ_CASES) random small unitig sets (any k in [3, 32], any w <= k, skew thresholds
+    from 0 to none, a handful to a few hundred unitigs, low-complexity and repeated sequence so that canonical k-mers
+    collide, heavy buckets form and the skew index is used), queried with ragged reads with substitutions and Ns in both
+    modes, with flat k-mer batches, through the host and the device builder.  Everything must equal the oracle."""
+    rng = np.random.default_rng(20261018)
+    n_cases = int(os.environ.get("MAZU_FUZZ_CASES", "150"))
+    for case in range(n_cases):
+        k = int(rng.integers(3, 33))
+        w = int(rng.integers(1, k + 1))
+        skew = [0, 1, 2, 8, 64, NOSKEW][int(rng.integers(0, 6))]
+        n_unitigs = int(rng.integers(1, 200 if k > 10 else 12))
+        alphabet = int(rng.integers(1, 5))  # 1..4 letters: low complexity makes duplicates and heavy buckets
+        lens = k + rng.integers(0, 60, size=n_unitigs)
+        accum = np.zeros(n_unitigs + 1, dtype=np.uint64)
+        accum[1:] = np.cumsum(lens)
+        codes = rng.integers(0, alphabet, size=int(accum[-1]), dtype=np.uint8)
+        if rng.random() < 0.3 and n_unitigs > 1:  # repeat a unitig verbatim: every one of its k-mers is duplicated
+            a, b = int(accum[0]), int(accum[1])
+            ln = min(b - a, int(lens[-1]))
+            codes[int(accum[-2]):int(accum[-2]) + ln] = codes[a:a + ln]
+        us = mz.UnitigSet(k, mz.pack_2bit(codes), len(codes), accum)
+        seed = int(rng.integers(0, 1 << 30))
+        what = "case %d: k=%d w=%d skew=%s unitigs=%d alphabet=%d" % (case, k, w, skew, n_unitigs, alphabet)
+        o = OracleIndex.from_packed(k, us.useq_words, us.n_bases, accum, 1, w=w, skew=skew, seed=seed)
+        for builder in ("host", "gpu"):
+            g = mz.SSHash.from_unitig_set(us, w, skew, seed=seed, builder=builder)
+            assert g.k2u_validate_self() == o.k2u_validate_self(), what
+            bases, offs = _gen.sample_reads(codes, 60, 3 * k + 40, seed=case, frac_ref=0.7, sub_rate=0.02, n_rate=0.004, ragged=True)
+            for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+                want, wcnt, wk = o.query_reads(bases, offs, streaming=mode == mz.MODE_STREAMING, reset_per_read=True)
+                got, gcnt, gk = g.query_reads(bases, offs, mode=mode)
+                assert_hits_equal(got, want, what + " mode %d builder %s" % (mode, builder))
+                assert list(gcnt) == list(wcnt), what
+            q = np.concatenate([_gen.kmer_words_from_codes(codes, k),
+                                rng.integers(0, 1 << 62, size=300, dtype=np.uint64) & np.uint64((1 << (2 * k)) - 1 if k < 32 else 0xFFFFFFFFFFFFFFFF)])
+            assert_hits_equal(g.k2u_batch(q), o.k2u_batch(q), what + " k2u_batch builder " + builder)
+
+
 def test_palindromic_kmers_even_k():
     """even k: a palindromic k-mer equals its reverse complement; the reference reports IdentityMatch first."""
     k = 8
