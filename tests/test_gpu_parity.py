@@ -545,6 +545,62 @@ def test_decode_and_project_synthetic_high_multiplicity(kind):
     assert e.value.code == mz.ERR_NO_U2POS
 
 
+def test_fuzz_decode_tables():
+    """Differential fuzzing of the occurrence decode / projection (K4): field widths from 12 to 60 bits (beyond 48 the staged
+    kernel falls back to the generic tile path), lists from empty to thousands of entries so that tiles start and end at
+    every alignment inside, at and across list boundaries, queries with repeats and misses, both encodings."""
+    rng = np.random.default_rng(424242)
+    k = 21
+    for case in range(24):
+        U = int(rng.integers(5, 400))
+        codes, accum = _gen.synthetic_unitigs(U, 30, k, seed=1000 + case)
+        us = mz.UnitigSet(k, mz.pack_2bit(codes), len(codes), accum)
+        g = mz.SSHash.from_unitig_set(us, 11, 16)
+        o = OracleIndex.from_packed(k, us.useq_words, us.n_bases, accum, 1, w=11, skew=16)
+        kind = "dense" if case % 3 == 0 else "piscem"
+        n_refs = int(2 ** rng.integers(1, 28)) if kind == "piscem" else int(rng.integers(1, 1 << 20))
+        max_ref_len = int(2 ** rng.integers(8, 31)) if kind == "piscem" else (1 << 27)
+        mult = rng.integers(0, 4, size=U).astype(np.uint64)                       # many short (and empty) lists ...
+        heavy = rng.random(U) < 0.08
+        mult[heavy] = rng.integers(200, 3000, size=int(heavy.sum()))                # ... and a few long ones
+        offsets = np.zeros(U + 1, dtype=np.uint64)
+        offsets[1:] = np.cumsum(mult)
+        n = int(offsets[-1])
+        ref_ids = rng.integers(0, n_refs, size=n, dtype=np.uint32)
+        poss = rng.integers(0, max(1, max_ref_len - 2000), size=n, dtype=np.uint32)
+        fws = rng.integers(0, 2, size=n, dtype=np.uint8)
+        o.attach_u2pos(0 if kind == "dense" else 1, offsets, ref_ids, poss, fws, max_ref_len, n_refs)
+        off_vec = mz.PackedVec.pack(offsets)
+        if kind == "dense":
+            words = ((poss.astype(np.uint64) | (fws.astype(np.uint64) << np.uint64(31))) << np.uint64(32)) | ref_ids.astype(np.uint64)
+            g.attach_u2pos_dense(words, off_vec)
+            what = "case %d dense U=%d occs=%d" % (case, U, n)
+        else:
+            out = np.zeros(3, dtype=np.uint32)
+            assert O.lib().orc_required_num_bits(max_ref_len, n_refs, O._ptr(out)) == 0
+            pos_bits, ref_bits, total = (int(x) for x in out)
+            ref_shift, pos_mask = pos_bits + 1, (1 << pos_bits) - 1
+            enc = (ref_ids.astype(np.uint64) << np.uint64(ref_shift)) | (poss.astype(np.uint64) << np.uint64(1)) | fws.astype(np.uint64)
+            g.attach_u2pos_piscem(mz.PackedVec.pack(enc, total), ref_shift, pos_mask, off_vec)
+            what = "case %d piscem width=%d U=%d occs=%d" % (case, total, U, n)
+        q = rng.integers(0, U, size=int(rng.integers(1, 3000))).astype(np.uint32)
+        q[rng.random(len(q)) < 0.05] = mz.MISS
+        if heavy.any():  # make sure long lists are queried, several times in a row
+            hv = np.nonzero(heavy)[0].astype(np.uint32)
+            q = np.concatenate([q, np.repeat(hv[:4], 3), q[:50]])
+        a, b = g.decode_occs(q), o.decode_occs(q)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), what
+        hits = np.zeros(len(q), dtype=mz.HIT_DTYPE)
+        ulen = np.diff(accum).astype(np.uint32)
+        valid = q != mz.MISS
+        hits["unitig_id"] = q
+        hits["unitig_len"][valid] = ulen[q[valid]]
+        hits["pos"][valid] = (rng.random(int(valid.sum())) * (ulen[q[valid]] - k + 1)).astype(np.uint32)
+        hits["match"] = np.where(valid, rng.integers(1, 3, size=len(q)), 0)
+        a, b = g.project_hits(hits), o.project_hits(hits)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), what + " (projection)"
+
+
 # --------------------------------------------------------------------------------------------
 # larger synthetic index: size-independent properties + sampled oracle comparison
 # --------------------------------------------------------------------------------------------
