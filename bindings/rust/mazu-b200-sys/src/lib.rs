@@ -106,6 +106,7 @@ extern "C" {
                                              out: *mut *mut mazu_index_t) -> mazu_status_t;
     pub fn mazu_b200_index_create_pfhash_gpu(unitigs: *const mazu_unitig_set_desc_t, device: i32, out: *mut *mut mazu_index_t) -> mazu_status_t;
     pub fn mazu_b200_debug_table_digest(idx: *const mazu_index_t, which: i32, digest: *mut u64, n_bytes: *mut u64) -> mazu_status_t;
+    pub fn mazu_b200_debug_probe_key(idx: *const mazu_index_t, fw_words: *const u64, n: u64, out_block: *mut u32, stream: *mut c_void) -> mazu_status_t;
     pub fn mazu_b200_index_create_pfhash(unitigs: *const mazu_unitig_set_desc_t, device: i32, out: *mut *mut mazu_index_t) -> mazu_status_t;
     pub fn mazu_b200_index_create_pfhash_from_parts(unitigs: *const mazu_unitig_set_desc_t, mphf: *const mazu_boophf_desc_t,
                                                     pos: *const mazu_packed_vec_desc_t, device: i32, out: *mut *mut mazu_index_t) -> mazu_status_t;

@@ -145,6 +145,10 @@ mazu_status_t mazu_b200_index_create_pfhash_gpu(const mazu_unitig_set_desc_t* un
 /* test hook: FNV-1a digest and logical size of one device table (0 MPHF blocks, 1 bucket-bound blocks, 2 their exceptions,
  * 3 packed positions, 4 skew MPHF blocks, 5 skew positions, 6 MPHF fallback keys) */
 mazu_status_t mazu_b200_debug_table_digest(const mazu_index_t* idx, int32_t which, uint64_t* digest, uint64_t* n_bytes);
+/* measurement hook: level-0 MPHF block of every query's key (the minimizer for SSHash, the canonical k-mer for PFHash);
+ * device pointers.  Sorting a flat batch by this key makes its MPHF / bounds / positions accesses sequential: used by
+ * profiles/sorted_probe_experiment.py to bound what "sorted probe batches" could gain. */
+mazu_status_t mazu_b200_debug_probe_key(const mazu_index_t* idx, const uint64_t* fw_words, uint64_t n, uint32_t* out_block, void* stream);
 /* PFHash::from_unitig_set(unitigs)                                     src/kphf/pfhash.rs:40-73 */
 mazu_status_t mazu_b200_index_create_pfhash(const mazu_unitig_set_desc_t* unitigs, int32_t device, mazu_index_t** out);
 /* PFHash::from_parts(unitigs, BooPHF, pos)                             src/kphf/pfhash.rs:34-36 */

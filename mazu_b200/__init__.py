@@ -109,6 +109,7 @@ def _signatures():
         "mazu_b200_index_create_sshash_gpu": (i32, [C.POINTER(UnitigSetDesc), u32, u64, u64, i32, pp]),
         "mazu_b200_index_create_pfhash_gpu": (i32, [C.POINTER(UnitigSetDesc), i32, pp]),
         "mazu_b200_debug_table_digest": (i32, [vp, i32, vp, vp]),
+        "mazu_b200_debug_probe_key": (i32, [vp, vp, u64, vp, vp]),
         "mazu_b200_index_create_pfhash": (i32, [C.POINTER(UnitigSetDesc), i32, pp]),
         "mazu_b200_index_create_pfhash_from_parts": (i32, [C.POINTER(UnitigSetDesc), C.POINTER(BooPHFDesc), C.POINTER(PackedVecDesc), i32, pp]),
         "mazu_b200_index_rebuild_k2u": (i32, [vp, i32, u32, u64, u64, pp]),

@@ -244,6 +244,16 @@ mazu_status_t mazu_b200_index_create_pfhash_gpu(const mazu_unitig_set_desc_t* un
   });
 }
 
+mazu_status_t mazu_b200_debug_probe_key(const mazu_index_t* idx, const uint64_t* fw_words, uint64_t n, uint32_t* out_block, void* stream) {
+  return guarded([&] {
+    if (!idx || (n && (!fw_words || !out_block))) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    if (!n) return;
+    DeviceGuard g(idx->device);
+    probe_key_kernel<<<idx->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(idx->view, fw_words, n, out_block);
+    MZ_CUDA(cudaGetLastError());
+  });
+}
+
 mazu_status_t mazu_b200_debug_table_digest(const mazu_index_t* idx, int32_t which, uint64_t* digest, uint64_t* n_bytes) {
   return guarded([&] {
     if (!idx || !digest || !n_bytes || which < 0 || which >= (int)idx->tables.size()) throw Error(MAZU_ERR_INVALID_ARG, "bad argument");

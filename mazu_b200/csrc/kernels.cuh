@@ -129,6 +129,21 @@ __global__ void __launch_bounds__(256) k2u_batch_kernel(const __grid_constant__ 
   }
 }
 
+// measurement hook: level-0 MPHF block of every query's key
+__global__ void probe_key_kernel(const __grid_constant__ IndexView ix, const u64* __restrict__ fw_words, u64 n, u32* __restrict__ out_block) {
+  const u32 k = ix.unitigs.k;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u64 fw = fw_words[i] & kmer_mask(k), rc = revcomp(fw, k);
+    u64 key = fw <= rc ? fw : rc;
+    if (ix.k2u_kind == MAZU_K2U_SSHASH) key = canonical_minimizer_naive(fw, rc, k, ix.w, ix.seed).word;
+    u64 blk = 0;
+    u32 bit = 0;
+    if (ix.mphf.family == MPHF_FAMILY_NATIVE) native_slot(key, 0, ix.mphf.size[0], blk, bit);
+    else blk = mulhi64(boophf_hash64(key, BOOPHF_SEED0), ix.mphf.size[0]) / MPHF_BLOCK_BITS;
+    out_block[i] = (u32)blk;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Read kernels (K1 / K2-on-reads / K3).  A warp owns one read and walks it in chunks of QR_CHUNK
 // k-mer start positions; everything a chunk needs is staged in that warp's slice of shared memory:
