@@ -27,6 +27,7 @@ Other workloads (--workload), same JSON line:
 --impl reference times that CPU port (all host threads) on the same config and prints the same line.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -392,7 +393,22 @@ def main():
                 index.query_reads(hb, None, n_reads=e2e_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=hits, counts=h_cnt,
                                   mem=mz.MEM_HOST_IN_DEVICE_OUT)
 
-            e2e_extra = {"host_reads_in_device_records_out": (e2e_devout_step, 24,
+            # hit runs: a lossless compact form of the same records (codes + run starts); the buffers are reused across steps
+            h_codes = torch.empty(e2e_units, dtype=torch.uint8, pin_memory=True)
+            h_runs = torch.empty((max(1 << 20, e2e_units // 8), 4), dtype=torch.int32, pin_memory=True)
+            h_rro = torch.zeros(e2e_reads + 1, dtype=torch.int64, pin_memory=True)
+            runs_state = {"n_runs": 0}
+
+            def e2e_runs_step():
+                n_runs = C.c_uint64(0)
+                mz._check(mz.lib().mazu_b200_query_reads_runs(index._h, mz._any_ptr(hb), None, e2e_reads, READ_LEN, mode, None, mz._any_ptr(h_codes),
+                                                              mz._any_ptr(h_runs), h_runs.shape[0], mz._any_ptr(h_rro), C.byref(n_runs), mz._np_ptr(h_cnt)))
+                runs_state["n_runs"] = n_runs.value
+
+            e2e_extra = {"hit_runs": (e2e_runs_step, None,
+                         "mazu_b200_query_reads_runs: pinned host reads in; one code byte per k-mer slot + the 16-byte record of every run start + "
+                         "per-read run offsets out (lossless: mazu_b200_expand_hit_runs rebuilds the exact records)"),
+                         "host_reads_in_device_records_out": (e2e_devout_step, 24,
                          "MAZU_MEM_HOST_IN_DEVICE_OUT: pinned host reads in, 16-byte records stay in HBM (input of project_hits on the device), "
                          "the three counters of `kphf bench` (src/bin/kphf/main.rs:282-284) come back")}
 
@@ -511,7 +527,6 @@ def main():
         alg = (32.0 * n_q + (6 + 12) * total) / total  # bytes per occurrence: offsets pair per query + 42-bit word in + 12 B out
         kernel_name = "mazu::occ_fill_tma_kernel<false> (+ occ_lens_kernel + cub scan)"
         launches_per_step = 4
-        import ctypes as C
 
         def step():
             mz._check(mz.lib().mazu_b200_decode_occs(index._h, mz._any_ptr(d_q), n_q, mz._any_ptr(d_offs), mz._any_ptr(d_out), total, None,
@@ -652,8 +667,16 @@ def main():
             tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            if name == "hit_runs":
+                d2h = eu + 16 * runs_state["n_runs"] + 8 * (e2e_reads + 1) + 24
             e2e[name] = {"value": float(eu) * args.steps * world / float(tt.item()), "unit": unit, "h2d_bytes_per_step": e2e_bytes[0] * world,
                          "d2h_bytes_per_step": d2h * world, "api": api}
+            if name == "hit_runs":  # the expansion on the host reproduces the full records (checked on the head of the batch)
+                m = min(e2e_reads, 20000)
+                exp = mz.ModIndex.expand_hit_runs(h_codes.numpy()[: m * nk_per_read], h_runs.numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE),
+                                                  h_rro.numpy().view(np.uint64)[: m + 1], uniform_slots=nk_per_read)
+                e2e[name]["expands_to_full_records"] = bool(np.array_equal(exp.view(np.uint32).reshape(-1, 4), hits[: m * nk_per_read].cpu().numpy().view(np.uint32)))
+                e2e[name]["n_runs_per_step_per_gpu"] = runs_state["n_runs"]
 
     if rank != 0:
         if world > 1:

@@ -129,6 +129,11 @@ extern "C" {
     pub fn mazu_b200_query_reads_compact(idx: *const mazu_index_t, bases: *const u8, read_offsets: *const u64, n_reads: u64,
                                          uniform_read_len: u64, mode: i32, kmer_offsets: *mut u64, out_hits: *mut mazu_hit8_t,
                                          counts: *mut u64, mem: i32, stream: *mut c_void) -> mazu_status_t;
+    pub fn mazu_b200_query_reads_runs(idx: *const mazu_index_t, bases: *const u8, read_offsets: *const u64, n_reads: u64, uniform_read_len: u64,
+                                      mode: i32, kmer_offsets: *mut u64, out_codes: *mut u8, out_runs: *mut mazu_hit_t, cap_runs: u64,
+                                      out_read_run_offsets: *mut u64, out_n_runs: *mut u64, counts: *mut u64) -> mazu_status_t;
+    pub fn mazu_b200_expand_hit_runs(codes: *const u8, runs: *const mazu_hit_t, read_run_offsets: *const u64, kmer_offsets: *const u64,
+                                     n_reads: u64, uniform_slots: u64, out_hits: *mut mazu_hit_t) -> mazu_status_t;
     pub fn mazu_b200_count_kmer_slots(idx: *const mazu_index_t, read_offsets: *const u64, n_reads: u64, uniform_read_len: u64) -> u64;
     pub fn mazu_b200_encode_reads(idx: *const mazu_index_t, bases: *const u8, read_offsets: *const u64, n_reads: u64, uniform_read_len: u64,
                                   kmer_offsets: *const u64, out_fw: *mut u64, out_rc: *mut u64, out_mm_word: *mut u64,

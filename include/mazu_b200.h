@@ -213,6 +213,22 @@ mazu_status_t mazu_b200_query_reads(const mazu_index_t* idx, const uint8_t* base
 mazu_status_t mazu_b200_query_reads_compact(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets,
                                             uint64_t n_reads, uint64_t uniform_read_len, int32_t mode, uint64_t* kmer_offsets,
                                             mazu_hit8_t* out_hits, uint64_t* counts, int32_t mem, void* stream);
+/* same call for PCIe-bound callers (host buffers only): the hit records as RUNS.  Consecutive k-mers of a read that hit walk along
+ * one unitig, so slot s "continues" slot s-1 when both hit the same unitig with the same match type and pos differs by +1
+ * (Identity) or -1 (Twin).  Outputs:
+ *   out_codes             one byte per k-mer slot: 0 miss, 1 hit continuing the previous slot's run, 2 hit starting a run, 3 skipped
+ *   out_runs              the full mazu_hit_t of every run start, in slot order (cap_runs records; at most one per slot)
+ *   out_read_run_offsets  n_reads + 1: index in out_runs of read r's first run
+ *   out_n_runs            runs written; if it exceeds cap_runs the call fails with MAZU_ERR_INVALID_ARG and this is the capacity needed
+ * ~1.1 bytes per lookup cross PCIe instead of 16; mazu_b200_expand_hit_runs rebuilds the exact mazu_hit_t array on the host. */
+mazu_status_t mazu_b200_query_reads_runs(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets,
+                                         uint64_t n_reads, uint64_t uniform_read_len, int32_t mode, uint64_t* kmer_offsets,
+                                         uint8_t* out_codes, mazu_hit_t* out_runs, uint64_t cap_runs, uint64_t* out_read_run_offsets,
+                                         uint64_t* out_n_runs, uint64_t* counts);
+/* host-side decoder of the run format (multi-threaded, no device work): out_hits[slot] for every slot of every read.
+ * kmer_offsets may be NULL for uniform batches (uniform_slots = read_len - k + 1). */
+mazu_status_t mazu_b200_expand_hit_runs(const uint8_t* codes, const mazu_hit_t* runs, const uint64_t* read_run_offsets,
+                                        const uint64_t* kmer_offsets, uint64_t n_reads, uint64_t uniform_slots, mazu_hit_t* out_hits);
 /* number of k-mer slots query_reads writes for this batch (host arithmetic; read_offsets on host or NULL) */
 uint64_t mazu_b200_count_kmer_slots(const mazu_index_t* idx, const uint64_t* read_offsets, uint64_t n_reads,
                                     uint64_t uniform_read_len);

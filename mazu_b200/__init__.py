@@ -126,6 +126,8 @@ def _signatures():
         "mazu_b200_count_kmer_slots": (u64, [vp, vp, u64, u64]),
         "mazu_b200_query_reads": (i32, [vp, vp, vp, u64, u64, i32, vp, vp, vp, i32, vp]),
         "mazu_b200_query_reads_compact": (i32, [vp, vp, vp, u64, u64, i32, vp, vp, vp, i32, vp]),
+        "mazu_b200_query_reads_runs": (i32, [vp, vp, vp, u64, u64, i32, vp, vp, vp, u64, vp, vp, vp]),
+        "mazu_b200_expand_hit_runs": (i32, [vp, vp, vp, vp, u64, u64, vp]),
         "mazu_b200_encode_reads": (i32, [vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp]),
         "mazu_b200_decode_occs": (i32, [vp, vp, u64, vp, vp, u64, vp, i32, vp]),
         "mazu_b200_project_hits": (i32, [vp, vp, u64, vp, vp, u64, vp, i32, vp]),
@@ -420,6 +422,41 @@ class ModIndex:
         _check(fn(self._h, _any_ptr(bases), _any_ptr(read_offsets), n_reads, uniform_read_len, mode,
                   _any_ptr(kmer_offsets), _any_ptr(out_hits), _any_ptr(counts), MEM_DEVICE, _any_ptr(stream)))
         return out_hits, counts, kmer_offsets
+
+    def query_reads_runs(self, bases, read_offsets=None, uniform_read_len=0, mode=MODE_RANDOM, codes=None, runs=None, read_run_offsets=None):
+        """query_reads with the hit records as runs (host buffers): returns (codes, runs[:n_runs], read_run_offsets, counts, kmer_offsets)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        if uniform_read_len:
+            n_reads, ro = len(bases) // uniform_read_len, None
+            koffs = None
+        else:
+            ro = np.ascontiguousarray(read_offsets, dtype=np.uint64)
+            n_reads = len(ro) - 1
+            koffs = np.zeros(n_reads + 1, dtype=np.uint64)
+        n_slots = self.count_kmer_slots(ro, n_reads, uniform_read_len)
+        codes = np.empty(n_slots, dtype=np.uint8) if codes is None else codes
+        rro = np.zeros(n_reads + 1, dtype=np.uint64) if read_run_offsets is None else read_run_offsets
+        cnt = np.zeros(3, dtype=np.uint64)
+        n_runs = C.c_uint64(0)
+        if runs is None:
+            runs = np.empty(max(1024, n_slots // 16), dtype=HIT_DTYPE)
+        while True:
+            rc = lib().mazu_b200_query_reads_runs(self._h, _np_ptr(bases), _np_ptr(ro), n_reads, uniform_read_len, mode, _np_ptr(koffs), _any_ptr(codes),
+                                                  _any_ptr(runs), len(runs), _any_ptr(rro), C.byref(n_runs), _np_ptr(cnt))
+            if rc != 0 and n_runs.value > len(runs):  # capacity: the call reports what it needs
+                runs = np.empty(n_runs.value, dtype=HIT_DTYPE)
+                continue
+            _check(rc)
+            break
+        return codes, runs[: n_runs.value], rro, cnt, koffs
+
+    @staticmethod
+    def expand_hit_runs(codes, runs, read_run_offsets, kmer_offsets=None, uniform_slots=0, out=None):
+        n_reads = len(read_run_offsets) - 1
+        out = np.empty(len(codes), dtype=HIT_DTYPE) if out is None else out
+        _check(lib().mazu_b200_expand_hit_runs(_any_ptr(codes), _any_ptr(runs), _any_ptr(read_run_offsets), _np_ptr(kmer_offsets), n_reads, uniform_slots,
+                                               _any_ptr(out)))
+        return out
 
     def encode_reads(self, bases, read_offsets, n_reads, uniform_read_len, kmer_offsets, out_fw, out_rc, out_mm, out_off, out_valid,
                      stream=None):

@@ -468,12 +468,23 @@ uint64_t mazu_b200_count_kmer_slots(const mazu_index_t* idx, const uint64_t* rea
   return acc;
 }
 
+// hit-run output of mazu_b200_query_reads_runs (host buffers)
+struct RunsOut {
+  uint8_t* codes;
+  mazu_hit_t* runs;
+  uint64_t cap_runs;
+  uint64_t* read_run_offsets;  // n_reads + 1
+  uint64_t n_runs = 0;
+};
+
 static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
                                       uint64_t uniform_read_len, int32_t mode, uint64_t* kmer_offsets, void* out_hits, uint32_t compact,
-                                      uint64_t* counts, int32_t mem, void* stream) {
+                                      uint64_t* counts, int32_t mem, void* stream, RunsOut* ro = nullptr) {
   const u64 rec = compact ? 8 : 16;
   return guarded([&] {
     if (!idx) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    if (ro && (mem != MAZU_MEM_HOST || compact || out_hits)) throw Error(MAZU_ERR_INVALID_ARG, "hit runs are a host-buffer output");
+    if (ro && n_reads && (!ro->codes || !ro->read_run_offsets || (ro->cap_runs && !ro->runs))) throw Error(MAZU_ERR_INVALID_ARG, "null run buffers");
     if (mode != MAZU_MODE_RANDOM && mode != MAZU_MODE_STREAMING) throw Error(MAZU_ERR_INVALID_ARG, "unknown query mode");
     if (n_reads && !bases) throw Error(MAZU_ERR_INVALID_ARG, "null bases");
     if (n_reads && !uniform_read_len && !read_offsets) throw Error(MAZU_ERR_INVALID_ARG, "read_offsets is required for ragged reads");
@@ -563,8 +574,73 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
         d_ro[b] = scratch.get((max_reads + 1) * 8);
         d_ko[b] = scratch.get((max_reads + 1) * 8);
       }
-      if (out_hits && !dev_out) d_hits[b] = scratch.get(max_slots * rec + 16);
+      if ((out_hits && !dev_out) || ro) d_hits[b] = scratch.get(max_slots * rec + 16);
     }
+    // run buffers the device can address (pinned host memory: torch pin_memory, mazu_b200_alloc_pinned, cudaHostAlloc) take the
+    // sync-free path: run records are stored straight into them at a device-side running base; otherwise the host waits for each
+    // chunk's total to place its runs (below)
+    Hit* runs_dev = nullptr;
+    u64* d_base = nullptr;
+    u64* d_total_copy[2] = {nullptr, nullptr};
+    cudaEvent_t base_ev = nullptr;
+    struct EvGuard {
+      cudaEvent_t* e;
+      ~EvGuard() {
+        if (*e) cudaEventDestroy(*e);
+      }
+    } ev_guard{&base_ev};
+    if (ro && ro->cap_runs) {
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, ro->runs) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) runs_dev = (Hit*)at.devicePointer;
+      else cudaGetLastError();
+    }
+    if (runs_dev) {
+      d_base = (u64*)scratch.get(8);
+      MZ_CUDA(cudaMemsetAsync(d_base, 0, 8, sp.s[0]));
+      d_total_copy[0] = (u64*)scratch.get(8);
+      d_total_copy[1] = (u64*)scratch.get(8);
+      MZ_CUDA(cudaEventCreateWithFlags(&base_ev, cudaEventDisableTiming));
+      MZ_CUDA(cudaEventRecord(base_ev, sp.s[0]));
+    }
+    // hit runs: codes, per-read run counts / offsets and (worst case: every slot starts a run) the run records, per buffer;
+    // the offsets come back through a small pinned array because the host needs each chunk's total to place its runs
+    void *d_codes[2] = {nullptr, nullptr}, *d_rc[2] = {nullptr, nullptr}, *d_rro[2] = {nullptr, nullptr}, *d_runs[2] = {nullptr, nullptr};
+    u64* h_rro[2] = {nullptr, nullptr};
+    struct PinnedPair {
+      u64** p;
+      ~PinnedPair() {
+        for (int i = 0; i < 2; ++i)
+          if (p[i]) cudaFreeHost(p[i]);
+      }
+    } pinned_guard{h_rro};
+    if (ro) {
+      for (int b = 0; b < 2; ++b) {
+        d_codes[b] = scratch.get(max_slots + 16);
+        d_rc[b] = scratch.get((max_reads + 1) * 8);
+        d_rro[b] = scratch.get((max_reads + 1) * 8);
+        if (!runs_dev) {
+          d_runs[b] = scratch.get(max_slots * 16 + 16);
+          MZ_CUDA(cudaHostAlloc((void**)&h_rro[b], (max_reads + 1) * 8, cudaHostAllocDefault));
+        }
+      }
+      ro->n_runs = 0;
+      if (n_reads == 0) ro->read_run_offsets[0] = 0;
+    }
+    const u64 uniform_slots = uniform_read_len >= k ? uniform_read_len - k + 1 : 0;
+    // second half of a chunk in hit-run mode: wait for its offsets, place its runs, publish its offsets
+    auto finish_runs = [&](size_t c, int bb) {
+      const u64 r0 = cuts[c], nr = cuts[c + 1] - cuts[c];
+      MZ_CUDA(cudaStreamSynchronize(sp.s[bb]));
+      const u64 total = h_rro[bb][nr];
+      if (ro->n_runs + total > ro->cap_runs) {
+        ro->n_runs += total;  // keep counting so the caller learns the capacity it needs
+      } else {
+        if (total) MZ_CUDA(cudaMemcpyAsync(ro->runs + ro->n_runs, d_runs[bb], total * 16, cudaMemcpyDeviceToHost, sp.s[bb]));
+        for (u64 i = 0; i < nr; ++i) ro->read_run_offsets[r0 + i] = ro->n_runs + h_rro[bb][i];
+        ro->n_runs += total;
+        ro->read_run_offsets[r0 + nr] = ro->n_runs;
+      }
+    };
     scratch.publish(sp.s[1]);
     int b = 0;
     for (size_t c = 0; c + 1 < cuts.size(); ++c, b ^= 1) {
@@ -585,9 +661,43 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       const u8* dbases = (const u8*)d_bases[b] - (uniform_read_len ? 0 : b0);
       void* dh = nullptr;
       if (out_hits && dev_out) dh = (char*)out_hits + (uniform_read_len ? s0 * rec : 0);
-      else if (out_hits) dh = (char*)d_hits[b] - (uniform_read_len ? 0 : s0 * rec);
+      else if (out_hits || ro) dh = (char*)d_hits[b] - (uniform_read_len ? 0 : s0 * rec);
       launch_query_reads(idx, dbases, dro, r1 - r0, uniform_read_len, mode, dko, dh, compact, (u64*)d_counts, s);
       if (out_hits && !dev_out && ns) MZ_CUDA(cudaMemcpyAsync((char*)out_hits + s0 * rec, d_hits[b], ns * rec, cudaMemcpyDeviceToHost, s));
+      if (ro) {
+        const u64 nr = r1 - r0;
+        const Hit* hh = (const Hit*)dh;
+        u8* cc = (u8*)d_codes[b] - (uniform_read_len ? 0 : s0);
+        MZ_CUDA(cudaMemsetAsync(d_rc[b], 0, (nr + 1) * 8, s));
+        const int grid = (int)std::min<u64>((nr + 7) / 8, (u64)idx->sm_count * 8);
+        hit_run_codes_kernel<<<grid, 256, 0, s>>>(hh, dko, nr, uniform_slots, cc, (u64*)d_rc[b]);
+        MZ_CUDA(cudaGetLastError());
+        device_exclusive_scan((const u64*)d_rc[b], (u64*)d_rro[b], nr, idx->pool, s);
+        if (runs_dev) {
+          // the running base lives on the device: this chunk reads it after the previous chunk (other stream) has advanced it
+          MZ_CUDA(cudaMemcpyAsync(d_total_copy[b], (u64*)d_rro[b] + nr, 8, cudaMemcpyDeviceToDevice, s));  // the fill kernel overwrites offsets in place
+          MZ_CUDA(cudaStreamWaitEvent(s, base_ev, 0));
+          hit_run_fill_global_kernel<<<grid, 256, 0, s>>>(hh, cc, dko, nr, uniform_slots, (u64*)d_rro[b], d_base, ro->cap_runs, runs_dev);
+          hit_run_advance_kernel<<<1, 32, 0, s>>>(d_base, d_total_copy[b]);
+          MZ_CUDA(cudaGetLastError());
+          MZ_CUDA(cudaEventRecord(base_ev, s));
+          if (ns) MZ_CUDA(cudaMemcpyAsync(ro->codes + s0, d_codes[b], ns, cudaMemcpyDeviceToHost, s));
+          if (nr) MZ_CUDA(cudaMemcpyAsync(ro->read_run_offsets + r0, d_rro[b], nr * 8, cudaMemcpyDeviceToHost, s));
+        } else {
+          hit_run_fill_kernel<<<grid, 256, 0, s>>>(hh, cc, dko, nr, uniform_slots, (const u64*)d_rro[b], 0, max_slots, (Hit*)d_runs[b]);
+          MZ_CUDA(cudaGetLastError());
+          if (ns) MZ_CUDA(cudaMemcpyAsync(ro->codes + s0, d_codes[b], ns, cudaMemcpyDeviceToHost, s));
+          MZ_CUDA(cudaMemcpyAsync(h_rro[b], d_rro[b], (nr + 1) * 8, cudaMemcpyDeviceToHost, s));
+          if (c > 0) finish_runs(c - 1, b ^ 1);  // the previous chunk finishes while this one runs
+        }
+      }
+    }
+    if (ro && !runs_dev && cuts.size() > 1) finish_runs(cuts.size() - 2, b ^ 1);
+    if (ro && runs_dev) {
+      MZ_CUDA(cudaStreamSynchronize(sp.s[0]));
+      MZ_CUDA(cudaStreamSynchronize(sp.s[1]));
+      MZ_CUDA(cudaMemcpy(&ro->n_runs, d_base, 8, cudaMemcpyDeviceToHost));
+      ro->read_run_offsets[n_reads] = ro->n_runs;
     }
     MZ_CUDA(cudaStreamSynchronize(sp.s[1]));
     if (counts) MZ_CUDA(cudaMemcpyAsync(counts, d_counts, 24, cudaMemcpyDeviceToHost, sp.s[0]));
@@ -599,6 +709,56 @@ mazu_status_t mazu_b200_query_reads(const mazu_index_t* idx, const uint8_t* base
                                     uint64_t uniform_read_len, int32_t mode, uint64_t* kmer_offsets, mazu_hit_t* out_hits,
                                     uint64_t* counts, int32_t mem, void* stream) {
   return query_reads_impl(idx, bases, read_offsets, n_reads, uniform_read_len, mode, kmer_offsets, out_hits, 0, counts, mem, stream);
+}
+
+mazu_status_t mazu_b200_query_reads_runs(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                                         uint64_t uniform_read_len, int32_t mode, uint64_t* kmer_offsets, uint8_t* out_codes,
+                                         mazu_hit_t* out_runs, uint64_t cap_runs, uint64_t* out_read_run_offsets, uint64_t* out_n_runs,
+                                         uint64_t* counts) {
+  RunsOut ro{out_codes, out_runs, cap_runs, out_read_run_offsets};
+  mazu_status_t rc = query_reads_impl(idx, bases, read_offsets, n_reads, uniform_read_len, mode, kmer_offsets, nullptr, 0, counts, MAZU_MEM_HOST,
+                                      nullptr, &ro);
+  if (out_n_runs) *out_n_runs = ro.n_runs;
+  if (rc == MAZU_OK && ro.n_runs > cap_runs) {
+    g_err = "run capacity too small: need " + std::to_string(ro.n_runs) + " records";
+    return MAZU_ERR_INVALID_ARG;
+  }
+  return rc;
+}
+
+mazu_status_t mazu_b200_expand_hit_runs(const uint8_t* codes, const mazu_hit_t* runs, const uint64_t* read_run_offsets,
+                                        const uint64_t* kmer_offsets, uint64_t n_reads, uint64_t uniform_slots, mazu_hit_t* out_hits) {
+  return guarded([&] {
+    if (n_reads && (!codes || !read_run_offsets || !out_hits)) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    const unsigned T = host_threads();
+    parallel_ranges(n_reads, T, [&](unsigned, u64 lo, u64 hi) {
+      for (u64 r = lo; r < hi; ++r) {
+        const u64 s0 = kmer_offsets ? kmer_offsets[r] : r * uniform_slots;
+        const u64 ns = kmer_offsets ? kmer_offsets[r + 1] - s0 : uniform_slots;
+        u64 ri = read_run_offsets[r];
+        mazu_hit_t prev{~0u, ~0u, ~0u, MAZU_NO_MATCH};
+        for (u64 i = 0; i < ns; ++i) {
+          mazu_hit_t h{~0u, ~0u, ~0u, MAZU_NO_MATCH};
+          switch (codes[s0 + i]) {
+            case 1:  // continues the previous slot's run
+              h = prev;
+              h.pos = prev.match == MAZU_IDENTITY_MATCH ? prev.pos + 1u : prev.pos - 1u;
+              break;
+            case 2:
+              h = runs[ri++];
+              break;
+            case 3:
+              h.match = MAZU_SKIPPED;
+              break;
+            default:
+              break;
+          }
+          out_hits[s0 + i] = h;
+          prev = h;
+        }
+      }
+    });
+  });
 }
 
 mazu_status_t mazu_b200_query_reads_compact(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,

@@ -721,6 +721,110 @@ __global__ void kmer_counts_kernel(const u64* __restrict__ read_offsets, u64 n_r
 }
 
 // ---------------------------------------------------------------------------------------------
+// Hit runs: a lossless, compact form of a read batch's hit records for PCIe-bound callers.
+// Consecutive k-mers of a read that hit walk along one unitig, so their records are redundant: slot s continues the
+// run of slot s-1 when both are hits on the same unitig with the same match type and pos differs by +1 (Identity: the
+// read runs along the unitig) or -1 (Twin: against it).  Output: one code byte per k-mer slot
+//   0 miss | 1 hit, continues the previous slot's run | 2 hit, starts a run (its 16-byte record is in `runs`) | 3 skipped window
+// plus the run records in slot order and read_run_offsets[r] = index of read r's first run.  Typical volume: ~1.1 bytes
+// per lookup instead of 16.  mazu_b200_expand_hit_runs() rebuilds the exact records.
+// ---------------------------------------------------------------------------------------------
+enum : u32 { RUN_MISS = 0, RUN_CONT = 1, RUN_START = 2, RUN_SKIPPED = 3 };
+__device__ __forceinline__ u32 run_code_of(const Hit& h, const Hit& prev, bool has_prev) {
+  if (h.match == SKIPPED) return RUN_SKIPPED;
+  if (h.match != IDENTITY_MATCH && h.match != TWIN_MATCH) return RUN_MISS;
+  const bool cont = has_prev && prev.match == h.match && prev.unitig_id == h.unitig_id &&
+                    h.pos == (h.match == IDENTITY_MATCH ? prev.pos + 1u : prev.pos - 1u);
+  return cont ? RUN_CONT : RUN_START;
+}
+// pass 1: codes for every slot, run count per read (a warp per read)
+__global__ void __launch_bounds__(256) hit_run_codes_kernel(const Hit* __restrict__ hits, const u64* __restrict__ kmer_offsets, u64 n_reads,
+                                                            u64 uniform_slots, u8* __restrict__ codes, u64* __restrict__ run_counts) {
+  const u32 lane = threadIdx.x & 31;
+  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  for (u64 r = warp; r < n_reads; r += n_warps) {
+    const u64 s0 = kmer_offsets ? kmer_offsets[r] : r * uniform_slots;
+    const u64 ns = kmer_offsets ? kmer_offsets[r + 1] - s0 : uniform_slots;
+    Hit carry = hit_none(NO_MATCH);
+    u32 n_runs = 0;
+    for (u64 b = 0; b < ns; b += 32) {
+      const u64 i = b + lane;
+      Hit h = hit_none(NO_MATCH);
+      if (i < ns) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(hits + s0 + i));
+        h = Hit{v.x, v.y, v.z, v.w};
+      }
+      Hit p;
+      p.unitig_id = __shfl_up_sync(0xffffffffu, h.unitig_id, 1);
+      p.unitig_len = 0;
+      p.pos = __shfl_up_sync(0xffffffffu, h.pos, 1);
+      p.match = __shfl_up_sync(0xffffffffu, h.match, 1);
+      if (lane == 0) p = carry;
+      const u32 c = run_code_of(h, p, b + lane > 0);
+      if (i < ns) codes[s0 + i] = (u8)c;
+      n_runs += __popc(__ballot_sync(0xffffffffu, i < ns && c == RUN_START));
+      carry.unitig_id = __shfl_sync(0xffffffffu, h.unitig_id, 31);
+      carry.pos = __shfl_sync(0xffffffffu, h.pos, 31);
+      carry.match = __shfl_sync(0xffffffffu, h.match, 31);
+    }
+    if (lane == 0) run_counts[r] = n_runs;
+  }
+}
+// pass 2: the records of the run starts, in slot order, at read_run_offsets[r] + rank
+__global__ void __launch_bounds__(256) hit_run_fill_kernel(const Hit* __restrict__ hits, const u8* __restrict__ codes,
+                                                           const u64* __restrict__ kmer_offsets, u64 n_reads, u64 uniform_slots,
+                                                           const u64* __restrict__ read_run_offsets, u64 run_base, u64 cap, Hit* __restrict__ runs) {
+  const u32 lane = threadIdx.x & 31;
+  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  for (u64 r = warp; r < n_reads; r += n_warps) {
+    const u64 s0 = kmer_offsets ? kmer_offsets[r] : r * uniform_slots;
+    const u64 ns = kmer_offsets ? kmer_offsets[r + 1] - s0 : uniform_slots;
+    u64 o = read_run_offsets[r] - run_base;
+    for (u64 b = 0; b < ns; b += 32) {
+      const u64 i = b + lane;
+      const bool start = i < ns && codes[s0 + i] == RUN_START;
+      const u32 m = __ballot_sync(0xffffffffu, start);
+      if (start) {
+        const u64 dst = o + __popc(m & ((1u << lane) - 1u));
+        if (dst < cap) store_hit(runs + dst, hits[s0 + i]);
+      }
+      o += __popc(m);
+    }
+  }
+}
+
+// sync-free variant of pass 2 for run buffers the device can address (pinned host memory): records go straight to
+// runs[*base + offset], the chunk's offsets are globalised in place, and one thread advances *base afterwards
+__global__ void __launch_bounds__(256) hit_run_fill_global_kernel(const Hit* __restrict__ hits, const u8* __restrict__ codes,
+                                                                  const u64* __restrict__ kmer_offsets, u64 n_reads, u64 uniform_slots,
+                                                                  u64* __restrict__ read_run_offsets, const u64* __restrict__ base_ptr, u64 cap,
+                                                                  Hit* __restrict__ runs) {
+  const u32 lane = threadIdx.x & 31;
+  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  const u64 base = *base_ptr;
+  for (u64 r = warp; r < n_reads; r += n_warps) {
+    const u64 s0 = kmer_offsets ? kmer_offsets[r] : r * uniform_slots;
+    const u64 ns = kmer_offsets ? kmer_offsets[r + 1] - s0 : uniform_slots;
+    u64 o = read_run_offsets[r] + base;
+    __syncwarp();
+    if (lane == 0) read_run_offsets[r] = o;  // becomes the global offset the host receives
+    for (u64 b = 0; b < ns; b += 32) {
+      const u64 i = b + lane;
+      const bool start = i < ns && codes[s0 + i] == RUN_START;
+      const u32 m = __ballot_sync(0xffffffffu, start);
+      if (start) {
+        const u64 dst = o + __popc(m & ((1u << lane) - 1u));
+        if (dst < cap) store_hit(runs + dst, hits[s0 + i]);
+      }
+      o += __popc(m);
+    }
+  }
+}
+__global__ void hit_run_advance_kernel(u64* __restrict__ base_ptr, const u64* __restrict__ chunk_total) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *base_ptr += *chunk_total;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K4: U2Pos decode / projection
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void occ_range(const IndexView& ix, u32 uid, u64& s, u64& e) {

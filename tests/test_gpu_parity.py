@@ -910,6 +910,45 @@ def test_c_example_runs(tmp_path):
     assert "projected reference positions: 6" in r.stdout
 
 
+@pytest.mark.parametrize("ragged", [True, False])
+def test_hit_runs_expand_to_the_exact_records(yeast_dense, yeast_sshash, yeast_queries, ragged):
+    """mazu_b200_query_reads_runs + mazu_b200_expand_hit_runs == mazu_b200_query_reads == oracle, record for record; the run
+    format is far smaller than the records it stands for; a too-small run buffer reports the capacity it needs."""
+    import ctypes as C
+    _, ref_codes = yeast_queries
+    bases, offs = _gen.sample_reads(ref_codes, 5000, 170, seed=51, frac_ref=0.7, sub_rate=0.01, n_rate=0.002, ragged=ragged)
+    for g, o in (yeast_sshash, yeast_dense):
+        for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+            want, wcnt, wk = o.query_reads(bases, offs, streaming=mode == mz.MODE_STREAMING, reset_per_read=True)
+            kw = dict(read_offsets=offs) if ragged else dict(uniform_read_len=170)
+            codes, runs, rro, cnt, koffs = g.query_reads_runs(bases, mode=mode, **kw)
+            assert list(cnt) == list(wcnt)
+            assert len(codes) == len(want) and rro[-1] == len(runs) and rro[0] == 0 and np.all(np.diff(rro.astype(np.int64)) >= 0)
+            if ragged:
+                assert np.array_equal(koffs, wk)
+                got = mz.ModIndex.expand_hit_runs(codes, runs, rro, kmer_offsets=koffs)
+            else:
+                got = mz.ModIndex.expand_hit_runs(codes, runs, rro, uniform_slots=170 - g.k + 1)
+            assert_hits_equal(got, want, "expanded runs, mode %d" % mode)
+            n_hit = int(((want["match"] == mz.IDENTITY_MATCH) | (want["match"] == mz.TWIN_MATCH)).sum())
+            assert int((codes == 2).sum()) == len(runs) and int(((codes == 1) | (codes == 2)).sum()) == n_hit
+            assert len(codes) + 16 * len(runs) + 8 * len(rro) < 0.2 * 16 * len(want)  # the point of the format
+            # pinned (device-addressable) run buffer: the sync-free path stores the records straight into it -- same bytes
+            pr = mz.PinnedArray((len(runs) + 7,), mz.HIT_DTYPE)
+            codes2, runs2, rro2, cnt2, _ = g.query_reads_runs(bases, mode=mode, runs=pr.array, **kw)
+            assert np.array_equal(codes2, codes) and np.array_equal(rro2, rro) and list(cnt2) == list(cnt)
+            assert np.array_equal(runs2.view(np.uint32), runs.view(np.uint32))
+    # capacity: one run record is not enough; the call says how many it needs
+    g, _ = yeast_sshash
+    n_reads = len(offs) - 1
+    n_runs = C.c_uint64(0)
+    codes = np.empty(g.count_kmer_slots(offs, n_reads, 0), dtype=np.uint8)
+    rc = mz.lib().mazu_b200_query_reads_runs(g._h, mz._np_ptr(bases), mz._np_ptr(offs), n_reads, 0, mz.MODE_RANDOM, None, mz._any_ptr(codes),
+                                             mz._any_ptr(np.empty(1, dtype=mz.HIT_DTYPE)), 1, mz._any_ptr(np.zeros(n_reads + 1, dtype=np.uint64)),
+                                             C.byref(n_runs), None)
+    assert rc == -7 and n_runs.value > 1
+
+
 def test_pinned_host_buffers(yeast_sshash, yeast_queries):
     """mazu_b200_alloc_pinned: page-locked buffers for callers that do not link CUDA; same answers as pageable numpy arrays"""
     g, o = yeast_sshash
