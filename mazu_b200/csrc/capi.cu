@@ -563,12 +563,33 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       max_slots = std::max(max_slots, slot_off(cuts[c + 1]) - slot_off(cuts[c]));
       max_reads = std::max(max_reads, cuts[c + 1] - cuts[c]);
     }
+    // run buffers the device can address (pinned host memory: torch pin_memory, mazu_b200_alloc_pinned, cudaHostAlloc) take the
+    // sync-free path: run records are published into them at a device-side running base; otherwise the host waits for each
+    // chunk's total to place its runs (below)
+    Hit* runs_dev = nullptr;
+    if (ro && ro->cap_runs) {
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, ro->runs) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) runs_dev = (Hit*)at.devicePointer;
+      else cudaGetLastError();
+    }
+    // two buffers / streams alternate; the sync-free run path uses three, because its per-chunk chain (H2D, lookups, encode, two
+    // D2H copies) is 2.3x as long as its compute and two streams leave the SMs idle a third of the time
+    const int NB = runs_dev ? 3 : 2;
     StreamPair sp;
+    struct ExtraStream {
+      cudaStream_t s = nullptr;
+      ~ExtraStream() {
+        if (s) cudaStreamDestroy(s);
+      }
+    } extra;
+    if (NB == 3) MZ_CUDA(cudaStreamCreateWithFlags(&extra.s, cudaStreamNonBlocking));
+    cudaStream_t st[3] = {sp.s[0], sp.s[1], extra.s};
     PoolScratch scratch(idx->pool, sp.s[0]);
-    void *d_bases[2] = {nullptr, nullptr}, *d_ro[2] = {nullptr, nullptr}, *d_ko[2] = {nullptr, nullptr}, *d_hits[2] = {nullptr, nullptr};
+    void *d_bases[3] = {nullptr, nullptr, nullptr}, *d_ro[3] = {nullptr, nullptr, nullptr}, *d_ko[3] = {nullptr, nullptr, nullptr},
+         *d_hits[3] = {nullptr, nullptr, nullptr};
     void* d_counts = scratch.get(3 * 8);
     MZ_CUDA(cudaMemsetAsync(d_counts, 0, 24, sp.s[0]));
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NB; ++b) {
       d_bases[b] = scratch.get(max_bases + 16);
       if (!uniform_read_len) {
         d_ro[b] = scratch.get((max_reads + 1) * 8);
@@ -576,12 +597,8 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       }
       if ((out_hits && !dev_out) || ro) d_hits[b] = scratch.get(max_slots * rec + 16);
     }
-    // run buffers the device can address (pinned host memory: torch pin_memory, mazu_b200_alloc_pinned, cudaHostAlloc) take the
-    // sync-free path: run records are stored straight into them at a device-side running base; otherwise the host waits for each
-    // chunk's total to place its runs (below)
-    Hit* runs_dev = nullptr;
     u64* d_base = nullptr;
-    u64* d_total_copy[2] = {nullptr, nullptr};
+    u64* d_total_copy[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t base_ev = nullptr;
     struct EvGuard {
       cudaEvent_t* e;
@@ -589,22 +606,17 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
         if (*e) cudaEventDestroy(*e);
       }
     } ev_guard{&base_ev};
-    if (ro && ro->cap_runs) {
-      cudaPointerAttributes at{};
-      if (cudaPointerGetAttributes(&at, ro->runs) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) runs_dev = (Hit*)at.devicePointer;
-      else cudaGetLastError();
-    }
     if (runs_dev) {
       d_base = (u64*)scratch.get(8);
       MZ_CUDA(cudaMemsetAsync(d_base, 0, 8, sp.s[0]));
-      d_total_copy[0] = (u64*)scratch.get(8);
-      d_total_copy[1] = (u64*)scratch.get(8);
+      for (int b = 0; b < NB; ++b) d_total_copy[b] = (u64*)scratch.get(8);
       MZ_CUDA(cudaEventCreateWithFlags(&base_ev, cudaEventDisableTiming));
       MZ_CUDA(cudaEventRecord(base_ev, sp.s[0]));
     }
     // hit runs: codes, per-read run counts / offsets and (worst case: every slot starts a run) the run records, per buffer;
     // the offsets come back through a small pinned array because the host needs each chunk's total to place its runs
-    void *d_codes[2] = {nullptr, nullptr}, *d_rc[2] = {nullptr, nullptr}, *d_rro[2] = {nullptr, nullptr}, *d_runs[2] = {nullptr, nullptr};
+    void *d_codes[3] = {nullptr, nullptr, nullptr}, *d_rc[3] = {nullptr, nullptr, nullptr}, *d_rro[3] = {nullptr, nullptr, nullptr},
+         *d_runs[3] = {nullptr, nullptr, nullptr};
     u64* h_rro[2] = {nullptr, nullptr};
     struct PinnedPair {
       u64** p;
@@ -614,14 +626,12 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       }
     } pinned_guard{h_rro};
     if (ro) {
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < NB; ++b) {
         d_codes[b] = scratch.get(max_slots + 16);
         d_rc[b] = scratch.get((max_reads + 1) * 8);
         d_rro[b] = scratch.get((max_reads + 1) * 8);
-        if (!runs_dev) {
-          d_runs[b] = scratch.get(max_slots * 16 + 16);
-          MZ_CUDA(cudaHostAlloc((void**)&h_rro[b], (max_reads + 1) * 8, cudaHostAllocDefault));
-        }
+        d_runs[b] = scratch.get(max_slots * 16 + 16);
+        if (!runs_dev) MZ_CUDA(cudaHostAlloc((void**)&h_rro[b], (max_reads + 1) * 8, cudaHostAllocDefault));
       }
       ro->n_runs = 0;
       if (n_reads == 0) ro->read_run_offsets[0] = 0;
@@ -642,12 +652,13 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       }
     };
     scratch.publish(sp.s[1]);
+    if (NB == 3) scratch.publish(extra.s);
     int b = 0;
-    for (size_t c = 0; c + 1 < cuts.size(); ++c, b ^= 1) {
+    for (size_t c = 0; c + 1 < cuts.size(); ++c, b = (b + 1) % NB) {
       u64 r0 = cuts[c], r1 = cuts[c + 1];
       u64 b0 = base_off(r0), nb = base_off(r1) - b0;
       u64 s0 = slot_off(r0), ns = slot_off(r1) - s0;
-      cudaStream_t s = sp.s[b];
+      cudaStream_t s = st[b];
       MZ_CUDA(cudaMemcpyAsync(d_bases[b], bases + b0, nb, cudaMemcpyHostToDevice, s));
       const u64* dro = nullptr;
       const u64* dko = nullptr;
@@ -677,7 +688,9 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
           // the running base lives on the device: this chunk reads it after the previous chunk (other stream) has advanced it
           MZ_CUDA(cudaMemcpyAsync(d_total_copy[b], (u64*)d_rro[b] + nr, 8, cudaMemcpyDeviceToDevice, s));  // the fill kernel overwrites offsets in place
           MZ_CUDA(cudaStreamWaitEvent(s, base_ev, 0));
-          hit_run_fill_global_kernel<<<grid, 256, 0, s>>>(hh, cc, dko, nr, uniform_slots, (u64*)d_rro[b], d_base, ro->cap_runs, runs_dev);
+          hit_run_fill_kernel<<<grid, 256, 0, s>>>(hh, cc, dko, nr, uniform_slots, (const u64*)d_rro[b], 0, max_slots, (Hit*)d_runs[b]);
+          hit_run_publish_kernel<<<idx->sm_count * 2, 256, 0, s>>>((u64*)d_rro[b], nr, (const Hit*)d_runs[b], d_total_copy[b], d_base, ro->cap_runs,
+                                                                   runs_dev);
           hit_run_advance_kernel<<<1, 32, 0, s>>>(d_base, d_total_copy[b]);
           MZ_CUDA(cudaGetLastError());
           MZ_CUDA(cudaEventRecord(base_ev, s));
@@ -696,6 +709,7 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
     if (ro && runs_dev) {
       MZ_CUDA(cudaStreamSynchronize(sp.s[0]));
       MZ_CUDA(cudaStreamSynchronize(sp.s[1]));
+      if (extra.s) MZ_CUDA(cudaStreamSynchronize(extra.s));
       MZ_CUDA(cudaMemcpy(&ro->n_runs, d_base, 8, cudaMemcpyDeviceToHost));
       ro->read_run_offsets[n_reads] = ro->n_runs;
     }

@@ -820,6 +820,18 @@ __global__ void __launch_bounds__(256) hit_run_fill_global_kernel(const Hit* __r
     }
   }
 }
+// sync-free publication of a chunk's runs: offsets become global, the chunk-local run records are copied into the caller's
+// (device-addressable, usually pinned host) buffer with fully coalesced 16-byte stores -- writing them one record at a time
+// from the fill kernel crossed PCIe as tiny transactions
+__global__ void __launch_bounds__(256) hit_run_publish_kernel(u64* __restrict__ read_run_offsets, u64 n_reads, const Hit* __restrict__ local_runs,
+                                                              const u64* __restrict__ chunk_total, const u64* __restrict__ base_ptr, u64 cap,
+                                                              Hit* __restrict__ runs) {
+  const u64 base = *base_ptr, total = *chunk_total;
+  const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x, nt = (u64)gridDim.x * blockDim.x;
+  for (u64 r = tid; r < n_reads; r += nt) read_run_offsets[r] += base;
+  for (u64 i = tid; i < total; i += nt)
+    if (base + i < cap) store_hit(runs + base + i, local_runs[i]);
+}
 __global__ void hit_run_advance_kernel(u64* __restrict__ base_ptr, const u64* __restrict__ chunk_total) {
   if (blockIdx.x == 0 && threadIdx.x == 0) *base_ptr += *chunk_total;
 }
