@@ -91,3 +91,38 @@ def test_host_builders_self_consistent(tmp_path):
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
     assert "host_check: 0 failures" in r.stdout
+
+
+def test_hit_run_decoder_round_trip():
+    """mazu_b200_expand_hit_runs is host code (a format decoder, no device work): encode the oracle's records as runs with a
+    plain numpy restatement of the format and check the library's decoder gives the records back, ragged and uniform."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _gen
+    from _oracle import OracleIndex
+    o = OracleIndex.dense_from_pf1(os.path.join(ROOT, "tests", "data", "pf1", "yeast_chr01_index")).rebuild_k2u(1, w=15, skew=32, seed=0)
+    ref_codes = _gen.unpack_2bit(o.refseq_words(), int(o.ref_prefix()[-1]))
+    for ragged in (True, False):
+        bases, offs = _gen.sample_reads(ref_codes, 800, 160, seed=77, frac_ref=0.7, sub_rate=0.01, n_rate=0.003, ragged=ragged)
+        hits, _, koffs = o.query_reads(bases, offs)
+        n = len(hits)
+        is_hit = (hits["match"] == mz.IDENTITY_MATCH) | (hits["match"] == mz.TWIN_MATCH)
+        first = np.zeros(n, dtype=bool)
+        first[koffs[:-1][np.diff(koffs.astype(np.int64)) > 0].astype(np.int64)] = True  # first slot of every non-empty read
+        prev = np.roll(hits, 1)
+        step = np.where(hits["match"] == mz.IDENTITY_MATCH, prev["pos"] + np.uint32(1), prev["pos"] - np.uint32(1))
+        cont = is_hit & ~first & (prev["match"] == hits["match"]) & (prev["unitig_id"] == hits["unitig_id"]) & (hits["pos"] == step)
+        codes = np.zeros(n, dtype=np.uint8)
+        codes[is_hit & cont] = 1
+        codes[is_hit & ~cont] = 2
+        codes[hits["match"] == mz.SKIPPED] = 3
+        runs = np.ascontiguousarray(hits[codes == 2])
+        starts_before = np.concatenate([[0], np.cumsum(codes == 2)])
+        rro = starts_before[koffs.astype(np.int64)].astype(np.uint64)
+        if ragged:
+            got = mz.ModIndex.expand_hit_runs(codes, runs, rro, kmer_offsets=koffs)
+        else:
+            got = mz.ModIndex.expand_hit_runs(codes, runs, rro, uniform_slots=160 - o.k + 1)
+        assert np.array_equal(got.view(np.uint32), hits.view(np.uint32))
+        assert len(runs) < n // 8
