@@ -19,7 +19,10 @@ Other workloads (--workload), same JSON line:
   config5-kmers  the same index queried with a flat batch of random-order k-mers (k2u_batch): the random-access HBM regime
 
   value      whole-job units/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e        same metric through the C ABI with HOST (pinned) buffers: H2D of the inputs and D2H of every result record
+  e2e        same metric through the C ABI with HOST (pinned) buffers: H2D of the inputs and D2H of every 16-byte result record
+             (the headline); e2e.bound compares its D2H rate with the measured PCIe peak.  Reported next to it, never instead:
+             compact_records (8-byte records), hit_runs (lossless run format, ~1.2 B per lookup, expansion checked),
+             host_reads_in_device_records_out (records stay in HBM for the next device stage)
   roofline   dominant kernel: algorithmic bytes / measured kernel time vs the measured peak
   cpu_baseline   the CPU oracle (a C++ port of mazu's query path; the Rust reference cannot be built here)
              timed on this box's host cores on a bounded sample of the same workload
