@@ -126,3 +126,22 @@ def test_hit_run_decoder_round_trip():
             got = mz.ModIndex.expand_hit_runs(codes, runs, rro, uniform_slots=160 - o.k + 1)
         assert np.array_equal(got.view(np.uint32), hits.view(np.uint32))
         assert len(runs) < n // 8
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` needs no GPU: it must print ONE JSON line with the driver's keys (metric, value, unit, n_gpus,
+    steps, warmup, ms_per_step, higher_is_better, scaling, vs_baseline, dtype, data, config.workload) plus impl / cpu_baseline / e2e."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-seconds", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "lookups/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert "workload" in d["config"] and d["config"]["workload"].startswith("configs[1]")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
