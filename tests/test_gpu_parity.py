@@ -561,8 +561,8 @@ def test_fuzz_decode_tables():
         n_refs = int(2 ** rng.integers(1, 28)) if kind == "piscem" else int(rng.integers(1, 1 << 20))
         max_ref_len = int(2 ** rng.integers(8, 31)) if kind == "piscem" else (1 << 27)
         mult = rng.integers(0, 4, size=U).astype(np.uint64)                       # many short (and empty) lists ...
-        heavy = rng.random(U) < 0.08
-        mult[heavy] = rng.integers(200, 3000, size=int(heavy.sum()))                # ... and a few long ones
+        heavy = rng.random(U) < (0.08 if case % 4 else 0.9)                          # ... and a few long ones (every 4th case: mostly
+        mult[heavy] = rng.integers(200, 3000, size=int(heavy.sum()))                # long lists, which is what selects the staged kernel)
         offsets = np.zeros(U + 1, dtype=np.uint64)
         offsets[1:] = np.cumsum(mult)
         n = int(offsets[-1])
