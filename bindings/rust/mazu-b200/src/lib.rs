@@ -240,6 +240,29 @@ impl GpuIndex {
         Ok(counts)
     }
 
+    /// `query_reads` with the result as hit RUNS (one code byte per k-mer slot + the record of every run start + per-read run
+    /// offsets; ~1.2 B per lookup over PCIe instead of 16).  Pinned buffers take the library's synchronisation-free path.
+    /// Returns the number of runs written; `expand_hit_runs` rebuilds the exact per-slot records.
+    pub fn query_reads_runs(&self, bases: &PinnedBuf<u8>, read_offsets: &[u64], streaming: bool, codes: &mut PinnedBuf<u8>,
+                            runs: &mut PinnedBuf<Hit>, read_run_offsets: &mut [u64], kmer_offsets: &mut [u64]) -> Result<(usize, [u64; 3])> {
+        let n_reads = (read_offsets.len() - 1) as u64;
+        let mut counts = [0u64; 3];
+        let mut n_runs = 0u64;
+        let mode = if streaming { sys::MAZU_MODE_STREAMING } else { sys::MAZU_MODE_RANDOM };
+        check(unsafe {
+            sys::mazu_b200_query_reads_runs(self.raw, bases.ptr, read_offsets.as_ptr(), n_reads, 0, mode, kmer_offsets.as_mut_ptr(), codes.ptr, runs.ptr,
+                                            runs.len as u64, read_run_offsets.as_mut_ptr(), &mut n_runs, counts.as_mut_ptr())
+        })?;
+        Ok((n_runs as usize, counts))
+    }
+    /// Host-side decoder of the run format (no device work).
+    pub fn expand_hit_runs(codes: &[u8], runs: &[Hit], read_run_offsets: &[u64], kmer_offsets: &[u64], out: &mut [Hit]) -> Result<()> {
+        check(unsafe {
+            sys::mazu_b200_expand_hit_runs(codes.as_ptr(), runs.as_ptr(), read_run_offsets.as_ptr(), kmer_offsets.as_ptr(),
+                                           (read_run_offsets.len() - 1) as u64, 0, out.as_mut_ptr())
+        })
+    }
+
     /// Batched `GetRefPos::project_hits` (src/index.rs:156-216): occurrences of hit i are `out[offsets[i]..offsets[i+1]]`.
     pub fn project_hits(&self, hits: &[Hit]) -> Result<(Vec<u64>, Vec<MappedRefPos>)> {
         self.occ_call(Some(hits), None)
