@@ -461,7 +461,7 @@ def main():
             import _oracle
             qs = np.concatenate([_gen.kmer_words_from_codes(ref_codes, K), uk])
             rng = np.random.default_rng(1)
-            reps = max(1, min(400, (args.reads * nk_per_read) // len(qs)))  # >= 2e8 queries at the default size
+            reps = max(1, min(430, (args.reads * nk_per_read) // len(qs)))  # >= 2e8 queries at the default size
             q = np.tile(qs, reps)
             rng.shuffle(q)
             kmers = torch.from_numpy(q.view(np.int64)).to(dev)
