@@ -147,5 +147,5 @@ extern "C" {
     pub fn mazu_b200_k2u_validate_self(idx: *const mazu_index_t, counts: *mut u64) -> mazu_status_t;
     pub fn mazu_b200_alloc_pinned(bytes: u64, out: *mut *mut c_void) -> mazu_status_t;
     pub fn mazu_b200_free_pinned(p: *mut c_void);
-    pub fn mazu_b200_measure_random_gather(table_bytes: u64, n_gathers: u64, iters: i32, device: i32, sectors_per_s: *mut f64) -> mazu_status_t;
+    pub fn mazu_b200_debug_gather_probe(table_bytes: u64, n_items: u64, granule_bytes: i32, ilp: i32, blocks_per_sm: i32, iters: i32, device: i32, items_per_s: *mut f64) -> mazu_status_t;
 }

@@ -142,13 +142,6 @@ mazu_status_t mazu_b200_index_create_sshash_gpu(const mazu_unitig_set_desc_t* un
                                                 uint64_t hash_seed, int32_t device, mazu_index_t** out);
 /* PFHash::from_unitig_set on the device (tables bit-identical to mazu_b200_index_create_pfhash) */
 mazu_status_t mazu_b200_index_create_pfhash_gpu(const mazu_unitig_set_desc_t* unitigs, int32_t device, mazu_index_t** out);
-/* test hook: FNV-1a digest and logical size of one device table (0 MPHF blocks, 1 bucket-bound blocks, 2 their exceptions,
- * 3 packed positions, 4 skew MPHF blocks, 5 skew positions, 6 MPHF fallback keys) */
-mazu_status_t mazu_b200_debug_table_digest(const mazu_index_t* idx, int32_t which, uint64_t* digest, uint64_t* n_bytes);
-/* measurement hook: level-0 MPHF block of every query's key (the minimizer for SSHash, the canonical k-mer for PFHash);
- * device pointers.  Sorting a flat batch by this key makes its MPHF / bounds / positions accesses sequential: used by
- * profiles/sorted_probe_experiment.py to bound what "sorted probe batches" could gain. */
-mazu_status_t mazu_b200_debug_probe_key(const mazu_index_t* idx, const uint64_t* fw_words, uint64_t n, uint32_t* out_block, void* stream);
 /* PFHash::from_unitig_set(unitigs)                                     src/kphf/pfhash.rs:40-73 */
 mazu_status_t mazu_b200_index_create_pfhash(const mazu_unitig_set_desc_t* unitigs, int32_t device, mazu_index_t** out);
 /* PFHash::from_parts(unitigs, BooPHF, pos)                             src/kphf/pfhash.rs:34-36 */
@@ -277,14 +270,6 @@ mazu_status_t mazu_b200_k2u_validate_self(const mazu_index_t* idx, uint64_t coun
  * ------------------------------------------------------------------------------------------- */
 mazu_status_t mazu_b200_alloc_pinned(uint64_t bytes, void** out);
 void mazu_b200_free_pinned(void* p);
-
-/* ---------------------------------------------------------------------------------------------
- * Measurement helper: independent random 32-byte gathers over a table (the P_rand denominator of
- * DESIGN.md / BASELINE.md section 2).  table_bytes of device memory are allocated internally.
- * Returns achieved sectors per second in *sectors_per_s.
- * ------------------------------------------------------------------------------------------- */
-mazu_status_t mazu_b200_measure_random_gather(uint64_t table_bytes, uint64_t n_gathers, int32_t iters, int32_t device,
-                                              double* sectors_per_s);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MAZU_B200_LIB") or os.path.join(_HERE, "libmazu_b200.so")  # override: A/B of two builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mazu_b200.h")
+DEBUG_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mazu_b200_debug.h")  # test / measurement hooks, not the boundary
 
 HIT_DTYPE = np.dtype([("unitig_id", "<u4"), ("unitig_len", "<u4"), ("pos", "<u4"), ("match", "<u4")])
 TILE_DTYPE = np.dtype([("unitig_id", "<u4"), ("unitig_len", "<u4"), ("pos", "<u4"), ("fw", "<u4")])
@@ -134,7 +135,7 @@ def _signatures():
         "mazu_b200_iter_unitigs_on_ref": (i32, [vp, u64, vp, u64, vp]),
         "mazu_b200_validate_self": (i32, [vp, vp]),
         "mazu_b200_k2u_validate_self": (i32, [vp, vp]),
-        "mazu_b200_measure_random_gather": (i32, [u64, u64, i32, i32, C.POINTER(C.c_double)]),
+        "mazu_b200_debug_gather_probe": (i32, [u64, u64, i32, i32, i32, i32, i32, C.POINTER(C.c_double)]),
     }
 
 
@@ -572,7 +573,8 @@ class PFHash:
         return ModIndex.pfhash_from_unitig_set(unitigs, device, builder)
 
 
-def measure_random_gather(table_bytes, n_gathers, iters=3, device=0):
+def gather_probe(table_bytes, n_items, granule_bytes=32, ilp=1, blocks_per_sm=8, iters=3, device=0):
+    """One point of the random-access roofline sweep (include/mazu_b200_debug.h): granules per second."""
     out = C.c_double(0.0)
-    _check(lib().mazu_b200_measure_random_gather(table_bytes, n_gathers, iters, device, C.byref(out)))
+    _check(lib().mazu_b200_debug_gather_probe(table_bytes, n_items, granule_bytes, ilp, blocks_per_sm, iters, device, C.byref(out)))
     return out.value

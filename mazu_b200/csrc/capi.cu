@@ -3,6 +3,7 @@
 // entry point launches the CUDA kernels of kernels.cuh or fails with MAZU_ERR_CUDA.
 #include "device_index.cuh"
 #include "gpu_build_driver.cuh"
+#include "../../include/mazu_b200_debug.h"
 
 namespace {
 
@@ -67,6 +68,11 @@ void launch_k2u_batch(const mazu_index* ix, const u64* d_words, u64 n, Hit* d_ou
 
 void device_exclusive_scan(const u64* d_in, u64* d_out, u64 n, cudaMemPool_t pool, cudaStream_t s);
 
+// resident CTAs per SM the random-access read kernel is compiled for (4 -> <= 64 registers; 3 -> <= 80); A/B knob
+#ifndef MAZU_QR_RANDOM_OCC
+#define MAZU_QR_RANDOM_OCC 4
+#endif
+
 template <int MODE, int KIND, u32 FAMILY, int OCC>
 void launch_qr_occ(const mazu_index* ix, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, const u64* d_kmer_offsets,
                    void* d_out, u32 compact, u64* d_counts, const u64* d_seg_offsets, cudaStream_t s) {
@@ -96,7 +102,7 @@ void launch_qr(const mazu_index* ix, const u8* d_bases, const u64* d_read_offset
       MZ_CUDA(cudaGetLastError());
       device_exclusive_scan((const u64*)cnt, (u64*)seg, n_reads, ix->pool, s);
     }
-    launch_qr_occ<MODE, KIND, FAMILY, 0>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, (const u64*)seg, s);
+    launch_qr_occ<MODE, KIND, FAMILY, MAZU_QR_RANDOM_OCC>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, (const u64*)seg, s);
     if (cnt) MZ_CUDA(cudaFreeAsync(cnt, s));
     if (seg) MZ_CUDA(cudaFreeAsync(seg, s));
   }
@@ -968,34 +974,97 @@ mazu_status_t mazu_b200_k2u_validate_self(const mazu_index_t* idx, uint64_t coun
   return guarded([&] { run_validate(idx, true, counts); });
 }
 
-mazu_status_t mazu_b200_measure_random_gather(uint64_t table_bytes, uint64_t n_gathers, int32_t iters, int32_t device, double* sectors_per_s) {
+}  // extern "C"
+
+namespace {
+struct ProbeTable {  // kept between calls of the same size: a sweep point then costs its launches only
+  void* p = nullptr;
+  u64 bytes = 0;
+  int device = -1;
+  void release() {
+    if (p) {
+      cudaSetDevice(device);
+      cudaFree(p);
+    }
+    p = nullptr;
+    bytes = 0;
+  }
+};
+ProbeTable g_probe;
+std::mutex g_probe_mu;
+
+template <int LANES>
+void launch_gather_probe(int ilp, int grid, size_t smem, const uint4* table, u64 n_granules, u64 n_items, u64 seed, unsigned long long* sink) {
+#define MZ_GP(I)                                                                                              \
+  {                                                                                                           \
+    MZ_CUDA(cudaFuncSetAttribute(gather_probe_kernel<LANES, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    gather_probe_kernel<LANES, I><<<grid, 256, smem>>>(table, n_granules, n_items, seed, sink);              \
+  }
+  switch (ilp) {
+    case 1: MZ_GP(1) break;
+    case 2: MZ_GP(2) break;
+    case 4: MZ_GP(4) break;
+    case 8: MZ_GP(8) break;
+    default: throw Error(MAZU_ERR_INVALID_ARG, "ilp must be 1, 2, 4 or 8");
+  }
+#undef MZ_GP
+}
+}  // namespace
+
+extern "C" {
+
+mazu_status_t mazu_b200_debug_gather_probe(uint64_t table_bytes, uint64_t n_items, int32_t granule_bytes, int32_t ilp, int32_t blocks_per_sm,
+                                           int32_t iters, int32_t device, double* items_per_s) {
   return guarded([&] {
-    if (!sectors_per_s || table_bytes < 64) throw Error(MAZU_ERR_INVALID_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(g_probe_mu);
+    if (table_bytes == 0) {
+      g_probe.release();
+      return;
+    }
+    if (!items_per_s || table_bytes < 4096 || blocks_per_sm < 1 || blocks_per_sm > 8) throw Error(MAZU_ERR_INVALID_ARG, "bad argument");
     DeviceGuard g(device);
     cudaDeviceProp prop;
     MZ_CUDA(cudaGetDeviceProperties(&prop, device));
-    DevBuf table(table_bytes, device), sink(8, device);
-    MZ_CUDA(cudaMemset(table.p, 1, table_bytes));
+    if (g_probe.bytes != table_bytes || g_probe.device != device) {
+      g_probe.release();
+      MZ_CUDA(cudaMalloc(&g_probe.p, table_bytes));
+      g_probe.bytes = table_bytes;
+      g_probe.device = device;
+      MZ_CUDA(cudaMemset(g_probe.p, 1, table_bytes));
+    }
+    DevBuf sink(8, device);
     MZ_CUDA(cudaMemset(sink.p, 0, 8));
+    // dynamic shared memory as ballast: exactly blocks_per_sm CTAs fit an SM
+    const size_t smem_total = prop.sharedMemPerMultiprocessor, reserved = prop.reservedSharedMemPerBlock;
+    size_t smem = blocks_per_sm >= 8 ? 0 : smem_total / blocks_per_sm - reserved - 256;
+    smem = std::min<size_t>(smem, prop.sharedMemPerBlockOptin);
+    const int grid = prop.multiProcessorCount * blocks_per_sm;
+    const u64 n_granules = table_bytes / (u64)granule_bytes;
     cudaEvent_t e0, e1;
     MZ_CUDA(cudaEventCreate(&e0));
     MZ_CUDA(cudaEventCreate(&e1));
     double best = 0;
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, random_gather_kernel, 256, 0);
-    int grid = prop.multiProcessorCount * std::max(occ, 1);
     for (int it = 0; it < iters + 1; ++it) {
       MZ_CUDA(cudaEventRecord(e0));
-      random_gather_kernel<<<grid, 256>>>((const uint4*)table.p, table_bytes / 32, n_gathers, 0x1234 + it, (unsigned long long*)sink.p);
+      const uint4* t = (const uint4*)g_probe.p;
+      unsigned long long* sk = (unsigned long long*)sink.p;
+      switch (granule_bytes) {
+        case 16: launch_gather_probe<1>(ilp, grid, smem, t, n_granules, n_items, 0x1234 + it, sk); break;
+        case 32: launch_gather_probe<2>(ilp, grid, smem, t, n_granules, n_items, 0x1234 + it, sk); break;
+        case 64: launch_gather_probe<4>(ilp, grid, smem, t, n_granules, n_items, 0x1234 + it, sk); break;
+        case 128: launch_gather_probe<8>(ilp, grid, smem, t, n_granules, n_items, 0x1234 + it, sk); break;
+        default: throw Error(MAZU_ERR_INVALID_ARG, "granule_bytes must be 16, 32, 64 or 128");
+      }
+      MZ_CUDA(cudaGetLastError());
       MZ_CUDA(cudaEventRecord(e1));
       MZ_CUDA(cudaEventSynchronize(e1));
       float ms = 0;
       MZ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-      if (it > 0) best = std::max(best, (double)n_gathers / (ms * 1e-3));
+      if (it > 0) best = std::max(best, (double)n_items / (ms * 1e-3));
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    *sectors_per_s = best;
+    *items_per_s = best;
   });
 }
 

@@ -138,6 +138,8 @@ std::shared_ptr<UnitigsDev> upload_unitigs(const UnitigSetHost& us, int dev) {
   auto d = std::make_shared<UnitigsDev>();
   const u64 L = us.total_len(), U = us.n_unitigs();
   if (U >> 32) throw Error(MAZU_ERR_INVALID_ARG, "more than 2^32 unitigs");
+  for (u64 i = 0; i < U; ++i)  // hit records and unitig lines carry 32-bit lengths
+    if (us.accum[i + 1] - us.accum[i] >= (1ULL << 32) - 512) throw Error(MAZU_ERR_INVALID_ARG, "a unitig is longer than 2^32 - 512 bases");
   u64 nw = (2 * L + 63) / 64;
   auto b_seq = upload(us.useq.data(), std::min<u64>(nw, us.useq.size()), dev, 4);
   // directory: unitig containing the first base of every 2^DIR_SHIFT block
@@ -154,8 +156,6 @@ std::shared_ptr<UnitigsDev> upload_unitigs(const UnitigSetHost& us, int dev) {
   }
   auto b_dir = upload(dir, dev);
   auto b_starts = upload(us.accum, dev, 4);
-  d->bufs = {b_seq, b_dir, b_starts};
-  d->bytes = b_seq->bytes + b_dir->bytes + b_starts->bytes;
   d->view.useq = (const u64*)b_seq->p;
   d->view.dir = (const u32*)b_dir->p;
   d->view.starts = (const u64*)b_starts->p;
@@ -163,6 +163,16 @@ std::shared_ptr<UnitigsDev> upload_unitigs(const UnitigSetHost& us, int dev) {
   d->view.n_unitigs = U;
   d->view.k = us.k;
   d->view.dir_shift = DIR_SHIFT;
+  // unitig lines: what the query kernels read (window + id + bounds of a candidate in one 128-byte line)
+  const u64 n_lines = (L >> ULINE_SHIFT) + 2;
+  auto b_lines = std::make_shared<DevBuf>(n_lines * sizeof(UnitigLine), dev);
+  d->view.lines = (const UnitigLine*)b_lines->p;
+  build_unitig_lines_kernel<<<(int)std::min<u64>((n_lines + 255) / 256, 148 * 8), 256>>>(d->view, n_lines, std::min<u64>(nw, us.useq.size()) + 4,
+                                                                                        (UnitigLine*)b_lines->p);
+  MZ_CUDA(cudaGetLastError());
+  MZ_CUDA(cudaDeviceSynchronize());
+  d->bufs = {b_seq, b_dir, b_starts, b_lines};
+  d->bytes = b_seq->bytes + b_dir->bytes + b_starts->bytes + b_lines->bytes;
   return d;
 }
 

@@ -311,10 +311,39 @@ MZ_HD void blocked_ef_get2(const BlockedEFView& ef, u64 i, u64& a, u64& b) {
 // locate(pos) replaces the reference's rank over an L-bit end-marker vector plus 3-4 Elias-Fano
 // get()s (unitig_set.rs:178-209) with one directory sector + one or two `starts` sectors.
 // ---------------------------------------------------------------------------------------------
+// Unitig line: everything a verified candidate needs, in ONE 128-byte DRAM line (the granularity a random access
+// pays for on this part: profiles/r02_prand.json).  Line i covers bases [256 i, 256 i + 256), base = 256 i:
+//   seq[9]       the line's 256 bases + the 32 bases that follow, so a k-mer window (k <= 32) never straddles lines
+//   first_id     unitig containing `base`                start_delta  base - start of that unitig
+//   end_delta    (end of the unitig containing base + 255) - base
+//   ends[4]      bit j <=> base + j is the last base of a unitig (the reference's end-marker bit-vector,
+//                unitig_set.rs:146-149, cut into the line it belongs to)
+//   per 64-base word w of `ends` (one byte each, packed in a u32):
+//     cnt_before   markers in words < w
+//     prev_end     offset of the last marker in words < w   (0xFF: none -> the unitig of `base`)
+//     next_end     offset of the first marker in words > w  (0: none -> end_delta)
+//   so a lookup reads ONE word of `ends`, whatever the offset.
+// get_kmer_u64_from_useq_pos + pos_to_id + unitig_start_pos + unitig_end_pos (unitig_set.rs:185-229) = this one line;
+// the flat arrays above cost three (window, directory, starts).  Built on the device from useq / dir / starts
+// (build_unitig_lines_kernel); the flat arrays stay for the builders, the query kernels only touch lines.
+static const u32 ULINE_SHIFT = 8;
+struct alignas(128) UnitigLine {
+  u64 seq[9];
+  u32 first_id;
+  u32 start_delta;
+  u32 end_delta;
+  u32 cnt_before;
+  u32 prev_end;
+  u32 next_end;
+  u64 ends[4];
+};
+static_assert(sizeof(UnitigLine) == 128, "UnitigLine must be one 128-byte line");
+
 struct UnitigsView {
   const u64* useq;
   const u32* dir;
   const u64* starts;
+  const UnitigLine* lines;
   u64 total_len;
   u64 n_unitigs;
   u32 k;
@@ -340,6 +369,37 @@ MZ_HD void unitig_locate(const UnitigsView& u, u64 pos, u64& id, u64& start, u64
   start = MZ_LDG(u.starts + i);
   end = e;
 }
+
+#if defined(MAZU_FLAT_UNITIGS)  // A/B build: the round-1 layout (window, directory, starts in three separate arrays)
+MZ_HD u64 line_window(const UnitigsView& u, u64 pos) { return useq_window(u, pos); }
+MZ_HD void line_locate(const UnitigsView& u, u64 pos, u64& id, u64& start, u64& end) { unitig_locate(u, pos, id, start, end); }
+#elif defined(__CUDA_ARCH__) || defined(__CUDACC__)
+// the same two primitives over unitig lines (query kernels): one DRAM line per verified candidate
+__device__ __forceinline__ u64 line_window(const UnitigsView& u, u64 pos) {
+  const u64* ln = reinterpret_cast<const u64*>(u.lines + (pos >> ULINE_SHIFT));
+  const u32 off = (u32)pos & 255u, wi = off >> 5, sh = 2 * (off & 31u);
+  u64 x = __ldg(ln + wi) >> sh;
+  if (sh + 2 * u.k > 64) x |= __ldg(ln + wi + 1) << (64 - sh);
+  return x & kmer_mask(u.k);
+}
+__device__ __forceinline__ void line_locate(const UnitigsView& u, u64 pos, u64& id, u64& start, u64& end) {
+  const UnitigLine* L = u.lines + (pos >> ULINE_SHIFT);
+  const u32 off = (u32)pos & 255u, wq = off >> 6;
+  const u64 e = __ldg(L->ends + wq);
+  const uint2 a = __ldg(reinterpret_cast<const uint2*>(&L->first_id));  // first_id, start_delta
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(&L->end_delta));  // end_delta, cnt_before, prev_end, next_end
+  const u64 below = (1ULL << (off & 63u)) - 1ULL;
+  const u64 lo = e & below, hi = e & ~below;  // markers before `off` / at or after `off` inside this word
+  const u32 sh = 8 * wq;
+  const u32 prev = (b.z >> sh) & 255u, next = (b.w >> sh) & 255u;
+  const u64 base = pos & ~255ULL;
+  id = (u64)a.x + ((b.y >> sh) & 255u) + (u32)__popcll(lo);
+  if (lo) start = base + (u64)(64 * wq + 64 - __clzll((long long)lo));
+  else start = prev != 255u ? base + prev + 1 : base - a.y;
+  if (hi) end = base + (u64)(64 * wq + __ffsll((long long)hi));
+  else end = next != 0u ? base + next + 1 : base + b.x;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // The whole index as the kernels see it (passed by value as a __grid_constant__ parameter).

@@ -37,6 +37,49 @@ __device__ __forceinline__ void store_rec(void* base, u64 idx, const Hit& h, boo
   else store_hit(reinterpret_cast<Hit*>(base) + idx, h);
 }
 
+// Unitig lines (index_layout.hpp) from the flat arrays, one thread per line.  n_words = readable words of useq.
+__global__ void __launch_bounds__(256) build_unitig_lines_kernel(const __grid_constant__ UnitigsView u, u64 n_lines, u64 n_words,
+                                                                 UnitigLine* __restrict__ lines) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_lines; i += (u64)gridDim.x * blockDim.x) {
+    UnitigLine L;
+    const u64 base = i << ULINE_SHIFT;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) L.seq[j] = 8 * i + j < n_words ? u.useq[8 * i + j] : 0ULL;
+    L.ends[0] = L.ends[1] = L.ends[2] = L.ends[3] = 0ULL;
+    L.first_id = (u32)(u.n_unitigs ? u.n_unitigs - 1 : 0);
+    L.start_delta = L.end_delta = 0;
+    if (base < u.total_len) {
+      u64 id, start, end;
+      unitig_locate(u, base, id, start, end);
+      L.first_id = (u32)id;
+      L.start_delta = (u32)(base - start);
+      while (end <= base + 256) {  // unitigs ending inside the line: their last base is base + (end - 1 - base)
+        const u32 j = (u32)(end - 1 - base);
+        L.ends[j >> 6] |= 1ULL << (j & 63);
+        if (++id >= u.n_unitigs) break;
+        end = u.starts[id + 1];
+      }
+      L.end_delta = (u32)(end - base);  // only read when no unitig ends at or after the queried base inside this line
+    }
+    u32 cnt = 0, prev = 255u;
+    L.cnt_before = L.prev_end = L.next_end = 0;
+#pragma unroll
+    for (u32 w = 0; w < 4; ++w) {
+      L.cnt_before |= cnt << (8 * w);
+      L.prev_end |= prev << (8 * w);
+      if (L.ends[w]) prev = 64 * w + 63 - (u32)__clzll((long long)L.ends[w]);
+      cnt += (u32)__popcll(L.ends[w]);
+    }
+    u32 next = 0;
+#pragma unroll
+    for (int w = 3; w >= 0; --w) {
+      L.next_end |= next << (8 * w);
+      if (L.ends[w]) next = 64 * w + (u32)__ffsll((long long)L.ends[w]) - 1;
+    }
+    lines[i] = L;
+  }
+}
+
 // kmers::CanonicalKmer::get_word_equivalency
 __device__ __forceinline__ u32 word_equivalency(u64 fw, u64 rc, u64 kw) {
   return kw == fw ? (u32)IDENTITY_MATCH : (kw == rc ? (u32)TWIN_MATCH : (u32)NO_MATCH);
@@ -46,7 +89,7 @@ __device__ __forceinline__ u32 word_equivalency(u64 fw, u64 rc, u64 kw) {
 // guard of src/kphf/sshash.rs:513-514,539-541 when `guard` is set)
 __device__ __forceinline__ bool finish_hit(const UnitigsView& u, u64 km_pos, u32 mt, bool guard, Hit& out, u64* ustart = nullptr) {
   u64 id, start, end;
-  unitig_locate(u, km_pos, id, start, end);
+  line_locate(u, km_pos, id, start, end);
   if (guard && km_pos + u.k > end) return false;
   if (ustart) *ustart = start;
   out.unitig_id = (u32)id;
@@ -63,7 +106,7 @@ __device__ __forceinline__ bool pfhash_k2u(const IndexView& ix, u64 fw, u64 rc, 
   if (!mphf_lookup(ix.mphf, word, h)) return false;
   if (h >= ix.pos.len) return false;
   u64 km_pos = packed_get(ix.pos, h);
-  u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, km_pos));
+  u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
   if (mt == NO_MATCH) return false;
   return finish_hit(ix.unitigs, km_pos, mt, false, out);
 }
@@ -82,7 +125,7 @@ __device__ __forceinline__ bool sshash_k2u(const IndexView& ix, u64 fw, u64 rc, 
     if (!mphf_lookup(ix.skew_mphf, word, hs)) return false;
     if (hs >= ix.skew_pos.len) return false;
     u64 p = packed_get(ix.skew_pos, hs);
-    u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, p));
+    u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, p));
     if (mt == NO_MATCH) return false;
     return finish_hit(ix.unitigs, p, mt, false, out);
   }
@@ -93,12 +136,12 @@ __device__ __forceinline__ bool sshash_k2u(const IndexView& ix, u64 fw, u64 rc, 
     u64 mm_pos = packed_get(ix.pos, pi);
     if (mm_pos >= offset && mm_pos - offset <= last_km_start_pos) {  // sshash.rs:498
       u64 km_pos = mm_pos - offset;
-      u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, km_pos));
+      u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
       if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out)) return true;
     }
     if (mm_pos >= rc_offset && mm_pos - rc_offset <= last_km_start_pos) {  // sshash.rs:527
       u64 km_pos = mm_pos - rc_offset;
-      u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, km_pos));
+      u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
       if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out)) return true;
     }
   }
@@ -354,7 +397,7 @@ __device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpSta
     if (!mphf_lookup_t<FAMILY>(ix.skew_mphf, word, hs)) return false;
     if (hs >= ix.skew_pos.len) return false;
     u64 pos = packed_get(ix.skew_pos, hs);
-    u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, pos));
+    u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, pos));
     if (mt == NO_MATCH) return false;
     return finish_hit(ix.unitigs, pos, mt, false, out, ustart);
   }
@@ -367,12 +410,12 @@ __device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpSta
     u64 mm_pos = packed_get(ix.pos, pos_start + e);
     if (mm_pos >= offset && mm_pos - offset <= last_km_start_pos) {  // sshash.rs:498
       u64 km_pos = mm_pos - offset;
-      u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, km_pos));
+      u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
       if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out, ustart)) return true;
     }
     if (rc_offset != offset && mm_pos >= rc_offset && mm_pos - rc_offset <= last_km_start_pos) {  // sshash.rs:527 (same window when equal)
       u64 km_pos = mm_pos - rc_offset;
-      u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, km_pos));
+      u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
       if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out, ustart)) return true;
     }
   }
@@ -386,7 +429,7 @@ __device__ __forceinline__ bool pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc
   if (!mphf_lookup_t<FAMILY>(ix.mphf, word, h)) return false;
   if (h >= ix.pos.len) return false;
   u64 km_pos = packed_get(ix.pos, h);
-  u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, km_pos));
+  u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
   if (mt == NO_MATCH) return false;
   return finish_hit(ix.unitigs, km_pos, mt, false, out, ustart);
 }
@@ -439,10 +482,10 @@ __device__ __forceinline__ bool sampled_pfhash_k2u_t(const IndexView& ix, u64 fw
     // is_valid_useq_pos (unitig_set.rs:235-245)
     if (pos > ix.unitigs.total_len - k) return false;
     u64 id, s, e;
-    unitig_locate(ix.unitigs, pos, id, s, e);
+    line_locate(ix.unitigs, pos, id, s, e);
     if (pos + k > e) return false;
   }
-  u32 mt = word_equivalency(fw, rc, useq_window(ix.unitigs, pos));
+  u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, pos));
   if (mt == NO_MATCH) return false;
   return finish_hit(ix.unitigs, pos, mt, false, out, ustart);
 }
@@ -598,7 +641,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const _
             bool differs = false;
             if (mine && valid && s_warm && (u64)s_pos + 1 + k <= (u64)s_ulen &&
                 !(cold_hit && cold.unitig_id == s_uid && cold.pos == s_pos + 1)) {
-              u32 m = word_equivalency(fw, rc, useq_window(ix.unitigs, s_ustart + s_pos + 1));
+              u32 m = word_equivalency(fw, rc, line_window(ix.unitigs, s_ustart + s_pos + 1));
               if (m != NO_MATCH) {  // the walk answers here although the cold lookup answered elsewhere (or missed)
                 res = Hit{s_uid, s_ulen, s_pos + 1, m};
                 res_hit = true;
@@ -1297,19 +1340,26 @@ __global__ void __launch_bounds__(256) k2u_validate_self_kernel(const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
-// Roofline probe: independent random 32-byte gathers (one aligned uint4 pair per thread step)
+// Roofline probe: independent random reads of aligned granules (16 / 32 / 64 / 128 bytes), swept over granule size,
+// loads in flight per thread and resident CTAs per SM by profiles/measure_prand.py.  A granule is read by LANES adjacent
+// lanes with one 16-byte load each (LANES = 8: a warp instruction touches four random 128-byte lines).
 // ---------------------------------------------------------------------------------------------
-// One independent gather per thread and iteration; memory-level parallelism comes from the 2048
-// resident threads per SM.  (A variant with 8 gathers in flight per thread measured LOWER: 2.6e10 vs
-// 3.4e10 sectors/s over a 32 GiB table -- profiles/r01_prand.json keeps the better figure.)
-__global__ void __launch_bounds__(256) random_gather_kernel(const uint4* __restrict__ table, u64 n_sectors, u64 n_gathers, u64 seed,
-                                                            unsigned long long* __restrict__ sink) {
+template <int LANES, int ILP>
+__global__ void __launch_bounds__(256) gather_probe_kernel(const uint4* __restrict__ table, u64 n_granules, u64 n_items, u64 seed,
+                                                           unsigned long long* __restrict__ sink) {
+  const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x, nt = (u64)gridDim.x * blockDim.x;
+  const u64 group = tid / LANES, n_groups = nt / LANES;
+  const u32 sub = (u32)(tid % LANES);
   u64 acc = 0;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_gathers; i += (u64)gridDim.x * blockDim.x) {
-    u64 h = fmix64(i * 0x9E3779B97F4A7C15ULL + seed);
-    u64 s = mulhi64(h, n_sectors);
-    uint4 a = __ldg(table + 2 * s);
-    acc += a.x + a.w;
+  for (u64 i = group * ILP; i < n_items; i += n_groups * ILP) {
+    uint4 v[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      const u64 g = mulhi64(fmix64((i + j) * 0x9E3779B97F4A7C15ULL + seed), n_granules);
+      v[j] = __ldg(table + g * LANES + sub);
+    }
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) acc += v[j].x + v[j].w;
   }
   if (acc == 0x1234567887654321ULL) atomicAdd(sink, 1ULL);
 }

@@ -95,7 +95,7 @@ static void check_unitig_dir(const UnitigSetHost& us) {
     while (us.accum[ui + 1] <= p) ++ui;
     dir[b] = (u32)ui;
   }
-  UnitigsView v{us.useq.data(), dir.data(), us.accum.data(), L, U, us.k, shift};
+  UnitigsView v{us.useq.data(), dir.data(), us.accum.data(), nullptr, L, U, us.k, shift};
   for (u64 p = 0; p < L; p += (L > 2000000 ? 7 : 1)) {
     u64 id, s, e;
     unitig_locate(v, p, id, s, e);

@@ -13,10 +13,19 @@ import mazu_b200 as mz
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _header_symbols():
-    text = open(mz.HEADER_PATH).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(mazu_b200_[a-z0-9_]+)\s*\(", text)))
+def _header_symbols(paths=None):
+    out = set()
+    for path in paths or (mz.HEADER_PATH, mz.DEBUG_HEADER_PATH):
+        text = open(path).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        out |= set(re.findall(r"\b(mazu_b200_[a-z0-9_]+)\s*\(", text))
+    return sorted(out)
+
+
+def test_debug_hooks_live_in_their_own_header():
+    """the drop-in boundary (mazu_b200.h) declares no debug / measurement hook; those are in mazu_b200_debug.h"""
+    assert not [s for s in _header_symbols([mz.HEADER_PATH]) if "debug" in s or "measure" in s]
+    assert all("debug" in s for s in _header_symbols([mz.DEBUG_HEADER_PATH]))
 
 
 def test_header_matches_binding():
