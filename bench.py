@@ -1,29 +1,34 @@
 #!/usr/bin/env python
 """bench.py -- k-mer lookups/s of the batched query path on N B200s (one process per GPU).
 
-Default workload (BASELINE.json configs[1], the configuration the metric is quoted on): SSHash rebuilt
-from the yeast chr01 unitigs of tests/data/pf1/yeast_chr01_index (k=31, w=15, skew 32, hash seed 0),
-queried in random-access mode with synthetic 150 bp reads: 50 % sampled from the 230,218 bp reference
-on a random strand, 50 % uniform random ACGT.  One "step" = one pass of the hot path (encode ->
-canonical k-mers -> minimizers -> MPHF -> bucket bounds -> positions -> verify -> unitig id / offset /
+Default workload = BASELINE.json configs[4], the largest single-GPU configuration and the only one in the HBM-random
+regime the north star is about: a synthetic human-scale unitig set (seed 45: 36,145,130 unitigs of length 31 + Geom(68),
+~2.46e9 k-mers), SSHash k=31 w=19 skew 64 built on the device (5.8 GB of tables + 1.8 GB of unitig lines >> the 126 MB L2),
+queried in random-access mode (K2U::k2u per k-mer) with synthetic 150 bp reads generated on the device: 70 % sampled from
+the unitig sequence on a random strand with 1 % substitutions, 30 % uniform random.  One "step" = one pass of the hot
+path (encode -> canonical k-mers -> minimizers -> MPHF -> bucket bounds -> positions -> verify -> unitig id / offset /
 orientation) over one batch of --reads reads per GPU (default 10 M reads = 1.2e9 k-mer lookups).
-Multi-GPU: index replicated, reads sharded (each rank its own batch, weak scaling), no data-path
-collective; one all_reduce of three counters after the timed region.
+Multi-GPU: index replicated (every rank builds the same index on its GPU), reads sharded (each rank its own batch, weak
+scaling), no data-path collective; one all_reduce of three counters after the timed region.
 
 Other workloads (--workload), same JSON line:
-  config3        the same index through .as_streaming(): 70 % reference-sampled reads with 1 % substitutions / 30 % random
-  config1        pufferfish yeast_chr01 DenseIndex (PFHash + C++ BooPHF): all reference + unitig k-mers, shuffled, via k2u_batch
-  config4        U2Pos occurrence decode on a synthetic high-multiplicity unitig table (metric: occurrences/s)
-  config5        synthetic unitig set (len 31+Geom(68)), SSHash k=31 w=19 skew 64, --scale 1.0 = 36,145,130 unitigs / ~2.5e9 k-mers;
-                 index >> L2, reads generated on the device (70/30 mix); --mode random|streaming
-  config5-kmers  the same index queried with a flat batch of random-order k-mers (k2u_batch): the random-access HBM regime
+  config2        configs[1]: SSHash(yeast chr01 unitigs, k=31, w=15, skew 32), 50 % reference-sampled / 50 % random reads (index L2-resident)
+  config3        configs[2]: the same index through .as_streaming(): 70 % reference-sampled reads with 1 % substitutions / 30 % random
+  config1        configs[0]: pufferfish yeast_chr01 DenseIndex (PFHash + C++ BooPHF): all reference + unitig k-mers, shuffled, via k2u_batch
+  config4        configs[3]: U2Pos occurrence decode on a synthetic high-multiplicity unitig table (metric: occurrences/s)
+  config5        the default; --scale shrinks the unitig set, --mode random|streaming
+  config5-kmers  the same index queried with a flat batch of random-order k-mers (k2u_batch)
 
   value      whole-job units/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e        same metric through the C ABI with HOST (pinned) buffers: H2D of the inputs and D2H of every 16-byte result record
-             (the headline); e2e.bound compares its D2H rate with the measured PCIe peak.  Reported next to it, never instead:
-             compact_records (8-byte records), hit_runs (lossless run format, ~1.2 B per lookup, expansion checked),
-             host_reads_in_device_records_out (records stay in HBM for the next device stage)
-  roofline   dominant kernel: algorithmic bytes / measured kernel time vs the measured peak
+  e2e        same metric through the C ABI with HOST (pinned) buffers, copies inside the timed region.  The host result of
+             a read batch is the lossless hit-run format (mazu_b200_query_reads_runs: one code byte per k-mer slot + the
+             16-byte record of every run start; mazu_b200_expand_hit_runs rebuilds every record, checked here): e2e.value.
+             Reported next to it on a bounded slice of the same reads: full_records (every 16-byte record over PCIe, bound
+             by the measured D2H peak), compact_records (8 bytes), host_reads_in_device_records_out (records stay in HBM)
+  roofline   dominant kernel.  Random-access workloads: achieved = DRAM bytes/s the kernel moves (lookups/s x DRAM bytes
+             per lookup from the ncu capture of this launch shape, profiles/traffic.json) against the measured
+             random-access line-rate peak P_rand (profiles/r02_prand.json); the SURVEY 8(d) algorithmic figure is reported
+             next to it.  Streaming decode (config4): algorithmic bytes against the measured HBM copy peak.
   cpu_baseline   the CPU oracle (a C++ port of mazu's query path; the Rust reference cannot be built here)
              timed on this box's host cores on a bounded sample of the same workload
 
@@ -59,10 +64,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mazu_b200", choices=["mazu_b200", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3", "config4", "config5", "config5-kmers"])
+    ap.add_argument("--workload", default="config5", choices=["config1", "config2", "config3", "config4", "config5", "config5-kmers"])
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads (or k-mers / 120, or unitig queries) per GPU per step")
     ap.add_argument("--mode", default=None, choices=["random", "streaming"])
-    ap.add_argument("--scale", type=float, default=0.1, help="config5: fraction of the human-scale unitig count")
+    ap.add_argument("--scale", type=float, default=1.0, help="config5: fraction of the human-scale unitig count (36,145,130 unitigs)")
+    ap.add_argument("--cpu-scale", type=float, default=0.1, help="config5: unitig-set scale of the CPU port's index (its builder needs ~25 s per 0.1 on 16 cores)")
+    ap.add_argument("--e2e-slice", type=int, default=2_500_000, help="reads of the batch the full-record / compact e2e variants run on")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU seconds for the cpu_baseline sample")
@@ -166,67 +173,104 @@ def yeast_ref_codes(o):
     return _gen.unpack_2bit(o.refseq_words(), int(o.ref_prefix()[-1]))
 
 
-def mix_of(mode):
+def mix_of(workload, mode):
+    """(fraction of reads sampled from the indexed sequence, substitution rate)."""
+    if workload in ("config5", "config3"):
+        return 0.7, 0.01
     return (0.5, 0.0) if mode == "random" else (0.7, 0.01)
 
 
-def time_oracle_reads(os_idx, ref_codes, target_seconds, mode, threads, k, seed=4242):
-    """CPU port on a bounded sample: calibrate on 20k reads, then size the sample for ~target_seconds."""
-    import _gen
-    frac_ref, sub = mix_of(mode)
-    streaming = mode == "streaming"
-    cal = _gen.sample_reads_fast(ref_codes, 20000, READ_LEN, seed, frac_ref, sub)
-    offs = np.arange(20001, dtype=np.uint64) * READ_LEN
-    t0 = time.time()
-    _, c, _ = os_idx.query_reads(cal, offs, streaming=streaming, want_hits=False, n_threads=threads)
-    rate = float(c[0]) / max(time.time() - t0, 1e-6)
-    n_reads = int(min(2_000_000, max(20000, rate * target_seconds / (READ_LEN - k + 1))))
-    bases = _gen.sample_reads_fast(ref_codes, n_reads, READ_LEN, seed + 1, frac_ref, sub)
-    offs = np.arange(n_reads + 1, dtype=np.uint64) * READ_LEN
-    t0 = time.time()
-    _, c, _ = os_idx.query_reads(bases, offs, streaming=streaming, want_hits=True, n_threads=threads)
-    dt = time.time() - t0
-    return float(c[0]) / dt, n_reads, dt, c
+class CpuPort:
+    """The CPU arm of a read workload: the oracle index + a generator of reads of the same mix as the GPU arm.
+    config2/3: the yeast index (exactly the GPU arm's index).  config5: the same synthetic unitig set (seed 45) at
+    --cpu-scale, because the port's builder cannot produce the full-scale index inside a bench run; its threaded builder
+    is the reference's rayon builder restated (oracle/mazu_oracle.hpp)."""
+
+    def __init__(self, args):
+        import _gen
+        import _oracle
+        self.args = args
+        self.threads = os.cpu_count() or 1
+        self.frac_ref, self.sub = mix_of(args.workload, args.mode)
+        t0 = time.time()
+        if args.workload == "config5":
+            self.scale = min(args.cpu_scale, args.scale)
+            n_unitigs = max(1000, int(HUMAN_UNITIGS * self.scale))
+            words, n_bases, accum = _gen.synthetic_unitigs_packed(n_unitigs, 68, 31, seed=45)
+            self.idx = _oracle.OracleIndex.from_packed(31, words, n_bases, accum, 1, w=19, skew=64, seed=0, build_threads=self.threads)
+            self.codes = _gen.unpack_2bit(words, n_bases)
+            self.index_note = ("index: the same synthetic unitig set at scale %.3g (%d unitigs, %d k-mers; the GPU arm's is scale %.3g), "
+                               "built by the port's threaded builder in %.0f s" % (self.scale, n_unitigs, self.idx.n_kmers, args.scale, time.time() - t0))
+        else:
+            o, self.idx = load_oracle_yeast(sshash=args.workload != "config1")
+            self.codes = yeast_ref_codes(o)
+            self.index_note = "index: the GPU arm's yeast chr01 index"
+        self.k = self.idx.k
+        self.build_s = time.time() - t0
+
+    def reads(self, n_reads, seed):
+        import _gen
+        if self.args.workload == "config5":
+            return _gen.reads_from_packed(None, len(self.codes), n_reads, READ_LEN, seed, self.frac_ref, self.sub, codes=self.codes)
+        return _gen.sample_reads_fast(self.codes, n_reads, READ_LEN, seed, self.frac_ref, self.sub)
+
+    def run(self, bases, threads=None, want_hits=True):
+        n = len(bases) // READ_LEN
+        offs = np.arange(n + 1, dtype=np.uint64) * READ_LEN
+        t0 = time.time()
+        _, c, _ = self.idx.query_reads(bases, offs, streaming=self.args.mode == "streaming", want_hits=want_hits,
+                                       n_threads=self.threads if threads is None else threads)
+        return float(c[0]), time.time() - t0, c
+
+    def calibrate(self, seconds, threads=None, cap=2_000_000):
+        """reads per sample so that one pass takes about `seconds`."""
+        cal = self.reads(20000, 4242)
+        n, dt, _ = self.run(cal, threads, want_hits=False)
+        rate = n / max(dt, 1e-6)
+        return int(min(cap, max(20000, rate * seconds / (READ_LEN - self.k + 1))))
+
+
+def bench_config(args):
+    """`config` of the JSON line: identical for the GPU arm and the --impl reference arm."""
+    cfg = {"workload": workload_name(args), "mode": args.mode, "read_len": READ_LEN, "units_per_gpu_per_step": args.reads}
+    if args.workload.startswith("config5"):
+        cfg["index_scale"] = args.scale
+    return cfg
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path.  The Rust crate cannot be built in
     this image (no cargo/rustc, four un-vendored crates), so this arm runs the C++ port (oracle/) with all
-    host threads on the default workload's index; each step is a bounded sample of the workload."""
+    host threads; each step is a bounded sample of the workload (same read mix; see CpuPort for the index)."""
     if rank != 0:
         return
-    import _gen
-    o, os_idx = load_oracle_yeast(sshash=args.workload != "config1")
-    ref_codes = yeast_ref_codes(o)
-    threads = os.cpu_count() or 1
-    streaming = args.mode == "streaming"
-    frac_ref, sub = mix_of(args.mode)
-    k = os_idx.k
-    cal = _gen.sample_reads_fast(ref_codes, 20000, READ_LEN, 99, frac_ref, sub)
-    offs = np.arange(20001, dtype=np.uint64) * READ_LEN
-    t0 = time.time()
-    _, c, _ = os_idx.query_reads(cal, offs, streaming=streaming, want_hits=False, n_threads=threads)
-    rate = float(c[0]) / max(time.time() - t0, 1e-6)
-    n_reads = int(min(args.reads, max(20000, rate * 4.0 / (READ_LEN - k + 1))))
-    bases = _gen.sample_reads_fast(ref_codes, n_reads, READ_LEN, 42, frac_ref, sub)
-    offs = np.arange(n_reads + 1, dtype=np.uint64) * READ_LEN
+    if args.workload in ("config4", "config5-kmers"):
+        print(json.dumps({"impl": "reference", "unavailable": "--impl reference covers the read workloads (config1/2/3/5)"}), flush=True)
+        return
+    if args.workload == "config1":
+        args.mode = "random"
+    port = CpuPort(args)
+    per_step_s = max(0.5, min(4.0, 100.0 / max(1, args.steps + args.warmup)))
+    n_reads = min(args.reads, port.calibrate(per_step_s))
+    bases = port.reads(n_reads, 42)
     for _ in range(args.warmup):
-        os_idx.query_reads(bases[:READ_LEN * 20000], offs[:20001], streaming=streaming, want_hits=True, n_threads=threads)
+        port.run(bases[: READ_LEN * min(n_reads, 20000)])
     t0 = time.time()
     total = 0
     for _ in range(args.steps):
-        _, c, _ = os_idx.query_reads(bases, offs, streaming=streaming, want_hits=True, n_threads=threads)
-        total += int(c[0])
+        n, _, c = port.run(bases)
+        total += int(n)
     dt = time.time() - t0
     v = total / dt
-    sample = "%d reads x %d bp (%d lookups) per step, %d steps" % (n_reads, READ_LEN, n_reads * (READ_LEN - k + 1), args.steps)
+    sample = "%d reads x %d bp (%d lookups) per step, %d steps; %s" % (n_reads, READ_LEN, n_reads * (READ_LEN - port.k + 1), args.steps, port.index_note)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-        "data": "synthetic", "config": {"workload": workload_name(args), "mode": args.mode, "read_len": READ_LEN},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+        "data": "synthetic", "config": bench_config(args),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": port.threads, "kind": "port", "sample": sample,
                          "note": "C++ restatement of mazu's query path (oracle/); the Rust reference cannot be built in this image"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "counts": {"n_kmers": int(c[0]), "n_hit": int(c[1]), "n_miss": int(c[2])},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -234,15 +278,59 @@ def run_reference(args, rank, world):
 
 def workload_name(args):
     return {
-        "config1": "configs[0]: pufferfish yeast_chr01 DenseIndex (PFHash + BooPHF): all reference k-mers + unitig fw/rc k-mers, shuffled (seed 1), k2u_batch",
-        "config2": "configs[1]: SSHash(yeast chr01 unitigs, k=31, m=15, skew=32, seed 0) random-access queries of %d synthetic 150bp reads per GPU "
-                   "(50%% reference-sampled random strand / 50%% uniform random)" % args.reads,
-        "config3": "configs[2]: same SSHash index via as_streaming(), %d synthetic 150bp reads per GPU (70%% reference-sampled with 1%% substitutions / 30%% random)" % args.reads,
-        "config4": "configs[3]: u2pos occurrence decode, synthetic table (4096 refs, max ref 2^27, Zipf(1.2) multiplicity <= 65536), queries ~ multiplicity",
-        "config5": "configs[4]: synthetic unitig set scale %.3g (%d unitigs, len 31+Geom(68)), SSHash k=31 w=19 skew 64, %d synthetic 150bp reads per GPU (70/30 mix)" %
-                   (args.scale, int(HUMAN_UNITIGS * args.scale), args.reads),
-        "config5-kmers": "configs[4] index (scale %.3g) queried with a flat random-order k-mer batch (50%% present / 50%% random), k2u_batch" % args.scale,
+        "config1": "configs[0]: pufferfish yeast_chr01 DenseIndex (PFHash+BooPHF), all ref + unitig k-mers shuffled, k2u_batch",
+        "config2": "configs[1]: SSHash(yeast chr01, k31 m15 skew32), random access, 150bp reads 50% ref / 50% random",
+        "config3": "configs[2]: same SSHash via as_streaming(), 150bp reads 70% ref with 1% subs / 30% random",
+        "config4": "configs[3]: u2pos decode, synthetic table (4096 refs, Zipf(1.2) multiplicity <= 65536)",
+        "config5": "configs[4]: human-scale synthetic SSHash (k31 w19 skew64), 150bp reads 70% ref 1% subs / 30% random",
+        "config5-kmers": "configs[4] index queried with a flat random-order k-mer batch (50% present), k2u_batch",
     }[args.workload]
+
+
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is allocated
+    (first touch places the pages): with 8 ranks on one host, staging through the far socket halves the copy rate."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = open(base + "/local_cpulist").read().strip()
+        if node < 0 or not cpus:
+            return {"numa_node": node, "bound": False}
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return {"numa_node": node, "bound": True, "n_cpus": len(ids)}
+        return {"numa_node": node, "bound": False}
+    except Exception as e:  # not fatal: the run is only slower
+        return {"bound": False, "error": str(e)[:80]}
+
+
+def measured_traffic(W, mode_name, scale):
+    """DRAM bytes per unit of the dominant kernel from the committed ncu captures (profiles/traffic.json): the entry
+    whose workload / mode match and whose index scale is the closest to this run's.  Returns (bytes_per_unit, label)."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None, None
+    best = None
+    for name, e in tj.items():
+        if not isinstance(e, dict) or e.get("workload") != W or e.get("mode", "random") != mode_name:
+            continue
+        d = abs(float(e.get("scale", 1.0)) - scale)
+        if best is None or d < best[0]:
+            best = (d, name, e)
+    if best is None:
+        return None, None
+    _, name, e = best
+    per = e.get("dram_bytes_per_lookup", e.get("dram_bytes_per_unit"))
+    label = "ncu --set full (%s): %d units per captured launch, index scale %s, %s" % (name, e.get("lookups_per_launch", 0), e.get("scale", "n/a"), e.get("_source", ""))
+    return per, label
 
 
 def main():
@@ -269,22 +357,24 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: mazu_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream()
     gen = torch.Generator(device=dev)
     gen.manual_seed(42 + rank)
     mode = mz.MODE_RANDOM if args.mode == "random" else mz.MODE_STREAMING
-    frac_ref, sub_rate = mix_of(args.mode)
     W = args.workload
-    info = {}
+    frac_ref, sub_rate = mix_of(W, args.mode)
+    info = {"host": {"cpus": os.cpu_count(), "numa_binding": numa}}
     unit, metric = UNIT, METRIC
     check = None          # callable -> bool : parity spot check (rank 0)
-    e2e_step = None       # callable: one end-to-end step through host buffers
-    e2e_compact_step = None  # same with 8-byte records
-    e2e_extra = {}        # name -> (callable, d2h bytes per step, api description): further end-to-end variants, reported next to the headline
+    e2e_step = None       # callable: one end-to-end step through host buffers (the headline e2e)
+    e2e_extra = {}        # name -> (callable, units, h2d bytes, d2h bytes or None, api description): further end-to-end variants
     e2e_bytes = (0, 0)
     e2e_units = None      # units per e2e step (defaults to n_units)
+    e2e_api = None
+    e2e_post = None       # callable(e2e dict): checks / extra fields after the e2e loop
     cpu_fn = None         # callable -> cpu_baseline dict
     t_build = time.time()
 
@@ -295,7 +385,6 @@ def main():
         o, os_idx = load_oracle_yeast(sshash=W != "config1")
         ref_codes = yeast_ref_codes(o)
         alg = ALG_PFHASH if W == "config1" else ALG_SSHASH
-        peak_kind = "hbm"
     elif W in ("config5", "config5-kmers"):
         n_unitigs = max(1000, int(HUMAN_UNITIGS * args.scale))
         words, n_bases, accum = _gen.synthetic_unitigs_packed(n_unitigs, 68, 31, seed=45)
@@ -308,14 +397,11 @@ def main():
                          "mphf_levels": index.info(mz.INFO_MPHF_LEVELS)}
         useq_dev = torch.from_numpy(np.concatenate([words, np.zeros(2, dtype=np.uint64)]).view(np.int64)).to(dev)
         alg = ALG_SSHASH
-        peak_kind = "prand"
     else:  # config4
         k = 31
         n_unitigs = 40_000  # Zipf(1.2) clipped to 65,536 has mean ~1,600: 40k unitigs give the ~6e7 occurrences SURVEY 8(d) sizes config 4 for
-        codes, accum = _gen.synthetic_unitigs(2000, 68, k, seed=44)  # the K2U half is irrelevant for the decode; keep it tiny
         rng = np.random.default_rng(44)
-        us = mz.UnitigSet(k, mz.pack_2bit(codes), len(codes), accum)
-        # a unitig set with n_unitigs entries is needed for the offsets vector: build a trivial one
+        # the K2U half is irrelevant for the decode: a trivial unitig set with n_unitigs entries backs the offsets vector
         lens = np.full(n_unitigs, k, dtype=np.uint64)
         accum4 = np.zeros(n_unitigs + 1, dtype=np.uint64)
         np.cumsum(lens, out=accum4[1:])
@@ -333,7 +419,6 @@ def main():
         enc = (ref_ids << np.uint64(pos_bits + 1)) | (poss << np.uint64(1)) | fws
         index.attach_u2pos_piscem(mz.PackedVec.pack(enc, 1 + pos_bits + ref_bits), pos_bits + 1, (1 << pos_bits) - 1, mz.PackedVec.pack(offsets))
         info["index"] = {"n_unitigs": n_unitigs, "n_occs": n_occ, "encoding": "piscem 42-bit packed"}
-        peak_kind = "hbm"
     info["index_build_s"] = round(time.time() - t_build, 2)
     info["index_device_bytes"] = index.device_bytes
     K = index.k
@@ -344,7 +429,7 @@ def main():
         n_reads = args.reads
         n_units = n_reads * nk_per_read
         if W == "config5":
-            bases = _gen.device_reads_from_packed(torch, useq_dev, n_bases, n_reads, READ_LEN, gen, 0.7, 0.01)
+            bases = _gen.device_reads_from_packed(torch, useq_dev, n_bases, n_reads, READ_LEN, gen, frac_ref, sub_rate)
         else:
             ref_t = torch.from_numpy(ref_codes.astype(np.uint8)).to(dev)
             bases = torch.empty(n_reads * READ_LEN, dtype=torch.uint8, device=dev)
@@ -373,47 +458,64 @@ def main():
                               mem=mz.MEM_DEVICE, stream=stream.cuda_stream)
 
         if not args.no_e2e:
-            # pinned host buffers: 150 B in + 1920 B out per read.  With several ranks on one host the e2e step is a
-            # bounded batch of the same reads so that N ranks never pin more than ~8 GB each.
-            e2e_reads = n_reads if world == 1 else min(n_reads, 2_500_000)
+            # Host buffers are pinned.  The headline e2e is the hit-run call on the WHOLE batch at every N (150 B in, ~1.2 B per
+            # lookup out: 10 M reads pin ~5 GB per rank).  The full-record / compact variants move 16 / 8 B per lookup
+            # (19.2 GB for the whole batch): they run on the first --e2e-slice reads of the same batch, at every N alike.
+            e2e_reads = n_reads
             e2e_units = e2e_reads * nk_per_read
+            sl_reads = min(n_reads, args.e2e_slice)
+            sl_units = sl_reads * nk_per_read
             h_bases = torch.empty(e2e_reads * READ_LEN, dtype=torch.uint8, pin_memory=True)
             h_bases.copy_(bases[: e2e_reads * READ_LEN])
-            h_hits = torch.empty((e2e_units, 4), dtype=torch.int32, pin_memory=True)
             h_cnt = np.zeros(3, dtype=np.uint64)
             hb = h_bases.numpy()
-
-            def e2e_step():
-                index.query_reads(hb, None, n_reads=e2e_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=h_hits, counts=h_cnt)
-
-            e2e_bytes = (e2e_reads * READ_LEN, e2e_units * 16 + 24)
-            h_hits8 = torch.empty((e2e_units, 2), dtype=torch.int32, pin_memory=True)
-
-            def e2e_compact_step():
-                index.query_reads(hb, None, n_reads=e2e_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=h_hits8, counts=h_cnt, compact=True)
-
-            def e2e_devout_step():  # reads from pinned host memory, records left in HBM for the next device stage, counters back
-                index.query_reads(hb, None, n_reads=e2e_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=hits, counts=h_cnt,
-                                  mem=mz.MEM_HOST_IN_DEVICE_OUT)
-
-            # hit runs: a lossless compact form of the same records (codes + run starts); the buffers are reused across steps
+            # hit runs: a lossless compact form of the records (codes + run starts); the buffers are reused across steps
             h_codes = torch.empty(e2e_units, dtype=torch.uint8, pin_memory=True)
             h_runs = torch.empty((max(1 << 20, e2e_units // 8), 4), dtype=torch.int32, pin_memory=True)
             h_rro = torch.zeros(e2e_reads + 1, dtype=torch.int64, pin_memory=True)
             runs_state = {"n_runs": 0}
 
-            def e2e_runs_step():
+            def e2e_step():
                 n_runs = C.c_uint64(0)
                 mz._check(mz.lib().mazu_b200_query_reads_runs(index._h, mz._any_ptr(hb), None, e2e_reads, READ_LEN, mode, None, mz._any_ptr(h_codes),
                                                               mz._any_ptr(h_runs), h_runs.shape[0], mz._any_ptr(h_rro), C.byref(n_runs), mz._np_ptr(h_cnt)))
                 runs_state["n_runs"] = n_runs.value
 
-            e2e_extra = {"hit_runs": (e2e_runs_step, None,
-                         "mazu_b200_query_reads_runs: pinned host reads in; one code byte per k-mer slot + the 16-byte record of every run start + "
-                         "per-read run offsets out (lossless: mazu_b200_expand_hit_runs rebuilds the exact records)"),
-                         "host_reads_in_device_records_out": (e2e_devout_step, 24,
-                         "MAZU_MEM_HOST_IN_DEVICE_OUT: pinned host reads in, 16-byte records stay in HBM (input of project_hits on the device), "
-                         "the three counters of `kphf bench` (src/bin/kphf/main.rs:282-284) come back")}
+            e2e_api = ("mazu_b200_query_reads_runs (C ABI, host buffers): pinned ASCII reads in; out: one code byte per k-mer slot + the 16-byte "
+                       "record of every run start + per-read run offsets (lossless: mazu_b200_expand_hit_runs rebuilds every record)")
+
+            def e2e_post(e):
+                e["h2d_bytes_per_step"] = e2e_reads * READ_LEN * world
+                e["d2h_bytes_per_step"] = (e2e_units + 16 * runs_state["n_runs"] + 8 * (e2e_reads + 1) + 24) * world
+                e["n_runs_per_step_per_gpu"] = runs_state["n_runs"]
+                m = min(e2e_reads, 20000)  # the expansion on the host reproduces the full records (checked on the head of the batch)
+                exp = mz.ModIndex.expand_hit_runs(h_codes.numpy()[: m * nk_per_read], h_runs.numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE),
+                                                  h_rro.numpy().view(np.uint64)[: m + 1], uniform_slots=nk_per_read)
+                e["expands_to_full_records"] = bool(np.array_equal(exp.view(np.uint32).reshape(-1, 4), hits[: m * nk_per_read].cpu().numpy().view(np.uint32)))
+                e["counts_match_device_path"] = bool(int(h_cnt[0]) == e2e_units and int(h_cnt[1]) > 0)
+
+            h_hits = torch.empty((sl_units, 4), dtype=torch.int32, pin_memory=True)
+            hb_sl = hb[: sl_reads * READ_LEN]
+
+            def e2e_full_step():
+                index.query_reads(hb_sl, None, n_reads=sl_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=h_hits, counts=h_cnt)
+
+            def e2e_compact_step():  # the 8-byte records reuse the first half of the same pinned buffer
+                index.query_reads(hb_sl, None, n_reads=sl_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=h_hits, counts=h_cnt, compact=True)
+
+            def e2e_devout_step():  # reads from pinned host memory, records left in HBM for the next device stage, counters back
+                index.query_reads(hb, None, n_reads=e2e_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=hits, counts=h_cnt,
+                                  mem=mz.MEM_HOST_IN_DEVICE_OUT)
+
+            e2e_extra = {
+                "full_records": (e2e_full_step, sl_units, sl_reads * READ_LEN, sl_units * 16 + 24,
+                                 "mazu_b200_query_reads(MAZU_MEM_HOST): every 16-byte record over PCIe; first %d reads of the batch" % sl_reads),
+                "compact_records": (e2e_compact_step, sl_units, sl_reads * READ_LEN, sl_units * 8 + 24,
+                                    "mazu_b200_query_reads_compact: 8-byte {unitig_id, pos|match<<30} records; first %d reads of the batch" % sl_reads),
+                "host_reads_in_device_records_out": (e2e_devout_step, e2e_units, e2e_reads * READ_LEN, 24,
+                                                     "MAZU_MEM_HOST_IN_DEVICE_OUT: pinned host reads in, 16-byte records stay in HBM (input of project_hits on the "
+                                                     "device), the three counters of `kphf bench` (src/bin/kphf/main.rs:282-284) come back"),
+            }
 
         def check():
             if W == "config5":  # no oracle index at this scale: verify sampled hits directly against the packed sequence
@@ -437,6 +539,11 @@ def main():
                 rc = np.array([_oracle.lib().orc_revcomp(int(x), K) for x in fw[~ident][:20000]], dtype=np.uint64)
                 ok = bool(np.array_equal(uk[ident], fw[ident])) and bool(np.array_equal(uk[~ident][:20000], rc))
                 ok &= bool((h["unitig_len"][slot] == (accum[h["unitig_id"][slot].astype(np.int64) + 1] - accum[h["unitig_id"][slot].astype(np.int64)])).all())
+                # the hit fraction must match the generator: 70 % of reads x 0.99^31 surviving k-mers x the ~70 % of a read's windows
+                # that do not straddle a unitig boundary (unitigs of mean length 98) = 35.5 %; completeness is checked exactly
+                # against the CPU port on its own index (cpu_baseline.gpu_path_equals_port_on_its_index)
+                frac = len(slot) / float(len(h))
+                ok &= 0.30 < frac < 0.42
                 return ok and len(slot) > 0
             n_chk = min(n_reads, 5000)
             chk = bases[: n_chk * READ_LEN].cpu().numpy()
@@ -444,15 +551,26 @@ def main():
             got = hits[: n_chk * nk_per_read].cpu().numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE)
             return bool(np.array_equal(got, want))
 
-        if W != "config5":
-            def cpu_fn():
-                threads = os.cpu_count() or 1
-                v, n_s, dt, c = time_oracle_reads(os_idx, ref_codes, args.cpu_seconds, args.mode, threads, K)
-                v1, _, _, _ = time_oracle_reads(os_idx, ref_codes, min(args.cpu_seconds, 6.0), args.mode, 1, K)
-                return {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": "%d reads x %d bp (%d lookups) of the same workload, %.1f s" % (n_s, READ_LEN, int(c[0]), dt),
-                        "single_thread_value": v1, "ns_per_kmer_single_thread": 1e9 / v1,
-                        "note": "C++ restatement of mazu's query path (oracle/); the Rust reference cannot be built in this image"}
+        def cpu_fn():
+            port = CpuPort(args)
+            n_s = port.calibrate(args.cpu_seconds)
+            sample = port.reads(n_s, 4243)
+            n, dt, c = port.run(sample)
+            n1_s = max(20000, n_s // port.threads)
+            n1, dt1, _ = port.run(sample[: n1_s * READ_LEN], threads=1)
+            out = {"value": n / dt, "unit": UNIT, "cores": port.threads, "kind": "port",
+                   "sample": "%d reads x %d bp (%d lookups) of the same read mix, %.1f s; %s" % (n_s, READ_LEN, int(c[0]), dt, port.index_note),
+                   "single_thread_value": n1 / dt1, "ns_per_kmer_single_thread": 1e9 / (n1 / dt1),
+                   "hit_fraction": float(c[1]) / max(1.0, float(c[0])),
+                   "note": "C++ restatement of mazu's query path (oracle/); the Rust reference cannot be built in this image"}
+            if W == "config5":  # the port against the GPU path on the port's own (smaller) index: same reads, same answers
+                small = _gen.synthetic_unitigs_packed(max(1000, int(HUMAN_UNITIGS * port.scale)), 68, 31, seed=45)
+                g_small = mz.SSHash.from_unitig_set(mz.UnitigSet(31, *small), 19, 64, seed=0, device=local_rank, builder="gpu")
+                m = min(n_s, 20000)
+                got, _, _ = g_small.query_reads(sample[: m * READ_LEN], None, uniform_read_len=READ_LEN, mode=mode)
+                want, _, _ = port.idx.query_reads(sample[: m * READ_LEN], np.arange(m + 1, dtype=np.uint64) * READ_LEN, streaming=(mode == mz.MODE_STREAMING))
+                out["gpu_path_equals_port_on_its_index"] = bool(np.array_equal(got, want))
+            return out
 
     elif W in ("config1", "config5-kmers"):
         if W == "config1":
@@ -478,15 +596,20 @@ def main():
             index.k2u_batch(kmers, out=hits, mem=mz.MEM_DEVICE, stream=stream.cuda_stream, n=n_units)
 
         if not args.no_e2e:
-            h_k = torch.empty(n_units, dtype=torch.int64, pin_memory=True)
-            h_k.copy_(kmers)
-            h_hits = torch.empty((n_units, 4), dtype=torch.int32, pin_memory=True)
+            e2e_units = min(n_units, args.e2e_slice * nk_per_read)
+            h_k = torch.empty(e2e_units, dtype=torch.int64, pin_memory=True)
+            h_k.copy_(kmers[:e2e_units])
+            h_hits = torch.empty((e2e_units, 4), dtype=torch.int32, pin_memory=True)
             hk = h_k.numpy().view(np.uint64)
 
             def e2e_step():
                 index.k2u_batch(hk, out=h_hits)
 
-            e2e_bytes = (n_units * 8, n_units * 16)
+            e2e_bytes = (e2e_units * 8, e2e_units * 16)
+            e2e_api = "mazu_b200_k2u_batch(MAZU_MEM_HOST): pinned k-mer words in, every 16-byte record out; first %d k-mers of the batch" % e2e_units
+
+            def e2e_post(e):
+                e["matches_device_path"] = bool(torch.equal(h_hits[:1_000_000], hits[:1_000_000].cpu()))
 
         def check():
             n_chk = min(n_units, 200000)
@@ -586,6 +709,33 @@ def main():
             ok &= np.array_equal(out_h[offs_h[:-1].astype(np.int64), 1], poss[first].astype(np.uint32))
             return bool(ok)
 
+        def cpu_fn():
+            """the port's U2Pos decode (decode_unitig_occs, dense_unitig_table.rs:127-153) on the same table, all host threads"""
+            import _oracle
+            threads = os.cpu_count() or 1
+            o4 = _oracle.OracleIndex.from_packed(k, words4, int(accum4[-1]), accum4, 0)
+            o4.attach_u2pos(1, offsets, ref_ids, poss, fws, max_ref_len, n_refs)
+            # bounded sample: queries whose lists sum to ~1.5e8 occurrences per thread-second budget
+            budget = int(2.5e7 * args.cpu_seconds * threads / 4)
+            n_s = int(max(1, min(n_q, np.searchsorted(cum, budget))))
+            parts = np.array_split(qids[:n_s], threads)
+            done = [0] * threads
+
+            def work(t):
+                offs_t, occ_t = o4.decode_occs(parts[t])
+                done[t] = len(occ_t)
+
+            ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+            t0 = time.time()
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+            dt = time.time() - t0
+            return {"value": sum(done) / dt, "unit": unit, "cores": threads, "kind": "port",
+                    "sample": "%d of the same queries (%d occurrences), %.1f s" % (n_s, sum(done), dt),
+                    "note": "C++ restatement of PiscemUnitigTable::decode_unitig_occs (oracle/), one slice of the queries per host thread"}
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -621,65 +771,42 @@ def main():
     value = float(n_units) * args.steps * world / (max_ms * 1e-3)
     kernel_ms = float(np.mean(step_ms))
 
-    e2e = None
-    if e2e_step is not None:
-        e2e_step()
+    def timed_host_loop(fn):
+        """K end-to-end steps through host buffers between barriers: wall clock, max over ranks."""
+        fn()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            e2e_step()
+            fn()
         barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    e2e = None
+    if e2e_step is not None:
+        dt = timed_host_loop(e2e_step)
         eu = e2e_units if e2e_units is not None else n_units
-        e2e = {"value": float(eu) * args.steps * world / float(tt.item()), "unit": unit, "units_per_step_per_gpu": eu,
-               "h2d_bytes_per_step": e2e_bytes[0] * world,
-               "d2h_bytes_per_step": e2e_bytes[1] * world, "steps": args.steps,
-               "api": "C ABI with MAZU_MEM_HOST: pinned host inputs in, every result record out",
-               "matches_device_path": bool(torch.equal(h_hits[:1_000_000], hits[:1_000_000].cpu()))}
-        try:  # what bounds it: the box's pinned-copy bandwidth with both directions busy (profiles/pcie_probe.py)
+        e2e = {"value": float(eu) * args.steps * world / dt, "unit": unit, "units_per_step_per_gpu": eu,
+               "h2d_bytes_per_step": e2e_bytes[0] * world, "d2h_bytes_per_step": e2e_bytes[1] * world, "steps": args.steps, "api": e2e_api}
+        if e2e_post is not None:
+            e2e_post(e2e)
+        pc = None
+        try:  # the box's pinned-copy bandwidth (profiles/pcie_probe.py): what bounds the variants that move every record
             pc = json.load(open(os.path.join(ROOT, "profiles", "r01_pcie.json")))
-            d2h_gbs = e2e_bytes[1] * args.steps / float(tt.item()) / 1e9
-            e2e["bound"] = {"kind": "pcie d2h (16 B per lookup out)", "achieved_d2h_gbs_per_gpu": d2h_gbs, "measured_d2h_peak_gbs": pc["d2h_gbs"],
-                            "measured_d2h_with_h2d_busy_gbs": pc["duplex_each_gbs"], "frac_of_d2h_peak": d2h_gbs / pc["d2h_gbs"]}
         except Exception:
             pass
-        if e2e_compact_step is not None:
-            e2e_compact_step()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                e2e_compact_step()
-            barrier()
-            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e["compact_records"] = {"value": float(eu) * args.steps * world / float(tt.item()), "unit": unit,
-                                      "d2h_bytes_per_step": (eu * 8 + 24) * world,
-                                      "api": "mazu_b200_query_reads_compact: 8-byte {unitig_id, pos|match<<30} records"}
-
-        for name, (fn, d2h, api) in e2e_extra.items():
-            fn()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                fn()
-            barrier()
-            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            if name == "hit_runs":
-                d2h = eu + 16 * runs_state["n_runs"] + 8 * (e2e_reads + 1) + 24
-            e2e[name] = {"value": float(eu) * args.steps * world / float(tt.item()), "unit": unit, "h2d_bytes_per_step": e2e_bytes[0] * world,
-                         "d2h_bytes_per_step": d2h * world, "api": api}
-            if name == "hit_runs":  # the expansion on the host reproduces the full records (checked on the head of the batch)
-                m = min(e2e_reads, 20000)
-                exp = mz.ModIndex.expand_hit_runs(h_codes.numpy()[: m * nk_per_read], h_runs.numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE),
-                                                  h_rro.numpy().view(np.uint64)[: m + 1], uniform_slots=nk_per_read)
-                e2e[name]["expands_to_full_records"] = bool(np.array_equal(exp.view(np.uint32).reshape(-1, 4), hits[: m * nk_per_read].cpu().numpy().view(np.uint32)))
-                e2e[name]["n_runs_per_step_per_gpu"] = runs_state["n_runs"]
+        for name, (fn, units, h2d, d2h, api) in e2e_extra.items():
+            dtx = timed_host_loop(fn)
+            e2e[name] = {"value": float(units) * args.steps * world / dtx, "unit": unit, "units_per_step_per_gpu": units,
+                         "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "api": api}
+            if name == "full_records":
+                e2e[name]["matches_device_path"] = bool(torch.equal(h_hits[:1_000_000], hits[:1_000_000].cpu()))
+                if pc:
+                    d2h_gbs = d2h * args.steps / dtx / 1e9
+                    e2e[name]["bound"] = {"kind": "pcie d2h (16 B per lookup out)", "achieved_d2h_gbs_per_gpu": d2h_gbs, "measured_d2h_peak_gbs": pc["d2h_gbs"],
+                                          "measured_d2h_with_h2d_busy_gbs": pc["duplex_each_gbs"], "frac_of_d2h_peak": d2h_gbs / pc["d2h_gbs"]}
 
     if rank != 0:
         if world > 1:
@@ -696,68 +823,69 @@ def main():
                                      "note": "failures that are not 'not found' are duplicated canonical k-mers of the random unitig set (expected ~1.3 pairs at 2.5e9 k-mers)"}
     cpu = cpu_fn() if (cpu_fn and not args.no_cpu_baseline and world == 1) else None
 
+    # ---------------------------------------------------------------- roofline
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):
         peaks = json.load(open(pk_path))
-    achieved = n_units * alg / (kernel_ms * 1e-3) / 1e9
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_source = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+    alg_gbs = n_units * alg / (kernel_ms * 1e-3) / 1e9
+    per_unit, traffic_label = measured_traffic(W, args.mode, args.scale if W.startswith("config5") else 1.0)
+    traffic = per_unit * n_units if per_unit is not None else None
+    index_in_l2 = index.device_bytes < (100 << 20)
     if W == "config4":
-        note = "streaming decode: algorithmic bytes = 32 B (offset pair) per queried unitig + 6 B packed word in + 12 B record out per occurrence"
+        roof = {"bound": "hbm", "achieved": alg_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": alg_gbs / hbm_peak, "traffic": traffic,
+                "peak_source": hbm_source, "algorithmic_bytes_per_unit": alg,
+                "note": "streaming decode: algorithmic bytes = 32 B (offset pair) per queried unitig + 6 B packed word in + 12 B record out per occurrence"}
+    elif index_in_l2:
+        # configs[0..2]: the index (0.4 MB) lives in L1/L2, DRAM only carries the compulsory stream (read bases in, records out),
+        # so the HBM roofline of these launches is that stream; the kernel itself is issue-bound
+        stream_b = 17.25 if W != "config1" else 24.0
+        ach = n_units * stream_b / (kernel_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "peak_source": hbm_source,
+                "algorithmic_bytes_per_unit": stream_b,
+                "note": "index is L2-resident: the only bytes that must cross DRAM are the stream (%.2f B per lookup: read bases in + 16-byte record out); "
+                        "the SURVEY 8(d) ideal-layout figure (%.2f B, every structure touch a DRAM sector) is reported as `survey_8d` and is NOT an HBM "
+                        "fraction here; the kernel is issue-bound (ncu: profiles/*prof_random.summary.txt)" % (stream_b, alg),
+                "survey_8d": {"bytes_per_unit": alg, "gbs": alg_gbs, "ratio_to_hbm_peak": alg_gbs / hbm_peak}}
     else:
-        note = ("algorithmic bytes = SURVEY 8(d) ideal-layout figure with nothing cached or shared; consecutive k-mers of a read share "
-                "minimizer, bucket and window sectors and small indexes are L2-resident, so `traffic` (measured DRAM bytes) is far below it "
-                "and frac can exceed 1 -- see DESIGN.md 7b for the DRAM/issue figures from ncu")
-    if peak_kind == "hbm":
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_source = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
-    else:
-        pr = json.load(open(os.path.join(ROOT, "profiles", "r01_prand.json")))
-        peak = float(pr["32GiB"]["GBps"])
-        peak_source = "P_rand: measured independent random 32-byte gathers over a 32 GiB table (profiles/r01_prand.json), in GB/s of sectors"
-    traffic = None
-    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr_path):
+        # configs[4]: random-access regime.  A random access moves one 128-byte DRAM line whatever it uses of it (ncu on the probe),
+        # so the ceiling is the measured random LINE rate P_rand, and what the kernel achieves is the DRAM bytes it really moves.
         try:
-            tj = json.load(open(tr_path))
-            if W in ("config2", "config3"):
-                per = tj.get("query_reads_kernel<%d>" % (0 if mode == mz.MODE_RANDOM else 1), {}).get("dram_bytes_per_lookup")
-            elif W == "config5" and mode == mz.MODE_RANDOM:
-                per = tj.get("config5 query_reads_kernel<0>", {}).get("dram_bytes_per_lookup")
-            elif W == "config5-kmers":
-                per = tj.get("config5 k2u_batch_kernel", {}).get("dram_bytes_per_lookup")
-            else:
-                per = None
-            traffic = per * n_units if per is not None else None
-            if W == "config4":
-                traffic = tj.get("occ_fill_kernel<false>", {}).get("dram_bytes_per_launch")
+            pr = json.load(open(os.path.join(ROOT, "profiles", "r02_prand.json")))
+            p_lines, p_src = float(pr["lines_per_s"]), "profiles/r02_prand.json (max over the granule / loads-in-flight / occupancy sweep, %s GiB table)" % pr.get("table_gib")
         except Exception:
-            traffic = None
+            pr = json.load(open(os.path.join(ROOT, "profiles", "r01_prand.json")))
+            p_lines, p_src = float(pr["32GiB"]["sectors_per_s"]), "profiles/r01_prand.json (round-1 probe: one configuration only)"
+        peak = p_lines * 128 / 1e9
+        if per_unit is not None:
+            ach = per_unit * n_units / (kernel_ms * 1e-3) / 1e9
+            how = "DRAM bytes per lookup measured by ncu x lookups / CUDA-event kernel time"
+        else:
+            ach, how = alg_gbs, "no ncu capture for this workload/scale: SURVEY 8(d) algorithmic bytes / kernel time"
+        roof = {"bound": "hbm", "regime": "random access (128-byte DRAM lines)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "peak_source": "P_rand = %.4g random 128-byte lines/s x 128 B: %s" % (p_lines, p_src), "achieved_source": how,
+                "dram_lines_per_unit": (per_unit / 128.0) if per_unit is not None else None, "frac_of_hbm_copy_peak": ach / hbm_peak,
+                "survey_8d": {"bytes_per_unit": alg, "gbs": alg_gbs, "ratio_to_hbm_peak": alg_gbs / hbm_peak, "ratio_to_p_rand": alg_gbs / peak,
+                              "note": "ideal-layout figure with nothing shared between the k-mers of a read: a label, not a DRAM measurement"}}
+    roof.update({"traffic_source": traffic_label, "units_per_launch": n_units, "kernel_ms": kernel_ms, "step_ms": [round(x, 3) for x in step_ms]})
+
+    cfg = bench_config(args)
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-        "data": "synthetic (torch.Generator seed 42+rank on the device; fixture sequences from tests/data)",
-        "config": {"workload": workload_name(args), "mode": args.mode, "units_per_step_per_gpu": n_units,
-                   "parallelism": "index replicated x%d, inputs sharded by batch, no collective" % world,
-                   "l2_policy": "inputs and results per step (%.2f GB) are larger than the 126 MB L2" % ((e2e_bytes[0] + e2e_bytes[1]) / 1e9 if e2e_bytes[0] else n_units * 17.25 / 1e9)},
+        "data": "synthetic (torch.Generator seed 42+rank on the device; unitig set: numpy seed 45 / fixture sequences from tests/data)",
+        "config": cfg,
+        "l2_policy": "inputs + results per step (%.2f GB) are larger than the 126 MB L2%s" %
+                     (n_units * 17.25 / 1e9, "" if index_in_l2 else "; so is the index (%.1f GB)" % (index.device_bytes / 1e9)),
+        "parallelism": "index replicated x%d, inputs sharded by batch, no collective" % world,
         "clocks": clk.summary(),
         "gpu_launches": args.steps * launches_per_step,
         "kernel": kernel_name,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_source, "algorithmic_bytes_per_unit": alg, "units_per_launch": n_units, "kernel_ms": kernel_ms,
-                     "step_ms": [round(x, 3) for x in step_ms], "note": note,
-                     # what the kernel is actually limited by (ncu, profiles/*.summary.txt): measured DRAM bytes / time against the same peak
-                     "dram_frac_measured": (traffic / (kernel_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0))) if traffic else None},
+        "roofline": roof,
         "parity_spot_check": parity_ok,
     }
-    # both denominators, always -- the streaming HBM peak and the measured random-gather rate (32-byte sectors)
-    try:
-        pr = json.load(open(os.path.join(ROOT, "profiles", "r01_prand.json")))
-        p_rand = float(pr["32GiB"]["GBps"])
-        line["roofline"]["vs_hbm_stream_peak"] = achieved / float(peaks.get("hbm_gbs", 6650.0))
-        line["roofline"]["vs_random_gather_peak"] = achieved / p_rand
-        line["roofline"]["random_gather_peak_gbs_of_sectors"] = p_rand
-    except Exception:
-        pass
     line.update(info)
     if cnt_line:
         line["counts"] = cnt_line

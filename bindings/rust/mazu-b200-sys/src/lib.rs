@@ -68,6 +68,10 @@ pub struct mazu_index_t {
     _private: [u8; 0],
 }
 #[repr(C)]
+pub struct mazu_fasta_t {
+    _private: [u8; 0],
+}
+#[repr(C)]
 pub struct mazu_unitig_set_desc_t {
     pub k: u32,
     pub useq_words: *const u64,
@@ -147,5 +151,17 @@ extern "C" {
     pub fn mazu_b200_k2u_validate_self(idx: *const mazu_index_t, counts: *mut u64) -> mazu_status_t;
     pub fn mazu_b200_alloc_pinned(bytes: u64, out: *mut *mut c_void) -> mazu_status_t;
     pub fn mazu_b200_free_pinned(p: *mut c_void);
+    pub fn mazu_b200_unitig_seq(idx: *const mazu_index_t, unitig_id: u64, out_words: *mut u64, cap_words: u64, len: *mut u64) -> mazu_status_t;
+    pub fn mazu_b200_fasta_open(path: *const c_char, out: *mut *mut mazu_fasta_t) -> mazu_status_t;
+    pub fn mazu_b200_fasta_close(f: *mut mazu_fasta_t);
+    pub fn mazu_b200_fasta_n_records(f: *const mazu_fasta_t) -> u64;
+    pub fn mazu_b200_fasta_bases(f: *const mazu_fasta_t) -> *const u8;
+    pub fn mazu_b200_fasta_offsets(f: *const mazu_fasta_t) -> *const u64;
+    pub fn mazu_b200_fasta_name(f: *const mazu_fasta_t, record: u64) -> *const c_char;
+    pub fn mazu_b200_validate_fasta(idx: *const mazu_index_t, path: *const c_char, mode: i32, counts: *mut u64) -> mazu_status_t;
+    pub fn mazu_b200_validate_reads(idx: *const mazu_index_t, bases: *const u8, read_offsets: *const u64, n_reads: u64, mode: i32, counts: *mut u64) -> mazu_status_t;
+    pub fn mazu_b200_index_replicate(src: *const mazu_index_t, devices: *const i32, n_devices: i32, out: *mut *mut mazu_index_t) -> mazu_status_t;
+    pub fn mazu_b200_query_reads_sharded(handles: *const *const mazu_index_t, n_handles: i32, bases: *const u8, read_offsets: *const u64, n_reads: u64, uniform_read_len: u64, mode: i32, kmer_offsets: *mut u64, out_hits: *mut mazu_hit_t, counts: *mut u64) -> mazu_status_t;
+    pub fn mazu_b200_query_reads_runs_sharded(handles: *const *const mazu_index_t, n_handles: i32, bases: *const u8, read_offsets: *const u64, n_reads: u64, uniform_read_len: u64, mode: i32, kmer_offsets: *mut u64, out_codes: *mut u8, out_runs: *mut mazu_hit_t, cap_runs: u64, out_read_run_offsets: *mut u64, out_n_runs: *mut u64, counts: *mut u64) -> mazu_status_t;
     pub fn mazu_b200_debug_gather_probe(table_bytes: u64, n_items: u64, granule_bytes: i32, ilp: i32, blocks_per_sm: i32, iters: i32, device: i32, items_per_s: *mut f64) -> mazu_status_t;
 }

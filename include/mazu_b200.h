@@ -179,6 +179,10 @@ enum { MAZU_INFO_K = 0, MAZU_INFO_N_UNITIGS = 1, MAZU_INFO_N_KMERS = 2, MAZU_INF
 uint64_t mazu_b200_index_info(const mazu_index_t* idx, int32_t what);
 /* K2U::unitig_len(id)  src/kphf/mod.rs:61 ; UnitigSet::unitig_start_pos  src/unitig_set.rs:197-199 */
 mazu_status_t mazu_b200_unitig_len(const mazu_index_t* idx, uint64_t unitig_id, uint64_t* len, uint64_t* start_pos);
+/* K2U::unitig_seq(id) (src/kphf/mod.rs:64; UnitigSet::unitig_seq src/unitig_set.rs:189-195): the unitig's bases as 2-bit codes
+ * packed LSB-first into out_words (base j at bits [2j, 2j+2) of the word array, ceil(len / 32) words; cap_words is the
+ * capacity).  Served from the handle's host-side UnitigSet, so a Rust `impl K2U` needs no copy of its own. */
+mazu_status_t mazu_b200_unitig_seq(const mazu_index_t* idx, uint64_t unitig_id, uint64_t* out_words, uint64_t cap_words, uint64_t* len);
 
 /* ---------------------------------------------------------------------------------------------
  * Queries
@@ -239,7 +243,10 @@ mazu_status_t mazu_b200_encode_reads(const mazu_index_t* idx, const uint8_t* bas
  * UnitigOcc::decode_piscem src/spt_compact.rs:99-110).  unitig id ~0 (a miss) yields an empty list.
  *   out_offsets  n+1 prefix of list lengths (always written)
  *   out_occs     capacity `cap` records; may be NULL to only size the output (then *out_total is the need)
- * Returns MAZU_ERR_INVALID_ARG if cap is too small (out_total still valid). */
+ * Returns MAZU_ERR_INVALID_ARG if cap is too small (out_total still valid).  With MAZU_MEM_DEVICE and out_total == NULL
+ * the call does not synchronise and cannot return that error: an undersized buffer is then filled up to `cap` records,
+ * never beyond, and out_offsets[n] (device) holds the size the full output needs.  Unitig ids outside the table
+ * (including ~0) yield empty lists. */
 mazu_status_t mazu_b200_decode_occs(const mazu_index_t* idx, const uint32_t* unitig_ids, uint64_t n, uint64_t* out_offsets,
                                     mazu_occ_t* out_occs, uint64_t cap, uint64_t* out_total, int32_t mem, void* stream);
 /* GetRefPos::project_hits / project_onto_u_occs for a batch of hits (src/index.rs:174-216): same output
@@ -261,6 +268,55 @@ mazu_status_t mazu_b200_validate_self(const mazu_index_t* idx, uint64_t counts[5
  * counts[3] = failures that were plain misses (the rest of n_fail found the k-mer at ANOTHER position, i.e. the
  * unitig set holds a duplicated canonical k-mer, which the reference's validate_self would also reject). */
 mazu_status_t mazu_b200_k2u_validate_self(const mazu_index_t* idx, uint64_t counts[5]);
+
+/* ---------------------------------------------------------------------------------------------
+ * FASTA / FASTQ ingest and Validate::validate_fasta  (the caller on the other side of the path)
+ * ------------------------------------------------------------------------------------------- */
+/* FastaReader (src/util.rs:93-149): a record starts at a line beginning with '>' (the rest of the line is its name, verbatim),
+ * every following line up to the next '>' is appended to its sequence.  A file whose first byte is '@' is read as FASTQ
+ * (records of four lines: @name, sequence, +, qualities).  '\r' before a line end is dropped.  The whole file is held in memory. */
+typedef struct mazu_fasta mazu_fasta_t;
+mazu_status_t mazu_b200_fasta_open(const char* path, mazu_fasta_t** out);
+void mazu_b200_fasta_close(mazu_fasta_t* f);
+uint64_t mazu_b200_fasta_n_records(const mazu_fasta_t* f);
+/* the records' sequences, concatenated (ASCII, as in the file), and n_records + 1 byte offsets: the (bases, read_offsets) pair
+ * mazu_b200_query_reads takes.  The pointers stay valid until mazu_b200_fasta_close. */
+const uint8_t* mazu_b200_fasta_bases(const mazu_fasta_t* f);
+const uint64_t* mazu_b200_fasta_offsets(const mazu_fasta_t* f);
+const char* mazu_b200_fasta_name(const mazu_fasta_t* f, uint64_t record);
+/* Validate::validate_fasta (src/index/validate.rs:83-100) with mode = MAZU_MODE_RANDOM; StreamingIndex::validate_fasta
+ * (src/index/caching.rs:204-218) with MAZU_MODE_STREAMING: record i of the file is reference i, and every k-mer the
+ * CanonicalKmerIterator yields at position p of record i (windows with a non-ACGT base are skipped, lower case counts as upper)
+ * must be found and project onto (ref i, pos p).  Lookups and the check of the projected positions run on the device.
+ * counts = {n_queries, n_identity, n_twin, n_projected, n_fail}; the reference panics when n_fail != 0. */
+mazu_status_t mazu_b200_validate_fasta(const mazu_index_t* idx, const char* path, int32_t mode, uint64_t counts[5]);
+/* the same check for records already in memory (validate_ckmers over a batch, src/index/validate.rs:54-81): host buffers */
+mazu_status_t mazu_b200_validate_reads(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                                       int32_t mode, uint64_t counts[5]);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: the index is immutable, so it is REPLICATED per device and reads are SHARDED in contiguous
+ * blocks; no collective on the data path, the counters of the shards are summed on the host -- the shape of
+ * K2U::validate_self_parallel (src/kphf/mod.rs:105-139: rayon over independent units, one reduction at the end).
+ * ------------------------------------------------------------------------------------------- */
+/* Copies every device table of `src` onto each device of `devices` with device-to-device copies (NVLink peer copies where
+ * the devices can reach each other; no host-side rebuild, no second upload): out[i] is an independent handle on
+ * devices[i] that shares src's host-side metadata.  A device equal to src's own gets a full copy too. */
+mazu_status_t mazu_b200_index_replicate(const mazu_index_t* src, const int32_t* devices, int32_t n_devices, mazu_index_t** out);
+/* mazu_b200_query_reads (host buffers) over n replicas: reads are cut into n contiguous blocks of about equal size in
+ * bases, block i runs on handles[i] from its own host thread with its own streams, every record lands in its slot of
+ * out_hits, counts is the sum over the shards.  All handles must hold the same index (same k, unitigs, K2U). */
+mazu_status_t mazu_b200_query_reads_sharded(const mazu_index_t* const* handles, int32_t n_handles, const uint8_t* bases,
+                                            const uint64_t* read_offsets, uint64_t n_reads, uint64_t uniform_read_len, int32_t mode,
+                                            uint64_t* kmer_offsets, mazu_hit_t* out_hits, uint64_t* counts);
+/* mazu_b200_query_reads_runs over n replicas.  out_runs is cut into n regions of cap_runs / n records, shard i fills region
+ * i; out_read_run_offsets[r] (n_reads entries are meaningful) is the index in out_runs of read r's first run, which is all
+ * mazu_b200_expand_hit_runs needs -- the runs of different shards are NOT adjacent.  *out_n_runs = total number of runs;
+ * MAZU_ERR_INVALID_ARG if a shard's region is too small (then *out_n_runs = n x the largest shard's need). */
+mazu_status_t mazu_b200_query_reads_runs_sharded(const mazu_index_t* const* handles, int32_t n_handles, const uint8_t* bases,
+                                                 const uint64_t* read_offsets, uint64_t n_reads, uint64_t uniform_read_len, int32_t mode,
+                                                 uint64_t* kmer_offsets, uint8_t* out_codes, mazu_hit_t* out_runs, uint64_t cap_runs,
+                                                 uint64_t* out_read_run_offsets, uint64_t* out_n_runs, uint64_t* counts);
 
 /* ---------------------------------------------------------------------------------------------
  * Page-locked host memory for MAZU_MEM_HOST callers that do not link the CUDA runtime themselves (a Rust

@@ -135,6 +135,18 @@ def _signatures():
         "mazu_b200_iter_unitigs_on_ref": (i32, [vp, u64, vp, u64, vp]),
         "mazu_b200_validate_self": (i32, [vp, vp]),
         "mazu_b200_k2u_validate_self": (i32, [vp, vp]),
+        "mazu_b200_unitig_seq": (i32, [vp, u64, vp, u64, vp]),
+        "mazu_b200_fasta_open": (i32, [cp, pp]),
+        "mazu_b200_fasta_close": (None, [vp]),
+        "mazu_b200_fasta_n_records": (u64, [vp]),
+        "mazu_b200_fasta_bases": (vp, [vp]),
+        "mazu_b200_fasta_offsets": (vp, [vp]),
+        "mazu_b200_fasta_name": (cp, [vp, u64]),
+        "mazu_b200_validate_fasta": (i32, [vp, cp, i32, vp]),
+        "mazu_b200_validate_reads": (i32, [vp, vp, vp, u64, i32, vp]),
+        "mazu_b200_index_replicate": (i32, [vp, vp, i32, pp]),
+        "mazu_b200_query_reads_sharded": (i32, [vp, i32, vp, vp, u64, u64, i32, vp, vp, vp]),
+        "mazu_b200_query_reads_runs_sharded": (i32, [vp, i32, vp, vp, u64, u64, i32, vp, vp, vp, u64, vp, vp, vp]),
         "mazu_b200_debug_gather_probe": (i32, [u64, u64, i32, i32, i32, i32, i32, C.POINTER(C.c_double)]),
     }
 
@@ -511,8 +523,108 @@ class ModIndex:
         _check(lib().mazu_b200_k2u_validate_self(self._h, _np_ptr(c)))
         return [int(x) for x in c]
 
+    def validate_fasta(self, path, mode=MODE_RANDOM):
+        """Validate::validate_fasta / StreamingIndex::validate_fasta: the library reads the file (FASTA or FASTQ)."""
+        c = np.zeros(5, dtype=np.uint64)
+        _check(lib().mazu_b200_validate_fasta(self._h, os.fspath(path).encode(), mode, _np_ptr(c)))
+        return [int(x) for x in c]
+
+    def validate_reads(self, bases, read_offsets, mode=MODE_RANDOM):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        ro = np.ascontiguousarray(read_offsets, dtype=np.uint64)
+        c = np.zeros(5, dtype=np.uint64)
+        _check(lib().mazu_b200_validate_reads(self._h, _np_ptr(bases), _np_ptr(ro), len(ro) - 1, mode, _np_ptr(c)))
+        return [int(x) for x in c]
+
+    def unitig_seq(self, ui):
+        """K2U::unitig_seq(id) as a string."""
+        n = C.c_uint64(0)
+        _check(lib().mazu_b200_unitig_seq(self._h, ui, None, 0, C.byref(n)))
+        w = np.zeros((n.value + 31) // 32, dtype=np.uint64)
+        _check(lib().mazu_b200_unitig_seq(self._h, ui, _np_ptr(w), len(w), C.byref(n)))
+        codes = ((w[:, None] >> (np.arange(32, dtype=np.uint64) * np.uint64(2))[None, :]) & np.uint64(3)).astype(np.uint8).reshape(-1)[: n.value]
+        return np.frombuffer(b"ACGT", dtype=np.uint8)[codes].tobytes().decode()
+
+    def replicate(self, devices):
+        """mazu_b200_index_replicate: device-to-device copies of every table onto each device of `devices`."""
+        dv = np.ascontiguousarray(devices, dtype=np.int32)
+        out = (C.c_void_p * len(dv))()
+        _check(lib().mazu_b200_index_replicate(self._h, _np_ptr(dv), len(dv), out))
+        return [ModIndex(h) for h in out]
+
     def as_streaming(self):
         return StreamingIndex(self)
+
+
+def _handle_array(indexes):
+    arr = (C.c_void_p * len(indexes))()
+    for i, ix in enumerate(indexes):
+        arr[i] = ix._h.value
+    return arr
+
+
+def query_reads_sharded(indexes, bases, read_offsets=None, uniform_read_len=0, mode=MODE_RANDOM, out_hits=None):
+    """mazu_b200_query_reads_sharded over replicas (host buffers): returns (hits, counts, kmer_offsets)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    if uniform_read_len:
+        n_reads, ro = len(bases) // uniform_read_len, None
+    else:
+        ro = np.ascontiguousarray(read_offsets, dtype=np.uint64)
+        n_reads = len(ro) - 1
+    koffs = np.zeros(n_reads + 1, dtype=np.uint64)
+    if out_hits is None:
+        out_hits = np.empty(indexes[0].count_kmer_slots(ro, n_reads, uniform_read_len), dtype=HIT_DTYPE)
+    cnt = np.zeros(3, dtype=np.uint64)
+    _check(lib().mazu_b200_query_reads_sharded(_handle_array(indexes), len(indexes), _np_ptr(bases), _np_ptr(ro), n_reads, uniform_read_len, mode,
+                                               _np_ptr(koffs), _any_ptr(out_hits), _np_ptr(cnt)))
+    return out_hits, cnt, koffs
+
+
+def query_reads_runs_sharded(indexes, bases, read_offsets=None, uniform_read_len=0, mode=MODE_RANDOM, codes=None, runs=None, read_run_offsets=None):
+    """mazu_b200_query_reads_runs_sharded: returns (codes, runs (whole array), read_run_offsets, counts, kmer_offsets, n_runs)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    if uniform_read_len:
+        n_reads, ro = len(bases) // uniform_read_len, None
+    else:
+        ro = np.ascontiguousarray(read_offsets, dtype=np.uint64)
+        n_reads = len(ro) - 1
+    koffs = np.zeros(n_reads + 1, dtype=np.uint64)
+    n_slots = indexes[0].count_kmer_slots(ro, n_reads, uniform_read_len)
+    codes = np.empty(n_slots, dtype=np.uint8) if codes is None else codes
+    rro = np.zeros(n_reads + 1, dtype=np.uint64) if read_run_offsets is None else read_run_offsets
+    if runs is None:
+        runs = np.empty(max(1024 * len(indexes), n_slots // 8), dtype=HIT_DTYPE)
+    cnt = np.zeros(3, dtype=np.uint64)
+    n_runs = C.c_uint64(0)
+    while True:
+        rc = lib().mazu_b200_query_reads_runs_sharded(_handle_array(indexes), len(indexes), _np_ptr(bases), _np_ptr(ro), n_reads, uniform_read_len, mode,
+                                                      _np_ptr(koffs), _any_ptr(codes), _any_ptr(runs), len(runs), _any_ptr(rro), C.byref(n_runs), _np_ptr(cnt))
+        if rc != 0 and n_runs.value > len(runs):
+            runs = np.empty(n_runs.value, dtype=HIT_DTYPE)
+            continue
+        _check(rc)
+        break
+    return codes, runs, rro, cnt, koffs, n_runs.value
+
+
+class Fasta:
+    """FastaReader (src/util.rs:93-149) through the library: records of a FASTA / FASTQ file as (bases, offsets, names)."""
+
+    def __init__(self, path):
+        h = C.c_void_p(0)
+        _check(lib().mazu_b200_fasta_open(os.fspath(path).encode(), C.byref(h)))
+        try:
+            n = int(lib().mazu_b200_fasta_n_records(h))
+            self.offsets = np.ctypeslib.as_array(C.cast(lib().mazu_b200_fasta_offsets(h), C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
+            total = int(self.offsets[-1])
+            self.bases = (np.ctypeslib.as_array(C.cast(lib().mazu_b200_fasta_bases(h), C.POINTER(C.c_uint8)), shape=(total,)).copy()
+                          if total else np.zeros(0, dtype=np.uint8))
+            self.names = [lib().mazu_b200_fasta_name(h, i).decode() for i in range(n)]
+        finally:
+            lib().mazu_b200_fasta_close(h)
+
+    def seqs(self):
+        return [self.bases[int(self.offsets[i]):int(self.offsets[i + 1])].tobytes().decode() for i in range(len(self.names))]
 
 
 class StreamingIndex:
@@ -527,6 +639,9 @@ class StreamingIndex:
     def query_reads(self, bases, read_offsets=None, **kw):
         kw["mode"] = MODE_STREAMING
         return self.index.query_reads(bases, read_offsets, **kw)
+
+    def validate_fasta(self, path):
+        return self.index.validate_fasta(path, MODE_STREAMING)
 
 
 class DenseIndex(ModIndex):

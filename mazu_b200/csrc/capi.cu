@@ -1,6 +1,8 @@
 // extern "C" surface of libmazu_b200.so (include/mazu_b200.h): index upload, kernel launches, and the
 // chunked host<->device pipelines behind MAZU_MEM_HOST calls.  There is no CPU fallback: every query
 // entry point launches the CUDA kernels of kernels.cuh or fails with MAZU_ERR_CUDA.
+#include <array>
+
 #include "device_index.cuh"
 #include "gpu_build_driver.cuh"
 #include "../../include/mazu_b200_debug.h"
@@ -26,7 +28,10 @@ mazu_index* finalize_index(std::unique_ptr<mazu_index> ix) {
     MZ_CUDA(cudaMemPoolSetAttribute(ix->pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
   if (!ix->d_unitigs) ix->d_unitigs = upload_unitigs(*ix->unitigs, ix->device);
+  for (size_t i = 0; i + 1 < ix->unitigs->accum.size(); ++i)
+    if (ix->unitigs->accum[i + 1] - ix->unitigs->accum[i] >= (1ULL << 30)) ix->compact_ok = false;
   ix->view.unitigs = ix->d_unitigs->view;
+  ix->tables[7] = {ix->view.unitigs.lines, ((ix->unitigs->total_len() >> ULINE_SHIFT) + 2) * sizeof(UnitigLine)};
   if (ix->gpu_builder) ix->gpu_builder(*ix);  // tables are produced in HBM (gpu_build.cuh)
   else upload_k2u(*ix);
   upload_u2pos(*ix);
@@ -68,6 +73,19 @@ void launch_k2u_batch(const mazu_index* ix, const u64* d_words, u64 n, Hit* d_ou
 
 void device_exclusive_scan(const u64* d_in, u64* d_out, u64 n, cudaMemPool_t pool, cudaStream_t s);
 
+// one stream-ordered allocation from the handle's pool, given back on the same stream when the scope ends (also when it
+// ends by an exception: the pool's release threshold is "keep everything", so a leak would never be returned)
+struct PoolBuf {
+  void* p = nullptr;
+  cudaStream_t s;
+  PoolBuf(cudaMemPool_t pool, size_t bytes, cudaStream_t st) : s(st) { MZ_CUDA(cudaMallocFromPoolAsync(&p, bytes ? bytes : 1, pool, st)); }
+  ~PoolBuf() {
+    if (p) cudaFreeAsync(p, s);
+  }
+  PoolBuf(const PoolBuf&) = delete;
+  PoolBuf& operator=(const PoolBuf&) = delete;
+};
+
 // resident CTAs per SM the random-access read kernel is compiled for (4 -> <= 64 registers; 3 -> <= 80); A/B knob
 #ifndef MAZU_QR_RANDOM_OCC
 #define MAZU_QR_RANDOM_OCC 4
@@ -93,18 +111,17 @@ void launch_qr(const mazu_index* ix, const u8* d_bases, const u64* d_read_offset
       launch_qr_occ<MODE, KIND, FAMILY, 4>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, nullptr, s);
   } else {
     // ragged batches: per-read work-item counts -> scan; the kernel cuts long reads into segments (kernels.cuh, QR_SEGMENT)
-    void *cnt = nullptr, *seg = nullptr;
+    std::unique_ptr<PoolBuf> cnt, seg;
     if (!uniform_len) {
-      MZ_CUDA(cudaMallocFromPoolAsync(&cnt, (n_reads + 1) * 8, ix->pool, s));
-      MZ_CUDA(cudaMallocFromPoolAsync(&seg, (n_reads + 1) * 8, ix->pool, s));
-      MZ_CUDA(cudaMemsetAsync(cnt, 0, (n_reads + 1) * 8, s));
-      segment_counts_kernel<<<(int)std::min<u64>((n_reads + 255) / 256, 4096), 256, 0, s>>>(d_read_offsets, n_reads, ix->unitigs->k, (u64*)cnt);
+      cnt = std::make_unique<PoolBuf>(ix->pool, (n_reads + 1) * 8, s);
+      seg = std::make_unique<PoolBuf>(ix->pool, (n_reads + 1) * 8, s);
+      MZ_CUDA(cudaMemsetAsync(cnt->p, 0, (n_reads + 1) * 8, s));
+      segment_counts_kernel<<<(int)std::min<u64>((n_reads + 255) / 256, 4096), 256, 0, s>>>(d_read_offsets, n_reads, ix->unitigs->k, (u64*)cnt->p);
       MZ_CUDA(cudaGetLastError());
-      device_exclusive_scan((const u64*)cnt, (u64*)seg, n_reads, ix->pool, s);
+      device_exclusive_scan((const u64*)cnt->p, (u64*)seg->p, n_reads, ix->pool, s);
     }
-    launch_qr_occ<MODE, KIND, FAMILY, MAZU_QR_RANDOM_OCC>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, (const u64*)seg, s);
-    if (cnt) MZ_CUDA(cudaFreeAsync(cnt, s));
-    if (seg) MZ_CUDA(cudaFreeAsync(seg, s));
+    launch_qr_occ<MODE, KIND, FAMILY, MAZU_QR_RANDOM_OCC>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts,
+                                                          seg ? (const u64*)seg->p : nullptr, s);
   }
 }
 
@@ -135,10 +152,8 @@ void device_exclusive_scan(const u64* d_in, u64* d_out, u64 n, cudaMemPool_t poo
   // run ExclusiveSum over n+1 elements with in[n] readable (callers allocate n+1).
   size_t tmp_bytes = 0;
   MZ_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_in, d_out, (size_t)(n + 1), s));
-  void* tmp = nullptr;
-  MZ_CUDA(cudaMallocFromPoolAsync(&tmp, tmp_bytes ? tmp_bytes : 1, pool, s));
-  MZ_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_in, d_out, (size_t)(n + 1), s));
-  MZ_CUDA(cudaFreeAsync(tmp, s));
+  PoolBuf tmp(pool, tmp_bytes, s);
+  MZ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, d_in, d_out, (size_t)(n + 1), s));
 }
 
 struct StreamPair {
@@ -159,6 +174,7 @@ struct PoolScratch {
   cudaMemPool_t pool;
   cudaStream_t s;
   std::vector<void*> ptrs;
+  std::vector<cudaStream_t> users;  // other streams the buffers were published to
   PoolScratch(cudaMemPool_t p, cudaStream_t st) : pool(p), s(st) {}
   void* get(size_t n) {
     void* p = nullptr;
@@ -173,8 +189,12 @@ struct PoolScratch {
     MZ_CUDA(cudaEventRecord(e, s));
     MZ_CUDA(cudaStreamWaitEvent(other, e, 0));
     cudaEventDestroy(e);
+    users.push_back(other);
   }
   ~PoolScratch() {
+    // the frees are ordered on `s` only: when the scope ends early (an exception in a multi-stream pipeline) work on the
+    // other streams may still be using the buffers, so wait for them first (a no-op on the normal path, which has synchronised)
+    for (cudaStream_t u : users) cudaStreamSynchronize(u);
     for (void* p : ptrs) cudaFreeAsync(p, s);
   }
   PoolScratch(const PoolScratch&) = delete;
@@ -477,10 +497,12 @@ uint64_t mazu_b200_count_kmer_slots(const mazu_index_t* idx, const uint64_t* rea
 // hit-run output of mazu_b200_query_reads_runs (host buffers)
 struct RunsOut {
   uint8_t* codes;
-  mazu_hit_t* runs;
-  uint64_t cap_runs;
-  uint64_t* read_run_offsets;  // n_reads + 1
-  uint64_t n_runs = 0;
+  mazu_hit_t* runs;            // the caller's whole run array
+  uint64_t cap_runs;           // end (exclusive) of the part of `runs` this call may fill
+  uint64_t* read_run_offsets;  // n_reads + 1 (the last entry only if write_end)
+  uint64_t n_runs = 0;         // runs this call produced (it keeps counting past the capacity)
+  uint64_t base = 0;           // index in `runs` of this call's first run (sharded calls: the shard's region)
+  bool write_end = true;       // write read_run_offsets[n_reads] (sharded calls: that entry belongs to the next shard)
 };
 
 static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
@@ -499,22 +521,19 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
     if (mem == MAZU_MEM_DEVICE) {
       cudaStream_t s = (cudaStream_t)stream;
       u64* d_koffs = kmer_offsets;
-      void* tmp_koffs = nullptr;
+      std::unique_ptr<PoolBuf> tmp_koffs;
       if (!uniform_read_len && n_reads) {
         if (!d_koffs) {
-          MZ_CUDA(cudaMallocFromPoolAsync(&tmp_koffs, (n_reads + 1) * 8, idx->pool, s));
-          d_koffs = (u64*)tmp_koffs;
+          tmp_koffs = std::make_unique<PoolBuf>(idx->pool, (n_reads + 1) * 8, s);
+          d_koffs = (u64*)tmp_koffs->p;
         }
-        void* lens = nullptr;
-        MZ_CUDA(cudaMallocFromPoolAsync(&lens, (n_reads + 1) * 8, idx->pool, s));
-        MZ_CUDA(cudaMemsetAsync(lens, 0, (n_reads + 1) * 8, s));
-        kmer_counts_kernel<<<(int)std::min<u64>((n_reads + 255) / 256, 4096), 256, 0, s>>>(read_offsets, n_reads, k, (u64*)lens);
+        PoolBuf lens(idx->pool, (n_reads + 1) * 8, s);
+        MZ_CUDA(cudaMemsetAsync(lens.p, 0, (n_reads + 1) * 8, s));
+        kmer_counts_kernel<<<(int)std::min<u64>((n_reads + 255) / 256, 4096), 256, 0, s>>>(read_offsets, n_reads, k, (u64*)lens.p);
         MZ_CUDA(cudaGetLastError());
-        device_exclusive_scan((const u64*)lens, d_koffs, n_reads, idx->pool, s);
-        MZ_CUDA(cudaFreeAsync(lens, s));
+        device_exclusive_scan((const u64*)lens.p, d_koffs, n_reads, idx->pool, s);
       }
       launch_query_reads(idx, bases, read_offsets, n_reads, uniform_read_len, mode, d_koffs, out_hits, compact, counts, s);
-      if (tmp_koffs) MZ_CUDA(cudaFreeAsync(tmp_koffs, s));
       return;
     }
     if (mem != MAZU_MEM_HOST && mem != MAZU_MEM_HOST_IN_DEVICE_OUT) throw Error(MAZU_ERR_INVALID_ARG, "unknown mem mode");
@@ -573,7 +592,7 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
     // sync-free path: run records are published into them at a device-side running base; otherwise the host waits for each
     // chunk's total to place its runs (below)
     Hit* runs_dev = nullptr;
-    if (ro && ro->cap_runs) {
+    if (ro && ro->cap_runs > ro->base) {
       cudaPointerAttributes at{};
       if (cudaPointerGetAttributes(&at, ro->runs) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) runs_dev = (Hit*)at.devicePointer;
       else cudaGetLastError();
@@ -614,7 +633,7 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
     } ev_guard{&base_ev};
     if (runs_dev) {
       d_base = (u64*)scratch.get(8);
-      MZ_CUDA(cudaMemsetAsync(d_base, 0, 8, sp.s[0]));
+      MZ_CUDA(cudaMemcpyAsync(d_base, &ro->base, 8, cudaMemcpyHostToDevice, sp.s[0]));  // the running index starts at this call's first run
       for (int b = 0; b < NB; ++b) d_total_copy[b] = (u64*)scratch.get(8);
       MZ_CUDA(cudaEventCreateWithFlags(&base_ev, cudaEventDisableTiming));
       MZ_CUDA(cudaEventRecord(base_ev, sp.s[0]));
@@ -640,7 +659,7 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
         if (!runs_dev) MZ_CUDA(cudaHostAlloc((void**)&h_rro[b], (max_reads + 1) * 8, cudaHostAllocDefault));
       }
       ro->n_runs = 0;
-      if (n_reads == 0) ro->read_run_offsets[0] = 0;
+      if (n_reads == 0 && ro->read_run_offsets && ro->write_end) ro->read_run_offsets[0] = ro->base;
     }
     const u64 uniform_slots = uniform_read_len >= k ? uniform_read_len - k + 1 : 0;
     // second half of a chunk in hit-run mode: wait for its offsets, place its runs, publish its offsets
@@ -648,13 +667,14 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       const u64 r0 = cuts[c], nr = cuts[c + 1] - cuts[c];
       MZ_CUDA(cudaStreamSynchronize(sp.s[bb]));
       const u64 total = h_rro[bb][nr];
-      if (ro->n_runs + total > ro->cap_runs) {
+      if (ro->base + ro->n_runs + total > ro->cap_runs) {
         ro->n_runs += total;  // keep counting so the caller learns the capacity it needs
       } else {
-        if (total) MZ_CUDA(cudaMemcpyAsync(ro->runs + ro->n_runs, d_runs[bb], total * 16, cudaMemcpyDeviceToHost, sp.s[bb]));
-        for (u64 i = 0; i < nr; ++i) ro->read_run_offsets[r0 + i] = ro->n_runs + h_rro[bb][i];
+        const u64 at = ro->base + ro->n_runs;
+        if (total) MZ_CUDA(cudaMemcpyAsync(ro->runs + at, d_runs[bb], total * 16, cudaMemcpyDeviceToHost, sp.s[bb]));
+        for (u64 i = 0; i < nr; ++i) ro->read_run_offsets[r0 + i] = at + h_rro[bb][i];
         ro->n_runs += total;
-        ro->read_run_offsets[r0 + nr] = ro->n_runs;
+        if (ro->write_end || r0 + nr < n_reads) ro->read_run_offsets[r0 + nr] = at + total;
       }
     };
     scratch.publish(sp.s[1]);
@@ -716,8 +736,10 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       MZ_CUDA(cudaStreamSynchronize(sp.s[0]));
       MZ_CUDA(cudaStreamSynchronize(sp.s[1]));
       if (extra.s) MZ_CUDA(cudaStreamSynchronize(extra.s));
-      MZ_CUDA(cudaMemcpy(&ro->n_runs, d_base, 8, cudaMemcpyDeviceToHost));
-      ro->read_run_offsets[n_reads] = ro->n_runs;
+      u64 end = 0;
+      MZ_CUDA(cudaMemcpy(&end, d_base, 8, cudaMemcpyDeviceToHost));
+      ro->n_runs = end - ro->base;
+      if (ro->write_end) ro->read_run_offsets[n_reads] = end;
     }
     MZ_CUDA(cudaStreamSynchronize(sp.s[1]));
     if (counts) MZ_CUDA(cudaMemcpyAsync(counts, d_counts, 24, cudaMemcpyDeviceToHost, sp.s[0]));
@@ -784,20 +806,268 @@ mazu_status_t mazu_b200_expand_hit_runs(const uint8_t* codes, const mazu_hit_t* 
 mazu_status_t mazu_b200_query_reads_compact(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
                                             uint64_t uniform_read_len, int32_t mode, uint64_t* kmer_offsets, mazu_hit8_t* out_hits,
                                             uint64_t* counts, int32_t mem, void* stream) {
-  if (idx) {
-    // pos shares a word with the match type: every unitig must be shorter than 2^30 bases
-    const auto& acc = idx->unitigs->accum;
-    static thread_local const mazu_index* checked = nullptr;
-    if (checked != idx) {
-      for (size_t i = 0; i + 1 < acc.size(); ++i)
-        if (acc[i + 1] - acc[i] >= (1ULL << 30)) {
-          g_err = "compact hit records need every unitig shorter than 2^30 bases";
-          return MAZU_ERR_INVALID_ARG;
-        }
-      checked = idx;
-    }
+  if (idx && !idx->compact_ok) {  // pos shares a word with the match type
+    g_err = "compact hit records need every unitig shorter than 2^30 bases";
+    return MAZU_ERR_INVALID_ARG;
   }
   return query_reads_impl(idx, bases, read_offsets, n_reads, uniform_read_len, mode, kmer_offsets, out_hits, 1, counts, mem, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU: replicate the device tables, shard the reads
+// ---------------------------------------------------------------------------------------------
+mazu_status_t mazu_b200_index_replicate(const mazu_index_t* src, const int32_t* devices, int32_t n_devices, mazu_index_t** out) {
+  return guarded([&] {
+    if (!src || !devices || !out || n_devices <= 0) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    int n_dev = 0;
+    MZ_CUDA(cudaGetDeviceCount(&n_dev));
+    for (int i = 0; i < n_devices; ++i) {
+      out[i] = nullptr;
+      if (devices[i] < 0 || devices[i] >= n_dev) throw Error(MAZU_ERR_INVALID_ARG, "device ordinal out of range");
+    }
+    {
+      DeviceGuard gs(src->device);
+      MZ_CUDA(cudaDeviceSynchronize());  // everything that built `src` has finished
+    }
+    std::vector<std::unique_ptr<mazu_index>> made;
+    for (int i = 0; i < n_devices; ++i) {
+      const int dev = devices[i];
+      DeviceGuard g(dev);
+      if (dev != src->device) {  // direct peer copies (NVLink) when the two devices can reach each other; staged by the driver otherwise
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, dev, src->device) == cudaSuccess && can) {
+          cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) MZ_CUDA(e);
+          cudaGetLastError();
+        }
+      }
+      auto ix = std::make_unique<mazu_index>();
+      ix->device = dev;
+      ix->unitigs = src->unitigs;
+      ix->k2u = src->k2u;
+      ix->u2pos = src->u2pos;
+      ix->refs = src->refs;
+      ix->compact_ok = src->compact_ok;
+      ix->view = src->view;
+      ix->tables = src->tables;
+      cudaDeviceProp prop;
+      MZ_CUDA(cudaGetDeviceProperties(&prop, dev));
+      ix->sm_count = prop.multiProcessorCount;
+      {
+        cudaMemPoolProps pp{};
+        pp.allocType = cudaMemAllocationTypePinned;
+        pp.handleTypes = cudaMemHandleTypeNone;
+        pp.location.type = cudaMemLocationTypeDevice;
+        pp.location.id = dev;
+        MZ_CUDA(cudaMemPoolCreate(&ix->pool, &pp));
+        unsigned long long keep = ~0ULL;
+        MZ_CUDA(cudaMemPoolSetAttribute(ix->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      }
+      // copy every buffer of every group, remember where it went
+      struct Span {
+        const char* lo;
+        const char* hi;
+        char* to;
+      };
+      std::vector<Span> spans;
+      auto copy_bufs = [&](const std::vector<DevBufP>& from, std::vector<DevBufP>& to, size_t& bytes) {
+        for (const DevBufP& b : from) {
+          auto nb = std::make_shared<DevBuf>(b->bytes, dev);
+          if (b->bytes) MZ_CUDA(cudaMemcpyPeerAsync(nb->p, dev, b->p, src->device, b->bytes, 0));
+          spans.push_back(Span{(const char*)b->p, (const char*)b->p + std::max<size_t>(b->bytes, 1), (char*)nb->p});
+          to.push_back(nb);
+          bytes += nb->bytes;
+        }
+      };
+      if (src->d_unitigs) {
+        ix->d_unitigs = std::make_shared<UnitigsDev>();
+        copy_bufs(src->d_unitigs->bufs, ix->d_unitigs->bufs, ix->d_unitigs->bytes);
+      }
+      if (src->d_k2u) {
+        ix->d_k2u = std::make_shared<K2UDev>();
+        copy_bufs(src->d_k2u->bufs, ix->d_k2u->bufs, ix->d_k2u->bytes);
+      }
+      if (src->d_u2pos) {
+        ix->d_u2pos = std::make_shared<U2PosDev>();
+        copy_bufs(src->d_u2pos->bufs, ix->d_u2pos->bufs, ix->d_u2pos->bytes);
+      }
+      if (src->d_refs) {
+        ix->d_refs = std::make_shared<RefsDev>();
+        copy_bufs(src->d_refs->bufs, ix->d_refs->bufs, ix->d_refs->bytes);
+      }
+      auto remap = [&](auto& ptr) {
+        using P = std::remove_reference_t<decltype(ptr)>;
+        const char* p = (const char*)ptr;
+        if (!p) return;
+        for (const Span& sp : spans)
+          if (p >= sp.lo && p < sp.hi) {
+            ptr = (P)(sp.to + (p - sp.lo));
+            return;
+          }
+        throw Error(MAZU_ERR_OTHER, "internal: an index pointer lies outside every device buffer of its handle");
+      };
+      IndexView& v = ix->view;
+      auto remap_mphf = [&](RankedLevels& m) {
+        remap(m.blocks);
+        remap(m.fb_keys);
+        remap(m.fb_vals);
+      };
+      remap(v.unitigs.useq);
+      remap(v.unitigs.dir);
+      remap(v.unitigs.starts);
+      remap(v.unitigs.lines);
+      remap_mphf(v.mphf);
+      remap(v.pos.words);
+      remap(v.sizes.blocks);
+      remap(v.sizes.exceptions);
+      remap_mphf(v.skew_mphf);
+      remap(v.skew_pos.words);
+      remap_mphf(v.sampled);
+      remap(v.canonical_bits);
+      remap(v.direction_bits);
+      remap(v.ext_sizes.words);
+      remap(v.ext_bases.words);
+      remap(v.ctable_words);
+      remap(v.contig_offsets.words);
+      remap(v.refseq);
+      remap(v.ref_prefix);
+      for (auto& t : ix->tables) remap(t.first);
+      if (ix->d_unitigs) ix->d_unitigs->view = v.unitigs;
+      MZ_CUDA(cudaDeviceSynchronize());
+      made.push_back(std::move(ix));
+    }
+    for (int i = 0; i < n_devices; ++i) out[i] = made[i].release();
+  });
+}
+
+namespace {
+struct ShardPlan {
+  std::vector<u64> cut;   // n + 1 read boundaries
+  std::vector<u64> slot;  // first k-mer slot of every shard (+ total)
+};
+// contiguous blocks of about equal size in bases
+ShardPlan plan_shards(int n, const uint64_t* read_offsets, uint64_t n_reads, uint64_t uniform_read_len, u32 k, uint64_t* kmer_offsets) {
+  ShardPlan p;
+  p.cut.assign(n + 1, n_reads);
+  p.cut[0] = 0;
+  for (int i = 1; i < n; ++i) {
+    if (uniform_read_len) p.cut[i] = n_reads * (u64)i / n;
+    else {
+      const u64 target = read_offsets[0] + (read_offsets[n_reads] - read_offsets[0]) * (u64)i / n;
+      p.cut[i] = std::max<u64>(p.cut[i - 1], (u64)(std::lower_bound(read_offsets, read_offsets + n_reads + 1, target) - read_offsets));
+      p.cut[i] = std::min<u64>(p.cut[i], n_reads);
+    }
+  }
+  p.slot.assign(n + 1, 0);
+  if (uniform_read_len) {
+    const u64 per = uniform_read_len >= k ? uniform_read_len - k + 1 : 0;
+    for (int i = 0; i <= n; ++i) p.slot[i] = p.cut[i] * per;
+    if (kmer_offsets)
+      for (u64 r = 0; r <= n_reads; ++r) kmer_offsets[r] = r * per;
+  } else {
+    u64 acc = 0;
+    int sh = 0;
+    for (u64 r = 0; r <= n_reads; ++r) {
+      while (sh <= n && p.cut[sh] == r) p.slot[sh++] = acc;
+      if (kmer_offsets) kmer_offsets[r] = acc;
+      if (r < n_reads) {
+        const u64 len = read_offsets[r + 1] - read_offsets[r];
+        if (len >= k) acc += len - k + 1;
+      }
+    }
+  }
+  return p;
+}
+void check_replicas(const mazu_index_t* const* handles, int32_t n) {
+  if (!handles || n <= 0) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+  for (int i = 0; i < n; ++i) {
+    if (!handles[i]) throw Error(MAZU_ERR_INVALID_ARG, "null handle");
+    if (handles[i]->unitigs->k != handles[0]->unitigs->k || handles[i]->unitigs->total_len() != handles[0]->unitigs->total_len() ||
+        handles[i]->view.k2u_kind != handles[0]->view.k2u_kind)
+      throw Error(MAZU_ERR_INVALID_ARG, "the handles of a sharded call must hold the same index");
+  }
+}
+}  // namespace
+
+mazu_status_t mazu_b200_query_reads_sharded(const mazu_index_t* const* handles, int32_t n_handles, const uint8_t* bases,
+                                            const uint64_t* read_offsets, uint64_t n_reads, uint64_t uniform_read_len, int32_t mode,
+                                            uint64_t* kmer_offsets, mazu_hit_t* out_hits, uint64_t* counts) {
+  return guarded([&] {
+    check_replicas(handles, n_handles);
+    if (n_reads && !uniform_read_len && !read_offsets) throw Error(MAZU_ERR_INVALID_ARG, "read_offsets is required for ragged reads");
+    const ShardPlan p = plan_shards(n_handles, read_offsets, n_reads, uniform_read_len, handles[0]->unitigs->k, kmer_offsets);
+    std::vector<mazu_status_t> rc(n_handles, MAZU_OK);
+    std::vector<std::string> err(n_handles);
+    std::vector<std::array<u64, 3>> cnt(n_handles, std::array<u64, 3>{0, 0, 0});
+    std::vector<std::thread> ts;
+    for (int i = 0; i < n_handles; ++i)
+      ts.emplace_back([&, i] {  // one host thread + its own streams per device
+        const u64 r0 = p.cut[i], nr = p.cut[i + 1] - r0;
+        if (!nr) return;
+        const uint8_t* b = uniform_read_len ? bases + r0 * uniform_read_len : bases;
+        rc[i] = query_reads_impl(handles[i], b, uniform_read_len ? nullptr : read_offsets + r0, nr, uniform_read_len, mode, nullptr,
+                                 out_hits ? out_hits + p.slot[i] : nullptr, 0, cnt[i].data(), MAZU_MEM_HOST, nullptr, nullptr);
+        if (rc[i] != MAZU_OK) err[i] = g_err;
+      });
+    for (auto& t : ts) t.join();
+    for (int i = 0; i < n_handles; ++i)
+      if (rc[i] != MAZU_OK) throw Error(rc[i], "shard " + std::to_string(i) + ": " + err[i]);
+    if (counts)
+      for (int j = 0; j < 3; ++j) {
+        counts[j] = 0;
+        for (int i = 0; i < n_handles; ++i) counts[j] += cnt[i][j];
+      }
+  });
+}
+
+mazu_status_t mazu_b200_query_reads_runs_sharded(const mazu_index_t* const* handles, int32_t n_handles, const uint8_t* bases,
+                                                 const uint64_t* read_offsets, uint64_t n_reads, uint64_t uniform_read_len, int32_t mode,
+                                                 uint64_t* kmer_offsets, uint8_t* out_codes, mazu_hit_t* out_runs, uint64_t cap_runs,
+                                                 uint64_t* out_read_run_offsets, uint64_t* out_n_runs, uint64_t* counts) {
+  return guarded([&] {
+    check_replicas(handles, n_handles);
+    if (n_reads && !uniform_read_len && !read_offsets) throw Error(MAZU_ERR_INVALID_ARG, "read_offsets is required for ragged reads");
+    if (n_reads && (!out_codes || !out_read_run_offsets || (cap_runs && !out_runs))) throw Error(MAZU_ERR_INVALID_ARG, "null run buffers");
+    const ShardPlan p = plan_shards(n_handles, read_offsets, n_reads, uniform_read_len, handles[0]->unitigs->k, kmer_offsets);
+    const u64 region = cap_runs / (u64)n_handles;
+    std::vector<mazu_status_t> rc(n_handles, MAZU_OK);
+    std::vector<std::string> err(n_handles);
+    std::vector<std::array<u64, 3>> cnt(n_handles, std::array<u64, 3>{0, 0, 0});
+    std::vector<u64> n_runs(n_handles, 0);
+    std::vector<std::thread> ts;
+    for (int i = 0; i < n_handles; ++i)
+      ts.emplace_back([&, i] {
+        const u64 r0 = p.cut[i], nr = p.cut[i + 1] - r0;
+        if (!nr) return;
+        const uint8_t* b = uniform_read_len ? bases + r0 * uniform_read_len : bases;
+        // shard i fills out_runs[i * region, (i + 1) * region); its offsets are global indexes; entry r0 + nr belongs to the next shard
+        RunsOut ro{out_codes + p.slot[i], out_runs, (u64)(i + 1) * region, out_read_run_offsets + r0};
+        ro.base = (u64)i * region;
+        ro.write_end = false;
+        rc[i] = query_reads_impl(handles[i], b, uniform_read_len ? nullptr : read_offsets + r0, nr, uniform_read_len, mode, nullptr, nullptr, 0,
+                                 cnt[i].data(), MAZU_MEM_HOST, nullptr, &ro);
+        n_runs[i] = ro.n_runs;
+        if (rc[i] != MAZU_OK) err[i] = g_err;
+      });
+    for (auto& t : ts) t.join();
+    for (int i = 0; i < n_handles; ++i)
+      if (rc[i] != MAZU_OK) throw Error(rc[i], "shard " + std::to_string(i) + ": " + err[i]);
+    u64 total = 0, worst = 0;
+    for (int i = 0; i < n_handles; ++i) {
+      total += n_runs[i];
+      worst = std::max(worst, n_runs[i]);
+    }
+    if (out_n_runs) *out_n_runs = total;
+    if (worst > region) {
+      if (out_n_runs) *out_n_runs = worst * (u64)n_handles;
+      throw Error(MAZU_ERR_INVALID_ARG, "run capacity too small: need " + std::to_string(worst * (u64)n_handles) + " records");
+    }
+    if (counts)
+      for (int j = 0; j < 3; ++j) {
+        counts[j] = 0;
+        for (int i = 0; i < n_handles; ++i) counts[j] += cnt[i][j];
+      }
+  });
 }
 
 mazu_status_t mazu_b200_encode_reads(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
@@ -841,15 +1111,15 @@ static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu
     d_offs = scratch->get((n + 1) * 8);
     d_offsets = (u64*)d_offs;
   }
-  void* lens = nullptr;
-  MZ_CUDA(cudaMallocFromPoolAsync(&lens, (n + 1) * 8, idx->pool, s));
-  MZ_CUDA(cudaMemsetAsync(lens, 0, (n + 1) * 8, s));
-  if (n) {
-    occ_lens_kernel<<<(int)std::min<u64>((n + 255) / 256, (u64)idx->sm_count * 8), 256, 0, s>>>(idx->view, d_uids, d_hits, n, (u64*)lens);
-    MZ_CUDA(cudaGetLastError());
+  {
+    PoolBuf lens(idx->pool, (n + 1) * 8, s);
+    MZ_CUDA(cudaMemsetAsync(lens.p, 0, (n + 1) * 8, s));
+    if (n) {
+      occ_lens_kernel<<<(int)std::min<u64>((n + 255) / 256, (u64)idx->sm_count * 8), 256, 0, s>>>(idx->view, d_uids, d_hits, n, (u64*)lens.p);
+      MZ_CUDA(cudaGetLastError());
+    }
+    device_exclusive_scan((const u64*)lens.p, d_offsets, n, idx->pool, s);
   }
-  device_exclusive_scan((const u64*)lens, d_offsets, n, idx->pool, s);
-  MZ_CUDA(cudaFreeAsync(lens, s));
   u64 total = 0;
   bool need_total = mem == MAZU_MEM_HOST || out_total != nullptr;
   if (need_total) {
@@ -867,9 +1137,13 @@ static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu
     throw Error(MAZU_ERR_INVALID_ARG, "output capacity too small: need " + std::to_string(total) + " records");
   }
   OccRec* d_o = (OccRec*)out;
+  // the fill kernels clip to this many records: with device buffers and no out_total the host never learns the total, so
+  // an undersized `out` is filled up to `cap` and out_offsets[n] tells the caller what the full output needs
+  u64 fill_cap = cap;
   if (mem == MAZU_MEM_HOST) {
     d_out = scratch->get(total * 12 + 16);
     d_o = (OccRec*)d_out;
+    fill_cap = total;
   }
   if (n) {
     // tiles of the OUTPUT are grid-strided; the kernels read the total from out_offsets[n]
@@ -886,12 +1160,12 @@ static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu
         cudaFuncSetAttribute(occ_fill_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OCC_TMA_SMEM);
       });
       int grid = idx->sm_count;
-      if (project) occ_fill_tma_kernel<true><<<grid, OCC_TMA_WARPS * 32, OCC_TMA_SMEM, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o);
-      else occ_fill_tma_kernel<false><<<grid, OCC_TMA_WARPS * 32, OCC_TMA_SMEM, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o);
+      if (project) occ_fill_tma_kernel<true><<<grid, OCC_TMA_WARPS * 32, OCC_TMA_SMEM, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o, fill_cap);
+      else occ_fill_tma_kernel<false><<<grid, OCC_TMA_WARPS * 32, OCC_TMA_SMEM, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o, fill_cap);
     } else {
       int grid = idx->sm_count * 8;
-      if (project) occ_fill_kernel<true><<<grid, 256, 0, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o);
-      else occ_fill_kernel<false><<<grid, 256, 0, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o);
+      if (project) occ_fill_kernel<true><<<grid, 256, 0, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o, fill_cap);
+      else occ_fill_kernel<false><<<grid, 256, 0, s>>>(idx->view, d_uids, d_hits, n, d_offsets, d_o, fill_cap);
     }
     MZ_CUDA(cudaGetLastError());
   }
@@ -965,6 +1239,101 @@ static void run_validate(const mazu_index_t* idx, bool k2u_only, uint64_t counts
   }
   MZ_CUDA(cudaGetLastError());
   MZ_CUDA(cudaMemcpy(counts, d.p, 40, cudaMemcpyDeviceToHost));
+}
+
+// Validate::validate_ckmers for a batch of records: lookups through the read kernels, then the check of the projected
+// positions on the device (validate_reads_kernel).  Records are processed in chunks of ~64 M bases.
+static void validate_reads_impl(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads, int32_t mode,
+                                uint64_t counts[5]) {
+  if (!idx || !counts || (n_reads && (!bases || !read_offsets))) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+  if (mode != MAZU_MODE_RANDOM && mode != MAZU_MODE_STREAMING) throw Error(MAZU_ERR_INVALID_ARG, "unknown query mode");
+  if (idx->view.u2pos_kind == MAZU_U2POS_NONE) throw Error(MAZU_ERR_NO_U2POS, "validate: index has no U2Pos table");
+  const u32 k = idx->unitigs->k;
+  DeviceGuard g(idx->device);
+  StreamPair sp;
+  cudaStream_t s = sp.s[0];
+  PoolBuf d_counts(idx->pool, 40, s);
+  MZ_CUDA(cudaMemsetAsync(d_counts.p, 0, 40, s));
+  const u64 CHUNK = 64ull << 20;
+  std::vector<u64> rel;
+  for (u64 r0 = 0; r0 < n_reads;) {
+    u64 r1 = (u64)(std::upper_bound(read_offsets + r0 + 1, read_offsets + n_reads + 1, read_offsets[r0] + CHUNK) - read_offsets) - 1;
+    r1 = std::max(r1, r0 + 1);
+    const u64 nr = r1 - r0, b0 = read_offsets[r0], nb = read_offsets[r1] - b0;
+    rel.resize(nr + 1);
+    u64 slots = 0;
+    for (u64 i = 0; i <= nr; ++i) {
+      rel[i] = read_offsets[r0 + i] - b0;
+      if (i < nr) {
+        const u64 len = read_offsets[r0 + i + 1] - read_offsets[r0 + i];
+        if (len >= k) slots += len - k + 1;
+      }
+    }
+    PoolBuf d_bases(idx->pool, nb + 16, s), d_ro(idx->pool, (nr + 1) * 8, s), d_ko(idx->pool, (nr + 1) * 8, s), d_hits(idx->pool, slots * 16 + 16, s);
+    MZ_CUDA(cudaMemcpyAsync(d_bases.p, bases + b0, nb, cudaMemcpyHostToDevice, s));
+    MZ_CUDA(cudaMemcpyAsync(d_ro.p, rel.data(), (nr + 1) * 8, cudaMemcpyHostToDevice, s));
+    mazu_status_t rc = mazu_b200_query_reads(idx, (const uint8_t*)d_bases.p, (const uint64_t*)d_ro.p, nr, 0, mode, (uint64_t*)d_ko.p, (mazu_hit_t*)d_hits.p,
+                                             nullptr, MAZU_MEM_DEVICE, s);
+    if (rc != MAZU_OK) throw Error(rc, g_err);
+    if (slots) {
+      const int grid = (int)std::max<u64>(1, std::min<u64>((slots + 255) / 256, (u64)idx->sm_count * 8));
+      validate_reads_kernel<<<grid, 256, 0, s>>>(idx->view, (const Hit*)d_hits.p, (const u64*)d_ko.p, nr, r0, (unsigned long long*)d_counts.p);
+      MZ_CUDA(cudaGetLastError());
+    }
+    MZ_CUDA(cudaStreamSynchronize(s));  // `rel` is reused by the next chunk
+    r0 = r1;
+  }
+  MZ_CUDA(cudaMemcpyAsync(counts, d_counts.p, 40, cudaMemcpyDeviceToHost, s));
+  MZ_CUDA(cudaStreamSynchronize(s));
+}
+
+struct mazu_fasta {
+  FastaHost h;
+};
+
+mazu_status_t mazu_b200_fasta_open(const char* path, mazu_fasta_t** out) {
+  return guarded([&] {
+    if (!path || !out) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    auto f = std::make_unique<mazu_fasta>();
+    f->h = read_fasta_file(path);
+    *out = f.release();
+  });
+}
+void mazu_b200_fasta_close(mazu_fasta_t* f) { delete f; }
+uint64_t mazu_b200_fasta_n_records(const mazu_fasta_t* f) { return f ? f->h.n_records() : 0; }
+const uint8_t* mazu_b200_fasta_bases(const mazu_fasta_t* f) { return f ? f->h.bases.data() : nullptr; }
+const uint64_t* mazu_b200_fasta_offsets(const mazu_fasta_t* f) { return f ? f->h.offsets.data() : nullptr; }
+const char* mazu_b200_fasta_name(const mazu_fasta_t* f, uint64_t record) { return f && record < f->h.names.size() ? f->h.names[record].c_str() : nullptr; }
+
+mazu_status_t mazu_b200_validate_reads(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads, int32_t mode,
+                                       uint64_t counts[5]) {
+  return guarded([&] { validate_reads_impl(idx, bases, read_offsets, n_reads, mode, counts); });
+}
+mazu_status_t mazu_b200_validate_fasta(const mazu_index_t* idx, const char* path, int32_t mode, uint64_t counts[5]) {
+  return guarded([&] {
+    if (!path) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    FastaHost f = read_fasta_file(path);
+    validate_reads_impl(idx, f.bases.data(), f.offsets.data(), f.n_records(), mode, counts);
+  });
+}
+
+mazu_status_t mazu_b200_unitig_seq(const mazu_index_t* idx, uint64_t unitig_id, uint64_t* out_words, uint64_t cap_words, uint64_t* len) {
+  return guarded([&] {
+    if (!idx || !len) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    const UnitigSetHost& us = *idx->unitigs;
+    if (unitig_id >= us.n_unitigs()) throw Error(MAZU_ERR_INVALID_ARG, "unitig id out of range");
+    const u64 s0 = us.accum[unitig_id], n = us.accum[unitig_id + 1] - s0, nw = (n + 31) / 32;
+    *len = n;
+    if (!out_words) return;
+    if (cap_words < nw) throw Error(MAZU_ERR_INVALID_ARG, "output capacity too small: need " + std::to_string(nw) + " words");
+    for (u64 j = 0; j < nw; ++j) {
+      const u64 bit = 2 * (s0 + 32 * j), wi = bit >> 6, sh = bit & 63;
+      u64 x = us.useq[wi] >> sh;
+      if (sh) x |= us.useq[wi + 1] << (64 - sh);
+      const u64 left = n - 32 * j;
+      out_words[j] = left >= 32 ? x : (x & ((1ULL << (2 * left)) - 1ULL));
+    }
+  });
 }
 
 mazu_status_t mazu_b200_validate_self(const mazu_index_t* idx, uint64_t counts[5]) {

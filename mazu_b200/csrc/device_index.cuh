@@ -122,6 +122,7 @@ struct mazu_index {
   cudaMemPool_t pool = nullptr;
   // function attributes are per device: the staged decode kernel's dynamic shared memory limit is raised once per handle
   mutable std::once_flag occ_attr_once;
+  bool compact_ok = true;  // every unitig shorter than 2^30 bases: mazu_hit8_t can hold pos | match << 30
   ~mazu_index() {
     if (pool) cudaMemPoolDestroy(pool);
   }

@@ -4,6 +4,7 @@
 // src/pf1/mod.rs:213-236, src/cuttlefish.rs:11-183, src/spt.rs:67-140, src/spt_compact.rs:221-389).
 #pragma once
 #include <fstream>
+#include <iterator>
 #include <sstream>
 #include <unordered_map>
 
@@ -129,6 +130,62 @@ inline std::string read_text(const std::string& path) {
   std::stringstream ss;
   ss << f.rdbuf();
   return ss.str();
+}
+
+// FastaReader (src/util.rs:93-149) over a whole file: the first line and every later line starting with '>' is a header
+// (name = the line without its first character, verbatim), all other lines are appended to the current record's sequence.
+// A file whose first byte is '@' is read as FASTQ with four lines per record.  Sequences are kept as written (case, N).
+struct FastaHost {
+  std::vector<u8> bases;
+  std::vector<u64> offsets{0};
+  std::vector<std::string> names;
+  u64 n_records() const { return offsets.size() - 1; }
+};
+inline FastaHost read_fasta_file(const std::string& path) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) throw Error(MAZU_ERR_IO, "cannot open " + path);
+  std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  FastaHost out;
+  out.bases.reserve(text.size());
+  const bool fastq = !text.empty() && text[0] == '@';
+  size_t p = 0, line_no = 0;
+  bool first = true;
+  auto next_line = [&](size_t& b, size_t& e) -> bool {  // BufRead::lines: split at '\n', drop one trailing '\r'
+    if (p >= text.size()) return false;
+    size_t nl = text.find('\n', p);
+    b = p;
+    e = nl == std::string::npos ? text.size() : nl;
+    p = nl == std::string::npos ? text.size() : nl + 1;
+    if (e > b && text[e - 1] == '\r') --e;
+    ++line_no;
+    return true;
+  };
+  size_t b, e;
+  if (fastq) {
+    while (next_line(b, e)) {
+      if (e == b) continue;  // blank line between records
+      if (text[b] != '@') throw Error(MAZU_ERR_INVALID_DATA, "FASTQ: record header expected at line " + std::to_string(line_no));
+      out.names.emplace_back(text, b + 1, e - b - 1);
+      size_t sb, se, xb, xe;
+      if (!next_line(sb, se)) throw Error(MAZU_ERR_INVALID_DATA, "FASTQ: truncated record");
+      out.bases.insert(out.bases.end(), text.begin() + sb, text.begin() + se);
+      out.offsets.push_back(out.bases.size());
+      if (!next_line(xb, xe) || xe == xb || text[xb] != '+') throw Error(MAZU_ERR_INVALID_DATA, "FASTQ: '+' line expected at line " + std::to_string(line_no));
+      if (!next_line(xb, xe) || xe - xb != se - sb) throw Error(MAZU_ERR_INVALID_DATA, "FASTQ: quality line does not match the sequence at line " + std::to_string(line_no));
+    }
+    return out;
+  }
+  while (next_line(b, e)) {
+    if (first || (e > b && text[b] == '>')) {  // util.rs:131-133: the first line is a header whatever it starts with
+      if (!first) out.offsets.push_back(out.bases.size());
+      out.names.emplace_back(text, e > b ? b + 1 : b, e > b ? e - b - 1 : 0);
+      first = false;
+    } else {
+      out.bases.insert(out.bases.end(), text.begin() + b, text.begin() + e);
+    }
+  }
+  if (!first) out.offsets.push_back(out.bases.size());
+  return out;
 }
 
 struct LoadedIndex {

@@ -925,7 +925,7 @@ __global__ void occ_lens_kernel(const __grid_constant__ IndexView ix, const u32*
       uid = uids[i];
     }
     u64 len = 0;
-    if (uid != ~0u) {
+    if ((u64)uid < ix.unitigs.n_unitigs) {  // ~0 (a miss) and any other id outside the table: empty list
       u64 s, e;
       occ_range(ix, uid, s, e);
       len = e - s;
@@ -958,6 +958,7 @@ template <bool PROJECT>
 __device__ __forceinline__ void occ_fill_tile(const IndexView& ix, const u32* __restrict__ uids, const Hit* __restrict__ hits,
                                               const u64* __restrict__ out_offsets, OccRec* __restrict__ out, u64 t0, u64 t1, u64 qlo, u64 qhi,
                                               u32 lane, u32 k, bool out_aligned) {
+  // callers clip t1 to the capacity of `out`: records beyond it are never computed
   if (qhi - qlo <= 32) {
     // few, long lists in this tile: walk the overlapping queries (warp-uniform), lanes stride over each
     // segment with plain arithmetic -- no per-record search; 4 independent records in flight per lane
@@ -1047,12 +1048,12 @@ template <bool PROJECT>
 // (40 / 32 registers, spills) measured 5 % / 18 % slower
 __global__ void __launch_bounds__(256, 1) occ_fill_kernel(const __grid_constant__ IndexView ix, const u32* __restrict__ uids,
                                                        const Hit* __restrict__ hits, u64 n, const u64* __restrict__ out_offsets,
-                                                       OccRec* __restrict__ out) {
+                                                       OccRec* __restrict__ out, u64 cap) {
   const u32 lane = threadIdx.x & 31;
   const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u64 n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
   const u32 k = ix.unitigs.k;
-  const u64 total = __ldg(out_offsets + n);
+  const u64 total = min(__ldg(out_offsets + n), cap);  // an undersized buffer is filled up to its capacity, never beyond
   const bool out_aligned = (reinterpret_cast<unsigned long long>(out) & 15ULL) == 0;
   for (u64 t0 = warp * OCC_TILE; t0 < total; t0 += n_warps * OCC_TILE) {
     const u64 t1 = min(t0 + OCC_TILE, total);
@@ -1135,13 +1136,13 @@ __device__ __forceinline__ void occ_plan_tile(const IndexView& ix, const u32* __
 template <bool PROJECT>
 __global__ void __launch_bounds__(OCC_TMA_WARPS * 32, 1) occ_fill_tma_kernel(const __grid_constant__ IndexView ix, const u32* __restrict__ uids,
                                                                               const Hit* __restrict__ hits, u64 n,
-                                                                              const u64* __restrict__ out_offsets, OccRec* __restrict__ out) {
+                                                                              const u64* __restrict__ out_offsets, OccRec* __restrict__ out, u64 cap) {
   extern __shared__ __align__(128) unsigned char occ_smem[];
   namespace ptx = cuda::ptx;
   const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const u64 warp = (u64)blockIdx.x * OCC_TMA_WARPS + wib, n_warps = (u64)gridDim.x * OCC_TMA_WARPS;
   const u32 k = ix.unitigs.k;
-  const u64 total = __ldg(out_offsets + n);
+  const u64 total = min(__ldg(out_offsets + n), cap);  // an undersized buffer is filled up to its capacity, never beyond
   const bool out_aligned = (reinterpret_cast<unsigned long long>(out) & 15ULL) == 0;
   const bool stage_ok = out_aligned && (ix.u2pos_kind == MAZU_U2POS_DENSE || ix.ctable_width <= 48);
   unsigned char* in_buf[2];
@@ -1294,6 +1295,43 @@ __global__ void __launch_bounds__(256) validate_self_kernel(const __grid_constan
     for (u64 j = s; j < e; ++j) {
       OccRec m = project_occ(k, h, occ_decode(ix, j));
       found |= (m.pos == (u32)(p - rs)) && (m.ref_id == (u32)lo);
+    }
+    v[3] += (u32)(e - s);
+    if (!found) ++v[4];
+  }
+  block_accumulate(counts, v);
+}
+// Validate::validate_ckmers over a batch of records (src/index/validate.rs:54-81, src/index/caching.rs:175-201): thread per
+// k-mer slot of the hit records query_reads produced; record r of the batch is reference ref0 + r.  Every yielded k-mer must
+// have a projected position (ref0 + r, position of the slot in its record).
+__global__ void __launch_bounds__(256) validate_reads_kernel(const __grid_constant__ IndexView ix, const Hit* __restrict__ hits,
+                                                             const u64* __restrict__ kmer_offsets, u64 n_reads, u64 ref0,
+                                                             unsigned long long* counts) {
+  const u32 k = ix.unitigs.k;
+  const u64 total = kmer_offsets[n_reads];
+  u32 v[5] = {0, 0, 0, 0, 0};
+  for (u64 slot = (u64)blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += (u64)gridDim.x * blockDim.x) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(hits + slot));
+    const Hit h{q.x, q.y, q.z, q.w};
+    if (h.match == SKIPPED) continue;  // a window the CanonicalKmerIterator does not yield
+    ++v[0];
+    if (h.match == NO_MATCH) {  // "No MRPs found for true +ve kmer"
+      ++v[4];
+      continue;
+    }
+    ++v[h.match == IDENTITY_MATCH ? 1 : 2];
+    u64 lo = 0, hi = n_reads;  // largest r with kmer_offsets[r] <= slot
+    while (hi - lo > 1) {
+      u64 mid = (lo + hi) >> 1;
+      if (kmer_offsets[mid] <= slot) lo = mid; else hi = mid;
+    }
+    const u64 pos = slot - kmer_offsets[lo], ref_id = ref0 + lo;
+    u64 s, e;
+    occ_range(ix, h.unitig_id, s, e);
+    bool found = false;
+    for (u64 j = s; j < e; ++j) {
+      OccRec m = project_occ(k, h, occ_decode(ix, j));
+      found |= ((u64)m.pos == pos) && ((u64)m.ref_id == ref_id);
     }
     v[3] += (u32)(e - s);
     if (!found) ++v[4];

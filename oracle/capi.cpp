@@ -152,6 +152,13 @@ int orc_required_num_bits(u64 longest_ref, u64 num_refs, u32* out3) {
   return guard([&] { required_num_bits(longest_ref, num_refs, out3[0], out3[1], out3[2]); });
 }
 u64 orc_revcomp(u64 w, int k) { return revcomp_word(w, k); }
+u64 orc_revcomp_loop(u64 w, int k) { return revcomp_word_loop(w, k); }
+// threads for the one-time builders (default 1); returns the previous value
+int orc_set_build_threads(int n) {
+  int prev = build_threads();
+  build_threads() = n < 1 ? 1 : n;
+  return prev;
+}
 u64 orc_mm_hash32(u64 x, u64 seed) { return mm_hash32(x, seed); }
 void orc_canonical_minimizer(u64 fw, int k, int w, u64 seed, u64* word, u64* offset) {
   Minimizer m = canonical_minimizer(fw, k, w, seed);

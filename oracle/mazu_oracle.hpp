@@ -1,7 +1,8 @@
 // =====================================================================================
 //  mazu_oracle.hpp  --  TEST INFRASTRUCTURE ONLY.  NOT PART OF THE PRODUCT.
 //
-//  A plain, single-threaded CPU restatement of the batched k-mer query path of
+//  A plain CPU restatement (queries single-threaded per call site, the one-time builder
+//  optionally threaded like the reference's rayon builder) of the batched k-mer query path of
 //  COMBINE-lab/mazu (Rust), used as the bit-exactness checker for the CUDA path and as the
 //  timed "port" CPU baseline in bench.py.  Only tests/, __graft_entry__.smoke() and
 //  bench.py's cpu_baseline / --impl reference legs may load this code.  The product
@@ -34,7 +35,9 @@
 #include <memory>
 #include <sstream>
 #include <stdexcept>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -81,13 +84,69 @@ inline int base_code(u8 c) {
   }
 }
 inline u64 kmer_mask(int k) { return k >= 32 ? ~0ULL : ((1ULL << (2 * k)) - 1); }
+// reverse complement of the low 2k bits: complement (3 - b), reverse the order of the 2-bit bases, shift down.
+// (Same value as the per-base loop `rc |= (3 - b_i) << 2(k-1-i)`; tests/test_oracle_golden.py checks it against that loop.)
 inline u64 revcomp_word(u64 fw, int k) {
+  u64 x = ~fw;
+  x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+  x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+  x = __builtin_bswap64(x);
+  return k >= 32 ? x : (x >> (64 - 2 * k));
+}
+inline u64 revcomp_word_loop(u64 fw, int k) {
   u64 rc = 0;
   for (int i = 0; i < k; ++i) {
     u64 b = (fw >> (2 * i)) & 3;
     rc |= (3 - b) << (2 * (k - 1 - i));
   }
   return rc;
+}
+struct BuildTimer {  // MAZU_ORACLE_TIMING=1: phase times of the one-time builders on stderr
+  bool on = getenv("MAZU_ORACLE_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    auto n = std::chrono::steady_clock::now();
+    if (on) fprintf(stderr, "[oracle build] %-24s %.2f s\n", what, std::chrono::duration<double>(n - t).count());
+    t = n;
+  }
+};
+// threads the one-time builders may use (the reference builds with rayon: par_sort_by_key sshash.rs:150,202,273)
+inline int& build_threads() {
+  static int t = 1;
+  return t;
+}
+template <class F>
+inline void parallel_blocks(u64 n, F&& f) {  // f(block index, begin, end) over `build_threads()` contiguous blocks
+  const int T = (int)std::max<u64>(1, std::min<u64>((u64)build_threads(), n));
+  if (T <= 1) {
+    f(0, (u64)0, n);
+    return;
+  }
+  std::vector<std::thread> ts;
+  for (int t = 0; t < T; ++t) ts.emplace_back([&, t] { f(t, n * t / T, n * (t + 1) / T); });
+  for (auto& th : ts) th.join();
+}
+// stable sort by key with the builder's threads: blocks sorted independently, then merged pairwise (stable)
+template <class T, class Less>
+inline void parallel_stable_sort(std::vector<T>& v, Less less) {
+  const int nb = (int)std::max<u64>(1, std::min<u64>((u64)build_threads(), v.size() / 4096 + 1));
+  if (nb <= 1) {
+    std::stable_sort(v.begin(), v.end(), less);
+    return;
+  }
+  std::vector<u64> cut(nb + 1);
+  for (int b = 0; b <= nb; ++b) cut[b] = v.size() * (u64)b / nb;
+  {
+    std::vector<std::thread> ts;
+    for (int b = 0; b < nb; ++b) ts.emplace_back([&, b] { std::stable_sort(v.begin() + cut[b], v.begin() + cut[b + 1], less); });
+    for (auto& th : ts) th.join();
+  }
+  for (int width = 1; width < nb; width *= 2) {
+    std::vector<std::thread> ts;
+    for (int b = 0; b + width < nb; b += 2 * width)
+      ts.emplace_back([&, b, width] { std::inplace_merge(v.begin() + cut[b], v.begin() + cut[b + width], v.begin() + cut[std::min(nb, b + 2 * width)], less); });
+    for (auto& th : ts) th.join();
+  }
 }
 inline std::string word_to_string(u64 w, int k) {
   std::string s(k, 'A');
@@ -710,23 +769,23 @@ struct SSHash : K2U {
   static void collect_unitig(const UnitigSet& us, u64 ui, int w, u64 seed, std::vector<MinimizerOcc>& out) {
     int k = us.k;
     u64 s = us.unitig_start_pos(ui), e = us.unitig_end_pos(ui);
-    for (int pass = 0; pass < 2; ++pass) {  // pass 0: fw-canonical k-mers, pass 1: rc-canonical k-mers
-      bool have_prev = false;
-      MinimizerOcc prev{0, 0};
-      for (u64 p = s; p + k <= e; ++p) {
-        u64 fw = us.useq.get_kmer_u64(p, k);
-        u64 rc = revcomp_word(fw, k);
-        bool fw_canon = fw <= rc;
-        if (fw_canon != (pass == 0)) continue;
-        Minimizer mm = canonical_minimizer(fw, k, w, seed);
-        // position of the minimizer occurrence on the forward strand (offset is in fw-mer coordinates)
-        u64 mpos = p + mm.offset;
-        MinimizerOcc cur{mm.word, mpos};
-        if (!have_prev || !(cur == prev)) out.push_back(cur);
-        prev = cur;
-        have_prev = true;
-      }
+    // the fw-canonical stream goes straight to `out`, the rc-canonical stream is buffered and appended after it: the same
+    // two run-length-deduped streams, in the same order, as walking the unitig twice
+    std::vector<MinimizerOcc> rc_stream;
+    bool have_prev[2] = {false, false};
+    MinimizerOcc prev[2] = {{0, 0}, {0, 0}};
+    for (u64 p = s; p + k <= e; ++p) {
+      u64 fw = us.useq.get_kmer_u64(p, k);
+      u64 rc = revcomp_word(fw, k);
+      const int pass = fw <= rc ? 0 : 1;
+      Minimizer mm = canonical_minimizer(fw, k, w, seed);
+      // position of the minimizer occurrence on the forward strand (offset is in fw-mer coordinates)
+      MinimizerOcc cur{mm.word, p + mm.offset};
+      if (!have_prev[pass] || !(cur == prev[pass])) (pass == 0 ? out : rc_stream).push_back(cur);
+      prev[pass] = cur;
+      have_prev[pass] = true;
     }
+    out.insert(out.end(), rc_stream.begin(), rc_stream.end());
   }
 
   static std::unique_ptr<SSHash> from_unitig_set(UnitigSet us_in, int w, u64 skew_param, u64 seed) {
@@ -739,12 +798,22 @@ struct SSHash : K2U {
     h.w = w;
     h.seed = seed;
     h.skew_param = skew_param;
+    BuildTimer timer;
     // 1. collect minimizers (sshash.rs:97-143)
     std::vector<MinimizerOcc> minimizers;
-    for (u64 ui = 0; ui < us.n_unitigs(); ++ui) collect_unitig(us, ui, w, seed, minimizers);
+    {
+      std::vector<std::vector<MinimizerOcc>> parts((size_t)std::max(1, build_threads()));
+      parallel_blocks(us.n_unitigs(), [&](int t, u64 lo, u64 hi) {
+        for (u64 ui = lo; ui < hi; ++ui) collect_unitig(us, ui, w, seed, parts[t]);
+      });
+      for (auto& part : parts) {  // blocks are contiguous unitig ranges: concatenation keeps the unitig order
+        minimizers.insert(minimizers.end(), part.begin(), part.end());
+        std::vector<MinimizerOcc>().swap(part);
+      }
+    }
+    timer.lap("collect");
     // 2. sort (stable, as rayon par_sort_by_key) and group (sshash.rs:150-172)
-    std::stable_sort(minimizers.begin(), minimizers.end(),
-                     [](const MinimizerOcc& a, const MinimizerOcc& b) { return a.word < b.word; });
+    parallel_stable_sort(minimizers, [](const MinimizerOcc& a, const MinimizerOcc& b) { return a.word < b.word; });
     std::vector<u64> mm_occs, mm_set;
     {
       u64 cur = minimizers[0].word, occs = 0;
@@ -760,20 +829,29 @@ struct SSHash : K2U {
       mm_occs.push_back(occs);
       mm_set.push_back(cur);
     }
+    timer.lap("sort + group");
     // 3. MPHF over minimizers (sshash.rs:177)
     h.mphf = OracleMphf::build(mm_set, 1.7);
+    timer.lap("mphf");
     // 4. bucket sizes in MPHF order -> prefix sum (sshash.rs:181-189)
-    std::vector<u64> n_occs(mm_set.size(), USIZE_MAX);
-    for (size_t i = 0; i < mm_set.size(); ++i) n_occs[h.mphf.hash(mm_set[i])] = mm_occs[i];
+    std::vector<u64> n_occs(mm_set.size(), USIZE_MAX), mm_hash(mm_set.size());
+    parallel_blocks(mm_set.size(), [&](int, u64 lo, u64 hi) {  // the MPHF is a bijection: every thread writes its own slots
+      for (u64 i = lo; i < hi; ++i) {
+        mm_hash[i] = h.mphf.hash(mm_set[i]);
+        n_occs[mm_hash[i]] = mm_occs[i];
+      }
+    });
     std::vector<u64> occs_prefix_sum = prefix_sum(n_occs);
-    // 5. scatter positions (sshash.rs:196-219)
+    // 5. scatter positions (sshash.rs:196-219; the reference scatters through an UnsafeSlice from a rayon loop)
     std::vector<u64> pos(minimizers.size(), USIZE_MAX);
     std::vector<u64> ranges = prefix_sum(mm_occs);
-    for (size_t i = 0; i < mm_set.size(); ++i) {
-      u64 hh = h.mphf.hash(mm_set[i]);
-      u64 sh = occs_prefix_sum[hh];
-      for (u64 j = ranges[i]; j < ranges[i + 1]; ++j) pos[sh + (j - ranges[i])] = minimizers[j].pos;
-    }
+    parallel_blocks(mm_set.size(), [&](int, u64 lo, u64 hi) {
+      for (u64 i = lo; i < hi; ++i) {
+        u64 sh = occs_prefix_sum[mm_hash[i]];
+        for (u64 j = ranges[i]; j < ranges[i + 1]; ++j) pos[sh + (j - ranges[i])] = minimizers[j].pos;
+      }
+    });
+    timer.lap("bucket sizes + scatter");
     // 6. skew index (sshash.rs:222-296)
     if (skew_param != USIZE_MAX) {
       std::vector<std::pair<u64, u64>> skew_tuples;
@@ -792,8 +870,7 @@ struct SSHash : K2U {
           }
         }
       }
-      std::stable_sort(skew_tuples.begin(), skew_tuples.end(),
-                       [](const std::pair<u64, u64>& a, const std::pair<u64, u64>& b) { return a.first < b.first; });
+      parallel_stable_sort(skew_tuples, [](const std::pair<u64, u64>& a, const std::pair<u64, u64>& b) { return a.first < b.first; });
       // dedup_by_key keeps the first of each run (sshash.rs:273-274)
       std::vector<std::pair<u64, u64>> ded;
       for (auto& t : skew_tuples)
@@ -806,10 +883,12 @@ struct SSHash : K2U {
       for (auto& t : ded) sp[h.skew_mphf.hash(t.first)] = t.second;
       h.skew_pos = IntVector::packed(sp);
     }
+    timer.lap("skew index");
     // finish (sshash.rs:310-329)
     h.occs_prefix_sum = EFVector::from_slice(occs_prefix_sum);
     h.pos = IntVector::packed(pos);
     h.n_minimizer_occs = pos.size();
+    timer.lap("elias-fano + packing");
     return H;
   }
 

@@ -152,3 +152,25 @@ def device_kmers_from_packed(torch, useq_words_dev, n_bases, n, k, gen, frac_pos
     rnd = torch.randint(0, 1 << 62, (n,), generator=gen, device=dev) & mask
     is_pos = torch.rand(n, generator=gen, device=dev) < frac_pos
     return torch.where(is_pos, w, rnd)
+
+
+def reads_from_packed(words, n_bases, n_reads, read_len, seed, frac_ref, sub_rate, codes=None):
+    """numpy twin of device_reads_from_packed (the CPU arms of bench.py): the same mix drawn with numpy's generator.
+    `codes` = unpack_2bit(words, n_bases) if the caller already holds it (one byte per base)."""
+    rng = np.random.default_rng(seed)
+    if codes is None:
+        codes = unpack_2bit(words, n_bases)
+    rows = np.lib.stride_tricks.sliding_window_view(codes, read_len)
+    out = rng.integers(0, 4, size=(n_reads, read_len), dtype=np.uint8)
+    is_ref = np.nonzero(rng.random(n_reads) < frac_ref)[0]
+    starts = rng.integers(0, n_bases - read_len + 1, size=len(is_ref))
+    ref = rows[starts]
+    strand = rng.random(len(is_ref)) < 0.5
+    ref[strand] = COMP[ref[strand][:, ::-1]]
+    out[is_ref] = ref
+    out = out.reshape(-1)
+    if sub_rate > 0:
+        n_sub = rng.binomial(out.size, sub_rate)
+        at = rng.integers(0, out.size, size=n_sub)
+        out[at] = (out[at] + rng.integers(1, 4, size=n_sub, dtype=np.uint8)) & 3
+    return ACGT[out]

@@ -53,6 +53,8 @@ def lib():
             "orc_decode_piscem": (None, [u64, u64, u64, vp]),
             "orc_required_num_bits": (i32, [u64, u64, vp]),
             "orc_revcomp": (u64, [u64, i32]),
+            "orc_revcomp_loop": (u64, [u64, i32]),
+            "orc_set_build_threads": (i32, [i32]),
             "orc_mm_hash32": (u64, [u64, u64]),
             "orc_canonical_minimizer": (None, [u64, i32, i32, u64, vp, vp]),
             "orc_encode_read": (u64, [vp, u64, i32, i32, u64, vp, vp, vp, vp, vp]),
@@ -149,10 +151,15 @@ class OracleIndex:
         return cls(lib().orc_index_from_seqs(concat, _ptr(offs), len(seqs), k, kind, w, skew, seed))
 
     @classmethod
-    def from_packed(cls, k, words, n_bases, accum, kind, w=0, skew=USIZE_MAX, seed=0):
+    def from_packed(cls, k, words, n_bases, accum, kind, w=0, skew=USIZE_MAX, seed=0, build_threads=1):
+        """build_threads > 1: the one-time builder runs threaded (the reference's builder is rayon-parallel); same tables."""
         words = np.ascontiguousarray(words, dtype=np.uint64)
         accum = np.ascontiguousarray(accum, dtype=np.uint64)
-        return cls(lib().orc_index_from_packed(k, _ptr(words), n_bases, _ptr(accum), len(accum) - 1, kind, w, skew, seed))
+        prev = lib().orc_set_build_threads(build_threads)
+        try:
+            return cls(lib().orc_index_from_packed(k, _ptr(words), n_bases, _ptr(accum), len(accum) - 1, kind, w, skew, seed))
+        finally:
+            lib().orc_set_build_threads(prev)
 
     def rebuild_k2u(self, kind, w=0, skew=USIZE_MAX, seed=0):
         return OracleIndex(lib().orc_index_rebuild_k2u(self.h, kind, w, skew, seed))

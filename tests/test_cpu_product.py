@@ -137,13 +137,15 @@ def test_hit_run_decoder_round_trip():
         assert len(runs) < n // 8
 
 
-def test_bench_reference_arm_contract():
+@pytest.mark.parametrize("extra,prefix", [(["--workload", "config2"], "configs[1]"), (["--cpu-scale", "0.002"], "configs[4]")])
+def test_bench_reference_arm_contract(extra, prefix):
     """`bench.py --impl reference` needs no GPU: it must print ONE JSON line with the driver's keys (metric, value, unit, n_gpus,
-    steps, warmup, ms_per_step, higher_is_better, scaling, vs_baseline, dtype, data, config.workload) plus impl / cpu_baseline / e2e."""
+    steps, warmup, ms_per_step, higher_is_better, scaling, vs_baseline, dtype, data, config.workload) plus impl / cpu_baseline / e2e.
+    The default workload is configs[4] (the port builds its index at --cpu-scale); `config` is the GPU arm's, key for key."""
     import json
     import sys
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-seconds", "1"],
-                       capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-seconds", "1"] + extra,
+                       capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -151,6 +153,14 @@ def test_bench_reference_arm_contract():
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config"):
         assert key in d, key
     assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "lookups/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert "workload" in d["config"] and d["config"]["workload"].startswith("configs[1]")
+    assert d["config"]["workload"].startswith(prefix) and len(d["config"]["workload"]) <= 118  # the driver keeps 120 characters
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # same config dict as the GPU arm would print for the same flags
+    sys.path.insert(0, ROOT)
+    import bench
+    sys.argv = ["bench.py"] + extra
+    assert d["config"] == bench.bench_config(bench.parse_args())
+    if prefix == "configs[4]":
+        # 70 % reference reads x 0.99^31 surviving k-mers x ~70 % of the windows of a 150 bp read inside one unitig (mean length 98)
+        assert 0.3 < d["counts"]["n_hit"] / d["counts"]["n_kmers"] < 0.42

@@ -424,7 +424,15 @@ def test_validate_fasta_tiny_with_poly_n(kind):
         g, o = mz.PiscemIndex.from_cf_prefix(TINY_CF, 3, 2), OracleIndex.from_cf(TINY_CF, 1, w=3, skew=2)
     else:
         g, o = mz.PufferfishDenseIndex.from_cf_prefix(TINY_CF), OracleIndex.from_cf(TINY_CF, 0)
-    bases, offs = fasta_as_reads(TINY_CF + ".fa")
+    # Validate::validate_fasta / StreamingIndex::validate_fasta through the C ABI: the LIBRARY reads the file (poly-N, lower case)
+    for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+        got = g.validate_fasta(TINY_CF + ".fa", mode)
+        assert got == o.validate_fasta(TINY_CF + ".fa", streaming=bool(mode)) and got[0] == 16 and got[4] == 0
+    assert g.as_streaming().validate_fasta(TINY_CF + ".fa")[4] == 0
+    fa = mz.Fasta(TINY_CF + ".fa")
+    bases, offs = fa.bases, fa.offsets
+    b2, o2 = fasta_as_reads(TINY_CF + ".fa")
+    assert np.array_equal(bases, b2) and np.array_equal(offs, o2)
     for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
         want, cnt = _check_reads(g, o, bases, offs, mode)
         assert cnt[0] == 16 and cnt[2] == 0
@@ -451,7 +459,11 @@ def test_validate_fasta_yeast_chr7_long_record(kind):
         assert g.n_minimizers == o.n_minimizers < g.n_kmers
     else:
         g, o = mz.PufferfishDenseIndex.from_cf_prefix(YEAST_CF), OracleIndex.from_cf(YEAST_CF, 0)
-    bases, offs = fasta_as_reads(YEAST_CF + ".fa")
+    for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+        got = g.validate_fasta(YEAST_CF + ".fa", mode)
+        assert got == o.validate_fasta(YEAST_CF + ".fa", streaming=bool(mode)) and got[0] == 1090910 and got[4] == 0
+    fa = mz.Fasta(YEAST_CF + ".fa")
+    bases, offs = fa.bases, fa.offsets
     for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
         want, cnt = _check_reads(g, o, bases, offs, mode)
         assert cnt[0] == 1090910 and cnt[2] == 0
@@ -466,6 +478,66 @@ def test_validate_fasta_yeast_chr7_long_record(kind):
     ok[owner[(mrps["ref_id"] == 0) & (mrps["pos"] == owner)]] = True
     assert ok.all()
     assert g.k2u_validate_self() == o.k2u_validate_self()
+
+
+def test_validate_fasta_reports_failures(tmp_path, yeast_dense):
+    """records that are NOT the index's references: every k-mer that misses, or maps elsewhere, is a failure (the reference panics)"""
+    g, o = yeast_dense
+    ref_codes = _gen.unpack_2bit(o.refseq_words(), int(o.ref_prefix()[-1]))
+    ref = _gen.ACGT[ref_codes[:5000]].tobytes().decode()
+    rng = np.random.default_rng(5)
+    rnd = _gen.ACGT[rng.integers(0, 4, 600)].tobytes().decode()
+    # record 0 = a true prefix of reference 0 (passes, lower-cased and wrapped); record 1 = a slice from position 1000, so its k-mers
+    # project onto (ref 0, 1000 + p), not (ref 1, p): found but failing; record 2 = random sequence: misses; record 3 shorter than k
+    path = tmp_path / "mix.fa"
+    with open(path, "w") as f:
+        f.write(">r0 a prefix\n")
+        low = ref[:3000].lower()
+        for i in range(0, len(low), 70):
+            f.write(low[i:i + 70] + "\r\n")
+        f.write(">r1\n" + ref[1000:1500] + "\n>r2\n" + rnd + "\nNNNN\n>r3\nACGT\n")
+    for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+        got = g.validate_fasta(path, mode)
+        want = o.validate_fasta(str(path), streaming=bool(mode))
+        assert got == want
+        assert got[0] == (3000 - 30) + (500 - 30) + (600 - 30) and got[4] == (500 - 30) + (600 - 30)
+    fa = mz.Fasta(path)
+    assert fa.names == ["r0 a prefix", "r1", "r2", "r3"] and fa.seqs()[0] == ref[:3000].lower() and fa.seqs()[2] == rnd + "NNNN"
+    assert g.validate_reads(fa.bases, fa.offsets) == g.validate_fasta(path)
+    with pytest.raises(mz.MazuError) as e:
+        g.validate_fasta(tmp_path / "missing.fa")
+    assert e.value.code == -1
+
+
+def test_fasta_reader_semantics(tmp_path):
+    """FastaReader's own unit test (src/util.rs:157-185) + FASTQ; host code, but it is the ingest of the GPU validate path"""
+    p = tmp_path / "a.fa"
+    p.write_text(">A\nACG\nAC\n>B\nACG\nACG\nC")
+    fa = mz.Fasta(p)
+    assert fa.names == ["A", "B"] and fa.seqs() == ["ACGAC", "ACGACGC"] and list(fa.offsets) == [0, 5, 12]
+    q = tmp_path / "a.fq"
+    q.write_text("@r1 x\nACGTN\n+\nIIIII\n@r2\nGG\n+r2\nII\n")
+    fq = mz.Fasta(q)
+    assert fq.names == ["r1 x", "r2"] and fq.seqs() == ["ACGTN", "GG"]
+    bad = tmp_path / "bad.fq"
+    bad.write_text("@r1\nACGT\n+\nIII\n")
+    with pytest.raises(mz.MazuError) as e:
+        mz.Fasta(bad)
+    assert e.value.code == -2
+    empty = tmp_path / "e.fa"
+    empty.write_text("")
+    assert mz.Fasta(empty).names == []
+
+
+def test_unitig_seq_accessor(yeast_dense):
+    """K2U::unitig_seq (src/kphf/mod.rs:64) through the ABI equals the oracle's unitig sequence"""
+    g, o = yeast_dense
+    codes = _gen.unpack_2bit(o.useq_words(), o.total_len)
+    for ui in (0, 1, 17, o.n_unitigs - 1):
+        s0, n = o.unitig_start(ui), o.unitig_len(ui)
+        assert g.unitig_seq(ui) == _gen.ACGT[codes[s0:s0 + n]].tobytes().decode()
+    with pytest.raises(mz.MazuError):
+        g.unitig_seq(o.n_unitigs)
 
 
 # --------------------------------------------------------------------------------------------
@@ -543,6 +615,56 @@ def test_decode_and_project_synthetic_high_multiplicity(kind):
     with pytest.raises(mz.MazuError) as e:
         mz.SSHash.from_unitig_set(us, 19, 64).decode_occs(q)
     assert e.value.code == mz.ERR_NO_U2POS
+
+
+@pytest.mark.parametrize("kind", ["dense", "piscem"])
+def test_decode_device_mode_undersized_buffer_is_never_overrun(kind):
+    """MAZU_MEM_DEVICE without out_total cannot report a too-small buffer (no synchronisation): the fill kernels must stop at
+    `cap`.  A guard region behind the buffer stays untouched, the records before it are exact, out_offsets[n] reports the
+    need; long lists take the staged (bulk-copy) kernel, short ones the plain one.  Unitig ids outside the table are empty lists."""
+    import torch
+    import ctypes as C
+    k = 31
+    for U, lo_mult in ((300, 5000), (3000, 1)):
+        codes, accum = _gen.synthetic_unitigs(U, 68, k, seed=44)
+        us = mz.UnitigSet(k, mz.pack_2bit(codes), len(codes), accum)
+        g = mz.PFHash.from_unitig_set(us)
+        o = OracleIndex.from_packed(k, us.useq_words, us.n_bases, accum, 0)
+        n_refs, max_ref_len = 4096, 1 << 27
+        offsets, ref_ids, poss, fws = _synthetic_u2pos(U, n_refs, max_ref_len, 44, 5000)
+        if lo_mult > 1:  # make every list long so the launcher picks the staged kernel
+            mult = np.maximum(np.diff(offsets), 200).astype(np.uint64)
+            offsets = np.concatenate([[0], np.cumsum(mult)]).astype(np.uint64)
+            n = int(offsets[-1])
+            rng = np.random.default_rng(7)
+            ref_ids, poss, fws = rng.integers(0, n_refs, n, dtype=np.uint64), rng.integers(0, max_ref_len - 4096, n, dtype=np.uint64), rng.integers(0, 2, n, dtype=np.uint64)
+        o.attach_u2pos(0 if kind == "dense" else 1, offsets, ref_ids, poss, fws, max_ref_len, n_refs)
+        off_vec = mz.PackedVec.pack(offsets)
+        if kind == "dense":
+            g.attach_u2pos_dense(((poss.astype(np.uint64) | (fws.astype(np.uint64) << np.uint64(31))) << np.uint64(32)) | ref_ids.astype(np.uint64), off_vec)
+        else:
+            enc = (ref_ids.astype(np.uint64) << np.uint64(29)) | (poss.astype(np.uint64) << np.uint64(1)) | fws.astype(np.uint64)
+            g.attach_u2pos_piscem(mz.PackedVec.pack(enc, 42), 29, (1 << 28) - 1, off_vec)
+        q = np.random.default_rng(3).integers(0, U, size=4000).astype(np.uint32)
+        q[5] = U + 7          # outside the table: an empty list, not an out-of-bounds read
+        q[9] = mz.MISS
+        want_offs, want = o.decode_occs(np.where(q >= U, mz.MISS, q).astype(np.uint32))
+        total = int(want_offs[-1])
+        for cap in (total, total - 1, total // 2 + 3, 1, 0):
+            guard = 4096
+            d_q = torch.from_numpy(q.view(np.int32)).cuda()
+            d_offs = torch.zeros(len(q) + 1, dtype=torch.int64, device="cuda")
+            d_out = torch.full(((cap + guard), 3), -1, dtype=torch.int32, device="cuda")
+            mz._check(mz.lib().mazu_b200_decode_occs(g._h, mz._any_ptr(d_q), len(q), mz._any_ptr(d_offs), mz._any_ptr(d_out), cap, None, mz.MEM_DEVICE, None))
+            torch.cuda.synchronize()
+            got = d_out.cpu().numpy().view(np.uint32)
+            assert np.array_equal(d_offs.cpu().numpy().view(np.uint64), want_offs)
+            assert (got[cap:] == 0xFFFFFFFF).all(), "records written beyond the capacity (cap %d of %d)" % (cap, total)
+            assert np.array_equal(got[:cap].reshape(-1).view(mz.OCC_DTYPE), want[:cap])
+        # with out_total the host learns the need and the call reports the error
+        tot = C.c_uint64(0)
+        rc = mz.lib().mazu_b200_decode_occs(g._h, mz._any_ptr(d_q), len(q), mz._any_ptr(d_offs), mz._any_ptr(d_out), total - 1, C.byref(tot), mz.MEM_DEVICE, None)
+        assert rc == -7 and tot.value == total
 
 
 def test_fuzz_decode_tables():
@@ -996,6 +1118,58 @@ def test_two_devices_in_one_process(yeast_queries):
     assert [int(a) + int(b) for a, b in zip(res[0][1], res[1][1])] == [int(x) for x in wcnt]  # the final host-side gather of counters
     pr = np.concatenate([res[0][3], res[1][3]])
     assert np.array_equal(pr.view(np.uint32).reshape(-1, 3), np.asarray(wpr).view(np.uint32).reshape(-1, 3))
+
+
+def test_replicate_and_sharded_queries(yeast_sshash, yeast_queries):
+    """mazu_b200_index_replicate + the sharded calls: replicas are bit-identical copies made device to device,
+    a sharded call over them returns exactly the single-handle answers.  With one visible GPU both replicas live on device 0
+    (the copy / pointer-rebasing / sharding / run-region logic is the same); with two or more they are on different devices."""
+    g, o = yeast_sshash
+    _, ref_codes = yeast_queries
+    n_dev = mz.device_count()
+    devices = [0, 1 % n_dev, 2 % n_dev]
+    reps = g.replicate(devices)
+    assert [r.device for r in reps] == devices
+    for which in range(8):  # every named table is byte-identical on every replica
+        assert all(r.table_digest(which) == g.table_digest(which) for r in reps)
+    assert all(r.k2u_validate_self() == g.k2u_validate_self() for r in reps)
+    for ragged in (True, False):
+        bases, offs = _gen.sample_reads(ref_codes, 3001, 150, seed=11, frac_ref=0.7, sub_rate=0.01, n_rate=0.002, ragged=ragged)
+        for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+            want, wcnt, wko = o.query_reads(bases, offs, streaming=bool(mode))
+            if ragged:
+                got, cnt, ko = mz.query_reads_sharded(reps, bases, read_offsets=offs, mode=mode)
+            else:
+                got, cnt, ko = mz.query_reads_sharded(reps, bases, uniform_read_len=150, mode=mode)
+            assert_hits_equal(got, want, "sharded ragged=%s mode=%d" % (ragged, mode))
+            assert list(cnt) == list(wcnt) and np.array_equal(ko, wko)
+            kw = dict(read_offsets=offs) if ragged else dict(uniform_read_len=150)
+            codes, runs, rro, cnt2, ko2, n_runs = mz.query_reads_runs_sharded(reps, bases, mode=mode, **kw)
+            exp = mz.ModIndex.expand_hit_runs(codes, runs, rro, kmer_offsets=ko2)
+            assert_hits_equal(exp, want, "sharded runs ragged=%s mode=%d" % (ragged, mode))
+            assert list(cnt2) == list(wcnt) and n_runs == int((codes == 2).sum())
+            # pinned run buffers take the sync-free path
+            pr = mz.PinnedArray(len(runs), mz.HIT_DTYPE)
+            pc = mz.PinnedArray(len(codes), np.uint8)
+            po = mz.PinnedArray(len(rro), np.uint64)
+            c3, r3, o3, cnt3, ko3, n3 = mz.query_reads_runs_sharded(reps, bases, mode=mode, codes=pc.array, runs=pr.array, read_run_offsets=po.array, **kw)
+            assert_hits_equal(mz.ModIndex.expand_hit_runs(c3, r3, o3, kmer_offsets=ko3), want, "sharded pinned runs")
+            assert n3 == n_runs
+    # a region too small for one shard's runs is reported with the capacity needed
+    bases, offs = _gen.sample_reads(ref_codes, 900, 150, seed=12, frac_ref=1.0, sub_rate=0.05)
+    with pytest.raises(mz.MazuError) as e:
+        import ctypes as C
+        codes = np.empty(g.count_kmer_slots(offs), dtype=np.uint8)
+        runs = np.empty(6, dtype=mz.HIT_DTYPE)
+        rro = np.zeros(len(offs), dtype=np.uint64)
+        n_runs = C.c_uint64(0)
+        mz._check(mz.lib().mazu_b200_query_reads_runs_sharded(mz._handle_array(reps), len(reps), mz._np_ptr(bases), mz._np_ptr(offs), len(offs) - 1, 0, 0, None,
+                                                               mz._np_ptr(codes), mz._np_ptr(runs), len(runs), mz._np_ptr(rro), C.byref(n_runs), None))
+    assert e.value.code == -7 and n_runs.value > 6
+    # the dense (PFHash + U2Pos + references) handle replicates too: validate_self needs every group of tables
+    gd = mz.DenseIndex.deserialize_from_cpp(YEAST_CHR01)
+    rd = gd.replicate([n_dev - 1])[0]
+    assert rd.validate_self() == gd.validate_self() == [230188, 170689, 59499, 262130, 0]
 
 
 def test_scratch_pool_is_reused_and_released(yeast_sshash, yeast_queries):
