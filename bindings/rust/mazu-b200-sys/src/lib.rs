@@ -151,6 +151,7 @@ extern "C" {
     pub fn mazu_b200_k2u_validate_self(idx: *const mazu_index_t, counts: *mut u64) -> mazu_status_t;
     pub fn mazu_b200_alloc_pinned(bytes: u64, out: *mut *mut c_void) -> mazu_status_t;
     pub fn mazu_b200_free_pinned(p: *mut c_void);
+    pub fn mazu_b200_get_ref_pos_reads(idx: *const mazu_index_t, bases: *const u8, read_offsets: *const u64, n_reads: u64, uniform_read_len: u64, mode: i32, n_slots: u64, kmer_offsets: *mut u64, out_hits: *mut mazu_hit_t, out_offsets: *mut u64, out_mrps: *mut mazu_occ_t, cap: u64, out_total: *mut u64, counts: *mut u64, mem: i32, stream: *mut c_void) -> mazu_status_t;
     pub fn mazu_b200_unitig_seq(idx: *const mazu_index_t, unitig_id: u64, out_words: *mut u64, cap_words: u64, len: *mut u64) -> mazu_status_t;
     pub fn mazu_b200_fasta_open(path: *const c_char, out: *mut *mut mazu_fasta_t) -> mazu_status_t;
     pub fn mazu_b200_fasta_close(f: *mut mazu_fasta_t);

@@ -56,6 +56,7 @@ enum { MAZU_NO_MATCH = 0, MAZU_IDENTITY_MATCH = 1, MAZU_TWIN_MATCH = 2,
 enum { MAZU_MEM_HOST = 0, MAZU_MEM_DEVICE = 1, MAZU_MEM_HOST_IN_DEVICE_OUT = 2 };
 enum { MAZU_MODE_RANDOM = 0,    /* K2U::k2u per k-mer                 (src/bin/kphf/main.rs:311-322) */
        MAZU_MODE_STREAMING = 1  /* .as_streaming() / StreamingK2U     (src/index/caching.rs:65-103); cursor reset per read */ };
+/* (A streaming answer differs from K2U::k2u only for k-mers the unitig set holds twice: see MAZU_INFO_KMERS_UNIQUE.) */
 enum { MAZU_K2U_PFHASH = 0, MAZU_K2U_SSHASH = 1,
        MAZU_K2U_SAMPLED_PFHASH = 2 /* pufferfish sparse index, load-only (src/kphf/pfhash.rs:137-285) */ };
 enum { MAZU_U2POS_NONE = 0, MAZU_U2POS_DENSE = 1, MAZU_U2POS_PISCEM = 2 };
@@ -175,7 +176,10 @@ enum { MAZU_INFO_K = 0, MAZU_INFO_N_UNITIGS = 1, MAZU_INFO_N_KMERS = 2, MAZU_INF
        MAZU_INFO_N_KMERS_IN_SKEW_INDEX = 5 /* sshash.rs:337-339 */, MAZU_INFO_N_REFS = 6, MAZU_INFO_N_TOTAL_OCCS = 7,
        MAZU_INFO_K2U_KIND = 8, MAZU_INFO_U2POS_KIND = 9, MAZU_INFO_DEVICE_BYTES = 10, MAZU_INFO_W = 11,
        MAZU_INFO_N_MINIMIZER_OCCS = 12, MAZU_INFO_MPHF_LEVELS = 13, MAZU_INFO_DEVICE = 14,
-       MAZU_INFO_SAMPLE_SIZE = 15, MAZU_INFO_EXTENSION_SIZE = 16 /* SampledPFHash, src/kphf/pfhash.rs:149-150 */ };
+       MAZU_INFO_SAMPLE_SIZE = 15, MAZU_INFO_EXTENSION_SIZE = 16 /* SampledPFHash, src/kphf/pfhash.rs:149-150 */,
+       MAZU_INFO_KMERS_UNIQUE = 17 /* 1: the canonical k-mers of the unitig set are pairwise distinct (checked on the device at
+                                      creation).  MAZU_MODE_STREAMING then returns the records of MAZU_MODE_RANDOM by construction and is
+                                      served by the random-access kernel; the cursor-walk kernel runs for sets with duplicated k-mers */ };
 uint64_t mazu_b200_index_info(const mazu_index_t* idx, int32_t what);
 /* K2U::unitig_len(id)  src/kphf/mod.rs:61 ; UnitigSet::unitig_start_pos  src/unitig_set.rs:197-199 */
 mazu_status_t mazu_b200_unitig_len(const mazu_index_t* idx, uint64_t unitig_id, uint64_t* len, uint64_t* start_pos);
@@ -253,6 +257,22 @@ mazu_status_t mazu_b200_decode_occs(const mazu_index_t* idx, const uint32_t* uni
  * convention as decode_occs but records are MappedRefPos.  Misses / skipped records yield empty lists. */
 mazu_status_t mazu_b200_project_hits(const mazu_index_t* idx, const mazu_hit_t* hits, uint64_t n, uint64_t* out_offsets,
                                      mazu_occ_t* out_mrps, uint64_t cap, uint64_t* out_total, int32_t mem, void* stream);
+
+/* GetRefPos::get_ref_pos + project_hits over a read batch in ONE pass (src/index.rs:156-216 inside the read loop of
+ * validate_ckmers, src/index/validate.rs:54-81): reads -> K2UPos -> occurrence list -> MappedRefPos, without materialising and
+ * re-reading the hit records.  Outputs, per k-mer slot (slot = kmer_offsets[r] + position in read r):
+ *   out_offsets  n_slots + 1: prefix of the slots' list lengths (misses and skipped windows have empty lists)
+ *   out_mrps     the projected positions in slot order, capacity `cap` records
+ *   out_hits     optional: the K2UPos records, as mazu_b200_query_reads writes them
+ *   out_total    optional: number of records (if given the call synchronises and returns MAZU_ERR_INVALID_ARG when cap is too
+ *                small; without it an undersized buffer is filled up to cap, never beyond, and out_offsets[n_slots] tells)
+ * n_slots must be mazu_b200_count_kmer_slots() of the batch (the size of out_offsets - 1).  Results equal
+ * mazu_b200_query_reads followed by mazu_b200_project_hits record for record; MAZU_MODE_STREAMING on an index with duplicated
+ * k-mers runs exactly that chain. */
+mazu_status_t mazu_b200_get_ref_pos_reads(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                                          uint64_t uniform_read_len, int32_t mode, uint64_t n_slots, uint64_t* kmer_offsets,
+                                          mazu_hit_t* out_hits, uint64_t* out_offsets, mazu_occ_t* out_mrps, uint64_t cap,
+                                          uint64_t* out_total, uint64_t* counts, int32_t mem, void* stream);
 
 /* ModIndex::iter_unitigs_on_ref / RefSeqContigIterator (src/index.rs:363-424): the unitig tiling of reference `ref_id`.
  * Records are RefSeqUnitigOcc {unitig_id, unitig_len, pos (on the reference), fw} in a mazu_hit_t (match field = 1 forward,

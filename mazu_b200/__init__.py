@@ -46,7 +46,7 @@ ERR_NO_REFSEQ = -9
 
 (INFO_K, INFO_N_UNITIGS, INFO_N_KMERS, INFO_SUM_UNITIGS_LEN, INFO_N_MINIMIZERS, INFO_N_KMERS_IN_SKEW_INDEX, INFO_N_REFS,
  INFO_N_TOTAL_OCCS, INFO_K2U_KIND, INFO_U2POS_KIND, INFO_DEVICE_BYTES, INFO_W, INFO_N_MINIMIZER_OCCS, INFO_MPHF_LEVELS,
- INFO_DEVICE, INFO_SAMPLE_SIZE, INFO_EXTENSION_SIZE) = range(17)
+ INFO_DEVICE, INFO_SAMPLE_SIZE, INFO_EXTENSION_SIZE, INFO_KMERS_UNIQUE) = range(18)
 
 
 class PinnedArray:
@@ -132,6 +132,7 @@ def _signatures():
         "mazu_b200_encode_reads": (i32, [vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp]),
         "mazu_b200_decode_occs": (i32, [vp, vp, u64, vp, vp, u64, vp, i32, vp]),
         "mazu_b200_project_hits": (i32, [vp, vp, u64, vp, vp, u64, vp, i32, vp]),
+        "mazu_b200_get_ref_pos_reads": (i32, [vp, vp, vp, u64, u64, i32, u64, vp, vp, vp, vp, u64, vp, vp, i32, vp]),
         "mazu_b200_iter_unitigs_on_ref": (i32, [vp, u64, vp, u64, vp]),
         "mazu_b200_validate_self": (i32, [vp, vp]),
         "mazu_b200_k2u_validate_self": (i32, [vp, vp]),
@@ -375,6 +376,7 @@ class ModIndex:
     n_total_occs = property(lambda s: s.info(INFO_N_TOTAL_OCCS))
     device_bytes = property(lambda s: s.info(INFO_DEVICE_BYTES))
     device = property(lambda s: s.info(INFO_DEVICE))
+    kmers_unique = property(lambda s: bool(s.info(INFO_KMERS_UNIQUE)))
 
     def unitig_len(self, ui):
         ln, st = C.c_uint64(0), C.c_uint64(0)
@@ -495,6 +497,32 @@ class ModIndex:
         """GetRefPos::project_hits for a batch of hit records (host mode)."""
         hits = np.ascontiguousarray(hits, dtype=HIT_DTYPE)
         return self._occ_call(lib().mazu_b200_project_hits, hits, len(hits))
+
+    def get_ref_pos_reads(self, bases, read_offsets=None, uniform_read_len=0, mode=MODE_RANDOM, want_hits=True):
+        """GetRefPos::get_ref_pos + project_hits over reads in one pass (host mode): (hits, offsets, mrps, counts, kmer_offsets)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        if uniform_read_len:
+            n_reads, ro = len(bases) // uniform_read_len, None
+        else:
+            ro = np.ascontiguousarray(read_offsets, dtype=np.uint64)
+            n_reads = len(ro) - 1
+        n_slots = self.count_kmer_slots(ro, n_reads, uniform_read_len)
+        koffs = np.zeros(n_reads + 1, dtype=np.uint64)
+        hits = np.empty(n_slots, dtype=HIT_DTYPE) if want_hits else None
+        offs = np.zeros(n_slots + 1, dtype=np.uint64)
+        cnt = np.zeros(3, dtype=np.uint64)
+        total = C.c_uint64(0)
+        cap = max(1024, 2 * n_slots)
+        while True:
+            out = np.empty(cap, dtype=OCC_DTYPE)
+            rc = lib().mazu_b200_get_ref_pos_reads(self._h, _np_ptr(bases), _np_ptr(ro), n_reads, uniform_read_len, mode, n_slots, _np_ptr(koffs),
+                                                   _np_ptr(hits), _np_ptr(offs), _np_ptr(out), cap, C.byref(total), _np_ptr(cnt), MEM_HOST, None)
+            if rc != 0 and total.value > cap:
+                cap = total.value
+                continue
+            _check(rc)
+            break
+        return hits, offs, out[: total.value], cnt, koffs
 
     def get_ref_pos_eager(self, kmer):
         """GetRefPos::get_ref_pos_eager for one k-mer string: None or list of (ref_id, pos, fw)."""

@@ -9,6 +9,22 @@
 
 namespace {
 
+// every unitig k-mer looked up once: found anywhere but at its own position <=> the set holds a canonical k-mer twice
+void detect_unique_kmers(mazu_index& ix) {
+  static const bool skip = getenv("MAZU_B200_FORCE_WALK") != nullptr;  // measurement knob: always take the cursor-walk kernel
+  ix.kmers_unique = false;
+  if (skip || ix.unitigs->total_len() < ix.unitigs->k) return;
+  DevBuf d(8, ix.device);
+  MZ_CUDA(cudaMemset(d.p, 0, 8));
+  const u64 n = ix.unitigs->total_len();
+  const int grid = (int)std::max<u64>(1, std::min<u64>((n + 255) / 256, (u64)ix.sm_count * 8));
+  count_duplicated_kmers_kernel<<<grid, 256>>>(ix.view, (unsigned long long*)d.p);
+  MZ_CUDA(cudaGetLastError());
+  u64 bad = 0;
+  MZ_CUDA(cudaMemcpy(&bad, d.p, 8, cudaMemcpyDeviceToHost));
+  ix.kmers_unique = bad == 0;
+}
+
 mazu_index* finalize_index(std::unique_ptr<mazu_index> ix) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) throw Error(MAZU_ERR_CUDA, "no CUDA device visible: libmazu_b200 has no CPU fallback");
@@ -37,6 +53,7 @@ mazu_index* finalize_index(std::unique_ptr<mazu_index> ix) {
   upload_u2pos(*ix);
   upload_refs(*ix);
   MZ_CUDA(cudaDeviceSynchronize());
+  detect_unique_kmers(*ix);
   return ix.release();
 }
 
@@ -116,7 +133,7 @@ void launch_qr(const mazu_index* ix, const u8* d_bases, const u64* d_read_offset
       cnt = std::make_unique<PoolBuf>(ix->pool, (n_reads + 1) * 8, s);
       seg = std::make_unique<PoolBuf>(ix->pool, (n_reads + 1) * 8, s);
       MZ_CUDA(cudaMemsetAsync(cnt->p, 0, (n_reads + 1) * 8, s));
-      segment_counts_kernel<<<(int)std::min<u64>((n_reads + 255) / 256, 4096), 256, 0, s>>>(d_read_offsets, n_reads, ix->unitigs->k, (u64*)cnt->p);
+      segment_counts_kernel<<<(int)std::min<u64>((n_reads + 255) / 256, 4096), 256, 0, s>>>(d_read_offsets, n_reads, ix->unitigs->k, QR_SEGMENT, (u64*)cnt->p);
       MZ_CUDA(cudaGetLastError());
       device_exclusive_scan((const u64*)cnt->p, (u64*)seg->p, n_reads, ix->pool, s);
     }
@@ -129,8 +146,9 @@ void launch_query_reads(const mazu_index* ix, const u8* d_bases, const u64* d_re
                         const u64* d_kmer_offsets, void* d_out, u32 compact, u64* d_counts, cudaStream_t s) {
   if (n_reads == 0) return;
   const bool ss = ix->view.k2u_kind == MAZU_K2U_SSHASH;
-  const bool native = ix->view.mphf.family == MPHF_FAMILY_NATIVE;
-  const bool st = mode == MAZU_MODE_STREAMING;
+  const bool native = ix->view.mphf.family != MPHF_FAMILY_BOOPHF;  // SSHash: fingerprinted cascade for the minimizers, native MPHF for the skew index
+  // distinct canonical k-mers: the cursor walk cannot answer anything the lookup does not (kernels.cuh, count_duplicated_kmers_kernel)
+  const bool st = mode == MAZU_MODE_STREAMING && !ix->kmers_unique;
 #define MZ_QR(M, K, F) launch_qr<M, K, F>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, s)
   if (ss) {
     if (!native) throw Error(MAZU_ERR_OTHER, "internal: SSHash index without a native MPHF");
@@ -424,7 +442,7 @@ uint64_t mazu_b200_index_info(const mazu_index_t* idx, int32_t what) {
     case MAZU_INFO_N_UNITIGS: return idx->unitigs->n_unitigs();
     case MAZU_INFO_N_KMERS: return idx->unitigs->n_kmers();
     case MAZU_INFO_SUM_UNITIGS_LEN: return idx->unitigs->total_len();
-    case MAZU_INFO_N_MINIMIZERS: return idx->k2u->kind == MAZU_K2U_SSHASH ? idx->k2u->sizes.n : 0;  // len of the prefix sum (sshash.rs:333-335)
+    case MAZU_INFO_N_MINIMIZERS: return idx->k2u->kind == MAZU_K2U_SSHASH ? idx->k2u->n_minimizers + 1 : 0;  // len of the reference's prefix sum (sshash.rs:333-335)
     case MAZU_INFO_N_KMERS_IN_SKEW_INDEX: return idx->k2u->n_skew_kmers;
     case MAZU_INFO_N_REFS: return idx->refs ? idx->refs->n_refs() : 0;
     case MAZU_INFO_N_TOTAL_OCCS: return idx->u2pos ? idx->u2pos->n_occs : 0;
@@ -437,6 +455,7 @@ uint64_t mazu_b200_index_info(const mazu_index_t* idx, int32_t what) {
     case MAZU_INFO_DEVICE: return (u64)idx->device;
     case MAZU_INFO_SAMPLE_SIZE: return idx->k2u->sample_size;
     case MAZU_INFO_EXTENSION_SIZE: return idx->k2u->extension_size;
+    case MAZU_INFO_KMERS_UNIQUE: return idx->kmers_unique ? 1 : 0;
   }
   return 0;
 }
@@ -848,6 +867,7 @@ mazu_status_t mazu_b200_index_replicate(const mazu_index_t* src, const int32_t* 
       ix->u2pos = src->u2pos;
       ix->refs = src->refs;
       ix->compact_ok = src->compact_ok;
+      ix->kmers_unique = src->kmers_unique;
       ix->view = src->view;
       ix->tables = src->tables;
       cudaDeviceProp prop;
@@ -1173,6 +1193,139 @@ static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu
     if (total) MZ_CUDA(cudaMemcpyAsync(out, d_o, total * 12, cudaMemcpyDeviceToHost, s));
     MZ_CUDA(cudaStreamSynchronize(s));
   }
+}
+
+// fused reads -> MappedRefPos (get_ref_pos_reads_kernel); device pointers, work enqueued on `s`
+static void launch_get_ref_pos_reads(const mazu_index_t* idx, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len,
+                                     const u64* d_kmer_offsets, Hit* d_hits, u64* d_counts, u64 n_slots, u64* d_offsets, OccRec* d_out, u64 cap,
+                                     u64* d_total, cudaStream_t s) {
+  const u32 k = idx->unitigs->k;
+  std::unique_ptr<PoolBuf> cnt, seg;
+  u64 n_tiles;
+  if (uniform_len) {
+    const u64 nk = uniform_len >= k ? uniform_len - k + 1 : 0;
+    n_tiles = n_reads * (nk <= (u64)QR_CHUNK ? 1 : (nk + QR_CHUNK - 1) / QR_CHUNK);
+  } else {  // one tile per chunk of QR_CHUNK k-mer positions, at least one per read
+    cnt = std::make_unique<PoolBuf>(idx->pool, (n_reads + 1) * 8, s);
+    seg = std::make_unique<PoolBuf>(idx->pool, (n_reads + 1) * 8, s);
+    MZ_CUDA(cudaMemsetAsync(cnt->p, 0, (n_reads + 1) * 8, s));
+    segment_counts_kernel<<<(int)std::min<u64>((n_reads + 255) / 256, 4096), 256, 0, s>>>(d_read_offsets, n_reads, k, (u64)QR_CHUNK, (u64*)cnt->p);
+    MZ_CUDA(cudaGetLastError());
+    device_exclusive_scan((const u64*)cnt->p, (u64*)seg->p, n_reads, idx->pool, s);
+    MZ_CUDA(cudaMemcpyAsync(&n_tiles, (u64*)seg->p + n_reads, 8, cudaMemcpyDeviceToHost, s));
+    MZ_CUDA(cudaStreamSynchronize(s));
+  }
+  PoolBuf status(idx->pool, (n_tiles + 1) * 8, s), ticket(idx->pool, 8, s);
+  MZ_CUDA(cudaMemsetAsync(status.p, 0, (n_tiles + 1) * 8, s));
+  MZ_CUDA(cudaMemsetAsync(ticket.p, 0, 8, s));
+  ProjOut pj{(unsigned long long*)status.p, (unsigned long long*)ticket.p, d_offsets, d_out, cap, n_slots, n_tiles, d_total};
+  if (n_tiles == 0) {
+    MZ_CUDA(cudaMemsetAsync(d_offsets, 0, 8, s));
+    if (d_total) MZ_CUDA(cudaMemsetAsync(d_total, 0, 8, s));
+    return;
+  }
+  const bool ss = idx->view.k2u_kind == MAZU_K2U_SSHASH, boophf = idx->view.mphf.family == MPHF_FAMILY_BOOPHF;
+#define MZ_GRP(K, F)                                                                                                              \
+  {                                                                                                                                \
+    auto kern = get_ref_pos_reads_kernel<K, F>;                                                                                    \
+    int grid = grid_for(kern, QR_WARPS * 32, idx, 1, ~0ULL >> 8);                                                                  \
+    kern<<<grid, QR_WARPS * 32, 0, s>>>(idx->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_hits,          \
+                                        (unsigned long long*)d_counts, seg ? (const u64*)seg->p : nullptr, pj);                    \
+  }
+  if (ss) MZ_GRP(MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE)
+  else if (idx->view.k2u_kind == MAZU_K2U_SAMPLED_PFHASH) MZ_GRP(MAZU_K2U_SAMPLED_PFHASH, MPHF_FAMILY_BOOPHF)
+  else if (boophf) MZ_GRP(MAZU_K2U_PFHASH, MPHF_FAMILY_BOOPHF)
+  else MZ_GRP(MAZU_K2U_PFHASH, MPHF_FAMILY_NATIVE)
+#undef MZ_GRP
+  MZ_CUDA(cudaGetLastError());
+}
+
+mazu_status_t mazu_b200_get_ref_pos_reads(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                                          uint64_t uniform_read_len, int32_t mode, uint64_t n_slots, uint64_t* kmer_offsets, mazu_hit_t* out_hits,
+                                          uint64_t* out_offsets, mazu_occ_t* out_mrps, uint64_t cap, uint64_t* out_total, uint64_t* counts,
+                                          int32_t mem, void* stream) {
+  return guarded([&] {
+    if (!idx || !out_offsets || (n_reads && !bases) || (cap && !out_mrps)) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    if (idx->view.u2pos_kind == MAZU_U2POS_NONE) throw Error(MAZU_ERR_NO_U2POS, "index has no U2Pos table");
+    if (mode != MAZU_MODE_RANDOM && mode != MAZU_MODE_STREAMING) throw Error(MAZU_ERR_INVALID_ARG, "unknown query mode");
+    if (mem != MAZU_MEM_HOST && mem != MAZU_MEM_DEVICE) throw Error(MAZU_ERR_INVALID_ARG, "unknown mem mode");
+    if (n_reads && !uniform_read_len && !read_offsets) throw Error(MAZU_ERR_INVALID_ARG, "read_offsets is required for ragged reads");
+    const u32 k = idx->unitigs->k;
+    DeviceGuard g(idx->device);
+    if (mem == MAZU_MEM_HOST) {
+      if (n_slots != mazu_b200_count_kmer_slots(idx, read_offsets, n_reads, uniform_read_len)) throw Error(MAZU_ERR_INVALID_ARG, "n_slots does not match the reads");
+      StreamPair sp;
+      cudaStream_t s = sp.s[0];
+      const u64 nb = uniform_read_len ? n_reads * uniform_read_len : (n_reads ? read_offsets[n_reads] - read_offsets[0] : 0);
+      PoolBuf d_bases(idx->pool, nb + 16, s), d_ro(idx->pool, (n_reads + 1) * 8, s), d_ko(idx->pool, (n_reads + 1) * 8, s),
+          d_hits(idx->pool, out_hits ? n_slots * 16 + 16 : 16, s), d_offs(idx->pool, (n_slots + 1) * 8, s), d_out(idx->pool, cap * 12 + 16, s),
+          d_cnt(idx->pool, 24, s), d_tot(idx->pool, 8, s);
+      if (nb) MZ_CUDA(cudaMemcpyAsync(d_bases.p, bases + (uniform_read_len ? 0 : read_offsets[0]), nb, cudaMemcpyHostToDevice, s));
+      std::vector<u64> rel;
+      if (!uniform_read_len) {
+        rel.resize(n_reads + 1);
+        for (u64 i = 0; i <= n_reads; ++i) rel[i] = read_offsets[i] - read_offsets[0];
+        MZ_CUDA(cudaMemcpyAsync(d_ro.p, rel.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+      }
+      MZ_CUDA(cudaMemsetAsync(d_cnt.p, 0, 24, s));
+      u64 total = 0;
+      mazu_status_t rc = mazu_b200_get_ref_pos_reads(idx, (const uint8_t*)d_bases.p, uniform_read_len ? nullptr : (const uint64_t*)d_ro.p, n_reads,
+                                                     uniform_read_len, mode, n_slots, (uint64_t*)d_ko.p, out_hits ? (mazu_hit_t*)d_hits.p : nullptr,
+                                                     (uint64_t*)d_offs.p, (mazu_occ_t*)d_out.p, cap, &total, (uint64_t*)d_cnt.p, MAZU_MEM_DEVICE, s);
+      if (out_total) *out_total = total;
+      if (rc != MAZU_OK && !(rc == MAZU_ERR_INVALID_ARG && total > cap)) throw Error(rc, g_err);
+      MZ_CUDA(cudaMemcpyAsync(out_offsets, d_offs.p, (n_slots + 1) * 8, cudaMemcpyDeviceToHost, s));
+      if (out_hits && n_slots) MZ_CUDA(cudaMemcpyAsync(out_hits, d_hits.p, n_slots * 16, cudaMemcpyDeviceToHost, s));
+      if (kmer_offsets) {
+        if (uniform_read_len) {
+          const u64 per = uniform_read_len >= k ? uniform_read_len - k + 1 : 0;
+          for (u64 r = 0; r <= n_reads; ++r) kmer_offsets[r] = r * per;
+        } else {
+          MZ_CUDA(cudaMemcpyAsync(kmer_offsets, d_ko.p, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, s));
+        }
+      }
+      if (counts) MZ_CUDA(cudaMemcpyAsync(counts, d_cnt.p, 24, cudaMemcpyDeviceToHost, s));
+      if (total && total <= cap) MZ_CUDA(cudaMemcpyAsync(out_mrps, d_out.p, total * 12, cudaMemcpyDeviceToHost, s));
+      MZ_CUDA(cudaStreamSynchronize(s));
+      if (total > cap) throw Error(MAZU_ERR_INVALID_ARG, "output capacity too small: need " + std::to_string(total) + " records");
+      return;
+    }
+    // ---- device buffers ----
+    cudaStream_t s = (cudaStream_t)stream;
+    u64* d_koffs = kmer_offsets;
+    std::unique_ptr<PoolBuf> tmp_koffs, d_tot;
+    if (!uniform_read_len && n_reads) {
+      if (!d_koffs) {
+        tmp_koffs = std::make_unique<PoolBuf>(idx->pool, (n_reads + 1) * 8, s);
+        d_koffs = (u64*)tmp_koffs->p;
+      }
+      PoolBuf lens(idx->pool, (n_reads + 1) * 8, s);
+      MZ_CUDA(cudaMemsetAsync(lens.p, 0, (n_reads + 1) * 8, s));
+      kmer_counts_kernel<<<(int)std::min<u64>((n_reads + 255) / 256, 4096), 256, 0, s>>>(read_offsets, n_reads, k, (u64*)lens.p);
+      MZ_CUDA(cudaGetLastError());
+      device_exclusive_scan((const u64*)lens.p, d_koffs, n_reads, idx->pool, s);
+    }
+    if (out_total) d_tot = std::make_unique<PoolBuf>(idx->pool, 8, s);
+    if (mode == MAZU_MODE_STREAMING && !idx->kmers_unique) {
+      // the cursor walk is sequential per read and its answers can differ from the lookups' (duplicated k-mers): unfused chain
+      std::unique_ptr<PoolBuf> tmp_hits;
+      Hit* d_hits = (Hit*)out_hits;
+      if (!d_hits) {
+        tmp_hits = std::make_unique<PoolBuf>(idx->pool, n_slots * 16 + 16, s);
+        d_hits = (Hit*)tmp_hits->p;
+      }
+      launch_query_reads(idx, bases, read_offsets, n_reads, uniform_read_len, mode, d_koffs, d_hits, 0, counts, s);
+      occ_driver(idx, nullptr, (const mazu_hit_t*)d_hits, n_slots, out_offsets, out_mrps, cap, out_total, MAZU_MEM_DEVICE, s);
+      return;
+    }
+    launch_get_ref_pos_reads(idx, bases, read_offsets, n_reads, uniform_read_len, d_koffs, (Hit*)out_hits, counts, n_slots, out_offsets,
+                             (OccRec*)out_mrps, cap, d_tot ? (u64*)d_tot->p : nullptr, s);
+    if (out_total) {
+      MZ_CUDA(cudaMemcpyAsync(out_total, d_tot->p, 8, cudaMemcpyDeviceToHost, s));
+      MZ_CUDA(cudaStreamSynchronize(s));
+      if (*out_total > cap) throw Error(MAZU_ERR_INVALID_ARG, "output capacity too small: need " + std::to_string(*out_total) + " records");
+    }
+  });
 }
 
 mazu_status_t mazu_b200_decode_occs(const mazu_index_t* idx, const uint32_t* unitig_ids, uint64_t n, uint64_t* out_offsets,

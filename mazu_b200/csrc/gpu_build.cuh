@@ -190,9 +190,58 @@ __global__ void mphf_filter_kernel(const u64* __restrict__ keys, u64 n, u32 leve
   }
 }
 
+// stage 4': the fingerprinted cascade (index_layout.hpp, MPHF_FAMILY_CASCADE; host twin: MphfHost::build_cascade).
+// seen / coll are plain bitmaps of `size` bits; keys carry the index of their group so the slot can be recorded per group.
+__global__ void cascade_mark_kernel(const u64* __restrict__ keys, u64 n, u32 level, u64 size, u32* __restrict__ seen, u32* __restrict__ coll) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u64 sl = cascade_slot(fmix64(keys[i]), level, size);
+    const u32 m = 1u << (sl & 31);
+    const u32 old = atomicOr(seen + (sl >> 5), m);
+    if (old & m) atomicOr(coll + (sl >> 5), m);
+  }
+}
+// keys alone in their slot are placed (state = fingerprint, slot recorded); colliders mark the slot and move on to the next level
+__global__ void cascade_place_kernel(const u64* __restrict__ keys, const u64* __restrict__ idx, u64 n, u32 level, u64 size, u64 off,
+                                     const u32* __restrict__ coll, u8* __restrict__ states, u64* __restrict__ slots, u64* __restrict__ next_keys,
+                                     u64* __restrict__ next_idx, unsigned long long* __restrict__ next_n) {
+  for (u64 i0 = (u64)blockIdx.x * blockDim.x; i0 < n; i0 += (u64)gridDim.x * blockDim.x) {
+    const u64 i = i0 + threadIdx.x;
+    bool keep = false;
+    u64 key = 0, id = 0;
+    if (i < n) {
+      key = keys[i];
+      id = idx ? idx[i] : i;
+      const u64 hk = fmix64(key), sl = cascade_slot(hk, level, size);
+      keep = (coll[sl >> 5] >> (sl & 31)) & 1u;
+      states[sl] = keep ? (u8)CASCADE_COLLIDED : (u8)cascade_fp(hk);  // every collider of a slot writes the same byte
+      if (!keep) slots[id] = off + sl;
+    }
+    const u32 m = __ballot_sync(0xffffffffu, keep);
+    u64 basei = 0;
+    if ((threadIdx.x & 31) == 0 && m) basei = atomicAdd(next_n, (unsigned long long)__popc(m));
+    basei = __shfl_sync(0xffffffffu, basei, 0);
+    if (keep) {
+      const u64 o = basei + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+      next_keys[o] = key;
+      next_idx[o] = id;
+    }
+  }
+}
+__global__ void cascade_sizes_kernel(const u64* __restrict__ slots, const u64* __restrict__ ranges, u64 M, u64 R, u64* __restrict__ sizes_by_slot,
+                                     unsigned long long* __restrict__ bad) {
+  for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < M; g += (u64)gridDim.x * blockDim.x) {
+    const u64 h = slots[g];
+    if (h >= R) {
+      atomicAdd(bad, 1ULL);
+      continue;
+    }
+    sizes_by_slot[h] = ranges[g + 1] - ranges[g];
+  }
+}
+
 // stage 5
 __global__ void group_hash_kernel(const __grid_constant__ RankedLevels m, const u64* __restrict__ set, const u64* __restrict__ ranges, u64 M,
-                                  u64* __restrict__ hashes, u64* __restrict__ sizes_by_h, u8* __restrict__ fps, unsigned long long* __restrict__ bad) {
+                                  u64* __restrict__ hashes, u64* __restrict__ sizes_by_h, unsigned long long* __restrict__ bad) {
   for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < M; g += (u64)gridDim.x * blockDim.x) {
     u64 h;
     if (!mphf_lookup_t<MPHF_FAMILY_NATIVE>(m, set[g], h) || h >= M) {
@@ -201,7 +250,6 @@ __global__ void group_hash_kernel(const __grid_constant__ RankedLevels m, const 
     }
     hashes[g] = h;
     if (sizes_by_h) sizes_by_h[h] = ranges[g + 1] - ranges[g];
-    if (fps) fps[h] = (u8)mphf_fingerprint(set[g]);
   }
 }
 // stage 6: tuple j of group g goes to prefix[hash(g)] + (j - ranges[g])

@@ -136,6 +136,96 @@ DevMphf build_mphf_gpu(CubTemp& tmp, const u64* d_keys, u64 n, double gamma, int
   return m;
 }
 
+struct DevCascade {
+  RankedLevels view{};
+  std::vector<DevBufP> bufs;  // fallback keys / values
+  size_t bytes = 0;
+  DevBufP states;  // one byte per slot (R of them)
+  DevBufP slots;   // slot of every input key
+  u64 R = 0, n_fb = 0;
+};
+// MphfHost::build_cascade on the device: same level sizes, same slots, hence the same states
+DevCascade build_cascade_gpu(const u64* d_keys, u64 n, int dev, int sm) {
+  DevCascade c;
+  c.view.family = MPHF_FAMILY_CASCADE;
+  c.slots = std::make_shared<DevBuf>(std::max<u64>(n, 1) * 8, dev);
+  MZ_CUDA(cudaMemset(c.slots->p, 0xFF, std::max<u64>(n, 1) * 8));
+  auto cur_k = std::make_shared<DevBuf>(std::max<u64>(n, 1) * 8, dev), nxt_k = std::make_shared<DevBuf>(std::max<u64>(n, 1) * 8, dev);
+  auto cur_i = std::make_shared<DevBuf>(std::max<u64>(n, 1) * 8, dev), nxt_i = std::make_shared<DevBuf>(std::max<u64>(n, 1) * 8, dev);
+  if (n) MZ_CUDA(cudaMemcpy(cur_k->p, d_keys, n * 8, cudaMemcpyDeviceToDevice));
+  DevBuf counter(8, dev);
+  std::vector<DevBufP> level_states;
+  std::vector<u64> level_size;
+  u64 n_cur = n, off = 0;
+  for (u32 lvl = 0; lvl < MPHF_MAX_LEVELS && n_cur > 0; ++lvl) {
+    const u64 size = cascade_level_size(n_cur, lvl), nw = (size + 31) / 32;
+    DevBuf seen(nw * 4, dev), coll(nw * 4, dev);
+    auto st = std::make_shared<DevBuf>(size, dev);
+    MZ_CUDA(cudaMemset(seen.p, 0, nw * 4));
+    MZ_CUDA(cudaMemset(coll.p, 0, nw * 4));
+    MZ_CUDA(cudaMemset(st->p, 0, size));
+    MZ_CUDA(cudaMemset(counter.p, 0, 8));
+    cascade_mark_kernel<<<grid_1d(n_cur, sm), 256>>>((const u64*)cur_k->p, n_cur, lvl, size, (u32*)seen.p, (u32*)coll.p);
+    cascade_place_kernel<<<grid_1d(n_cur, sm), 256>>>((const u64*)cur_k->p, lvl == 0 ? nullptr : (const u64*)cur_i->p, n_cur, lvl, size, off,
+                                                       (const u32*)coll.p, (u8*)st->p, (u64*)c.slots->p, (u64*)nxt_k->p, (u64*)nxt_i->p,
+                                                       (unsigned long long*)counter.p);
+    MZ_CUDA(cudaGetLastError());
+    const u64 n_next = d2h_value((const u64*)counter.p);
+    c.view.size[lvl] = size;
+    c.view.block_off[lvl] = off;
+    c.view.rank_base[lvl] = 0;
+    c.view.n_levels = lvl + 1;
+    level_states.push_back(st);
+    level_size.push_back(size);
+    off += size;
+    std::swap(cur_k, nxt_k);
+    std::swap(cur_i, nxt_i);
+    n_cur = n_next;
+  }
+  // leftovers -> sorted fallback, slots behind the last level
+  std::vector<u64> lk(n_cur), li(n_cur);
+  if (n_cur) {
+    MZ_CUDA(cudaMemcpy(lk.data(), cur_k->p, n_cur * 8, cudaMemcpyDeviceToHost));
+    MZ_CUDA(cudaMemcpy(li.data(), cur_i->p, n_cur * 8, cudaMemcpyDeviceToHost));
+  }
+  std::vector<std::pair<u64, u64>> left(n_cur);
+  for (u64 i = 0; i < n_cur; ++i) left[i] = {lk[i], li[i]};
+  std::sort(left.begin(), left.end());
+  std::vector<u64> fbk, fbv;
+  std::vector<u8> fb_states;
+  for (size_t i = 0; i < left.size(); ++i) {
+    if (i == 0 || left[i].first != left[i - 1].first) {
+      fbk.push_back(left[i].first);
+      fbv.push_back(off + fbk.size() - 1);
+      fb_states.push_back((u8)cascade_fp(fmix64(left[i].first)));
+    }
+    const u64 slot = off + fbk.size() - 1;
+    MZ_CUDA(cudaMemcpy((u64*)c.slots->p + left[i].second, &slot, 8, cudaMemcpyHostToDevice));
+  }
+  c.n_fb = fbk.size();
+  c.R = off + c.n_fb;
+  c.view.n_keys = c.R;
+  c.view.n_fb = (u32)c.n_fb;
+  if (fbk.empty()) {
+    fbk.push_back(0);
+    fbv.push_back(0);
+  }
+  auto fk = upload(fbk, dev), fv = upload(fbv, dev);
+  c.view.fb_keys = (const u64*)fk->p;
+  c.view.fb_vals = (const u64*)fv->p;
+  c.view.blocks = nullptr;
+  c.bufs = {fk, fv};
+  c.bytes = fk->bytes + fv->bytes;
+  c.states = std::make_shared<DevBuf>(std::max<u64>(c.R, 1), dev);
+  u64 o = 0;
+  for (size_t l = 0; l < level_states.size(); ++l) {
+    MZ_CUDA(cudaMemcpy((char*)c.states->p + o, level_states[l]->p, level_size[l], cudaMemcpyDeviceToDevice));
+    o += level_size[l];
+  }
+  if (!fb_states.empty()) MZ_CUDA(cudaMemcpy((char*)c.states->p + o, fb_states.data(), fb_states.size(), cudaMemcpyHostToDevice));
+  return c;
+}
+
 // bit-pack a device array of u64 values; returns the buffer and the width chosen like PackedVec::packed
 DevBufP pack_gpu(CubTemp& tmp, const u64* d_vals, u64 n, int dev, int sm, u32& width_out, u64& logical_bytes, u32 fixed_width = 0) {
   u32 width = fixed_width;
@@ -259,18 +349,20 @@ void build_sshash_gpu(mazu_index& ix, u32 w, u64 skew_param, u64 seed, double ga
   DevBufP mm_set, ranges, gid;
   const u64 M = group_sorted_gpu(tmp, (const u64*)words_s->p, nullptr, n, dev, sm, mm_set, ranges, nullptr, gid);
   words_s.reset();
-  // 4. MPHF over the minimizer set
-  DevMphf mphf = build_mphf_gpu(tmp, (const u64*)mm_set->p, M, gamma, dev, sm);
-  for (auto& b : mphf.bufs) keep(b);
-  // 5. bucket sizes in MPHF order, fingerprints, prefix sum
-  DevBuf hashes(M * 8, dev), sizes_by_h((M + 1) * 8, dev), prefix((M + 1) * 8, dev), fps(M + 1, dev), bad(8, dev);
-  MZ_CUDA(cudaMemset(sizes_by_h.p, 0, (M + 1) * 8));
+  // 4. perfect hash over the minimizer set: the fingerprinted cascade; its value is the minimizer's slot
+  DevCascade casc = build_cascade_gpu((const u64*)mm_set->p, M, dev, sm);
+  for (auto& b : casc.bufs) keep(b);
+  const u64 R = casc.R;
+  // 5. bucket sizes in slot order (one, possibly empty, bucket per slot), prefix sum
+  DevBuf sizes_by_h((R + 1) * 8, dev), prefix((R + 1) * 8, dev), bad(8, dev);
+  MZ_CUDA(cudaMemset(sizes_by_h.p, 0, (R + 1) * 8));
   MZ_CUDA(cudaMemset(bad.p, 0, 8));
-  group_hash_kernel<<<grid_1d(M, sm), 256>>>(mphf.view, (const u64*)mm_set->p, (const u64*)ranges->p, M, (u64*)hashes.p, (u64*)sizes_by_h.p,
-                                             (u8*)fps.p, (unsigned long long*)bad.p);
+  cascade_sizes_kernel<<<grid_1d(M, sm), 256>>>((const u64*)casc.slots->p, (const u64*)ranges->p, M, R, (u64*)sizes_by_h.p, (unsigned long long*)bad.p);
   MZ_CUDA(cudaGetLastError());
-  if (d2h_value((const u64*)bad.p) != 0) throw Error(MAZU_ERR_OTHER, "internal: GPU-built MPHF is not a bijection on its keys");
-  exclusive_scan_u64(tmp, (const u64*)sizes_by_h.p, (u64*)prefix.p, M + 1);
+  if (d2h_value((const u64*)bad.p) != 0) throw Error(MAZU_ERR_OTHER, "internal: a minimizer was not placed by the GPU-built cascade");
+  exclusive_scan_u64(tmp, (const u64*)sizes_by_h.p, (u64*)prefix.p, R + 1);
+  const DevBuf& hashes = *casc.slots;
+  const DevBuf& fps = *casc.states;
   // 6. scatter positions into bucket order
   DevBuf pos_out(n * 8, dev);
   scatter_positions_kernel<<<grid_1d(n, sm), 256>>>((const u64*)poss_s->p, (const u64*)gid->p, (const u64*)ranges->p, (const u64*)hashes.p,
@@ -281,8 +373,8 @@ void build_sshash_gpu(mazu_index& ix, u32 w, u64 skew_param, u64 seed, double ga
   u64 pos_bytes = 0;
   DevBufP pos_packed = pack_gpu(tmp, (const u64*)pos_out.p, n, dev, sm, pos_width, pos_bytes);
   keep(pos_packed);
-  // 8. blocked Elias-Fano of the prefix sums (+ fingerprints)
-  const u64 nE = M + 1, u = d2h_value((const u64*)prefix.p + M);
+  // 8. blocked Elias-Fano of the prefix sums (+ the slot states / fingerprints)
+  const u64 nE = R + 1, u = d2h_value((const u64*)prefix.p + R);
   u64 l = msb(u / nE);
   if (l == 0) l = 1;
   u32 log_s = 5;
@@ -291,7 +383,7 @@ void build_sshash_gpu(mazu_index& ix, u32 w, u64 skew_param, u64 seed, double ga
   const u64 S = 1ULL << log_s, nbE = (nE + S - 1) / S;
   DevBuf exc_flags((nbE + 1) * 8, dev), exc_index((nbE + 1) * 8, dev);
   MZ_CUDA(cudaMemset(exc_flags.p, 0, (nbE + 1) * 8));
-  ef_blocks_kernel<false><<<grid_1d(nbE, sm), 256>>>((const u64*)prefix.p, nE, (u32)l, log_s, 8, all_exc, (const u8*)fps.p, M, (u64*)exc_flags.p, nullptr,
+  ef_blocks_kernel<false><<<grid_1d(nbE, sm), 256>>>((const u64*)prefix.p, nE, (u32)l, log_s, 8, all_exc, (const u8*)fps.p, R, (u64*)exc_flags.p, nullptr,
                                                       nullptr, nullptr);
   MZ_CUDA(cudaGetLastError());
   exclusive_scan_u64(tmp, (const u64*)exc_flags.p, (u64*)exc_index.p, nbE + 1);
@@ -299,7 +391,7 @@ void build_sshash_gpu(mazu_index& ix, u32 w, u64 skew_param, u64 seed, double ga
   DevBufP ef_blocks = std::make_shared<DevBuf>((nbE * 8 + 8) * 8, dev), ef_exc = std::make_shared<DevBuf>(std::max<u64>(1, n_exc * (S + 1)) * 8, dev);
   MZ_CUDA(cudaMemset(ef_blocks->p, 0, (nbE * 8 + 8) * 8));
   MZ_CUDA(cudaMemset(ef_exc->p, 0, std::max<u64>(1, n_exc * (S + 1)) * 8));
-  ef_blocks_kernel<true><<<grid_1d(nbE, sm), 256>>>((const u64*)prefix.p, nE, (u32)l, log_s, 8, all_exc, (const u8*)fps.p, M, nullptr,
+  ef_blocks_kernel<true><<<grid_1d(nbE, sm), 256>>>((const u64*)prefix.p, nE, (u32)l, log_s, 8, all_exc, (const u8*)fps.p, R, nullptr,
                                                      (const u64*)exc_index.p, (u64*)ef_blocks->p, (u64*)ef_exc->p);
   MZ_CUDA(cudaGetLastError());
   keep(ef_blocks);
@@ -320,18 +412,18 @@ void build_sshash_gpu(mazu_index& ix, u32 w, u64 skew_param, u64 seed, double ga
   H->sizes.n_exception_blocks = n_exc;
   IndexView& v = ix.view;
   v.k2u_kind = MAZU_K2U_SSHASH;
-  v.mphf = mphf.view;
+  v.mphf = casc.view;
   v.pos = PackedVecView{(const u64*)pos_packed->p, n, pos_width, 0};
   v.sizes = BlockedEFView{(const u64*)ef_blocks->p, (const u64*)ef_exc->p, nE, (u32)l, log_s, 8, 0};
   v.w = w;
   v.seed = seed;
   v.skew_param = skew_param;
   v.has_skew = 0;
-  ix.tables[0] = {v.mphf.blocks, mphf.block_bytes};
+  ix.tables[0] = {nullptr, 0};  // the cascade has no table of its own: its states ride in the bucket-bound blocks
   ix.tables[1] = {v.sizes.blocks, nbE * 8 * 8};
   ix.tables[2] = {v.sizes.exceptions, n_exc * (S + 1) * 8};
   ix.tables[3] = {v.pos.words, pos_bytes};
-  ix.tables[6] = {v.mphf.fb_keys, mphf.n_fb * 8};
+  ix.tables[6] = {v.mphf.fb_keys, casc.n_fb * 8};
   // 7. skew index
   if (skew_param != MAZU_SKEW_NONE) {
     H->has_skew = true;
@@ -362,7 +454,7 @@ void build_sshash_gpu(mazu_index& ix, u32 w, u64 skew_param, u64 seed, double ga
       smphf = build_mphf_gpu(tmp, (const u64*)km_set->p, Ms, gamma, dev, sm);
       DevBuf hashes2(Ms * 8, dev), svals(Ms * 8, dev);
       MZ_CUDA(cudaMemset(bad.p, 0, 8));
-      group_hash_kernel<<<grid_1d(Ms, sm), 256>>>(smphf.view, (const u64*)km_set->p, (const u64*)ranges2->p, Ms, (u64*)hashes2.p, nullptr, nullptr,
+      group_hash_kernel<<<grid_1d(Ms, sm), 256>>>(smphf.view, (const u64*)km_set->p, (const u64*)ranges2->p, Ms, (u64*)hashes2.p, nullptr,
                                                   (unsigned long long*)bad.p);
       MZ_CUDA(cudaGetLastError());
       if (d2h_value((const u64*)bad.p) != 0) throw Error(MAZU_ERR_OTHER, "internal: GPU-built skew MPHF is not a bijection on its keys");

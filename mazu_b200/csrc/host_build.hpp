@@ -364,6 +364,77 @@ struct MphfHost {
     return m;
   }
   u64 n_fb_real() const { return n_fb_real_; }
+  // Fingerprinted cascade over distinct u64 keys (index_layout.hpp, MPHF_FAMILY_CASCADE): the perfect hash of the SSHash
+  // minimizers (stands where the reference uses boomphf::Mphf::new_parallel(1.7, ..), src/kphf/sshash.rs:177).
+  // states[g] = the byte of slot g (EMPTY / COLLIDED / fingerprint), slots[i] = the slot of keys[i].
+  static MphfHost build_cascade(const std::vector<u64>& keys_in, unsigned threads, std::vector<u8>& states, std::vector<u64>& slots) {
+    MphfHost m;
+    m.meta.family = MPHF_FAMILY_CASCADE;
+    const u64 n_in = keys_in.size();
+    slots.assign(n_in, ~0ULL);
+    states.clear();
+    std::vector<u64> idx(n_in), next_idx;
+    for (u64 i = 0; i < n_in; ++i) idx[i] = i;
+    u64 off = 0;
+    for (u32 lvl = 0; lvl < MPHF_MAX_LEVELS && !idx.empty(); ++lvl) {
+      const u64 n = idx.size(), size = cascade_level_size(n, lvl);
+      std::vector<u64> seen((size + 63) / 64, 0), coll((size + 63) / 64, 0);
+      parallel_ranges(n, threads, [&](unsigned, u64 lo, u64 hi) {
+        for (u64 i = lo; i < hi; ++i) {
+          const u64 sl = cascade_slot(fmix64(keys_in[idx[i]]), lvl, size), mask = 1ULL << (sl & 63);
+          const u64 old = __atomic_fetch_or(&seen[sl >> 6], mask, __ATOMIC_RELAXED);
+          if (old & mask) __atomic_fetch_or(&coll[sl >> 6], mask, __ATOMIC_RELAXED);
+        }
+      });
+      states.resize(off + size, (u8)CASCADE_EMPTY);
+      std::vector<std::vector<u64>> nexts(threads ? threads : 1);
+      parallel_ranges(n, threads, [&](unsigned t, u64 lo, u64 hi) {
+        for (u64 i = lo; i < hi; ++i) {
+          const u64 hk = fmix64(keys_in[idx[i]]), sl = cascade_slot(hk, lvl, size);
+          if ((coll[sl >> 6] >> (sl & 63)) & 1) {
+            states[off + sl] = (u8)CASCADE_COLLIDED;  // every collider writes the same byte
+            nexts[t].push_back(idx[i]);
+          } else {
+            states[off + sl] = (u8)cascade_fp(hk);
+            slots[idx[i]] = off + sl;
+          }
+        }
+      });
+      m.meta.size[lvl] = size;
+      m.meta.block_off[lvl] = off;
+      m.meta.rank_base[lvl] = 0;
+      m.meta.n_levels = lvl + 1;
+      off += size;
+      next_idx.clear();
+      for (auto& v : nexts) next_idx.insert(next_idx.end(), v.begin(), v.end());
+      idx.swap(next_idx);
+    }
+    // leftovers (duplicated keys, or keys that collided on every level): sorted fallback, slots behind the last level
+    std::vector<std::pair<u64, u64>> left;
+    for (u64 i : idx) left.push_back({keys_in[i], i});
+    std::sort(left.begin(), left.end());
+    u64 n_fb = 0;
+    for (size_t i = 0; i < left.size(); ++i) {
+      if (i == 0 || left[i].first != left[i - 1].first) {
+        m.fb_keys.push_back(left[i].first);
+        m.fb_vals.push_back(off + n_fb);
+        states.push_back((u8)cascade_fp(fmix64(left[i].first)));
+        ++n_fb;
+      }
+      slots[left[i].second] = off + n_fb - 1;
+    }
+    m.meta.n_keys = off + n_fb;  // the RANGE of the hash (one bucket per slot), not the number of keys
+    m.n_fb_real_ = n_fb;
+    if (m.fb_keys.empty()) {
+      m.fb_keys.push_back(0);
+      m.fb_vals.push_back(0);
+    }
+    return m;
+  }
+  bool cascade_lookup_host(const BlockedEFView& ef, u64 key, u64& out) const {
+    RankedLevels v = view();
+    return cascade_lookup(v, ef, key, out);
+  }
 
  private:
   std::vector<u64> level_ones_;
@@ -545,19 +616,18 @@ inline std::shared_ptr<K2UHost> build_sshash(std::shared_ptr<const UnitigSetHost
   const u64 M = mm_set.size();
   H->n_minimizers = M;
   H->n_minimizer_occs = minimizers.size();
-  // 3. MPHF over the minimizer set (sshash.rs:177)
-  H->mphf = MphfHost::build_native(mm_set, gamma, T);
-  // 4. bucket sizes in MPHF order -> prefix sum (sshash.rs:181-189)
-  std::vector<u64> hashes(M);
-  parallel_ranges(M, T, [&](unsigned, u64 lo, u64 hi) {
-    for (u64 i = lo; i < hi; ++i) hashes[i] = H->mphf.hash(mm_set[i]);
-  });
-  std::vector<u64> prefix(M + 1, 0);
+  // 3. perfect hash over the minimizer set (sshash.rs:177): the fingerprinted cascade; its value is the minimizer's slot
+  std::vector<u8> states;
+  std::vector<u64> hashes;
+  H->mphf = MphfHost::build_cascade(mm_set, T, states, hashes);
+  const u64 R = H->mphf.meta.n_keys;  // slots: one (possibly empty) bucket each
+  // 4. bucket sizes in slot order -> prefix sum (sshash.rs:181-189)
+  std::vector<u64> prefix(R + 1, 0);
   for (u64 i = 0; i < M; ++i) {
-    if (hashes[i] >= M) throw Error(MAZU_ERR_OTHER, "internal: MPHF value out of range");
+    if (hashes[i] >= R) throw Error(MAZU_ERR_OTHER, "internal: perfect-hash value out of range");
     prefix[hashes[i] + 1] = ranges[i + 1] - ranges[i];
   }
-  for (u64 i = 0; i < M; ++i) prefix[i + 1] += prefix[i];
+  for (u64 i = 0; i < R; ++i) prefix[i + 1] += prefix[i];
   // 5. scatter positions (sshash.rs:196-219)
   std::vector<u64> pos(minimizers.size());
   parallel_ranges(M, T, [&](unsigned, u64 lo, u64 hi) {
@@ -598,12 +668,8 @@ inline std::shared_ptr<K2UHost> build_sshash(std::shared_ptr<const UnitigSetHost
     sp.resize(km_set.size());
     H->skew_pos = PackedVec::packed(sp);
   }
-  // finish (sshash.rs:310-329): Elias-Fano encode the prefix sums, bit-pack the positions
-  std::vector<u8> fps(M, 0);
-  parallel_ranges(M, T, [&](unsigned, u64 lo, u64 hi) {
-    for (u64 i = lo; i < hi; ++i) fps[hashes[i]] = (u8)mphf_fingerprint(mm_set[i]);
-  });
-  H->sizes = BlockedEF::build(prefix, &fps);
+  // finish (sshash.rs:310-329): Elias-Fano encode the prefix sums (the slot states ride in the blocks), bit-pack the positions
+  H->sizes = BlockedEF::build(prefix, &states);
   H->pos = PackedVec::packed(pos);
   return H;
 }

@@ -23,7 +23,7 @@ namespace mazu {
 
 static const u32 MPHF_MAX_LEVELS = 32;
 static const u32 MPHF_BLOCK_BITS = 224;  // payload bits per 32-byte block (7 x u32) + 1 x u32 rank
-enum : u32 { MPHF_FAMILY_BOOPHF = 0, MPHF_FAMILY_NATIVE = 1 };
+enum : u32 { MPHF_FAMILY_BOOPHF = 0, MPHF_FAMILY_NATIVE = 1, MPHF_FAMILY_CASCADE = 2 };
 
 // ---------------------------------------------------------------------------------------------
 // Ranked bitset blocks: the storage of both MPHF flavours.
@@ -37,8 +37,8 @@ struct RankedLevels {
   u32 family;
   u32 n_levels;
   u64 n_keys;
-  u64 size[MPHF_MAX_LEVELS];       // BOOPHF: n_bits of the level (fastrange modulus); NATIVE: n_blocks
-  u64 block_off[MPHF_MAX_LEVELS];  // first block of the level
+  u64 size[MPHF_MAX_LEVELS];       // BOOPHF: n_bits of the level (fastrange modulus); NATIVE: n_blocks; CASCADE: slots of the level
+  u64 block_off[MPHF_MAX_LEVELS];  // first block of the level (CASCADE: first global slot of the level)
   u64 rank_base[MPHF_MAX_LEVELS];  // keys placed in earlier levels
   const u64* fb_keys;              // fallback ("final hash"): sorted keys ...
   const u64* fb_vals;              // ... and their hash values
@@ -218,16 +218,67 @@ struct BlockedEFView {
   u32 _pad;
 };
 
-// Fingerprint of an MPHF key, stored next to the bucket bounds of slot h (same 64-byte block, same 128-byte
-// DRAM line).  An MPHF maps most NON-member keys to some slot (boomphf's try_hash does the same,
-// src/kphf/sshash.rs:478); the reference then pays bucket bounds + positions + window compare to find out.
-// A fingerprint mismatch proves "not a member" after one load; a match (1/256 of non-members) proceeds as the
-// reference does, so answers are unchanged.
-MZ_HD u32 mphf_fingerprint(u64 key) { return (u32)(fmix64(key ^ 0xD6E8FEB86659FD93ULL) >> 56); }
+// the state / fingerprint byte of element i (words 4..7 of its block; see the fingerprinted cascade below)
 MZ_HD u32 blocked_ef_fp(const BlockedEFView& ef, u64 i) {
   u64 blk = i >> ef.log_s;
   u32 j = (u32)(i & ((1ULL << ef.log_s) - 1ULL));
   return (u32)((MZ_LDG(ef.blocks + blk * ef.wpb + 4 + (j >> 3)) >> (8 * (j & 7))) & 0xFFULL);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fingerprinted cascade (MPHF_FAMILY_CASCADE): the perfect hash of the SSHash minimizers.
+// A BBHash-style cascade whose VALUE is the slot itself (level offset + slot in level) instead of the slot's rank, so it
+// needs no bit tables and no rank: the only per-slot state is one byte, and that byte is the fingerprint byte the bucket
+// bounds block of the slot already carries (words 4..7 of the 64-byte blocked-Elias-Fano block):
+//     0 EMPTY      no key of the level maps here        -> a queried key is provably not a member
+//     1 COLLIDED   two or more keys map here            -> they were all sent to the next level: go on
+//     2..255       exactly one key: its fingerprint     -> equal: found, the bounds are in the block just read; else not a member
+// A member pays 1.65 probes on average (each the 128-byte line that also holds its bucket bounds), a non-member 1.1 --
+// the reference's chain (MPHF levels, then Elias-Fano bounds, src/kphf/sshash.rs:478-483) pays both and learns that a
+// minimizer is foreign only at the k-mer compare.  The hash is not minimal: the bounds array has one (possibly empty)
+// bucket per slot, ~3.7 slots per key at 2 bytes each.  Leftover keys (after MPHF_MAX_LEVELS levels) sit in the sorted
+// fallback list with slots behind the last level.
+// ---------------------------------------------------------------------------------------------
+static const u32 CASCADE_EMPTY = 0, CASCADE_COLLIDED = 1;
+MZ_HD u32 cascade_fp(u64 hk) { return 2u + mulhi32((u32)(hk ^ (hk >> 29)) * 0x9E3779B1u, 254u); }
+MZ_HD u64 cascade_slot(u64 hk, u32 level, u64 size) {
+  u64 x = (hk ^ ((u64)(level + 1) * 0x9E3779B97F4A7C15ULL)) * 0xD6E8FEB86659FD93ULL;
+  x ^= x >> 32;
+  return mulhi64(x * 0xFF51AFD7ED558CCDULL, size);
+}
+// slots of level `l` for `n` keys: 2 slots per key on the first two levels (61 % of the keys of a level are alone in their
+// slot), then 4 and 8: the few keys left are placed quickly and the cascade stays shallow
+MZ_HD u64 cascade_level_size(u64 n, u32 level) {
+  const u64 g = level < 2 ? 2 : (level == 2 ? 4 : 8);
+  const u64 s = g * n;
+  return s < 32 ? 32 : s;
+}
+MZ_HD bool cascade_lookup(const RankedLevels& m, const BlockedEFView& ef, u64 key, u64& out) {
+  const u64 hk = fmix64(key);
+  const u32 fp = cascade_fp(hk);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (u32 l = 0; l < m.n_levels; ++l) {
+    const u64 g = m.block_off[l] + cascade_slot(hk, l, m.size[l]);
+    const u32 st = blocked_ef_fp(ef, g);
+    if (st == fp) {
+      out = g;
+      return true;
+    }
+    if (st != CASCADE_COLLIDED) return false;
+  }
+  u32 lo = 0, hi = m.n_fb;
+  while (lo < hi) {
+    u32 mid = (lo + hi) >> 1;
+    u64 kk = MZ_LDG(m.fb_keys + mid);
+    if (kk == key) {
+      out = MZ_LDG(m.fb_vals + mid);
+      return true;
+    }
+    if (kk < key) lo = mid + 1; else hi = mid;
+  }
+  return false;
 }
 
 // position of the j-th (0-based) set bit of the 128-bit value hi:lo; caller guarantees it exists

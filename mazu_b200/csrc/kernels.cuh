@@ -114,9 +114,8 @@ __device__ __forceinline__ bool pfhash_k2u(const IndexView& ix, u64 fw, u64 rc, 
 // SSHash::k2u (src/kphf/sshash.rs:471-555) given the canonical minimizer (word, offset in fw-mer coordinates)
 __device__ __forceinline__ bool sshash_k2u(const IndexView& ix, u64 fw, u64 rc, u64 mm_word, u32 offset, Hit& out) {
   u64 h;
-  if (!mphf_lookup(ix.mphf, mm_word, h)) return false;
+  if (!cascade_lookup(ix.mphf, ix.sizes, mm_word, h)) return false;  // fingerprinted cascade: slot + membership filter in one (index_layout.hpp)
   if (h + 1 >= ix.sizes.n) return false;
-  if (blocked_ef_fp(ix.sizes, h) != mphf_fingerprint(mm_word)) return false;  // provably not a member (index_layout.hpp)
   u64 pos_start, pos_end;
   blocked_ef_get2(ix.sizes, h, pos_start, pos_end);  // occs_prefix_sum.get(h), get(h+1)
   if (pos_end - pos_start > ix.skew_param) {         // k2u_skew_index (sshash.rs:415-433)
@@ -181,7 +180,8 @@ __global__ void probe_key_kernel(const __grid_constant__ IndexView ix, const u64
     if (ix.k2u_kind == MAZU_K2U_SSHASH) key = canonical_minimizer_naive(fw, rc, k, ix.w, ix.seed).word;
     u64 blk = 0;
     u32 bit = 0;
-    if (ix.mphf.family == MPHF_FAMILY_NATIVE) native_slot(key, 0, ix.mphf.size[0], blk, bit);
+    if (ix.mphf.family == MPHF_FAMILY_CASCADE) blk = cascade_slot(fmix64(key), 0, ix.mphf.size[0]) >> 5;
+    else if (ix.mphf.family == MPHF_FAMILY_NATIVE) native_slot(key, 0, ix.mphf.size[0], blk, bit);
     else blk = mulhi64(boophf_hash64(key, BOOPHF_SEED0), ix.mphf.size[0]) / MPHF_BLOCK_BITS;
     out_block[i] = (u32)blk;
   }
@@ -372,7 +372,7 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
       u64 mmw = mm_word_of(fw, rc, S.off[p], k, w);
       u64 h, a = 0, b = 0;
       u32 n = 0;
-      if (mphf_lookup_t<FAMILY>(ix.mphf, mmw, h) && h + 1 < ix.sizes.n && blocked_ef_fp(ix.sizes, h) == mphf_fingerprint(mmw)) {
+      if (cascade_lookup(ix.mphf, ix.sizes, mmw, h) && h + 1 < ix.sizes.n) {  // the probe that finds the slot has fetched its bounds block
         blocked_ef_get2(ix.sizes, h, a, b);
         u64 cnt = b - a;
         n = cnt > ix.skew_param ? BN_SKEW : (u32)cnt;
@@ -749,11 +749,11 @@ __global__ void __launch_bounds__(QR_WARPS * 32) encode_reads_kernel(const __gri
 
 // per-read k-mer slot counts (input of the exclusive scan that yields kmer_offsets)
 // per-read work items of the random-access kernel: ceil(k-mer slots / QR_SEGMENT), at least one
-__global__ void segment_counts_kernel(const u64* __restrict__ read_offsets, u64 n_reads, u32 k, u64* __restrict__ counts) {
+__global__ void segment_counts_kernel(const u64* __restrict__ read_offsets, u64 n_reads, u32 k, u64 segment, u64* __restrict__ counts) {
   for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (u64)gridDim.x * blockDim.x) {
     u64 len = read_offsets[r + 1] - read_offsets[r];
     u64 nk = len >= k ? len - k + 1 : 0;
-    counts[r] = nk <= QR_SEGMENT ? 1 : (nk + QR_SEGMENT - 1) / QR_SEGMENT;
+    counts[r] = nk <= segment ? 1 : (nk + segment - 1) / segment;
   }
 }
 __global__ void kmer_counts_kernel(const u64* __restrict__ read_offsets, u64 n_reads, u32 k, u64* __restrict__ counts) {
@@ -911,6 +911,201 @@ __device__ __forceinline__ OccRec project_occ(u32 k, const Hit& h, const OccRec&
   u32 o = h.match == IDENTITY_MATCH ? 1u : 0u;
   m.fw = occ.fw ? o : (o ^ 1u);
   return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused GetRefPos::get_ref_pos over reads (src/index.rs:156-216 + the read loop of validate_ckmers): reads -> K2UPos ->
+// occurrence list -> MappedRefPos in ONE kernel.  The unfused chain writes the 16-byte hit records, re-reads them twice
+// (list lengths, fill) and scans per-slot lengths in between; here a warp keeps the hits of its tile (one chunk of <= 128
+// k-mer positions) in its shared-memory stage, scans the list lengths with shuffles, and obtains the tile's position in
+// the output with a single-pass decoupled look-back over one status word per tile (flag << 62 | value): the only global
+// traffic besides the lookups is 8 bytes of offset per slot and the 12-byte records themselves.
+// Tiles are handed out in order by a ticket counter, so a tile only ever waits for tiles that are already running.
+// ---------------------------------------------------------------------------------------------
+struct ProjOut {
+  unsigned long long* status;  // one word per tile, zeroed before the launch
+  unsigned long long* ticket;  // next tile, zeroed before the launch
+  u64* out_offsets;            // n_slots + 1
+  OccRec* out;                 // `cap` records
+  u64 cap;
+  u64 n_slots;
+  u64 n_tiles;
+  u64* out_total;              // optional device word
+};
+static const unsigned long long PJ_AGG = 1ULL << 62, PJ_INCL = 2ULL << 62, PJ_VAL = (1ULL << 62) - 1ULL;
+
+__device__ __forceinline__ u64 tile_exclusive_prefix(unsigned long long* status, u64 tile, u64 aggregate, u32 lane) {
+  if (tile == 0) {
+    if (lane == 0) atomicExch(status, PJ_INCL | aggregate);
+    return 0;
+  }
+  if (lane == 0) atomicExch(status + tile, PJ_AGG | aggregate);
+  u64 excl = 0;
+  long long base = (long long)tile - 1;
+  while (true) {
+    const long long i = base - (long long)lane;
+    unsigned long long v = PJ_INCL;  // before tile 0: an inclusive prefix of 0
+    if (i >= 0) v = *reinterpret_cast<volatile unsigned long long*>(status + i);
+    const u32 flag = (u32)(v >> 62);
+    const u32 incl = __ballot_sync(0xffffffffu, flag == 2u), invalid = __ballot_sync(0xffffffffu, flag == 0u);
+    const u32 first = incl ? (u32)__ffs(incl) - 1u : 32u;                      // nearest predecessor with an inclusive prefix
+    const u32 upto = first >= 31u ? 0xffffffffu : ((2u << first) - 1u);        // lanes whose value is needed
+    if (invalid & upto) continue;                                              // a needed predecessor has not published yet
+    u64 x = ((1u << lane) & upto) ? (u64)(v & PJ_VAL) : 0ULL;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    excl += x;
+    if (first < 32u) break;
+    base -= 32;
+  }
+  if (lane == 0) atomicExch(status + tile, PJ_INCL | (excl + aggregate));
+  return excl;
+}
+
+template <int KIND, u32 FAMILY>
+__global__ void __launch_bounds__(QR_WARPS * 32, 3) get_ref_pos_reads_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
+                                                                            const u64* __restrict__ read_offsets, u64 n_reads, u64 uniform_len,
+                                                                            const u64* __restrict__ kmer_offsets, Hit* __restrict__ out_hits,
+                                                                            unsigned long long* __restrict__ counts,
+                                                                            const u64* __restrict__ seg_offsets, const ProjOut pj) {
+  __shared__ WarpStage s_stage[QR_WARPS];
+  const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  WarpStage& S = s_stage[wib];
+  const u32 k = ix.unitigs.k;
+  constexpr bool SS = KIND == MAZU_K2U_SSHASH;
+  u32 n_valid = 0, n_hit = 0;
+  // tiles: chunk c of read r.  Uniform reads: arithmetic; ragged reads: seg_offsets (segments of QR_CHUNK k-mer positions)
+  const u64 uni_nk = uniform_len >= k ? uniform_len - k + 1 : 0;
+  const u64 uni_cpr = uni_nk <= QR_CHUNK ? 1 : (uni_nk + QR_CHUNK - 1) / QR_CHUNK;
+  while (true) {
+    unsigned long long tile = 0;
+    if (lane == 0) tile = atomicAdd(pj.ticket, 1ULL);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= pj.n_tiles) break;
+    u64 r, c0;
+    if (uniform_len) {
+      r = tile / uni_cpr;
+      c0 = (tile - r * uni_cpr) * QR_CHUNK;
+    } else {
+      u64 lo = 0, hi = n_reads;  // largest r with seg_offsets[r] <= tile
+      while (hi - lo > 1) {
+        u64 mid = (lo + hi) >> 1;
+        if (seg_offsets[mid] <= tile) lo = mid; else hi = mid;
+      }
+      r = lo;
+      c0 = (tile - seg_offsets[r]) * QR_CHUNK;
+    }
+    u64 beg, len, slot0;
+    if (uniform_len) {
+      beg = r * uniform_len;
+      len = uniform_len;
+      slot0 = r * uni_nk;
+    } else {
+      beg = read_offsets[r];
+      len = read_offsets[r + 1] - beg;
+      slot0 = kmer_offsets[r];
+    }
+    const u64 nk = len >= k ? len - k + 1 : 0;
+    const u32 n_c = c0 < nk ? (u32)min((u64)QR_CHUNK, nk - c0) : 0u;
+    __syncwarp();
+    if (n_c) {
+      ChunkInfo ci;
+      stage_encode(bases + beg, len, c0, n_c, k, lane, S, ci);
+      __syncwarp();
+      if (SS) stage_buckets<FAMILY>(ix, ci, lane, S);
+#pragma unroll 1
+      for (u32 p = lane; p < n_c; p += 32) {
+        Hit h = hit_none(SKIPPED);
+        u32 n_occ = 0;
+        if (chunk_valid(ci, p)) {
+          u64 fw = S.fw[p], rc = SS ? S.rc[p] : revcomp(fw, k);
+          bool ok = SS ? verify_sshash<FAMILY>(ix, S, p, fw, rc, h)
+                       : (KIND == MAZU_K2U_SAMPLED_PFHASH ? sampled_pfhash_k2u_t<FAMILY>(ix, fw, rc, h, nullptr) : pfhash_k2u_t<FAMILY>(ix, fw, rc, h));
+          ++n_valid;
+          if (ok) {
+            ++n_hit;
+            u64 s, e;
+            occ_range(ix, h.unitig_id, s, e);  // U2Pos::encoded_unitig_occs
+            n_occ = (u32)(e - s);
+          } else {
+            h = hit_none(NO_MATCH);
+          }
+        }
+        if (out_hits) store_hit(out_hits + slot0 + c0 + p, h);
+        // the hit stays in the warp's stage: slot p of fw / rc is only ever read by the lane that owns p
+        S.fw[p] = (u64)h.unitig_id | ((u64)h.pos << 32);
+        S.rc[p] = (u64)h.unitig_len | ((u64)h.match << 32);
+        S.hf[p] = n_occ;
+      }
+    }
+    __syncwarp();
+    // list lengths -> exclusive offsets inside the tile (slot order: p = 32 t + lane)
+    u32 ex[4], cnt[4], carry = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const u32 p = 32 * t + lane;
+      const u32 v = p < n_c ? S.hf[p] : 0u;
+      u32 inc = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const u32 y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (u32)d) inc += y;
+      }
+      cnt[t] = v;
+      ex[t] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    const u64 E = tile_exclusive_prefix(pj.status, tile, carry, lane);
+    if (tile == pj.n_tiles - 1 && lane == 0) {
+      pj.out_offsets[pj.n_slots] = E + carry;
+      if (pj.out_total) *pj.out_total = E + carry;
+    }
+    // offsets of the tile's slots, then the projected records (project_onto_u_occ, index.rs:194-216)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const u32 p = 32 * t + lane;
+      const bool mine = p < n_c;
+      if (mine) pj.out_offsets[slot0 + c0 + p] = E + ex[t];
+      Hit h = hit_none(NO_MATCH);
+      u64 first = 0;
+      if (mine && cnt[t]) {
+        const u64 a = S.fw[p], b = S.rc[p];
+        h = Hit{(u32)a, (u32)b, (u32)(a >> 32), (u32)(b >> 32)};
+        first = packed_get(ix.contig_offsets, h.unitig_id);
+      }
+      const u64 o0 = E + ex[t];
+      // long lists are written by the whole warp, short ones by their lane
+      u32 big = __ballot_sync(0xffffffffu, mine && cnt[t] >= 32u);
+      if (mine && cnt[t] < 32u)
+        for (u32 j = 0; j < cnt[t]; ++j)
+          if (o0 + j < pj.cap) pj.out[o0 + j] = project_occ(k, h, occ_decode(ix, first + j));
+      while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        Hit hb;
+        hb.unitig_id = __shfl_sync(0xffffffffu, h.unitig_id, src);
+        hb.unitig_len = __shfl_sync(0xffffffffu, h.unitig_len, src);
+        hb.pos = __shfl_sync(0xffffffffu, h.pos, src);
+        hb.match = __shfl_sync(0xffffffffu, h.match, src);
+        const u64 fb = __shfl_sync(0xffffffffu, first, src), ob = __shfl_sync(0xffffffffu, o0, src);
+        const u32 nb = __shfl_sync(0xffffffffu, cnt[t], src);
+        for (u32 j = lane; j < nb; j += 32)
+          if (ob + j < pj.cap) pj.out[ob + j] = project_occ(k, hb, occ_decode(ix, fb + j));
+      }
+    }
+  }
+  if (counts) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      n_valid += __shfl_xor_sync(0xffffffffu, n_valid, d);
+      n_hit += __shfl_xor_sync(0xffffffffu, n_hit, d);
+    }
+    if (lane == 0 && n_valid) {
+      atomicAdd(counts + 0, (unsigned long long)n_valid);
+      atomicAdd(counts + 1, (unsigned long long)n_hit);
+      atomicAdd(counts + 2, (unsigned long long)(n_valid - n_hit));
+    }
+  }
 }
 
 // list lengths: from unitig ids (hits == nullptr) or from hit records
@@ -1375,6 +1570,28 @@ __global__ void __launch_bounds__(256) k2u_validate_self_kernel(const __grid_con
     }
   }
   block_accumulate(counts, v);
+}
+
+// Are the canonical k-mers of the unitig set pairwise distinct (true for every compacted de Bruijn graph)?  Thread per useq
+// position: the k-mer there must be found AT that position; a hit elsewhere means the set holds the k-mer twice.  When they
+// are distinct, StreamingK2U (src/index/caching.rs:65-103) answers exactly what K2U::k2u answers -- a warm hit at
+// (unitig, pos + 1) is an occurrence of the k-mer, and there is only one -- so the launcher serves streaming queries
+// with the random-access kernel; the cursor walk is only needed for sets with duplicated k-mers.
+__global__ void __launch_bounds__(256) count_duplicated_kmers_kernel(const __grid_constant__ IndexView ix, unsigned long long* n_elsewhere) {
+  const u32 k = ix.unitigs.k;
+  const u64 total = ix.unitigs.total_len;
+  u32 bad = 0;
+  for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p + k <= total; p += (u64)gridDim.x * blockDim.x) {
+    u64 id, s, e;
+    unitig_locate(ix.unitigs, p, id, s, e);
+    if (p + k > e) continue;
+    const u64 fw = useq_window(ix.unitigs, p), rc = revcomp(fw, k);
+    Hit h;
+    if (!k2u_any(ix, fw, rc, h) || h.unitig_id != (u32)id || h.pos != (u32)(p - s)) ++bad;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(n_elsewhere, (unsigned long long)bad);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -119,10 +119,10 @@ static void check_sshash_tables(const K2UHost& h) {
         u64 qf = t ? rc : fw, qr = t ? fw : rc;
         MinimizerResult mm = canonical_minimizer_naive(qf, qr, k, w, h.seed);
         u64 hh;
-        bool ok = mphf_lookup(mv, mm.word, hh);
-        CHECK(ok && hh + 1 < ev.n, "minimizer not in mphf");
+        bool ok = mv.family == MPHF_FAMILY_CASCADE && cascade_lookup(mv, ev, mm.word, hh);
+        CHECK(ok && hh + 1 < ev.n, "minimizer not in the cascade");
         if (!ok) continue;
-        CHECK(ev.wpb == 8 && blocked_ef_fp(ev, hh) == mphf_fingerprint(mm.word), "fingerprint of a member minimizer");
+        CHECK(ev.wpb == 8 && blocked_ef_fp(ev, hh) == cascade_fp(fmix64(mm.word)), "fingerprint of a member minimizer");
         u64 a, b;
         blocked_ef_get2(ev, hh, a, b);
         CHECK(b > a, "empty bucket");

@@ -409,10 +409,24 @@ def test_streaming_exact_with_duplicate_kmers():
     for w, skew in [(7, NOSKEW), (5, 1), (11, 0)]:
         g = mz.SSHash.from_unitig_set(us, w, skew)
         o = OracleIndex.from_seqs(seqs, k, 1, w=w, skew=skew)
+        assert not g.kmers_unique  # detected at creation: the cursor-walk kernel serves streaming queries
         r_want, _ = _check_reads(g, o, bases, offs, mz.MODE_RANDOM)
         s_want, _ = _check_reads(g, o, bases, offs, mz.MODE_STREAMING)
         differs |= not np.array_equal(r_want, s_want)
     assert differs, "test input should make streaming and random-access answers differ"
+
+
+def test_unique_kmers_make_streaming_equal_random(yeast_dense, yeast_sshash, yeast_queries):
+    """A set with pairwise distinct canonical k-mers (any cdBG): a warm hit of StreamingK2U is the k-mer's only occurrence, so
+    streaming answers equal K2U::k2u record for record; the library detects this at creation (MAZU_INFO_KMERS_UNIQUE) and serves
+    streaming queries with the random-access kernel.  Both modes still equal the oracle's streaming / random walks."""
+    _, ref_codes = yeast_queries
+    bases, offs = _gen.sample_reads(ref_codes, 1500, 150, seed=21, frac_ref=0.7, sub_rate=0.01, n_rate=0.002, ragged=True)
+    for g, o in (yeast_dense, yeast_sshash):
+        assert g.kmers_unique
+        r_want, _ = _check_reads(g, o, bases, offs, mz.MODE_RANDOM)
+        s_want, _ = _check_reads(g, o, bases, offs, mz.MODE_STREAMING)
+        assert np.array_equal(r_want, s_want)
 
 
 # --------------------------------------------------------------------------------------------
