@@ -69,12 +69,13 @@ def parse_args():
     ap.add_argument("--mode", default=None, choices=["random", "streaming"])
     ap.add_argument("--scale", type=float, default=1.0, help="config5: fraction of the human-scale unitig count (36,145,130 unitigs)")
     ap.add_argument("--cpu-scale", type=float, default=0.1, help="config5: unitig-set scale of the CPU port's index (its builder needs ~25 s per 0.1 on 16 cores)")
-    ap.add_argument("--e2e-slice", type=int, default=2_500_000, help="reads of the batch the full-record / compact e2e variants run on")
+    ap.add_argument("--e2e-slice", type=int, default=1_000_000, help="reads of the batch the full-record / compact e2e variants run on")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU seconds for the cpu_baseline sample")
     ap.add_argument("--builder", default="gpu", choices=["host", "gpu"], help="config5: where SSHash::from_unitig_set runs")
     ap.add_argument("--validate", action="store_true", help="config5: also run k2u_validate_self on the device (every unitig k-mer)")
+    ap.add_argument("--no-chain", action="store_true", help="config2/3: skip the get_ref_pos chain measurement (reads -> MappedRefPos)")
     a = ap.parse_args()
     if a.mode is None:
         a.mode = "streaming" if a.workload == "config3" else "random"
@@ -471,7 +472,7 @@ def main():
             hb = h_bases.numpy()
             # hit runs: a lossless compact form of the records (codes + run starts); the buffers are reused across steps
             h_codes = torch.empty(e2e_units, dtype=torch.uint8, pin_memory=True)
-            h_runs = torch.empty((max(1 << 20, e2e_units // 8), 4), dtype=torch.int32, pin_memory=True)
+            h_runs = torch.empty((max(1 << 20, e2e_units // 16), 4), dtype=torch.int32, pin_memory=True)
             h_rro = torch.zeros(e2e_reads + 1, dtype=torch.int64, pin_memory=True)
             runs_state = {"n_runs": 0}
 
@@ -507,7 +508,27 @@ def main():
                 index.query_reads(hb, None, n_reads=e2e_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=hits, counts=h_cnt,
                                   mem=mz.MEM_HOST_IN_DEVICE_OUT)
 
-            e2e_extra = {
+            # packed interface for PCIe-bound hosts: 2-bit reads in (packed once, outside the timed loop, as a caller holding
+            # SeqVector-style reads would), 2-bit codes out
+            packed_ok = nk_per_read % 4 == 0
+            if packed_ok:
+                wpr = (READ_LEN + 31) // 32
+                h_words = torch.empty(e2e_reads * wpr, dtype=torch.int64, pin_memory=True)
+                mz.pack_reads(hb, READ_LEN, words=h_words, want_mask=False)
+                h_codes2 = torch.empty((e2e_units + 3) // 4, dtype=torch.uint8, pin_memory=True)
+
+                def e2e_packed_step():
+                    n_runs = C.c_uint64(0)
+                    mz._check(mz.lib().mazu_b200_query_reads_runs_packed(index._h, mz._any_ptr(h_words), None, e2e_reads, READ_LEN, mode, mz._any_ptr(h_codes2),
+                                                                         mz._any_ptr(h_runs), h_runs.shape[0], mz._any_ptr(h_rro), C.byref(n_runs), mz._np_ptr(h_cnt)))
+                    runs_state["n_runs_packed"] = n_runs.value
+
+            e2e_extra = {}
+            if packed_ok:
+                e2e_extra["hit_runs_packed"] = (e2e_packed_step, e2e_units, e2e_reads * wpr * 8, None,
+                                                "mazu_b200_query_reads_runs_packed: 2-bit packed reads in (40 B per 150 bp read), 2-bit run codes + run records + "
+                                                "per-read run offsets out; mazu_b200_expand_hit_runs_packed rebuilds every record")
+            e2e_extra.update({
                 "full_records": (e2e_full_step, sl_units, sl_reads * READ_LEN, sl_units * 16 + 24,
                                  "mazu_b200_query_reads(MAZU_MEM_HOST): every 16-byte record over PCIe; first %d reads of the batch" % sl_reads),
                 "compact_records": (e2e_compact_step, sl_units, sl_reads * READ_LEN, sl_units * 8 + 24,
@@ -515,7 +536,7 @@ def main():
                 "host_reads_in_device_records_out": (e2e_devout_step, e2e_units, e2e_reads * READ_LEN, 24,
                                                      "MAZU_MEM_HOST_IN_DEVICE_OUT: pinned host reads in, 16-byte records stay in HBM (input of project_hits on the "
                                                      "device), the three counters of `kphf bench` (src/bin/kphf/main.rs:282-284) come back"),
-            }
+            })
 
         def check():
             if W == "config5":  # no oracle index at this scale: verify sampled hits directly against the packed sequence
@@ -550,6 +571,53 @@ def main():
             want, _, _ = os_idx.query_reads(chk, np.arange(n_chk + 1, dtype=np.uint64) * READ_LEN, streaming=(mode == mz.MODE_STREAMING))
             got = hits[: n_chk * nk_per_read].cpu().numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE)
             return bool(np.array_equal(got, want))
+
+        def chain_line():
+            """GetRefPos::get_ref_pos over reads (src/index.rs:156-216), everything on the device: the fused kernel
+            (mazu_b200_get_ref_pos_reads) against the unfused chain (query_reads -> project_hits) on the same reads."""
+            m = min(n_reads, 4_000_000)
+            ns = m * nk_per_read
+            d_offs = torch.zeros(ns + 1, dtype=torch.int64, device=dev)
+            mz._check(mz.lib().mazu_b200_project_hits(index._h, mz._any_ptr(hits), ns, mz._any_ptr(d_offs), None, 0, None, mz.MEM_DEVICE, mz._any_ptr(stream.cuda_stream)))
+            torch.cuda.synchronize()
+            total = int(d_offs[ns].item())
+            d_out = torch.empty((total + 16, 3), dtype=torch.int32, device=dev)
+            d_out2 = torch.empty((total + 16, 3), dtype=torch.int32, device=dev)
+            d_offs2 = torch.zeros(ns + 1, dtype=torch.int64, device=dev)
+            sp = mz._any_ptr(stream.cuda_stream)
+
+            def unfused():
+                index.query_reads(bases, None, n_reads=m, uniform_read_len=READ_LEN, mode=mode, out_hits=hits, counts=None, mem=mz.MEM_DEVICE, stream=stream.cuda_stream)
+                mz._check(mz.lib().mazu_b200_project_hits(index._h, mz._any_ptr(hits), ns, mz._any_ptr(d_offs), mz._any_ptr(d_out), total, None, mz.MEM_DEVICE, sp))
+
+            def project_only():
+                mz._check(mz.lib().mazu_b200_project_hits(index._h, mz._any_ptr(hits), ns, mz._any_ptr(d_offs), mz._any_ptr(d_out), total, None, mz.MEM_DEVICE, sp))
+
+            def fused():
+                mz._check(mz.lib().mazu_b200_get_ref_pos_reads(index._h, mz._any_ptr(bases), None, m, READ_LEN, mode, ns, None, None, mz._any_ptr(d_offs2),
+                                                               mz._any_ptr(d_out2), total, None, None, mz.MEM_DEVICE, sp))
+
+            def timed(fn):
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(args.steps):
+                    fn()
+                b.record(stream)
+                torch.cuda.synchronize()
+                return a.elapsed_time(b) / args.steps
+
+            t_un, t_pr, t_fu = timed(unfused), timed(project_only), timed(fused)
+            same = bool(torch.equal(d_offs, d_offs2)) and bool(torch.equal(d_out[:total], d_out2[:total]))
+            return {"reads": m, "kmer_slots": ns, "projected_positions": total,
+                    "unfused": {"ms": t_un, "kmers_per_s": ns / (t_un * 1e-3), "project_hits_ms": t_pr, "api": "mazu_b200_query_reads + mazu_b200_project_hits"},
+                    "fused": {"ms": t_fu, "kmers_per_s": ns / (t_fu * 1e-3), "api": "mazu_b200_get_ref_pos_reads (lookups + per-tile totals, scan over tiles, tile-wise emit)"},
+                    "fused_equals_unfused": same}
+
+        if W in ("config2", "config3") and not args.no_chain:
+            info["chain_fn"] = chain_line
 
         def cpu_fn():
             port = CpuPort(args)
@@ -800,7 +868,13 @@ def main():
         for name, (fn, units, h2d, d2h, api) in e2e_extra.items():
             dtx = timed_host_loop(fn)
             e2e[name] = {"value": float(units) * args.steps * world / dtx, "unit": unit, "units_per_step_per_gpu": units,
-                         "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "api": api}
+                         "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": (d2h or 0) * world, "api": api}
+            if name == "hit_runs_packed":
+                e2e[name]["d2h_bytes_per_step"] = ((units + 3) // 4 + 16 * runs_state["n_runs_packed"] + 8 * (e2e_reads + 1) + 24) * world
+                m = min(e2e_reads, 20000)
+                exp = mz.ModIndex.expand_hit_runs_packed(h_codes2.numpy()[: m * nk_per_read // 4], h_runs.numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE),
+                                                         h_rro.numpy().view(np.uint64)[: m + 1], nk_per_read)
+                e2e[name]["expands_to_full_records"] = bool(np.array_equal(exp.view(np.uint32).reshape(-1, 4), hits[: m * nk_per_read].cpu().numpy().view(np.uint32)))
             if name == "full_records":
                 e2e[name]["matches_device_path"] = bool(torch.equal(h_hits[:1_000_000], hits[:1_000_000].cpu()))
                 if pc:
@@ -817,6 +891,8 @@ def main():
     parity_ok = bool(check()) if check else None
     if "projected_fn" in info:
         info["projected"] = info.pop("projected_fn")()
+    if "chain_fn" in info:
+        info["get_ref_pos_chain"] = info.pop("chain_fn")()
     if args.validate and W.startswith("config5"):
         c = index.k2u_validate_self()
         info["k2u_validate_self"] = {"n_queries": c[0], "n_identity": c[1], "n_twin": c[2], "n_fail": c[4], "n_fail_not_found": c[3],

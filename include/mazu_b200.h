@@ -218,14 +218,31 @@ mazu_status_t mazu_b200_query_reads_compact(const mazu_index_t* idx, const uint8
  * one unitig, so slot s "continues" slot s-1 when both hit the same unitig with the same match type and pos differs by +1
  * (Identity) or -1 (Twin).  Outputs:
  *   out_codes             one byte per k-mer slot: 0 miss, 1 hit continuing the previous slot's run, 2 hit starting a run, 3 skipped
- *   out_runs              the full mazu_hit_t of every run start, in slot order (cap_runs records; at most one per slot)
- *   out_read_run_offsets  n_reads + 1: index in out_runs of read r's first run
+ *   out_runs              the full mazu_hit_t of every run start (cap_runs records; at most one per slot); the runs of one read are
+ *                         consecutive and in slot order, the order of different reads' runs is unspecified
+ *   out_read_run_offsets  n_reads + 1: entry r = index in out_runs of read r's first run (not monotone in r), entry n_reads = number of runs
  *   out_n_runs            runs written; if it exceeds cap_runs the call fails with MAZU_ERR_INVALID_ARG and this is the capacity needed
  * ~1.1 bytes per lookup cross PCIe instead of 16; mazu_b200_expand_hit_runs rebuilds the exact mazu_hit_t array on the host. */
 mazu_status_t mazu_b200_query_reads_runs(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets,
                                          uint64_t n_reads, uint64_t uniform_read_len, int32_t mode, uint64_t* kmer_offsets,
                                          uint8_t* out_codes, mazu_hit_t* out_runs, uint64_t cap_runs, uint64_t* out_read_run_offsets,
                                          uint64_t* out_n_runs, uint64_t* counts);
+/* The same call for hosts where PCIe / host memory bandwidth is the limit (several GPUs behind one host): reads arrive 2-bit
+ * packed and the run codes leave 2 bits per slot -- 0.31 + 0.25 bytes per lookup cross PCIe instead of 1.25 + 1.
+ *   packed_reads  uniform reads in the kmers::SeqVector layout: read r = words [r * wpr, (r + 1) * wpr), wpr = ceil(read_len / 32),
+ *                 base j at bits [2j, 2j + 2) of its words, A=0 C=1 G=2 T=3 (mazu_b200_pack_reads makes it from ASCII)
+ *   n_mask        optional, 1 bit per base, ceil(read_len / 64) words per read: set = the base is not ACGT (NULL: none is)
+ *   out_codes2    2 bits per k-mer slot: slot s at bits [2 (s % 4), 2 (s % 4) + 2) of byte s / 4, same code values
+ * read_len - k + 1 must be a multiple of 4.  mazu_b200_expand_hit_runs_packed rebuilds every mazu_hit_t on the host. */
+mazu_status_t mazu_b200_query_reads_runs_packed(const mazu_index_t* idx, const uint64_t* packed_reads, const uint64_t* n_mask,
+                                                uint64_t n_reads, uint64_t read_len, int32_t mode, uint8_t* out_codes2,
+                                                mazu_hit_t* out_runs, uint64_t cap_runs, uint64_t* out_read_run_offsets,
+                                                uint64_t* out_n_runs, uint64_t* counts);
+/* ASCII -> 2-bit words (+ N mask) on the host, multi-threaded; *n_non_acgt (optional) counts the masked bases */
+mazu_status_t mazu_b200_pack_reads(const uint8_t* bases, uint64_t n_reads, uint64_t read_len, uint64_t* out_words, uint64_t* out_n_mask,
+                                   uint64_t* n_non_acgt);
+mazu_status_t mazu_b200_expand_hit_runs_packed(const uint8_t* codes2, const mazu_hit_t* runs, const uint64_t* read_run_offsets,
+                                               uint64_t n_reads, uint64_t uniform_slots, mazu_hit_t* out_hits);
 /* host-side decoder of the run format (multi-threaded, no device work): out_hits[slot] for every slot of every read.
  * kmer_offsets may be NULL for uniform batches (uniform_slots = read_len - k + 1). */
 mazu_status_t mazu_b200_expand_hit_runs(const uint8_t* codes, const mazu_hit_t* runs, const uint64_t* read_run_offsets,

@@ -129,6 +129,9 @@ def _signatures():
         "mazu_b200_query_reads_compact": (i32, [vp, vp, vp, u64, u64, i32, vp, vp, vp, i32, vp]),
         "mazu_b200_query_reads_runs": (i32, [vp, vp, vp, u64, u64, i32, vp, vp, vp, u64, vp, vp, vp]),
         "mazu_b200_expand_hit_runs": (i32, [vp, vp, vp, vp, u64, u64, vp]),
+        "mazu_b200_query_reads_runs_packed": (i32, [vp, vp, vp, u64, u64, i32, vp, vp, u64, vp, vp, vp]),
+        "mazu_b200_pack_reads": (i32, [vp, u64, u64, vp, vp, vp]),
+        "mazu_b200_expand_hit_runs_packed": (i32, [vp, vp, vp, u64, u64, vp]),
         "mazu_b200_encode_reads": (i32, [vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp]),
         "mazu_b200_decode_occs": (i32, [vp, vp, u64, vp, vp, u64, vp, i32, vp]),
         "mazu_b200_project_hits": (i32, [vp, vp, u64, vp, vp, u64, vp, i32, vp]),
@@ -465,6 +468,32 @@ class ModIndex:
             break
         return codes, runs[: n_runs.value], rro, cnt, koffs
 
+    def query_reads_runs_packed(self, words, n_mask, n_reads, read_len, mode=MODE_RANDOM, codes2=None, runs=None, read_run_offsets=None):
+        """mazu_b200_query_reads_runs_packed: 2-bit reads in, 2-bit codes out: (codes2, runs[:n_runs], read_run_offsets, counts)."""
+        n_slots = n_reads * max(read_len - self.k + 1, 0)
+        codes2 = np.zeros((n_slots + 3) // 4, dtype=np.uint8) if codes2 is None else codes2
+        rro = np.zeros(n_reads + 1, dtype=np.uint64) if read_run_offsets is None else read_run_offsets
+        cnt = np.zeros(3, dtype=np.uint64)
+        n_runs = C.c_uint64(0)
+        if runs is None:
+            runs = np.empty(max(1024, n_slots // 16), dtype=HIT_DTYPE)
+        while True:
+            rc = lib().mazu_b200_query_reads_runs_packed(self._h, _any_ptr(words), _any_ptr(n_mask), n_reads, read_len, mode, _any_ptr(codes2),
+                                                         _any_ptr(runs), len(runs), _any_ptr(rro), C.byref(n_runs), _np_ptr(cnt))
+            if rc != 0 and n_runs.value > len(runs):
+                runs = np.empty(n_runs.value, dtype=HIT_DTYPE)
+                continue
+            _check(rc)
+            break
+        return codes2, runs[: n_runs.value], rro, cnt
+
+    @staticmethod
+    def expand_hit_runs_packed(codes2, runs, read_run_offsets, uniform_slots, out=None):
+        n_reads = len(read_run_offsets) - 1
+        out = np.empty(n_reads * uniform_slots, dtype=HIT_DTYPE) if out is None else out
+        _check(lib().mazu_b200_expand_hit_runs_packed(_any_ptr(codes2), _any_ptr(runs), _any_ptr(read_run_offsets), n_reads, uniform_slots, _any_ptr(out)))
+        return out
+
     @staticmethod
     def expand_hit_runs(codes, runs, read_run_offsets, kmer_offsets=None, uniform_slots=0, out=None):
         n_reads = len(read_run_offsets) - 1
@@ -714,6 +743,19 @@ class PFHash:
     @staticmethod
     def from_unitig_set(unitigs, device=0, builder="host"):
         return ModIndex.pfhash_from_unitig_set(unitigs, device, builder)
+
+
+def pack_reads(bases, read_len, words=None, n_mask=None, want_mask=True):
+    """mazu_b200_pack_reads: ASCII uniform reads -> (2-bit words, N mask or None, number of non-ACGT bases)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8) if isinstance(bases, np.ndarray) else bases
+    n_reads = (len(bases) if isinstance(bases, np.ndarray) else bases.numel()) // read_len
+    wpr, mpr = (read_len + 31) // 32, (read_len + 63) // 64
+    words = np.zeros(n_reads * wpr, dtype=np.uint64) if words is None else words
+    if n_mask is None and want_mask:
+        n_mask = np.zeros(n_reads * mpr, dtype=np.uint64)
+    bad = C.c_uint64(0)
+    _check(lib().mazu_b200_pack_reads(_any_ptr(bases), n_reads, read_len, _any_ptr(words), _any_ptr(n_mask), C.byref(bad)))
+    return words, n_mask, int(bad.value)
 
 
 def gather_probe(table_bytes, n_items, granule_bytes=32, ilp=1, blocks_per_sm=8, iters=3, device=0):

@@ -174,6 +174,57 @@ void device_exclusive_scan(const u64* d_in, u64* d_out, u64 n, cudaMemPool_t poo
   MZ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, d_in, d_out, (size_t)(n + 1), s));
 }
 
+// Tiles of the fused kernels: one per chunk of QR_CHUNK k-mer positions, at least one per read.  Uniform reads need no table.
+// Ragged reads: seg (n_reads + 1 first-tile indexes) is built on the device; n_tiles comes from the caller when it can count on
+// the host (host pipelines), else it is read back (one synchronisation).
+struct TileTable {
+  std::unique_ptr<PoolBuf> cnt, seg;
+  u64 n_tiles = 0;
+};
+void make_tiles(const mazu_index* idx, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, u64 n_tiles_known, cudaStream_t s, TileTable& t) {
+  const u32 k = idx->unitigs->k;
+  if (uniform_len) {
+    const u64 nk = uniform_len >= k ? uniform_len - k + 1 : 0;
+    t.n_tiles = n_reads * (nk <= (u64)QR_CHUNK ? 1 : (nk + QR_CHUNK - 1) / QR_CHUNK);
+    return;
+  }
+  t.cnt = std::make_unique<PoolBuf>(idx->pool, (n_reads + 1) * 8, s);
+  t.seg = std::make_unique<PoolBuf>(idx->pool, (n_reads + 1) * 8, s);
+  MZ_CUDA(cudaMemsetAsync(t.cnt->p, 0, (n_reads + 1) * 8, s));
+  segment_counts_kernel<<<(int)std::min<u64>((n_reads + 255) / 256, 4096), 256, 0, s>>>(d_read_offsets, n_reads, k, (u64)QR_CHUNK, (u64*)t.cnt->p);
+  MZ_CUDA(cudaGetLastError());
+  device_exclusive_scan((const u64*)t.cnt->p, (u64*)t.seg->p, n_reads, idx->pool, s);
+  if (n_tiles_known != ~0ULL) {
+    t.n_tiles = n_tiles_known;
+  } else {
+    MZ_CUDA(cudaMemcpyAsync(&t.n_tiles, (u64*)t.seg->p + n_reads, 8, cudaMemcpyDeviceToHost, s));
+    MZ_CUDA(cudaStreamSynchronize(s));
+  }
+}
+
+// fused reads -> hit runs (query_reads_runs_kernel): codes per slot, chunk-local run records, per-read run offsets; d_rro[n_reads]
+// is the run cursor (the chunk's run count afterwards).  Only for chunks whose reads all fit one tile.
+void launch_query_reads_runs(const mazu_index* idx, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, const u64* d_kmer_offsets,
+                             u64* d_counts, u8* d_codes, Hit* d_runs, u64* d_rro, u64 cap, cudaStream_t s) {
+  MZ_CUDA(cudaMemsetAsync(d_rro + n_reads, 0, 8, s));
+  if (!n_reads) return;
+  RunsTileOut ro{d_codes, d_runs, d_rro, (unsigned long long*)(d_rro + n_reads), cap};
+  const bool ss = idx->view.k2u_kind == MAZU_K2U_SSHASH, boophf = idx->view.mphf.family == MPHF_FAMILY_BOOPHF;
+#define MZ_QRR(K, F)                                                                                                          \
+  {                                                                                                                            \
+    auto kern = query_reads_runs_kernel<K, F>;                                                                                 \
+    int grid = grid_for(kern, QR_WARPS * 32, idx, QR_WARPS, n_reads);                                                          \
+    kern<<<grid, QR_WARPS * 32, 0, s>>>(idx->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets,              \
+                                        (unsigned long long*)d_counts, ro);                                                    \
+  }
+  if (ss) MZ_QRR(MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE)
+  else if (idx->view.k2u_kind == MAZU_K2U_SAMPLED_PFHASH) MZ_QRR(MAZU_K2U_SAMPLED_PFHASH, MPHF_FAMILY_BOOPHF)
+  else if (boophf) MZ_QRR(MAZU_K2U_PFHASH, MPHF_FAMILY_BOOPHF)
+  else MZ_QRR(MAZU_K2U_PFHASH, MPHF_FAMILY_NATIVE)
+#undef MZ_QRR
+  MZ_CUDA(cudaGetLastError());
+}
+
 struct StreamPair {
   cudaStream_t s[2] = {nullptr, nullptr};
   StreamPair() {
@@ -522,6 +573,10 @@ struct RunsOut {
   uint64_t n_runs = 0;         // runs this call produced (it keeps counting past the capacity)
   uint64_t base = 0;           // index in `runs` of this call's first run (sharded calls: the shard's region)
   bool write_end = true;       // write read_run_offsets[n_reads] (sharded calls: that entry belongs to the next shard)
+  // packed I/O (mazu_b200_query_reads_runs_packed): uniform reads arrive as 2-bit words (+ optional N mask), codes leave 2 bits per slot
+  const uint64_t* packed_words = nullptr;
+  const uint64_t* packed_nmask = nullptr;
+  bool codes2 = false;
 };
 
 static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* read_offsets, uint64_t n_reads,
@@ -533,8 +588,10 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
     if (ro && (mem != MAZU_MEM_HOST || compact || out_hits)) throw Error(MAZU_ERR_INVALID_ARG, "hit runs are a host-buffer output");
     if (ro && n_reads && (!ro->codes || !ro->read_run_offsets || (ro->cap_runs && !ro->runs))) throw Error(MAZU_ERR_INVALID_ARG, "null run buffers");
     if (mode != MAZU_MODE_RANDOM && mode != MAZU_MODE_STREAMING) throw Error(MAZU_ERR_INVALID_ARG, "unknown query mode");
-    if (n_reads && !bases) throw Error(MAZU_ERR_INVALID_ARG, "null bases");
+    const bool packed_in = ro && ro->packed_words;
+    if (n_reads && !bases && !packed_in) throw Error(MAZU_ERR_INVALID_ARG, "null bases");
     if (n_reads && !uniform_read_len && !read_offsets) throw Error(MAZU_ERR_INVALID_ARG, "read_offsets is required for ragged reads");
+    if (ro && (packed_in || ro->codes2) && !uniform_read_len) throw Error(MAZU_ERR_INVALID_ARG, "packed reads / packed codes need uniform reads");
     const u32 k = idx->unitigs->k;
     DeviceGuard g(idx->device);
     if (mem == MAZU_MEM_DEVICE) {
@@ -591,7 +648,7 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       u64 r = 0;
       while (r < n_reads) {
         u64 r1;
-        if (uniform_read_len) r1 = std::min(n_reads, r + std::max<u64>(1, TARGET / uniform_read_len));
+        if (uniform_read_len) r1 = std::min(n_reads, r + std::max<u64>(4, (TARGET / uniform_read_len) & ~3ULL));  // a multiple of 4 reads: packed codes stay byte aligned
         else {
           u64 lim = read_offsets[r] + TARGET;
           r1 = (u64)(std::upper_bound(read_offsets + r + 1, read_offsets + n_reads + 1, lim) - read_offsets) - 1;
@@ -616,6 +673,15 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       if (cudaPointerGetAttributes(&at, ro->runs) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) runs_dev = (Hit*)at.devicePointer;
       else cudaGetLastError();
     }
+    // hit runs come straight out of the fused kernel unless the cursor walk is needed (streaming on a set with duplicated k-mers)
+    static const bool unfused_knob = getenv("MAZU_B200_UNFUSED_RUNS") != nullptr;  // A/B knob: the round-1 chain of four kernels
+    bool fused_runs = ro && !(mode == MAZU_MODE_STREAMING && !idx->kmers_unique) && !unfused_knob;
+    if (fused_runs) {  // the fused kernel owns one read per warp and one chunk per read: every read must fit QR_CHUNK k-mer positions
+      const u64 max_len = (u64)QR_CHUNK + k - 1;
+      if (uniform_read_len) fused_runs = uniform_read_len <= max_len;
+      else
+        for (u64 r = 0; r < n_reads && fused_runs; ++r) fused_runs = read_offsets[r + 1] - read_offsets[r] <= max_len;
+    }
     // two buffers / streams alternate; the sync-free run path uses three, because its per-chunk chain (H2D, lookups, encode, two
     // D2H copies) is 2.3x as long as its compute and two streams leave the SMs idle a third of the time
     const int NB = runs_dev ? 3 : 2;
@@ -639,8 +705,17 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
         d_ro[b] = scratch.get((max_reads + 1) * 8);
         d_ko[b] = scratch.get((max_reads + 1) * 8);
       }
-      if ((out_hits && !dev_out) || ro) d_hits[b] = scratch.get(max_slots * rec + 16);
+      if ((out_hits && !dev_out) || (ro && !fused_runs)) d_hits[b] = scratch.get(max_slots * rec + 16);
     }
+    const u64 wpr = uniform_read_len ? (uniform_read_len + 31) / 32 : 0, mpr = uniform_read_len ? (uniform_read_len + 63) / 64 : 0;
+    void *d_pw[3] = {nullptr, nullptr, nullptr}, *d_pm[3] = {nullptr, nullptr, nullptr}, *d_codes2[3] = {nullptr, nullptr, nullptr};
+    if (packed_in)
+      for (int b = 0; b < NB; ++b) {
+        d_pw[b] = scratch.get(max_reads * wpr * 8 + 16);
+        if (ro->packed_nmask) d_pm[b] = scratch.get(max_reads * mpr * 8 + 16);
+      }
+    if (ro && ro->codes2)
+      for (int b = 0; b < NB; ++b) d_codes2[b] = scratch.get(max_slots / 4 + 16);
     u64* d_base = nullptr;
     u64* d_total_copy[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t base_ev = nullptr;
@@ -696,6 +771,17 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
         if (ro->write_end || r0 + nr < n_reads) ro->read_run_offsets[r0 + nr] = at + total;
       }
     };
+    // codes of one chunk back to the host: one byte per slot, or 2 bits per slot (chunks start at a multiple of 4 slots)
+    auto copy_codes = [&](int bb, u64 s0, u64 ns, cudaStream_t s) {
+      if (!ns) return;
+      if (ro->codes2) {
+        pack_codes_kernel<<<idx->sm_count * 4, 256, 0, s>>>((const u8*)d_codes[bb], ns, (u8*)d_codes2[bb]);
+        MZ_CUDA(cudaGetLastError());
+        MZ_CUDA(cudaMemcpyAsync(ro->codes + s0 / 4, d_codes2[bb], (ns + 3) / 4, cudaMemcpyDeviceToHost, s));
+      } else {
+        MZ_CUDA(cudaMemcpyAsync(ro->codes + s0, d_codes[bb], ns, cudaMemcpyDeviceToHost, s));
+      }
+    };
     scratch.publish(sp.s[1]);
     if (NB == 3) scratch.publish(extra.s);
     int b = 0;
@@ -704,7 +790,15 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       u64 b0 = base_off(r0), nb = base_off(r1) - b0;
       u64 s0 = slot_off(r0), ns = slot_off(r1) - s0;
       cudaStream_t s = st[b];
-      MZ_CUDA(cudaMemcpyAsync(d_bases[b], bases + b0, nb, cudaMemcpyHostToDevice, s));
+      if (packed_in) {  // 2-bit words over PCIe, ASCII only ever exists in HBM
+        const u64 nrc = r1 - r0;
+        MZ_CUDA(cudaMemcpyAsync(d_pw[b], ro->packed_words + r0 * wpr, nrc * wpr * 8, cudaMemcpyHostToDevice, s));
+        if (ro->packed_nmask) MZ_CUDA(cudaMemcpyAsync(d_pm[b], ro->packed_nmask + r0 * mpr, nrc * mpr * 8, cudaMemcpyHostToDevice, s));
+        unpack_reads_kernel<<<idx->sm_count * 8, 256, 0, s>>>((const u64*)d_pw[b], (const u64*)d_pm[b], nrc, uniform_read_len, (u8*)d_bases[b]);
+        MZ_CUDA(cudaGetLastError());
+      } else {
+        MZ_CUDA(cudaMemcpyAsync(d_bases[b], bases + b0, nb, cudaMemcpyHostToDevice, s));
+      }
       const u64* dro = nullptr;
       const u64* dko = nullptr;
       if (!uniform_read_len) {
@@ -718,33 +812,37 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       void* dh = nullptr;
       if (out_hits && dev_out) dh = (char*)out_hits + (uniform_read_len ? s0 * rec : 0);
       else if (out_hits || ro) dh = (char*)d_hits[b] - (uniform_read_len ? 0 : s0 * rec);
-      launch_query_reads(idx, dbases, dro, r1 - r0, uniform_read_len, mode, dko, dh, compact, (u64*)d_counts, s);
+      if (!fused_runs) launch_query_reads(idx, dbases, dro, r1 - r0, uniform_read_len, mode, dko, dh, compact, (u64*)d_counts, s);
       if (out_hits && !dev_out && ns) MZ_CUDA(cudaMemcpyAsync((char*)out_hits + s0 * rec, d_hits[b], ns * rec, cudaMemcpyDeviceToHost, s));
       if (ro) {
         const u64 nr = r1 - r0;
         const Hit* hh = (const Hit*)dh;
         u8* cc = (u8*)d_codes[b] - (uniform_read_len ? 0 : s0);
-        MZ_CUDA(cudaMemsetAsync(d_rc[b], 0, (nr + 1) * 8, s));
         const int grid = (int)std::min<u64>((nr + 7) / 8, (u64)idx->sm_count * 8);
-        hit_run_codes_kernel<<<grid, 256, 0, s>>>(hh, dko, nr, uniform_slots, cc, (u64*)d_rc[b]);
-        MZ_CUDA(cudaGetLastError());
-        device_exclusive_scan((const u64*)d_rc[b], (u64*)d_rro[b], nr, idx->pool, s);
+        if (fused_runs) {  // one kernel: lookups, run codes, run records (chunk-local), per-read run offsets
+          launch_query_reads_runs(idx, dbases, dro, nr, uniform_read_len, dko, (u64*)d_counts, cc, (Hit*)d_runs[b], (u64*)d_rro[b], max_slots, s);
+        } else {
+          MZ_CUDA(cudaMemsetAsync(d_rc[b], 0, (nr + 1) * 8, s));
+          hit_run_codes_kernel<<<grid, 256, 0, s>>>(hh, dko, nr, uniform_slots, cc, (u64*)d_rc[b]);
+          MZ_CUDA(cudaGetLastError());
+          device_exclusive_scan((const u64*)d_rc[b], (u64*)d_rro[b], nr, idx->pool, s);
+        }
         if (runs_dev) {
           // the running base lives on the device: this chunk reads it after the previous chunk (other stream) has advanced it
           MZ_CUDA(cudaMemcpyAsync(d_total_copy[b], (u64*)d_rro[b] + nr, 8, cudaMemcpyDeviceToDevice, s));  // the fill kernel overwrites offsets in place
           MZ_CUDA(cudaStreamWaitEvent(s, base_ev, 0));
-          hit_run_fill_kernel<<<grid, 256, 0, s>>>(hh, cc, dko, nr, uniform_slots, (const u64*)d_rro[b], 0, max_slots, (Hit*)d_runs[b]);
+          if (!fused_runs) hit_run_fill_kernel<<<grid, 256, 0, s>>>(hh, cc, dko, nr, uniform_slots, (const u64*)d_rro[b], 0, max_slots, (Hit*)d_runs[b]);
           hit_run_publish_kernel<<<idx->sm_count * 2, 256, 0, s>>>((u64*)d_rro[b], nr, (const Hit*)d_runs[b], d_total_copy[b], d_base, ro->cap_runs,
                                                                    runs_dev);
           hit_run_advance_kernel<<<1, 32, 0, s>>>(d_base, d_total_copy[b]);
           MZ_CUDA(cudaGetLastError());
           MZ_CUDA(cudaEventRecord(base_ev, s));
-          if (ns) MZ_CUDA(cudaMemcpyAsync(ro->codes + s0, d_codes[b], ns, cudaMemcpyDeviceToHost, s));
+          copy_codes(b, s0, ns, s);
           if (nr) MZ_CUDA(cudaMemcpyAsync(ro->read_run_offsets + r0, d_rro[b], nr * 8, cudaMemcpyDeviceToHost, s));
         } else {
-          hit_run_fill_kernel<<<grid, 256, 0, s>>>(hh, cc, dko, nr, uniform_slots, (const u64*)d_rro[b], 0, max_slots, (Hit*)d_runs[b]);
+          if (!fused_runs) hit_run_fill_kernel<<<grid, 256, 0, s>>>(hh, cc, dko, nr, uniform_slots, (const u64*)d_rro[b], 0, max_slots, (Hit*)d_runs[b]);
           MZ_CUDA(cudaGetLastError());
-          if (ns) MZ_CUDA(cudaMemcpyAsync(ro->codes + s0, d_codes[b], ns, cudaMemcpyDeviceToHost, s));
+          copy_codes(b, s0, ns, s);
           MZ_CUDA(cudaMemcpyAsync(h_rro[b], d_rro[b], (nr + 1) * 8, cudaMemcpyDeviceToHost, s));
           if (c > 0) finish_runs(c - 1, b ^ 1);  // the previous chunk finishes while this one runs
         }
@@ -785,6 +883,95 @@ mazu_status_t mazu_b200_query_reads_runs(const mazu_index_t* idx, const uint8_t*
     return MAZU_ERR_INVALID_ARG;
   }
   return rc;
+}
+
+mazu_status_t mazu_b200_query_reads_runs_packed(const mazu_index_t* idx, const uint64_t* packed_reads, const uint64_t* n_mask, uint64_t n_reads,
+                                                uint64_t read_len, int32_t mode, uint8_t* out_codes2, mazu_hit_t* out_runs, uint64_t cap_runs,
+                                                uint64_t* out_read_run_offsets, uint64_t* out_n_runs, uint64_t* counts) {
+  if (!read_len || (n_reads && !packed_reads)) {
+    g_err = "packed reads are uniform: read_len > 0 and packed_reads are required";
+    return MAZU_ERR_INVALID_ARG;
+  }
+  if (idx && ((read_len >= idx->unitigs->k ? read_len - idx->unitigs->k + 1 : 0) & 3)) {
+    g_err = "packed codes need a multiple of 4 k-mer slots per read (read_len - k + 1)";
+    return MAZU_ERR_INVALID_ARG;
+  }
+  RunsOut ro{out_codes2, out_runs, cap_runs, out_read_run_offsets};
+  ro.packed_words = packed_reads;
+  ro.packed_nmask = n_mask;
+  ro.codes2 = true;
+  mazu_status_t rc = query_reads_impl(idx, nullptr, nullptr, n_reads, read_len, mode, nullptr, nullptr, 0, counts, MAZU_MEM_HOST, nullptr, &ro);
+  if (out_n_runs) *out_n_runs = ro.n_runs;
+  if (rc == MAZU_OK && ro.n_runs > cap_runs) {
+    g_err = "run capacity too small: need " + std::to_string(ro.n_runs) + " records";
+    return MAZU_ERR_INVALID_ARG;
+  }
+  return rc;
+}
+
+mazu_status_t mazu_b200_pack_reads(const uint8_t* bases, uint64_t n_reads, uint64_t read_len, uint64_t* out_words, uint64_t* out_n_mask,
+                                   uint64_t* n_non_acgt) {
+  return guarded([&] {
+    if (!read_len || (n_reads && (!bases || !out_words))) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    const u64 wpr = (read_len + 31) / 32, mpr = (read_len + 63) / 64;
+    std::atomic<u64> bad{0};
+    parallel_ranges(n_reads, host_threads(), [&](unsigned, u64 lo, u64 hi) {
+      u64 nb = 0;
+      for (u64 r = lo; r < hi; ++r) {
+        u64* w = out_words + r * wpr;
+        u64* m = out_n_mask ? out_n_mask + r * mpr : nullptr;
+        for (u64 j = 0; j < wpr; ++j) w[j] = 0;
+        if (m)
+          for (u64 j = 0; j < mpr; ++j) m[j] = 0;
+        const u8* b = bases + r * read_len;
+        for (u64 j = 0; j < read_len; ++j) {
+          const u32 c = base_code(b[j]);
+          if (c > 3) {
+            ++nb;
+            if (m) m[j >> 6] |= 1ULL << (j & 63);
+          } else {
+            w[j >> 5] |= (u64)c << (2 * (j & 31));
+          }
+        }
+      }
+      bad += nb;
+    });
+    if (n_non_acgt) *n_non_acgt = bad.load();
+  });
+}
+
+mazu_status_t mazu_b200_expand_hit_runs_packed(const uint8_t* codes2, const mazu_hit_t* runs, const uint64_t* read_run_offsets, uint64_t n_reads,
+                                               uint64_t uniform_slots, mazu_hit_t* out_hits) {
+  return guarded([&] {
+    if (n_reads && (!codes2 || !read_run_offsets || !out_hits)) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    parallel_ranges(n_reads, host_threads(), [&](unsigned, u64 lo, u64 hi) {
+      for (u64 r = lo; r < hi; ++r) {
+        const u64 s0 = r * uniform_slots;
+        u64 ri = read_run_offsets[r];
+        mazu_hit_t prev{~0u, ~0u, ~0u, MAZU_NO_MATCH};
+        for (u64 i = 0; i < uniform_slots; ++i) {
+          const u64 s = s0 + i;
+          mazu_hit_t h{~0u, ~0u, ~0u, MAZU_NO_MATCH};
+          switch ((codes2[s >> 2] >> (2 * (s & 3))) & 3u) {
+            case 1:
+              h = prev;
+              h.pos = prev.match == MAZU_IDENTITY_MATCH ? prev.pos + 1u : prev.pos - 1u;
+              break;
+            case 2:
+              h = runs[ri++];
+              break;
+            case 3:
+              h.match = MAZU_SKIPPED;
+              break;
+            default:
+              break;
+          }
+          out_hits[s] = h;
+          prev = h;
+        }
+      }
+    });
+  });
 }
 
 mazu_status_t mazu_b200_expand_hit_runs(const uint8_t* codes, const mazu_hit_t* runs, const uint64_t* read_run_offsets,
@@ -1195,48 +1382,42 @@ static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu
   }
 }
 
-// fused reads -> MappedRefPos (get_ref_pos_reads_kernel); device pointers, work enqueued on `s`
+// reads -> MappedRefPos by tiles (get_ref_pos_pass1_kernel -> scan over tiles -> get_ref_pos_pass2_kernel); device pointers, work on `s`
 static void launch_get_ref_pos_reads(const mazu_index_t* idx, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len,
                                      const u64* d_kmer_offsets, Hit* d_hits, u64* d_counts, u64 n_slots, u64* d_offsets, OccRec* d_out, u64 cap,
                                      u64* d_total, cudaStream_t s) {
-  const u32 k = idx->unitigs->k;
-  std::unique_ptr<PoolBuf> cnt, seg;
-  u64 n_tiles;
-  if (uniform_len) {
-    const u64 nk = uniform_len >= k ? uniform_len - k + 1 : 0;
-    n_tiles = n_reads * (nk <= (u64)QR_CHUNK ? 1 : (nk + QR_CHUNK - 1) / QR_CHUNK);
-  } else {  // one tile per chunk of QR_CHUNK k-mer positions, at least one per read
-    cnt = std::make_unique<PoolBuf>(idx->pool, (n_reads + 1) * 8, s);
-    seg = std::make_unique<PoolBuf>(idx->pool, (n_reads + 1) * 8, s);
-    MZ_CUDA(cudaMemsetAsync(cnt->p, 0, (n_reads + 1) * 8, s));
-    segment_counts_kernel<<<(int)std::min<u64>((n_reads + 255) / 256, 4096), 256, 0, s>>>(d_read_offsets, n_reads, k, (u64)QR_CHUNK, (u64*)cnt->p);
-    MZ_CUDA(cudaGetLastError());
-    device_exclusive_scan((const u64*)cnt->p, (u64*)seg->p, n_reads, idx->pool, s);
-    MZ_CUDA(cudaMemcpyAsync(&n_tiles, (u64*)seg->p + n_reads, 8, cudaMemcpyDeviceToHost, s));
-    MZ_CUDA(cudaStreamSynchronize(s));
-  }
-  PoolBuf status(idx->pool, (n_tiles + 1) * 8, s), ticket(idx->pool, 8, s);
-  MZ_CUDA(cudaMemsetAsync(status.p, 0, (n_tiles + 1) * 8, s));
-  MZ_CUDA(cudaMemsetAsync(ticket.p, 0, 8, s));
-  ProjOut pj{(unsigned long long*)status.p, (unsigned long long*)ticket.p, d_offsets, d_out, cap, n_slots, n_tiles, d_total};
+  TileTable tt;
+  make_tiles(idx, d_read_offsets, n_reads, uniform_len, ~0ULL, s, tt);
+  const u64 n_tiles = tt.n_tiles;
   if (n_tiles == 0) {
     MZ_CUDA(cudaMemsetAsync(d_offsets, 0, 8, s));
     if (d_total) MZ_CUDA(cudaMemsetAsync(d_total, 0, 8, s));
     return;
   }
+  std::unique_ptr<PoolBuf> tmp_hits;
+  if (!d_hits) {  // the caller does not want the K2UPos records: they still carry pass 1's answers to pass 2
+    tmp_hits = std::make_unique<PoolBuf>(idx->pool, n_slots * 16 + 16, s);
+    d_hits = (Hit*)tmp_hits->p;
+  }
+  PoolBuf totals(idx->pool, (n_tiles + 1) * 8, s), base(idx->pool, (n_tiles + 1) * 8, s);
+  MZ_CUDA(cudaMemsetAsync((u64*)totals.p + n_tiles, 0, 8, s));
+  TileMap tm{d_read_offsets, d_kmer_offsets, tt.seg ? (const u64*)tt.seg->p : nullptr, n_reads, uniform_len, n_tiles};
   const bool ss = idx->view.k2u_kind == MAZU_K2U_SSHASH, boophf = idx->view.mphf.family == MPHF_FAMILY_BOOPHF;
-#define MZ_GRP(K, F)                                                                                                              \
-  {                                                                                                                                \
-    auto kern = get_ref_pos_reads_kernel<K, F>;                                                                                    \
-    int grid = grid_for(kern, QR_WARPS * 32, idx, 1, ~0ULL >> 8);                                                                  \
-    kern<<<grid, QR_WARPS * 32, 0, s>>>(idx->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_hits,          \
-                                        (unsigned long long*)d_counts, seg ? (const u64*)seg->p : nullptr, pj);                    \
+#define MZ_GRP(K, F)                                                                                                     \
+  {                                                                                                                       \
+    auto kern = get_ref_pos_pass1_kernel<K, F>;                                                                           \
+    int grid = grid_for(kern, QR_WARPS * 32, idx, QR_WARPS, n_tiles);                                                     \
+    kern<<<grid, QR_WARPS * 32, 0, s>>>(idx->view, d_bases, tm, d_hits, (unsigned long long*)d_counts, (u64*)totals.p);   \
   }
   if (ss) MZ_GRP(MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE)
   else if (idx->view.k2u_kind == MAZU_K2U_SAMPLED_PFHASH) MZ_GRP(MAZU_K2U_SAMPLED_PFHASH, MPHF_FAMILY_BOOPHF)
   else if (boophf) MZ_GRP(MAZU_K2U_PFHASH, MPHF_FAMILY_BOOPHF)
   else MZ_GRP(MAZU_K2U_PFHASH, MPHF_FAMILY_NATIVE)
 #undef MZ_GRP
+  MZ_CUDA(cudaGetLastError());
+  device_exclusive_scan((const u64*)totals.p, (u64*)base.p, n_tiles, idx->pool, s);
+  const int grid2 = (int)std::max<u64>(1, std::min<u64>((n_tiles + 7) / 8, (u64)idx->sm_count * 8));
+  get_ref_pos_pass2_kernel<<<grid2, 256, 0, s>>>(idx->view, tm, d_hits, (const u64*)base.p, n_slots, d_offsets, d_out, cap, d_total);
   MZ_CUDA(cudaGetLastError());
 }
 
@@ -1304,6 +1485,11 @@ mazu_status_t mazu_b200_get_ref_pos_reads(const mazu_index_t* idx, const uint8_t
       kmer_counts_kernel<<<(int)std::min<u64>((n_reads + 255) / 256, 4096), 256, 0, s>>>(read_offsets, n_reads, k, (u64*)lens.p);
       MZ_CUDA(cudaGetLastError());
       device_exclusive_scan((const u64*)lens.p, d_koffs, n_reads, idx->pool, s);
+    }
+    if (n_reads == 0) {  // nothing to look up: an empty prefix
+      MZ_CUDA(cudaMemsetAsync(out_offsets, 0, 8, s));
+      if (out_total) *out_total = 0;
+      return;
     }
     if (out_total) d_tot = std::make_unique<PoolBuf>(idx->pool, 8, s);
     if (mode == MAZU_MODE_STREAMING && !idx->kmers_unique) {

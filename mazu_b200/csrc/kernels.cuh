@@ -879,6 +879,32 @@ __global__ void hit_run_advance_kernel(u64* __restrict__ base_ptr, const u64* __
   if (blockIdx.x == 0 && threadIdx.x == 0) *base_ptr += *chunk_total;
 }
 
+// 2-bit packed reads (kmers::SeqVector layout: base j of a read at bits [2j, 2j+2) of its words, A0 C1 G2 T3) -> ASCII, for
+// callers that ship reads 2-bit packed over PCIe (0.25 byte per base instead of 1).  n_mask (optional, 1 bit per base, word
+// stride ceil(read_len / 64) per read): set bit = the base is not ACGT and becomes 'N'.
+__global__ void __launch_bounds__(256) unpack_reads_kernel(const u64* __restrict__ words, const u64* __restrict__ n_mask, u64 n_reads, u64 read_len,
+                                                           u8* __restrict__ bases) {
+  const u64 wpr = (read_len + 31) / 32, mpr = (read_len + 63) / 64, total = n_reads * read_len;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
+    const u64 r = i / read_len, j = i - r * read_len;
+    const u32 c = (u32)(words[r * wpr + (j >> 5)] >> (2 * (j & 31))) & 3u;
+    u8 ch = (u8)((0x54474341u >> (8 * c)) & 0xFFu);  // "ACGT"
+    if (n_mask && ((n_mask[r * mpr + (j >> 6)] >> (j & 63)) & 1ULL)) ch = (u8)'N';
+    bases[i] = ch;
+  }
+}
+// run codes, one byte per slot -> 2 bits per slot (slot s at bits [2 (s & 3), 2 (s & 3) + 2) of byte s >> 2)
+__global__ void __launch_bounds__(256) pack_codes_kernel(const u8* __restrict__ codes, u64 n_slots, u8* __restrict__ out) {
+  const u64 nb = (n_slots + 3) / 4;
+  for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (u64)gridDim.x * blockDim.x) {
+    u32 x = 0;
+#pragma unroll
+    for (u32 q = 0; q < 4; ++q)
+      if (4 * b + q < n_slots) x |= (u32)(codes[4 * b + q] & 3u) << (2 * q);
+    out[b] = (u8)x;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K4: U2Pos decode / projection
 // ---------------------------------------------------------------------------------------------
@@ -914,100 +940,67 @@ __device__ __forceinline__ OccRec project_occ(u32 k, const Hit& h, const OccRec&
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused GetRefPos::get_ref_pos over reads (src/index.rs:156-216 + the read loop of validate_ckmers): reads -> K2UPos ->
-// occurrence list -> MappedRefPos in ONE kernel.  The unfused chain writes the 16-byte hit records, re-reads them twice
-// (list lengths, fill) and scans per-slot lengths in between; here a warp keeps the hits of its tile (one chunk of <= 128
-// k-mer positions) in its shared-memory stage, scans the list lengths with shuffles, and obtains the tile's position in
-// the output with a single-pass decoupled look-back over one status word per tile (flag << 62 | value): the only global
-// traffic besides the lookups is 8 bytes of offset per slot and the 12-byte records themselves.
-// Tiles are handed out in order by a ticket counter, so a tile only ever waits for tiles that are already running.
+// GetRefPos::get_ref_pos over reads (src/index.rs:156-216 + the read loop of validate_ckmers): reads -> K2UPos ->
+// occurrence list -> MappedRefPos, organised by TILES (one chunk of <= QR_CHUNK k-mer positions of one read) so that
+// the variable-length output needs a scan over tiles only, not over slots, and no search:
+//   pass 1  get_ref_pos_pass1_kernel   the lookups of query_reads_kernel; the warp also sums the occurrence-list lengths
+//                                      of its tile's hits while they are in its shared-memory stage -> tile_totals[tile]
+//   scan    exclusive scan of tile_totals (n_tiles items: 1/120 of the per-slot scan of the unfused chain)
+//   pass 2  get_ref_pos_pass2_kernel   a warp re-reads its tile's hit records (coalesced), scans the list lengths with
+//                                      shuffles, and writes the slot offsets and the projected records at tile_base + local
+// against the unfused chain (occ_lens_kernel over every slot -> per-slot scan -> fill with a search per tile of the output).
+// (A single-kernel version with a ticket counter and decoupled look-back was built first and measured SLOWER than the
+// unfused chain, 32 vs 25 ms for 4.8e8 slots: with 4,736 warps in flight a tile walks back through thousands of
+// predecessors that have published an aggregate but not yet an inclusive prefix.)
 // ---------------------------------------------------------------------------------------------
-struct ProjOut {
-  unsigned long long* status;  // one word per tile, zeroed before the launch
-  unsigned long long* ticket;  // next tile, zeroed before the launch
-  u64* out_offsets;            // n_slots + 1
-  OccRec* out;                 // `cap` records
-  u64 cap;
-  u64 n_slots;
-  u64 n_tiles;
-  u64* out_total;              // optional device word
+struct TileMap {  // tile -> (read, first k-mer position): arithmetic for uniform reads, seg_offsets for ragged ones
+  const u64* read_offsets;
+  const u64* kmer_offsets;
+  const u64* seg_offsets;
+  u64 n_reads, uniform_len, n_tiles;
 };
-static const unsigned long long PJ_AGG = 1ULL << 62, PJ_INCL = 2ULL << 62, PJ_VAL = (1ULL << 62) - 1ULL;
-
-__device__ __forceinline__ u64 tile_exclusive_prefix(unsigned long long* status, u64 tile, u64 aggregate, u32 lane) {
-  if (tile == 0) {
-    if (lane == 0) atomicExch(status, PJ_INCL | aggregate);
-    return 0;
+__device__ __forceinline__ void tile_locate(const TileMap& tm, u32 k, u64 tile, u64& beg, u64& len, u64& slot0, u64& c0, u32& n_c) {
+  u64 r;
+  if (tm.uniform_len) {
+    const u64 nk = tm.uniform_len >= k ? tm.uniform_len - k + 1 : 0;
+    const u64 cpr = nk <= (u64)QR_CHUNK ? 1 : (nk + QR_CHUNK - 1) / QR_CHUNK;
+    r = tile / cpr;
+    c0 = (tile - r * cpr) * QR_CHUNK;
+    beg = r * tm.uniform_len;
+    len = tm.uniform_len;
+    slot0 = r * nk;
+  } else {
+    u64 lo = 0, hi = tm.n_reads;  // largest r with seg_offsets[r] <= tile
+    while (hi - lo > 1) {
+      u64 mid = (lo + hi) >> 1;
+      if (tm.seg_offsets[mid] <= tile) lo = mid; else hi = mid;
+    }
+    r = lo;
+    c0 = (tile - tm.seg_offsets[r]) * QR_CHUNK;
+    beg = tm.read_offsets[r];
+    len = tm.read_offsets[r + 1] - beg;
+    slot0 = tm.kmer_offsets[r];
   }
-  if (lane == 0) atomicExch(status + tile, PJ_AGG | aggregate);
-  u64 excl = 0;
-  long long base = (long long)tile - 1;
-  while (true) {
-    const long long i = base - (long long)lane;
-    unsigned long long v = PJ_INCL;  // before tile 0: an inclusive prefix of 0
-    if (i >= 0) v = *reinterpret_cast<volatile unsigned long long*>(status + i);
-    const u32 flag = (u32)(v >> 62);
-    const u32 incl = __ballot_sync(0xffffffffu, flag == 2u), invalid = __ballot_sync(0xffffffffu, flag == 0u);
-    const u32 first = incl ? (u32)__ffs(incl) - 1u : 32u;                      // nearest predecessor with an inclusive prefix
-    const u32 upto = first >= 31u ? 0xffffffffu : ((2u << first) - 1u);        // lanes whose value is needed
-    if (invalid & upto) continue;                                              // a needed predecessor has not published yet
-    u64 x = ((1u << lane) & upto) ? (u64)(v & PJ_VAL) : 0ULL;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-    excl += x;
-    if (first < 32u) break;
-    base -= 32;
-  }
-  if (lane == 0) atomicExch(status + tile, PJ_INCL | (excl + aggregate));
-  return excl;
+  const u64 nk = len >= k ? len - k + 1 : 0;
+  n_c = c0 < nk ? (u32)min((u64)QR_CHUNK, nk - c0) : 0u;
 }
 
 template <int KIND, u32 FAMILY>
-__global__ void __launch_bounds__(QR_WARPS * 32, 3) get_ref_pos_reads_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
-                                                                            const u64* __restrict__ read_offsets, u64 n_reads, u64 uniform_len,
-                                                                            const u64* __restrict__ kmer_offsets, Hit* __restrict__ out_hits,
-                                                                            unsigned long long* __restrict__ counts,
-                                                                            const u64* __restrict__ seg_offsets, const ProjOut pj) {
+__global__ void __launch_bounds__(QR_WARPS * 32, 4) get_ref_pos_pass1_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
+                                                                            const TileMap tm, Hit* __restrict__ out_hits,
+                                                                            unsigned long long* __restrict__ counts, u64* __restrict__ tile_totals) {
   __shared__ WarpStage s_stage[QR_WARPS];
   const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   WarpStage& S = s_stage[wib];
   const u32 k = ix.unitigs.k;
   constexpr bool SS = KIND == MAZU_K2U_SSHASH;
   u32 n_valid = 0, n_hit = 0;
-  // tiles: chunk c of read r.  Uniform reads: arithmetic; ragged reads: seg_offsets (segments of QR_CHUNK k-mer positions)
-  const u64 uni_nk = uniform_len >= k ? uniform_len - k + 1 : 0;
-  const u64 uni_cpr = uni_nk <= QR_CHUNK ? 1 : (uni_nk + QR_CHUNK - 1) / QR_CHUNK;
-  while (true) {
-    unsigned long long tile = 0;
-    if (lane == 0) tile = atomicAdd(pj.ticket, 1ULL);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= pj.n_tiles) break;
-    u64 r, c0;
-    if (uniform_len) {
-      r = tile / uni_cpr;
-      c0 = (tile - r * uni_cpr) * QR_CHUNK;
-    } else {
-      u64 lo = 0, hi = n_reads;  // largest r with seg_offsets[r] <= tile
-      while (hi - lo > 1) {
-        u64 mid = (lo + hi) >> 1;
-        if (seg_offsets[mid] <= tile) lo = mid; else hi = mid;
-      }
-      r = lo;
-      c0 = (tile - seg_offsets[r]) * QR_CHUNK;
-    }
-    u64 beg, len, slot0;
-    if (uniform_len) {
-      beg = r * uniform_len;
-      len = uniform_len;
-      slot0 = r * uni_nk;
-    } else {
-      beg = read_offsets[r];
-      len = read_offsets[r + 1] - beg;
-      slot0 = kmer_offsets[r];
-    }
-    const u64 nk = len >= k ? len - k + 1 : 0;
-    const u32 n_c = c0 < nk ? (u32)min((u64)QR_CHUNK, nk - c0) : 0u;
+  for (u64 tile = (u64)blockIdx.x * QR_WARPS + wib; tile < tm.n_tiles; tile += (u64)gridDim.x * QR_WARPS) {
+    u64 beg, len, slot0, c0;
+    u32 n_c;
+    tile_locate(tm, k, tile, beg, len, slot0, c0, n_c);
     __syncwarp();
+    u32 total = 0;
     if (n_c) {
       ChunkInfo ci;
       stage_encode(bases + beg, len, c0, n_c, k, lane, S, ci);
@@ -1016,7 +1009,6 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 3) get_ref_pos_reads_kernel(con
 #pragma unroll 1
       for (u32 p = lane; p < n_c; p += 32) {
         Hit h = hit_none(SKIPPED);
-        u32 n_occ = 0;
         if (chunk_valid(ci, p)) {
           u64 fw = S.fw[p], rc = SS ? S.rc[p] : revcomp(fw, k);
           bool ok = SS ? verify_sshash<FAMILY>(ix, S, p, fw, rc, h)
@@ -1026,59 +1018,77 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 3) get_ref_pos_reads_kernel(con
             ++n_hit;
             u64 s, e;
             occ_range(ix, h.unitig_id, s, e);  // U2Pos::encoded_unitig_occs
-            n_occ = (u32)(e - s);
+            total += (u32)(e - s);
           } else {
             h = hit_none(NO_MATCH);
           }
         }
-        if (out_hits) store_hit(out_hits + slot0 + c0 + p, h);
-        // the hit stays in the warp's stage: slot p of fw / rc is only ever read by the lane that owns p
-        S.fw[p] = (u64)h.unitig_id | ((u64)h.pos << 32);
-        S.rc[p] = (u64)h.unitig_len | ((u64)h.match << 32);
-        S.hf[p] = n_occ;
+        store_hit(out_hits + slot0 + c0 + p, h);
       }
     }
-    __syncwarp();
-    // list lengths -> exclusive offsets inside the tile (slot order: p = 32 t + lane)
-    u32 ex[4], cnt[4], carry = 0;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const u32 p = 32 * t + lane;
-      const u32 v = p < n_c ? S.hf[p] : 0u;
-      u32 inc = v;
+    for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+    if (lane == 0) tile_totals[tile] = total;
+  }
+  if (counts) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      n_valid += __shfl_xor_sync(0xffffffffu, n_valid, d);
+      n_hit += __shfl_xor_sync(0xffffffffu, n_hit, d);
+    }
+    if (lane == 0 && n_valid) {
+      atomicAdd(counts + 0, (unsigned long long)n_valid);
+      atomicAdd(counts + 1, (unsigned long long)n_hit);
+      atomicAdd(counts + 2, (unsigned long long)(n_valid - n_hit));
+    }
+  }
+}
+
+// pass 2: tile_base = exclusive scan of tile_totals (n_tiles + 1 entries, the last one the total)
+__global__ void __launch_bounds__(256) get_ref_pos_pass2_kernel(const __grid_constant__ IndexView ix, const TileMap tm, const Hit* __restrict__ hits,
+                                                                const u64* __restrict__ tile_base, u64 n_slots, u64* __restrict__ out_offsets,
+                                                                OccRec* __restrict__ out, u64 cap, u64* __restrict__ out_total) {
+  const u32 lane = threadIdx.x & 31;
+  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  const u32 k = ix.unitigs.k;
+  if (warp == 0 && lane == 0) {
+    out_offsets[n_slots] = tile_base[tm.n_tiles];
+    if (out_total) *out_total = tile_base[tm.n_tiles];
+  }
+  for (u64 tile = warp; tile < tm.n_tiles; tile += n_warps) {
+    u64 beg, len, slot0, c0;
+    u32 n_c;
+    tile_locate(tm, k, tile, beg, len, slot0, c0, n_c);
+    u64 o = tile_base[tile];
+#pragma unroll 1
+    for (u32 p0 = 0; p0 < n_c; p0 += 32) {
+      const u32 p = p0 + lane;
+      const bool mine = p < n_c;
+      Hit h = hit_none(NO_MATCH);
+      u64 first = 0;
+      u32 cnt = 0;
+      if (mine) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(hits + slot0 + c0 + p));
+        h = Hit{q.x, q.y, q.z, q.w};
+        if (h.match == IDENTITY_MATCH || h.match == TWIN_MATCH) {
+          u64 e;
+          occ_range(ix, h.unitig_id, first, e);
+          cnt = (u32)(e - first);
+        }
+      }
+      u32 inc = cnt;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const u32 y = __shfl_up_sync(0xffffffffu, inc, d);
         if (lane >= (u32)d) inc += y;
       }
-      cnt[t] = v;
-      ex[t] = carry + inc - v;
-      carry += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    const u64 E = tile_exclusive_prefix(pj.status, tile, carry, lane);
-    if (tile == pj.n_tiles - 1 && lane == 0) {
-      pj.out_offsets[pj.n_slots] = E + carry;
-      if (pj.out_total) *pj.out_total = E + carry;
-    }
-    // offsets of the tile's slots, then the projected records (project_onto_u_occ, index.rs:194-216)
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const u32 p = 32 * t + lane;
-      const bool mine = p < n_c;
-      if (mine) pj.out_offsets[slot0 + c0 + p] = E + ex[t];
-      Hit h = hit_none(NO_MATCH);
-      u64 first = 0;
-      if (mine && cnt[t]) {
-        const u64 a = S.fw[p], b = S.rc[p];
-        h = Hit{(u32)a, (u32)b, (u32)(a >> 32), (u32)(b >> 32)};
-        first = packed_get(ix.contig_offsets, h.unitig_id);
-      }
-      const u64 o0 = E + ex[t];
-      // long lists are written by the whole warp, short ones by their lane
-      u32 big = __ballot_sync(0xffffffffu, mine && cnt[t] >= 32u);
-      if (mine && cnt[t] < 32u)
-        for (u32 j = 0; j < cnt[t]; ++j)
-          if (o0 + j < pj.cap) pj.out[o0 + j] = project_occ(k, h, occ_decode(ix, first + j));
+      const u64 o0 = o + inc - cnt;
+      if (mine) out_offsets[slot0 + c0 + p] = o0;
+      // short lists are written by their lane, long ones by the whole warp (project_onto_u_occ, index.rs:194-216)
+      u32 big = __ballot_sync(0xffffffffu, cnt >= 32u);
+      if (cnt < 32u)
+        for (u32 j = 0; j < cnt; ++j)
+          if (o0 + j < cap) out[o0 + j] = project_occ(k, h, occ_decode(ix, first + j));
       while (big) {
         const int src = __ffs(big) - 1;
         big &= big - 1;
@@ -1088,9 +1098,123 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 3) get_ref_pos_reads_kernel(con
         hb.pos = __shfl_sync(0xffffffffu, h.pos, src);
         hb.match = __shfl_sync(0xffffffffu, h.match, src);
         const u64 fb = __shfl_sync(0xffffffffu, first, src), ob = __shfl_sync(0xffffffffu, o0, src);
-        const u32 nb = __shfl_sync(0xffffffffu, cnt[t], src);
+        const u32 nb = __shfl_sync(0xffffffffu, cnt, src);
         for (u32 j = lane; j < nb; j += 32)
-          if (ob + j < pj.cap) pj.out[ob + j] = project_occ(k, hb, occ_decode(ix, fb + j));
+          if (ob + j < cap) out[ob + j] = project_occ(k, hb, occ_decode(ix, fb + j));
+      }
+      o += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused hit runs: reads -> K2UPos -> run codes + run records in ONE kernel (the host result of a read batch, see "Hit runs"
+// above), for batches whose reads all fit one chunk (<= QR_CHUNK k-mer positions: every short-read batch).  A warp owns a
+// read: it derives every slot's code from its neighbour's hit with shuffles, counts the run starts, reserves that many
+// records with ONE atomicAdd on the batch's run cursor, and writes one code byte per slot + the 16-byte record of every
+// run start.  The runs of a read are consecutive; the order of different reads' runs in the array is whatever order the
+// warps reserved them in -- read_run_offsets[r] says where read r's runs start, which is all the decoder needs.
+// Replaces query_reads_kernel (16 B per slot written) + hit_run_codes_kernel (16 B per slot read) + scan + hit_run_fill_kernel.
+// (An ordered single-pass layout was built first -- tickets + decoupled look-back over one status word per tile -- and
+// measured 2x slower than the kernels it replaced: with 4,736 warps in flight a tile walks back through thousands of
+// predecessors that have published an aggregate but not yet an inclusive prefix.)
+// ---------------------------------------------------------------------------------------------
+struct RunsTileOut {
+  u8* codes;                   // one byte per k-mer slot
+  Hit* runs;                   // run records, chunk-local indexes
+  u64* read_run_offsets;       // n_reads entries: index of every read's first run
+  unsigned long long* cursor;  // next free run record (zeroed before the launch; the batch's run count afterwards)
+  u64 cap;                     // capacity of `runs`
+};
+
+template <int KIND, u32 FAMILY>
+__global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
+                                                                           const u64* __restrict__ read_offsets, u64 n_reads, u64 uniform_len,
+                                                                           const u64* __restrict__ kmer_offsets, unsigned long long* __restrict__ counts,
+                                                                           const RunsTileOut ro) {
+  __shared__ WarpStage s_stage[QR_WARPS];
+  const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  WarpStage& S = s_stage[wib];
+  const u32 k = ix.unitigs.k;
+  constexpr bool SS = KIND == MAZU_K2U_SSHASH;
+  u32 n_valid = 0, n_hit = 0;
+  for (u64 r = (u64)blockIdx.x * QR_WARPS + wib; r < n_reads; r += (u64)gridDim.x * QR_WARPS) {
+    u64 beg, len, slot0;
+    if (uniform_len) {
+      beg = r * uniform_len;
+      len = uniform_len;
+      slot0 = uniform_len >= k ? r * (uniform_len - k + 1) : 0;
+    } else {
+      beg = read_offsets[r];
+      len = read_offsets[r + 1] - beg;
+      slot0 = kmer_offsets[r];
+    }
+    const u32 n_c = len >= k ? (u32)min((u64)QR_CHUNK, len - k + 1) : 0u;  // the launcher guarantees len - k + 1 <= QR_CHUNK
+    __syncwarp();
+    Hit hh[4];
+    u32 code[4], n_runs = 0;
+    if (n_c) {
+      ChunkInfo ci;
+      stage_encode(bases + beg, len, 0, n_c, k, lane, S, ci);
+      __syncwarp();
+      if (SS) stage_buckets<FAMILY>(ix, ci, lane, S);
+      // one copy of the lookup (the loop is not unrolled: instruction-cache footprint); hits are parked in the warp's stage
+#pragma unroll 1
+      for (u32 p = lane; p < n_c; p += 32) {
+        Hit h = hit_none(SKIPPED);
+        if (chunk_valid(ci, p)) {
+          u64 fw = S.fw[p], rc = SS ? S.rc[p] : revcomp(fw, k);
+          bool ok = SS ? verify_sshash<FAMILY>(ix, S, p, fw, rc, h)
+                       : (KIND == MAZU_K2U_SAMPLED_PFHASH ? sampled_pfhash_k2u_t<FAMILY>(ix, fw, rc, h, nullptr) : pfhash_k2u_t<FAMILY>(ix, fw, rc, h));
+          ++n_valid;
+          if (ok) ++n_hit; else h = hit_none(NO_MATCH);
+        }
+        S.fw[p] = (u64)h.unitig_id | ((u64)h.pos << 32);
+        S.rc[p] = (u64)h.unitig_len | ((u64)h.match << 32);
+      }
+      __syncwarp();
+      Hit carry = hit_none(NO_MATCH);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const u32 p = 32 * t + lane;
+        Hit h = hit_none(SKIPPED);
+        if (p < n_c) {
+          const u64 a = S.fw[p], b = S.rc[p];
+          h = Hit{(u32)a, (u32)b, (u32)(a >> 32), (u32)(b >> 32)};
+        }
+        Hit pv;
+        pv.unitig_id = __shfl_up_sync(0xffffffffu, h.unitig_id, 1);
+        pv.unitig_len = 0;
+        pv.pos = __shfl_up_sync(0xffffffffu, h.pos, 1);
+        pv.match = __shfl_up_sync(0xffffffffu, h.match, 1);
+        if (lane == 0) pv = carry;
+        code[t] = run_code_of(h, pv, p > 0);
+        hh[t] = h;
+        n_runs += __popc(__ballot_sync(0xffffffffu, p < n_c && code[t] == RUN_START));
+        carry.unitig_id = __shfl_sync(0xffffffffu, h.unitig_id, 31);
+        carry.pos = __shfl_sync(0xffffffffu, h.pos, 31);
+        carry.match = __shfl_sync(0xffffffffu, h.match, 31);
+      }
+    }
+    unsigned long long E = 0;
+    if (lane == 0) {
+      E = n_runs ? atomicAdd(ro.cursor, (unsigned long long)n_runs) : 0ULL;
+      ro.read_run_offsets[r] = E;
+    }
+    E = __shfl_sync(0xffffffffu, E, 0);
+    if (n_c) {
+      u64 o = E;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const u32 p = 32 * t + lane;
+        const bool start = p < n_c && code[t] == RUN_START;
+        const u32 m = __ballot_sync(0xffffffffu, start);
+        if (p < n_c) ro.codes[slot0 + p] = (u8)code[t];
+        if (start) {
+          const u64 dst = o + __popc(m & ((1u << lane) - 1u));
+          if (dst < ro.cap) store_hit(ro.runs + dst, hh[t]);
+        }
+        o += __popc(m);
       }
     }
   }

@@ -137,6 +137,50 @@ def test_hit_run_decoder_round_trip():
         assert len(runs) < n // 8
 
 
+def test_pack_reads_and_packed_run_decoder():
+    """host halves of the packed run interface (no device work): mazu_b200_pack_reads against numpy bit packing, and
+    mazu_b200_expand_hit_runs_packed against mazu_b200_expand_hit_runs on the same runs with 2-bit codes."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    n_reads, read_len, k = 300, 150, 31
+    bases = np.frombuffer(b"ACGTacgtNx", dtype=np.uint8)[rng.choice(10, size=n_reads * read_len, p=[.2, .2, .2, .2, .04, .04, .04, .04, .02, .02])].copy()
+    words, mask, bad = mz.pack_reads(bases, read_len)
+    codes = np.full(256, 4, dtype=np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        codes[ch] = i
+        codes[ch | 0x20] = i
+    c = codes[bases].reshape(n_reads, read_len)
+    assert bad == int((c == 4).sum())
+    wpr, mpr = (read_len + 31) // 32, (read_len + 63) // 64
+    want_w = np.zeros((n_reads, wpr), dtype=np.uint64)
+    want_m = np.zeros((n_reads, mpr), dtype=np.uint64)
+    for j in range(read_len):
+        want_w[:, j // 32] |= np.where(c[:, j] < 4, c[:, j], 0).astype(np.uint64) << np.uint64(2 * (j % 32))
+        want_m[:, j // 64] |= (c[:, j] == 4).astype(np.uint64) << np.uint64(j % 64)
+    assert np.array_equal(words.reshape(n_reads, wpr), want_w) and np.array_equal(mask.reshape(n_reads, mpr), want_m)
+    # decoder: random codes / runs, byte codes vs 2-bit codes
+    slots = read_len - k + 1
+    code = rng.choice(4, size=n_reads * slots, p=[.4, .45, .05, .1]).astype(np.uint8)
+    code.reshape(n_reads, slots)[:, 0] = np.where(code.reshape(n_reads, slots)[:, 0] == 1, 2, code.reshape(n_reads, slots)[:, 0])  # a read never starts with "continues"
+    flat = code.reshape(-1)
+    for i in range(1, len(flat)):  # "continues" must follow a hit
+        if flat[i] == 1 and flat[i - 1] not in (1, 2):
+            flat[i] = 2
+    runs = np.zeros(int((flat == 2).sum()), dtype=mz.HIT_DTYPE)
+    runs["unitig_id"] = rng.integers(0, 1000, len(runs))
+    runs["unitig_len"] = 5000
+    runs["pos"] = rng.integers(200, 4000, len(runs))
+    runs["match"] = rng.integers(1, 3, len(runs))
+    rro = np.concatenate([[0], np.cumsum((flat == 2).reshape(n_reads, slots).sum(axis=1))]).astype(np.uint64)
+    want = mz.ModIndex.expand_hit_runs(flat, runs, rro, uniform_slots=slots)
+    packed = np.zeros((len(flat) + 3) // 4, dtype=np.uint8)
+    for q in range(4):
+        part = flat[q::4]
+        packed[: len(part)] |= (part << (2 * q)).astype(np.uint8)
+    got = mz.ModIndex.expand_hit_runs_packed(packed, runs, rro, slots)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
 @pytest.mark.parametrize("extra,prefix", [(["--workload", "config2"], "configs[1]"), (["--cpu-scale", "0.002"], "configs[4]")])
 def test_bench_reference_arm_contract(extra, prefix):
     """`bench.py --impl reference` needs no GPU: it must print ONE JSON line with the driver's keys (metric, value, unit, n_gpus,

@@ -494,6 +494,76 @@ def test_validate_fasta_yeast_chr7_long_record(kind):
     assert g.k2u_validate_self() == o.k2u_validate_self()
 
 
+@pytest.mark.parametrize("which", ["sshash", "dense"])
+def test_fused_get_ref_pos_reads_equals_the_chain(yeast_dense, yeast_sshash, yeast_queries, which):
+    """mazu_b200_get_ref_pos_reads (reads -> K2UPos -> occurrences -> MappedRefPos in one kernel, single-pass look-back) must equal
+    query_reads followed by project_hits on the oracle, record for record: ragged reads with N / short / empty reads, uniform
+    reads, long reads spanning many tiles, both modes."""
+    g, o = yeast_sshash if which == "sshash" else yeast_dense
+    _, ref_codes = yeast_queries
+    cases = [_gen.sample_reads(ref_codes, 2500, 150, seed=31, frac_ref=0.7, sub_rate=0.01, n_rate=0.002, ragged=True),
+             _gen.sample_reads(ref_codes, 40, 5000, seed=32, frac_ref=0.9, sub_rate=0.002, n_rate=0.0005, ragged=True)]
+    for bases, offs in cases:
+        for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+            want_hits, wcnt, wko = o.query_reads(bases, offs, streaming=bool(mode))
+            want_offs, want_mrps = o.project_hits(want_hits)
+            hits, poffs, mrps, cnt, ko = g.get_ref_pos_reads(bases, read_offsets=offs, mode=mode)
+            assert_hits_equal(hits, want_hits, "fused hits")
+            assert np.array_equal(poffs, want_offs) and np.array_equal(mrps, want_mrps)
+            assert list(cnt) == list(wcnt) and np.array_equal(ko, wko)
+    bases, offs = _gen.sample_reads(ref_codes, 3000, 150, seed=33, frac_ref=0.6, sub_rate=0.01)
+    want_hits, wcnt, _ = o.query_reads(bases, offs)
+    want_offs, want_mrps = o.project_hits(want_hits)
+    hits, poffs, mrps, cnt, _ = g.get_ref_pos_reads(bases, uniform_read_len=150, want_hits=False)
+    assert hits is None and np.array_equal(poffs, want_offs) and np.array_equal(mrps, want_mrps) and list(cnt) == list(wcnt)
+    # empty batch and a batch without a single k-mer
+    _, poffs, mrps, cnt, _ = g.get_ref_pos_reads(np.zeros(0, dtype=np.uint8), read_offsets=np.zeros(1, dtype=np.uint64))
+    assert list(poffs) == [0] and len(mrps) == 0
+    _, poffs, mrps, cnt, _ = g.get_ref_pos_reads(np.frombuffer(b"ACGTACGT", dtype=np.uint8), read_offsets=np.array([0, 3, 3, 8], dtype=np.uint64))
+    assert list(poffs) == [0] and len(mrps) == 0 and list(cnt) == [0, 0, 0]
+
+
+def test_fused_get_ref_pos_high_multiplicity_and_small_capacity():
+    """long occurrence lists are written by the whole warp; an undersized device buffer is never overrun"""
+    import torch
+    import ctypes as C
+    k, U = 31, 400
+    codes, accum = _gen.synthetic_unitigs(U, 68, k, seed=51)
+    us = mz.UnitigSet(k, mz.pack_2bit(codes), len(codes), accum)
+    g = mz.SSHash.from_unitig_set(us, 19, 64)
+    o = OracleIndex.from_packed(k, us.useq_words, us.n_bases, accum, 1, w=19, skew=64)
+    n_refs, max_ref_len = 4096, 1 << 27
+    offsets, ref_ids, poss, fws = _synthetic_u2pos(U, n_refs, max_ref_len, 52, 3000)
+    o.attach_u2pos(1, offsets, ref_ids, poss, fws, max_ref_len, n_refs)
+    enc = (ref_ids.astype(np.uint64) << np.uint64(29)) | (poss.astype(np.uint64) << np.uint64(1)) | fws.astype(np.uint64)
+    g.attach_u2pos_piscem(mz.PackedVec.pack(enc, 42), 29, (1 << 28) - 1, mz.PackedVec.pack(offsets))
+    bases, offs = _gen.sample_reads(codes, 600, 150, seed=53, frac_ref=0.8, sub_rate=0.01, n_rate=0.001, ragged=True)
+    want_hits, wcnt, _ = o.query_reads(bases, offs)
+    want_offs, want_mrps = o.project_hits(want_hits)
+    assert int(np.diff(want_offs).max()) >= 32  # lists long enough for the warp-cooperative path
+    hits, poffs, mrps, cnt, _ = g.get_ref_pos_reads(bases, read_offsets=offs)
+    assert_hits_equal(hits, want_hits, "fused hits")
+    assert np.array_equal(poffs, want_offs) and np.array_equal(mrps, want_mrps)
+    # device mode, capacity smaller than the output, no out_total: filled up to cap, guard untouched, need reported in out_offsets[n]
+    n_slots, total = len(want_hits), len(want_mrps)
+    d_b = torch.from_numpy(bases).cuda()
+    d_ro = torch.from_numpy(offs.view(np.int64)).cuda()
+    for cap in (total, total // 3, 0):
+        d_offs = torch.zeros(n_slots + 1, dtype=torch.int64, device="cuda")
+        d_out = torch.full((cap + 1024, 3), -1, dtype=torch.int32, device="cuda")
+        mz._check(mz.lib().mazu_b200_get_ref_pos_reads(g._h, mz._any_ptr(d_b), mz._any_ptr(d_ro), len(offs) - 1, 0, 0, n_slots, None, None,
+                                                       mz._any_ptr(d_offs), mz._any_ptr(d_out), cap, None, None, mz.MEM_DEVICE, None))
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy().view(np.uint32)
+        assert np.array_equal(d_offs.cpu().numpy().view(np.uint64), want_offs)
+        assert (got[cap:] == 0xFFFFFFFF).all() and np.array_equal(got[:cap].reshape(-1).view(mz.OCC_DTYPE), want_mrps[:cap])
+    tot = C.c_uint64(0)
+    d_out = torch.full((total + 8, 3), -1, dtype=torch.int32, device="cuda")
+    rc = mz.lib().mazu_b200_get_ref_pos_reads(g._h, mz._any_ptr(d_b), mz._any_ptr(d_ro), len(offs) - 1, 0, 0, n_slots, None, None,
+                                              mz._any_ptr(d_offs), mz._any_ptr(d_out), total - 1, C.byref(tot), None, mz.MEM_DEVICE, None)
+    assert rc == -7 and tot.value == total
+
+
 def test_validate_fasta_reports_failures(tmp_path, yeast_dense):
     """records that are NOT the index's references: every k-mer that misses, or maps elsewhere, is a failure (the reference panics)"""
     g, o = yeast_dense
@@ -1046,25 +1116,27 @@ def test_c_example_runs(tmp_path):
     assert "projected reference positions: 6" in r.stdout
 
 
+@pytest.mark.parametrize("read_len", [150, 170])
 @pytest.mark.parametrize("ragged", [True, False])
-def test_hit_runs_expand_to_the_exact_records(yeast_dense, yeast_sshash, yeast_queries, ragged):
+def test_hit_runs_expand_to_the_exact_records(yeast_dense, yeast_sshash, yeast_queries, ragged, read_len):
     """mazu_b200_query_reads_runs + mazu_b200_expand_hit_runs == mazu_b200_query_reads == oracle, record for record; the run
-    format is far smaller than the records it stands for; a too-small run buffer reports the capacity it needs."""
+    format is far smaller than the records it stands for; a too-small run buffer reports the capacity it needs.
+    150 bp reads fit one chunk and take the fused kernel (lookups + run encoding in one pass), 170 bp reads the four-kernel chain."""
     import ctypes as C
     _, ref_codes = yeast_queries
-    bases, offs = _gen.sample_reads(ref_codes, 5000, 170, seed=51, frac_ref=0.7, sub_rate=0.01, n_rate=0.002, ragged=ragged)
+    bases, offs = _gen.sample_reads(ref_codes, 5000, read_len, seed=51, frac_ref=0.7, sub_rate=0.01, n_rate=0.002, ragged=ragged)
     for g, o in (yeast_sshash, yeast_dense):
         for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
             want, wcnt, wk = o.query_reads(bases, offs, streaming=mode == mz.MODE_STREAMING, reset_per_read=True)
-            kw = dict(read_offsets=offs) if ragged else dict(uniform_read_len=170)
+            kw = dict(read_offsets=offs) if ragged else dict(uniform_read_len=read_len)
             codes, runs, rro, cnt, koffs = g.query_reads_runs(bases, mode=mode, **kw)
             assert list(cnt) == list(wcnt)
-            assert len(codes) == len(want) and rro[-1] == len(runs) and rro[0] == 0 and np.all(np.diff(rro.astype(np.int64)) >= 0)
+            assert len(codes) == len(want) and rro[-1] == len(runs) and int(rro.max()) <= len(runs)
             if ragged:
                 assert np.array_equal(koffs, wk)
                 got = mz.ModIndex.expand_hit_runs(codes, runs, rro, kmer_offsets=koffs)
             else:
-                got = mz.ModIndex.expand_hit_runs(codes, runs, rro, uniform_slots=170 - g.k + 1)
+                got = mz.ModIndex.expand_hit_runs(codes, runs, rro, uniform_slots=read_len - g.k + 1)
             assert_hits_equal(got, want, "expanded runs, mode %d" % mode)
             n_hit = int(((want["match"] == mz.IDENTITY_MATCH) | (want["match"] == mz.TWIN_MATCH)).sum())
             assert int((codes == 2).sum()) == len(runs) and int(((codes == 1) | (codes == 2)).sum()) == n_hit
@@ -1072,8 +1144,11 @@ def test_hit_runs_expand_to_the_exact_records(yeast_dense, yeast_sshash, yeast_q
             # pinned (device-addressable) run buffer: the sync-free path stores the records straight into it -- same bytes
             pr = mz.PinnedArray((len(runs) + 7,), mz.HIT_DTYPE)
             codes2, runs2, rro2, cnt2, _ = g.query_reads_runs(bases, mode=mode, runs=pr.array, **kw)
-            assert np.array_equal(codes2, codes) and np.array_equal(rro2, rro) and list(cnt2) == list(cnt)
-            assert np.array_equal(runs2.view(np.uint32), runs.view(np.uint32))
+            assert np.array_equal(codes2, codes) and list(cnt2) == list(cnt) and len(runs2) == len(runs)
+            # (where a read's runs sit in the array is unspecified: compare what they expand to, and the multiset of records)
+            got2 = mz.ModIndex.expand_hit_runs(codes2, runs2, rro2, kmer_offsets=koffs) if ragged else mz.ModIndex.expand_hit_runs(codes2, runs2, rro2, uniform_slots=read_len - g.k + 1)
+            assert_hits_equal(got2, want, "expanded runs (pinned buffers), mode %d" % mode)
+            assert np.array_equal(np.sort(runs2.view(np.uint32).reshape(-1, 4), axis=0), np.sort(runs.view(np.uint32).reshape(-1, 4), axis=0))
     # capacity: one run record is not enough; the call says how many it needs
     g, _ = yeast_sshash
     n_reads = len(offs) - 1
@@ -1083,6 +1158,31 @@ def test_hit_runs_expand_to_the_exact_records(yeast_dense, yeast_sshash, yeast_q
                                              mz._any_ptr(np.empty(1, dtype=mz.HIT_DTYPE)), 1, mz._any_ptr(np.zeros(n_reads + 1, dtype=np.uint64)),
                                              C.byref(n_runs), None)
     assert rc == -7 and n_runs.value > 1
+
+
+def test_packed_reads_in_packed_codes_out(yeast_sshash, yeast_dense, yeast_queries):
+    """mazu_b200_query_reads_runs_packed: 2-bit packed reads (+ N mask) over PCIe, 2-bit codes back; expands to exactly the
+    records of the ASCII call and of the oracle, N windows and lower case included; both modes, several pipeline chunks."""
+    _, ref_codes = yeast_queries
+    n_reads, read_len = 6000, 150
+    bases, offs = _gen.sample_reads(ref_codes, n_reads, read_len, seed=61, frac_ref=0.7, sub_rate=0.01, n_rate=0.003)
+    words, mask, bad = mz.pack_reads(bases, read_len)
+    assert bad == int(((bases == ord("N")) | (bases == ord("n"))).sum()) > 0
+    os.environ["MAZU_B200_CHUNK_MIB"] = "1"  # several chunks
+    try:
+        for g, o in (yeast_sshash, yeast_dense):
+            for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+                want, wcnt, _ = o.query_reads(bases, offs, streaming=bool(mode))
+                codes2, runs, rro, cnt = g.query_reads_runs_packed(words, mask, n_reads, read_len, mode=mode)
+                got = mz.ModIndex.expand_hit_runs_packed(codes2, runs, rro, read_len - g.k + 1)
+                assert_hits_equal(got, want, "packed runs mode %d" % mode)
+                assert list(cnt) == list(wcnt) and len(codes2) == (len(want) + 3) // 4
+    finally:
+        del os.environ["MAZU_B200_CHUNK_MIB"]
+    # without a mask the N positions read as 'A': the caller's contract, not checked here; wrong shapes are rejected
+    g, _ = yeast_sshash
+    with pytest.raises(mz.MazuError):
+        g.query_reads_runs_packed(words, mask, n_reads, 151)  # 121 slots per read: not a multiple of 4
 
 
 def test_pinned_host_buffers(yeast_sshash, yeast_queries):
