@@ -68,7 +68,7 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads (or k-mers / 120, or unitig queries) per GPU per step")
     ap.add_argument("--mode", default=None, choices=["random", "streaming"])
     ap.add_argument("--scale", type=float, default=1.0, help="config5: fraction of the human-scale unitig count (36,145,130 unitigs)")
-    ap.add_argument("--cpu-scale", type=float, default=0.1, help="config5: unitig-set scale of the CPU port's index (its builder needs ~25 s per 0.1 on 16 cores)")
+    ap.add_argument("--cpu-scale", type=float, default=0.25, help="config5: unitig-set scale of the CPU port's index (its threaded builder needs ~11 s per 0.1 on 16 cores)")
     ap.add_argument("--e2e-slice", type=int, default=1_000_000, help="reads of the batch the full-record / compact e2e variants run on")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
