@@ -476,17 +476,16 @@ def main():
             h_rro = torch.zeros(e2e_reads + 1, dtype=torch.int64, pin_memory=True)
             runs_state = {"n_runs": 0}
 
-            def e2e_step():
+            def e2e_ascii_step():
                 n_runs = C.c_uint64(0)
                 mz._check(mz.lib().mazu_b200_query_reads_runs(index._h, mz._any_ptr(hb), None, e2e_reads, READ_LEN, mode, None, mz._any_ptr(h_codes),
                                                               mz._any_ptr(h_runs), h_runs.shape[0], mz._any_ptr(h_rro), C.byref(n_runs), mz._np_ptr(h_cnt)))
                 runs_state["n_runs"] = n_runs.value
 
-            e2e_api = ("mazu_b200_query_reads_runs (C ABI, host buffers): pinned ASCII reads in; out: one code byte per k-mer slot + the 16-byte "
-                       "record of every run start + per-read run offsets (lossless: mazu_b200_expand_hit_runs rebuilds every record)")
+            ascii_api = ("mazu_b200_query_reads_runs (C ABI, host buffers): pinned ASCII reads in; out: one code byte per k-mer slot + the 16-byte "
+                         "record of every run start + per-read run offsets (lossless: mazu_b200_expand_hit_runs rebuilds every record)")
 
-            def e2e_post(e):
-                e["h2d_bytes_per_step"] = e2e_reads * READ_LEN * world
+            def ascii_post(e):
                 e["d2h_bytes_per_step"] = (e2e_units + 16 * runs_state["n_runs"] + 8 * (e2e_reads + 1) + 24) * world
                 e["n_runs_per_step_per_gpu"] = runs_state["n_runs"]
                 m = min(e2e_reads, 20000)  # the expansion on the host reproduces the full records (checked on the head of the batch)
@@ -508,26 +507,50 @@ def main():
                 index.query_reads(hb, None, n_reads=e2e_reads, uniform_read_len=READ_LEN, mode=mode, out_hits=hits, counts=h_cnt,
                                   mem=mz.MEM_HOST_IN_DEVICE_OUT)
 
-            # packed interface for PCIe-bound hosts: 2-bit reads in (packed once, outside the timed loop, as a caller holding
-            # SeqVector-style reads would), 2-bit codes out
+            # The headline e2e: the packed run interface -- reads held 2-bit packed by the caller (mazu's own SeqVector
+            # representation), 2-bit run codes + run records + per-read run offsets back.  0.31 + 0.5 bytes per lookup cross PCIe,
+            # which is what lets 8 GPUs behind one host scale (profiles/r02i_pcie_8gpu.json: the host moves 92 GB/s of D2H in total).
+            # Packing ASCII -> 2-bit (mazu_b200_pack_reads, host threads) is done once, outside the timed loop, and its rate is
+            # reported; the ASCII-in call is measured next to it (`ascii_reads`).
             packed_ok = nk_per_read % 4 == 0
+            e2e_extra = {}
             if packed_ok:
                 wpr = (READ_LEN + 31) // 32
                 h_words = torch.empty(e2e_reads * wpr, dtype=torch.int64, pin_memory=True)
+                t_pack = time.perf_counter()
                 mz.pack_reads(hb, READ_LEN, words=h_words, want_mask=False)
+                t_pack = time.perf_counter() - t_pack
                 h_codes2 = torch.empty((e2e_units + 3) // 4, dtype=torch.uint8, pin_memory=True)
 
-                def e2e_packed_step():
+                def e2e_step():
                     n_runs = C.c_uint64(0)
                     mz._check(mz.lib().mazu_b200_query_reads_runs_packed(index._h, mz._any_ptr(h_words), None, e2e_reads, READ_LEN, mode, mz._any_ptr(h_codes2),
                                                                          mz._any_ptr(h_runs), h_runs.shape[0], mz._any_ptr(h_rro), C.byref(n_runs), mz._np_ptr(h_cnt)))
                     runs_state["n_runs_packed"] = n_runs.value
 
-            e2e_extra = {}
-            if packed_ok:
-                e2e_extra["hit_runs_packed"] = (e2e_packed_step, e2e_units, e2e_reads * wpr * 8, None,
-                                                "mazu_b200_query_reads_runs_packed: 2-bit packed reads in (40 B per 150 bp read), 2-bit run codes + run records + "
-                                                "per-read run offsets out; mazu_b200_expand_hit_runs_packed rebuilds every record")
+                e2e_api = ("mazu_b200_query_reads_runs_packed (C ABI, host buffers): pinned 2-bit packed reads in (40 B per 150 bp read); out: 2-bit run code "
+                           "per k-mer slot + the 16-byte record of every run start + per-read run offsets (lossless: mazu_b200_expand_hit_runs_packed "
+                           "rebuilds every record)")
+
+                def e2e_post(e):
+                    e["h2d_bytes_per_step"] = e2e_reads * wpr * 8 * world
+                    e["d2h_bytes_per_step"] = ((e2e_units + 3) // 4 + 16 * runs_state["n_runs_packed"] + 8 * (e2e_reads + 1) + 24) * world
+                    e["n_runs_per_step_per_gpu"] = runs_state["n_runs_packed"]
+                    e["input"] = ("2-bit packed reads; packing the ASCII batch with mazu_b200_pack_reads (host threads) took %.0f ms = %.1f GB/s of ASCII, "
+                                  "outside the timed loop" % (t_pack * 1e3, e2e_reads * READ_LEN / t_pack / 1e9))
+                    m = min(e2e_reads, 20000)  # the expansion on the host reproduces the full records (checked on the head of the batch)
+                    exp = mz.ModIndex.expand_hit_runs_packed(h_codes2.numpy()[: m * nk_per_read // 4], h_runs.numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE),
+                                                             h_rro.numpy().view(np.uint64)[: m + 1], nk_per_read)
+                    e["expands_to_full_records"] = bool(np.array_equal(exp.view(np.uint32).reshape(-1, 4), hits[: m * nk_per_read].cpu().numpy().view(np.uint32)))
+                    e["counts_match_device_path"] = bool(int(h_cnt[0]) == e2e_units and int(h_cnt[1]) > 0)
+
+                e2e_extra["ascii_reads"] = (e2e_ascii_step, e2e_units, e2e_reads * READ_LEN, None, ascii_api)
+            else:  # read lengths whose slot count is not a multiple of 4: the byte-coded run call is the headline
+                e2e_step, e2e_api = e2e_ascii_step, ascii_api
+
+                def e2e_post(e):
+                    e["h2d_bytes_per_step"] = e2e_reads * READ_LEN * world
+                    ascii_post(e)
             e2e_extra.update({
                 "full_records": (e2e_full_step, sl_units, sl_reads * READ_LEN, sl_units * 16 + 24,
                                  "mazu_b200_query_reads(MAZU_MEM_HOST): every 16-byte record over PCIe; first %d reads of the batch" % sl_reads),
@@ -860,6 +883,15 @@ def main():
                "h2d_bytes_per_step": e2e_bytes[0] * world, "d2h_bytes_per_step": e2e_bytes[1] * world, "steps": args.steps, "api": e2e_api}
         if e2e_post is not None:
             e2e_post(e2e)
+        e2e["achieved_h2d_gbs_total"] = e2e["h2d_bytes_per_step"] * args.steps / dt / 1e9
+        e2e["achieved_d2h_gbs_total"] = e2e["d2h_bytes_per_step"] * args.steps / dt / 1e9
+        try:  # what the HOST can move with all N GPUs copying at once (profiles/pcie_probe_multi.py, measured on this pool's boxes)
+            src = {1: "r01_pcie.json", 2: "r02h_pcie_2gpu.json", 8: "r02i_pcie_8gpu.json"}.get(world)
+            if src:
+                hc = json.load(open(os.path.join(ROOT, "profiles", src)))
+                e2e["host_copy_ceiling"] = dict(hc, source="profiles/" + src)
+        except Exception:
+            pass
         pc = None
         try:  # the box's pinned-copy bandwidth (profiles/pcie_probe.py): what bounds the variants that move every record
             pc = json.load(open(os.path.join(ROOT, "profiles", "r01_pcie.json")))
@@ -869,12 +901,8 @@ def main():
             dtx = timed_host_loop(fn)
             e2e[name] = {"value": float(units) * args.steps * world / dtx, "unit": unit, "units_per_step_per_gpu": units,
                          "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": (d2h or 0) * world, "api": api}
-            if name == "hit_runs_packed":
-                e2e[name]["d2h_bytes_per_step"] = ((units + 3) // 4 + 16 * runs_state["n_runs_packed"] + 8 * (e2e_reads + 1) + 24) * world
-                m = min(e2e_reads, 20000)
-                exp = mz.ModIndex.expand_hit_runs_packed(h_codes2.numpy()[: m * nk_per_read // 4], h_runs.numpy().view(np.uint32).reshape(-1).view(mz.HIT_DTYPE),
-                                                         h_rro.numpy().view(np.uint64)[: m + 1], nk_per_read)
-                e2e[name]["expands_to_full_records"] = bool(np.array_equal(exp.view(np.uint32).reshape(-1, 4), hits[: m * nk_per_read].cpu().numpy().view(np.uint32)))
+            if name == "ascii_reads":
+                ascii_post(e2e[name])
             if name == "full_records":
                 e2e[name]["matches_device_path"] = bool(torch.equal(h_hits[:1_000_000], hits[:1_000_000].cpu()))
                 if pc:

@@ -83,8 +83,17 @@ void check_k(const mazu_index* ix, u32 k) {
 
 void launch_k2u_batch(const mazu_index* ix, const u64* d_words, u64 n, Hit* d_out, cudaStream_t s) {
   if (n == 0) return;
-  int grid = grid_for(k2u_batch_kernel, 256, ix, 256, n);
-  k2u_batch_kernel<<<grid, 256, 0, s>>>(ix->view, d_words, n, d_out);
+  static const bool one_phase = getenv("MAZU_B200_FLAT_ONE_PHASE") != nullptr;  // A/B knob: the round-1 thread-per-k-mer kernel
+  if (!one_phase && ix->view.k2u_kind == MAZU_K2U_SSHASH) {
+    int grid = grid_for(k2u_batch_two_phase_kernel<MAZU_K2U_SSHASH>, 256, ix, 256, n);
+    k2u_batch_two_phase_kernel<MAZU_K2U_SSHASH><<<grid, 256, 0, s>>>(ix->view, d_words, n, d_out);
+  } else if (!one_phase && ix->view.k2u_kind == MAZU_K2U_PFHASH) {
+    int grid = grid_for(k2u_batch_two_phase_kernel<MAZU_K2U_PFHASH>, 256, ix, 256, n);
+    k2u_batch_two_phase_kernel<MAZU_K2U_PFHASH><<<grid, 256, 0, s>>>(ix->view, d_words, n, d_out);
+  } else {
+    int grid = grid_for(k2u_batch_kernel, 256, ix, 256, n);
+    k2u_batch_kernel<<<grid, 256, 0, s>>>(ix->view, d_words, n, d_out);
+  }
   MZ_CUDA(cudaGetLastError());
 }
 

@@ -27,6 +27,8 @@ struct OccRec {
 };
 
 __device__ __forceinline__ Hit hit_none(u32 match) { return Hit{~0u, ~0u, ~0u, match}; }
+// fire-and-forget fetch of the line holding *p into L2: used where a later dependent load's address is already known
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void store_hit(Hit* out, const Hit& h) {
   *reinterpret_cast<uint4*>(out) = make_uint4(h.unitig_id, h.unitig_len, h.pos, h.match);
 }
@@ -111,10 +113,9 @@ __device__ __forceinline__ bool pfhash_k2u(const IndexView& ix, u64 fw, u64 rc, 
   return finish_hit(ix.unitigs, km_pos, mt, false, out);
 }
 
-// SSHash::k2u (src/kphf/sshash.rs:471-555) given the canonical minimizer (word, offset in fw-mer coordinates)
-__device__ __forceinline__ bool sshash_k2u(const IndexView& ix, u64 fw, u64 rc, u64 mm_word, u32 offset, Hit& out) {
-  u64 h;
-  if (!cascade_lookup(ix.mphf, ix.sizes, mm_word, h)) return false;  // fingerprinted cascade: slot + membership filter in one (index_layout.hpp)
+// SSHash::k2u (src/kphf/sshash.rs:471-555), second half: from the minimizer's slot h (bucket bounds -> skew index or bucket
+// entries -> candidate windows -> unitig id / bounds).  `offset` = minimizer offset in fw-mer coordinates.
+__device__ __forceinline__ bool sshash_finish(const IndexView& ix, u64 fw, u64 rc, u64 h, u32 offset, Hit& out) {
   if (h + 1 >= ix.sizes.n) return false;
   u64 pos_start, pos_end;
   blocked_ef_get2(ix.sizes, h, pos_start, pos_end);  // occs_prefix_sum.get(h), get(h+1)
@@ -146,6 +147,12 @@ __device__ __forceinline__ bool sshash_k2u(const IndexView& ix, u64 fw, u64 rc, 
   }
   return false;
 }
+// SSHash::k2u given the canonical minimizer (word, offset in fw-mer coordinates)
+__device__ __forceinline__ bool sshash_k2u(const IndexView& ix, u64 fw, u64 rc, u64 mm_word, u32 offset, Hit& out) {
+  u64 h;
+  if (!cascade_lookup(ix.mphf, ix.sizes, mm_word, h)) return false;  // fingerprinted cascade: slot + membership filter in one (index_layout.hpp)
+  return sshash_finish(ix, fw, rc, h, offset, out);
+}
 
 template <u32 FAMILY>
 __device__ __forceinline__ bool sampled_pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc, Hit& out, u64* ustart);
@@ -169,6 +176,75 @@ __global__ void __launch_bounds__(256) k2u_batch_kernel(const __grid_constant__ 
     if (!k2u_any(ix, fw, rc, h)) h = hit_none(NO_MATCH);
     store_hit(out + i, h);
   }
+}
+
+// The same call in two converged phases (SSHash and PFHash indexes).  Thread per k-mer as above, but a lookup is cut where
+// its lanes part ways: phase A = minimizer + cascade probe (SSHash) / MPHF levels (PFHash) -- half of a mixed batch ends here
+// as a miss -- and phase B = bounds, bucket entries, window compare, unitig id / bounds.  Survivors of phase A are compacted
+// into a per-warp queue in shared memory; phase B only ever runs on 32 queued k-mers at a time, so its loads and its long
+// dependent chain are issued by full warps (ncu on the one-phase kernel: 14 of 32 lanes active per instruction on a 50 %
+// positive batch, 12 on the all-positive PFHash batch of config 1).
+struct FlatEntry {
+  u64 fw, aux, idx;
+};
+static const int KB_WARPS = 8;
+template <int KIND>
+__global__ void __launch_bounds__(KB_WARPS * 32) k2u_batch_two_phase_kernel(const __grid_constant__ IndexView ix, const u64* __restrict__ fw_words,
+                                                                           u64 n, Hit* __restrict__ out) {
+  __shared__ FlatEntry s_q[KB_WARPS][64];
+  const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  FlatEntry* q = s_q[wib];
+  const u32 k = ix.unitigs.k;
+  const u64 warp = (u64)blockIdx.x * KB_WARPS + wib, n_warps = (u64)gridDim.x * KB_WARPS;
+  u32 q_n = 0;
+  auto phase_b = [&](u32 first, u32 count) {  // entries [first, first + count) of the queue, one per lane
+    if (lane < count) {
+      const FlatEntry e = q[first + lane];
+      const u64 fw = e.fw, rc = revcomp(fw, k);
+      Hit h;
+      bool ok;
+      if (KIND == MAZU_K2U_SSHASH) {
+        ok = sshash_finish(ix, fw, rc, e.aux & ((1ULL << 56) - 1ULL), (u32)(e.aux >> 56), h);
+      } else {
+        ok = false;
+        if (e.aux < ix.pos.len) {
+          const u64 km_pos = packed_get(ix.pos, e.aux);
+          const u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
+          if (mt != NO_MATCH) ok = finish_hit(ix.unitigs, km_pos, mt, false, h);
+        }
+      }
+      if (!ok) h = hit_none(NO_MATCH);
+      store_hit(out + e.idx, h);
+    }
+    __syncwarp();
+  };
+  for (u64 base = warp * 32; base < n; base += n_warps * 32) {
+    const u64 i = base + lane;
+    bool found = false;
+    u64 fw = 0, aux = 0;
+    if (i < n) {
+      fw = fw_words[i] & kmer_mask(k);
+      const u64 rc = revcomp(fw, k);
+      if (KIND == MAZU_K2U_SSHASH) {
+        const MinimizerResult m = canonical_minimizer_naive(fw, rc, k, ix.w, ix.seed);
+        u64 g;
+        found = cascade_lookup(ix.mphf, ix.sizes, m.word, g);
+        aux = g | ((u64)m.offset << 56);
+      } else {
+        found = mphf_lookup(ix.mphf, fw <= rc ? fw : rc, aux);
+      }
+      if (!found) store_hit(out + i, hit_none(NO_MATCH));
+    }
+    const u32 m = __ballot_sync(0xffffffffu, found);
+    if (found) q[q_n + __popc(m & ((1u << lane) - 1u))] = FlatEntry{fw, aux, i};
+    q_n += __popc(m);
+    __syncwarp();
+    if (q_n >= 32) {
+      q_n -= 32;
+      phase_b(q_n, 32);
+    }
+  }
+  if (q_n) phase_b(0, q_n);
 }
 
 // measurement hook: level-0 MPHF block of every query's key
@@ -376,6 +452,9 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
         blocked_ef_get2(ix.sizes, h, a, b);
         u64 cnt = b - a;
         n = cnt > ix.skew_param ? BN_SKEW : (u32)cnt;
+#ifdef MAZU_PREFETCH  // measured and rejected (profiles/experiments/README.md): -2 % config 5, -5 % config 2
+        if (cnt && n != BN_SKEW) prefetch_l2(ix.pos.words + ((a * ix.pos.width) >> 6));
+#endif
       }
       S.bstart[p] = a;
       S.bn[p] = n;
@@ -545,6 +624,12 @@ __global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const _
     }
     const u8* seq = bases + beg;
     const u64 nk = len >= k ? len - k + 1 : 0;
+#ifdef MAZU_PREFETCH  // measured and rejected together with the prefetch in stage B
+    if (uniform_len && !segmented) {  // the warp's next read: its bases are the first thing stage E waits for
+      const u64 nxt = item + (u64)gridDim.x * QR_WARPS;
+      if (nxt < n_items && lane < 2) prefetch_l2(bases + nxt * uniform_len + 128 * lane);
+    }
+#endif
     StreamState st;
     st.warm = 0;
     st.uid = st.ulen = st.pos = ~0u;
