@@ -302,6 +302,72 @@ impl GpuIndex {
         check(unsafe { sys::mazu_b200_k2u_validate_self(self.raw, c.as_mut_ptr()) })?;
         Ok(c)
     }
+    /// `Validate::validate_fasta` (src/index/validate.rs:83-100) / `StreamingIndex::validate_fasta` (src/index/caching.rs:204-218):
+    /// the library reads the FASTA / FASTQ file; record i is reference i.  {n_queries, n_identity, n_twin, n_projected, n_fail}.
+    pub fn validate_fasta<P: AsRef<Path>>(&self, path: P, streaming: bool) -> Result<[u64; 5]> {
+        let c_path = CString::new(path.as_ref().to_string_lossy().as_bytes()).map_err(|e| Error::InvalidArg(e.to_string()))?;
+        let mut c = [0u64; 5];
+        check(unsafe { sys::mazu_b200_validate_fasta(self.raw, c_path.as_ptr(), streaming as i32, c.as_mut_ptr()) })?;
+        Ok(c)
+    }
+    /// `GetRefPos::get_ref_pos` + `project_hits` over a read batch in one call (src/index.rs:156-216): (slot offsets, positions).
+    pub fn get_ref_pos_reads(&self, bases: &[u8], read_offsets: &[u64], streaming: bool) -> Result<(Vec<u64>, Vec<MappedRefPos>)> {
+        let n_reads = (read_offsets.len() - 1) as u64;
+        let n_slots = unsafe { sys::mazu_b200_count_kmer_slots(self.raw, read_offsets.as_ptr(), n_reads, 0) };
+        let mut offs = vec![0u64; n_slots as usize + 1];
+        let mut cap = 2 * n_slots + 1024;
+        loop {
+            let mut out = vec![MappedRefPos { ref_id: 0, pos: 0, fw: 0 }; cap as usize];
+            let mut total = 0u64;
+            let rc = unsafe {
+                sys::mazu_b200_get_ref_pos_reads(self.raw, bases.as_ptr(), read_offsets.as_ptr(), n_reads, 0, streaming as i32, n_slots,
+                                                 std::ptr::null_mut(), std::ptr::null_mut(), offs.as_mut_ptr(), out.as_mut_ptr() as *mut sys::mazu_occ_t,
+                                                 cap, &mut total, std::ptr::null_mut(), 0 /* MAZU_MEM_HOST */, std::ptr::null_mut())
+            };
+            if rc != 0 && total > cap {
+                cap = total;
+                continue;
+            }
+            check(rc)?;
+            out.truncate(total as usize);
+            return Ok((offs, out));
+        }
+    }
+    /// `K2U::unitig_seq` (src/kphf/mod.rs:64): the unitig's 2-bit words (base j at bits [2j, 2j+2)) and its length.
+    pub fn unitig_seq_words(&self, id: usize) -> Result<(Vec<u64>, usize)> {
+        let mut len = 0u64;
+        check(unsafe { sys::mazu_b200_unitig_seq(self.raw, id as u64, std::ptr::null_mut(), 0, &mut len) })?;
+        let mut w = vec![0u64; ((len + 31) / 32) as usize];
+        check(unsafe { sys::mazu_b200_unitig_seq(self.raw, id as u64, w.as_mut_ptr(), w.len() as u64, &mut len) })?;
+        Ok((w, len as usize))
+    }
+    /// One copy of the index per device, made with device-to-device copies (the index is replicated, reads are sharded).
+    pub fn replicate(&self, devices: &[i32]) -> Result<Vec<GpuIndex>> {
+        let mut raw = vec![std::ptr::null_mut(); devices.len()];
+        check(unsafe { sys::mazu_b200_index_replicate(self.raw, devices.as_ptr(), devices.len() as i32, raw.as_mut_ptr()) })?;
+        Ok(raw.into_iter().map(|r| GpuIndex { raw: r }).collect())
+    }
+}
+
+/// Replicas of one index on several devices: `query_reads` shards the reads over them in contiguous blocks
+/// (one host thread + streams per device inside the library) and sums the counters -- the shape of
+/// `K2U::validate_self_parallel` (src/kphf/mod.rs:105-139).
+pub struct GpuIndexSet {
+    pub replicas: Vec<GpuIndex>,
+}
+impl GpuIndexSet {
+    pub fn query_reads(&self, bases: &[u8], read_offsets: &[u64], streaming: bool) -> Result<(Vec<Hit>, [u64; 3])> {
+        let handles: Vec<*const sys::mazu_index_t> = self.replicas.iter().map(|r| r.raw as *const _).collect();
+        let n_reads = (read_offsets.len() - 1) as u64;
+        let n_slots = unsafe { sys::mazu_b200_count_kmer_slots(handles[0], read_offsets.as_ptr(), n_reads, 0) };
+        let mut hits = vec![Hit { unitig_id: !0, unitig_len: !0, pos: !0, r#match: 0 }; n_slots as usize];
+        let mut counts = [0u64; 3];
+        check(unsafe {
+            sys::mazu_b200_query_reads_sharded(handles.as_ptr(), handles.len() as i32, bases.as_ptr(), read_offsets.as_ptr(), n_reads, 0, streaming as i32,
+                                               std::ptr::null_mut(), hits.as_mut_ptr() as *mut sys::mazu_hit_t, counts.as_mut_ptr())
+        })?;
+        Ok((hits, counts))
+    }
 }
 
 // With `mazu` as a dependency the trait impl is a thin shim (UnitigSet kept next to the handle for unitig_seq / AsRef):

@@ -83,17 +83,8 @@ void check_k(const mazu_index* ix, u32 k) {
 
 void launch_k2u_batch(const mazu_index* ix, const u64* d_words, u64 n, Hit* d_out, cudaStream_t s) {
   if (n == 0) return;
-  static const bool one_phase = getenv("MAZU_B200_FLAT_ONE_PHASE") != nullptr;  // A/B knob: the round-1 thread-per-k-mer kernel
-  if (!one_phase && ix->view.k2u_kind == MAZU_K2U_SSHASH) {
-    int grid = grid_for(k2u_batch_two_phase_kernel<MAZU_K2U_SSHASH>, 256, ix, 256, n);
-    k2u_batch_two_phase_kernel<MAZU_K2U_SSHASH><<<grid, 256, 0, s>>>(ix->view, d_words, n, d_out);
-  } else if (!one_phase && ix->view.k2u_kind == MAZU_K2U_PFHASH) {
-    int grid = grid_for(k2u_batch_two_phase_kernel<MAZU_K2U_PFHASH>, 256, ix, 256, n);
-    k2u_batch_two_phase_kernel<MAZU_K2U_PFHASH><<<grid, 256, 0, s>>>(ix->view, d_words, n, d_out);
-  } else {
-    int grid = grid_for(k2u_batch_kernel, 256, ix, 256, n);
-    k2u_batch_kernel<<<grid, 256, 0, s>>>(ix->view, d_words, n, d_out);
-  }
+  int grid = grid_for(k2u_batch_kernel, 256, ix, 256, n);
+  k2u_batch_kernel<<<grid, 256, 0, s>>>(ix->view, d_words, n, d_out);
   MZ_CUDA(cudaGetLastError());
 }
 
@@ -183,14 +174,14 @@ void device_exclusive_scan(const u64* d_in, u64* d_out, u64 n, cudaMemPool_t poo
   MZ_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, d_in, d_out, (size_t)(n + 1), s));
 }
 
-// Tiles of the fused kernels: one per chunk of QR_CHUNK k-mer positions, at least one per read.  Uniform reads need no table.
-// Ragged reads: seg (n_reads + 1 first-tile indexes) is built on the device; n_tiles comes from the caller when it can count on
-// the host (host pipelines), else it is read back (one synchronisation).
+// Tiles of get_ref_pos over reads: one per chunk of QR_CHUNK k-mer positions, at least one per read.  Uniform reads need no
+// table; for ragged reads seg (n_reads + 1 first-tile indexes) is built on the device and the tile count read back (one
+// synchronisation per call).
 struct TileTable {
   std::unique_ptr<PoolBuf> cnt, seg;
   u64 n_tiles = 0;
 };
-void make_tiles(const mazu_index* idx, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, u64 n_tiles_known, cudaStream_t s, TileTable& t) {
+void make_tiles(const mazu_index* idx, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, cudaStream_t s, TileTable& t) {
   const u32 k = idx->unitigs->k;
   if (uniform_len) {
     const u64 nk = uniform_len >= k ? uniform_len - k + 1 : 0;
@@ -203,12 +194,8 @@ void make_tiles(const mazu_index* idx, const u64* d_read_offsets, u64 n_reads, u
   segment_counts_kernel<<<(int)std::min<u64>((n_reads + 255) / 256, 4096), 256, 0, s>>>(d_read_offsets, n_reads, k, (u64)QR_CHUNK, (u64*)t.cnt->p);
   MZ_CUDA(cudaGetLastError());
   device_exclusive_scan((const u64*)t.cnt->p, (u64*)t.seg->p, n_reads, idx->pool, s);
-  if (n_tiles_known != ~0ULL) {
-    t.n_tiles = n_tiles_known;
-  } else {
-    MZ_CUDA(cudaMemcpyAsync(&t.n_tiles, (u64*)t.seg->p + n_reads, 8, cudaMemcpyDeviceToHost, s));
-    MZ_CUDA(cudaStreamSynchronize(s));
-  }
+  MZ_CUDA(cudaMemcpyAsync(&t.n_tiles, (u64*)t.seg->p + n_reads, 8, cudaMemcpyDeviceToHost, s));
+  MZ_CUDA(cudaStreamSynchronize(s));
 }
 
 // fused reads -> hit runs (query_reads_runs_kernel): codes per slot, chunk-local run records, per-read run offsets; d_rro[n_reads]
@@ -1396,7 +1383,7 @@ static void launch_get_ref_pos_reads(const mazu_index_t* idx, const u8* d_bases,
                                      const u64* d_kmer_offsets, Hit* d_hits, u64* d_counts, u64 n_slots, u64* d_offsets, OccRec* d_out, u64 cap,
                                      u64* d_total, cudaStream_t s) {
   TileTable tt;
-  make_tiles(idx, d_read_offsets, n_reads, uniform_len, ~0ULL, s, tt);
+  make_tiles(idx, d_read_offsets, n_reads, uniform_len, s, tt);
   const u64 n_tiles = tt.n_tiles;
   if (n_tiles == 0) {
     MZ_CUDA(cudaMemsetAsync(d_offsets, 0, 8, s));

@@ -242,9 +242,21 @@ MZ_HD u32 blocked_ef_fp(const BlockedEFView& ef, u64 i) {
 static const u32 CASCADE_EMPTY = 0, CASCADE_COLLIDED = 1;
 MZ_HD u32 cascade_fp(u64 hk) { return 2u + mulhi32((u32)(hk ^ (hk >> 29)) * 0x9E3779B1u, 254u); }
 MZ_HD u64 cascade_slot(u64 hk, u32 level, u64 size) {
-  u64 x = (hk ^ ((u64)(level + 1) * 0x9E3779B97F4A7C15ULL)) * 0xD6E8FEB86659FD93ULL;
-  x ^= x >> 32;
-  return mulhi64(x * 0xFF51AFD7ED558CCDULL, size);
+  if (size >> 32) {  // levels of more than 2^32 slots (> 2e9 minimizers): 64-bit arithmetic
+    u64 x = (hk ^ ((u64)(level + 1) * 0x9E3779B97F4A7C15ULL)) * 0xD6E8FEB86659FD93ULL;
+    x ^= x >> 32;
+    return mulhi64(x * 0xFF51AFD7ED558CCDULL, size);
+  }
+  // hk is already a full 64-bit mix of the key: a cheap 32-bit remix per level picks the slot (32 bits of hash are enough to
+  // address < 2^32 slots uniformly; the level loop is the divergent part of a lookup, so it is kept short)
+  u32 a = (u32)(hk >> 32) + level * 0x9E3779B1u;
+  const u32 b = (u32)hk ^ (level * 0x85EBCA77u);
+  a ^= b;
+  a *= 0x2C1B3C6Du;
+  a ^= a >> 15;
+  a *= 0x297A2D39u;
+  a ^= a >> 16;
+  return mulhi32(a, (u32)size);
 }
 // slots of level `l` for `n` keys: 2 slots per key on the first two levels (61 % of the keys of a level are alone in their
 // slot), then 4 and 8: the few keys left are placed quickly and the cascade stays shallow

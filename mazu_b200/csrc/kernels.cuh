@@ -178,75 +178,6 @@ __global__ void __launch_bounds__(256) k2u_batch_kernel(const __grid_constant__ 
   }
 }
 
-// The same call in two converged phases (SSHash and PFHash indexes).  Thread per k-mer as above, but a lookup is cut where
-// its lanes part ways: phase A = minimizer + cascade probe (SSHash) / MPHF levels (PFHash) -- half of a mixed batch ends here
-// as a miss -- and phase B = bounds, bucket entries, window compare, unitig id / bounds.  Survivors of phase A are compacted
-// into a per-warp queue in shared memory; phase B only ever runs on 32 queued k-mers at a time, so its loads and its long
-// dependent chain are issued by full warps (ncu on the one-phase kernel: 14 of 32 lanes active per instruction on a 50 %
-// positive batch, 12 on the all-positive PFHash batch of config 1).
-struct FlatEntry {
-  u64 fw, aux, idx;
-};
-static const int KB_WARPS = 8;
-template <int KIND>
-__global__ void __launch_bounds__(KB_WARPS * 32) k2u_batch_two_phase_kernel(const __grid_constant__ IndexView ix, const u64* __restrict__ fw_words,
-                                                                           u64 n, Hit* __restrict__ out) {
-  __shared__ FlatEntry s_q[KB_WARPS][64];
-  const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  FlatEntry* q = s_q[wib];
-  const u32 k = ix.unitigs.k;
-  const u64 warp = (u64)blockIdx.x * KB_WARPS + wib, n_warps = (u64)gridDim.x * KB_WARPS;
-  u32 q_n = 0;
-  auto phase_b = [&](u32 first, u32 count) {  // entries [first, first + count) of the queue, one per lane
-    if (lane < count) {
-      const FlatEntry e = q[first + lane];
-      const u64 fw = e.fw, rc = revcomp(fw, k);
-      Hit h;
-      bool ok;
-      if (KIND == MAZU_K2U_SSHASH) {
-        ok = sshash_finish(ix, fw, rc, e.aux & ((1ULL << 56) - 1ULL), (u32)(e.aux >> 56), h);
-      } else {
-        ok = false;
-        if (e.aux < ix.pos.len) {
-          const u64 km_pos = packed_get(ix.pos, e.aux);
-          const u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
-          if (mt != NO_MATCH) ok = finish_hit(ix.unitigs, km_pos, mt, false, h);
-        }
-      }
-      if (!ok) h = hit_none(NO_MATCH);
-      store_hit(out + e.idx, h);
-    }
-    __syncwarp();
-  };
-  for (u64 base = warp * 32; base < n; base += n_warps * 32) {
-    const u64 i = base + lane;
-    bool found = false;
-    u64 fw = 0, aux = 0;
-    if (i < n) {
-      fw = fw_words[i] & kmer_mask(k);
-      const u64 rc = revcomp(fw, k);
-      if (KIND == MAZU_K2U_SSHASH) {
-        const MinimizerResult m = canonical_minimizer_naive(fw, rc, k, ix.w, ix.seed);
-        u64 g;
-        found = cascade_lookup(ix.mphf, ix.sizes, m.word, g);
-        aux = g | ((u64)m.offset << 56);
-      } else {
-        found = mphf_lookup(ix.mphf, fw <= rc ? fw : rc, aux);
-      }
-      if (!found) store_hit(out + i, hit_none(NO_MATCH));
-    }
-    const u32 m = __ballot_sync(0xffffffffu, found);
-    if (found) q[q_n + __popc(m & ((1u << lane) - 1u))] = FlatEntry{fw, aux, i};
-    q_n += __popc(m);
-    __syncwarp();
-    if (q_n >= 32) {
-      q_n -= 32;
-      phase_b(q_n, 32);
-    }
-  }
-  if (q_n) phase_b(0, q_n);
-}
-
 // measurement hook: level-0 MPHF block of every query's key
 __global__ void probe_key_kernel(const __grid_constant__ IndexView ix, const u64* __restrict__ fw_words, u64 n, u32* __restrict__ out_block) {
   const u32 k = ix.unitigs.k;
