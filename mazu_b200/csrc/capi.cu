@@ -680,19 +680,25 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
     }
     // two buffers / streams alternate; the sync-free run path uses three, because its per-chunk chain (H2D, lookups, encode, two
     // D2H copies) is 2.3x as long as its compute and two streams leave the SMs idle a third of the time
-    const int NB = runs_dev ? 3 : 2;
+    static const int MAXB = 6;
+    static const int nb_knob = [] {  // tuning knob: buffers / streams of the sync-free run pipeline (default 3)
+      const char* e = getenv("MAZU_B200_RUN_STREAMS");
+      const int v = e ? atoi(e) : 3;
+      return v < 2 ? 2 : (v > MAXB ? MAXB : v);
+    }();
+    const int NB = runs_dev ? nb_knob : 2;
     StreamPair sp;
-    struct ExtraStream {
-      cudaStream_t s = nullptr;
-      ~ExtraStream() {
-        if (s) cudaStreamDestroy(s);
+    struct ExtraStreams {
+      cudaStream_t s[MAXB - 2] = {};
+      ~ExtraStreams() {
+        for (auto x : s)
+          if (x) cudaStreamDestroy(x);
       }
     } extra;
-    if (NB == 3) MZ_CUDA(cudaStreamCreateWithFlags(&extra.s, cudaStreamNonBlocking));
-    cudaStream_t st[3] = {sp.s[0], sp.s[1], extra.s};
+    for (int b = 2; b < NB; ++b) MZ_CUDA(cudaStreamCreateWithFlags(&extra.s[b - 2], cudaStreamNonBlocking));
+    cudaStream_t st[MAXB] = {sp.s[0], sp.s[1], extra.s[0], extra.s[1], extra.s[2], extra.s[3]};
     PoolScratch scratch(idx->pool, sp.s[0]);
-    void *d_bases[3] = {nullptr, nullptr, nullptr}, *d_ro[3] = {nullptr, nullptr, nullptr}, *d_ko[3] = {nullptr, nullptr, nullptr},
-         *d_hits[3] = {nullptr, nullptr, nullptr};
+    void *d_bases[MAXB] = {}, *d_ro[MAXB] = {}, *d_ko[MAXB] = {}, *d_hits[MAXB] = {};
     void* d_counts = scratch.get(3 * 8);
     MZ_CUDA(cudaMemsetAsync(d_counts, 0, 24, sp.s[0]));
     for (int b = 0; b < NB; ++b) {
@@ -704,7 +710,7 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       if ((out_hits && !dev_out) || (ro && !fused_runs)) d_hits[b] = scratch.get(max_slots * rec + 16);
     }
     const u64 wpr = uniform_read_len ? (uniform_read_len + 31) / 32 : 0, mpr = uniform_read_len ? (uniform_read_len + 63) / 64 : 0;
-    void *d_pw[3] = {nullptr, nullptr, nullptr}, *d_pm[3] = {nullptr, nullptr, nullptr}, *d_codes2[3] = {nullptr, nullptr, nullptr};
+    void *d_pw[MAXB] = {}, *d_pm[MAXB] = {}, *d_codes2[MAXB] = {};
     if (packed_in)
       for (int b = 0; b < NB; ++b) {
         d_pw[b] = scratch.get(max_reads * wpr * 8 + 16);
@@ -713,7 +719,7 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
     if (ro && ro->codes2)
       for (int b = 0; b < NB; ++b) d_codes2[b] = scratch.get(max_slots / 4 + 16);
     u64* d_base = nullptr;
-    u64* d_total_copy[3] = {nullptr, nullptr, nullptr};
+    u64* d_total_copy[MAXB] = {};
     cudaEvent_t base_ev = nullptr;
     struct EvGuard {
       cudaEvent_t* e;
@@ -730,8 +736,7 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
     }
     // hit runs: codes, per-read run counts / offsets and (worst case: every slot starts a run) the run records, per buffer;
     // the offsets come back through a small pinned array because the host needs each chunk's total to place its runs
-    void *d_codes[3] = {nullptr, nullptr, nullptr}, *d_rc[3] = {nullptr, nullptr, nullptr}, *d_rro[3] = {nullptr, nullptr, nullptr},
-         *d_runs[3] = {nullptr, nullptr, nullptr};
+    void *d_codes[MAXB] = {}, *d_rc[MAXB] = {}, *d_rro[MAXB] = {}, *d_runs[MAXB] = {};
     u64* h_rro[2] = {nullptr, nullptr};
     struct PinnedPair {
       u64** p;
@@ -778,8 +783,7 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
         MZ_CUDA(cudaMemcpyAsync(ro->codes + s0, d_codes[bb], ns, cudaMemcpyDeviceToHost, s));
       }
     };
-    scratch.publish(sp.s[1]);
-    if (NB == 3) scratch.publish(extra.s);
+    for (int bb = 1; bb < NB; ++bb) scratch.publish(st[bb]);
     int b = 0;
     for (size_t c = 0; c + 1 < cuts.size(); ++c, b = (b + 1) % NB) {
       u64 r0 = cuts[c], r1 = cuts[c + 1];
@@ -846,9 +850,7 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
     }
     if (ro && !runs_dev && cuts.size() > 1) finish_runs(cuts.size() - 2, b ^ 1);
     if (ro && runs_dev) {
-      MZ_CUDA(cudaStreamSynchronize(sp.s[0]));
-      MZ_CUDA(cudaStreamSynchronize(sp.s[1]));
-      if (extra.s) MZ_CUDA(cudaStreamSynchronize(extra.s));
+      for (int bb = 0; bb < NB; ++bb) MZ_CUDA(cudaStreamSynchronize(st[bb]));
       u64 end = 0;
       MZ_CUDA(cudaMemcpy(&end, d_base, 8, cudaMemcpyDeviceToHost));
       ro->n_runs = end - ro->base;
