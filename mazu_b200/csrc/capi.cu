@@ -681,9 +681,11 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
     // two buffers / streams alternate; the sync-free run path uses three, because its per-chunk chain (H2D, lookups, encode, two
     // D2H copies) is 2.3x as long as its compute and two streams leave the SMs idle a third of the time
     static const int MAXB = 6;
-    static const int nb_knob = [] {  // tuning knob: buffers / streams of the sync-free run pipeline (default 3)
+    static const int nb_knob = [] {  // buffers / streams of the sync-free run pipeline.  Measured on config 5 (ASCII reads in, byte codes
+      // out): 3 -> 1.93e10, 4 -> 2.07e10, 6 -> 2.39e10 lookups/s; a chunk's chain of copies and kernels is several times as
+      // long as its compute, so the pipeline has to be that deep to keep the SMs busy
       const char* e = getenv("MAZU_B200_RUN_STREAMS");
-      const int v = e ? atoi(e) : 3;
+      const int v = e ? atoi(e) : 6;
       return v < 2 ? 2 : (v > MAXB ? MAXB : v);
     }();
     const int NB = runs_dev ? nb_knob : 2;
