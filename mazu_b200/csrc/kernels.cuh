@@ -30,11 +30,9 @@ __device__ __forceinline__ Hit hit_none(u32 match) { return Hit{~0u, ~0u, ~0u, m
 // fire-and-forget fetch of the line holding *p into L2: used where a later dependent load's address is already known
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void store_hit(Hit* out, const Hit& h) {
-#ifdef MAZU_STREAM_STORES  // A/B build: evict-first stores for the result stream (19 GB per step that is never read back by the kernel)
+  // evict-first store: the result stream (16 B per lookup, 19 GB per step) is never read back by the kernel and should not push
+  // index lines out of the L2 (+1.6 % on config 5, +0.6 % on config 2 against a plain store)
   __stcs(reinterpret_cast<uint4*>(out), make_uint4(h.unitig_id, h.unitig_len, h.pos, h.match));
-#else
-  *reinterpret_cast<uint4*>(out) = make_uint4(h.unitig_id, h.unitig_len, h.pos, h.match);
-#endif
 }
 
 // record store: 16-byte mazu_hit_t, or the 8-byte mazu_hit8_t {unitig_id, pos | match << 30} of the compact calls
