@@ -9,20 +9,22 @@
 
 namespace {
 
-// every unitig k-mer looked up once: found anywhere but at its own position <=> the set holds a canonical k-mer twice
+// every unitig k-mer looked up once: found anywhere but at its own position <=> the set holds a canonical k-mer twice; the unitig
+// lines of both positions are flagged (the walk kernel settles cursors only around flagged lines)
 void detect_unique_kmers(mazu_index& ix) {
-  static const bool skip = getenv("MAZU_B200_FORCE_WALK") != nullptr;  // measurement knob: always take the cursor-walk kernel
+  static const bool force_walk = getenv("MAZU_B200_FORCE_WALK") != nullptr;  // measurement knob: always take the cursor-walk kernel
   ix.kmers_unique = false;
-  if (skip || ix.unitigs->total_len() < ix.unitigs->k) return;
+  if (ix.unitigs->total_len() < ix.unitigs->k) return;
   DevBuf d(8, ix.device);
   MZ_CUDA(cudaMemset(d.p, 0, 8));
   const u64 n = ix.unitigs->total_len();
   const int grid = (int)std::max<u64>(1, std::min<u64>((n + 255) / 256, (u64)ix.sm_count * 8));
-  count_duplicated_kmers_kernel<<<grid, 256>>>(ix.view, (unsigned long long*)d.p);
+  // the lines are written once more here (flags), before the handle is handed out; they are read-only from then on
+  flag_duplicated_kmers_kernel<<<grid, 256>>>(ix.view, const_cast<UnitigLine*>(ix.view.unitigs.lines), (unsigned long long*)d.p);
   MZ_CUDA(cudaGetLastError());
   u64 bad = 0;
   MZ_CUDA(cudaMemcpy(&bad, d.p, 8, cudaMemcpyDeviceToHost));
-  ix.kmers_unique = bad == 0;
+  ix.kmers_unique = bad == 0 && !force_walk;
 }
 
 mazu_index* finalize_index(std::unique_ptr<mazu_index> ix) {

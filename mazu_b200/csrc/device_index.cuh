@@ -143,7 +143,7 @@ std::shared_ptr<UnitigsDev> upload_unitigs(const UnitigSetHost& us, int dev) {
   const u64 L = us.total_len(), U = us.n_unitigs();
   if (U >> 32) throw Error(MAZU_ERR_INVALID_ARG, "more than 2^32 unitigs");
   for (u64 i = 0; i < U; ++i)  // hit records and unitig lines carry 32-bit lengths
-    if (us.accum[i + 1] - us.accum[i] >= (1ULL << 32) - 512) throw Error(MAZU_ERR_INVALID_ARG, "a unitig is longer than 2^32 - 512 bases");
+    if (us.accum[i + 1] - us.accum[i] >= (1ULL << 31) - 512) throw Error(MAZU_ERR_INVALID_ARG, "a unitig is longer than 2^31 - 512 bases");
   u64 nw = (2 * L + 63) / 64;
   auto b_seq = upload(us.useq.data(), std::min<u64>(nw, us.useq.size()), dev, 4);
   // directory: unitig containing the first base of every 2^DIR_SHIFT block

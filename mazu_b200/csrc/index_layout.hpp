@@ -148,9 +148,22 @@ MZ_HD bool mphf_lookup_t(const RankedLevels& m, u64 key, u64& out) {
         s0 = b;
         s1 = a;
       }
-      u64 pos = mulhi64(h, m.size[l]);  // fast_range_64 (mod.rs:136-144)
-      u64 blk = pos / MPHF_BLOCK_BITS;
-      u32 bit = (u32)(pos - blk * MPHF_BLOCK_BITS);
+      // fast_range_64 (mod.rs:136-144): (h * n_bits) >> 64.  Levels of fewer than 2^32 slots (every pufferfish index below
+      // 4e9 k-mers at gamma 3.5... and all fixtures) take two 32x32 multiplies and a 32-bit division instead of the 64-bit ones.
+      u64 blk;
+      u32 bit;
+      const u64 nb = m.size[l];
+      if ((nb >> 32) == 0) {
+        const u64 hi = (h >> 32) * nb, lo = (h & 0xFFFFFFFFULL) * nb;
+        const u32 pos = (u32)((hi + (lo >> 32)) >> 32);
+        const u32 b32 = pos / MPHF_BLOCK_BITS;
+        blk = b32;
+        bit = pos - b32 * MPHF_BLOCK_BITS;
+      } else {
+        const u64 pos = mulhi64(h, nb);
+        blk = pos / MPHF_BLOCK_BITS;
+        bit = (u32)(pos - blk * MPHF_BLOCK_BITS);
+      }
       if (ranked_test(m, l, blk, bit)) {
         hit_level = l;
         hit_blk = blk;
@@ -378,7 +391,9 @@ MZ_HD void blocked_ef_get2(const BlockedEFView& ef, u64 i, u64& a, u64& b) {
 // pays for on this part: profiles/r02_prand.json).  Line i covers bases [256 i, 256 i + 256), base = 256 i:
 //   seq[9]       the line's 256 bases + the 32 bases that follow, so a k-mer window (k <= 32) never straddles lines
 //   first_id     unitig containing `base`                start_delta  base - start of that unitig
-//   end_delta    (end of the unitig containing base + 255) - base
+//   end_delta    (end of the unitig containing base + 255) - base, in the low 31 bits; bit 31 = DUP flag: some k-mer that starts
+//                in this line occurs more than once in the unitig set (set at creation, flag_duplicated_kmers_kernel).  A
+//                streaming answer can differ from K2U::k2u only for such k-mers, so the walk kernel settles cursors only there
 //   ends[4]      bit j <=> base + j is the last base of a unitig (the reference's end-marker bit-vector,
 //                unitig_set.rs:146-149, cut into the line it belongs to)
 //   per 64-base word w of `ends` (one byte each, packed in a u32):
@@ -433,10 +448,7 @@ MZ_HD void unitig_locate(const UnitigsView& u, u64 pos, u64& id, u64& start, u64
   end = e;
 }
 
-#if defined(MAZU_FLAT_UNITIGS)  // A/B build: the round-1 layout (window, directory, starts in three separate arrays)
-MZ_HD u64 line_window(const UnitigsView& u, u64 pos) { return useq_window(u, pos); }
-MZ_HD void line_locate(const UnitigsView& u, u64 pos, u64& id, u64& start, u64& end) { unitig_locate(u, pos, id, start, end); }
-#elif defined(__CUDA_ARCH__) || defined(__CUDACC__)
+#if defined(__CUDA_ARCH__) || defined(__CUDACC__)
 // the same two primitives over unitig lines (query kernels): one DRAM line per verified candidate
 __device__ __forceinline__ u64 line_window(const UnitigsView& u, u64 pos) {
   const u64* ln = reinterpret_cast<const u64*>(u.lines + (pos >> ULINE_SHIFT));
@@ -445,7 +457,8 @@ __device__ __forceinline__ u64 line_window(const UnitigsView& u, u64 pos) {
   if (sh + 2 * u.k > 64) x |= __ldg(ln + wi + 1) << (64 - sh);
   return x & kmer_mask(u.k);
 }
-__device__ __forceinline__ void line_locate(const UnitigsView& u, u64 pos, u64& id, u64& start, u64& end) {
+static const u32 ULINE_DUP = 0x80000000u;
+__device__ __forceinline__ void line_locate(const UnitigsView& u, u64 pos, u64& id, u64& start, u64& end, u32* dup = nullptr) {
   const UnitigLine* L = u.lines + (pos >> ULINE_SHIFT);
   const u32 off = (u32)pos & 255u, wq = off >> 6;
   const u64 e = __ldg(L->ends + wq);
@@ -460,7 +473,8 @@ __device__ __forceinline__ void line_locate(const UnitigsView& u, u64 pos, u64& 
   if (lo) start = base + (u64)(64 * wq + 64 - __clzll((long long)lo));
   else start = prev != 255u ? base + prev + 1 : base - a.y;
   if (hi) end = base + (u64)(64 * wq + __ffsll((long long)hi));
-  else end = next != 0u ? base + next + 1 : base + b.x;
+  else end = next != 0u ? base + next + 1 : base + (b.x & ~ULINE_DUP);
+  if (dup) *dup = b.x >> 31;
 }
 #endif
 

@@ -91,9 +91,9 @@ __device__ __forceinline__ u32 word_equivalency(u64 fw, u64 rc, u64 kw) {
 
 // K2UPos from a verified useq position: pos_to_id, unitig_len, unitig_start_pos (+ the boundary
 // guard of src/kphf/sshash.rs:513-514,539-541 when `guard` is set)
-__device__ __forceinline__ bool finish_hit(const UnitigsView& u, u64 km_pos, u32 mt, bool guard, Hit& out, u64* ustart = nullptr) {
+__device__ __forceinline__ bool finish_hit(const UnitigsView& u, u64 km_pos, u32 mt, bool guard, Hit& out, u64* ustart = nullptr, u32* dup = nullptr) {
   u64 id, start, end;
-  line_locate(u, km_pos, id, start, end);
+  line_locate(u, km_pos, id, start, end, dup);
   if (guard && km_pos + u.k > end) return false;
   if (ustart) *ustart = start;
   out.unitig_id = (u32)id;
@@ -157,7 +157,7 @@ __device__ __forceinline__ bool sshash_k2u(const IndexView& ix, u64 fw, u64 rc, 
 }
 
 template <u32 FAMILY>
-__device__ __forceinline__ bool sampled_pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc, Hit& out, u64* ustart);
+__device__ __forceinline__ bool sampled_pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc, Hit& out, u64* ustart, u32* dup = nullptr);
 __device__ __forceinline__ bool k2u_any(const IndexView& ix, u64 fw, u64 rc, Hit& out) {
   if (ix.k2u_kind == MAZU_K2U_PFHASH) return pfhash_k2u(ix, fw, rc, out);
   if (ix.k2u_kind == MAZU_K2U_SAMPLED_PFHASH) return sampled_pfhash_k2u_t<MPHF_FAMILY_BOOPHF>(ix, fw, rc, out, nullptr);
@@ -398,7 +398,8 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
 
 // stage V for one k-mer of an SSHash index: the loop of sshash.rs:494-552 / k2u_skew_index
 template <u32 FAMILY>
-__device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpStage& S, u32 p, u64 fw, u64 rc, Hit& out, u64* ustart = nullptr) {
+__device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpStage& S, u32 p, u64 fw, u64 rc, Hit& out, u64* ustart = nullptr,
+                                              u32* dup = nullptr) {
   const u32 lp = S.leader[p];
   const u32 n = S.bn[lp];
   if (n == 0) return false;
@@ -411,7 +412,7 @@ __device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpSta
     u64 pos = packed_get(ix.skew_pos, hs);
     u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, pos));
     if (mt == NO_MATCH) return false;
-    return finish_hit(ix.unitigs, pos, mt, false, out, ustart);
+    return finish_hit(ix.unitigs, pos, mt, false, out, ustart, dup);
   }
   const u64 pos_start = S.bstart[lp];
   const u64 offset = S.off[p];
@@ -423,19 +424,19 @@ __device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpSta
     if (mm_pos >= offset && mm_pos - offset <= last_km_start_pos) {  // sshash.rs:498
       u64 km_pos = mm_pos - offset;
       u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
-      if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out, ustart)) return true;
+      if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out, ustart, dup)) return true;
     }
     if (rc_offset != offset && mm_pos >= rc_offset && mm_pos - rc_offset <= last_km_start_pos) {  // sshash.rs:527 (same window when equal)
       u64 km_pos = mm_pos - rc_offset;
       u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
-      if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out, ustart)) return true;
+      if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out, ustart, dup)) return true;
     }
   }
   return false;
 }
 
 template <u32 FAMILY>
-__device__ __forceinline__ bool pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc, Hit& out, u64* ustart = nullptr) {
+__device__ __forceinline__ bool pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc, Hit& out, u64* ustart = nullptr, u32* dup = nullptr) {
   u64 word = fw <= rc ? fw : rc;
   u64 h;
   if (!mphf_lookup_t<FAMILY>(ix.mphf, word, h)) return false;
@@ -443,13 +444,13 @@ __device__ __forceinline__ bool pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc
   u64 km_pos = packed_get(ix.pos, h);
   u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
   if (mt == NO_MATCH) return false;
-  return finish_hit(ix.unitigs, km_pos, mt, false, out, ustart);
+  return finish_hit(ix.unitigs, km_pos, mt, false, out, ustart, dup);
 }
 
 // SampledPFHash::k2u (src/kphf/pfhash.rs:190-285): sampled k-mers carry their position; the others walk
 // <= extension_size stored bases to the nearest sampled k-mer, re-hash, and shift the sampled position back.
 template <u32 FAMILY>
-__device__ __forceinline__ bool sampled_pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc, Hit& out, u64* ustart) {
+__device__ __forceinline__ bool sampled_pfhash_k2u_t(const IndexView& ix, u64 fw, u64 rc, Hit& out, u64* ustart, u32* dup) {
   const u32 k = ix.unitigs.k;
   u64 idx;
   if (!mphf_lookup_t<FAMILY>(ix.mphf, fw <= rc ? fw : rc, idx)) return false;
@@ -499,7 +500,7 @@ __device__ __forceinline__ bool sampled_pfhash_k2u_t(const IndexView& ix, u64 fw
   }
   u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, pos));
   if (mt == NO_MATCH) return false;
-  return finish_hit(ix.unitigs, pos, mt, false, out, ustart);
+  return finish_hit(ix.unitigs, pos, mt, false, out, ustart, dup);
 }
 
 struct StreamState {  // StreamingK2U { is_warm, prev_k2upos } (src/index/caching.rs:13-17)
@@ -617,16 +618,39 @@ __global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const _
           u64 fw = 0, rc = 0;
           Hit cold = hit_none(NO_MATCH);
           u64 cold_ustart = 0;
+          u32 cold_dup = 0;
           bool cold_hit = false;
           if (valid) {
             fw = S.fw[q];
             rc = SS ? S.rc[q] : revcomp(fw, k);
-            cold_hit = SS ? verify_sshash<FAMILY>(ix, S, q, fw, rc, cold, &cold_ustart)
-                          : (KIND == MAZU_K2U_SAMPLED_PFHASH ? sampled_pfhash_k2u_t<FAMILY>(ix, fw, rc, cold, &cold_ustart)
-                                                             : pfhash_k2u_t<FAMILY>(ix, fw, rc, cold, &cold_ustart));
+            cold_hit = SS ? verify_sshash<FAMILY>(ix, S, q, fw, rc, cold, &cold_ustart, &cold_dup)
+                          : (KIND == MAZU_K2U_SAMPLED_PFHASH ? sampled_pfhash_k2u_t<FAMILY>(ix, fw, rc, cold, &cold_ustart, &cold_dup)
+                                                             : pfhash_k2u_t<FAMILY>(ix, fw, rc, cold, &cold_ustart, &cold_dup));
             if (!cold_hit) cold = hit_none(NO_MATCH);
           }
           const u32 chm = __ballot_sync(0xffffffffu, cold_hit);
+          // The walk can answer differently from the lookup only for a k-mer the unitig set holds twice, and every occurrence of
+          // such a k-mer lies in a line flagged at creation (ULINE_DUP).  A group without a flagged cold hit therefore commits its
+          // cold answers as they are; the cursor is simply its last hit.
+          if (__ballot_sync(0xffffffffu, cold_hit && cold_dup) == 0) {
+            if (active) {
+              if (valid) {
+                ++n_valid;
+                if (cold_hit) ++n_hit;
+              }
+              if (o) store_rec(o, q, valid ? cold : hit_none(SKIPPED), compact);
+            }
+            if (chm) {
+              const int last = 31 - __clz(chm);
+              st.uid = __shfl_sync(0xffffffffu, cold.unitig_id, last);
+              st.ulen = __shfl_sync(0xffffffffu, cold.unitig_len, last);
+              st.pos = __shfl_sync(0xffffffffu, cold.pos, last);
+              st.o = __shfl_sync(0xffffffffu, cold.match, last);
+              st.ustart = __shfl_sync(0xffffffffu, cold_ustart, last);
+              st.warm = 1;
+            }
+            continue;
+          }
           u32 start = 0;  // first lane of the group that has not committed yet
 #pragma unroll 1
           while (true) {
@@ -1715,11 +1739,15 @@ __global__ void __launch_bounds__(256) k2u_validate_self_kernel(const __grid_con
 }
 
 // Are the canonical k-mers of the unitig set pairwise distinct (true for every compacted de Bruijn graph)?  Thread per useq
-// position: the k-mer there must be found AT that position; a hit elsewhere means the set holds the k-mer twice.  When they
-// are distinct, StreamingK2U (src/index/caching.rs:65-103) answers exactly what K2U::k2u answers -- a warm hit at
-// (unitig, pos + 1) is an occurrence of the k-mer, and there is only one -- so the launcher serves streaming queries
-// with the random-access kernel; the cursor walk is only needed for sets with duplicated k-mers.
-__global__ void __launch_bounds__(256) count_duplicated_kmers_kernel(const __grid_constant__ IndexView ix, unsigned long long* n_elsewhere) {
+// position: the k-mer there must be found AT that position; a hit elsewhere means the set holds the k-mer twice.
+//  * No duplicate: StreamingK2U (src/index/caching.rs:65-103) answers exactly what K2U::k2u answers -- a warm hit at
+//    (unitig, pos + 1) is an occurrence of the k-mer, and there is only one -- so the launcher serves streaming queries with
+//    the random-access kernel.
+//  * Duplicates: both the position at hand and the position the lookup returned get their unitig line flagged (ULINE_DUP):
+//    every occurrence of a duplicated k-mer then lies in a flagged line, and the walk kernel settles cursors only in groups
+//    that touch one.
+__global__ void __launch_bounds__(256) flag_duplicated_kmers_kernel(const __grid_constant__ IndexView ix, UnitigLine* __restrict__ lines,
+                                                                    unsigned long long* n_elsewhere) {
   const u32 k = ix.unitigs.k;
   const u64 total = ix.unitigs.total_len;
   u32 bad = 0;
@@ -1729,7 +1757,12 @@ __global__ void __launch_bounds__(256) count_duplicated_kmers_kernel(const __gri
     if (p + k > e) continue;
     const u64 fw = useq_window(ix.unitigs, p), rc = revcomp(fw, k);
     Hit h;
-    if (!k2u_any(ix, fw, rc, h) || h.unitig_id != (u32)id || h.pos != (u32)(p - s)) ++bad;
+    const bool found = k2u_any(ix, fw, rc, h);
+    if (!found || h.unitig_id != (u32)id || h.pos != (u32)(p - s)) {
+      ++bad;
+      atomicOr(&lines[p >> ULINE_SHIFT].end_delta, ULINE_DUP);
+      if (found) atomicOr(&lines[(ix.unitigs.starts[h.unitig_id] + h.pos) >> ULINE_SHIFT].end_delta, ULINE_DUP);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
