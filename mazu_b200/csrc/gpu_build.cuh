@@ -69,8 +69,9 @@ __global__ void __launch_bounds__(QR_WARPS * 32) collect_minimizers_kernel(const
           x = d < 32 ? (S.fw[QR_CHUNK - 1] >> (2 * d)) : 0ULL;
         }
         u64 wf = x & wmask;
-        S.hf[q] = mm_hash32(wf, seed) & MM_KEY_MASK;
-        S.hr[QR_BASES - 1 - q] = mm_hash32(revcomp(wf, w), seed) & MM_KEY_MASK;
+        const u32 key = mm_key(wf, revcomp(wf, w), seed);
+        S.hf[q] = key;
+        S.hr[QR_BASES - 1 - q] = key;
       }
       __syncwarp();
 #pragma unroll 1
@@ -84,8 +85,9 @@ __global__ void __launch_bounds__(QR_WARPS * 32) collect_minimizers_kernel(const
           bool fw_canon = fw <= rc;
           const u32* h = fw_canon ? S.hf + p : S.hr + (QR_BASES - 1 - p - span);
           u32 bi = window_min(h, span) & 31u;
-          mmw = ((fw_canon ? fw : rc) >> (2 * bi)) & wmask;
-          apos = s + c0 + p + (fw_canon ? bi : span - bi);  // occurrence position on the forward strand
+          const u32 off_fw = fw_canon ? bi : span - bi;
+          mmw = mm_word_of(fw, rc, off_fw, k, w);
+          apos = s + c0 + p + off_fw;  // occurrence position on the forward strand
           stream = fw_canon ? 0u : 1u;
         }
 #pragma unroll

@@ -526,8 +526,7 @@ inline void collect_unitig_minimizers(const UnitigSetHost& us, u64 ui, u32 w, u6
       f = ((f >> 2) | (c << (2 * (w - 1)))) & wmask;
       r = ((r << 2) | (3 - c)) & wmask;
       if (i + 1 >= w) {
-        hf[i + 1 - w] = mm_hash32(f, seed) & MM_KEY_MASK;
-        hr[i + 1 - w] = mm_hash32(r, seed) & MM_KEY_MASK;
+        hf[i + 1 - w] = hr[i + 1 - w] = mm_key(f, r, seed);  // strand-symmetric key (minimizer order v3)
       }
     }
   }
@@ -545,15 +544,16 @@ inline void collect_unitig_minimizers(const UnitigSetHost& us, u64 ui, u32 w, u6
       u64 p = i + 1 - k;  // k-mer start inside the unitig
       bool fw_canon = fw <= rc;
       if (fw_canon != (pass == 0)) continue;
-      // smallest (hash key | offset in the canonical k-mer): minimizer order v2 (kmer.hpp)
+      // smallest (hash key | offset in the canonical k-mer): minimizer order v3 (kmer.hpp)
       u32 best = 0xFFFFFFFFu;
       for (u32 ci = 0; ci <= span; ++ci) {
         u32 key = (fw_canon ? hf[p + ci] : hr[p + span - ci]) | ci;
         best = key < best ? key : best;
       }
       u32 best_i = best & 31u;
-      u64 word = ((fw_canon ? fw : rc) >> (2 * best_i)) & wmask;
       u64 off_fw = fw_canon ? best_i : (span - best_i);  // offset in fw-mer coordinates
+      const u64 wf = (fw >> (2 * off_fw)) & wmask, wr = (rc >> (2 * (span - off_fw))) & wmask;
+      u64 word = wf <= wr ? wf : wr;
       MinOcc cur{word, s + p + off_fw};
       if (!have_prev || cur.word != prev.word || cur.pos != prev.pos) out.push_back(cur);
       prev = cur;

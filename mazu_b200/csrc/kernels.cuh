@@ -134,8 +134,14 @@ __device__ __forceinline__ bool sshash_finish(const IndexView& ix, u64 fw, u64 r
   const u32 k = ix.unitigs.k;
   const u64 last_km_start_pos = ix.unitigs.total_len - k;
   const u64 rc_offset = (u64)(k - offset - ix.w);
+  u64 prev_mm_pos = ~0ULL;
   for (u64 pi = pos_start; pi < pos_end; ++pi) {
     u64 mm_pos = packed_get(ix.pos, pi);
+    // Under the strand-symmetric minimizer order a super-k-mer that spans a strand flip is pushed by both of the reference's
+    // streams (sshash.rs:100-143), so a bucket often holds the same position twice in a row: the same two candidates, which
+    // have just failed.
+    if (mm_pos == prev_mm_pos) continue;
+    prev_mm_pos = mm_pos;
     if (mm_pos >= offset && mm_pos - offset <= last_km_start_pos) {  // sshash.rs:498
       u64 km_pos = mm_pos - offset;
       u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
@@ -278,9 +284,8 @@ __device__ __forceinline__ bool chunk_valid(const ChunkInfo& ci, u32 q) {
 
 // canonical-orientation minimizer word of the k-mer at chunk position p, from its stored offset
 __device__ __forceinline__ u64 mm_word_of(u64 fw, u64 rc, u32 off_fw, u32 k, u32 w) {
-  bool fw_canon = fw <= rc;
-  u32 ci = fw_canon ? off_fw : (k - w - off_fw);
-  return ((fw_canon ? fw : rc) >> (2 * ci)) & kmer_mask(w);
+  const u64 wf = (fw >> (2 * off_fw)) & kmer_mask(w), wr = (rc >> (2 * (k - w - off_fw))) & kmer_mask(w);  // the w-mer on either strand
+  return wf <= wr ? wf : wr;
 }
 
 // smallest (hash key | offset) over h[0..span]; unrolled for the spans of the named configs
@@ -313,7 +318,8 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
 #pragma unroll
   for (int t = 0; t < 4; ++t) S.rc[32 * t + lane] = revcomp(S.fw[32 * t + lane], k);
   __syncwarp();
-  // w-mer hash keys for chunk positions [0, 160): w-mer q is the low 2w bits of k-mer q (q < 128),
+  // w-mer hash keys for chunk positions [0, 160), stored twice (hf upwards, hr REVERSED) so that the window scan of a
+  // fw-canonical and of an rc-canonical k-mer both run upwards with `| c`: w-mer q is the low 2w bits of k-mer q (q < 128),
   // positions beyond come from the tail of k-mer 127.  Its reverse complement is the low 2w bits of
   // rc(k-mer q - span) (the top w bases of that k-mer), so no w-mer is reverse-complemented on its own.
   // Only w-mers q <= 127 + span belong to a k-mer of the chunk; the keys beyond are never read.
@@ -328,8 +334,9 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
     }
     u64 wf = x & wmask;
     u64 wr = q >= span ? S.rc[min(q - span, (u32)QR_CHUNK - 1)] : (S.rc[0] >> (2 * (span - q)));
-    S.hf[q] = mm_hash32(wf, ix.seed) & MM_KEY_MASK;
-    S.hr[QR_BASES - 1 - q] = mm_hash32(wr & wmask, ix.seed) & MM_KEY_MASK;
+    const u32 key = mm_key(wf, wr & wmask, ix.seed);  // one strand-symmetric key per w-mer position (minimizer order v3)
+    S.hf[q] = key;
+    S.hr[QR_BASES - 1 - q] = key;
   }
   __syncwarp();
   // per k-mer minimizer, leader detection, leader compaction
@@ -349,8 +356,9 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
       const u32* h = fw_canon ? S.hf + p : S.hr + (QR_BASES - 1 - p - span);
       u32 best = window_min(h, span);
       u32 bi = best & 31u;
-      mmw = ((fw_canon ? fw : rc) >> (2 * bi)) & wmask;
-      S.off[p] = (u8)(fw_canon ? bi : span - bi);
+      const u32 off_fw = fw_canon ? bi : span - bi;
+      mmw = mm_word_of(fw, rc, off_fw, k, w);
+      S.off[p] = (u8)off_fw;
     }
     // neighbour's minimizer (lane-1, or lane 31 of the previous pass)
     u64 prev_mm = __shfl_up_sync(0xffffffffu, mmw, 1);
@@ -419,8 +427,11 @@ __device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpSta
   const u64 rc_offset = (u64)(k - ix.w) - offset;
   const u64 last_km_start_pos = ix.unitigs.total_len - k;
 #pragma unroll 1
+  u64 prev_mm_pos = ~0ULL;
   for (u32 e = 0; e < n; ++e) {
     u64 mm_pos = packed_get(ix.pos, pos_start + e);
+    if (mm_pos == prev_mm_pos) continue;  // same entry twice in a row (both streams of the builder): same candidates, already failed
+    prev_mm_pos = mm_pos;
     if (mm_pos >= offset && mm_pos - offset <= last_km_start_pos) {  // sshash.rs:498
       u64 km_pos = mm_pos - offset;
       u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));

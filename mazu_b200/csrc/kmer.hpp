@@ -56,10 +56,14 @@ MZ_HD u64 mulhi64(u64 a, u64 b) {
 #endif
 }
 
-// Minimizer order v2 (DESIGN.md "Minimizer order"): a seeded 32-bit multiplicative mixer of the
-// w-mer word.  A w-mer at offset ci (0..k-w, k-w <= 31) of the CANONICAL k-mer gets the key
-//     (mm_hash32(wmer) & 0xFFFFFFE0) | ci
-// and the minimizer is the w-mer with the smallest key (top 27 hash bits, ties -> leftmost).
+// Minimizer order v3 (DESIGN.md "Minimizer order"): a seeded 32-bit multiplicative mixer of the
+// STRAND-SYMMETRIC w-mer word min(wmer, revcomp(wmer)).  The w-mer at offset ci (0..k-w, k-w <= 31) of the
+// CANONICAL k-mer gets the key
+//     (mm_hash32(min(wmer, rc(wmer))) & 0xFFFFFFE0) | ci
+// the w-mer with the smallest key wins (top 27 hash bits, ties -> leftmost in the canonical k-mer), and the
+// minimizer WORD is min(wmer, rc(wmer)).  A k-mer and its neighbour therefore keep their minimizer when the
+// canonical strand flips between them (it flips every other k-mer on average): a 150 bp read has ~18
+// super-k-mers instead of ~60 under v2, which hashed the w-mer as read off the canonical strand.
 // Stands in for kmers::canonical_minimizer + wyhash 0.5.0 (neither is in the reference tree, so
 // no hash could be pinned); k-mer -> unitig results do not depend on it.
 MZ_HD u32 mm_hash32(u64 x, u64 seed) {
@@ -106,19 +110,22 @@ struct MinimizerResult {
   u64 word;
   u32 offset;
 };
+MZ_HD u32 mm_key(u64 wf, u64 wr, u64 seed) { return mm_hash32(wf <= wr ? wf : wr, seed) & MM_KEY_MASK; }
 MZ_HD MinimizerResult canonical_minimizer_naive(u64 fw, u64 rc, u32 k, u32 w, u64 seed) {
-  bool fw_canon = fw <= rc;
-  u64 c = fw_canon ? fw : rc;
-  u64 wmask = kmer_mask(w);
+  const bool fw_canon = fw <= rc;
+  const u64 c = fw_canon ? fw : rc, d = fw_canon ? rc : fw;  // canonical strand, other strand
+  const u64 wmask = kmer_mask(w);
+  const u32 span = k - w;
   u32 best = 0xFFFFFFFFu;
-  for (u32 i = 0; i + w <= k; ++i) {
-    u32 key = (mm_hash32((c >> (2 * i)) & wmask, seed) & MM_KEY_MASK) | i;
+  for (u32 i = 0; i <= span; ++i) {  // the w-mer at offset i of c is the reverse complement of the one at offset span - i of d
+    u32 key = mm_key((c >> (2 * i)) & wmask, (d >> (2 * (span - i))) & wmask, seed) | i;
     best = key < best ? key : best;
   }
-  u32 best_i = best & 31u;
+  const u32 best_i = best & 31u;
+  const u64 a = (c >> (2 * best_i)) & wmask, b = (d >> (2 * (span - best_i))) & wmask;
   MinimizerResult r;
-  r.word = (c >> (2 * best_i)) & wmask;
-  r.offset = fw_canon ? best_i : (k - best_i - w);
+  r.word = a <= b ? a : b;
+  r.offset = fw_canon ? best_i : (span - best_i);
   return r;
 }
 

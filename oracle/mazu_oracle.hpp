@@ -219,10 +219,12 @@ inline void for_each_canonical_kmer(const u8* seq, u64 len, int k, F&& f) {
 // ------------------------------------------------------------------------------------
 // Minimizer order.  PARITY UNPINNED: stands in for kmers::Kmer::canonical_minimizer(w,&bh)
 // with bh = WyHashState(seed) (kphf/mod.rs:32-52); neither `kmers` nor `wyhash` is in the
-// reference tree.  Order v2 (shared definition): the w-mer at offset ci of the
-// CANONICAL k-mer has key (mm_hash32(wmer) & 0xFFFFFFE0) | ci; the smallest key wins (top 27
-// hash bits, ties -> leftmost).  Definition of "canonical minimizer" (sshash.rs:32-37):
-// mini(g*) = mini(min(g, g')).
+// reference tree.  Order v3 (shared definition): the w-mer at offset ci of the
+// CANONICAL k-mer has key (mm_hash32(min(wmer, rc(wmer))) & 0xFFFFFFE0) | ci; the smallest key
+// wins (top 27 hash bits, ties -> leftmost) and the minimizer word is min(wmer, rc(wmer)) -- the
+// order is symmetric in the strand, so neighbouring k-mers keep their minimizer when the
+// canonical strand flips.  Definition of "canonical minimizer" (sshash.rs:32-37):
+// mini(g*) = mini(min(g, g')): still a function of the canonical k-mer only.
 // ------------------------------------------------------------------------------------
 inline u32 mm_hash32(u64 x, u64 seed) {
   u32 h = ((u32)x ^ (u32)seed) * 0x85EBCA6Bu;
@@ -242,17 +244,19 @@ struct Minimizer {
 };
 inline Minimizer canonical_minimizer(u64 fw_word, int k, int w, u64 seed) {
   u64 rc = revcomp_word(fw_word, k);
-  u64 c = fw_word <= rc ? fw_word : rc;
   const bool fw_canon = fw_word <= rc;
+  const u64 c = fw_canon ? fw_word : rc, d = fw_canon ? rc : fw_word;  // canonical strand / the other one
   const u64 wmask = kmer_mask(w);
   Minimizer best{0, 0};
   u32 best_key = 0;
   for (int i = 0; i + w <= k; ++i) {  // i = offset inside the canonical k-mer
     u64 wm = (c >> (2 * i)) & wmask;
-    u32 key = (mm_hash32(wm, seed) & 0xFFFFFFE0u) | (u32)i;
+    u64 wm_rc = (d >> (2 * (k - w - i))) & wmask;  // the same w-mer read off the other strand
+    u64 sym = wm <= wm_rc ? wm : wm_rc;
+    u32 key = (mm_hash32(sym, seed) & 0xFFFFFFE0u) | (u32)i;
     if (i == 0 || key < best_key) {
       best_key = key;
-      best = Minimizer{wm, fw_canon ? (u64)i : (u64)(k - i - w)};
+      best = Minimizer{sym, fw_canon ? (u64)i : (u64)(k - i - w)};
     }
   }
   return best;
