@@ -85,6 +85,14 @@ void check_k(const mazu_index* ix, u32 k) {
 
 void launch_k2u_batch(const mazu_index* ix, const u64* d_words, u64 n, Hit* d_out, cudaStream_t s) {
   if (n == 0) return;
+  if (ix->view.k2u_kind == MAZU_K2U_PFHASH) {  // several keys per lane through one MPHF level loop
+    const bool native = ix->view.mphf.family == MPHF_FAMILY_NATIVE;
+    auto kern = native ? k2u_batch_pfhash_kernel<MPHF_FAMILY_NATIVE> : k2u_batch_pfhash_kernel<MPHF_FAMILY_BOOPHF>;
+    int grid = grid_for(kern, 256, ix, (u64)KB_N * 256, n);
+    kern<<<grid, 256, 0, s>>>(ix->view, d_words, n, d_out);
+    MZ_CUDA(cudaGetLastError());
+    return;
+  }
   int grid = grid_for(k2u_batch_kernel, 256, ix, 256, n);
   k2u_batch_kernel<<<grid, 256, 0, s>>>(ix->view, d_words, n, d_out);
   MZ_CUDA(cudaGetLastError());

@@ -106,6 +106,23 @@ MZ_HD u64 ranked_rank(const RankedLevels& m, u32 level, u64 blk, u32 bit) {
 // member -- is what a warp of mixed lookups pays for.  Costs ~5.2 instead of 3.3 bits per key.
 MZ_HD double native_level_gamma(double gamma, u32 level) { return level < 2 ? gamma : (level == 2 ? 4.0 * gamma : 32.0 * gamma); }
 
+// fast_range_64 (mod.rs:136-144): slot = (h * n_bits) >> 64, then (block, bit) in the re-blocked level.  Levels of fewer than
+// 2^32 slots (every pufferfish index below 4e9 k-mers, and all fixtures) take two 32x32 multiplies and a 32-bit division
+// instead of the 64-bit ones.
+MZ_HD void boophf_slot(u64 h, u64 nb, u64& blk, u32& bit) {
+  if ((nb >> 32) == 0) {
+    const u64 hi = (h >> 32) * nb, lo = (h & 0xFFFFFFFFULL) * nb;
+    const u32 pos = (u32)((hi + (lo >> 32)) >> 32);
+    const u32 b32 = pos / MPHF_BLOCK_BITS;
+    blk = b32;
+    bit = pos - b32 * MPHF_BLOCK_BITS;
+  } else {
+    const u64 pos = mulhi64(h, nb);
+    blk = pos / MPHF_BLOCK_BITS;
+    bit = (u32)(pos - blk * MPHF_BLOCK_BITS);
+  }
+}
+
 // MPHF::try_hash_u64 (src/kphf/mod.rs:54-56).  BOOPHF reproduces BooPHF<u64>::lookup
 // (src/pf1/boophf/mod.rs:96-181) bit-exactly; NATIVE is this library's own BBHash-style MPHF.
 // Like boomphf::try_hash, a non-member key may return a false-positive value < n_keys.
@@ -148,22 +165,9 @@ MZ_HD bool mphf_lookup_t(const RankedLevels& m, u64 key, u64& out) {
         s0 = b;
         s1 = a;
       }
-      // fast_range_64 (mod.rs:136-144): (h * n_bits) >> 64.  Levels of fewer than 2^32 slots (every pufferfish index below
-      // 4e9 k-mers at gamma 3.5... and all fixtures) take two 32x32 multiplies and a 32-bit division instead of the 64-bit ones.
       u64 blk;
       u32 bit;
-      const u64 nb = m.size[l];
-      if ((nb >> 32) == 0) {
-        const u64 hi = (h >> 32) * nb, lo = (h & 0xFFFFFFFFULL) * nb;
-        const u32 pos = (u32)((hi + (lo >> 32)) >> 32);
-        const u32 b32 = pos / MPHF_BLOCK_BITS;
-        blk = b32;
-        bit = pos - b32 * MPHF_BLOCK_BITS;
-      } else {
-        const u64 pos = mulhi64(h, nb);
-        blk = pos / MPHF_BLOCK_BITS;
-        bit = (u32)(pos - blk * MPHF_BLOCK_BITS);
-      }
+      boophf_slot(h, m.size[l], blk, bit);
       if (ranked_test(m, l, blk, bit)) {
         hit_level = l;
         hit_blk = blk;
@@ -189,6 +193,77 @@ MZ_HD bool mphf_lookup_t(const RankedLevels& m, u64 key, u64& out) {
   }
   return false;
 }
+// lookup_in_final_hash (mod.rs:177-181) / native leftovers
+MZ_HD bool mphf_fallback(const RankedLevels& m, u64 key, u64& out) {
+  u32 lo = 0, hi = m.n_fb;
+  while (lo < hi) {
+    u32 mid = (lo + hi) >> 1;
+    u64 kk = MZ_LDG(m.fb_keys + mid);
+    if (kk == key) {
+      out = MZ_LDG(m.fb_vals + mid);
+      return true;
+    }
+    if (kk < key) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+
+#if defined(__CUDACC__)
+// The level loop of mphf_lookup_t for SEVERAL keys per lane, the lane refilling itself: a lane whose key is placed moves on to
+// its next key in the same loop iteration count as its neighbours keep probing levels, so the warp's loop runs
+// max-over-lanes(sum of levels of the lane's keys) times instead of (number of keys) x max-over-lanes(levels of one key) --
+// 61-69 % of the lanes busy per iteration for 4-8 keys per lane, against 28 % for one key per lane (a level places ~61 % of
+// its keys, the slowest of 32 lanes needs ~6 levels).
+// In : a[j * stride] (and b[j * stride] for BOOPHF) = the level-0 (level-1) hash of the lane's key j < n_mine -- BOOPHF:
+//      boophf_hash64(key, SEED0 / SEED1), the MultiHashState of src/pf1/boophf/hash.rs:91-97; NATIVE: fmix64(key).
+// Out: a[j * stride] = MPHF_MULTI_NONE, or level << 56 | block << 8 | bit of the set slot (rank it with mphf_multi_rank).
+// The arrays live in shared memory (they are indexed by the lane's own progress).
+static const u64 MPHF_MULTI_NONE = ~0ULL;
+template <u32 FAMILY>
+__device__ __forceinline__ void mphf_levels_multi(const RankedLevels& m, u64* a, u64* b, u32 stride, u32 n_mine) {
+  if (n_mine == 0) return;
+  u32 j = 0, l = 0;
+  u64 s0 = a[0], s1 = FAMILY == MPHF_FAMILY_NATIVE ? 0ULL : b[0];
+  const u32 n_levels = m.n_levels;
+#pragma unroll 1
+  while (j < n_mine) {
+    u64 blk;
+    u32 bit;
+    if (FAMILY == MPHF_FAMILY_NATIVE) {
+      native_slot_from(s0, l, m.size[l], blk, bit);
+    } else {
+      u64 h = l == 0 ? s0 : s1;
+      if (l >= 2) {  // xorshift128+ step of the MultiHashState (hash.rs:111-135)
+        u64 x = s0, y = s1;
+        x ^= x << 23;
+        x = x ^ y ^ (x >> 17) ^ (y >> 26);
+        h = x + y;
+        s0 = y;
+        s1 = x;
+      }
+      boophf_slot(h, m.size[l], blk, bit);
+    }
+    const bool hit = ranked_test(m, l, blk, bit);
+    if (hit || l + 1 >= n_levels) {
+      a[j * stride] = hit ? ((u64)l << 56) | (blk << 8) | bit : MPHF_MULTI_NONE;
+      ++j;
+      l = 0;
+      if (j < n_mine) {
+        s0 = a[j * stride];
+        if (FAMILY != MPHF_FAMILY_NATIVE) s1 = b[j * stride];
+      }
+    } else {
+      ++l;
+    }
+  }
+}
+__device__ __forceinline__ bool mphf_multi_rank(const RankedLevels& m, u64 packed, u64 key, u64& out) {
+  if (packed == MPHF_MULTI_NONE) return mphf_fallback(m, key, out);
+  out = ranked_rank(m, (u32)(packed >> 56), (packed >> 8) & 0xFFFFFFFFFFFFULL, (u32)(packed & 255u));
+  return true;
+}
+#endif
+
 MZ_HD bool mphf_lookup(const RankedLevels& m, u64 key, u64& out) {
   return m.family == MPHF_FAMILY_NATIVE ? mphf_lookup_t<MPHF_FAMILY_NATIVE>(m, key, out) : mphf_lookup_t<MPHF_FAMILY_BOOPHF>(m, key, out);
 }
@@ -246,10 +321,10 @@ MZ_HD u32 blocked_ef_fp(const BlockedEFView& ef, u64 i) {
 //     0 EMPTY      no key of the level maps here        -> a queried key is provably not a member
 //     1 COLLIDED   two or more keys map here            -> they were all sent to the next level: go on
 //     2..255       exactly one key: its fingerprint     -> equal: found, the bounds are in the block just read; else not a member
-// A member pays 1.65 probes on average (each the 128-byte line that also holds its bucket bounds), a non-member 1.1 --
+// A member pays 1.28 probes on average (each the 128-byte line that also holds its bucket bounds), a non-member 1.03 --
 // the reference's chain (MPHF levels, then Elias-Fano bounds, src/kphf/sshash.rs:478-483) pays both and learns that a
 // minimizer is foreign only at the k-mer compare.  The hash is not minimal: the bounds array has one (possibly empty)
-// bucket per slot, ~3.7 slots per key at 2 bytes each.  Leftover keys (after MPHF_MAX_LEVELS levels) sit in the sorted
+// bucket per slot, ~5.3 slots per key at 2 bytes each.  Leftover keys (after MPHF_MAX_LEVELS levels) sit in the sorted
 // fallback list with slots behind the last level.
 // ---------------------------------------------------------------------------------------------
 static const u32 CASCADE_EMPTY = 0, CASCADE_COLLIDED = 1;
@@ -271,10 +346,17 @@ MZ_HD u64 cascade_slot(u64 hk, u32 level, u64 size) {
   a ^= a >> 16;
   return mulhi32(a, (u32)size);
 }
-// slots of level `l` for `n` keys: 2 slots per key on the first two levels (61 % of the keys of a level are alone in their
-// slot), then 4 and 8: the few keys left are placed quickly and the cascade stays shallow
+// slots of level `l` for `n` keys: 4 slots per key on the first two levels (78 % of the keys of a level are alone in their
+// slot, a member pays 1.28 probes on average, and 78 % of the level-0 slots are empty so a non-member usually stops at once),
+// then 8.  Measured against 2/2/4/8 (profiles/experiments/README.md, round 2): config 5 reads +3.4 %, flat k-mers +8.8 %,
+// for 1.2 GB more index at human scale (5.3 slots of 2 bytes per key instead of 3.7).
 MZ_HD u64 cascade_level_size(u64 n, u32 level) {
-  const u64 g = level < 2 ? 2 : (level == 2 ? 4 : 8);
+#ifndef MAZU_CASCADE_G0
+#define MAZU_CASCADE_G0 4
+#define MAZU_CASCADE_G1 4
+#define MAZU_CASCADE_G2 8
+#endif
+  const u64 g = level == 0 ? MAZU_CASCADE_G0 : (level == 1 ? MAZU_CASCADE_G1 : (level == 2 ? MAZU_CASCADE_G2 : 8));
   const u64 s = g * n;
   return s < 32 ? 32 : s;
 }

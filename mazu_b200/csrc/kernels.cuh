@@ -186,6 +186,56 @@ __global__ void __launch_bounds__(256) k2u_batch_kernel(const __grid_constant__ 
   }
 }
 
+// K2U::k2u over a flat batch on a PFHash index (src/kphf/pfhash.rs:108-134; configs[0]: the pufferfish DenseIndex).
+// The MPHF level loop is the divergent part of such a lookup -- one key per lane keeps 12 of 32 lanes busy
+// (profiles/r01k_prof_config1.summary.txt) -- so a lane takes KB_N keys and walks them through ONE loop, refilling itself
+// (mphf_levels_multi); the hashes before the loop and rank / position / window / unitig bounds after it run with all lanes.
+static const int KB_N = 4;
+template <u32 FAMILY>
+__global__ void __launch_bounds__(256) k2u_batch_pfhash_kernel(const __grid_constant__ IndexView ix, const u64* __restrict__ fw_words, u64 n,
+                                                               Hit* __restrict__ out) {
+  __shared__ u64 sa[KB_N * 256];
+  __shared__ u64 sb[FAMILY == MPHF_FAMILY_NATIVE ? 1 : KB_N * 256];
+  const u32 k = ix.unitigs.k, tid = threadIdx.x;
+  const u64 kmask = kmer_mask(k), tile = (u64)KB_N * 256;
+  for (u64 base = (u64)blockIdx.x * tile; base < n; base += (u64)gridDim.x * tile) {
+    u64 fw[KB_N];
+    u32 n_mine = 0;
+#pragma unroll
+    for (int j = 0; j < KB_N; ++j) {
+      const u64 i = base + (u64)j * 256 + tid;
+      fw[j] = 0;
+      if (i < n) {
+        fw[j] = fw_words[i] & kmask;
+        const u64 rc = revcomp(fw[j], k), key = fw[j] <= rc ? fw[j] : rc;
+        if (FAMILY == MPHF_FAMILY_NATIVE) {
+          sa[j * 256 + tid] = fmix64(key);
+        } else {
+          sa[j * 256 + tid] = boophf_hash64(key, BOOPHF_SEED0);
+          sb[j * 256 + tid] = boophf_hash64(key, BOOPHF_SEED1);
+        }
+        n_mine = j + 1;
+      }
+    }
+    mphf_levels_multi<FAMILY>(ix.mphf, sa + tid, sb + (FAMILY == MPHF_FAMILY_NATIVE ? 0 : tid), 256, n_mine);
+#pragma unroll
+    for (int j = 0; j < KB_N; ++j) {
+      const u64 i = base + (u64)j * 256 + tid;
+      if (i < n) {
+        const u64 rc = revcomp(fw[j], k);
+        Hit h = hit_none(NO_MATCH);
+        u64 hv;
+        if (mphf_multi_rank(ix.mphf, sa[j * 256 + tid], fw[j] <= rc ? fw[j] : rc, hv) && hv < ix.pos.len) {
+          const u64 km_pos = packed_get(ix.pos, hv);
+          const u32 mt = word_equivalency(fw[j], rc, line_window(ix.unitigs, km_pos));
+          if (mt == NO_MATCH || !finish_hit(ix.unitigs, km_pos, mt, false, h)) h = hit_none(NO_MATCH);
+        }
+        store_hit(out + i, h);
+      }
+    }
+  }
+}
+
 // measurement hook: level-0 MPHF block of every query's key
 __global__ void probe_key_kernel(const __grid_constant__ IndexView ix, const u64* __restrict__ fw_words, u64 n, u32* __restrict__ out_block) {
   const u32 k = ix.unitigs.k;
