@@ -455,7 +455,7 @@ def main():
                 bases[r0 * READ_LEN:(r0 + n) * READ_LEN] = acgt[codes.long()].reshape(-1)
         hits = torch.empty((n_units, 4), dtype=torch.int32, device=dev)
         counts = torch.zeros(3, dtype=torch.int64, device=dev)
-        kernel_name = "mazu::query_reads_kernel<%d,SSHASH,NATIVE>" % (0 if mode == mz.MODE_RANDOM else 1)
+        kernel_name = "mazu::query_reads_kernel<%d,SSHASH,CASCADE>" % (0 if mode == mz.MODE_RANDOM else 1)
         launches_per_step = 1
 
         def step():
@@ -678,7 +678,7 @@ def main():
             q = np.tile(qs, reps)
             rng.shuffle(q)
             kmers = torch.from_numpy(q.view(np.int64)).to(dev)
-            kernel_name = "mazu::k2u_batch_kernel (PFHash/BooPHF)"
+            kernel_name = "mazu::k2u_batch_pfhash_kernel<BOOPHF>"
         else:
             n = args.reads * nk_per_read
             kmers = _gen.device_kmers_from_packed(torch, useq_dev, n_bases, n, K, gen, 0.5)
