@@ -279,10 +279,16 @@ static const u32 BN_SKEW = 0xFFFFFFFFu;
 struct WarpStage {
   u64 fw[QR_CHUNK];      // forward k-mer word per chunk position (garbage where invalid)
   u64 rc[QR_CHUNK];      // its reverse complement, written by stage M (SSHash only) so stages B and V do not recompute it
-  u64 bstart[QR_CHUNK];  // leaders only: first bucket entry
+  u64 bstart[QR_CHUNK];  // leaders only: index of the first bucket entry
+  union {
+    struct {
+      u32 hf[QR_BASES];  // w-mer hash keys (stage M) ...
+      u32 hr[QR_BASES];  // ... and the same keys stored REVERSED (hr[QR_BASES-1-q]) so both strands scan upwards
+    };
+    u64 bfirst[QR_CHUNK];  // leaders only: the first bucket entry itself (minimizer position), fetched by the leader once the
+                           // keys are dead (stage B); 2 * QR_BASES * 4 >= QR_CHUNK * 8
+  };
   u32 bn[QR_CHUNK];      // leaders only: bucket size, 0 = minimizer unknown, BN_SKEW = heavy bucket
-  u32 hf[QR_BASES];      // w-mer hash keys, forward strand
-  u32 hr[QR_BASES];      // w-mer hash keys, reverse strand, stored REVERSED (hr[QR_BASES-1-q]) so both strands scan upwards
   u8 off[QR_CHUNK];      // minimizer offset in fw-mer coordinates
   u8 leader[QR_CHUNK];   // chunk position of this k-mer's leader
   u8 lead_list[QR_CHUNK];
@@ -443,6 +449,9 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
         blocked_ef_get2(ix.sizes, h, a, b);
         u64 cnt = b - a;
         n = cnt > ix.skew_param ? BN_SKEW : (u32)cnt;
+        // the bucket's first entry now, once per super-k-mer: stage V then starts at the unitig line (one dependent DRAM access
+        // per group of 32 k-mers instead of two)
+        if (cnt && n != BN_SKEW) S.bfirst[p] = packed_get(ix.pos, a);
 #ifdef MAZU_PREFETCH  // measured and rejected (profiles/experiments/README.md): -2 % config 5, -5 % config 2
         if (cnt && n != BN_SKEW) prefetch_l2(ix.pos.words + ((a * ix.pos.width) >> 6));
 #endif
@@ -479,7 +488,7 @@ __device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpSta
 #pragma unroll 1
   u64 prev_mm_pos = ~0ULL;
   for (u32 e = 0; e < n; ++e) {
-    u64 mm_pos = packed_get(ix.pos, pos_start + e);
+    u64 mm_pos = e == 0 ? S.bfirst[lp] : packed_get(ix.pos, pos_start + e);
     if (mm_pos == prev_mm_pos) continue;  // same entry twice in a row (both streams of the builder): same candidates, already failed
     prev_mm_pos = mm_pos;
     if (mm_pos >= offset && mm_pos - offset <= last_km_start_pos) {  // sshash.rs:498
