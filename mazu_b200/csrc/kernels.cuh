@@ -275,6 +275,7 @@ static const int QR_CHUNK = 128;  // k-mer start positions per chunk
 static const int QR_BASES = 160;  // bases staged per chunk (CHUNK + k - 1 <= 159)
 static const u64 QR_SEGMENT = 2048;  // k-mer positions per work item when a long read is cut up (a multiple of QR_CHUNK)
 static const u32 BN_SKEW = 0xFFFFFFFFu;
+static const u32 QR_LOC = 64, QR_NO_LOC = 255;
 
 struct WarpStage {
   u64 fw[QR_CHUNK];      // forward k-mer word per chunk position (garbage where invalid)
@@ -292,7 +293,13 @@ struct WarpStage {
   u8 off[QR_CHUNK];      // minimizer offset in fw-mer coordinates
   u8 leader[QR_CHUNK];   // chunk position of this k-mer's leader
   u8 lead_list[QR_CHUNK];
+  // the unitig around the first bucket entry, located by the leader (first QR_LOC leaders of a chunk; a 150 bp read has ~18):
+  u8 lrank[QR_CHUNK];    // leaders only: slot in the three arrays below, QR_NO_LOC = none
+  u32 uid[QR_LOC];       // unitig id
+  u32 sdelta[QR_LOC];    // entry - unitig start
+  u32 edelta[QR_LOC];    // unitig end - entry; bit 31: DUP flag of the lines a k-mer of the super-k-mer can start in
 };
+static_assert(sizeof(WarpStage) * QR_WARPS <= 48 * 1024, "WarpStage must fit the static shared-memory limit");
 
 struct ChunkInfo {
   u32 vm[4];  // ballot masks: bit `lane` of vm[t] <=> k-mer 32t+lane is a valid window inside the read
@@ -365,7 +372,7 @@ __device__ __forceinline__ u32 window_min(const u32* __restrict__ h, u32 span) {
 }
 
 // stage M + stage B (SSHash only)
-template <u32 FAMILY>
+template <u32 FAMILY, bool WALK = false>  // WALK: the streaming walk also wants the DUP flags of the super-k-mer's lines
 __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkInfo& ci, u32 lane, WarpStage& S) {
   const u32 k = ix.unitigs.k, w = ix.w, span = k - w;
   const u64 wmask = kmer_mask(w);
@@ -444,20 +451,39 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
       u64 fw = S.fw[p], rc = S.rc[p];
       u64 mmw = mm_word_of(fw, rc, S.off[p], k, w);
       u64 h, a = 0, b = 0;
-      u32 n = 0;
+      u32 n = 0, loc = QR_NO_LOC;
       if (cascade_lookup(ix.mphf, ix.sizes, mmw, h) && h + 1 < ix.sizes.n) {  // the probe that finds the slot has fetched its bounds block
         blocked_ef_get2(ix.sizes, h, a, b);
         u64 cnt = b - a;
         n = cnt > ix.skew_param ? BN_SKEW : (u32)cnt;
         // the bucket's first entry now, once per super-k-mer: stage V then starts at the unitig line (one dependent DRAM access
         // per group of 32 k-mers instead of two)
-        if (cnt && n != BN_SKEW) S.bfirst[p] = packed_get(ix.pos, a);
+        if (cnt && n != BN_SKEW) {
+          const u64 mm_pos = packed_get(ix.pos, a);
+          S.bfirst[p] = mm_pos;
+          // ... and the unitig that holds it.  A k-mer verified against this entry starts at mm_pos - (offset <= k - w), so it
+          // either lies inside this unitig or crosses its start (then the boundary guard of sshash.rs:513-514 rejects it):
+          // stage V needs no unitig lookup of its own for the first entry, and the line it compares against is already on its way.
+          if (i + lane < QR_LOC) {
+            u64 id, st, en;
+            u32 dup;
+            line_locate(ix.unitigs, mm_pos, id, st, en, &dup);
+            // DUP flag for the streaming walk (index_layout.hpp, ULINE_DUP): of the line of the entry, or of the line before it
+            // when a k-mer of this super-k-mer can start there (a superset never hurts: flagged groups settle their cursors)
+            if (WALK && (u32)(mm_pos & 255u) < k - w && mm_pos >= 256) dup |= __ldg(&ix.unitigs.lines[(mm_pos >> ULINE_SHIFT) - 1].end_delta) >> 31;
+            S.uid[i + lane] = (u32)id;
+            S.sdelta[i + lane] = (u32)(mm_pos - st);
+            S.edelta[i + lane] = (u32)(en - mm_pos) | (dup << 31);  // unitigs are shorter than 2^31
+            loc = i + lane;
+          }
+        }
 #ifdef MAZU_PREFETCH  // measured and rejected (profiles/experiments/README.md): -2 % config 5, -5 % config 2
         if (cnt && n != BN_SKEW) prefetch_l2(ix.pos.words + ((a * ix.pos.width) >> 6));
 #endif
       }
       S.bstart[p] = a;
       S.bn[p] = n;
+      S.lrank[p] = (u8)loc;
     }
   }
   __syncwarp();
@@ -482,24 +508,41 @@ __device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpSta
     return finish_hit(ix.unitigs, pos, mt, false, out, ustart, dup);
   }
   const u64 pos_start = S.bstart[lp];
-  const u64 offset = S.off[p];
-  const u64 rc_offset = (u64)(k - ix.w) - offset;
+  const u32 offset = S.off[p];
+  const u32 rc_offset = (k - ix.w) - offset;
   const u64 last_km_start_pos = ix.unitigs.total_len - k;
-#pragma unroll 1
+  const u32 loc = S.lrank[lp];
   u64 prev_mm_pos = ~0ULL;
+#pragma unroll 1
   for (u32 e = 0; e < n; ++e) {
     u64 mm_pos = e == 0 ? S.bfirst[lp] : packed_get(ix.pos, pos_start + e);
     if (mm_pos == prev_mm_pos) continue;  // same entry twice in a row (both streams of the builder): same candidates, already failed
     prev_mm_pos = mm_pos;
-    if (mm_pos >= offset && mm_pos - offset <= last_km_start_pos) {  // sshash.rs:498
-      u64 km_pos = mm_pos - offset;
-      u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
-      if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out, ustart, dup)) return true;
-    }
-    if (rc_offset != offset && mm_pos >= rc_offset && mm_pos - rc_offset <= last_km_start_pos) {  // sshash.rs:527 (same window when equal)
-      u64 km_pos = mm_pos - rc_offset;
-      u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
-      if (mt != NO_MATCH && finish_hit(ix.unitigs, km_pos, mt, true, out, ustart, dup)) return true;
+    const bool located = e == 0 && loc != QR_NO_LOC;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {  // candidate from the fw offset (sshash.rs:498), then from the rc offset (sshash.rs:527; same window when equal)
+      const u32 o = c == 0 ? offset : rc_offset;
+      if (c == 1 && rc_offset == offset) break;
+      if (mm_pos >= o && mm_pos - o <= last_km_start_pos) {
+        const u64 km_pos = mm_pos - o;
+        const u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
+        if (mt != NO_MATCH) {
+          if (located) {  // unitig of the entry, from the leader: inside it <=> sdelta >= o; boundary guard <=> k - o <= edelta
+            const u32 sd = S.sdelta[loc], edf = S.edelta[loc], ed = edf & 0x7FFFFFFFu;
+            if (sd >= o && k - o <= ed) {
+              out.unitig_id = S.uid[loc];
+              out.unitig_len = sd + ed;
+              out.pos = sd - o;
+              out.match = mt;
+              if (ustart) *ustart = mm_pos - sd;
+              if (dup) *dup = edf >> 31;
+              return true;
+            }
+          } else if (finish_hit(ix.unitigs, km_pos, mt, true, out, ustart, dup)) {
+            return true;
+          }
+        }
+      }
     }
   }
   return false;
@@ -679,7 +722,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const _
         // (An earlier version extended warm cursors first and looked up cold only on demand; on a GPU the cold path is
         // already amortised per super-k-mer: always-cold + verify measured +5 % on config 3 and, being small enough for the
         // 64-register build, +15 % on a 1.7 GB index.)
-        if (SS) stage_buckets<FAMILY>(ix, ci, lane, S);
+        if (SS) stage_buckets<FAMILY, true>(ix, ci, lane, S);
 #pragma unroll 1
         for (u32 g0 = 0; g0 < n_c; g0 += 32) {
           const u32 q = g0 + lane;
