@@ -270,7 +270,10 @@ __global__ void probe_key_kernel(const __grid_constant__ IndexView ix, const u64
 // kernel holds ONE copy of each stage (the first version inlined the lookup four times; ncu showed
 // 72 % of stall samples in `no_instruction`, i.e. instruction-cache misses -- profiles/r01_*).
 // ---------------------------------------------------------------------------------------------
-static const int QR_WARPS = 8;    // warps per CTA
+#ifndef MAZU_QR_WARPS
+#define MAZU_QR_WARPS 8
+#endif
+static const int QR_WARPS = MAZU_QR_WARPS;  // warps per CTA (A/B knob)
 static const int QR_CHUNK = 128;  // k-mer start positions per chunk
 static const int QR_BASES = 160;  // bases staged per chunk (CHUNK + k - 1 <= 159)
 static const u64 QR_SEGMENT = 2048;  // k-mer positions per work item when a long read is cut up (a multiple of QR_CHUNK)
