@@ -211,7 +211,8 @@ void make_tiles(const mazu_index* idx, const u64* d_read_offsets, u64 n_reads, u
 // fused reads -> hit runs (query_reads_runs_kernel): codes per slot, chunk-local run records, per-read run offsets; d_rro[n_reads]
 // is the run cursor (the chunk's run count afterwards).  Only for chunks whose reads all fit one tile.
 void launch_query_reads_runs(const mazu_index* idx, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, const u64* d_kmer_offsets,
-                             u64* d_counts, u8* d_codes, Hit* d_runs, u64* d_rro, u64 cap, cudaStream_t s) {
+                             u64* d_counts, u8* d_codes, Hit* d_runs, u64* d_rro, u64 cap, cudaStream_t s, const u64* d_packed_words = nullptr,
+                             const u64* d_packed_nmask = nullptr) {
   MZ_CUDA(cudaMemsetAsync(d_rro + n_reads, 0, 8, s));
   if (!n_reads) return;
   RunsTileOut ro{d_codes, d_runs, d_rro, (unsigned long long*)(d_rro + n_reads), cap};
@@ -221,7 +222,7 @@ void launch_query_reads_runs(const mazu_index* idx, const u8* d_bases, const u64
     auto kern = query_reads_runs_kernel<K, F>;                                                                                 \
     int grid = grid_for(kern, QR_WARPS * 32, idx, QR_WARPS, n_reads);                                                          \
     kern<<<grid, QR_WARPS * 32, 0, s>>>(idx->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets,              \
-                                        (unsigned long long*)d_counts, ro);                                                    \
+                                        (unsigned long long*)d_counts, ro, d_packed_words, d_packed_nmask);                    \
   }
   if (ss) MZ_QRR(MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE)
   else if (idx->view.k2u_kind == MAZU_K2U_SAMPLED_PFHASH) MZ_QRR(MAZU_K2U_SAMPLED_PFHASH, MPHF_FAMILY_BOOPHF)
@@ -806,8 +807,10 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
         const u64 nrc = r1 - r0;
         MZ_CUDA(cudaMemcpyAsync(d_pw[b], ro->packed_words + r0 * wpr, nrc * wpr * 8, cudaMemcpyHostToDevice, s));
         if (ro->packed_nmask) MZ_CUDA(cudaMemcpyAsync(d_pm[b], ro->packed_nmask + r0 * mpr, nrc * mpr * 8, cudaMemcpyHostToDevice, s));
-        unpack_reads_kernel<<<idx->sm_count * 8, 256, 0, s>>>((const u64*)d_pw[b], (const u64*)d_pm[b], nrc, uniform_read_len, (u8*)d_bases[b]);
-        MZ_CUDA(cudaGetLastError());
+        if (!fused_runs) {  // the fused run kernel reads the packed words itself (stage_encode_packed)
+          unpack_reads_kernel<<<idx->sm_count * 8, 256, 0, s>>>((const u64*)d_pw[b], (const u64*)d_pm[b], nrc, uniform_read_len, (u8*)d_bases[b]);
+          MZ_CUDA(cudaGetLastError());
+        }
       } else {
         MZ_CUDA(cudaMemcpyAsync(d_bases[b], bases + b0, nb, cudaMemcpyHostToDevice, s));
       }
@@ -832,7 +835,8 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
         u8* cc = (u8*)d_codes[b] - (uniform_read_len ? 0 : s0);
         const int grid = (int)std::min<u64>((nr + 7) / 8, (u64)idx->sm_count * 8);
         if (fused_runs) {  // one kernel: lookups, run codes, run records (chunk-local), per-read run offsets
-          launch_query_reads_runs(idx, dbases, dro, nr, uniform_read_len, dko, (u64*)d_counts, cc, (Hit*)d_runs[b], (u64*)d_rro[b], max_slots, s);
+          launch_query_reads_runs(idx, dbases, dro, nr, uniform_read_len, dko, (u64*)d_counts, cc, (Hit*)d_runs[b], (u64*)d_rro[b], max_slots, s,
+                                  packed_in ? (const u64*)d_pw[b] : nullptr, packed_in ? (const u64*)d_pm[b] : nullptr);
         } else {
           MZ_CUDA(cudaMemsetAsync(d_rc[b], 0, (nr + 1) * 8, s));
           hit_run_codes_kernel<<<grid, 256, 0, s>>>(hh, dko, nr, uniform_slots, cc, (u64*)d_rc[b]);

@@ -309,6 +309,24 @@ struct ChunkInfo {
   u32 n_c;    // k-mer positions of this chunk that lie inside the read
 };
 
+// stage E, second half: every lane holds the chunk's packed words w[] and invalid-base masks inv[]; k-mer words to shared
+// memory, validity of the chunk's k-mer windows to four ballot masks
+__device__ __forceinline__ void stage_encode_finish(const u64 (&w)[6], const u32 (&inv)[6], u32 n_c, u32 k, u32 lane, WarpStage& S, ChunkInfo& ci) {
+  const u64 kmask = kmer_mask(k);
+  const u64 vmask = (1ULL << k) - 1ULL;  // k <= 32
+  const u32 sh = 2 * lane;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    u64 x = w[t] >> sh;
+    if (sh) x |= w[t + 1] << (64 - sh);
+    S.fw[32 * t + lane] = x & kmask;
+    u64 m = ((u64)inv[t] | ((u64)inv[t + 1] << 32)) >> lane;
+    bool valid = (32u * t + lane < n_c) && ((m & vmask) == 0ULL);
+    ci.vm[t] = __ballot_sync(0xffffffffu, valid);
+  }
+  ci.n_c = n_c;
+}
+
 // stage E
 __device__ __forceinline__ void stage_encode(const u8* __restrict__ seq, u64 len, u64 c0, u32 n_c, u32 k, u32 lane, WarpStage& S, ChunkInfo& ci) {
   u64 w[6];
@@ -327,19 +345,28 @@ __device__ __forceinline__ void stage_encode(const u8* __restrict__ seq, u64 len
   }
   w[5] = 0;
   inv[5] = 0xffffffffu;
-  const u64 kmask = kmer_mask(k);
-  const u64 vmask = (1ULL << k) - 1ULL;  // k <= 32
-  const u32 sh = 2 * lane;
+  stage_encode_finish(w, inv, n_c, k, lane, S, ci);
+}
+
+// stage E for a read that arrives 2-bit packed (kmers::SeqVector layout: base j at bits [2j, 2j+2) of word j / 32; optional
+// N mask, one bit per base) and fits one chunk: its words ARE the packed words stage E builds, so the warp loads them with
+// uniform (broadcast) loads and no ASCII copy of the read ever exists (mazu_b200_query_reads_runs_packed).
+__device__ __forceinline__ void stage_encode_packed(const u64* __restrict__ words, const u64* __restrict__ n_mask, u32 len, u32 n_c, u32 k, u32 lane,
+                                                    WarpStage& S, ChunkInfo& ci) {
+  const u32 wpr = (len + 31) / 32, mpr = (len + 63) / 64;  // len <= QR_BASES - 1: at most 5 words, 3 mask words
+  u64 w[6], nm[3];
+  u32 inv[6];
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    u64 x = w[t] >> sh;
-    if (sh) x |= w[t + 1] << (64 - sh);
-    S.fw[32 * t + lane] = x & kmask;
-    u64 m = ((u64)inv[t] | ((u64)inv[t + 1] << 32)) >> lane;
-    bool valid = (32u * t + lane < n_c) && ((m & vmask) == 0ULL);
-    ci.vm[t] = __ballot_sync(0xffffffffu, valid);
+  for (int j = 0; j < 3; ++j) nm[j] = (n_mask && (u32)j < mpr) ? __ldg(n_mask + j) : 0ULL;
+#pragma unroll
+  for (int t = 0; t < 5; ++t) {
+    w[t] = (u32)t < wpr ? __ldg(words + t) : 0ULL;
+    const int rem = (int)len - 32 * t;  // bases of the read in this word
+    inv[t] = (u32)(nm[t >> 1] >> (32 * (t & 1))) | (rem >= 32 ? 0u : (rem <= 0 ? 0xffffffffu : 0xffffffffu << rem));
   }
-  ci.n_c = n_c;
+  w[5] = 0;
+  inv[5] = 0xffffffffu;
+  stage_encode_finish(w, inv, n_c, k, lane, S, ci);
 }
 
 __device__ __forceinline__ bool chunk_valid(const ChunkInfo& ci, u32 q) {
@@ -1289,7 +1316,8 @@ template <int KIND, u32 FAMILY>
 __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
                                                                            const u64* __restrict__ read_offsets, u64 n_reads, u64 uniform_len,
                                                                            const u64* __restrict__ kmer_offsets, unsigned long long* __restrict__ counts,
-                                                                           const RunsTileOut ro) {
+                                                                           const RunsTileOut ro, const u64* __restrict__ packed_words,
+                                                                           const u64* __restrict__ packed_nmask) {
   __shared__ WarpStage s_stage[QR_WARPS];
   const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   WarpStage& S = s_stage[wib];
@@ -1313,7 +1341,10 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(cons
     u32 code[4], n_runs = 0;
     if (n_c) {
       ChunkInfo ci;
-      stage_encode(bases + beg, len, 0, n_c, k, lane, S, ci);
+      if (packed_words)  // uniform reads, 2-bit packed (the launcher passes these only with uniform_len)
+        stage_encode_packed(packed_words + r * ((len + 31) / 32), packed_nmask ? packed_nmask + r * ((len + 63) / 64) : nullptr, (u32)len, n_c, k, lane, S, ci);
+      else
+        stage_encode(bases + beg, len, 0, n_c, k, lane, S, ci);
       __syncwarp();
       if (SS) stage_buckets<FAMILY>(ix, ci, lane, S);
       // one copy of the lookup (the loop is not unrolled: instruction-cache footprint); hits are parked in the warp's stage
@@ -1359,6 +1390,13 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(cons
       E = n_runs ? atomicAdd(ro.cursor, (unsigned long long)n_runs) : 0ULL;
       ro.read_run_offsets[r] = E;
     }
+    if (n_c) {  // the codes do not depend on the reservation: they go out while the atomic is in flight
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const u32 p = 32 * t + lane;
+        if (p < n_c) ro.codes[slot0 + p] = (u8)code[t];
+      }
+    }
     E = __shfl_sync(0xffffffffu, E, 0);
     if (n_c) {
       u64 o = E;
@@ -1367,7 +1405,6 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(cons
         const u32 p = 32 * t + lane;
         const bool start = p < n_c && code[t] == RUN_START;
         const u32 m = __ballot_sync(0xffffffffu, start);
-        if (p < n_c) ro.codes[slot0 + p] = (u8)code[t];
         if (start) {
           const u64 dst = o + __popc(m & ((1u << lane) - 1u));
           if (dst < ro.cap) store_hit(ro.runs + dst, hh[t]);

@@ -1179,6 +1179,16 @@ def test_packed_reads_in_packed_codes_out(yeast_sshash, yeast_dense, yeast_queri
                 assert list(cnt) == list(wcnt) and len(codes2) == (len(want) + 3) // 4
     finally:
         del os.environ["MAZU_B200_CHUNK_MIB"]
+    # other read lengths: 1-4 packed words and 1-2 mask words per read (the fused kernel reads them in place), a last word
+    # that is only partly inside the read
+    g, o = yeast_sshash
+    for rl in (46, 66, 102, 130):
+        b2, o2 = _gen.sample_reads(ref_codes, 700, rl, seed=62 + rl, frac_ref=0.8, sub_rate=0.01, n_rate=0.004)
+        w2, m2, _ = mz.pack_reads(b2, rl)
+        want, wcnt, _ = o.query_reads(b2, o2)
+        codes2, runs, rro, cnt = g.query_reads_runs_packed(w2, m2, 700, rl)
+        assert_hits_equal(mz.ModIndex.expand_hit_runs_packed(codes2, runs, rro, rl - g.k + 1), want, "packed runs, read length %d" % rl)
+        assert list(cnt) == list(wcnt)
     # without a mask the N positions read as 'A': the caller's contract, not checked here; wrong shapes are rejected
     g, _ = yeast_sshash
     with pytest.raises(mz.MazuError):
