@@ -212,10 +212,10 @@ void make_tiles(const mazu_index* idx, const u64* d_read_offsets, u64 n_reads, u
 // is the run cursor (the chunk's run count afterwards).  Only for chunks whose reads all fit one tile.
 void launch_query_reads_runs(const mazu_index* idx, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, const u64* d_kmer_offsets,
                              u64* d_counts, u8* d_codes, Hit* d_runs, u64* d_rro, u64 cap, cudaStream_t s, const u64* d_packed_words = nullptr,
-                             const u64* d_packed_nmask = nullptr) {
+                             const u64* d_packed_nmask = nullptr, u8* d_codes2 = nullptr) {
   MZ_CUDA(cudaMemsetAsync(d_rro + n_reads, 0, 8, s));
   if (!n_reads) return;
-  RunsTileOut ro{d_codes, d_runs, d_rro, (unsigned long long*)(d_rro + n_reads), cap};
+  RunsTileOut ro{d_codes, d_codes2, d_runs, d_rro, (unsigned long long*)(d_rro + n_reads), cap};
   const bool ss = idx->view.k2u_kind == MAZU_K2U_SSHASH, boophf = idx->view.mphf.family == MPHF_FAMILY_BOOPHF;
 #define MZ_QRR(K, F)                                                                                                          \
   {                                                                                                                            \
@@ -789,8 +789,10 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
     auto copy_codes = [&](int bb, u64 s0, u64 ns, cudaStream_t s) {
       if (!ns) return;
       if (ro->codes2) {
-        pack_codes_kernel<<<idx->sm_count * 4, 256, 0, s>>>((const u8*)d_codes[bb], ns, (u8*)d_codes2[bb]);
-        MZ_CUDA(cudaGetLastError());
+        if (!fused_runs) {
+          pack_codes_kernel<<<idx->sm_count * 4, 256, 0, s>>>((const u8*)d_codes[bb], ns, (u8*)d_codes2[bb]);
+          MZ_CUDA(cudaGetLastError());
+        }
         MZ_CUDA(cudaMemcpyAsync(ro->codes + s0 / 4, d_codes2[bb], (ns + 3) / 4, cudaMemcpyDeviceToHost, s));
       } else {
         MZ_CUDA(cudaMemcpyAsync(ro->codes + s0, d_codes[bb], ns, cudaMemcpyDeviceToHost, s));
@@ -836,7 +838,8 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
         const int grid = (int)std::min<u64>((nr + 7) / 8, (u64)idx->sm_count * 8);
         if (fused_runs) {  // one kernel: lookups, run codes, run records (chunk-local), per-read run offsets
           launch_query_reads_runs(idx, dbases, dro, nr, uniform_read_len, dko, (u64*)d_counts, cc, (Hit*)d_runs[b], (u64*)d_rro[b], max_slots, s,
-                                  packed_in ? (const u64*)d_pw[b] : nullptr, packed_in ? (const u64*)d_pm[b] : nullptr);
+                                  packed_in ? (const u64*)d_pw[b] : nullptr, packed_in ? (const u64*)d_pm[b] : nullptr,
+                                  ro->codes2 ? (u8*)d_codes2[b] : nullptr);  // 2-bit codes straight from the kernel
         } else {
           MZ_CUDA(cudaMemsetAsync(d_rc[b], 0, (nr + 1) * 8, s));
           hit_run_codes_kernel<<<grid, 256, 0, s>>>(hh, dko, nr, uniform_slots, cc, (u64*)d_rc[b]);

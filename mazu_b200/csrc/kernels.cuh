@@ -1305,7 +1305,9 @@ __global__ void __launch_bounds__(256) get_ref_pos_pass2_kernel(const __grid_con
 // predecessors that have published an aggregate but not yet an inclusive prefix.)
 // ---------------------------------------------------------------------------------------------
 struct RunsTileOut {
-  u8* codes;                   // one byte per k-mer slot
+  u8* codes;                   // one byte per k-mer slot ...
+  u8* codes2;                  // ... or, when set, 2 bits per slot (slot s at bits [2 (s & 3), +2) of byte s >> 2; uniform reads whose
+                               // slot count is a multiple of 4, so every read owns whole bytes)
   Hit* runs;                   // run records, chunk-local indexes
   u64* read_run_offsets;       // n_reads entries: index of every read's first run
   unsigned long long* cursor;  // next free run record (zeroed before the launch; the batch's run count afterwards)
@@ -1394,7 +1396,14 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(cons
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const u32 p = 32 * t + lane;
-        if (p < n_c) ro.codes[slot0 + p] = (u8)code[t];
+        if (ro.codes2) {  // four neighbouring lanes share a byte
+          u32 v = p < n_c ? (code[t] & 3u) << (2 * (lane & 3u)) : 0u;
+          v |= __shfl_xor_sync(0xffffffffu, v, 1);
+          v |= __shfl_xor_sync(0xffffffffu, v, 2);
+          if ((lane & 3u) == 0 && p < n_c) ro.codes2[(slot0 + p) >> 2] = (u8)v;
+        } else if (p < n_c) {
+          ro.codes[slot0 + p] = (u8)code[t];
+        }
       }
     }
     E = __shfl_sync(0xffffffffu, E, 0);
