@@ -376,6 +376,7 @@ def main():
     check = None          # callable -> bool : parity spot check (rank 0)
     e2e_step = None       # callable: one end-to-end step through host buffers (the headline e2e)
     e2e_extra = {}        # name -> (callable, units, h2d bytes, d2h bytes or None, api description): further end-to-end variants
+    e2e_extra_post = {}   # name -> callable(dict): fills in what is only known after the variant has run
     e2e_bytes = (0, 0)
     e2e_units = None      # units per e2e step (defaults to n_units)
     e2e_api = None
@@ -518,6 +519,7 @@ def main():
             # reported; the ASCII-in call is measured next to it (`ascii_reads`).
             packed_ok = nk_per_read % 4 == 0
             e2e_extra = {}
+            e2e_extra_post = {}
             if packed_ok:
                 wpr = (READ_LEN + 31) // 32
                 h_words = torch.empty(e2e_reads * wpr, dtype=torch.int64, pin_memory=True)
@@ -549,6 +551,37 @@ def main():
                     e["counts_match_device_path"] = bool(int(h_cnt[0]) == e2e_units and int(h_cnt[1]) > 0)
 
                 e2e_extra["ascii_reads"] = (e2e_ascii_step, e2e_units, e2e_reads * READ_LEN, None, ascii_api)
+                # The sparsest lossless result: one 16-byte record per hit RUN and nothing per slot or per read
+                # (mazu_b200_query_reads_intervals_packed).  It is the headline where it applies (short reads, random access or
+                # unique k-mers); the run-code interface above is then reported next to it as `packed_runs`.
+                if nk_per_read <= 128 and (mode == mz.MODE_RANDOM or index.kmers_unique):
+                    h_iv = torch.empty((max(1 << 20, e2e_units // 16), 4), dtype=torch.int32, pin_memory=True)
+                    runs_step, runs_api, runs_post = e2e_step, e2e_api, e2e_post
+
+                    def e2e_step():
+                        n_iv = C.c_uint64(0)
+                        mz._check(mz.lib().mazu_b200_query_reads_intervals_packed(index._h, mz._any_ptr(h_words), None, e2e_reads, READ_LEN, mode,
+                                                                                  mz._any_ptr(h_iv), h_iv.shape[0], C.byref(n_iv), mz._np_ptr(h_cnt)))
+                        runs_state["n_iv"] = n_iv.value
+
+                    e2e_api = ("mazu_b200_query_reads_intervals_packed (C ABI, host buffers): pinned 2-bit packed reads in (40 B per 150 bp read); out: "
+                               "one 16-byte record {unitig, pos|orientation, read, first slot, length} per hit run, nothing per slot or per read "
+                               "(lossless: mazu_b200_expand_hit_intervals rebuilds every record)")
+
+                    def e2e_post(e):
+                        e["h2d_bytes_per_step"] = e2e_reads * wpr * 8 * world
+                        e["d2h_bytes_per_step"] = (16 * runs_state["n_iv"] + 32) * world
+                        e["n_runs_per_step_per_gpu"] = runs_state["n_iv"]
+                        e["input"] = ("2-bit packed reads; packing the ASCII batch with mazu_b200_pack_reads (host threads) took %.0f ms = %.1f GB/s of ASCII, "
+                                      "outside the timed loop" % (t_pack * 1e3, e2e_reads * READ_LEN / t_pack / 1e9))
+                        m = min(e2e_reads, 20000)  # the expansion on the host reproduces the full records (checked on the head of the batch)
+                        iv = h_iv.numpy().view(np.uint32).reshape(-1).view(mz.INTERVAL_DTYPE)[: runs_state["n_iv"]]
+                        exp = index.expand_hit_intervals(np.ascontiguousarray(iv[iv["read"] < m]), None, m, READ_LEN)
+                        e["expands_to_full_records"] = bool(np.array_equal(exp.view(np.uint32).reshape(-1, 4), hits[: m * nk_per_read].cpu().numpy().view(np.uint32)))
+                        e["counts_match_device_path"] = bool(int(h_cnt[0]) == e2e_units and int(h_cnt[1]) > 0)
+
+                    e2e_extra["packed_runs"] = (runs_step, e2e_units, e2e_reads * wpr * 8, None, runs_api)
+                    e2e_extra_post = {"packed_runs": runs_post}
             else:  # read lengths whose slot count is not a multiple of 4: the byte-coded run call is the headline
                 e2e_step, e2e_api = e2e_ascii_step, ascii_api
 
@@ -911,6 +944,8 @@ def main():
                          "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": (d2h or 0) * world, "api": api}
             if name == "ascii_reads":
                 ascii_post(e2e[name])
+            if name in e2e_extra_post:
+                e2e_extra_post[name](e2e[name])
             if name == "full_records":
                 e2e[name]["matches_device_path"] = bool(torch.equal(h_hits[:1_000_000], hits[:1_000_000].cpu()))
                 if pc:

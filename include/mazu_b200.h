@@ -243,6 +243,31 @@ mazu_status_t mazu_b200_pack_reads(const uint8_t* bases, uint64_t n_reads, uint6
                                    uint64_t* n_non_acgt);
 mazu_status_t mazu_b200_expand_hit_runs_packed(const uint8_t* codes2, const mazu_hit_t* runs, const uint64_t* read_run_offsets,
                                                uint64_t n_reads, uint64_t uniform_slots, mazu_hit_t* out_hits);
+/* The sparsest lossless host result of a short-read batch: one self-contained 16-byte record per RUN and nothing per k-mer
+ * slot or per read -- ~0.19 bytes per lookup on the bench's read mix (the run format above: 0.5).  For hosts that feed several
+ * GPUs, where the host's D2H bandwidth, not the GPUs, bounds the run format (DESIGN.md "Multi-GPU").
+ * A run is a maximal stretch of consecutive k-mer slots of one read whose hits walk along one unitig in one orientation
+ * (the same relation as in mazu_b200_query_reads_runs); slots in no run are misses or -- where the window holds a non-ACGT
+ * base, which the caller's n_mask says -- skipped.  The order of the records is unspecified.
+ *   packed_reads, n_mask  as in mazu_b200_query_reads_runs_packed
+ *   out_intervals         capacity `cap` records; *out_n receives the number of runs (if it exceeds cap the call fails with
+ *                         MAZU_ERR_INVALID_ARG and *out_n is the capacity needed)
+ * Restrictions (MAZU_ERR_INVALID_ARG otherwise): read_len - k + 1 <= 128 (short reads: one read per warp), n_reads < 2^32,
+ * and MAZU_MODE_STREAMING only on indexes whose k-mers are unique (MAZU_INFO_KMERS_UNIQUE; its answers are then k2u's).
+ * mazu_b200_expand_hit_intervals rebuilds every mazu_hit_t on the host (unitig lengths from the handle's UnitigSet). */
+typedef struct mazu_hit_interval {
+  uint32_t unitig_id;
+  uint32_t pos_o;  /* bits 0-30: K2UPos::pos of the run's first k-mer; bit 31: 1 = MatchType::TwinMatch (pos falls by 1 per slot), 0 = IdentityMatch (rises) */
+  uint32_t read;   /* index of the read in the batch */
+  uint16_t start;  /* first k-mer slot of the run inside the read */
+  uint16_t len;    /* number of slots */
+} mazu_hit_interval_t;
+mazu_status_t mazu_b200_query_reads_intervals_packed(const mazu_index_t* idx, const uint64_t* packed_reads, const uint64_t* n_mask,
+                                                     uint64_t n_reads, uint64_t read_len, int32_t mode,
+                                                     mazu_hit_interval_t* out_intervals, uint64_t cap, uint64_t* out_n, uint64_t* counts);
+/* host-side decoder (multi-threaded): out_hits[r * (read_len - k + 1) + slot]; n_mask as passed to the query (or NULL) */
+mazu_status_t mazu_b200_expand_hit_intervals(const mazu_index_t* idx, const mazu_hit_interval_t* intervals, uint64_t n_intervals,
+                                             const uint64_t* n_mask, uint64_t n_reads, uint64_t read_len, mazu_hit_t* out_hits);
 /* host-side decoder of the run format (multi-threaded, no device work): out_hits[slot] for every slot of every read.
  * kmer_offsets may be NULL for uniform batches (uniform_slots = read_len - k + 1). */
 mazu_status_t mazu_b200_expand_hit_runs(const uint8_t* codes, const mazu_hit_t* runs, const uint64_t* read_run_offsets,

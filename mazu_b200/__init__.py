@@ -27,6 +27,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mazu_b200.h")
 DEBUG_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mazu_b200_debug.h")  # test / measurement hooks, not the boundary
 
 HIT_DTYPE = np.dtype([("unitig_id", "<u4"), ("unitig_len", "<u4"), ("pos", "<u4"), ("match", "<u4")])
+INTERVAL_DTYPE = np.dtype([("unitig_id", "<u4"), ("pos_o", "<u4"), ("read", "<u4"), ("start", "<u2"), ("len", "<u2")])  # mazu_hit_interval_t
 TILE_DTYPE = np.dtype([("unitig_id", "<u4"), ("unitig_len", "<u4"), ("pos", "<u4"), ("fw", "<u4")])
 HIT8_DTYPE = np.dtype([("unitig_id", "<u4"), ("pos_match", "<u4")])
 OCC_DTYPE = np.dtype([("ref_id", "<u4"), ("pos", "<u4"), ("fw", "<u4")])
@@ -131,6 +132,8 @@ def _signatures():
         "mazu_b200_expand_hit_runs": (i32, [vp, vp, vp, vp, u64, u64, vp]),
         "mazu_b200_query_reads_runs_packed": (i32, [vp, vp, vp, u64, u64, i32, vp, vp, u64, vp, vp, vp]),
         "mazu_b200_pack_reads": (i32, [vp, u64, u64, vp, vp, vp]),
+        "mazu_b200_query_reads_intervals_packed": (i32, [vp, vp, vp, u64, u64, i32, vp, u64, vp, vp]),
+        "mazu_b200_expand_hit_intervals": (i32, [vp, vp, u64, vp, u64, u64, vp]),
         "mazu_b200_expand_hit_runs_packed": (i32, [vp, vp, vp, u64, u64, vp]),
         "mazu_b200_encode_reads": (i32, [vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp]),
         "mazu_b200_decode_occs": (i32, [vp, vp, u64, vp, vp, u64, vp, i32, vp]),
@@ -486,6 +489,28 @@ class ModIndex:
             _check(rc)
             break
         return codes2, runs[: n_runs.value], rro, cnt
+
+    def query_reads_intervals_packed(self, words, n_mask, n_reads, read_len, mode=MODE_RANDOM, intervals=None):
+        """mazu_b200_query_reads_intervals_packed: 2-bit reads in, one 16-byte record per hit run out: (intervals[:n], counts)."""
+        cnt = np.zeros(3, dtype=np.uint64)
+        n = C.c_uint64(0)
+        if intervals is None:
+            intervals = np.empty(max(1024, n_reads * max(read_len - self.k + 1, 0) // 16), dtype=INTERVAL_DTYPE)
+        while True:
+            rc = lib().mazu_b200_query_reads_intervals_packed(self._h, _any_ptr(words), _any_ptr(n_mask), n_reads, read_len, mode, _any_ptr(intervals),
+                                                              len(intervals), C.byref(n), _np_ptr(cnt))
+            if rc != 0 and n.value > len(intervals):
+                intervals = np.empty(n.value, dtype=INTERVAL_DTYPE)
+                continue
+            _check(rc)
+            break
+        return intervals[: n.value], cnt
+
+    def expand_hit_intervals(self, intervals, n_mask, n_reads, read_len, out=None):
+        """mazu_b200_expand_hit_intervals: every mazu_hit_t of the batch from the interval records (+ the N mask)."""
+        out = np.empty(n_reads * max(read_len - self.k + 1, 0), dtype=HIT_DTYPE) if out is None else out
+        _check(lib().mazu_b200_expand_hit_intervals(self._h, _any_ptr(intervals), len(intervals), _any_ptr(n_mask), n_reads, read_len, _any_ptr(out)))
+        return out
 
     @staticmethod
     def expand_hit_runs_packed(codes2, runs, read_run_offsets, uniform_slots, out=None):

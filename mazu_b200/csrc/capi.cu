@@ -212,10 +212,10 @@ void make_tiles(const mazu_index* idx, const u64* d_read_offsets, u64 n_reads, u
 // is the run cursor (the chunk's run count afterwards).  Only for chunks whose reads all fit one tile.
 void launch_query_reads_runs(const mazu_index* idx, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, const u64* d_kmer_offsets,
                              u64* d_counts, u8* d_codes, Hit* d_runs, u64* d_rro, u64 cap, cudaStream_t s, const u64* d_packed_words = nullptr,
-                             const u64* d_packed_nmask = nullptr, u8* d_codes2 = nullptr) {
+                             const u64* d_packed_nmask = nullptr, u8* d_codes2 = nullptr, uint4* d_intervals = nullptr, u64 read_base = 0) {
   MZ_CUDA(cudaMemsetAsync(d_rro + n_reads, 0, 8, s));
   if (!n_reads) return;
-  RunsTileOut ro{d_codes, d_codes2, d_runs, d_rro, (unsigned long long*)(d_rro + n_reads), cap};
+  RunsTileOut ro{d_codes, d_codes2, d_runs, d_rro, (unsigned long long*)(d_rro + n_reads), cap, d_intervals, read_base};
   const bool ss = idx->view.k2u_kind == MAZU_K2U_SSHASH, boophf = idx->view.mphf.family == MPHF_FAMILY_BOOPHF;
 #define MZ_QRR(K, F)                                                                                                          \
   {                                                                                                                            \
@@ -924,6 +924,153 @@ mazu_status_t mazu_b200_query_reads_runs_packed(const mazu_index_t* idx, const u
     return MAZU_ERR_INVALID_ARG;
   }
   return rc;
+}
+
+// Hit intervals (include/mazu_b200.h): packed uniform short reads in, one 16-byte record per run out.  Its own small pipeline:
+// per chunk H2D of the 2-bit words, the fused run kernel in interval mode (chunk-local records + count), then the records go
+// to the caller's buffer at a running base -- published by a kernel when the buffer is pinned (no host synchronisation at
+// all), or copied after a per-chunk synchronisation when it is pageable.
+mazu_status_t mazu_b200_query_reads_intervals_packed(const mazu_index_t* idx, const uint64_t* packed_reads, const uint64_t* n_mask,
+                                                     uint64_t n_reads, uint64_t read_len, int32_t mode, mazu_hit_interval_t* out_intervals,
+                                                     uint64_t cap, uint64_t* out_n, uint64_t* counts) {
+  static_assert(sizeof(mazu_hit_interval_t) == 16, "interval records are 16 bytes");
+  u64 n_total = 0;
+  mazu_status_t rc = guarded([&] {
+    if (!idx || !read_len || (n_reads && !packed_reads) || (cap && !out_intervals)) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    if (mode != MAZU_MODE_RANDOM && mode != MAZU_MODE_STREAMING) throw Error(MAZU_ERR_INVALID_ARG, "unknown query mode");
+    if (mode == MAZU_MODE_STREAMING && !idx->kmers_unique)
+      throw Error(MAZU_ERR_INVALID_ARG, "hit intervals come from the random-access kernel: streaming mode needs an index with unique k-mers");
+    const u32 k = idx->unitigs->k;
+    const u64 slots = read_len >= k ? read_len - k + 1 : 0;
+    if (slots > (u64)QR_CHUNK) throw Error(MAZU_ERR_INVALID_ARG, "hit intervals are for short reads: read_len - k + 1 <= 128");
+    if (n_reads >> 32) throw Error(MAZU_ERR_INVALID_ARG, "more than 2^32 reads in one call");
+    if (counts) counts[0] = counts[1] = counts[2] = 0;
+    if (!n_reads || !slots) return;
+    DeviceGuard g(idx->device);
+    const u64 wpr = (read_len + 31) / 32, mpr = (read_len + 63) / 64;
+    u64 TARGET = 32ull << 20;
+    if (const char* e = getenv("MAZU_B200_CHUNK_MIB")) {
+      long v = atol(e);
+      if (v > 0) TARGET = (u64)v << 20;
+    }
+    const u64 rpc = std::max<u64>(4, TARGET / read_len);  // reads per chunk
+    static const int NB = 6;
+    uint4* out_dev = nullptr;  // the caller's buffer as the device sees it (pinned memory), or null
+    {
+      cudaPointerAttributes at{};
+      if (cap && cudaPointerGetAttributes(&at, out_intervals) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) out_dev = (uint4*)at.devicePointer;
+      else cudaGetLastError();
+    }
+    struct Streams {
+      cudaStream_t s[NB] = {};
+      cudaEvent_t base_ev = nullptr;
+      ~Streams() {
+        for (auto x : s)
+          if (x) {
+            cudaStreamSynchronize(x);
+            cudaStreamDestroy(x);
+          }
+        if (base_ev) cudaEventDestroy(base_ev);
+      }
+    } st;
+    for (auto& x : st.s) MZ_CUDA(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+    MZ_CUDA(cudaEventCreateWithFlags(&st.base_ev, cudaEventDisableTiming));
+    PoolScratch scratch(idx->pool, st.s[0]);
+    const u64 max_reads = std::min(rpc, n_reads), max_slots = max_reads * slots;
+    void *d_pw[NB], *d_pm[NB] = {}, *d_iv[NB];
+    u64* d_cur[NB];  // [0] run cursor of the chunk (its count afterwards), [1] scratch read-run-offset slot the kernel never touches
+    u64* d_counts = (u64*)scratch.get(24);
+    u64* d_base = (u64*)scratch.get(8);
+    MZ_CUDA(cudaMemsetAsync(d_counts, 0, 24, st.s[0]));
+    MZ_CUDA(cudaMemsetAsync(d_base, 0, 8, st.s[0]));
+    for (int b = 0; b < NB; ++b) {
+      d_pw[b] = scratch.get(max_reads * wpr * 8 + 16);
+      if (n_mask) d_pm[b] = scratch.get(max_reads * mpr * 8 + 16);
+      d_iv[b] = scratch.get(max_slots * 16 + 16);  // worst case: every slot starts a run
+      d_cur[b] = (u64*)scratch.get(16);
+    }
+    for (int b = 1; b < NB; ++b) scratch.publish(st.s[b]);
+    MZ_CUDA(cudaEventRecord(st.base_ev, st.s[0]));
+    u64 host_base = 0;  // pageable path: records placed so far
+    int b = 0;
+    for (u64 r0 = 0; r0 < n_reads; r0 += rpc, b = (b + 1) % NB) {
+      const u64 nr = std::min(rpc, n_reads - r0);
+      cudaStream_t s = st.s[b];
+      MZ_CUDA(cudaMemcpyAsync(d_pw[b], packed_reads + r0 * wpr, nr * wpr * 8, cudaMemcpyHostToDevice, s));
+      if (n_mask) MZ_CUDA(cudaMemcpyAsync(d_pm[b], n_mask + r0 * mpr, nr * mpr * 8, cudaMemcpyHostToDevice, s));
+      // launch_query_reads_runs zeroes d_rro[n_reads] = the cursor: hand it an offsets pointer such that this is d_cur[b][0]
+      launch_query_reads_runs(idx, nullptr, nullptr, nr, read_len, nullptr, d_counts, nullptr, nullptr, d_cur[b] - nr, max_slots, s,
+                              (const u64*)d_pw[b], (const u64*)d_pm[b], nullptr, (uint4*)d_iv[b], r0);
+      if (out_dev) {
+        MZ_CUDA(cudaStreamWaitEvent(s, st.base_ev, 0));  // the running base: after the previous chunk has advanced it
+        hit_run_publish_kernel<<<idx->sm_count * 2, 256, 0, s>>>(nullptr, 0, (const Hit*)d_iv[b], d_cur[b], d_base, cap, (Hit*)out_dev);
+        hit_run_advance_kernel<<<1, 32, 0, s>>>(d_base, d_cur[b]);
+        MZ_CUDA(cudaGetLastError());
+        MZ_CUDA(cudaEventRecord(st.base_ev, s));
+      } else {
+        u64 total = 0;
+        MZ_CUDA(cudaMemcpyAsync(&total, d_cur[b], 8, cudaMemcpyDeviceToHost, s));
+        MZ_CUDA(cudaStreamSynchronize(s));
+        if (host_base < cap && total) {
+          const u64 n_fit = std::min(total, cap - host_base);
+          MZ_CUDA(cudaMemcpyAsync((uint4*)out_intervals + host_base, d_iv[b], n_fit * 16, cudaMemcpyDeviceToHost, s));
+        }
+        host_base += total;
+      }
+    }
+    for (auto x : st.s) MZ_CUDA(cudaStreamSynchronize(x));
+    if (out_dev) MZ_CUDA(cudaMemcpy(&n_total, d_base, 8, cudaMemcpyDeviceToHost));
+    else n_total = host_base;
+    if (counts) MZ_CUDA(cudaMemcpy(counts, d_counts, 24, cudaMemcpyDeviceToHost));
+  });
+  if (out_n) *out_n = n_total;
+  if (rc == MAZU_OK && n_total > cap) {
+    g_err = "interval capacity too small: need " + std::to_string(n_total) + " records";
+    return MAZU_ERR_INVALID_ARG;
+  }
+  return rc;
+}
+
+mazu_status_t mazu_b200_expand_hit_intervals(const mazu_index_t* idx, const mazu_hit_interval_t* intervals, uint64_t n_intervals,
+                                             const uint64_t* n_mask, uint64_t n_reads, uint64_t read_len, mazu_hit_t* out_hits) {
+  return guarded([&] {
+    if (!idx || (n_intervals && !intervals) || !read_len) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    const u32 k = idx->unitigs->k;
+    const u64 slots = read_len >= k ? read_len - k + 1 : 0, mpr = (read_len + 63) / 64;
+    if (n_reads && slots && !out_hits) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    const UnitigSetHost& us = *idx->unitigs;
+    const unsigned T = host_threads();
+    // every slot a miss, or skipped where its window holds a masked base
+    parallel_ranges(n_reads, T, [&](unsigned, u64 lo, u64 hi) {
+      for (u64 r = lo; r < hi; ++r) {
+        const u64* m = n_mask ? n_mask + r * mpr : nullptr;
+        long long last_bad = -1;  // most recent masked base at or before the window's last base
+        if (m)
+          for (u64 j = 0; j + 1 < k && j < read_len; ++j)
+            if ((m[j >> 6] >> (j & 63)) & 1ULL) last_bad = (long long)j;
+        for (u64 i = 0; i < slots; ++i) {
+          const u64 j = i + k - 1;
+          if (m && ((m[j >> 6] >> (j & 63)) & 1ULL)) last_bad = (long long)j;
+          out_hits[r * slots + i] = mazu_hit_t{~0u, ~0u, ~0u, last_bad >= (long long)i ? (u32)MAZU_SKIPPED : (u32)MAZU_NO_MATCH};
+        }
+      }
+    });
+    std::atomic<bool> bad{false};
+    parallel_ranges(n_intervals, T, [&](unsigned, u64 lo, u64 hi) {
+      for (u64 i = lo; i < hi; ++i) {
+        const mazu_hit_interval_t& v = intervals[i];
+        if (v.read >= n_reads || (u64)v.start + v.len > slots || v.unitig_id >= us.n_unitigs()) {
+          bad = true;
+          continue;
+        }
+        const bool twin = v.pos_o >> 31;
+        const u32 ulen = (u32)(us.accum[v.unitig_id + 1] - us.accum[v.unitig_id]), pos0 = v.pos_o & 0x7FFFFFFFu;
+        mazu_hit_t* o = out_hits + (u64)v.read * slots + v.start;
+        for (u32 j = 0; j < v.len; ++j) o[j] = mazu_hit_t{v.unitig_id, ulen, twin ? pos0 - j : pos0 + j, twin ? (u32)MAZU_TWIN_MATCH : (u32)MAZU_IDENTITY_MATCH};
+      }
+    });
+    if (bad) throw Error(MAZU_ERR_INVALID_DATA, "an interval record points outside the batch or the unitig set");
+  });
 }
 
 mazu_status_t mazu_b200_pack_reads(const uint8_t* bases, uint64_t n_reads, uint64_t read_len, uint64_t* out_words, uint64_t* out_n_mask,

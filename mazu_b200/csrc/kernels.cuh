@@ -1312,6 +1312,10 @@ struct RunsTileOut {
   u64* read_run_offsets;       // n_reads entries: index of every read's first run
   unsigned long long* cursor;  // next free run record (zeroed before the launch; the batch's run count afterwards)
   u64 cap;                     // capacity of `runs`
+  // interval mode (mazu_b200_query_reads_intervals_packed): when set, NOTHING above but cursor / cap is written; every run
+  // leaves as one self-contained 16-byte record {unitig id, position | twin << 31, read, first slot | length << 16}
+  uint4* intervals;
+  u64 read_base;               // index of the chunk's first read in the caller's batch
 };
 
 template <int KIND, u32 FAMILY>
@@ -1390,7 +1394,42 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(cons
     unsigned long long E = 0;
     if (lane == 0) {
       E = n_runs ? atomicAdd(ro.cursor, (unsigned long long)n_runs) : 0ULL;
-      ro.read_run_offsets[r] = E;
+      if (!ro.intervals) ro.read_run_offsets[r] = E;
+    }
+    if (ro.intervals) {
+      if (n_runs) {  // (warp-uniform)
+        // a run = its start slot + the CONT slots that follow it: 128 continuation flags as two 64-bit words, inverted so the
+        // run's end is a find-first-set
+        u32 cm[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) cm[t] = __ballot_sync(0xffffffffu, 32u * t + lane < n_c && code[t] == RUN_CONT);
+        const u64 stop_lo = ~((u64)cm[0] | ((u64)cm[1] << 32)), stop_hi = ~((u64)cm[2] | ((u64)cm[3] << 32));
+        u64 o = __shfl_sync(0xffffffffu, E, 0);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const u32 p = 32 * t + lane;
+          const bool start = p < n_c && code[t] == RUN_START;
+          const u32 m = __ballot_sync(0xffffffffu, start);
+          if (start) {
+            const u32 q = p + 1;  // first slot that may end the run
+            u32 end = QR_CHUNK;
+            if (q < 64) {
+              const u64 a = stop_lo >> q;
+              if (a) end = q + (u32)__ffsll((long long)a) - 1;
+              else if (stop_hi) end = 64 + (u32)__ffsll((long long)stop_hi) - 1;
+            } else if (q < 128) {
+              const u64 a = stop_hi >> (q - 64);
+              if (a) end = q + (u32)__ffsll((long long)a) - 1;
+            }
+            const u64 dst = o + __popc(m & ((1u << lane) - 1u));
+            if (dst < ro.cap)
+              ro.intervals[dst] = make_uint4(hh[t].unitig_id, hh[t].pos | (hh[t].match == TWIN_MATCH ? 0x80000000u : 0u), (u32)(ro.read_base + r),
+                                             p | ((end - p) << 16));
+          }
+          o += __popc(m);
+        }
+      }
+      continue;
     }
     if (n_c) {  // the codes do not depend on the reservation: they go out while the atomic is in flight
 #pragma unroll

@@ -1195,6 +1195,47 @@ def test_packed_reads_in_packed_codes_out(yeast_sshash, yeast_dense, yeast_queri
         g.query_reads_runs_packed(words, mask, n_reads, 151)  # 121 slots per read: not a multiple of 4
 
 
+def test_hit_intervals_expand_to_the_exact_records(yeast_sshash, yeast_dense, yeast_queries):
+    """mazu_b200_query_reads_intervals_packed: one 16-byte record per hit run and nothing else; with the caller's N mask it
+    expands to exactly the oracle's records -- several read lengths, N windows, both index kinds, pageable and pinned output
+    buffers, several pipeline chunks, capacity too small."""
+    import ctypes as C
+
+    _, ref_codes = yeast_queries
+    os.environ["MAZU_B200_CHUNK_MIB"] = "1"
+    try:
+        for rl, n_reads in ((150, 9000), (158, 3000), (100, 1500), (47, 1200), (31, 500)):
+            bases, offs = _gen.sample_reads(ref_codes, n_reads, rl, seed=90 + rl, frac_ref=0.75, sub_rate=0.01, n_rate=0.003)
+            words, mask, _ = mz.pack_reads(bases, rl)
+            for g, o in (yeast_sshash, yeast_dense):
+                want, wcnt, _ = o.query_reads(bases, offs)
+                for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):  # unique k-mers: streaming answers are k2u's
+                    iv, cnt = g.query_reads_intervals_packed(words, mask, n_reads, rl, mode=mode)
+                    assert_hits_equal(g.expand_hit_intervals(iv, mask, n_reads, rl), want, "intervals, read length %d mode %d" % (rl, mode))
+                    assert list(cnt) == list(wcnt)
+                    # maximal runs: one record per run start of the run format
+                    slots = rl - g.k + 1
+                    hit = (want["match"] == 1) | (want["match"] == 2)
+                    assert int(iv["len"].sum()) == int(hit.sum()) and int(iv["len"].max(initial=0)) <= slots
+        # pinned output buffer: records are published by the device, no per-chunk synchronisation
+        g, o = yeast_sshash
+        pin = mz.PinnedArray((len(iv) + 8,), mz.INTERVAL_DTYPE)
+        iv2, _ = g.query_reads_intervals_packed(words, mask, n_reads, rl, intervals=pin.array)
+        recs = lambda a: sorted(a.tobytes()[16 * i:16 * i + 16] for i in range(len(a)))  # the order of the records is unspecified
+        assert len(iv2) == len(iv) and recs(iv2) == recs(iv)
+        # too small a buffer: the call says how many records it needs and never writes past the capacity
+        small = np.zeros(4, dtype=mz.INTERVAL_DTYPE)
+        guard = small.copy()
+        n = C.c_uint64(0)
+        rc = mz.lib().mazu_b200_query_reads_intervals_packed(g._h, mz._any_ptr(words), mz._any_ptr(mask), n_reads, rl, 0, mz._any_ptr(small), 2, C.byref(n), None)
+        assert rc == -7 and n.value == len(iv) and np.array_equal(small[2:], guard[2:])
+        # long reads are not for this interface
+        with pytest.raises(mz.MazuError):
+            g.query_reads_intervals_packed(words, mask, 10, 400)
+    finally:
+        del os.environ["MAZU_B200_CHUNK_MIB"]
+
+
 def test_pinned_host_buffers(yeast_sshash, yeast_queries):
     """mazu_b200_alloc_pinned: page-locked buffers for callers that do not link CUDA; same answers as pageable numpy arrays"""
     g, o = yeast_sshash
