@@ -263,6 +263,30 @@ impl GpuIndex {
         })
     }
 
+    /// The sparsest lossless host result of a short-read batch: one 16-byte `HitInterval` per run of consecutive k-mer slots whose
+    /// hits walk along one unitig, nothing per slot or per read (~0.19 B per lookup over PCIe).  `packed_reads`: 2-bit words in the
+    /// `kmers::SeqVector` layout, `ceil(read_len / 32)` words per read; `n_mask`: one bit per base, set = not ACGT.  Returns the
+    /// number of intervals written; `expand_hit_intervals` rebuilds the per-slot records.
+    pub fn query_reads_intervals(&self, packed_reads: &PinnedBuf<u64>, n_mask: Option<&[u64]>, n_reads: usize, read_len: usize, streaming: bool,
+                                 out: &mut PinnedBuf<sys::mazu_hit_interval_t>) -> Result<(usize, [u64; 3])> {
+        let mut counts = [0u64; 3];
+        let mut n = 0u64;
+        let mode = if streaming { sys::MAZU_MODE_STREAMING } else { sys::MAZU_MODE_RANDOM };
+        check(unsafe {
+            sys::mazu_b200_query_reads_intervals_packed(self.raw, packed_reads.ptr, n_mask.map_or(std::ptr::null(), |m| m.as_ptr()), n_reads as u64,
+                                                        read_len as u64, mode, out.ptr, out.len as u64, &mut n, counts.as_mut_ptr())
+        })?;
+        Ok((n as usize, counts))
+    }
+    /// Host-side decoder of the interval format: `out[r * (read_len - k + 1) + slot]`.
+    pub fn expand_hit_intervals(&self, intervals: &[sys::mazu_hit_interval_t], n_mask: Option<&[u64]>, n_reads: usize, read_len: usize,
+                                out: &mut [Hit]) -> Result<()> {
+        check(unsafe {
+            sys::mazu_b200_expand_hit_intervals(self.raw, intervals.as_ptr(), intervals.len() as u64, n_mask.map_or(std::ptr::null(), |m| m.as_ptr()),
+                                                n_reads as u64, read_len as u64, out.as_mut_ptr())
+        })
+    }
+
     /// Batched `GetRefPos::project_hits` (src/index.rs:156-216): occurrences of hit i are `out[offsets[i]..offsets[i+1]]`.
     pub fn project_hits(&self, hits: &[Hit]) -> Result<(Vec<u64>, Vec<MappedRefPos>)> {
         self.occ_call(Some(hits), None)

@@ -212,10 +212,12 @@ void make_tiles(const mazu_index* idx, const u64* d_read_offsets, u64 n_reads, u
 // is the run cursor (the chunk's run count afterwards).  Only for chunks whose reads all fit one tile.
 void launch_query_reads_runs(const mazu_index* idx, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, const u64* d_kmer_offsets,
                              u64* d_counts, u8* d_codes, Hit* d_runs, u64* d_rro, u64 cap, cudaStream_t s, const u64* d_packed_words = nullptr,
-                             const u64* d_packed_nmask = nullptr, u8* d_codes2 = nullptr, uint4* d_intervals = nullptr, u64 read_base = 0) {
-  MZ_CUDA(cudaMemsetAsync(d_rro + n_reads, 0, 8, s));
+                             const u64* d_packed_nmask = nullptr, u8* d_codes2 = nullptr, uint4* d_intervals = nullptr, u64 read_base = 0,
+                             u64* d_cursor = nullptr) {
+  if (!d_cursor) d_cursor = d_rro + n_reads;  // run format: the entry behind the last read's offset doubles as the cursor
+  MZ_CUDA(cudaMemsetAsync(d_cursor, 0, 8, s));
   if (!n_reads) return;
-  RunsTileOut ro{d_codes, d_codes2, d_runs, d_rro, (unsigned long long*)(d_rro + n_reads), cap, d_intervals, read_base};
+  RunsTileOut ro{d_codes, d_codes2, d_runs, d_rro, (unsigned long long*)d_cursor, cap, d_intervals, read_base};
   const bool ss = idx->view.k2u_kind == MAZU_K2U_SSHASH, boophf = idx->view.mphf.family == MPHF_FAMILY_BOOPHF;
 #define MZ_QRR(K, F)                                                                                                          \
   {                                                                                                                            \
@@ -978,7 +980,7 @@ mazu_status_t mazu_b200_query_reads_intervals_packed(const mazu_index_t* idx, co
     PoolScratch scratch(idx->pool, st.s[0]);
     const u64 max_reads = std::min(rpc, n_reads), max_slots = max_reads * slots;
     void *d_pw[NB], *d_pm[NB] = {}, *d_iv[NB];
-    u64* d_cur[NB];  // [0] run cursor of the chunk (its count afterwards), [1] scratch read-run-offset slot the kernel never touches
+    u64* d_cur[NB];  // run cursor of the chunk (its run count afterwards)
     u64* d_counts = (u64*)scratch.get(24);
     u64* d_base = (u64*)scratch.get(8);
     MZ_CUDA(cudaMemsetAsync(d_counts, 0, 24, st.s[0]));
@@ -987,7 +989,7 @@ mazu_status_t mazu_b200_query_reads_intervals_packed(const mazu_index_t* idx, co
       d_pw[b] = scratch.get(max_reads * wpr * 8 + 16);
       if (n_mask) d_pm[b] = scratch.get(max_reads * mpr * 8 + 16);
       d_iv[b] = scratch.get(max_slots * 16 + 16);  // worst case: every slot starts a run
-      d_cur[b] = (u64*)scratch.get(16);
+      d_cur[b] = (u64*)scratch.get(8);
     }
     for (int b = 1; b < NB; ++b) scratch.publish(st.s[b]);
     MZ_CUDA(cudaEventRecord(st.base_ev, st.s[0]));
@@ -998,9 +1000,8 @@ mazu_status_t mazu_b200_query_reads_intervals_packed(const mazu_index_t* idx, co
       cudaStream_t s = st.s[b];
       MZ_CUDA(cudaMemcpyAsync(d_pw[b], packed_reads + r0 * wpr, nr * wpr * 8, cudaMemcpyHostToDevice, s));
       if (n_mask) MZ_CUDA(cudaMemcpyAsync(d_pm[b], n_mask + r0 * mpr, nr * mpr * 8, cudaMemcpyHostToDevice, s));
-      // launch_query_reads_runs zeroes d_rro[n_reads] = the cursor: hand it an offsets pointer such that this is d_cur[b][0]
-      launch_query_reads_runs(idx, nullptr, nullptr, nr, read_len, nullptr, d_counts, nullptr, nullptr, d_cur[b] - nr, max_slots, s,
-                              (const u64*)d_pw[b], (const u64*)d_pm[b], nullptr, (uint4*)d_iv[b], r0);
+      launch_query_reads_runs(idx, nullptr, nullptr, nr, read_len, nullptr, d_counts, nullptr, nullptr, nullptr, max_slots, s, (const u64*)d_pw[b],
+                              (const u64*)d_pm[b], nullptr, (uint4*)d_iv[b], r0, d_cur[b]);
       if (out_dev) {
         MZ_CUDA(cudaStreamWaitEvent(s, st.base_ev, 0));  // the running base: after the previous chunk has advanced it
         hit_run_publish_kernel<<<idx->sm_count * 2, 256, 0, s>>>(nullptr, 0, (const Hit*)d_iv[b], d_cur[b], d_base, cap, (Hit*)out_dev);
