@@ -219,9 +219,13 @@ void launch_query_reads_runs(const mazu_index* idx, const u8* d_bases, const u64
   if (!n_reads) return;
   RunsTileOut ro{d_codes, d_codes2, d_runs, d_rro, (unsigned long long*)d_cursor, cap, d_intervals, read_base};
   const bool ss = idx->view.k2u_kind == MAZU_K2U_SSHASH, boophf = idx->view.mphf.family == MPHF_FAMILY_BOOPHF;
+  const int io = d_intervals ? RUNS_IO_INTERVALS : (d_packed_words && d_codes2 ? RUNS_IO_PACKED : RUNS_IO_ASCII);
+  if (io == RUNS_IO_ASCII && (d_packed_words || d_codes2)) throw Error(MAZU_ERR_INVALID_ARG, "packed reads and 2-bit codes come together");
 #define MZ_QRR(K, F)                                                                                                          \
   {                                                                                                                            \
-    auto kern = query_reads_runs_kernel<K, F>;                                                                                 \
+    auto kern = io == RUNS_IO_INTERVALS ? query_reads_runs_kernel<K, F, RUNS_IO_INTERVALS>                                     \
+                                        : (io == RUNS_IO_PACKED ? query_reads_runs_kernel<K, F, RUNS_IO_PACKED>               \
+                                                                : query_reads_runs_kernel<K, F, RUNS_IO_ASCII>);              \
     int grid = grid_for(kern, QR_WARPS * 32, idx, QR_WARPS, n_reads);                                                          \
     kern<<<grid, QR_WARPS * 32, 0, s>>>(idx->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets,              \
                                         (unsigned long long*)d_counts, ro, d_packed_words, d_packed_nmask);                    \
@@ -691,6 +695,7 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
       else
         for (u64 r = 0; r < n_reads && fused_runs; ++r) fused_runs = read_offsets[r + 1] - read_offsets[r] <= max_len;
     }
+    if (fused_runs && packed_in != ro->codes2) fused_runs = false;  // the fused kernel is built for ASCII in / byte codes out and packed in / 2-bit codes out
     // two buffers / streams alternate; the sync-free run path uses three, because its per-chunk chain (H2D, lookups, encode, two
     // D2H copies) is 2.3x as long as its compute and two streams leave the SMs idle a third of the time
     static const int MAXB = 6;

@@ -1318,7 +1318,11 @@ struct RunsTileOut {
   u64 read_base;               // index of the chunk's first read in the caller's batch
 };
 
-template <int KIND, u32 FAMILY>
+// IO: 0 = ASCII reads in, one code byte per slot out; 1 = 2-bit packed reads in, 2-bit codes out; 2 = packed reads in, interval
+// records out.  One instantiation per mode: with all three in one body the kernel grew to 4,000 SASS instructions and every
+// mode lost 20 % to instruction fetch (profiles/experiments/README.md).
+enum { RUNS_IO_ASCII = 0, RUNS_IO_PACKED = 1, RUNS_IO_INTERVALS = 2 };
+template <int KIND, u32 FAMILY, int IO>
 __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
                                                                            const u64* __restrict__ read_offsets, u64 n_reads, u64 uniform_len,
                                                                            const u64* __restrict__ kmer_offsets, unsigned long long* __restrict__ counts,
@@ -1347,7 +1351,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(cons
     u32 code[4], n_runs = 0;
     if (n_c) {
       ChunkInfo ci;
-      if (packed_words)  // uniform reads, 2-bit packed (the launcher passes these only with uniform_len)
+      if (IO != RUNS_IO_ASCII)  // uniform reads, 2-bit packed
         stage_encode_packed(packed_words + r * ((len + 31) / 32), packed_nmask ? packed_nmask + r * ((len + 63) / 64) : nullptr, (u32)len, n_c, k, lane, S, ci);
       else
         stage_encode(bases + beg, len, 0, n_c, k, lane, S, ci);
@@ -1394,9 +1398,9 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(cons
     unsigned long long E = 0;
     if (lane == 0) {
       E = n_runs ? atomicAdd(ro.cursor, (unsigned long long)n_runs) : 0ULL;
-      if (!ro.intervals) ro.read_run_offsets[r] = E;
+      if (IO != RUNS_IO_INTERVALS) ro.read_run_offsets[r] = E;
     }
-    if (ro.intervals) {
+    if (IO == RUNS_IO_INTERVALS) {
       if (n_runs) {  // (warp-uniform)
         // a run = its start slot + the CONT slots that follow it: 128 continuation flags as two 64-bit words, inverted so the
         // run's end is a find-first-set
@@ -1435,7 +1439,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(cons
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const u32 p = 32 * t + lane;
-        if (ro.codes2) {  // four neighbouring lanes share a byte
+        if (IO == RUNS_IO_PACKED) {  // four neighbouring lanes share a byte
           u32 v = p < n_c ? (code[t] & 3u) << (2 * (lane & 3u)) : 0u;
           v |= __shfl_xor_sync(0xffffffffu, v, 1);
           v |= __shfl_xor_sync(0xffffffffu, v, 2);
