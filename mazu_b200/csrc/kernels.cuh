@@ -190,7 +190,10 @@ __global__ void __launch_bounds__(256) k2u_batch_kernel(const __grid_constant__ 
 // The MPHF level loop is the divergent part of such a lookup -- one key per lane keeps 12 of 32 lanes busy
 // (profiles/r01k_prof_config1.summary.txt) -- so a lane takes KB_N keys and walks them through ONE loop, refilling itself
 // (mphf_levels_multi); the hashes before the loop and rank / position / window / unitig bounds after it run with all lanes.
-static const int KB_N = 4;
+#ifndef MAZU_KB_N
+#define MAZU_KB_N 4
+#endif
+static const int KB_N = MAZU_KB_N;
 template <u32 FAMILY>
 __global__ void __launch_bounds__(256) k2u_batch_pfhash_kernel(const __grid_constant__ IndexView ix, const u64* __restrict__ fw_words, u64 n,
                                                                Hit* __restrict__ out) {
