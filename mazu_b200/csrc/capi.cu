@@ -157,7 +157,7 @@ void launch_query_reads(const mazu_index* ix, const u8* d_bases, const u64* d_re
   if (n_reads == 0) return;
   const bool ss = ix->view.k2u_kind == MAZU_K2U_SSHASH;
   const bool native = ix->view.mphf.family != MPHF_FAMILY_BOOPHF;  // SSHash: fingerprinted cascade for the minimizers, native MPHF for the skew index
-  // distinct canonical k-mers: the cursor walk cannot answer anything the lookup does not (kernels.cuh, count_duplicated_kmers_kernel)
+  // distinct canonical k-mers: the cursor walk cannot answer anything the lookup does not (kernels.cuh, flag_duplicated_kmers_kernel)
   const bool st = mode == MAZU_MODE_STREAMING && !ix->kmers_unique;
 #define MZ_QR(M, K, F) launch_qr<M, K, F>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, s)
   if (ss) {

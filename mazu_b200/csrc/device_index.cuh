@@ -123,7 +123,7 @@ struct mazu_index {
   // function attributes are per device: the staged decode kernel's dynamic shared memory limit is raised once per handle
   mutable std::once_flag occ_attr_once;
   bool compact_ok = true;  // every unitig shorter than 2^30 bases: mazu_hit8_t can hold pos | match << 30
-  // canonical k-mers pairwise distinct (count_duplicated_kmers_kernel at creation): streaming queries then equal random-access
+  // canonical k-mers pairwise distinct (flag_duplicated_kmers_kernel at creation): streaming queries then equal random-access
   // queries record for record and are served by the random-access kernel
   bool kmers_unique = false;
   ~mazu_index() {

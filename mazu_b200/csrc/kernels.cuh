@@ -510,9 +510,6 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
             loc = i + lane;
           }
         }
-#ifdef MAZU_PREFETCH  // measured and rejected (profiles/experiments/README.md): -2 % config 5, -5 % config 2
-        if (cnt && n != BN_SKEW) prefetch_l2(ix.pos.words + ((a * ix.pos.width) >> 6));
-#endif
       }
       S.bstart[p] = a;
       S.bn[p] = n;
@@ -704,7 +701,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const _
     }
     const u8* seq = bases + beg;
     const u64 nk = len >= k ? len - k + 1 : 0;
-#ifdef MAZU_PREFETCH  // measured and rejected together with the prefetch in stage B
+#ifdef MAZU_PREFETCH  // A/B knob: L2 prefetch of the warp's next read (profiles/experiments/README.md)
     if (uniform_len && !segmented) {  // the warp's next read: its bases are the first thing stage E waits for
       const u64 nxt = item + (u64)gridDim.x * QR_WARPS;
       if (nxt < n_items && lane < 2) prefetch_l2(bases + nxt * uniform_len + 128 * lane);
