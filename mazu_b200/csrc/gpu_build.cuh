@@ -132,6 +132,28 @@ __global__ void mark_heads_kernel(const u64* __restrict__ keys, u64 n, u64* __re
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
     flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1ULL : 0ULL;
 }
+// stage 3b (host twin: build_sshash step 2b): an entry equal to its predecessor -- the same (word, position) pushed by both of
+// the reference's streams -- is dropped unless its bucket goes to the skew index (more than skew_param entries)
+__global__ void mark_repeats_kernel(const u64* __restrict__ words, const u64* __restrict__ poss, const u64* __restrict__ gid,
+                                    const u64* __restrict__ ranges, u64 n, u64 skew_param, u64* __restrict__ keep) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    bool rep = i > 0 && words[i] == words[i - 1] && poss[i] == poss[i - 1];
+    if (rep) {
+      const u64 g = gid[i] - 1;
+      if (ranges[g + 1] - ranges[g] > skew_param) rep = false;
+    }
+    keep[i] = rep ? 0ULL : 1ULL;
+  }
+}
+__global__ void compact_pairs_kernel(const u64* __restrict__ words, const u64* __restrict__ poss, const u64* __restrict__ keep,
+                                     const u64* __restrict__ kidx, u64 n, u64* __restrict__ words_out, u64* __restrict__ poss_out) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+    if (keep[i]) {
+      const u64 o = kidx[i] - 1;  // kidx = inclusive scan of keep
+      words_out[o] = words[i];
+      poss_out[o] = poss[i];
+    }
+}
 // gid = inclusive scan of flags (1-based group number); heads write their key / first index
 __global__ void scatter_groups_kernel(const u64* __restrict__ keys, const u64* __restrict__ vals, const u64* __restrict__ flags,
                                       const u64* __restrict__ gid, u64 n, u64* __restrict__ set, u64* __restrict__ first_val,

@@ -335,7 +335,7 @@ void build_sshash_gpu(mazu_index& ix, u32 w, u64 skew_param, u64 seed, double ga
   collect_minimizers_kernel<false><<<cgrid, QR_WARPS * 32>>>(uv, w, seed, (u64*)counts.p, nullptr, nullptr, nullptr);
   MZ_CUDA(cudaGetLastError());
   exclusive_scan_u64(tmp, (const u64*)counts.p, (u64*)bases.p, 2 * U + 1);
-  const u64 n = d2h_value((const u64*)bases.p + 2 * U);
+  u64 n = d2h_value((const u64*)bases.p + 2 * U);
   if (n == 0) throw Error(MAZU_ERR_INVALID_DATA, "no minimizer occurrence collected");
   DevBufP words = std::make_shared<DevBuf>(n * 8, dev), poss = std::make_shared<DevBuf>(n * 8, dev);
   collect_minimizers_kernel<true><<<cgrid, QR_WARPS * 32>>>(uv, w, seed, nullptr, (const u64*)bases.p, (u64*)words->p, (u64*)poss->p);
@@ -347,7 +347,30 @@ void build_sshash_gpu(mazu_index& ix, u32 w, u64 skew_param, u64 seed, double ga
   poss.reset();
   // 3. group
   DevBufP mm_set, ranges, gid;
-  const u64 M = group_sorted_gpu(tmp, (const u64*)words_s->p, nullptr, n, dev, sm, mm_set, ranges, nullptr, gid);
+  u64 M = group_sorted_gpu(tmp, (const u64*)words_s->p, nullptr, n, dev, sm, mm_set, ranges, nullptr, gid);
+  // 3b. drop the second copy of an entry pushed by both streams (light buckets only), then group what is left
+  {
+    DevBuf keepf(n * 8, dev), kidx(n * 8, dev);
+    mark_repeats_kernel<<<grid_1d(n, sm), 256>>>((const u64*)words_s->p, (const u64*)poss_s->p, (const u64*)gid->p, (const u64*)ranges->p, n,
+                                                 skew_param, (u64*)keepf.p);
+    MZ_CUDA(cudaGetLastError());
+    inclusive_scan_u64(tmp, (const u64*)keepf.p, (u64*)kidx.p, n);
+    const u64 n_kept = d2h_value((const u64*)kidx.p + (n - 1));
+    if (n_kept != n) {
+      DevBufP words_c = std::make_shared<DevBuf>(n_kept * 8, dev), poss_c = std::make_shared<DevBuf>(n_kept * 8, dev);
+      compact_pairs_kernel<<<grid_1d(n, sm), 256>>>((const u64*)words_s->p, (const u64*)poss_s->p, (const u64*)keepf.p, (const u64*)kidx.p, n,
+                                                    (u64*)words_c->p, (u64*)poss_c->p);
+      MZ_CUDA(cudaGetLastError());
+      words_s = words_c;
+      poss_s = poss_c;
+      n = n_kept;
+      mm_set.reset();
+      ranges.reset();
+      gid.reset();
+      const u64 M2 = group_sorted_gpu(tmp, (const u64*)words_s->p, nullptr, n, dev, sm, mm_set, ranges, nullptr, gid);
+      if (M2 != M) throw Error(MAZU_ERR_OTHER, "internal: dropping repeated entries changed the minimizer set");
+    }
+  }
   words_s.reset();
   // 4. perfect hash over the minimizer set: the fingerprinted cascade; its value is the minimizer's slot
   DevCascade casc = build_cascade_gpu((const u64*)mm_set->p, M, dev, sm);

@@ -606,6 +606,25 @@ inline std::shared_ptr<K2UHost> build_sshash(std::shared_ptr<const UnitigSetHost
   }
   // 2. stable sort by word, group (sshash.rs:150-172)
   parallel_stable_sort_by_key(minimizers, [](const MinOcc& m) { return m.word; }, 2 * w, T);
+  // 2b. A super-k-mer that spans a flip of the canonical strand is pushed by both of the reference's streams (fw-canonical
+  // k-mers, then rc-canonical ones: sshash.rs:100-143), so after the stable sort its (word, position) sits twice in a row in
+  // its bucket -- under the strand-symmetric minimizer order that is the commonest bucket there is.  The second copy offers
+  // the two candidates of the first, which have just failed when the bucket loop gets to it (sshash.rs:494-552 returns at the
+  // first match): dropping it cannot change an answer, and a k-mer that misses stops one dependent access earlier.  Buckets
+  // that the reference sends to the skew index (more than skew_param entries, sshash.rs:232,486-490) are left as they are,
+  // so every bucket takes the same path as in the reference.
+  {
+    u64 out = 0;
+    for (u64 i = 0; i < minimizers.size();) {
+      u64 j = i;
+      while (j < minimizers.size() && minimizers[j].word == minimizers[i].word) ++j;
+      const bool heavy = j - i > skew_param;
+      for (u64 t = i; t < j; ++t)
+        if (heavy || t == i || minimizers[t].pos != minimizers[t - 1].pos) minimizers[out++] = minimizers[t];
+      i = j;
+    }
+    minimizers.resize(out);
+  }
   std::vector<u64> mm_set, ranges;  // ranges = prefix sum of mm_occs
   for (u64 i = 0; i < minimizers.size(); ++i)
     if (i == 0 || minimizers[i].word != minimizers[i - 1].word) {

@@ -134,14 +134,8 @@ __device__ __forceinline__ bool sshash_finish(const IndexView& ix, u64 fw, u64 r
   const u32 k = ix.unitigs.k;
   const u64 last_km_start_pos = ix.unitigs.total_len - k;
   const u64 rc_offset = (u64)(k - offset - ix.w);
-  u64 prev_mm_pos = ~0ULL;
-  for (u64 pi = pos_start; pi < pos_end; ++pi) {
+  for (u64 pi = pos_start; pi < pos_end; ++pi) {  // (the builders drop an entry equal to its predecessor: host_build.hpp step 2b)
     u64 mm_pos = packed_get(ix.pos, pi);
-    // Under the strand-symmetric minimizer order a super-k-mer that spans a strand flip is pushed by both of the reference's
-    // streams (sshash.rs:100-143), so a bucket often holds the same position twice in a row: the same two candidates, which
-    // have just failed.
-    if (mm_pos == prev_mm_pos) continue;
-    prev_mm_pos = mm_pos;
     if (mm_pos >= offset && mm_pos - offset <= last_km_start_pos) {  // sshash.rs:498
       u64 km_pos = mm_pos - offset;
       u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
@@ -542,12 +536,9 @@ __device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpSta
   const u32 rc_offset = (k - ix.w) - offset;
   const u64 last_km_start_pos = ix.unitigs.total_len - k;
   const u32 loc = S.lrank[lp];
-  u64 prev_mm_pos = ~0ULL;
 #pragma unroll 1
-  for (u32 e = 0; e < n; ++e) {
+  for (u32 e = 0; e < n; ++e) {  // (no entry equals its predecessor: the builders drop the copy the second stream pushes)
     u64 mm_pos = e == 0 ? S.bfirst[lp] : packed_get(ix.pos, pos_start + e);
-    if (mm_pos == prev_mm_pos) continue;  // same entry twice in a row (both streams of the builder): same candidates, already failed
-    prev_mm_pos = mm_pos;
     const bool located = e == 0 && loc != QR_NO_LOC;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {  // candidate from the fw offset (sshash.rs:498), then from the rc offset (sshash.rs:527; same window when equal)
