@@ -582,6 +582,29 @@ def main():
 
                     e2e_extra["packed_runs"] = (runs_step, e2e_units, e2e_reads * wpr * 8, None, runs_api)
                     e2e_extra_post = {"packed_runs": runs_post}
+
+                    # ... and the same records from the reads as the reference takes them: ASCII in (1.25 B per lookup), nothing packed
+                    # by the caller, nothing outside the timed loop
+                    def e2e_ascii_iv_step():
+                        n_iv = C.c_uint64(0)
+                        mz._check(mz.lib().mazu_b200_query_reads_intervals(index._h, mz._any_ptr(hb), e2e_reads, READ_LEN, mode, mz._any_ptr(h_iv),
+                                                                           h_iv.shape[0], C.byref(n_iv), mz._np_ptr(h_cnt)))
+                        runs_state["n_iv_ascii"] = n_iv.value
+
+                    def ascii_iv_post(e):
+                        e["d2h_bytes_per_step"] = (16 * runs_state["n_iv_ascii"] + 32) * world
+                        e["n_runs_per_step_per_gpu"] = runs_state["n_iv_ascii"]
+                        m = min(e2e_reads, 20000)
+                        iv = h_iv.numpy().view(np.uint32).reshape(-1).view(mz.INTERVAL_DTYPE)[: runs_state["n_iv_ascii"]]
+                        exp = index.expand_hit_intervals_ascii(np.ascontiguousarray(iv[iv["read"] < m]), hb[: m * READ_LEN], m, READ_LEN)
+                        e["expands_to_full_records"] = bool(np.array_equal(exp.view(np.uint32).reshape(-1, 4), hits[: m * nk_per_read].cpu().numpy().view(np.uint32)))
+                        e["counts_match_device_path"] = bool(int(h_cnt[0]) == e2e_units and int(h_cnt[1]) > 0)
+
+                    e2e_extra["ascii_intervals"] = (e2e_ascii_iv_step, e2e_units, e2e_reads * READ_LEN, None,
+                                                    "mazu_b200_query_reads_intervals (C ABI, host buffers): pinned ASCII reads in, as the reference takes "
+                                                    "them (150 B per read, no packing by the caller); out: one 16-byte record per hit run (lossless: "
+                                                    "mazu_b200_expand_hit_intervals_ascii rebuilds every record)")
+                    e2e_extra_post["ascii_intervals"] = ascii_iv_post
             else:  # read lengths whose slot count is not a multiple of 4: the byte-coded run call is the headline
                 e2e_step, e2e_api = e2e_ascii_step, ascii_api
 

@@ -166,6 +166,8 @@ extern "C" {
     pub fn mazu_b200_query_reads_runs_packed(idx: *const mazu_index_t, packed_reads: *const u64, n_mask: *const u64, n_reads: u64, read_len: u64, mode: i32, out_codes2: *mut u8, out_runs: *mut mazu_hit_t, cap_runs: u64, out_read_run_offsets: *mut u64, out_n_runs: *mut u64, counts: *mut u64) -> mazu_status_t;
     pub fn mazu_b200_query_reads_intervals_packed(idx: *const mazu_index_t, packed_reads: *const u64, n_mask: *const u64, n_reads: u64, read_len: u64, mode: i32, out_intervals: *mut mazu_hit_interval_t, cap: u64, out_n: *mut u64, counts: *mut u64) -> mazu_status_t;
     pub fn mazu_b200_expand_hit_intervals(idx: *const mazu_index_t, intervals: *const mazu_hit_interval_t, n_intervals: u64, n_mask: *const u64, n_reads: u64, read_len: u64, out_hits: *mut mazu_hit_t) -> mazu_status_t;
+    pub fn mazu_b200_query_reads_intervals(idx: *const mazu_index_t, bases: *const u8, n_reads: u64, read_len: u64, mode: i32, out_intervals: *mut mazu_hit_interval_t, cap: u64, out_n: *mut u64, counts: *mut u64) -> mazu_status_t;
+    pub fn mazu_b200_expand_hit_intervals_ascii(idx: *const mazu_index_t, intervals: *const mazu_hit_interval_t, n_intervals: u64, bases: *const u8, n_reads: u64, read_len: u64, out_hits: *mut mazu_hit_t) -> mazu_status_t;
     pub fn mazu_b200_pack_reads(bases: *const u8, n_reads: u64, read_len: u64, out_words: *mut u64, out_n_mask: *mut u64, n_non_acgt: *mut u64) -> mazu_status_t;
     pub fn mazu_b200_expand_hit_runs_packed(codes2: *const u8, runs: *const mazu_hit_t, read_run_offsets: *const u64, n_reads: u64, uniform_slots: u64, out_hits: *mut mazu_hit_t) -> mazu_status_t;
     pub fn mazu_b200_unitig_seq(idx: *const mazu_index_t, unitig_id: u64, out_words: *mut u64, cap_words: u64, len: *mut u64) -> mazu_status_t;

@@ -278,6 +278,27 @@ impl GpuIndex {
         })?;
         Ok((n as usize, counts))
     }
+    /// The same for ASCII reads (`n_reads * read_len` bytes, any case, non-ACGT skipped) -- the slices the reference hands to
+    /// `CanonicalKmerIterator::from_u8_slice` -- with nothing for the caller to pack.
+    pub fn query_reads_intervals_ascii(&self, bases: &PinnedBuf<u8>, n_reads: usize, read_len: usize, streaming: bool,
+                                       out: &mut PinnedBuf<sys::mazu_hit_interval_t>) -> Result<(usize, [u64; 3])> {
+        let mut counts = [0u64; 3];
+        let mut n = 0u64;
+        let mode = if streaming { sys::MAZU_MODE_STREAMING } else { sys::MAZU_MODE_RANDOM };
+        check(unsafe {
+            sys::mazu_b200_query_reads_intervals(self.raw, bases.ptr, n_reads as u64, read_len as u64, mode, out.ptr, out.len as u64, &mut n,
+                                                 counts.as_mut_ptr())
+        })?;
+        Ok((n as usize, counts))
+    }
+    /// Decoder for the ASCII call: skipped windows are read off the bases.
+    pub fn expand_hit_intervals_ascii(&self, intervals: &[sys::mazu_hit_interval_t], bases: &[u8], n_reads: usize, read_len: usize,
+                                      out: &mut [Hit]) -> Result<()> {
+        check(unsafe {
+            sys::mazu_b200_expand_hit_intervals_ascii(self.raw, intervals.as_ptr(), intervals.len() as u64, bases.as_ptr(), n_reads as u64,
+                                                      read_len as u64, out.as_mut_ptr())
+        })
+    }
     /// Host-side decoder of the interval format: `out[r * (read_len - k + 1) + slot]`.
     pub fn expand_hit_intervals(&self, intervals: &[sys::mazu_hit_interval_t], n_mask: Option<&[u64]>, n_reads: usize, read_len: usize,
                                 out: &mut [Hit]) -> Result<()> {

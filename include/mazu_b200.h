@@ -265,9 +265,17 @@ typedef struct mazu_hit_interval {
 mazu_status_t mazu_b200_query_reads_intervals_packed(const mazu_index_t* idx, const uint64_t* packed_reads, const uint64_t* n_mask,
                                                      uint64_t n_reads, uint64_t read_len, int32_t mode,
                                                      mazu_hit_interval_t* out_intervals, uint64_t cap, uint64_t* out_n, uint64_t* counts);
+/* The same result for reads as the reference takes them -- ASCII, n_reads x read_len bytes (the sequence slices handed to
+ * CanonicalKmerIterator::from_u8_slice in src/bin/kphf/main.rs:303,314 and src/index/validate.rs:57), any case, non-ACGT bases
+ * skipped: 1.25 bytes per lookup in, ~0.19 out, nothing for the caller to pack.  Same restrictions as the packed call. */
+mazu_status_t mazu_b200_query_reads_intervals(const mazu_index_t* idx, const uint8_t* bases, uint64_t n_reads, uint64_t read_len, int32_t mode,
+                                              mazu_hit_interval_t* out_intervals, uint64_t cap, uint64_t* out_n, uint64_t* counts);
 /* host-side decoder (multi-threaded): out_hits[r * (read_len - k + 1) + slot]; n_mask as passed to the query (or NULL) */
 mazu_status_t mazu_b200_expand_hit_intervals(const mazu_index_t* idx, const mazu_hit_interval_t* intervals, uint64_t n_intervals,
                                              const uint64_t* n_mask, uint64_t n_reads, uint64_t read_len, mazu_hit_t* out_hits);
+/* ... and for the ASCII call: the skipped windows are read off the caller's bases */
+mazu_status_t mazu_b200_expand_hit_intervals_ascii(const mazu_index_t* idx, const mazu_hit_interval_t* intervals, uint64_t n_intervals,
+                                                   const uint8_t* bases, uint64_t n_reads, uint64_t read_len, mazu_hit_t* out_hits);
 /* host-side decoder of the run format (multi-threaded, no device work): out_hits[slot] for every slot of every read.
  * kmer_offsets may be NULL for uniform batches (uniform_slots = read_len - k + 1). */
 mazu_status_t mazu_b200_expand_hit_runs(const uint8_t* codes, const mazu_hit_t* runs, const uint64_t* read_run_offsets,

@@ -134,6 +134,8 @@ def _signatures():
         "mazu_b200_pack_reads": (i32, [vp, u64, u64, vp, vp, vp]),
         "mazu_b200_query_reads_intervals_packed": (i32, [vp, vp, vp, u64, u64, i32, vp, u64, vp, vp]),
         "mazu_b200_expand_hit_intervals": (i32, [vp, vp, u64, vp, u64, u64, vp]),
+        "mazu_b200_query_reads_intervals": (i32, [vp, vp, u64, u64, i32, vp, u64, vp, vp]),
+        "mazu_b200_expand_hit_intervals_ascii": (i32, [vp, vp, u64, vp, u64, u64, vp]),
         "mazu_b200_expand_hit_runs_packed": (i32, [vp, vp, vp, u64, u64, vp]),
         "mazu_b200_encode_reads": (i32, [vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp]),
         "mazu_b200_decode_occs": (i32, [vp, vp, u64, vp, vp, u64, vp, i32, vp]),
@@ -505,6 +507,29 @@ class ModIndex:
             _check(rc)
             break
         return intervals[: n.value], cnt
+
+    def query_reads_intervals(self, bases, n_reads, read_len, mode=MODE_RANDOM, intervals=None):
+        """mazu_b200_query_reads_intervals: ASCII reads (n_reads x read_len bytes) in, one 16-byte record per hit run out."""
+        cnt = np.zeros(3, dtype=np.uint64)
+        n = C.c_uint64(0)
+        if intervals is None:
+            intervals = np.empty(max(1024, n_reads * max(read_len - self.k + 1, 0) // 16), dtype=INTERVAL_DTYPE)
+        while True:
+            rc = lib().mazu_b200_query_reads_intervals(self._h, _any_ptr(bases), n_reads, read_len, mode, _any_ptr(intervals), len(intervals),
+                                                       C.byref(n), _np_ptr(cnt))
+            if rc != 0 and n.value > len(intervals):
+                intervals = np.empty(n.value, dtype=INTERVAL_DTYPE)
+                continue
+            _check(rc)
+            break
+        return intervals[: n.value], cnt
+
+    def expand_hit_intervals_ascii(self, intervals, bases, n_reads, read_len, out=None):
+        """mazu_b200_expand_hit_intervals_ascii: every mazu_hit_t of the batch from the interval records + the ASCII reads."""
+        out = np.empty(n_reads * max(read_len - self.k + 1, 0), dtype=HIT_DTYPE) if out is None else out
+        _check(lib().mazu_b200_expand_hit_intervals_ascii(self._h, _any_ptr(intervals), len(intervals), _any_ptr(bases), n_reads, read_len,
+                                                          _any_ptr(out)))
+        return out
 
     def expand_hit_intervals(self, intervals, n_mask, n_reads, read_len, out=None):
         """mazu_b200_expand_hit_intervals: every mazu_hit_t of the batch from the interval records (+ the N mask)."""

@@ -219,13 +219,15 @@ void launch_query_reads_runs(const mazu_index* idx, const u8* d_bases, const u64
   if (!n_reads) return;
   RunsTileOut ro{d_codes, d_codes2, d_runs, d_rro, (unsigned long long*)d_cursor, cap, d_intervals, read_base};
   const bool ss = idx->view.k2u_kind == MAZU_K2U_SSHASH, boophf = idx->view.mphf.family == MPHF_FAMILY_BOOPHF;
-  const int io = d_intervals ? RUNS_IO_INTERVALS : (d_packed_words && d_codes2 ? RUNS_IO_PACKED : RUNS_IO_ASCII);
+  const int io = d_intervals ? (d_packed_words ? RUNS_IO_INTERVALS : RUNS_IO_INTERVALS_ASCII)
+                             : (d_packed_words && d_codes2 ? RUNS_IO_PACKED : RUNS_IO_ASCII);
   if (io == RUNS_IO_ASCII && (d_packed_words || d_codes2)) throw Error(MAZU_ERR_INVALID_ARG, "packed reads and 2-bit codes come together");
 #define MZ_QRR(K, F)                                                                                                          \
   {                                                                                                                            \
-    auto kern = io == RUNS_IO_INTERVALS ? query_reads_runs_kernel<K, F, RUNS_IO_INTERVALS>                                     \
-                                        : (io == RUNS_IO_PACKED ? query_reads_runs_kernel<K, F, RUNS_IO_PACKED>               \
-                                                                : query_reads_runs_kernel<K, F, RUNS_IO_ASCII>);              \
+    auto kern = io == RUNS_IO_INTERVALS         ? query_reads_runs_kernel<K, F, RUNS_IO_INTERVALS>                             \
+                : io == RUNS_IO_INTERVALS_ASCII ? query_reads_runs_kernel<K, F, RUNS_IO_INTERVALS_ASCII>                       \
+                : io == RUNS_IO_PACKED          ? query_reads_runs_kernel<K, F, RUNS_IO_PACKED>                                \
+                                                : query_reads_runs_kernel<K, F, RUNS_IO_ASCII>;                                \
     int grid = grid_for(kern, QR_WARPS * 32, idx, QR_WARPS, n_reads);                                                          \
     kern<<<grid, QR_WARPS * 32, 0, s>>>(idx->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets,              \
                                         (unsigned long long*)d_counts, ro, d_packed_words, d_packed_nmask);                    \
@@ -650,8 +652,8 @@ static mazu_status_t query_reads_impl(const mazu_index_t* idx, const uint8_t* ba
     }
     auto base_off = [&](u64 r) { return uniform_read_len ? r * uniform_read_len : read_offsets[r]; };
     auto slot_off = [&](u64 r) { return uniform_read_len ? r * (uniform_read_len >= k ? uniform_read_len - k + 1 : 0) : koffs[r]; };
-    // chunk boundaries: ~32 MiB of bases per chunk
-    u64 TARGET = 32ull << 20;
+    // chunk boundaries: ~16 MiB of bases per chunk (8 / 16 / 32 / 64 measured on the final kernels: profiles/experiments/README.md)
+    u64 TARGET = 16ull << 20;
     if (const char* e = getenv("MAZU_B200_CHUNK_MIB")) {  // tuning knob: bases per pipeline chunk
       long v = atol(e);
       if (v > 0) TARGET = (u64)v << 20;
@@ -937,13 +939,14 @@ mazu_status_t mazu_b200_query_reads_runs_packed(const mazu_index_t* idx, const u
 // per chunk H2D of the 2-bit words, the fused run kernel in interval mode (chunk-local records + count), then the records go
 // to the caller's buffer at a running base -- published by a kernel when the buffer is pinned (no host synchronisation at
 // all), or copied after a per-chunk synchronisation when it is pageable.
-mazu_status_t mazu_b200_query_reads_intervals_packed(const mazu_index_t* idx, const uint64_t* packed_reads, const uint64_t* n_mask,
-                                                     uint64_t n_reads, uint64_t read_len, int32_t mode, mazu_hit_interval_t* out_intervals,
-                                                     uint64_t cap, uint64_t* out_n, uint64_t* counts) {
+// `bases` set: the reads arrive as ASCII (n_reads x read_len bytes, the form the reference takes them in); else 2-bit packed.
+static mazu_status_t query_reads_intervals_impl(const mazu_index_t* idx, const uint8_t* bases, const uint64_t* packed_reads, const uint64_t* n_mask,
+                                                uint64_t n_reads, uint64_t read_len, int32_t mode, mazu_hit_interval_t* out_intervals,
+                                                uint64_t cap, uint64_t* out_n, uint64_t* counts) {
   static_assert(sizeof(mazu_hit_interval_t) == 16, "interval records are 16 bytes");
   u64 n_total = 0;
   mazu_status_t rc = guarded([&] {
-    if (!idx || !read_len || (n_reads && !packed_reads) || (cap && !out_intervals)) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
+    if (!idx || !read_len || (n_reads && !packed_reads && !bases) || (cap && !out_intervals)) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
     if (mode != MAZU_MODE_RANDOM && mode != MAZU_MODE_STREAMING) throw Error(MAZU_ERR_INVALID_ARG, "unknown query mode");
     if (mode == MAZU_MODE_STREAMING && !idx->kmers_unique)
       throw Error(MAZU_ERR_INVALID_ARG, "hit intervals come from the random-access kernel: streaming mode needs an index with unique k-mers");
@@ -955,7 +958,7 @@ mazu_status_t mazu_b200_query_reads_intervals_packed(const mazu_index_t* idx, co
     if (!n_reads || !slots) return;
     DeviceGuard g(idx->device);
     const u64 wpr = (read_len + 31) / 32, mpr = (read_len + 63) / 64;
-    u64 TARGET = 32ull << 20;
+    u64 TARGET = 16ull << 20;
     if (const char* e = getenv("MAZU_B200_CHUNK_MIB")) {
       long v = atol(e);
       if (v > 0) TARGET = (u64)v << 20;
@@ -991,8 +994,8 @@ mazu_status_t mazu_b200_query_reads_intervals_packed(const mazu_index_t* idx, co
     MZ_CUDA(cudaMemsetAsync(d_counts, 0, 24, st.s[0]));
     MZ_CUDA(cudaMemsetAsync(d_base, 0, 8, st.s[0]));
     for (int b = 0; b < NB; ++b) {
-      d_pw[b] = scratch.get(max_reads * wpr * 8 + 16);
-      if (n_mask) d_pm[b] = scratch.get(max_reads * mpr * 8 + 16);
+      d_pw[b] = scratch.get(bases ? max_reads * read_len + 16 : max_reads * wpr * 8 + 16);  // ASCII bases, or 2-bit words
+      if (n_mask && !bases) d_pm[b] = scratch.get(max_reads * mpr * 8 + 16);
       d_iv[b] = scratch.get(max_slots * 16 + 16);  // worst case: every slot starts a run
       d_cur[b] = (u64*)scratch.get(8);
     }
@@ -1003,10 +1006,16 @@ mazu_status_t mazu_b200_query_reads_intervals_packed(const mazu_index_t* idx, co
     for (u64 r0 = 0; r0 < n_reads; r0 += rpc, b = (b + 1) % NB) {
       const u64 nr = std::min(rpc, n_reads - r0);
       cudaStream_t s = st.s[b];
-      MZ_CUDA(cudaMemcpyAsync(d_pw[b], packed_reads + r0 * wpr, nr * wpr * 8, cudaMemcpyHostToDevice, s));
-      if (n_mask) MZ_CUDA(cudaMemcpyAsync(d_pm[b], n_mask + r0 * mpr, nr * mpr * 8, cudaMemcpyHostToDevice, s));
-      launch_query_reads_runs(idx, nullptr, nullptr, nr, read_len, nullptr, d_counts, nullptr, nullptr, nullptr, max_slots, s, (const u64*)d_pw[b],
-                              (const u64*)d_pm[b], nullptr, (uint4*)d_iv[b], r0, d_cur[b]);
+      if (bases) {
+        MZ_CUDA(cudaMemcpyAsync(d_pw[b], bases + r0 * read_len, nr * read_len, cudaMemcpyHostToDevice, s));
+        launch_query_reads_runs(idx, (const u8*)d_pw[b], nullptr, nr, read_len, nullptr, d_counts, nullptr, nullptr, nullptr, max_slots, s, nullptr,
+                                nullptr, nullptr, (uint4*)d_iv[b], r0, d_cur[b]);
+      } else {
+        MZ_CUDA(cudaMemcpyAsync(d_pw[b], packed_reads + r0 * wpr, nr * wpr * 8, cudaMemcpyHostToDevice, s));
+        if (n_mask) MZ_CUDA(cudaMemcpyAsync(d_pm[b], n_mask + r0 * mpr, nr * mpr * 8, cudaMemcpyHostToDevice, s));
+        launch_query_reads_runs(idx, nullptr, nullptr, nr, read_len, nullptr, d_counts, nullptr, nullptr, nullptr, max_slots, s, (const u64*)d_pw[b],
+                                (const u64*)d_pm[b], nullptr, (uint4*)d_iv[b], r0, d_cur[b]);
+      }
       if (out_dev) {
         MZ_CUDA(cudaStreamWaitEvent(s, st.base_ev, 0));  // the running base: after the previous chunk has advanced it
         hit_run_publish_kernel<<<idx->sm_count * 2, 256, 0, s>>>(nullptr, 0, (const Hit*)d_iv[b], d_cur[b], d_base, cap, (Hit*)out_dev);
@@ -1037,8 +1046,27 @@ mazu_status_t mazu_b200_query_reads_intervals_packed(const mazu_index_t* idx, co
   return rc;
 }
 
-mazu_status_t mazu_b200_expand_hit_intervals(const mazu_index_t* idx, const mazu_hit_interval_t* intervals, uint64_t n_intervals,
-                                             const uint64_t* n_mask, uint64_t n_reads, uint64_t read_len, mazu_hit_t* out_hits) {
+mazu_status_t mazu_b200_query_reads_intervals_packed(const mazu_index_t* idx, const uint64_t* packed_reads, const uint64_t* n_mask,
+                                                     uint64_t n_reads, uint64_t read_len, int32_t mode, mazu_hit_interval_t* out_intervals,
+                                                     uint64_t cap, uint64_t* out_n, uint64_t* counts) {
+  if (n_reads && !packed_reads) {
+    g_err = "null argument";
+    return MAZU_ERR_INVALID_ARG;
+  }
+  return query_reads_intervals_impl(idx, nullptr, packed_reads, n_mask, n_reads, read_len, mode, out_intervals, cap, out_n, counts);
+}
+mazu_status_t mazu_b200_query_reads_intervals(const mazu_index_t* idx, const uint8_t* bases, uint64_t n_reads, uint64_t read_len, int32_t mode,
+                                              mazu_hit_interval_t* out_intervals, uint64_t cap, uint64_t* out_n, uint64_t* counts) {
+  if (n_reads && !bases) {
+    g_err = "null argument";
+    return MAZU_ERR_INVALID_ARG;
+  }
+  return query_reads_intervals_impl(idx, bases, nullptr, nullptr, n_reads, read_len, mode, out_intervals, cap, out_n, counts);
+}
+
+static mazu_status_t expand_hit_intervals_impl(const mazu_index_t* idx, const mazu_hit_interval_t* intervals, uint64_t n_intervals,
+                                               const uint64_t* n_mask, const uint8_t* bases, uint64_t n_reads, uint64_t read_len,
+                                               mazu_hit_t* out_hits) {
   return guarded([&] {
     if (!idx || (n_intervals && !intervals) || !read_len) throw Error(MAZU_ERR_INVALID_ARG, "null argument");
     const u32 k = idx->unitigs->k;
@@ -1050,13 +1078,14 @@ mazu_status_t mazu_b200_expand_hit_intervals(const mazu_index_t* idx, const mazu
     parallel_ranges(n_reads, T, [&](unsigned, u64 lo, u64 hi) {
       for (u64 r = lo; r < hi; ++r) {
         const u64* m = n_mask ? n_mask + r * mpr : nullptr;
+        const u8* bs = bases ? bases + r * read_len : nullptr;  // ASCII reads: a base is masked when it is not ACGTacgt
+        auto masked = [&](u64 j) { return bs ? base_code(bs[j]) > 3 : (m && ((m[j >> 6] >> (j & 63)) & 1ULL)); };
         long long last_bad = -1;  // most recent masked base at or before the window's last base
-        if (m)
-          for (u64 j = 0; j + 1 < k && j < read_len; ++j)
-            if ((m[j >> 6] >> (j & 63)) & 1ULL) last_bad = (long long)j;
+        for (u64 j = 0; j + 1 < k && j < read_len; ++j)
+          if (masked(j)) last_bad = (long long)j;
         for (u64 i = 0; i < slots; ++i) {
           const u64 j = i + k - 1;
-          if (m && ((m[j >> 6] >> (j & 63)) & 1ULL)) last_bad = (long long)j;
+          if (masked(j)) last_bad = (long long)j;
           out_hits[r * slots + i] = mazu_hit_t{~0u, ~0u, ~0u, last_bad >= (long long)i ? (u32)MAZU_SKIPPED : (u32)MAZU_NO_MATCH};
         }
       }
@@ -1077,6 +1106,18 @@ mazu_status_t mazu_b200_expand_hit_intervals(const mazu_index_t* idx, const mazu
     });
     if (bad) throw Error(MAZU_ERR_INVALID_DATA, "an interval record points outside the batch or the unitig set");
   });
+}
+mazu_status_t mazu_b200_expand_hit_intervals(const mazu_index_t* idx, const mazu_hit_interval_t* intervals, uint64_t n_intervals,
+                                             const uint64_t* n_mask, uint64_t n_reads, uint64_t read_len, mazu_hit_t* out_hits) {
+  return expand_hit_intervals_impl(idx, intervals, n_intervals, n_mask, nullptr, n_reads, read_len, out_hits);
+}
+mazu_status_t mazu_b200_expand_hit_intervals_ascii(const mazu_index_t* idx, const mazu_hit_interval_t* intervals, uint64_t n_intervals,
+                                                   const uint8_t* bases, uint64_t n_reads, uint64_t read_len, mazu_hit_t* out_hits) {
+  if (n_reads && !bases) {
+    g_err = "null argument";
+    return MAZU_ERR_INVALID_ARG;
+  }
+  return expand_hit_intervals_impl(idx, intervals, n_intervals, nullptr, bases, n_reads, read_len, out_hits);
 }
 
 mazu_status_t mazu_b200_pack_reads(const uint8_t* bases, uint64_t n_reads, uint64_t read_len, uint64_t* out_words, uint64_t* out_n_mask,

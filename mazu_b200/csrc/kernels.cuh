@@ -1310,9 +1310,9 @@ struct RunsTileOut {
 };
 
 // IO: 0 = ASCII reads in, one code byte per slot out; 1 = 2-bit packed reads in, 2-bit codes out; 2 = packed reads in, interval
-// records out.  One instantiation per mode: with all three in one body the kernel grew to 4,000 SASS instructions and every
-// mode lost 20 % to instruction fetch (profiles/experiments/README.md).
-enum { RUNS_IO_ASCII = 0, RUNS_IO_PACKED = 1, RUNS_IO_INTERVALS = 2 };
+// records out; 3 = ASCII reads in, interval records out.  One instantiation per mode: with all of them in one body the kernel
+// grew to 4,000 SASS instructions and every mode lost 20 % to instruction fetch (profiles/experiments/README.md).
+enum { RUNS_IO_ASCII = 0, RUNS_IO_PACKED = 1, RUNS_IO_INTERVALS = 2, RUNS_IO_INTERVALS_ASCII = 3 };
 template <int KIND, u32 FAMILY, int IO>
 __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
                                                                            const u64* __restrict__ read_offsets, u64 n_reads, u64 uniform_len,
@@ -1342,7 +1342,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(cons
     u32 code[4], n_runs = 0;
     if (n_c) {
       ChunkInfo ci;
-      if (IO != RUNS_IO_ASCII)  // uniform reads, 2-bit packed
+      if (IO == RUNS_IO_PACKED || IO == RUNS_IO_INTERVALS)  // uniform reads, 2-bit packed
         stage_encode_packed(packed_words + r * ((len + 31) / 32), packed_nmask ? packed_nmask + r * ((len + 63) / 64) : nullptr, (u32)len, n_c, k, lane, S, ci);
       else
         stage_encode(bases + beg, len, 0, n_c, k, lane, S, ci);
@@ -1389,9 +1389,9 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(cons
     unsigned long long E = 0;
     if (lane == 0) {
       E = n_runs ? atomicAdd(ro.cursor, (unsigned long long)n_runs) : 0ULL;
-      if (IO != RUNS_IO_INTERVALS) ro.read_run_offsets[r] = E;
+      if (IO < RUNS_IO_INTERVALS) ro.read_run_offsets[r] = E;
     }
-    if (IO == RUNS_IO_INTERVALS) {
+    if (IO >= RUNS_IO_INTERVALS) {
       if (n_runs) {  // (warp-uniform)
         // a run = its start slot + the CONT slots that follow it: 128 continuation flags as two 64-bit words, inverted so the
         // run's end is a find-first-set

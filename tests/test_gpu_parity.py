@@ -1203,9 +1203,12 @@ def test_hit_intervals_expand_to_the_exact_records(yeast_sshash, yeast_dense, ye
 
     _, ref_codes = yeast_queries
     os.environ["MAZU_B200_CHUNK_MIB"] = "1"
+    recs = lambda a: sorted(a.tobytes()[16 * i:16 * i + 16] for i in range(len(a)))  # the order of the records is unspecified
     try:
         for rl, n_reads in ((150, 9000), (158, 3000), (100, 1500), (47, 1200), (31, 500)):
             bases, offs = _gen.sample_reads(ref_codes, n_reads, rl, seed=90 + rl, frac_ref=0.75, sub_rate=0.01, n_rate=0.003)
+            bases = bases.copy()
+            bases[::7] |= 0x20  # lower case is the same base (src/pf1/dense_index.rs:180-183)
             words, mask, _ = mz.pack_reads(bases, rl)
             for g, o in (yeast_sshash, yeast_dense):
                 want, wcnt, _ = o.query_reads(bases, offs)
@@ -1213,6 +1216,10 @@ def test_hit_intervals_expand_to_the_exact_records(yeast_sshash, yeast_dense, ye
                     iv, cnt = g.query_reads_intervals_packed(words, mask, n_reads, rl, mode=mode)
                     assert_hits_equal(g.expand_hit_intervals(iv, mask, n_reads, rl), want, "intervals, read length %d mode %d" % (rl, mode))
                     assert list(cnt) == list(wcnt)
+                    # the same records from the ASCII reads as the reference takes them (lower case, N and all): no packing by the caller
+                    iva, cnta = g.query_reads_intervals(bases, n_reads, rl, mode=mode)
+                    assert list(cnta) == list(wcnt) and recs(iva) == recs(iv)
+                    assert_hits_equal(g.expand_hit_intervals_ascii(iva, bases, n_reads, rl), want, "ASCII intervals, read length %d mode %d" % (rl, mode))
                     # maximal runs: one record per run start of the run format
                     slots = rl - g.k + 1
                     hit = (want["match"] == 1) | (want["match"] == 2)
@@ -1221,8 +1228,10 @@ def test_hit_intervals_expand_to_the_exact_records(yeast_sshash, yeast_dense, ye
         g, o = yeast_sshash
         pin = mz.PinnedArray((len(iv) + 8,), mz.INTERVAL_DTYPE)
         iv2, _ = g.query_reads_intervals_packed(words, mask, n_reads, rl, intervals=pin.array)
-        recs = lambda a: sorted(a.tobytes()[16 * i:16 * i + 16] for i in range(len(a)))  # the order of the records is unspecified
         assert len(iv2) == len(iv) and recs(iv2) == recs(iv)
+        pin.array[:] = 0
+        iv3, _ = g.query_reads_intervals(bases, n_reads, rl, intervals=pin.array)
+        assert len(iv3) == len(iv) and recs(iv3) == recs(iv)
         # too small a buffer: the call says how many records it needs and never writes past the capacity
         small = np.zeros(4, dtype=mz.INTERVAL_DTYPE)
         guard = small.copy()
