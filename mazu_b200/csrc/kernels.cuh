@@ -1221,7 +1221,10 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 4) get_ref_pos_pass1_kernel(con
 }
 
 // pass 2: tile_base = exclusive scan of tile_totals (n_tiles + 1 entries, the last one the total)
-__global__ void __launch_bounds__(256) get_ref_pos_pass2_kernel(const __grid_constant__ IndexView ix, const TileMap tm, const Hit* __restrict__ hits,
+#ifndef MAZU_P2_OCC
+#define MAZU_P2_OCC 4  // resident CTAs the tile-wise emit is compiled for (64 registers, no spills): 1 / 4 / 5 / 6 / 8 measured, profiles/experiments/README.md
+#endif
+__global__ void __launch_bounds__(256, MAZU_P2_OCC) get_ref_pos_pass2_kernel(const __grid_constant__ IndexView ix, const TileMap tm, const Hit* __restrict__ hits,
                                                                 const u64* __restrict__ tile_base, u64 n_slots, u64* __restrict__ out_offsets,
                                                                 OccRec* __restrict__ out, u64 cap, u64* __restrict__ out_total) {
   const u32 lane = threadIdx.x & 31;
@@ -1236,22 +1239,38 @@ __global__ void __launch_bounds__(256) get_ref_pos_pass2_kernel(const __grid_con
     u32 n_c;
     tile_locate(tm, k, tile, beg, len, slot0, c0, n_c);
     u64 o = tile_base[tile];
-#pragma unroll 1
-    for (u32 p0 = 0; p0 < n_c; p0 += 32) {
-      const u32 p = p0 + lane;
-      const bool mine = p < n_c;
-      Hit h = hit_none(NO_MATCH);
-      u64 first = 0;
-      u32 cnt = 0;
-      if (mine) {
+    // the tile's four groups of 32 slots: every group's loads (hit record -> list bounds) are issued before any group is
+    // scanned or written, so a warp has four independent dependent-load chains in flight instead of one
+    Hit hs[4];
+    u64 firsts[4];
+    u32 cnts[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const u32 p = 32u * t + lane;
+      hs[t] = hit_none(NO_MATCH);
+      if (p < n_c) {
         const uint4 q = __ldg(reinterpret_cast<const uint4*>(hits + slot0 + c0 + p));
-        h = Hit{q.x, q.y, q.z, q.w};
-        if (h.match == IDENTITY_MATCH || h.match == TWIN_MATCH) {
-          u64 e;
-          occ_range(ix, h.unitig_id, first, e);
-          cnt = (u32)(e - first);
-        }
+        hs[t] = Hit{q.x, q.y, q.z, q.w};
       }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      firsts[t] = 0;
+      cnts[t] = 0;
+      if (32u * t + lane < n_c && (hs[t].match == IDENTITY_MATCH || hs[t].match == TWIN_MATCH)) {
+        u64 e;
+        occ_range(ix, hs[t].unitig_id, firsts[t], e);
+        cnts[t] = (u32)(e - firsts[t]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const u32 p = 32u * t + lane;
+      if (32u * t >= n_c) break;  // (warp-uniform)
+      const bool mine = p < n_c;
+      const Hit h = hs[t];
+      const u64 first = firsts[t];
+      const u32 cnt = cnts[t];
       u32 inc = cnt;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
