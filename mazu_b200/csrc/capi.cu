@@ -1529,7 +1529,26 @@ static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu
     d_offs = scratch->get((n + 1) * 8);
     d_offsets = (u64*)d_offs;
   }
-  {
+  // the staged kernel pays off when tiles lie inside long lists (config 4: 92 % vs 85 % of the copy peak); with short lists
+  // (a read batch's hits: ~1 occurrence each) every tile takes the generic path and the plain kernel's larger grid is 17 % faster
+  const bool long_lists = idx->view.n_occs >= 64 * std::max<u64>(1, idx->unitigs->n_unitigs());
+  // hit batches with short lists go by TILES of QR_CHUNK records (project_tile_totals_kernel -> scan over tiles ->
+  // get_ref_pos_pass2_kernel, which writes offsets and records): 1/128 of the scan, no search, no list-length array
+  const bool by_tiles = project && n > 0 && !long_lists;
+  const u64 n_tiles = by_tiles ? (n + QR_CHUNK - 1) / QR_CHUNK : 0;
+  std::unique_ptr<PoolBuf> tile_base;
+  TileMap tm{nullptr, nullptr, nullptr, 0, 0, n_tiles, n};
+  const int grid_tiles = (int)std::max<u64>(1, std::min<u64>((n_tiles + 7) / 8, (u64)idx->sm_count * 8));
+  const u64* d_total_src = d_offsets + n;
+  if (by_tiles) {
+    PoolBuf totals(idx->pool, (n_tiles + 1) * 8, s);
+    tile_base = std::make_unique<PoolBuf>(idx->pool, (n_tiles + 1) * 8, s);
+    MZ_CUDA(cudaMemsetAsync((u64*)totals.p + n_tiles, 0, 8, s));
+    project_tile_totals_kernel<<<grid_tiles, 256, 0, s>>>(idx->view, d_hits, n, n_tiles, (u64*)totals.p);
+    MZ_CUDA(cudaGetLastError());
+    device_exclusive_scan((const u64*)totals.p, (u64*)tile_base->p, n_tiles, idx->pool, s);
+    d_total_src = (const u64*)tile_base->p + n_tiles;
+  } else {
     PoolBuf lens(idx->pool, (n + 1) * 8, s);
     MZ_CUDA(cudaMemsetAsync(lens.p, 0, (n + 1) * 8, s));
     if (n) {
@@ -1541,14 +1560,21 @@ static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu
   u64 total = 0;
   bool need_total = mem == MAZU_MEM_HOST || out_total != nullptr;
   if (need_total) {
-    MZ_CUDA(cudaMemcpyAsync(&total, d_offsets + n, 8, cudaMemcpyDeviceToHost, s));
+    MZ_CUDA(cudaMemcpyAsync(&total, d_total_src, 8, cudaMemcpyDeviceToHost, s));
     MZ_CUDA(cudaStreamSynchronize(s));
     if (out_total) *out_total = total;
   }
-  if (mem == MAZU_MEM_HOST) MZ_CUDA(cudaMemcpyAsync(out_offsets, d_offsets, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
-  if (!out) {
-    if (mem == MAZU_MEM_HOST) MZ_CUDA(cudaStreamSynchronize(s));
-    return;
+  if (mem == MAZU_MEM_HOST && !by_tiles) MZ_CUDA(cudaMemcpyAsync(out_offsets, d_offsets, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+  if (!out || (need_total && total > cap)) {
+    if (by_tiles) {  // the offsets come out of the emit pass: run it without records
+      get_ref_pos_pass2_kernel<<<grid_tiles, 256, 0, s>>>(idx->view, tm, d_hits, (const u64*)tile_base->p, n, d_offsets, nullptr, 0, nullptr);
+      MZ_CUDA(cudaGetLastError());
+      if (mem == MAZU_MEM_HOST) MZ_CUDA(cudaMemcpyAsync(out_offsets, d_offsets, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    }
+    if (!out) {
+      if (mem == MAZU_MEM_HOST) MZ_CUDA(cudaStreamSynchronize(s));
+      return;
+    }
   }
   if (need_total && total > cap) {
     if (mem == MAZU_MEM_HOST) MZ_CUDA(cudaStreamSynchronize(s));
@@ -1569,10 +1595,10 @@ static void occ_driver(const mazu_index_t* idx, const uint32_t* uids, const mazu
       const char* e = getenv("MAZU_B200_OCC_TMA");
       return e ? atoi(e) != 0 : true;
     }();
-    // the staged kernel pays off when tiles lie inside long lists (config 4: 92 % vs 85 % of the copy peak); with short lists
-    // (a read batch's hits: ~1 occurrence each) every tile takes the generic path and the plain kernel's larger grid is 17 % faster
-    const bool long_lists = idx->view.n_occs >= 64 * std::max<u64>(1, idx->unitigs->n_unitigs());
-    if (use_tma && long_lists) {  // bulk-copy staged fill: one CTA of 24 warps per SM, 174 KB of dynamic shared memory
+    if (by_tiles) {
+      get_ref_pos_pass2_kernel<<<grid_tiles, 256, 0, s>>>(idx->view, tm, d_hits, (const u64*)tile_base->p, n, d_offsets, d_o, fill_cap, nullptr);
+      if (mem == MAZU_MEM_HOST) MZ_CUDA(cudaMemcpyAsync(out_offsets, d_offsets, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    } else if (use_tma && long_lists) {  // bulk-copy staged fill: one CTA of 24 warps per SM, 174 KB of dynamic shared memory
       std::call_once(idx->occ_attr_once, [] {
         cudaFuncSetAttribute(occ_fill_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OCC_TMA_SMEM);
         cudaFuncSetAttribute(occ_fill_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OCC_TMA_SMEM);
@@ -1612,7 +1638,7 @@ static void launch_get_ref_pos_reads(const mazu_index_t* idx, const u8* d_bases,
   }
   PoolBuf totals(idx->pool, (n_tiles + 1) * 8, s), base(idx->pool, (n_tiles + 1) * 8, s);
   MZ_CUDA(cudaMemsetAsync((u64*)totals.p + n_tiles, 0, 8, s));
-  TileMap tm{d_read_offsets, d_kmer_offsets, tt.seg ? (const u64*)tt.seg->p : nullptr, n_reads, uniform_len, n_tiles};
+  TileMap tm{d_read_offsets, d_kmer_offsets, tt.seg ? (const u64*)tt.seg->p : nullptr, n_reads, uniform_len, n_tiles, 0};
   const bool ss = idx->view.k2u_kind == MAZU_K2U_SSHASH, boophf = idx->view.mphf.family == MPHF_FAMILY_BOOPHF;
 #define MZ_GRP(K, F)                                                                                                     \
   {                                                                                                                       \

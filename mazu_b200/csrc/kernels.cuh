@@ -1134,9 +1134,16 @@ struct TileMap {  // tile -> (read, first k-mer position): arithmetic for unifor
   const u64* kmer_offsets;
   const u64* seg_offsets;
   u64 n_reads, uniform_len, n_tiles;
+  u64 flat_n;  // != 0: no reads at all, the tiles cut a flat array of flat_n hit records (mazu_b200_project_hits)
 };
 __device__ __forceinline__ void tile_locate(const TileMap& tm, u32 k, u64 tile, u64& beg, u64& len, u64& slot0, u64& c0, u32& n_c) {
   u64 r;
+  if (tm.flat_n) {
+    beg = len = c0 = 0;
+    slot0 = tile * QR_CHUNK;
+    n_c = slot0 < tm.flat_n ? (u32)min((u64)QR_CHUNK, tm.flat_n - slot0) : 0u;
+    return;
+  }
   if (tm.uniform_len) {
     const u64 nk = tm.uniform_len >= k ? tm.uniform_len - k + 1 : 0;
     const u64 cpr = nk <= (u64)QR_CHUNK ? 1 : (nk + QR_CHUNK - 1) / QR_CHUNK;
@@ -1220,6 +1227,39 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 4) get_ref_pos_pass1_kernel(con
   }
 }
 
+// project_hits over a flat array of hit records, short lists (GetRefPos::project_hits, src/index.rs:174-216): the same two passes
+// without the lookups -- this kernel sums the list lengths of every tile of QR_CHUNK records, the scan runs over tiles, pass 2
+// below emits.  Replaces occ_lens_kernel -> per-record scan -> occ_fill_kernel (search per output tile) for hit batches.
+__global__ void __launch_bounds__(256) project_tile_totals_kernel(const __grid_constant__ IndexView ix, const Hit* __restrict__ hits, u64 n,
+                                                                  u64 n_tiles, u64* __restrict__ tile_totals) {
+  const u32 lane = threadIdx.x & 31;
+  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  for (u64 tile = warp; tile < n_tiles; tile += n_warps) {
+    const u64 slot0 = tile * QR_CHUNK;
+    Hit hs[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const u64 i = slot0 + 32u * t + lane;
+      hs[t] = hit_none(NO_MATCH);
+      if (i < n) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(hits + i));
+        hs[t] = Hit{q.x, q.y, q.z, q.w};
+      }
+    }
+    u32 total = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if ((hs[t].match == IDENTITY_MATCH || hs[t].match == TWIN_MATCH) && (u64)hs[t].unitig_id < ix.unitigs.n_unitigs) {  // ids outside the table: empty lists
+        u64 a, e;
+        occ_range(ix, hs[t].unitig_id, a, e);
+        total += (u32)(e - a);
+      }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+    if (lane == 0) tile_totals[tile] = total;
+  }
+}
+
 // pass 2: tile_base = exclusive scan of tile_totals (n_tiles + 1 entries, the last one the total)
 #ifndef MAZU_P2_OCC
 #define MAZU_P2_OCC 4  // resident CTAs the tile-wise emit is compiled for (64 registers, no spills): 1 / 4 / 5 / 6 / 8 measured, profiles/experiments/README.md
@@ -1257,7 +1297,7 @@ __global__ void __launch_bounds__(256, MAZU_P2_OCC) get_ref_pos_pass2_kernel(con
     for (int t = 0; t < 4; ++t) {
       firsts[t] = 0;
       cnts[t] = 0;
-      if (32u * t + lane < n_c && (hs[t].match == IDENTITY_MATCH || hs[t].match == TWIN_MATCH)) {
+      if (32u * t + lane < n_c && (hs[t].match == IDENTITY_MATCH || hs[t].match == TWIN_MATCH) && (u64)hs[t].unitig_id < ix.unitigs.n_unitigs) {
         u64 e;
         occ_range(ix, hs[t].unitig_id, firsts[t], e);
         cnts[t] = (u32)(e - firsts[t]);
@@ -1280,8 +1320,8 @@ __global__ void __launch_bounds__(256, MAZU_P2_OCC) get_ref_pos_pass2_kernel(con
       const u64 o0 = o + inc - cnt;
       if (mine) out_offsets[slot0 + c0 + p] = o0;
       // short lists are written by their lane, long ones by the whole warp (project_onto_u_occ, index.rs:194-216)
-      u32 big = __ballot_sync(0xffffffffu, cnt >= 32u);
-      if (cnt < 32u)
+      u32 big = out ? __ballot_sync(0xffffffffu, cnt >= 32u) : 0u;  // out == nullptr: offsets only (a sizing call)
+      if (out && cnt < 32u)
         for (u32 j = 0; j < cnt; ++j)
           if (o0 + j < cap) out[o0 + j] = project_occ(k, h, occ_decode(ix, first + j));
       while (big) {
