@@ -335,7 +335,12 @@ def measured_traffic(W, mode_name, scale):
     label = "ncu --set full (%s): %d units per captured launch, index scale %s, %s%s" % (
         name, e.get("lookups_per_launch", 0), e.get("scale", "n/a"), e.get("_source", ""),
         "" if d[0] == 0 else "; captured in %s mode, used as the estimate for %s mode" % (e.get("mode", "random"), mode_name))
+    global _TRAFFIC_ENTRY
+    _TRAFFIC_ENTRY = e if d[0] == 0 else None
     return per, label
+
+
+_TRAFFIC_ENTRY = None  # the traffic.json entry measured_traffic() settled on (same workload and mode), for the issue-side figures
 
 
 def main():
@@ -1041,6 +1046,12 @@ def main():
                 "survey_8d": {"bytes_per_unit": alg, "gbs": alg_gbs, "ratio_to_hbm_peak": alg_gbs / hbm_peak, "ratio_to_p_rand": alg_gbs / peak,
                               "note": "ideal-layout figure with nothing shared between the k-mers of a read: a label, not a DRAM measurement"}}
     roof.update({"traffic_source": traffic_label, "units_per_launch": n_units, "kernel_ms": kernel_ms, "step_ms": [round(x, 3) for x in step_ms]})
+    if _TRAFFIC_ENTRY and _TRAFFIC_ENTRY.get("ipc"):
+        # what actually bounds the lookup kernels once the DRAM traffic is this low: instruction issue (from the same ncu capture)
+        te = _TRAFFIC_ENTRY
+        roof["issue"] = {"ipc": te["ipc"], "peak_ipc": 4.0, "frac": te["ipc"] / 4.0, "issue_active_pct": te.get("issue_active_pct"),
+                         "warp_instructions_per_unit": te.get("warp_inst_per_lookup"), "threads_per_instruction": te.get("threads_per_inst"),
+                         "source": "same ncu capture as `traffic` (sm__inst_executed.avg.per_cycle_elapsed, smsp__issue_active)"}
 
     cfg = bench_config(args)
     line = {

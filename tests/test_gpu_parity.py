@@ -749,6 +749,42 @@ def test_decode_device_mode_undersized_buffer_is_never_overrun(kind):
         tot = C.c_uint64(0)
         rc = mz.lib().mazu_b200_decode_occs(g._h, mz._any_ptr(d_q), len(q), mz._any_ptr(d_offs), mz._any_ptr(d_out), total - 1, C.byref(tot), mz.MEM_DEVICE, None)
         assert rc == -7 and tot.value == total
+        # mazu_b200_project_hits on a hit batch: short lists go by tiles of 128 records (tile totals -> scan over tiles -> emit),
+        # long ones through the staged kernel.  Same contract: device buffers without out_total are clipped at cap, a sizing call
+        # (out == NULL) fills the offsets, unitig ids outside the table and misses are empty lists, any batch length.
+        rng = np.random.default_rng(11)
+        for nh in (4000, 129, 128, 1):
+            hits = np.zeros(nh, dtype=mz.HIT_DTYPE)
+            hits["unitig_id"] = q[:nh]
+            ulen = (accum[1:] - accum[:-1]).astype(np.uint32)
+            inside = q[:nh] < U
+            hits["unitig_len"] = np.where(inside, ulen[np.where(inside, q[:nh], 0)], 0)
+            hits["pos"] = (rng.integers(0, 1 << 30, nh) % np.maximum(hits["unitig_len"].astype(np.int64) - k + 1, 1)).astype(np.uint32)
+            hits["match"] = rng.integers(0, 4, nh).astype(np.uint32)  # NoMatch / Identity / Twin / skipped
+            hits["match"][q[:nh] == mz.MISS] = 0
+            ohits = hits.copy()
+            ohits["match"][~inside] = 0  # the oracle is not asked about ids it would reject
+            pw_offs, pw = o.project_hits(ohits)
+            ptotal = int(pw_offs[-1])
+            d_h = torch.from_numpy(hits.view(np.int32).reshape(-1, 4)).cuda()
+            d_po = torch.zeros(nh + 1, dtype=torch.int64, device="cuda")
+            tot = C.c_uint64(0)
+            mz._check(mz.lib().mazu_b200_project_hits(g._h, mz._any_ptr(d_h), nh, mz._any_ptr(d_po), None, 0, C.byref(tot), mz.MEM_DEVICE, None))
+            assert tot.value == ptotal and np.array_equal(d_po.cpu().numpy().view(np.uint64), pw_offs)
+            for cap in (ptotal, ptotal // 2 + 1, 0):
+                d_po.zero_()
+                d_pout = torch.full(((cap + 4096), 3), -1, dtype=torch.int32, device="cuda")
+                mz._check(mz.lib().mazu_b200_project_hits(g._h, mz._any_ptr(d_h), nh, mz._any_ptr(d_po), mz._any_ptr(d_pout), cap, None, mz.MEM_DEVICE, None))
+                torch.cuda.synchronize()
+                got = d_pout.cpu().numpy().view(np.uint32)
+                assert np.array_equal(d_po.cpu().numpy().view(np.uint64), pw_offs)
+                nw = min(cap, ptotal)
+                assert (got[nw:] == 0xFFFFFFFF).all(), "projected records written beyond the capacity (cap %d of %d)" % (cap, ptotal)
+                assert np.array_equal(got[:nw].reshape(-1).view(mz.OCC_DTYPE), pw[:nw])
+            if ptotal > 1:
+                rc = mz.lib().mazu_b200_project_hits(g._h, mz._any_ptr(d_h), nh, mz._any_ptr(d_po), mz._any_ptr(d_pout), ptotal - 1, C.byref(tot), mz.MEM_DEVICE, None)
+                assert rc == -7 and tot.value == ptotal
+            assert np.array_equal(g.project_hits(hits)[1], pw)  # host buffers
 
 
 def test_fuzz_decode_tables():
