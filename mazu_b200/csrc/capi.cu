@@ -118,24 +118,42 @@ struct PoolBuf {
 #define MAZU_QR_RANDOM_OCC 4
 #endif
 
-template <int MODE, int KIND, u32 FAMILY, int OCC>
+// (k, w) pairs the SSHash read kernels are ALSO compiled for with k and w folded into the code (kernels.cuh, KW): the pairs of
+// the named configurations (k31/w19: human-scale index, `index build --skew 64`; k31/w15: the yeast SSHash fixtures).  Any other
+// pair, and every PFHash index, runs the instantiation that reads k and w from the view.  MAZU_B200_GENERIC_KW=1 forces that
+// instantiation (A/B; test_read_kernels_kw_specialisations runs both).
+static u32 kw_code(const mazu_index* ix) {
+  const char* e = getenv("MAZU_B200_GENERIC_KW");  // read per call: the parity test flips it inside one process
+  const bool generic = e && *e && *e != '0';
+  if (generic || ix->view.k2u_kind != MAZU_K2U_SSHASH || ix->view.unitigs.k != 31) return 0;
+  return ix->view.w == 19 ? MZ_KW(31, 19) : ix->view.w == 15 ? MZ_KW(31, 15) : 0;
+}
+// MZ_KW_DISPATCH(code, CALL): CALL(KW) with KW a constant expression
+#define MZ_KW_DISPATCH(code, CALL)            \
+  switch (code) {                             \
+    case MZ_KW(31, 19): CALL(MZ_KW(31, 19)); break; \
+    case MZ_KW(31, 15): CALL(MZ_KW(31, 15)); break; \
+    default: CALL(0); break;                  \
+  }
+
+template <int MODE, int KIND, u32 FAMILY, int OCC, u32 KW>
 void launch_qr_occ(const mazu_index* ix, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, const u64* d_kmer_offsets,
                    void* d_out, u32 compact, u64* d_counts, const u64* d_seg_offsets, cudaStream_t s) {
-  auto kern = query_reads_kernel<MODE, KIND, FAMILY, OCC>;
+  auto kern = query_reads_kernel<MODE, KIND, FAMILY, OCC, KW>;
   // with a segment table the number of work items is only known on the device: launch every resident CTA, idle warps leave at once
   int grid = grid_for(kern, QR_WARPS * 32, ix, QR_WARPS, d_seg_offsets ? ~0ULL >> 8 : n_reads);
   kern<<<grid, QR_WARPS * 32, 0, s>>>(ix->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact,
                                       (unsigned long long*)d_counts, d_seg_offsets);
 }
-template <int MODE, int KIND, u32 FAMILY>
+template <int MODE, int KIND, u32 FAMILY, u32 KW = 0>
 void launch_qr(const mazu_index* ix, const u8* d_bases, const u64* d_read_offsets, u64 n_reads, u64 uniform_len, const u64* d_kmer_offsets,
                void* d_out, u32 compact, u64* d_counts, cudaStream_t s) {
   // streaming walk: 3 resident CTAs (80 registers) while the index sits in the 126 MB L2, 4 (64 registers) once it does not
   if constexpr (MODE == 1) {
     if (ix->device_bytes() <= (96ull << 20))
-      launch_qr_occ<MODE, KIND, FAMILY, 3>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, nullptr, s);
+      launch_qr_occ<MODE, KIND, FAMILY, 3, KW>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, nullptr, s);
     else
-      launch_qr_occ<MODE, KIND, FAMILY, 4>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, nullptr, s);
+      launch_qr_occ<MODE, KIND, FAMILY, 4, KW>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, nullptr, s);
   } else {
     // ragged batches: per-read work-item counts -> scan; the kernel cuts long reads into segments (kernels.cuh, QR_SEGMENT)
     std::unique_ptr<PoolBuf> cnt, seg;
@@ -147,7 +165,7 @@ void launch_qr(const mazu_index* ix, const u8* d_bases, const u64* d_read_offset
       MZ_CUDA(cudaGetLastError());
       device_exclusive_scan((const u64*)cnt->p, (u64*)seg->p, n_reads, ix->pool, s);
     }
-    launch_qr_occ<MODE, KIND, FAMILY, MAZU_QR_RANDOM_OCC>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts,
+    launch_qr_occ<MODE, KIND, FAMILY, MAZU_QR_RANDOM_OCC, KW>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts,
                                                           seg ? (const u64*)seg->p : nullptr, s);
   }
 }
@@ -162,7 +180,11 @@ void launch_query_reads(const mazu_index* ix, const u8* d_bases, const u64* d_re
 #define MZ_QR(M, K, F) launch_qr<M, K, F>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, s)
   if (ss) {
     if (!native) throw Error(MAZU_ERR_OTHER, "internal: SSHash index without a native MPHF");
-    if (st) MZ_QR(1, MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE); else MZ_QR(0, MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE);
+#define MZ_QR_SS(KW)                                                                                                               \
+  if (st) launch_qr<1, MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE, KW>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, s); \
+  else launch_qr<0, MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE, KW>(ix, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets, d_out, compact, d_counts, s)
+    MZ_KW_DISPATCH(kw_code(ix), MZ_QR_SS)
+#undef MZ_QR_SS
   } else if (ix->view.k2u_kind == MAZU_K2U_SAMPLED_PFHASH) {
     if (st) MZ_QR(1, MAZU_K2U_SAMPLED_PFHASH, MPHF_FAMILY_BOOPHF); else MZ_QR(0, MAZU_K2U_SAMPLED_PFHASH, MPHF_FAMILY_BOOPHF);
   } else if (native) {
@@ -222,20 +244,23 @@ void launch_query_reads_runs(const mazu_index* idx, const u8* d_bases, const u64
   const int io = d_intervals ? (d_packed_words ? RUNS_IO_INTERVALS : RUNS_IO_INTERVALS_ASCII)
                              : (d_packed_words && d_codes2 ? RUNS_IO_PACKED : RUNS_IO_ASCII);
   if (io == RUNS_IO_ASCII && (d_packed_words || d_codes2)) throw Error(MAZU_ERR_INVALID_ARG, "packed reads and 2-bit codes come together");
-#define MZ_QRR(K, F)                                                                                                          \
+#define MZ_QRR(K, F, KW)                                                                                                      \
   {                                                                                                                            \
-    auto kern = io == RUNS_IO_INTERVALS         ? query_reads_runs_kernel<K, F, RUNS_IO_INTERVALS>                             \
-                : io == RUNS_IO_INTERVALS_ASCII ? query_reads_runs_kernel<K, F, RUNS_IO_INTERVALS_ASCII>                       \
-                : io == RUNS_IO_PACKED          ? query_reads_runs_kernel<K, F, RUNS_IO_PACKED>                                \
-                                                : query_reads_runs_kernel<K, F, RUNS_IO_ASCII>;                                \
+    auto kern = io == RUNS_IO_INTERVALS         ? query_reads_runs_kernel<K, F, RUNS_IO_INTERVALS, KW>                         \
+                : io == RUNS_IO_INTERVALS_ASCII ? query_reads_runs_kernel<K, F, RUNS_IO_INTERVALS_ASCII, KW>                   \
+                : io == RUNS_IO_PACKED          ? query_reads_runs_kernel<K, F, RUNS_IO_PACKED, KW>                            \
+                                                : query_reads_runs_kernel<K, F, RUNS_IO_ASCII, KW>;                            \
     int grid = grid_for(kern, QR_WARPS * 32, idx, QR_WARPS, n_reads);                                                          \
     kern<<<grid, QR_WARPS * 32, 0, s>>>(idx->view, d_bases, d_read_offsets, n_reads, uniform_len, d_kmer_offsets,              \
                                         (unsigned long long*)d_counts, ro, d_packed_words, d_packed_nmask);                    \
   }
-  if (ss) MZ_QRR(MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE)
-  else if (idx->view.k2u_kind == MAZU_K2U_SAMPLED_PFHASH) MZ_QRR(MAZU_K2U_SAMPLED_PFHASH, MPHF_FAMILY_BOOPHF)
-  else if (boophf) MZ_QRR(MAZU_K2U_PFHASH, MPHF_FAMILY_BOOPHF)
-  else MZ_QRR(MAZU_K2U_PFHASH, MPHF_FAMILY_NATIVE)
+#define MZ_QRR_SS(KW) MZ_QRR(MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE, KW)
+  if (ss) {
+    MZ_KW_DISPATCH(kw_code(idx), MZ_QRR_SS)
+  } else if (idx->view.k2u_kind == MAZU_K2U_SAMPLED_PFHASH) MZ_QRR(MAZU_K2U_SAMPLED_PFHASH, MPHF_FAMILY_BOOPHF, 0)
+  else if (boophf) MZ_QRR(MAZU_K2U_PFHASH, MPHF_FAMILY_BOOPHF, 0)
+  else MZ_QRR(MAZU_K2U_PFHASH, MPHF_FAMILY_NATIVE, 0)
+#undef MZ_QRR_SS
 #undef MZ_QRR
   MZ_CUDA(cudaGetLastError());
 }
@@ -1640,16 +1665,19 @@ static void launch_get_ref_pos_reads(const mazu_index_t* idx, const u8* d_bases,
   MZ_CUDA(cudaMemsetAsync((u64*)totals.p + n_tiles, 0, 8, s));
   TileMap tm{d_read_offsets, d_kmer_offsets, tt.seg ? (const u64*)tt.seg->p : nullptr, n_reads, uniform_len, n_tiles, 0};
   const bool ss = idx->view.k2u_kind == MAZU_K2U_SSHASH, boophf = idx->view.mphf.family == MPHF_FAMILY_BOOPHF;
-#define MZ_GRP(K, F)                                                                                                     \
+#define MZ_GRP(K, F, KW)                                                                                                 \
   {                                                                                                                       \
-    auto kern = get_ref_pos_pass1_kernel<K, F>;                                                                           \
+    auto kern = get_ref_pos_pass1_kernel<K, F, KW>;                                                                       \
     int grid = grid_for(kern, QR_WARPS * 32, idx, QR_WARPS, n_tiles);                                                     \
     kern<<<grid, QR_WARPS * 32, 0, s>>>(idx->view, d_bases, tm, d_hits, (unsigned long long*)d_counts, (u64*)totals.p);   \
   }
-  if (ss) MZ_GRP(MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE)
-  else if (idx->view.k2u_kind == MAZU_K2U_SAMPLED_PFHASH) MZ_GRP(MAZU_K2U_SAMPLED_PFHASH, MPHF_FAMILY_BOOPHF)
-  else if (boophf) MZ_GRP(MAZU_K2U_PFHASH, MPHF_FAMILY_BOOPHF)
-  else MZ_GRP(MAZU_K2U_PFHASH, MPHF_FAMILY_NATIVE)
+#define MZ_GRP_SS(KW) MZ_GRP(MAZU_K2U_SSHASH, MPHF_FAMILY_NATIVE, KW)
+  if (ss) {
+    MZ_KW_DISPATCH(kw_code(idx), MZ_GRP_SS)
+  } else if (idx->view.k2u_kind == MAZU_K2U_SAMPLED_PFHASH) MZ_GRP(MAZU_K2U_SAMPLED_PFHASH, MPHF_FAMILY_BOOPHF, 0)
+  else if (boophf) MZ_GRP(MAZU_K2U_PFHASH, MPHF_FAMILY_BOOPHF, 0)
+  else MZ_GRP(MAZU_K2U_PFHASH, MPHF_FAMILY_NATIVE, 0)
+#undef MZ_GRP_SS
 #undef MZ_GRP
   MZ_CUDA(cudaGetLastError());
   device_exclusive_scan((const u64*)totals.p, (u64*)base.p, n_tiles, idx->pool, s);

@@ -509,6 +509,12 @@ struct UnitigsView {
   u32 k;
   u32 dir_shift;
 };
+// Compile-time (k, w) of a read-kernel instantiation: KW = MZ_KW(k, w), or 0 = take them from the view.  The read kernels are
+// issue-bound and k, w feed every mask, shift and window bound of stages M, B and V; with the two (k, w) pairs the named
+// configurations use folded into the code the SSHash read kernel issues 11 % fewer instructions per lookup (profiles/experiments).
+#define MZ_KW(k, w) (((u32)(k) << 8) | (u32)(w))
+template <u32 KW> MZ_HD u32 kw_k(u32 runtime_k) { return KW ? (KW >> 8) : runtime_k; }
+template <u32 KW> MZ_HD u32 kw_w(u32 runtime_w) { return KW ? (KW & 255u) : runtime_w; }
 // SeqVector::get_kmer_u64(pos, k): 2k bits at bit 2*pos (unitig_set.rs:226-229)
 MZ_HD u64 useq_window(const UnitigsView& u, u64 pos) {
   u64 bit = 2 * pos, wi = bit >> 6;
@@ -532,12 +538,14 @@ MZ_HD void unitig_locate(const UnitigsView& u, u64 pos, u64& id, u64& start, u64
 
 #if defined(__CUDA_ARCH__) || defined(__CUDACC__)
 // the same two primitives over unitig lines (query kernels): one DRAM line per verified candidate
+template <u32 KW = 0>
 __device__ __forceinline__ u64 line_window(const UnitigsView& u, u64 pos) {
+  const u32 k = kw_k<KW>(u.k);
   const u64* ln = reinterpret_cast<const u64*>(u.lines + (pos >> ULINE_SHIFT));
   const u32 off = (u32)pos & 255u, wi = off >> 5, sh = 2 * (off & 31u);
   u64 x = __ldg(ln + wi) >> sh;
-  if (sh + 2 * u.k > 64) x |= __ldg(ln + wi + 1) << (64 - sh);
-  return x & kmer_mask(u.k);
+  if (sh + 2 * k > 64) x |= __ldg(ln + wi + 1) << (64 - sh);
+  return x & kmer_mask(k);
 }
 static const u32 ULINE_DUP = 0x80000000u;
 __device__ __forceinline__ void line_locate(const UnitigsView& u, u64 pos, u64& id, u64& start, u64& end, u32* dup = nullptr) {

@@ -399,9 +399,9 @@ __device__ __forceinline__ u32 window_min(const u32* __restrict__ h, u32 span) {
 }
 
 // stage M + stage B (SSHash only)
-template <u32 FAMILY, bool WALK = false>  // WALK: the streaming walk also wants the DUP flags of the super-k-mer's lines
+template <u32 FAMILY, bool WALK = false, u32 KW = 0>  // WALK: the streaming walk also wants the DUP flags of the super-k-mer's lines
 __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkInfo& ci, u32 lane, WarpStage& S) {
-  const u32 k = ix.unitigs.k, w = ix.w, span = k - w;
+  const u32 k = kw_k<KW>(ix.unitigs.k), w = kw_w<KW>(ix.w), span = k - w;
   const u64 wmask = kmer_mask(w);
   __syncwarp();
   // reverse complement of every k-mer word of the chunk, once (stages M, B and V read it from here)
@@ -413,7 +413,14 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
   // positions beyond come from the tail of k-mer 127.  Its reverse complement is the low 2w bits of
   // rc(k-mer q - span) (the top w bases of that k-mer), so no w-mer is reverse-complemented on its own.
   // Only w-mers q <= 127 + span belong to a k-mer of the chunk; the keys beyond are never read.
-#pragma unroll 1
+  // random-access instantiations unroll this loop and the window loop below: +4 % on config 5, no spills at 64 registers
+  // (profiles/experiments, r03v); the streaming walk keeps them rolled (its 64-register build would spill)
+#ifdef MAZU_WALK_UNROLL
+  constexpr int UNROLL_KEYS = 5, UNROLL_MIN = 4;
+#else
+  constexpr int UNROLL_KEYS = WALK ? 1 : 5, UNROLL_MIN = WALK ? 1 : 4;
+#endif
+#pragma unroll UNROLL_KEYS
   for (int t = 0; t < 5; ++t) {
     u32 q = 32 * t + lane;
     u64 x;
@@ -433,7 +440,7 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
   u32 n_lead = 0;
   u64 carry_mm = 0;
   u32 carry_valid = 0, carry_leader = 0;
-#pragma unroll 1
+#pragma unroll UNROLL_MIN  // static t also keeps ChunkInfo in registers (the rolled loop indexes ci.vm[t] through local memory)
   for (int t = 0; t < 4; ++t) {
     const u32 p = 32 * t + lane;
     const u32 vmask = ci.vm[t];
@@ -514,26 +521,26 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
 }
 
 // stage V for one k-mer of an SSHash index: the loop of sshash.rs:494-552 / k2u_skew_index
-template <u32 FAMILY>
+template <u32 FAMILY, u32 KW = 0>
 __device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpStage& S, u32 p, u64 fw, u64 rc, Hit& out, u64* ustart = nullptr,
                                               u32* dup = nullptr) {
   const u32 lp = S.leader[p];
   const u32 n = S.bn[lp];
   if (n == 0) return false;
-  const u32 k = ix.unitigs.k;
+  const u32 k = kw_k<KW>(ix.unitigs.k);
   if (n == BN_SKEW) {
     if (!ix.has_skew) return false;
     u64 word = fw <= rc ? fw : rc, hs;
     if (!mphf_lookup_t<FAMILY>(ix.skew_mphf, word, hs)) return false;
     if (hs >= ix.skew_pos.len) return false;
     u64 pos = packed_get(ix.skew_pos, hs);
-    u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, pos));
+    u32 mt = word_equivalency(fw, rc, line_window<KW>(ix.unitigs, pos));
     if (mt == NO_MATCH) return false;
     return finish_hit(ix.unitigs, pos, mt, false, out, ustart, dup);
   }
   const u64 pos_start = S.bstart[lp];
   const u32 offset = S.off[p];
-  const u32 rc_offset = (k - ix.w) - offset;
+  const u32 rc_offset = (k - kw_w<KW>(ix.w)) - offset;
   const u64 last_km_start_pos = ix.unitigs.total_len - k;
   const u32 loc = S.lrank[lp];
 #pragma unroll 1
@@ -546,7 +553,7 @@ __device__ __forceinline__ bool verify_sshash(const IndexView& ix, const WarpSta
       if (c == 1 && rc_offset == offset) break;
       if (mm_pos >= o && mm_pos - o <= last_km_start_pos) {
         const u64 km_pos = mm_pos - o;
-        const u32 mt = word_equivalency(fw, rc, line_window(ix.unitigs, km_pos));
+        const u32 mt = word_equivalency(fw, rc, line_window<KW>(ix.unitigs, km_pos));
         if (mt != NO_MATCH) {
           if (located) {  // unitig of the entry, from the leader: inside it <=> sdelta >= o; boundary guard <=> k - o <= edelta
             const u32 sd = S.sdelta[loc], edf = S.edelta[loc], ed = edf & 0x7FFFFFFFu;
@@ -649,7 +656,8 @@ struct StreamState {  // StreamingK2U { is_warm, prev_k2upos } (src/index/cachin
 // walk wants its 80 registers while the index is cache-resident (+3.5 % on the yeast configs) and the extra warps once
 // lookups wait on DRAM (+13 % on a 1.7 GB index); the launcher picks by index size.  Random-access mode passes 0 (no
 // minimum: ptxas settles on 64 registers by itself).
-template <int MODE, int KIND, u32 FAMILY, int OCC>
+// KW = MZ_KW(k, w) of the index folded into the code (SSHash instantiations for the named (k, w) pairs), 0 = read from the view.
+template <int MODE, int KIND, u32 FAMILY, int OCC, u32 KW = 0>
 __global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
                                                                     const u64* __restrict__ read_offsets, u64 n_reads, u64 uniform_len,
                                                                     const u64* __restrict__ kmer_offsets, void* __restrict__ out, u32 compact,
@@ -657,7 +665,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const _
   __shared__ WarpStage s_stage[QR_WARPS];
   const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   WarpStage& S = s_stage[wib];
-  const u32 k = ix.unitigs.k;
+  const u32 k = kw_k<KW>(ix.unitigs.k);
   constexpr bool SS = KIND == MAZU_K2U_SSHASH;
   u32 n_valid = 0, n_hit = 0;
   const u32 lt_mask = (1u << lane) - 1u;
@@ -714,13 +722,13 @@ __global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const _
       __syncwarp();
       char* o = out ? static_cast<char*>(out) + (slot0 + c0) * (compact ? 8ULL : 16ULL) : nullptr;
       if (MODE == 0) {
-        if (SS) stage_buckets<FAMILY>(ix, ci, lane, S);
-#pragma unroll 1
+        if (SS) stage_buckets<FAMILY, false, KW>(ix, ci, lane, S);
+#pragma unroll 1  // (two copies of stage V: -15 %, r03w)
         for (u32 p = lane; p < n_c; p += 32) {
           Hit h = hit_none(SKIPPED);
           if (chunk_valid(ci, p)) {
             u64 fw = S.fw[p], rc = SS ? S.rc[p] : revcomp(fw, k);
-            bool ok = SS ? verify_sshash<FAMILY>(ix, S, p, fw, rc, h)
+            bool ok = SS ? verify_sshash<FAMILY, KW>(ix, S, p, fw, rc, h)
                          : (KIND == MAZU_K2U_SAMPLED_PFHASH ? sampled_pfhash_k2u_t<FAMILY>(ix, fw, rc, h, nullptr) : pfhash_k2u_t<FAMILY>(ix, fw, rc, h));
             ++n_valid;
             if (ok) ++n_hit; else h = hit_none(NO_MATCH);
@@ -743,7 +751,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const _
         // (An earlier version extended warm cursors first and looked up cold only on demand; on a GPU the cold path is
         // already amortised per super-k-mer: always-cold + verify measured +5 % on config 3 and, being small enough for the
         // 64-register build, +15 % on a 1.7 GB index.)
-        if (SS) stage_buckets<FAMILY, true>(ix, ci, lane, S);
+        if (SS) stage_buckets<FAMILY, true, KW>(ix, ci, lane, S);
 #pragma unroll 1
         for (u32 g0 = 0; g0 < n_c; g0 += 32) {
           const u32 q = g0 + lane;
@@ -757,7 +765,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const _
           if (valid) {
             fw = S.fw[q];
             rc = SS ? S.rc[q] : revcomp(fw, k);
-            cold_hit = SS ? verify_sshash<FAMILY>(ix, S, q, fw, rc, cold, &cold_ustart, &cold_dup)
+            cold_hit = SS ? verify_sshash<FAMILY, KW>(ix, S, q, fw, rc, cold, &cold_ustart, &cold_dup)
                           : (KIND == MAZU_K2U_SAMPLED_PFHASH ? sampled_pfhash_k2u_t<FAMILY>(ix, fw, rc, cold, &cold_ustart, &cold_dup)
                                                              : pfhash_k2u_t<FAMILY>(ix, fw, rc, cold, &cold_ustart, &cold_dup));
             if (!cold_hit) cold = hit_none(NO_MATCH);
@@ -817,7 +825,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const _
             bool differs = false;
             if (mine && valid && s_warm && (u64)s_pos + 1 + k <= (u64)s_ulen &&
                 !(cold_hit && cold.unitig_id == s_uid && cold.pos == s_pos + 1)) {
-              u32 m = word_equivalency(fw, rc, line_window(ix.unitigs, s_ustart + s_pos + 1));
+              u32 m = word_equivalency(fw, rc, line_window<KW>(ix.unitigs, s_ustart + s_pos + 1));
               if (m != NO_MATCH) {  // the walk answers here although the cold lookup answered elsewhere (or missed)
                 res = Hit{s_uid, s_ulen, s_pos + 1, m};
                 res_hit = true;
@@ -1168,14 +1176,14 @@ __device__ __forceinline__ void tile_locate(const TileMap& tm, u32 k, u64 tile, 
   n_c = c0 < nk ? (u32)min((u64)QR_CHUNK, nk - c0) : 0u;
 }
 
-template <int KIND, u32 FAMILY>
+template <int KIND, u32 FAMILY, u32 KW = 0>
 __global__ void __launch_bounds__(QR_WARPS * 32, 4) get_ref_pos_pass1_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
                                                                             const TileMap tm, Hit* __restrict__ out_hits,
                                                                             unsigned long long* __restrict__ counts, u64* __restrict__ tile_totals) {
   __shared__ WarpStage s_stage[QR_WARPS];
   const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   WarpStage& S = s_stage[wib];
-  const u32 k = ix.unitigs.k;
+  const u32 k = kw_k<KW>(ix.unitigs.k);
   constexpr bool SS = KIND == MAZU_K2U_SSHASH;
   u32 n_valid = 0, n_hit = 0;
   for (u64 tile = (u64)blockIdx.x * QR_WARPS + wib; tile < tm.n_tiles; tile += (u64)gridDim.x * QR_WARPS) {
@@ -1188,13 +1196,13 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 4) get_ref_pos_pass1_kernel(con
       ChunkInfo ci;
       stage_encode(bases + beg, len, c0, n_c, k, lane, S, ci);
       __syncwarp();
-      if (SS) stage_buckets<FAMILY>(ix, ci, lane, S);
+      if (SS) stage_buckets<FAMILY, false, KW>(ix, ci, lane, S);
 #pragma unroll 1
       for (u32 p = lane; p < n_c; p += 32) {
         Hit h = hit_none(SKIPPED);
         if (chunk_valid(ci, p)) {
           u64 fw = S.fw[p], rc = SS ? S.rc[p] : revcomp(fw, k);
-          bool ok = SS ? verify_sshash<FAMILY>(ix, S, p, fw, rc, h)
+          bool ok = SS ? verify_sshash<FAMILY, KW>(ix, S, p, fw, rc, h)
                        : (KIND == MAZU_K2U_SAMPLED_PFHASH ? sampled_pfhash_k2u_t<FAMILY>(ix, fw, rc, h, nullptr) : pfhash_k2u_t<FAMILY>(ix, fw, rc, h));
           ++n_valid;
           if (ok) {
@@ -1372,7 +1380,7 @@ struct RunsTileOut {
 // records out; 3 = ASCII reads in, interval records out.  One instantiation per mode: with all of them in one body the kernel
 // grew to 4,000 SASS instructions and every mode lost 20 % to instruction fetch (profiles/experiments/README.md).
 enum { RUNS_IO_ASCII = 0, RUNS_IO_PACKED = 1, RUNS_IO_INTERVALS = 2, RUNS_IO_INTERVALS_ASCII = 3 };
-template <int KIND, u32 FAMILY, int IO>
+template <int KIND, u32 FAMILY, int IO, u32 KW = 0>
 __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
                                                                            const u64* __restrict__ read_offsets, u64 n_reads, u64 uniform_len,
                                                                            const u64* __restrict__ kmer_offsets, unsigned long long* __restrict__ counts,
@@ -1381,7 +1389,7 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(cons
   __shared__ WarpStage s_stage[QR_WARPS];
   const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   WarpStage& S = s_stage[wib];
-  const u32 k = ix.unitigs.k;
+  const u32 k = kw_k<KW>(ix.unitigs.k);
   constexpr bool SS = KIND == MAZU_K2U_SSHASH;
   u32 n_valid = 0, n_hit = 0;
   for (u64 r = (u64)blockIdx.x * QR_WARPS + wib; r < n_reads; r += (u64)gridDim.x * QR_WARPS) {
@@ -1406,14 +1414,14 @@ __global__ void __launch_bounds__(QR_WARPS * 32, 4) query_reads_runs_kernel(cons
       else
         stage_encode(bases + beg, len, 0, n_c, k, lane, S, ci);
       __syncwarp();
-      if (SS) stage_buckets<FAMILY>(ix, ci, lane, S);
+      if (SS) stage_buckets<FAMILY, false, KW>(ix, ci, lane, S);
       // one copy of the lookup (the loop is not unrolled: instruction-cache footprint); hits are parked in the warp's stage
 #pragma unroll 1
       for (u32 p = lane; p < n_c; p += 32) {
         Hit h = hit_none(SKIPPED);
         if (chunk_valid(ci, p)) {
           u64 fw = S.fw[p], rc = SS ? S.rc[p] : revcomp(fw, k);
-          bool ok = SS ? verify_sshash<FAMILY>(ix, S, p, fw, rc, h)
+          bool ok = SS ? verify_sshash<FAMILY, KW>(ix, S, p, fw, rc, h)
                        : (KIND == MAZU_K2U_SAMPLED_PFHASH ? sampled_pfhash_k2u_t<FAMILY>(ix, fw, rc, h, nullptr) : pfhash_k2u_t<FAMILY>(ix, fw, rc, h));
           ++n_valid;
           if (ok) ++n_hit; else h = hit_none(NO_MATCH);

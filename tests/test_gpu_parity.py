@@ -1281,6 +1281,40 @@ def test_hit_intervals_expand_to_the_exact_records(yeast_sshash, yeast_dense, ye
         del os.environ["MAZU_B200_CHUNK_MIB"]
 
 
+@pytest.mark.parametrize("w,skew", [(19, 64), (15, 32), (17, 32)])
+def test_read_kernels_kw_specialisations(yeast_dense, yeast_queries, w, skew):
+    """The SSHash read kernels exist twice for (k, w) = (31, 19) and (31, 15): with k and w folded into the code and with
+    both read from the index (capi.cu: kw_code; (31, 17) has the second form only).  Every read interface must give the
+    oracle's records through either: records, counts, streaming, hit intervals, reads -> MappedRefPos."""
+    g0, o0 = yeast_dense
+    g, o = g0.rebuild_k2u(mz.K2U_SSHASH, w=w, skew_param=skew, seed=0), o0.rebuild_k2u(1, w=w, skew=skew, seed=0)
+    _, ref_codes = yeast_queries
+    rag = _gen.sample_reads(ref_codes, 2500, 260, seed=70 + w, frac_ref=0.7, sub_rate=0.01, n_rate=0.002, ragged=True)
+    uni = _gen.sample_reads(ref_codes, 4000, 150, seed=170 + w, frac_ref=0.7, sub_rate=0.01, n_rate=0.002)
+    want_u, wcnt_u, _ = o.query_reads(*uni)
+    woffs_u, wmrps_u = o.project_hits(want_u)
+    words, mask, _ = mz.pack_reads(uni[0], 150)
+    try:
+        for generic in ("0", "1"):
+            os.environ["MAZU_B200_GENERIC_KW"] = generic
+            for mode in (mz.MODE_RANDOM, mz.MODE_STREAMING):
+                _check_reads(g, o, rag[0], rag[1], mode)
+                got, cnt, _ = g.query_reads(uni[0], None, uniform_read_len=150, mode=mode)
+                want, wcnt, _ = o.query_reads(uni[0], uni[1], streaming=bool(mode), reset_per_read=True)
+                assert_hits_equal(got, want, "uniform reads, w=%d generic=%s mode=%d" % (w, generic, mode))
+                assert list(cnt) == list(wcnt)
+            iv, cnt = g.query_reads_intervals_packed(words, mask, 4000, 150)
+            assert_hits_equal(g.expand_hit_intervals(iv, mask, 4000, 150), want_u, "intervals, w=%d generic=%s" % (w, generic))
+            assert list(cnt) == list(wcnt_u)
+            iva, cnta = g.query_reads_intervals(uni[0], 4000, 150)
+            assert_hits_equal(g.expand_hit_intervals_ascii(iva, uni[0], 4000, 150), want_u, "ASCII intervals, w=%d generic=%s" % (w, generic))
+            hits, poffs, mrps, cnt, _ = g.get_ref_pos_reads(uni[0], uniform_read_len=150)
+            assert_hits_equal(hits, want_u, "get_ref_pos_reads, w=%d generic=%s" % (w, generic))
+            assert np.array_equal(poffs, woffs_u) and np.array_equal(mrps, wmrps_u) and list(cnt) == list(wcnt_u)
+    finally:
+        del os.environ["MAZU_B200_GENERIC_KW"]
+
+
 def test_pinned_host_buffers(yeast_sshash, yeast_queries):
     """mazu_b200_alloc_pinned: page-locked buffers for callers that do not link CUDA; same answers as pageable numpy arrays"""
     g, o = yeast_sshash
