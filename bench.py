@@ -106,6 +106,7 @@ class ClockSampler:
                     phys = int(ids[gpu_index])
             self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.nvml = pynvml
+            self.sample_nvml()  # NVML's first queries are slow (one run recorded a single sample in a 150 ms region): pay that here
         except Exception:
             self.nvml = None
 

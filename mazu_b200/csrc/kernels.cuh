@@ -413,12 +413,12 @@ __device__ __forceinline__ void stage_buckets(const IndexView& ix, const ChunkIn
   // positions beyond come from the tail of k-mer 127.  Its reverse complement is the low 2w bits of
   // rc(k-mer q - span) (the top w bases of that k-mer), so no w-mer is reverse-complemented on its own.
   // Only w-mers q <= 127 + span belong to a k-mer of the chunk; the keys beyond are never read.
-  // random-access instantiations unroll this loop and the window loop below: +4 % on config 5, no spills at 64 registers
-  // (profiles/experiments, r03v); the streaming walk keeps them rolled (its 64-register build would spill)
-#ifdef MAZU_WALK_UNROLL
-  constexpr int UNROLL_KEYS = 5, UNROLL_MIN = 4;
+  // this loop and the window loop below are unrolled: +4 % on config 5 (random access and streaming walk alike), no spills at
+  // 64 registers in the random-access kernels, the walk's 64-register build spills 40 bytes rolled or not (profiles/experiments)
+#ifdef MAZU_STAGE_M_ROLLED  // A/B knob
+  constexpr int UNROLL_KEYS = 1, UNROLL_MIN = 1;
 #else
-  constexpr int UNROLL_KEYS = WALK ? 1 : 5, UNROLL_MIN = WALK ? 1 : 4;
+  constexpr int UNROLL_KEYS = 5, UNROLL_MIN = 4;
 #endif
 #pragma unroll UNROLL_KEYS
   for (int t = 0; t < 5; ++t) {
