@@ -71,6 +71,23 @@ def test_library_has_sm100a_code():
     assert "sm_100a" in out.stdout
 
 
+def test_library_has_the_kw_instantiations_of_the_sshash_read_kernels():
+    """The SSHash read kernels are compiled with k and w read from the index (KW = 0) and with (31, 19) / (31, 15) folded into
+    the code (capi.cu: kw_code, kernels.cuh: KW).  The GPU parity test runs both forms; here: all of them are in the cubin."""
+    out = subprocess.run(["cuobjdump", "-elf", mz.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    text = out.stdout
+    kw = {"generic": "Lj0E", "k31 w19": "Lj%dE" % ((31 << 8) | 19), "k31 w15": "Lj%dE" % ((31 << 8) | 15)}
+    # mangled template argument lists: <MODE, KIND = SSHASH (1), FAMILY = NATIVE (1), OCC, KW> etc.
+    for label, code in kw.items():
+        assert re.search(r"query_reads_kernelILi0ELi1ELj1ELi\d+E%sE" % code, text), "random-access read kernel, " + label
+        assert re.search(r"query_reads_kernelILi1ELi1ELj1ELi\d+E%sE" % code, text), "streaming walk, " + label
+        assert re.search(r"get_ref_pos_pass1_kernelILi1ELj1E%sE" % code, text), "get_ref_pos pass 1, " + label
+        for io in range(4):
+            assert re.search(r"query_reads_runs_kernelILi1ELj1ELi%dE%sE" % (io, code), text), "fused run kernel io %d, %s" % (io, label)
+
+
 def test_no_cpu_fallback_without_device():
     """Without a CUDA device the product must fail loudly, never compute on the CPU."""
     if mz.device_count() > 0:
