@@ -654,8 +654,8 @@ struct StreamState {  // StreamingK2U { is_warm, prev_k2upos } (src/index/cachin
 //   KIND: MAZU_K2U_PFHASH / MAZU_K2U_SSHASH.  FAMILY: MPHF family of the index.
 // OCC = resident CTAs per SM the instantiation is compiled for (register budget: 3 -> <= 80, 4 -> <= 64).  The streaming
 // walk wants its 80 registers while the index is cache-resident (+3.5 % on the yeast configs) and the extra warps once
-// lookups wait on DRAM (+13 % on a 1.7 GB index); the launcher picks by index size.  Random-access mode passes 0 (no
-// minimum: ptxas settles on 64 registers by itself).
+// lookups wait on DRAM (+13 % on a 1.7 GB index); the launcher picks by index size.  Random-access mode is built for 4
+// (MAZU_QR_RANDOM_OCC; 3 CTAs / 80 registers measured 13 % slower on config 5).
 // KW = MZ_KW(k, w) of the index folded into the code (SSHash instantiations for the named (k, w) pairs), 0 = read from the view.
 template <int MODE, int KIND, u32 FAMILY, int OCC, u32 KW = 0>
 __global__ void __launch_bounds__(QR_WARPS * 32, OCC) query_reads_kernel(const __grid_constant__ IndexView ix, const u8* __restrict__ bases,
