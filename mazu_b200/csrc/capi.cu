@@ -1160,7 +1160,19 @@ mazu_status_t mazu_b200_pack_reads(const uint8_t* bases, uint64_t n_reads, uint6
         if (m)
           for (u64 j = 0; j < mpr; ++j) m[j] = 0;
         const u8* b = bases + r * read_len;
-        for (u64 j = 0; j < read_len; ++j) {
+        u64 j = 0;
+        for (; j + 8 <= read_len; j += 8) {  // eight bases per step (kmer.hpp: pack8_ascii); j is a multiple of 8: no word is straddled
+          u64 v;
+          memcpy(&v, b + j, 8);
+          u32 c16, inv;
+          pack8_ascii(v, c16, inv);
+          w[j >> 5] |= (u64)c16 << (2 * (j & 31));
+          if (inv) {
+            nb += (u64)__builtin_popcount(inv);
+            if (m) m[j >> 6] |= (u64)inv << (j & 63);
+          }
+        }
+        for (; j < read_len; ++j) {
           const u32 c = base_code(b[j]);
           if (c > 3) {
             ++nb;

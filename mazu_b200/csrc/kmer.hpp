@@ -30,6 +30,25 @@ MZ_HD u32 base_code(u32 c) {
   return ok ? code : 4u;
 }
 
+// Eight ASCII bases at once on the host (v little-endian: base j in byte j): their 2-bit codes in 16 bits (0 where the base is
+// not ACGTacgt) and one invalid flag per base -- base_code() on eight bytes with 64-bit arithmetic (mazu_b200_pack_reads).
+inline void pack8_ascii(u64 v, u32& codes16, u32& inv8) {
+  const u64 ONES = 0x0101010101010101ULL, LOW7 = 0x7F7F7F7F7F7F7F7FULL, HI = 0x8080808080808080ULL;
+  const u64 u = v & 0xDFDFDFDFDFDFDFDFULL;  // fold case
+  // 0x80 in every byte of u that differs from `letter` (exact: no carry leaves a byte)
+#define MZ_NE8(letter) (((((u ^ (ONES * (u64)(letter))) & LOW7) + LOW7) | (u ^ (ONES * (u64)(letter)))) & HI)
+  const u64 bad = (MZ_NE8('A') & MZ_NE8('C') & MZ_NE8('G') & MZ_NE8('T')) >> 7;  // bit 0 of every byte that is none of the four
+#undef MZ_NE8
+  u64 t = (u >> 1) & (ONES * 3);  // A->0 C->1 G->3 T->2
+  t ^= (t >> 1) & ONES;           // A0 C1 G2 T3
+  t &= ~(bad * 3);
+  t = (t | (t >> 6)) & 0x000F000F000F000FULL;  // gather the eight 2-bit fields
+  t = (t | (t >> 12)) & 0x000000FF000000FFULL;
+  t = (t | (t >> 24)) & 0xFFFFULL;
+  codes16 = (u32)t;
+  inv8 = (u32)((bad * 0x0102040810204080ULL) >> 56);  // bit 0 of byte j -> bit j
+}
+
 // reverse complement of the low 2k bits
 MZ_HD u64 revcomp(u64 x, u32 k) {
   x = ~x;  // complement: 3 - b

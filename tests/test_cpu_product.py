@@ -175,6 +175,23 @@ def test_pack_reads_and_packed_run_decoder():
         want_w[:, j // 32] |= np.where(c[:, j] < 4, c[:, j], 0).astype(np.uint64) << np.uint64(2 * (j % 32))
         want_m[:, j // 64] |= (c[:, j] == 4).astype(np.uint64) << np.uint64(j % 64)
     assert np.array_equal(words.reshape(n_reads, wpr), want_w) and np.array_equal(mask.reshape(n_reads, mpr), want_m)
+    # every byte value, read lengths around the 8-base steps of the packer and the 32- / 64-base word boundaries
+    for rl in (1, 7, 8, 9, 31, 32, 33, 63, 64, 65, 150, 151):
+        nr = 97
+        b = rng.integers(0, 256, size=nr * rl, dtype=np.uint8)
+        keep = rng.random(nr * rl) < 0.8  # mostly bases, the rest any byte
+        b[keep] = np.frombuffer(b"ACGTacgt", dtype=np.uint8)[rng.integers(0, 8, size=int(keep.sum()))]
+        if nr * rl >= 256:
+            b[:256] = np.arange(256, dtype=np.uint8)
+        w2, m2, bad2 = mz.pack_reads(b, rl)
+        cc = codes[b].reshape(nr, rl)
+        assert bad2 == int((cc == 4).sum()), rl
+        ww = np.zeros((nr, (rl + 31) // 32), dtype=np.uint64)
+        mm = np.zeros((nr, (rl + 63) // 64), dtype=np.uint64)
+        for j in range(rl):
+            ww[:, j // 32] |= np.where(cc[:, j] < 4, cc[:, j], 0).astype(np.uint64) << np.uint64(2 * (j % 32))
+            mm[:, j // 64] |= (cc[:, j] == 4).astype(np.uint64) << np.uint64(j % 64)
+        assert np.array_equal(w2.reshape(nr, -1), ww) and np.array_equal(m2.reshape(nr, -1), mm), rl
     # decoder: random codes / runs, byte codes vs 2-bit codes
     slots = read_len - k + 1
     code = rng.choice(4, size=n_reads * slots, p=[.4, .45, .05, .1]).astype(np.uint8)
